@@ -1,0 +1,285 @@
+"""Generate tests/golden/*.npz by RUNNING THE REFERENCE (imported in place from
+/root/reference through oracle/refshim.py) on the seeded problems of
+tests/problems.py, and cross-check oracle/sclmd_oracle.py against it.
+
+Run in the build container only:   python oracle/make_golden.py
+The fixtures store reference OUTPUTS (plus captured LAPACK eigensystems where
+the reference's result depends on eigenvector sign conventions).
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from oracle import refshim                      # noqa: E402
+from oracle import sclmd_oracle as O            # noqa: E402
+import problems as P                            # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+R = refshim.install()
+rmd, rbaths, rnoise, rfun = R["md"], R["baths"], R["noise"], R["functions"]
+
+
+def relerr(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def axyz(natoms):
+    return [["C", float(i), 0.0, 0.0] for i in range(natoms)]
+
+
+# ------------------------------------------------------------------ MD cases
+MD_CASES = {}
+
+
+md_case_ph_full, md_case_ph_local, md_case_e_extra, md_case_c1_shape = (
+    P.md_case_ph_full, P.md_case_ph_local, P.md_case_e_extra, P.md_case_c1_shape)
+
+
+def build_reference_md(c):
+    with refshim.quiet():
+        m = rmd.md(c["dt"], c["nmd"], c["T"], axyz=axyz(c["K"].shape[0] // 3), dyn=c["K"])
+        baths = []
+        for b in range(len(c["cids"])):
+            if c["kinds"][b] == "ph":
+                ml = c["kern"][b].shape[0]
+                if ml == 1:
+                    bb = rbaths.phbath(c["T"], c["cids"][b], 0.05, 10, c["dt"], c["nmd"])
+                    bb.gmem()
+                    assert np.array_equal(bb.kernel, c["kern"][b])
+                else:
+                    gwl, g = P.gamma_grid(4, len(c["cids"][b]), 5)
+                    bb = rbaths.phbath(c["T"], c["cids"][b], 0.05, 10, c["dt"], c["nmd"], ml=ml, gamma=g, gwl=gwl)
+                    bb.kernel = c["kern"][b]
+            else:
+                e = c["e"]
+                bb = rbaths.ebath(c["cids"][b], c["T"], c["dt"], c["nmd"], wmax=1.0, nw=50, bias=e["bias"][b],
+                                  efric=e["efric"][b], exim=e["exim"][b], exip=e["exip"][b],
+                                  zeta1=e["zeta1"][b], zeta2=e["zeta2"][b])
+            bb.noise = c["noise"][b]
+            m.AddBath(bb)
+            baths.append(bb)
+        if c["cons"] is not None:
+            m.AddConstr(c["cons"])
+        if c["q0"] is None:
+            np.random.seed(c["ic_seed"])
+            m.initialise()
+        else:
+            m.initialise()
+            m.q, m.p = c["q0"].copy(), c["p0"].copy()
+        m.ResetHis()
+    return m, baths
+
+
+def oracle_bath_inputs(c, rb):
+    """kernel + extra matrices exactly as the reference bath objects hold them after CheckEmat."""
+    out = []
+    for b, bb in enumerate(rb):
+        if c["kinds"][b] == "ph":
+            out.append(dict(kind="ph", cids=c["cids"][b], kernel=np.array(bb.kernel), bias=0.0,
+                            exim=None, zeta1=None, zeta2=None))
+        else:
+            out.append(dict(kind="e", cids=c["cids"][b], kernel=np.array(bb.kernel), bias=bb.bias,
+                            exim=bb.exim, zeta1=bb.zeta1, zeta2=bb.zeta2))
+    return out
+
+
+def run_md_case(name, c):
+    m, rb = build_reference_md(c)
+    K = np.array(m.dyn)                     # post-setDyn matrix is what the reference integrates
+    q0, p0 = np.array(m.q), np.array(m.p)
+    qs, ps = [], []
+    with refshim.quiet():
+        for _ in range(c["nsteps"]):
+            m.vv(0)
+            qs.append(np.array(m.q))
+            ps.append(np.array(m.p))
+    qs, ps = np.array(qs), np.array(ps)
+    curs = np.array([b.cur for b in rb])
+    # ---- oracle cross-checks
+    ob = oracle_bath_inputs(c, rb)
+    lit = O.LiteralMD(K, c["dt"], c["nmd"],
+                      [O.Bath(o["kind"], o["cids"], o["kernel"], c["noise"][i], c["dt"], c["nmd"], o["bias"],
+                              o["exim"], o["zeta1"], o["zeta2"]) for i, o in enumerate(ob)], c["cons"])
+    lit.q, lit.p = q0.copy(), p0.copy()
+    ens = O.EnsembleMD(K, c["dt"], c["nmd"], 1, c["cons"])
+    for i, o in enumerate(ob):
+        ens.add_bath(o["cids"], o["kernel"], c["noise"][i][None], o["bias"], o["exim"], o["zeta1"], o["zeta2"], o["kind"])
+    ens.q[0], ens.p[0] = q0, p0
+    el = ee = 0.0
+    for s in range(c["nsteps"]):
+        lit.vv()
+        ens.step()
+        el = max(el, relerr(lit.q, qs[s]), relerr(lit.p, ps[s]))
+        ee = max(ee, relerr(ens.q[0], qs[s]), relerr(ens.p[0], ps[s]))
+    ec = max(relerr(np.array([b.cur for b in lit.baths]), curs),
+             relerr(np.array([b["cur"][0] for b in ens.baths]), curs))
+    print("%-14s literal-vs-ref %.2e  ensemble-vs-ref %.2e  cur %.2e  etot %.2e" %
+          (name, el, ee, ec, relerr(ens.etot[0], m.etot)))
+    assert el < 1e-13 and ee < 1e-12 and ec < 1e-11, name
+    keep = slice(None) if qs.shape[1] <= 64 else slice(-1, None)   # big case: final state only
+    np.savez_compressed(os.path.join(GOLD, "md_%s.npz" % name), q=qs[keep], p=ps[keep], cur=curs, etot=m.etot,
+                        q0=q0, p0=p0, nsteps=c["nsteps"], dyn_checksum=float(np.sum(K * K)))
+
+
+# -------------------------------------------------------------- noise cases
+class Stream:
+    """replaces np.random.normal(loc, scale) inside the reference by loc + scale*z_k"""
+
+    def __init__(self, z):
+        self.z, self.k = z, 0
+
+    def __call__(self, loc=0.0, scale=1.0, size=None):
+        v = loc + scale * self.z[self.k]
+        self.k += 1
+        return v
+
+
+def run_noise_cases():
+    dt, nmd, nc, T = 0.25 / 0.658, 32, 4, 300.0
+    z = np.random.default_rng(60).standard_normal(4096)
+    captured = []
+    real_eigh = np.linalg.eigh
+
+    def cap_eigh(a):
+        av, au = real_eigh(a)
+        captured.append((np.array(av), np.array(au)))
+        return av, au
+    # --- phnoise on a gamma grid, with cutoff inside the frequency range
+    gwl, g = P.gamma_grid(7, nc, 61, wmax=0.3)
+    phcut = 0.5 * 2 * np.pi / dt / nmd * (nmd // 2)      # half of the Nyquist frequency -> zeros above
+    rnoise.LA.eigh = cap_eigh
+    saved = np.random.normal
+    np.random.normal = Stream(z)
+    with refshim.quiet():
+        ph = rnoise.phnoise(g, gwl, T, phcut, dt, nmd, False, True)
+    used_ph = np.random.normal.k
+    ph_eig = captured[:]
+    del captured[:]
+    # --- enoise with bias (complex Hermitian covariance)
+    efric, exim, exip = P.psd(3, 62, 0.05), P.antisym(3, 63, 0.01), P.sym(3, 64, 0.01)
+    np.random.normal = Stream(z[1000:])
+    with refshim.quiet():
+        en = rnoise.enoise(efric, exim, exip, 0.2, T, 2.0, dt, nmd, False, False)
+    used_e = np.random.normal.k
+    e_eig = captured[:]
+    np.random.normal = saved
+    rnoise.LA.eigh = real_eigh
+    # oracle replay with the captured eigensystems
+    it = iter(ph_eig)
+    s = Stream(z)
+    x = [O.vargau(*next(it), lambda sc: s(0.0, sc)) for _ in range(nmd // 2 + 1)]
+    oph = O.spectrum_to_series(np.array(x), dt, nmd)
+    it = iter(e_eig)
+    s = Stream(z[1000:])
+    x = [O.vargau(*next(it), lambda sc: s(0.0, sc)) for _ in range(nmd // 2 + 1)]
+    oen = O.spectrum_to_series(np.array(x), dt, nmd)
+    # covariances rebuilt by the oracle must equal V diag(l) V^H captured from the reference
+    ec = 0.0
+    for i, (av, au) in enumerate(ph_eig):
+        ec = max(ec, np.max(np.abs((au * av) @ au.conj().T - O.ph_covariance(i, g, gwl, T, phcut, dt, nmd))))
+    for i, (av, au) in enumerate(e_eig):
+        ec = max(ec, np.max(np.abs((au * av) @ au.conj().T - O.e_covariance(i, efric, exim, exip, 0.2, T, 2.0, dt, nmd, False, False))))
+    print("noise          ph %.2e  e %.2e  covariance abs err %.2e  draws %d/%d" %
+          (relerr(oph, ph), relerr(oen, en), ec, used_ph, used_e))
+    assert relerr(oph, ph) < 1e-13 and relerr(oen, en) < 1e-13 and ec < 1e-12
+    np.savez_compressed(os.path.join(GOLD, "noise.npz"), ph=ph, en=en, phcut=phcut,
+                        ph_av=np.array([a for a, _ in ph_eig]), ph_au=np.array([u for _, u in ph_eig]),
+                        e_av=np.array([a for a, _ in e_eig]), e_au=np.array([u for _, u in e_eig]),
+                        used_ph=used_ph, used_e=used_e)
+
+
+# ----------------------------------------------------------- scalar helpers
+def run_scalar_cases():
+    ws = np.array([0.0, 1e-6, 0.01, 0.05, 0.2, 0.35, 0.5, -0.03, -0.4])
+    rows = []
+    for w in ws:
+        for T in (0.0, 4.0, 300.0):
+            for cl in (False, True):
+                for zp in (False, True):
+                    with np.errstate(all="ignore"):
+                        r = rnoise.equ(w, 0.4, T, cl, zp)
+                        o = O.equ(w, 0.4, T, cl, zp)
+                    assert (r == o) or (np.isnan(r) and np.isnan(o)), (w, T, cl, zp, r, o)
+                    rows.append((w, T, cl, zp, r))
+    xs = np.array([0.0, 0.1, 0.25, 0.3, 0.7])
+    ys = np.array([1.0, 3.0, 2.0, 5.0, -1.0])
+    xq = np.array([-0.1, 0.0, 0.04, 0.05, 0.06, 0.1, 0.17, 0.175, 0.2, 0.275, 0.4, 0.5, 0.55, 0.7, 0.9])
+    fl = np.array([rfun.flinterp(x, xs, ys) for x in xq])
+    nn = np.array([rfun.nearest(x, xs) for x in xq])
+    assert np.array_equal(fl, np.array([O.flinterp(x, xs, ys) for x in xq]))
+    assert np.array_equal(nn, np.array([O.nearest(x, xs) for x in xq]))
+    for x, v in zip(xq, fl):
+        i0, i1, w = O.flinterp_index(x, xs)
+        assert abs(ys[i0] + w * (ys[i0] - ys[i1]) - v) < 1e-15
+    # gamt, both branches
+    gwl, g = P.gamma_grid(6, 3, 70, wmax=0.25)
+    wl = [0.3 * i / 40 for i in range(40)]
+    tl = [0.38 * i for i in range(9)]
+    with refshim.quiet():
+        g0 = rbaths.gamt(tl, wl, gwl, g, 0)
+        g1 = rbaths.gamt(tl, wl, gwl, g, 0.01)
+    print("gamt           eta=0 %.2e  eta!=0 %.2e" % (relerr(O.gamt(tl, wl, gwl, g, 0), g0), relerr(O.gamt(tl, wl, gwl, g, 0.01), g1)))
+    assert relerr(O.gamt(tl, wl, gwl, g, 0), g0) < 1e-13 and relerr(O.gamt(tl, wl, gwl, g, 0.01), g1) < 1e-13
+    np.savez_compressed(os.path.join(GOLD, "scalars.npz"), equ=np.array(rows, dtype=float), xq=xq, xs=xs, ys=ys, fl=fl, nn=nn,
+                        gamt0=g0, gamt1=g1)
+
+
+# -------------------------------------------------------------- NEGF / sig
+def run_negf_cases():
+    natoms = 12
+    K = P.spring_chain_dyn(natoms, seed=80) / O.RPC ** 2            # eV^2 -> ps^-2
+    fixed = [list(range(0, 3)), list(range(33, 36))]
+    bath = [list(range(3, 12)), list(range(24, 33))]
+    b = refshim.make_bpt(R, np.delete(np.delete(K, fixed[0] + fixed[1], 0), fixed[0] + fixed[1], 1), 0.1, bath, fixed,
+                         natoms, 0.25, 20)
+    with refshim.quiet():
+        cwd = os.getcwd()
+        os.chdir("/tmp")
+        b.gettm()
+        b.getps(300.0, 0.25, 20)
+        os.chdir(cwd)
+    kap = np.array([b.thermalconductance(T, 0.1) for T in (100.0, 300.0, 900.0)])
+    Kr = b.dynmat
+    iL, iR = O.bpt_reduce_index(bath[0], 3), O.bpt_reduce_index(bath[1], 3)
+    otm = np.array([O.bpt_tm(Kr, w, 0.1, iL, iR) for w in b.tmnumber[:, 0]])
+    ops = np.array([O.bpt_ps_nobias(Kr, w, 300.0, 0.1, iL, iR, np.arange(30)) for w in b.psnumber[:, 0]])
+    okap = np.array([O.thermalcurrent(b.tmnumber, T, 0.1) / (T * 0.1) for T in (100.0, 300.0, 900.0)])
+    print("bpt            tm %.2e  ps %.2e  kappa %.2e" % (relerr(otm, b.tmnumber[:, 1]), relerr(ops[1:], b.psnumber[1:, 1]), relerr(okap, kap)))
+    assert relerr(otm, b.tmnumber[:, 1]) < 1e-9 and relerr(okap, kap) < 1e-9
+    np.savez_compressed(os.path.join(GOLD, "bpt.npz"), tm=b.tmnumber, ps=b.psnumber, kappa=kap)
+    # sig
+    m = 4
+    K00, K11, K01 = P.chain_blocks(m, seed=81)
+    s = refshim.make_sig(R, K00, K11, K01, 0.06, 8, eta=2e-3)
+    with refshim.quiet():
+        cwd = os.getcwd()
+        os.chdir("/tmp")
+        seL, dosL = s.getse("L"), np.array(s.dos)
+        seR, dosR = s.getse("R"), np.array(s.dos)
+        s.gettm()
+        os.chdir(cwd)
+    oL = np.array([O.sig_selfenergy(s.K00, s.K11, s.K01, s.K10, w, s.eta, "L") for w in s.ep])
+    oR = np.array([O.sig_selfenergy(s.K00, s.K11, s.K01, s.K10, w, s.eta, "R") for w in s.ep])
+    otm = np.array([O.sig_tm(s.K00, s.K11, s.K01, s.K10, w, s.eta) for w in s.ep])
+    its = np.array([O.sig_sgf(s.K00, s.K11, s.K01, s.K10, w, s.eta, "R")[1] for w in s.ep])
+    print("sig            seL %.2e seR %.2e tm %.2e  iterations %s" % (relerr(oL, seL), relerr(oR, seR), relerr(otm, s.tmnumber[:, 1]), its))
+    assert relerr(oL, seL) < 1e-10 and relerr(oR, seR) < 1e-10 and relerr(otm, s.tmnumber[:, 1]) < 1e-8
+    np.savez_compressed(os.path.join(GOLD, "sig.npz"), seL=seL, seR=seR, dosL=dosL, dosR=dosR, tm=s.tmnumber, ep=s.ep, eta=s.eta)
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    for name, fn in (("ph_full", md_case_ph_full), ("ph_local", md_case_ph_local), ("e_extra", md_case_e_extra),
+                     ("c1_shape", md_case_c1_shape)):
+        run_md_case(name, fn())
+    run_noise_cases()
+    run_scalar_cases()
+    run_negf_cases()
+    print("golden fixtures written to", GOLD)

@@ -1,0 +1,171 @@
+"""Seeded synthetic problem definitions shared by oracle/make_golden.py, the
+parity tests and bench.py (SURVEY.md section 8d "Synthetic inputs").
+
+Everything is a pure function of its seed so the golden fixtures only need to
+store the reference's OUTPUTS; inputs are regenerated on both boxes.
+"""
+import numpy as np
+
+
+def spring_chain_dyn(natoms, seed, kmax=0.04, onsite=1e-6):
+    """Mass-weighted spring network on a quasi-1D ribbon: every atom bonds to
+    the next two atoms with random stiffness; returns symmetric PSD K [3n,3n]
+    with max eigenvalue ~ kmax (hbar*omega_max ~ 0.2 eV for kmax=0.04)."""
+    rng = np.random.default_rng(seed)
+    n = 3 * natoms
+    K = np.zeros((n, n))
+    pos = np.cumsum(rng.uniform(0.8, 1.2, size=(natoms, 3)), axis=0)
+    for i in range(natoms):
+        for j in (i + 1, i + 2):
+            if j >= natoms:
+                continue
+            e = pos[j] - pos[i]
+            e /= np.linalg.norm(e)
+            e = e + 0.35 * rng.standard_normal(3)      # give the bond some transverse stiffness
+            kb = rng.uniform(0.5, 1.0)
+            blk = kb * np.outer(e, e)
+            si, sj = slice(3 * i, 3 * i + 3), slice(3 * j, 3 * j + 3)
+            K[si, si] += blk
+            K[sj, sj] += blk
+            K[si, sj] -= blk
+            K[sj, si] -= blk
+    K = 0.5 * (K + K.T) + onsite * np.eye(n)
+    K *= kmax / np.linalg.eigvalsh(K).max()
+    return K
+
+
+def psd_project(K):
+    """What md.setDyn does to the matrix it is given (md.py:264-281)."""
+    K = 0.5 * (K + K.T)
+    av, au = np.linalg.eigh(K)
+    av = np.where(av < 0, 0.0, av)
+    return au @ np.diag(av) @ au.T
+
+
+def full_kernel(ml, nc, dt, seed, gamma0=0.02, tau=12.0, w0=0.15, eps=0.1):
+    """kernel[j] = gamma0 exp(-j dt/tau) cos(w0 j dt) (I + eps S), S symmetric seeded."""
+    rng = np.random.default_rng(seed)
+    S = rng.standard_normal((nc, nc))
+    S = 0.5 * (S + S.T) / np.sqrt(nc)
+    j = np.arange(ml)
+    s = gamma0 * np.exp(-j * dt / tau) * np.cos(w0 * j * dt)
+    return s[:, None, None] * (np.eye(nc) + eps * S)[None]
+
+
+def diag_kernel(ml, nc, dt, seed, gamma0=0.02, tau=12.0, w0=0.15):
+    rng = np.random.default_rng(seed)
+    amp = gamma0 * rng.uniform(0.5, 1.5, size=nc)
+    j = np.arange(ml)
+    return (np.exp(-j * dt / tau) * np.cos(w0 * j * dt))[:, None] * amp[None, :]
+
+
+def injected_noise(ntraj, nmd, nc, seed, sigma=0.01):
+    return sigma * np.random.default_rng(seed).standard_normal((ntraj, nmd, nc))
+
+
+def sym(n, seed, scale=1.0):
+    a = np.random.default_rng(seed).standard_normal((n, n))
+    return scale * 0.5 * (a + a.T)
+
+
+def antisym(n, seed, scale=1.0):
+    a = np.random.default_rng(seed).standard_normal((n, n))
+    return scale * 0.5 * (a - a.T)
+
+
+def psd(n, seed, scale=1.0):
+    a = np.random.default_rng(seed).standard_normal((n, n))
+    return scale * (a @ a.T) / n
+
+
+def gamma_grid(ngw, nc, seed, wmax=0.3):
+    """A PSD friction spectrum gamma(w) on a uniform grid [0,wmax]: [ngw,nc,nc]."""
+    gwl = np.linspace(0.0, wmax, ngw)
+    A, B = psd(nc, seed, 0.02), psd(nc, seed + 1, 0.02)
+    g = np.array([A * np.exp(-(w / 0.12) ** 2) + B * (w / wmax) * np.exp(-(w / 0.2) ** 2) for w in gwl])
+    return gwl, g
+
+
+def chain_blocks(m, seed=0, k=1.0, k2=0.15):
+    """Principal-layer blocks of a quasi-1D harmonic chain (m dofs per layer):
+    K00 = K11 on-site, K01 coupling layer0->layer1 (selfenergy.py:93-103).
+    Units ps^-2-like, O(1e3) to mimic real dynamical matrices."""
+    rng = np.random.default_rng(seed)
+    # energy  sum_n |a u_n - b u_{n+1}|^2 / 2  + onsite  ->  K00 = a^T a + b^T b, K01 = -a^T b
+    a = np.sqrt(1.0e3 * k) * (np.eye(m) + k2 * rng.uniform(-1.0, 1.0, (m, m)))
+    b = np.sqrt(1.0e3 * k) * (np.eye(m) + k2 * rng.uniform(-1.0, 1.0, (m, m)))
+    on = a.T @ a + b.T @ b + 5.0 * np.eye(m)
+    on = 0.5 * (on + on.T)
+    return on, on.copy(), -(a.T @ b)
+
+
+# ---------------------------------------------------------------- MD parity cases
+def md_case_ph_full():
+    """two phonon baths with full memory kernels of different length + constraints"""
+    natoms, dt, nmd, nsteps = 10, 0.25 / 0.658, 32, 40
+    K = spring_chain_dyn(natoms, seed=11)
+    cons = [list(range(0, 3)), list(range(27, 30))]
+    cid = [list(range(3, 9)), list(range(21, 27))]
+    mls = [5, 3]
+    kern = [full_kernel(mls[b], 6, dt, seed=20 + b) for b in range(2)]
+    noise = [injected_noise(1, nmd, 6, seed=30 + b)[0] for b in range(2)]
+    rng = np.random.default_rng(40)
+    q0, p0 = 0.05 * rng.standard_normal(30), 0.02 * rng.standard_normal(30)
+    for c in cons:
+        q0[c] = 0
+        p0[c] = 0
+    return dict(K=K, dt=dt, nmd=nmd, nsteps=nsteps, cons=cons, cids=cid, kern=kern, noise=noise,
+                q0=q0, p0=p0, kinds=["ph", "ph"], T=300.0)
+
+
+def md_case_ph_local():
+    """Debye phonon baths (ml=1, no dt factor), no constraints"""
+    natoms, dt, nmd, nsteps = 8, 0.25 / 0.658, 16, 20
+    K = spring_chain_dyn(natoms, seed=12)
+    cid = [list(range(0, 6)), list(range(18, 24))]
+    debye = 0.05
+    kern = [np.array([np.diag(debye * np.pi / 6.0 + np.zeros(6))]) for _ in range(2)]
+    noise = [injected_noise(1, nmd, 6, seed=33 + b)[0] for b in range(2)]
+    rng = np.random.default_rng(41)
+    return dict(K=K, dt=dt, nmd=nmd, nsteps=nsteps, cons=None, cids=cid, kern=kern, noise=noise,
+                q0=0.05 * rng.standard_normal(24), p0=0.02 * rng.standard_normal(24), kinds=["ph", "ph"], T=300.0)
+
+
+def md_case_e_extra():
+    """electron baths: one with exim/zeta1/zeta2 all set (extra forces act), one with
+    zeta1=zeta2=None (baths.py:233 quirk: exim force silently skipped) + constraints"""
+    natoms, dt, nmd, nsteps = 10, 0.5 / 0.658, 32, 36
+    K = spring_chain_dyn(natoms, seed=13)
+    cons = [list(range(0, 3)), list(range(27, 30))]
+    cid = [list(range(3, 12)), list(range(15, 24))]
+    noise = [injected_noise(1, nmd, 9, seed=36 + b)[0] for b in range(2)]
+    e = dict(efric=[psd(9, 50, 0.03), psd(9, 51, 0.03)],
+             exim=[antisym(9, 52, 0.01), antisym(9, 53, 0.01)],
+             exip=[sym(9, 54, 0.01), sym(9, 55, 0.01)],
+             zeta1=[sym(9, 56, 0.004), None], zeta2=[antisym(9, 57, 0.004), None],
+             bias=[0.7, 0.4])
+    rng = np.random.default_rng(42)
+    q0, p0 = 0.05 * rng.standard_normal(30), 0.02 * rng.standard_normal(30)
+    for c in cons:
+        q0[c] = 0
+        p0[c] = 0
+    return dict(K=K, dt=dt, nmd=nmd, nsteps=nsteps, cons=cons, cids=cid, noise=noise, e=e,
+                q0=q0, p0=p0, kinds=["e", "e"], T=300.0)
+
+
+def md_case_c1_shape():
+    """config-1 shape: 201 atoms, nph=603, fixed ends, two ml=1 baths on 150 dofs each with
+    efric = I/damp (examples/runmd.py:31-54), random-phase normal-mode initial conditions."""
+    natoms, dt, nmd, nsteps = 201, 0.25 / 0.658, 64, 24
+    K = spring_chain_dyn(natoms, seed=14)
+    cons = [list(range(0 * 3, 20 * 3)), list(range(181 * 3, 201 * 3))]
+    cid = [list(range(20 * 3, 70 * 3)), list(range(131 * 3, 181 * 3))]
+    damp = 100 / 0.658211814201041
+    e = dict(efric=[np.identity(150) / damp] * 2, exim=[None] * 2, exip=[None] * 2, zeta1=[None] * 2,
+             zeta2=[None] * 2, bias=[0.0, 0.0])
+    noise = [injected_noise(1, nmd, 150, seed=38 + b, sigma=0.003)[0] for b in range(2)]
+    return dict(K=K, dt=dt, nmd=nmd, nsteps=nsteps, cons=cons, cids=cid, noise=noise, e=e,
+                q0=None, p0=None, kinds=["e", "e"], T=300.0, ic_seed=77)
+
+
+MD_CASES = dict(ph_full=md_case_ph_full, ph_local=md_case_ph_local, e_extra=md_case_e_extra, c1_shape=md_case_c1_shape)

@@ -1,0 +1,159 @@
+"""The CPU oracle (oracle/sclmd_oracle.py) replayed against fixtures written by the
+REFERENCE itself (oracle/make_golden.py; reference imported in place from
+/root/reference in the build container).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+import problems as P
+from oracle import sclmd_oracle as O
+
+
+def relerr(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def oracle_baths(c):
+    """bath inputs as the reference holds them after CheckEmat / gmem."""
+    out = []
+    for b in range(len(c["cids"])):
+        if c["kinds"][b] == "ph":
+            out.append(dict(kind="ph", cids=c["cids"][b], kernel=c["kern"][b], bias=0.0, exim=None, zeta1=None, zeta2=None))
+        else:
+            e = c["e"]
+            sym = lambda a: None if a is None else 0.5 * (a + a.T)
+            asym = lambda a: None if a is None else 0.5 * (a - a.T)
+            out.append(dict(kind="e", cids=c["cids"][b], kernel=np.array([sym(e["efric"][b])]), bias=e["bias"][b],
+                            exim=asym(e["exim"][b]), zeta1=sym(e["zeta1"][b]), zeta2=asym(e["zeta2"][b])))
+    return out
+
+
+@pytest.mark.parametrize("name", list(P.MD_CASES))
+def test_md_literal_and_ensemble_match_reference(name, golden_dir):
+    c = P.MD_CASES[name]()
+    g = np.load(os.path.join(golden_dir, "md_%s.npz" % name))
+    K = P.psd_project(c["K"])
+    assert abs(float(np.sum(K * K)) - float(g["dyn_checksum"])) <= 1e-12 * float(g["dyn_checksum"])
+    ob = oracle_baths(c)
+    lit = O.LiteralMD(K, c["dt"], c["nmd"],
+                      [O.Bath(o["kind"], o["cids"], o["kernel"], c["noise"][i], c["dt"], c["nmd"], o["bias"],
+                              o["exim"], o["zeta1"], o["zeta2"]) for i, o in enumerate(ob)], c["cons"])
+    ntraj = 3
+    ens = O.EnsembleMD(K, c["dt"], c["nmd"], ntraj, c["cons"])
+    for i, o in enumerate(ob):
+        # trajectory 1 carries the golden noise, the others something else (independence check)
+        nz = np.stack([0.5 * c["noise"][i], c["noise"][i], -c["noise"][i]])
+        ens.add_bath(o["cids"], o["kernel"], nz, o["bias"], o["exim"], o["zeta1"], o["zeta2"], o["kind"])
+    lit.q, lit.p = g["q0"].copy(), g["p0"].copy()
+    ens.q[:], ens.p[:] = g["q0"], g["p0"]
+    n = int(g["nsteps"])
+    full = g["q"].shape[0] == n
+    for s in range(n):
+        lit.vv()
+        ens.step()
+        if full or s == n - 1:
+            k = s if full else 0
+            assert relerr(lit.q, g["q"][k]) < 1e-11 and relerr(lit.p, g["p"][k]) < 1e-11
+            assert relerr(ens.q[1], g["q"][k]) < 1e-11 and relerr(ens.p[1], g["p"][k]) < 1e-11
+    assert relerr(np.array([b.cur for b in lit.baths]), g["cur"]) < 1e-10
+    assert relerr(np.array([b["cur"][1] for b in ens.baths]), g["cur"]) < 1e-10
+    assert relerr(ens.etot[1], g["etot"]) < 1e-11
+    assert lit.t == n == ens.t
+
+
+def test_diag_kernel_equals_full_diagonal():
+    """diagonal-kernel storage is the full kernel with a diagonal matrix."""
+    c = P.md_case_ph_full()
+    K = P.psd_project(c["K"])
+    a = O.EnsembleMD(K, c["dt"], c["nmd"], 2, c["cons"])
+    b = O.EnsembleMD(K, c["dt"], c["nmd"], 2, c["cons"])
+    for i in range(2):
+        kd = P.diag_kernel(7, 6, c["dt"], seed=3 + i)
+        kf = np.array([np.diag(r) for r in kd])
+        nz = P.injected_noise(2, c["nmd"], 6, seed=9 + i)
+        a.add_bath(c["cids"][i], kd, nz)
+        b.add_bath(c["cids"][i], kf, nz)
+    a.run(45)
+    b.run(45)
+    assert relerr(a.q, b.q) < 1e-13 and relerr(a.p, b.p) < 1e-13
+
+
+def test_noise_replay(golden_dir):
+    g = np.load(os.path.join(golden_dir, "noise.npz"))
+    dt, nmd = 0.25 / 0.658, 32
+    z = np.random.default_rng(60).standard_normal(4096)
+
+    def replay(av, au, zz):
+        k = [0]
+
+        def draw(scale):
+            v = scale * zz[k[0]]
+            k[0] += 1
+            return v
+        x = [O.vargau(av[i], au[i], draw) for i in range(nmd // 2 + 1)]
+        return O.spectrum_to_series(np.array(x), dt, nmd), k[0]
+    ph, used = replay(g["ph_av"], g["ph_au"], z)
+    assert used == int(g["used_ph"]) and relerr(ph, g["ph"]) < 1e-13
+    en, used = replay(g["e_av"], g["e_au"], z[1000:])
+    assert used == int(g["used_e"]) and relerr(en, g["en"]) < 1e-13
+    # covariance restatement == the reference's captured eigensystems
+    gwl, gam = P.gamma_grid(7, 4, 61, wmax=0.3)
+    for i in range(nmd // 2 + 1):
+        A = O.ph_covariance(i, gam, gwl, 300.0, float(g["phcut"]), dt, nmd)
+        assert np.max(np.abs((g["ph_au"][i] * g["ph_av"][i]) @ g["ph_au"][i].conj().T - A)) < 1e-12
+    efric, exim, exip = P.psd(3, 62, 0.05), P.antisym(3, 63, 0.01), P.sym(3, 64, 0.01)
+    for i in range(nmd // 2 + 1):
+        A = O.e_covariance(i, efric, exim, exip, 0.2, 300.0, 2.0, dt, nmd, False, False)
+        assert np.max(np.abs((g["e_au"][i] * g["e_av"][i]) @ g["e_au"][i].conj().T - A)) < 1e-12
+    # the factor form used by the CUDA path gives the same series as vargau with indexed draws
+    L = np.array([O.eig_factor(O.ph_covariance(i, gam, gwl, 300.0, float(g["phcut"]), dt, nmd))[0] for i in range(nmd // 2 + 1)])
+    xi = z[:(nmd // 2 + 1) * 4].reshape(nmd // 2 + 1, 4)
+    s = O.noise_from_factors(L, xi, dt, nmd)
+    assert np.all(np.isfinite(s)) and relerr(s, s[(-np.arange(nmd)) % nmd]) < 1e-12   # real spectrum -> even series
+
+
+def test_scalars(golden_dir):
+    g = np.load(os.path.join(golden_dir, "scalars.npz"))
+    for w, T, cl, zp, r in g["equ"]:
+        with np.errstate(all="ignore"):
+            o = O.equ(w, 0.4, T, bool(cl), bool(zp))
+        assert o == r or (np.isnan(o) and np.isnan(r))
+    assert np.array_equal(np.array([O.flinterp(x, g["xs"], g["ys"]) for x in g["xq"]]), g["fl"])
+    assert np.array_equal(np.array([O.nearest(x, g["xs"]) for x in g["xq"]]), g["nn"])
+    gwl, gam = P.gamma_grid(6, 3, 70, wmax=0.25)
+    wl = [0.3 * i / 40 for i in range(40)]
+    tl = [0.38 * i for i in range(9)]
+    assert relerr(O.gamt(tl, wl, gwl, gam, 0), g["gamt0"]) < 1e-13
+    assert relerr(O.gamt(tl, wl, gwl, gam, 0.01), g["gamt1"]) < 1e-13
+    assert O.equ(0.0, 1.0, 300.0) == 2 * O.KB * 300.0
+
+
+def test_bpt(golden_dir):
+    g = np.load(os.path.join(golden_dir, "bpt.npz"))
+    K = P.spring_chain_dyn(12, seed=80) / O.RPC ** 2
+    fixed = list(range(0, 3)) + list(range(33, 36))
+    Kr = np.delete(np.delete(0.5 * (K + K.T), fixed, 0), fixed, 1)
+    iL, iR = O.bpt_reduce_index(range(3, 12), 3), O.bpt_reduce_index(range(24, 33), 3)
+    tm = np.array([O.bpt_tm(Kr, w, 0.1, iL, iR) for w in g["tm"][:, 0]])
+    assert relerr(tm, g["tm"][:, 1]) < 1e-9
+    assert np.array_equal(g["tm"][:, 0], np.linspace(0, 0.25 / O.RPC, 21))
+    ps = np.array([O.bpt_ps_nobias(Kr, w, 300.0, 0.1, iL, iR, np.arange(30)) for w in g["ps"][:, 0]])
+    assert relerr(ps[1:], g["ps"][1:, 1]) < 1e-9
+    kap = np.array([O.thermalcurrent(g["tm"], T, 0.1) / (T * 0.1) for T in (100.0, 300.0, 900.0)])
+    assert relerr(kap, g["kappa"]) < 1e-12
+
+
+def test_sig(golden_dir):
+    g = np.load(os.path.join(golden_dir, "sig.npz"))
+    K00, K11, K01 = P.chain_blocks(4, seed=81)
+    K10 = K01.T
+    eta = float(g["eta"])
+    for d, key in (("L", "seL"), ("R", "seR")):
+        se = np.array([O.sig_selfenergy(K00, K11, K01, K10, w, eta, d) for w in g["ep"]])
+        assert relerr(se, g[key]) < 1e-10
+    tm = np.array([O.sig_tm(K00, K11, K01, K10, w, eta) for w in g["ep"]])
+    assert relerr(tm, g["tm"][:, 1]) < 1e-8
+    # physics KAT: a perfect chain transmits one channel per dof inside the band
+    assert 3.9 < tm[3] < 4.0001
