@@ -1,0 +1,107 @@
+/* sclmd_b200.h -- C ABI of libsclmd_b200.so (hand-written sm_100a CUDA).
+ *
+ * The reference (ydsbbt/sclmd) is pure Python/NumPy and has NO FFI layer for
+ * this path: its boundary is the Python class API.  The
+ * entry points below are what a ctypes binding inside the reference's own
+ * classes would call; each one cites the reference code it replaces.
+ * INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; the message is in
+ *     sclmd_last_error() (thread-local).  No exception or abort crosses the ABI.
+ *   - the caller owns every host buffer (copied at call time); the library
+ *     owns all device memory behind opaque handles; *_destroy releases it.
+ *   - all floating point data is IEEE binary64, complex is interleaved (re,im).
+ *   - one handle <-> one CUDA device + one stream; handles are not thread-safe,
+ *     distinct handles are independent.
+ *   - there is no CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef SCLMD_B200_H
+#define SCLMD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCLMD_OK 0
+#define SCLMD_ERR_ARG (-1)
+#define SCLMD_ERR_CUDA (-2)
+#define SCLMD_ERR_STATE (-3)
+#define SCLMD_ERR_NOCONV (-4) /* sig: >=100 decimation iterations (selfenergy.py:127-130) */
+
+const char *sclmd_last_error(void);
+int sclmd_version(void);
+/* number of visible CUDA devices (<0 on error) and basic properties */
+int sclmd_device_count(void);
+int sclmd_device_info(int device, int *sm_count, int *cc_major, int *cc_minor, uint64_t *mem_bytes);
+
+/* FP64 peak probes for the roofline denominators: kind 0 = DFMA chain (FP64 pipe),
+ * kind 1 = DMMA.8x8x4 chain (FP64 tensor path). Result in TFLOP/s. */
+int sclmd_probe_fp64(int device, int kind, double *tflops);
+
+/* ------------------------------------------------------------------ MD ---
+ * Ensemble velocity-Verlet integrator: replaces md.vv / md.force /
+ * md.potforce(harmonic) / bath.bforce (sclmd/md.py:367-474,
+ * sclmd/baths.py:224-255,448-458, sclmd/functions.py:146-153) for `ntraj`
+ * independent noise realisations advanced together. */
+typedef struct sclmd_md sclmd_md;
+
+/* md.__init__ (md.py:56-130): nph dofs, time step dt, noise period nmd */
+int sclmd_md_create(int nph, int ntraj, double dt, int nmd, int device, sclmd_md **out);
+int sclmd_md_destroy(sclmd_md *h);
+
+/* md.setDyn (md.py:250-292): K[nph*nph] row-major, already PSD-projected by the host */
+int sclmd_md_set_dyn(sclmd_md *h, const double *K);
+/* md.AddConstr (md.py:189, 782-794): dofs zeroed in p,q after every step; n=0 clears */
+int sclmd_md_set_constraint(sclmd_md *h, const int32_t *idx, int n);
+
+#define SCLMD_KERNEL_FULL 0 /* kernel[ml][nc][nc] */
+#define SCLMD_KERNEL_DIAG 1 /* kernel[ml][nc]     */
+/* md.AddBath (md.py:167-183) for a bath whose force is
+ *   f = noise[t%nmd] - c0*sum_{j<ml} kernel[j].p_{t-j}[cids]      (c0 = dt if ml>1 else 1;
+ *       baths.py:448-458, 234-241)
+ *     + Mq.q_t[cids] + Mp.p_t[cids]                                (optional, ml==1 only:
+ *       Mq = bias*(exim - zeta1), Mp = -bias*zeta2; baths.py:243-249; pass NULL when the
+ *       reference's all-three-non-zero test at baths.py:233 fails)
+ * returns the bath index in *bath_out. */
+int sclmd_md_add_bath(sclmd_md *h, const int32_t *cids, int nc, int ml, const double *kernel,
+                      int kernel_kind, const double *Mq, const double *Mp, int *bath_out);
+
+/* bath.noise (baths.py:191,408): noise[ntraj_sel][nmd][nc] for trajectories
+ * [traj0, traj0+ntraj_sel) */
+int sclmd_md_set_noise(sclmd_md *h, int bath, int traj0, int ntraj_sel, const double *noise);
+int sclmd_md_get_noise(sclmd_md *h, int bath, int traj0, int ntraj_sel, double *noise);
+
+/* md.p, md.q, md.t (md.py:372,411): q,p are [ntraj][nph]; NULL pointers are skipped */
+int sclmd_md_set_state(sclmd_md *h, const double *q, const double *p, int64_t t);
+int sclmd_md_get_state(sclmd_md *h, double *q, double *p, int64_t *t);
+/* md.ResetHis (md.py:340-349): zero all history rings and friction tails */
+int sclmd_md_reset_history(sclmd_md *h);
+/* md.phis (md.py:346,387) restricted to the bath dofs, reference order (row 0 = newest):
+ * phis[ntraj][ml][nc] */
+int sclmd_md_get_history(sclmd_md *h, int bath, double *phis);
+int sclmd_md_set_history(sclmd_md *h, int bath, const double *phis);
+
+/* `nsteps` calls of md.vv (md.py:367-411) for every trajectory.  elapsed_ms (may be
+ * NULL) receives the device time measured with CUDA events on the handle's stream. */
+int sclmd_md_run(sclmd_md *h, int64_t nsteps, float *elapsed_ms);
+
+/* bath.cur (md.py:397) and md.etot (md.py:383): [ntraj][nmd], index t % nmd */
+int sclmd_md_get_current(sclmd_md *h, int bath, double *cur);
+int sclmd_md_get_etot(sclmd_md *h, double *etot);
+/* per-bath sum over the nmd slots of cur for each trajectory (np.mean(cur)*nmd, md.py:663):
+ * sums[ntraj] -- the payload of the multi-GPU all-reduce */
+int sclmd_md_get_current_sums(sclmd_md *h, int bath, double *sums);
+
+/* instrumentation: kernels launched by this handle so far; name/time of the dominant kernel */
+int64_t sclmd_md_launch_count(sclmd_md *h);
+/* time `reps` launches of the history-tail kernel of `bath` alone (CUDA events): avg ms */
+int sclmd_md_time_tail(sclmd_md *h, int bath, int reps, float *avg_ms);
+int sclmd_md_time_potforce(sclmd_md *h, int reps, float *avg_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,189 @@
+// FP64 "NT" GEMM on the DMMA pipe (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4, the only FP64
+// tensor shape sm_100a has; tcgen05 has no FP64 kind).
+//
+//   C_z[M x N] = alpha * sum_{seg in split z}  A_seg[M x Kseg] . B_seg[N x Kseg]^T
+//
+// Both operands are K-contiguous.  "Segments" let one launch contract over a history
+// ring buffer: segment s of A lives at slot (a_head - s) mod a_mod of the ring, segment
+// s of B at (b_seg0 + s).  gridDim.z = number of K-splits; each split writes its own
+// partial C (deterministic; the consumer adds them in order).
+//
+// Used for: the harmonic force  G = Q K^T  (md.py:467), full memory-kernel tails
+// (baths.py:453-457), time-local friction / exim / zeta matrices (baths.py:236-249).
+#pragma once
+#include "common.cuh"
+
+namespace sclmd {
+
+struct GemmArgs {
+    int M, N, Kseg, nseg, segs_per_split;
+    const double *A;
+    long long lda, a_seg_stride;
+    int a_head, a_mod;  // a_mod > 0: ring addressing slot = (a_head - seg) mod a_mod
+    const double *B;
+    long long ldb, b_seg_stride;
+    int b_seg0;
+    double *C;
+    long long ldc, c_split_stride;
+    double alpha;
+};
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ void cp_async16_zfill(void *smem, const void *gmem, int src_bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+template <int BM, int BN, int WM, int WN, int STAGES>
+struct GemmCfg {
+    static constexpr int BK = 16;
+    static constexpr int LDS = BK + 4;  // 160 B row stride: conflict-free 64-bit fragment loads
+    static constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
+    static constexpr int THREADS = WARPS_M * WARPS_N * 32;
+    static constexpr int FM = WM / 8, FN = WN / 8;
+    static constexpr size_t SMEM = (size_t)STAGES * (BM + BN) * LDS * sizeof(double);
+};
+
+template <int BM, int BN, int WM, int WN, int STAGES>
+__global__ void __launch_bounds__(GemmCfg<BM, BN, WM, WN, STAGES>::THREADS)
+dgemm_nt_seg_kernel(const GemmArgs g) {
+    using Cfg = GemmCfg<BM, BN, WM, WN, STAGES>;
+    constexpr int BK = Cfg::BK, LDS = Cfg::LDS, THREADS = Cfg::THREADS, FM = Cfg::FM, FN = Cfg::FN;
+    extern __shared__ __align__(16) double smem[];
+    double *As = smem;                               // [STAGES][BM][LDS]
+    double *Bs = smem + (size_t)STAGES * BM * LDS;   // [STAGES][BN][LDS]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp / Cfg::WARPS_N) * WM, wn = (warp % Cfg::WARPS_N) * WN;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int seg_begin = blockIdx.z * g.segs_per_split;
+    const int seg_end = min(g.nseg, seg_begin + g.segs_per_split);
+    const int ktiles = (g.Kseg + BK - 1) / BK;
+    const int niter = max(0, seg_end - seg_begin) * ktiles;
+
+    auto load_tile = [&](int it, int stage) {
+        const int seg = seg_begin + it / ktiles;
+        const int k0 = (it % ktiles) * BK;
+        long long aoff, boff;
+        if (g.a_mod > 0) {
+            int slot = (g.a_head - seg) % g.a_mod;
+            if (slot < 0) slot += g.a_mod;
+            aoff = (long long)slot * g.a_seg_stride;
+        } else {
+            aoff = (long long)seg * g.a_seg_stride;
+        }
+        boff = (long long)(g.b_seg0 + seg) * g.b_seg_stride;
+        double *as = As + (size_t)stage * BM * LDS;
+        double *bs = Bs + (size_t)stage * BN * LDS;
+        constexpr int CPR = BK / 2;  // 16-byte chunks per row
+#pragma unroll
+        for (int c = tid; c < BM * CPR; c += THREADS) {
+            const int r = c / CPR, kc = (c % CPR) * 2;
+            const int gr = min(m0 + r, g.M - 1);
+            const int rem = g.Kseg - (k0 + kc);
+            const int nb = rem >= 2 ? 16 : (rem == 1 ? 8 : 0);
+            const double *src = g.A + aoff + (long long)gr * g.lda + (nb ? k0 + kc : 0);
+            cp_async16_zfill(as + r * LDS + kc, src, nb);
+        }
+#pragma unroll
+        for (int c = tid; c < BN * CPR; c += THREADS) {
+            const int r = c / CPR, kc = (c % CPR) * 2;
+            const int gr = min(n0 + r, g.N - 1);
+            const int rem = g.Kseg - (k0 + kc);
+            const int nb = rem >= 2 ? 16 : (rem == 1 ? 8 : 0);
+            const double *src = g.B + boff + (long long)gr * g.ldb + (nb ? k0 + kc : 0);
+            cp_async16_zfill(bs + r * LDS + kc, src, nb);
+        }
+    };
+
+    double acc[FM][FN][2];
+#pragma unroll
+    for (int i = 0; i < FM; ++i)
+#pragma unroll
+        for (int j = 0; j < FN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < niter) load_tile(s, s);
+        cp_async_commit();
+    }
+    const int frow = lane >> 2, fcol = lane & 3;
+    for (int it = 0; it < niter; ++it) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {   // prefetch tile it+STAGES-1 into the stage consumed at iteration it-1
+            const int nx = it + STAGES - 1;
+            if (nx < niter) load_tile(nx, nx % STAGES);
+            cp_async_commit();
+        }
+        const double *as = As + (size_t)(it % STAGES) * BM * LDS + (wm + frow) * LDS + fcol;
+        const double *bs = Bs + (size_t)(it % STAGES) * BN * LDS + (wn + frow) * LDS + fcol;
+#pragma unroll
+        for (int kk = 0; kk < BK; kk += 4) {
+            double a[FM], b[FN];
+#pragma unroll
+            for (int i = 0; i < FM; ++i) a[i] = as[i * 8 * LDS + kk];
+#pragma unroll
+            for (int j = 0; j < FN; ++j) b[j] = bs[j * 8 * LDS + kk];
+#pragma unroll
+            for (int i = 0; i < FM; ++i)
+#pragma unroll
+                for (int j = 0; j < FN; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    double *C = g.C + (long long)blockIdx.z * g.c_split_stride;
+#pragma unroll
+    for (int i = 0; i < FM; ++i) {
+        const int r = m0 + wm + i * 8 + frow;
+        if (r >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < FN; ++j) {
+            const int c = n0 + wn + j * 8 + 2 * fcol;
+            double *dst = C + (long long)r * g.ldc + c;
+            if (c + 1 < g.N) {
+                *reinterpret_cast<double2 *>(dst) = make_double2(g.alpha * acc[i][j][0], g.alpha * acc[i][j][1]);
+            } else if (c < g.N) {
+                dst[0] = g.alpha * acc[i][j][0];
+            }
+        }
+    }
+}
+
+template <int BM, int BN, int WM, int WN, int STAGES>
+inline cudaError_t launch_dgemm_cfg(const GemmArgs &g, int nsplit, cudaStream_t st) {
+    using Cfg = GemmCfg<BM, BN, WM, WN, STAGES>;
+    auto kern = dgemm_nt_seg_kernel<BM, BN, WM, WN, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    dim3 grid(cdiv(g.N, BN), cdiv(g.M, BM), nsplit);
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(g);
+    return cudaGetLastError();
+}
+
+// Tile choice: big tiles when the problem fills the machine, small ones for skinny M (few
+// trajectories) so that more CTAs exist.
+inline cudaError_t launch_dgemm(const GemmArgs &g, int nsplit, cudaStream_t st) {
+    if (g.M > 64) return launch_dgemm_cfg<128, 128, 64, 32, 3>(g, nsplit, st);
+    if (g.M > 16) return launch_dgemm_cfg<64, 64, 32, 32, 4>(g, nsplit, st);
+    return launch_dgemm_cfg<16, 128, 16, 32, 4>(g, nsplit, st);
+}
+#endif
+
+}  // namespace sclmd

@@ -1,0 +1,687 @@
+// Ensemble velocity-Verlet integrator for the semi-classical generalized Langevin equation.
+//
+// Replaces md.vv / md.force / md.potforce(harmonic) / {ebath,phbath}.bforce of the reference
+// (sclmd/md.py:367-474, sclmd/baths.py:224-255,448-458) for `ntraj` independent noise
+// realisations.  Single-tail restatement: per bath the friction tail
+//   S = dt * sum_{j>=1} kernel[j] . p_{t+1-j}[cids]
+// is contracted ONCE per step from an HBM ring buffer of p[cids] and reused by force
+// evaluations B, C of step t and A of step t+1.
+//
+// HBM layout (row-major, leading dims padded to even so every row is 16-byte aligned)
+//   q,p,G,...   [ntraj][ld]            ld  = nph rounded up to 2, pads stay 0
+//   K           [nph][ld]
+//   ring_b      [ntraj][ml_b][ncp_b]   slot s holds p_{t'}[cids] with t' mod ml_b == s
+//   kernel_b    diag [ml_b+1][ncp_b] (last row 0)   |   full [ml_b][nc_b][ncp_b]
+//   noise_b     [nmd][ntraj][ncp_b]    time-major: a step streams one contiguous slab
+//   cur_b,etot  [nmd][ntraj]
+//   tailp_b     [nsplit_b][ntraj][ncp_b]   partial tails, summed in fixed order by consumers
+#include <algorithm>
+#include <memory>
+
+#include "common.cuh"
+#include "dgemm.cuh"
+
+using namespace sclmd;
+
+namespace {
+
+constexpr int MAXB = 8;
+
+struct BathDev {  // POD view passed to kernels
+    int nc, ncp, ml, nsplit, diag, has_lin, use_tail;
+    double c0;
+    const int *inv;          // [nph] -> position in bath or -1
+    const int *cids;         // [nc]
+    const double *k0;        // diag: kernel row 0 [ncp]
+    const double *noise;     // [nmd][ntraj][ncp]
+    const double *tailp;     // [nsplit][ntraj][ncp]
+    const double *lin;       // [ntraj][ncp]
+    double *ring;            // [ntraj][ml][ncp]
+    double *cur;             // [nmd][ntraj]
+};
+struct BathSet {
+    int nb;
+    BathDev b[MAXB];
+};
+
+struct Bath {
+    int nc = 0, ncp = 0, ml = 1, kind = 0, nsplit = 1, Kw = 0;
+    bool has_lin = false, has_extra = false;
+    double c0 = 1.0;
+    DevBuf<int> cids, inv;
+    DevBuf<double> kern, W, ring, xq, lin, tailp, noise, cur;
+};
+
+// ---------------------------------------------------------------- kernels
+__device__ __forceinline__ double bath_force(const BathDev &b, int traj, int ntraj, int a, int slab, double x) {
+    double fb = b.noise[((size_t)slab * ntraj + traj) * b.ncp + a];
+    if (b.diag) fb -= b.c0 * b.k0[a] * x;
+    if (b.has_lin) fb += b.lin[(size_t)traj * b.ncp + a];
+    if (b.use_tail) {
+        double s = 0.0;
+        for (int z = 0; z < b.nsplit; ++z) s += b.tailp[((size_t)z * ntraj + traj) * b.ncp + a];
+        fb -= s;
+    }
+    return fb;
+}
+
+// evaluation A (md.py:383-398): etot, ring push, f_A, p_half, q_next, heat current
+__global__ void __launch_bounds__(256) k_phase_a(BathSet bs, int nph, int ld, int ntraj, int nmd, long long t, double dt,
+                                                  const double *__restrict__ q, const double *__restrict__ p,
+                                                  const double *__restrict__ G, double *__restrict__ phalf,
+                                                  double *__restrict__ qn, double *__restrict__ etot) {
+    __shared__ double red[32];
+    const int traj = blockIdx.x;
+    const size_t row = (size_t)traj * ld;
+    const int slab = (int)(t % nmd);
+    double ke = 0.0, cur[MAXB];
+#pragma unroll
+    for (int b = 0; b < MAXB; ++b) cur[b] = 0.0;
+    for (int i = threadIdx.x; i < nph; i += blockDim.x) {
+        const double pi = p[row + i], qi = q[row + i];
+        double f = -G[row + i];
+#pragma unroll
+        for (int b = 0; b < MAXB; ++b) {
+            if (b < bs.nb) {
+                const int a = bs.b[b].inv[i];
+                if (a >= 0) {
+                    const double fb = bath_force(bs.b[b], traj, ntraj, a, slab, pi);
+                    cur[b] += fb * pi;
+                    f += fb;
+                    bs.b[b].ring[((size_t)traj * bs.b[b].ml + (int)(t % bs.b[b].ml)) * bs.b[b].ncp + a] = pi;
+                }
+            }
+        }
+        ke += 0.5 * pi * pi;
+        phalf[row + i] = pi + f * dt / 2.0;
+        qn[row + i] = qi + pi * dt + f * dt * dt / 2.0;
+    }
+    ke = block_sum(ke, red);
+    if (threadIdx.x == 0) etot[(size_t)slab * ntraj + traj] = ke;
+#pragma unroll
+    for (int b = 0; b < MAXB; ++b) {
+        if (b < bs.nb) {
+            const double c = block_sum(cur[b], red);
+            if (threadIdx.x == 0) bs.b[b].cur[(size_t)slab * ntraj + traj] = c;
+        }
+    }
+}
+
+// evaluation B or C (md.py:401-404): pout = phalf + dt/2 * F(t+1; x, qn); `final` applies the
+// constraint (md.py:407-408) and commits q.
+__global__ void __launch_bounds__(256) k_phase_bc(BathSet bs, int nph, int ld, int ntraj, int nmd, long long t, double dt,
+                                                   const double *__restrict__ x, const double *__restrict__ phalf,
+                                                   const double *__restrict__ Gn, double *__restrict__ pout,
+                                                   const double *__restrict__ qn, double *__restrict__ qout,
+                                                   const unsigned char *__restrict__ cons, int final, int fused) {
+    const int traj = blockIdx.x;
+    const size_t row = (size_t)traj * ld;
+    const int slab = (int)((t + 1) % nmd);
+    for (int i = threadIdx.x; i < nph; i += blockDim.x) {
+        const double ph = phalf[row + i], g = Gn[row + i];
+        double xi = fused ? ph : x[row + i];
+        double pnew = 0.0;
+        const int reps = fused ? 2 : 1;  // all baths time-local & diagonal: B and C in registers
+        for (int r = 0; r < reps; ++r) {
+            double f = -g;
+#pragma unroll
+            for (int b = 0; b < MAXB; ++b) {
+                if (b < bs.nb) {
+                    const int a = bs.b[b].inv[i];
+                    if (a >= 0) f += bath_force(bs.b[b], traj, ntraj, a, slab, xi);
+                }
+            }
+            pnew = ph + dt * f / 2.0;
+            xi = pnew;
+        }
+        if (final) {
+            double qv = qn[row + i];
+            if (cons && cons[i]) {
+                pnew = 0.0;
+                qv = 0.0;
+            }
+            qout[row + i] = qv;
+        }
+        pout[row + i] = pnew;
+    }
+}
+
+// xq[traj] = [ x[cids] | q[cids] ]  (operand of the time-local matrix product, baths.py:236-249)
+__global__ void k_gather_xq(const int *__restrict__ cids, int nc, int ncp, int Kw, int ld,
+                            const double *__restrict__ x, const double *__restrict__ q, double *__restrict__ xq) {
+    const int traj = blockIdx.x;
+    for (int a = threadIdx.x; a < nc; a += blockDim.x) {
+        const int i = cids[a];
+        xq[(size_t)traj * Kw + a] = x[(size_t)traj * ld + i];
+        if (Kw > ncp) xq[(size_t)traj * Kw + ncp + a] = q[(size_t)traj * ld + i];
+    }
+}
+
+// Diagonal-kernel friction tail (baths.py:453-457 restricted to j>=1), the HBM-streaming kernel:
+//   out[z][traj][c] = dt * sum_{s in rows of split z} kern[((head - s) mod ml) + 1][c] * ring[traj][s][c]
+// kern has ml+1 rows, row ml == 0, so the slot that would pair with j == ml drops out branch-free.
+// Thread = one column pair (16-byte loads) x one row group; T trajectories share each kernel load.
+template <int T>
+__global__ void __launch_bounds__(512) k_tail_diag(const double *__restrict__ ring, const double *__restrict__ kern,
+                                                    double *__restrict__ out, int ntraj, int ml, int ncp, int head,
+                                                    int rows_per_split, int cpt, int rg_count, double dt) {
+    extern __shared__ double red[];  // [rg_count][T][2*cpt]
+    const int cp = threadIdx.x % cpt, rg = threadIdx.x / cpt;
+    const int col = (blockIdx.z * cpt + cp) * 2;
+    const int traj0 = blockIdx.x * T;
+    const int r0 = blockIdx.y * rows_per_split, r1 = min(ml, r0 + rows_per_split);
+    const bool active = rg < rg_count && col < ncp;
+    double2 acc[T];
+#pragma unroll
+    for (int k = 0; k < T; ++k) acc[k] = make_double2(0.0, 0.0);
+    if (active) {
+        const size_t tstride = (size_t)ml * ncp;
+        const double *rbase = ring + (size_t)traj0 * tstride + col;
+        constexpr int U = 4;
+        int s = r0 + rg;
+        for (; s + (U - 1) * rg_count < r1; s += U * rg_count) {
+            double2 kv[U], hv[U][T];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int ss = s + u * rg_count;
+                int d = head - ss;
+                if (d < 0) d += ml;
+                kv[u] = *reinterpret_cast<const double2 *>(kern + (size_t)(d + 1) * ncp + col);
+#pragma unroll
+                for (int k = 0; k < T; ++k) {
+                    const int tr = min(traj0 + k, ntraj - 1) - traj0;
+                    hv[u][k] = ld_stream2(rbase + (size_t)tr * tstride + (size_t)ss * ncp);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int k = 0; k < T; ++k) {
+                    acc[k].x = fma(kv[u].x, hv[u][k].x, acc[k].x);
+                    acc[k].y = fma(kv[u].y, hv[u][k].y, acc[k].y);
+                }
+        }
+        for (; s < r1; s += rg_count) {
+            int d = head - s;
+            if (d < 0) d += ml;
+            const double2 kv = *reinterpret_cast<const double2 *>(kern + (size_t)(d + 1) * ncp + col);
+#pragma unroll
+            for (int k = 0; k < T; ++k) {
+                const int tr = min(traj0 + k, ntraj - 1) - traj0;
+                const double2 hv = ld_stream2(rbase + (size_t)tr * tstride + (size_t)s * ncp);
+                acc[k].x = fma(kv.x, hv.x, acc[k].x);
+                acc[k].y = fma(kv.y, hv.y, acc[k].y);
+            }
+        }
+    }
+    if (rg < rg_count) {
+#pragma unroll
+        for (int k = 0; k < T; ++k) {
+            red[((size_t)rg * T + k) * 2 * cpt + 2 * cp] = acc[k].x;
+            red[((size_t)rg * T + k) * 2 * cpt + 2 * cp + 1] = acc[k].y;
+        }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < T * 2 * cpt; e += blockDim.x) {
+        const int k = e / (2 * cpt), cc = e % (2 * cpt);
+        const int c = blockIdx.z * cpt * 2 + cc;
+        if (traj0 + k >= ntraj || c >= ncp) continue;
+        double s = 0.0;
+        for (int g = 0; g < rg_count; ++g) s += red[((size_t)g * T + k) * 2 * cpt + cc];
+        out[((size_t)blockIdx.y * ntraj + traj0 + k) * ncp + c] = dt * s;
+    }
+}
+
+__global__ void k_sum_slots(const double *__restrict__ cur, int nmd, int ntraj, double *__restrict__ sums) {
+    const int traj = blockIdx.x * blockDim.x + threadIdx.x;
+    if (traj >= ntraj) return;
+    double s = 0.0;
+    for (int k = 0; k < nmd; ++k) s += cur[(size_t)k * ntraj + traj];
+    sums[traj] = s;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- handle
+struct sclmd_md {
+    int nph = 0, ld = 0, ntraj = 0, nmd = 0, device = 0, nsm = 148;
+    double dt = 0;
+    long long t = 0;
+    bool g_valid = false, have_dyn = false;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    DevBuf<double> K, q, p, G, Gn, phalf, p1, qn, etot, scratch;
+    DevBuf<unsigned char> cons;
+    bool has_cons = false;
+    std::vector<std::unique_ptr<Bath>> baths;
+    int64_t launches = 0;
+
+    BathSet view() const {
+        BathSet s;
+        memset(&s, 0, sizeof(s));
+        s.nb = (int)baths.size();
+        for (int i = 0; i < s.nb; ++i) {
+            const Bath &b = *baths[i];
+            BathDev &d = s.b[i];
+            d.nc = b.nc; d.ncp = b.ncp; d.ml = b.ml; d.nsplit = b.nsplit;
+            d.diag = b.kind == SCLMD_KERNEL_DIAG;
+            d.has_lin = b.has_lin; d.use_tail = b.ml > 1; d.c0 = b.c0;
+            d.inv = b.inv.p; d.cids = b.cids.p; d.k0 = b.kern.p; d.noise = b.noise.p;
+            d.tailp = b.tailp.p; d.lin = b.lin.p; d.ring = b.ring.p; d.cur = b.cur.p;
+        }
+        return s;
+    }
+    bool any_lin() const {
+        for (auto &b : baths) if (b->has_lin) return true;
+        return false;
+    }
+
+    int potforce(const double *qsrc, double *dst) {  // dst = qsrc . K^T   (md.py:467, sign applied by consumers)
+        GemmArgs g{};
+        g.M = ntraj; g.N = nph; g.Kseg = ld; g.nseg = 1; g.segs_per_split = 1;
+        g.A = qsrc; g.lda = ld; g.a_seg_stride = 0; g.a_head = 0; g.a_mod = 0;
+        g.B = K.p; g.ldb = ld; g.b_seg_stride = 0; g.b_seg0 = 0;
+        g.C = dst; g.ldc = ld; g.c_split_stride = 0; g.alpha = 1.0;
+        SCLMD_CUDA(launch_dgemm(g, 1, st));
+        ++launches;
+        return 0;
+    }
+    int bath_lin(Bath &b, const double *x, const double *qq) {  // lin = [x|q][cids] . W^T
+        k_gather_xq<<<ntraj, 128, 0, st>>>(b.cids.p, b.nc, b.ncp, b.Kw, ld, x, qq, b.xq.p);
+        SCLMD_CUDA(cudaGetLastError());
+        GemmArgs g{};
+        g.M = ntraj; g.N = b.nc; g.Kseg = b.Kw; g.nseg = 1; g.segs_per_split = 1;
+        g.A = b.xq.p; g.lda = b.Kw; g.B = b.W.p; g.ldb = b.Kw;
+        g.C = b.lin.p; g.ldc = b.ncp; g.alpha = 1.0;
+        SCLMD_CUDA(launch_dgemm(g, 1, st));
+        launches += 2;
+        return 0;
+    }
+    int tail(Bath &b, int head) {  // partial tails from the ring with p_t already pushed at slot `head`
+        if (b.ml <= 1) return 0;
+        if (b.kind == SCLMD_KERNEL_DIAG) {
+            const int cp_total = b.ncp / 2;
+            const int cpt = std::min(cp_total, 256);
+            const int rg = std::max(1, std::min(512 / cpt, b.ml));
+            const int T = ntraj >= 4 ? 4 : 1;
+            dim3 grid(cdiv(ntraj, T), b.nsplit, cdiv(cp_total, cpt));
+            const int rps = cdiv(b.ml, b.nsplit);
+            const int threads = round_up(cpt * rg, 32);
+            const size_t sm = (size_t)rg * T * 2 * cpt * sizeof(double);
+            if (T == 4)
+                k_tail_diag<4><<<grid, threads, sm, st>>>(b.ring.p, b.kern.p, b.tailp.p, ntraj, b.ml, b.ncp, head, rps, cpt, rg, dt);
+            else
+                k_tail_diag<1><<<grid, threads, sm, st>>>(b.ring.p, b.kern.p, b.tailp.p, ntraj, b.ml, b.ncp, head, rps, cpt, rg, dt);
+            SCLMD_CUDA(cudaGetLastError());
+        } else {
+            GemmArgs g{};
+            g.M = ntraj; g.N = b.nc; g.Kseg = b.ncp; g.nseg = b.ml - 1;
+            g.segs_per_split = cdiv(g.nseg, b.nsplit);
+            g.A = b.ring.p; g.lda = (long long)b.ml * b.ncp; g.a_seg_stride = b.ncp; g.a_head = head; g.a_mod = b.ml;
+            g.B = b.kern.p; g.ldb = b.ncp; g.b_seg_stride = (long long)b.nc * b.ncp; g.b_seg0 = 1;
+            g.C = b.tailp.p; g.ldc = b.ncp; g.c_split_stride = (long long)ntraj * b.ncp; g.alpha = dt;
+            SCLMD_CUDA(launch_dgemm(g, b.nsplit, st));
+        }
+        ++launches;
+        return 0;
+    }
+
+    int step() {
+        BathSet bs = view();
+        const bool lin = any_lin();
+        if (!g_valid) {
+            if (int e = potforce(q.p, G.p)) return e;
+            g_valid = true;
+        }
+        if (lin)
+            for (auto &b : baths)
+                if (b->has_lin) if (int e = bath_lin(*b, p.p, q.p)) return e;
+        k_phase_a<<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, q.p, p.p, G.p, phalf.p, qn.p, etot.p);
+        SCLMD_CUDA(cudaGetLastError());
+        ++launches;
+        for (auto &b : baths) if (int e = tail(*b, (int)(t % b->ml))) return e;
+        if (int e = potforce(qn.p, Gn.p)) return e;
+        const unsigned char *cm = has_cons ? cons.p : nullptr;
+        if (!lin) {
+            k_phase_bc<<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, nullptr, phalf.p, Gn.p, p.p, qn.p, q.p, cm, 1, 1);
+            SCLMD_CUDA(cudaGetLastError());
+            ++launches;
+        } else {
+            for (auto &b : baths)
+                if (b->has_lin) if (int e = bath_lin(*b, phalf.p, qn.p)) return e;
+            k_phase_bc<<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, phalf.p, phalf.p, Gn.p, p1.p, qn.p, q.p, cm, 0, 0);
+            SCLMD_CUDA(cudaGetLastError());
+            for (auto &b : baths)
+                if (b->has_lin) if (int e = bath_lin(*b, p1.p, qn.p)) return e;
+            k_phase_bc<<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, p1.p, phalf.p, Gn.p, p.p, qn.p, q.p, cm, 1, 0);
+            SCLMD_CUDA(cudaGetLastError());
+            launches += 2;
+        }
+        if (has_cons) {
+            g_valid = false;  // q_{t+1} = constrain(q') != q'  -> K.q must be re-evaluated (md.py:449 cache miss)
+        } else {
+            std::swap(G.p, Gn.p);
+        }
+        ++t;
+        return 0;
+    }
+};
+
+// ---------------------------------------------------------------- C ABI
+extern "C" {
+
+int sclmd_md_create(int nph, int ntraj, double dt, int nmd, int device, sclmd_md **out) {
+    SCLMD_REQUIRE(out != nullptr, "sclmd_md_create: out is NULL");
+    *out = nullptr;
+    SCLMD_REQUIRE(nph > 0 && ntraj > 0 && nmd > 0 && dt > 0, "sclmd_md_create: nph, ntraj, nmd, dt must be positive");
+    if (int e = select_device(device)) return e;
+    std::unique_ptr<sclmd_md> h(new sclmd_md());
+    h->nph = nph; h->ld = round_up(nph, 2); h->ntraj = ntraj; h->nmd = nmd; h->dt = dt; h->device = device;
+    h->nsm = sm_count(device);
+    SCLMD_CUDA(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+    SCLMD_CUDA(cudaEventCreate(&h->ev0));
+    SCLMD_CUDA(cudaEventCreate(&h->ev1));
+    const size_t n = (size_t)ntraj * h->ld;
+    SCLMD_CUDA(h->K.alloc((size_t)nph * h->ld));
+    SCLMD_CUDA(h->q.alloc(n)); SCLMD_CUDA(h->p.alloc(n)); SCLMD_CUDA(h->G.alloc(n)); SCLMD_CUDA(h->Gn.alloc(n));
+    SCLMD_CUDA(h->phalf.alloc(n)); SCLMD_CUDA(h->p1.alloc(n)); SCLMD_CUDA(h->qn.alloc(n));
+    SCLMD_CUDA(h->etot.alloc((size_t)nmd * ntraj));
+    SCLMD_CUDA(h->cons.alloc(nph));
+    SCLMD_CUDA(h->scratch.alloc(ntraj));
+    *out = h.release();
+    return SCLMD_OK;
+}
+
+int sclmd_md_destroy(sclmd_md *h) {
+    if (!h) return SCLMD_OK;
+    cudaSetDevice(h->device);
+    if (h->st) cudaStreamSynchronize(h->st);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->st) cudaStreamDestroy(h->st);
+    delete h;
+    return SCLMD_OK;
+}
+
+int sclmd_md_set_dyn(sclmd_md *h, const double *K) {
+    SCLMD_REQUIRE(h && K, "sclmd_md_set_dyn: NULL argument");
+    SCLMD_CUDA(cudaSetDevice(h->device));
+    SCLMD_CUDA(cudaMemcpy2DAsync(h->K.p, h->ld * sizeof(double), K, h->nph * sizeof(double), h->nph * sizeof(double), h->nph,
+                                 cudaMemcpyHostToDevice, h->st));
+    SCLMD_CUDA(cudaStreamSynchronize(h->st));
+    h->have_dyn = true;
+    h->g_valid = false;
+    return SCLMD_OK;
+}
+
+int sclmd_md_set_constraint(sclmd_md *h, const int32_t *idx, int n) {
+    SCLMD_REQUIRE(h && (n == 0 || idx), "sclmd_md_set_constraint: NULL argument");
+    SCLMD_CUDA(cudaSetDevice(h->device));
+    std::vector<unsigned char> m(h->nph, 0);
+    for (int i = 0; i < n; ++i) {
+        SCLMD_REQUIRE(idx[i] >= 0 && idx[i] < h->nph, "sclmd_md_set_constraint: index %d out of range", idx[i]);
+        m[idx[i]] = 1;
+    }
+    SCLMD_CUDA(cudaMemcpy(h->cons.p, m.data(), h->nph, cudaMemcpyHostToDevice));
+    h->has_cons = n > 0;
+    return SCLMD_OK;
+}
+
+int sclmd_md_add_bath(sclmd_md *h, const int32_t *cids, int nc, int ml, const double *kernel, int kernel_kind,
+                      const double *Mq, const double *Mp, int *bath_out) {
+    SCLMD_REQUIRE(h && cids && kernel, "sclmd_md_add_bath: NULL argument");
+    SCLMD_REQUIRE(nc > 0 && ml >= 1, "sclmd_md_add_bath: nc and ml must be positive");
+    SCLMD_REQUIRE(kernel_kind == SCLMD_KERNEL_FULL || kernel_kind == SCLMD_KERNEL_DIAG, "sclmd_md_add_bath: bad kernel_kind");
+    SCLMD_REQUIRE((int)h->baths.size() < MAXB, "sclmd_md_add_bath: at most %d baths", MAXB);
+    SCLMD_REQUIRE(!(Mq || Mp) || ml == 1, "sclmd_md_add_bath: Mq/Mp only act for time-local baths (baths.py:243-249)");
+    SCLMD_CUDA(cudaSetDevice(h->device));
+    std::unique_ptr<Bath> b(new Bath());
+    b->nc = nc; b->ncp = round_up(nc, 2); b->ml = ml; b->kind = kernel_kind;
+    b->c0 = ml > 1 ? h->dt : 1.0;  // baths.py:454-457: the dt factor only exists for ml > 1
+    b->has_extra = (Mq || Mp);
+    b->has_lin = kernel_kind == SCLMD_KERNEL_FULL || b->has_extra;
+    const int ncp = b->ncp, ntraj = h->ntraj;
+    std::vector<int> inv(h->nph, -1);
+    for (int a = 0; a < nc; ++a) {
+        SCLMD_REQUIRE(cids[a] >= 0 && cids[a] < h->nph, "sclmd_md_add_bath: dof index %d out of range", cids[a]);
+        SCLMD_REQUIRE(inv[cids[a]] < 0, "sclmd_md_add_bath: duplicate dof index %d", cids[a]);
+        inv[cids[a]] = a;
+    }
+    SCLMD_CUDA(b->cids.alloc(nc)); SCLMD_CUDA(b->inv.alloc(h->nph));
+    SCLMD_CUDA(cudaMemcpy(b->cids.p, cids, nc * sizeof(int), cudaMemcpyHostToDevice));
+    SCLMD_CUDA(cudaMemcpy(b->inv.p, inv.data(), h->nph * sizeof(int), cudaMemcpyHostToDevice));
+    // kernel
+    if (kernel_kind == SCLMD_KERNEL_DIAG) {
+        SCLMD_CUDA(b->kern.alloc((size_t)(ml + 1) * ncp));
+        SCLMD_CUDA(cudaMemcpy2D(b->kern.p, ncp * sizeof(double), kernel, nc * sizeof(double), nc * sizeof(double), ml, cudaMemcpyHostToDevice));
+    } else {
+        SCLMD_CUDA(b->kern.alloc((size_t)ml * nc * ncp));
+        SCLMD_CUDA(cudaMemcpy2D(b->kern.p, ncp * sizeof(double), kernel, nc * sizeof(double), nc * sizeof(double), (size_t)ml * nc, cudaMemcpyHostToDevice));
+    }
+    if (b->has_lin) {  // W = [ -c0*K0 + Mp | Mq ]  (K0 = 0 here for diagonal kernels: handled elementwise)
+        b->Kw = b->has_extra ? 2 * ncp : ncp;
+        std::vector<double> W((size_t)nc * b->Kw, 0.0);
+        for (int a = 0; a < nc; ++a)
+            for (int c = 0; c < nc; ++c) {
+                double v = 0.0;
+                if (kernel_kind == SCLMD_KERNEL_FULL) v -= b->c0 * kernel[(size_t)a * nc + c];
+                if (Mp) v += Mp[(size_t)a * nc + c];
+                W[(size_t)a * b->Kw + c] = v;
+                if (b->has_extra && Mq) W[(size_t)a * b->Kw + ncp + c] = Mq[(size_t)a * nc + c];
+            }
+        SCLMD_CUDA(b->W.alloc(W.size()));
+        SCLMD_CUDA(cudaMemcpy(b->W.p, W.data(), W.size() * sizeof(double), cudaMemcpyHostToDevice));
+        SCLMD_CUDA(b->xq.alloc((size_t)ntraj * b->Kw));
+        SCLMD_CUDA(b->lin.alloc((size_t)ntraj * ncp));
+    }
+    SCLMD_CUDA(b->ring.alloc((size_t)ntraj * ml * ncp));
+    if (ml > 1) {
+        // enough CTAs to fill the machine a few times over, deterministic partial sums
+        int tiles = kernel_kind == SCLMD_KERNEL_DIAG ? cdiv(ntraj, ntraj >= 4 ? 4 : 1) * cdiv(ncp / 2, 256)
+                                                      : cdiv(ntraj, 128) * cdiv(nc, 128);
+        int want = kernel_kind == SCLMD_KERNEL_DIAG ? 4 * h->nsm : 2 * h->nsm;
+        b->nsplit = std::max(1, std::min({cdiv(want, tiles), 32, std::max(1, (ml - 1) / 64)}));
+        SCLMD_CUDA(b->tailp.alloc((size_t)b->nsplit * ntraj * ncp));
+    }
+    SCLMD_CUDA(b->noise.alloc((size_t)h->nmd * ntraj * ncp));
+    SCLMD_CUDA(b->cur.alloc((size_t)h->nmd * ntraj));
+    if (bath_out) *bath_out = (int)h->baths.size();
+    h->baths.push_back(std::move(b));
+    return SCLMD_OK;
+}
+
+static int check_bath(sclmd_md *h, int bath, const char *fn) {
+    SCLMD_REQUIRE(h, "%s: NULL handle", fn);
+    SCLMD_REQUIRE(bath >= 0 && bath < (int)h->baths.size(), "%s: bath index %d out of range", fn, bath);
+    return 0;
+}
+
+int sclmd_md_set_noise(sclmd_md *h, int bath, int traj0, int nsel, const double *noise) {
+    if (int e = check_bath(h, bath, "sclmd_md_set_noise")) return e;
+    SCLMD_REQUIRE(noise && traj0 >= 0 && nsel > 0 && traj0 + nsel <= h->ntraj, "sclmd_md_set_noise: bad trajectory range");
+    SCLMD_CUDA(cudaSetDevice(h->device));
+    Bath &b = *h->baths[bath];
+    // host [traj][nmd][nc] -> device [nmd][ntraj][ncp]: one strided copy per trajectory
+    for (int k = 0; k < nsel; ++k)
+        SCLMD_CUDA(cudaMemcpy2DAsync(b.noise.p + (size_t)(traj0 + k) * b.ncp, (size_t)h->ntraj * b.ncp * sizeof(double),
+                                     noise + (size_t)k * h->nmd * b.nc, b.nc * sizeof(double), b.nc * sizeof(double), h->nmd,
+                                     cudaMemcpyHostToDevice, h->st));
+    SCLMD_CUDA(cudaStreamSynchronize(h->st));
+    return SCLMD_OK;
+}
+
+int sclmd_md_get_noise(sclmd_md *h, int bath, int traj0, int nsel, double *noise) {
+    if (int e = check_bath(h, bath, "sclmd_md_get_noise")) return e;
+    SCLMD_REQUIRE(noise && traj0 >= 0 && nsel > 0 && traj0 + nsel <= h->ntraj, "sclmd_md_get_noise: bad trajectory range");
+    SCLMD_CUDA(cudaSetDevice(h->device));
+    Bath &b = *h->baths[bath];
+    for (int k = 0; k < nsel; ++k)
+        SCLMD_CUDA(cudaMemcpy2DAsync(noise + (size_t)k * h->nmd * b.nc, b.nc * sizeof(double),
+                                     b.noise.p + (size_t)(traj0 + k) * b.ncp, (size_t)h->ntraj * b.ncp * sizeof(double),
+                                     b.nc * sizeof(double), h->nmd, cudaMemcpyDeviceToHost, h->st));
+    SCLMD_CUDA(cudaStreamSynchronize(h->st));
+    return SCLMD_OK;
+}
+
+int sclmd_md_set_state(sclmd_md *h, const double *q, const double *p, int64_t t) {
+    SCLMD_REQUIRE(h, "sclmd_md_set_state: NULL handle");
+    SCLMD_CUDA(cudaSetDevice(h->device));
+    const size_t w = h->nph * sizeof(double), pitch = h->ld * sizeof(double);
+    if (q) SCLMD_CUDA(cudaMemcpy2DAsync(h->q.p, pitch, q, w, w, h->ntraj, cudaMemcpyHostToDevice, h->st));
+    if (p) SCLMD_CUDA(cudaMemcpy2DAsync(h->p.p, pitch, p, w, w, h->ntraj, cudaMemcpyHostToDevice, h->st));
+    SCLMD_CUDA(cudaStreamSynchronize(h->st));
+    if (t >= 0) h->t = t;
+    if (q) h->g_valid = false;
+    return SCLMD_OK;
+}
+
+int sclmd_md_get_state(sclmd_md *h, double *q, double *p, int64_t *t) {
+    SCLMD_REQUIRE(h, "sclmd_md_get_state: NULL handle");
+    SCLMD_CUDA(cudaSetDevice(h->device));
+    const size_t w = h->nph * sizeof(double), pitch = h->ld * sizeof(double);
+    if (q) SCLMD_CUDA(cudaMemcpy2DAsync(q, w, h->q.p, pitch, w, h->ntraj, cudaMemcpyDeviceToHost, h->st));
+    if (p) SCLMD_CUDA(cudaMemcpy2DAsync(p, w, h->p.p, pitch, w, h->ntraj, cudaMemcpyDeviceToHost, h->st));
+    SCLMD_CUDA(cudaStreamSynchronize(h->st));
+    if (t) *t = h->t;
+    return SCLMD_OK;
+}
+
+int sclmd_md_reset_history(sclmd_md *h) {
+    SCLMD_REQUIRE(h, "sclmd_md_reset_history: NULL handle");
+    SCLMD_CUDA(cudaSetDevice(h->device));
+    for (auto &b : h->baths) {
+        SCLMD_CUDA(cudaMemsetAsync(b->ring.p, 0, b->ring.n * sizeof(double), h->st));
+        if (b->tailp.p) SCLMD_CUDA(cudaMemsetAsync(b->tailp.p, 0, b->tailp.n * sizeof(double), h->st));
+    }
+    SCLMD_CUDA(cudaStreamSynchronize(h->st));
+    return SCLMD_OK;
+}
+
+// reference order: phis[i] = p_{t-1-i}[cids]  (md.py:387; row 0 newest) <-> ring slot (t-1-i) mod ml
+int sclmd_md_get_history(sclmd_md *h, int bath, double *phis) {
+    if (int e = check_bath(h, bath, "sclmd_md_get_history")) return e;
+    SCLMD_REQUIRE(phis, "sclmd_md_get_history: NULL buffer");
+    SCLMD_CUDA(cudaSetDevice(h->device));
+    Bath &b = *h->baths[bath];
+    std::vector<double> tmp(b.ring.n);
+    SCLMD_CUDA(cudaMemcpy(tmp.data(), b.ring.p, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int tr = 0; tr < h->ntraj; ++tr)
+        for (int i = 0; i < b.ml; ++i) {
+            long long s = (h->t - 1 - i) % b.ml;
+            if (s < 0) s += b.ml;
+            memcpy(phis + ((size_t)tr * b.ml + i) * b.nc, tmp.data() + ((size_t)tr * b.ml + s) * b.ncp, b.nc * sizeof(double));
+        }
+    return SCLMD_OK;
+}
+
+int sclmd_md_set_history(sclmd_md *h, int bath, const double *phis) {
+    if (int e = check_bath(h, bath, "sclmd_md_set_history")) return e;
+    SCLMD_REQUIRE(phis, "sclmd_md_set_history: NULL buffer");
+    SCLMD_CUDA(cudaSetDevice(h->device));
+    Bath &b = *h->baths[bath];
+    std::vector<double> tmp(b.ring.n, 0.0);
+    for (int tr = 0; tr < h->ntraj; ++tr)
+        for (int i = 0; i < b.ml; ++i) {
+            long long s = (h->t - 1 - i) % b.ml;
+            if (s < 0) s += b.ml;
+            memcpy(tmp.data() + ((size_t)tr * b.ml + s) * b.ncp, phis + ((size_t)tr * b.ml + i) * b.nc, b.nc * sizeof(double));
+        }
+    SCLMD_CUDA(cudaMemcpy(b.ring.p, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice));
+    // the tail for evaluation A of the next step: ring as if p_{t-1} had just been pushed
+    if (b.ml > 1) {
+        long long head = (h->t - 1) % b.ml;
+        if (head < 0) head += b.ml;
+        if (int e = h->tail(b, (int)head)) return e;
+        SCLMD_CUDA(cudaStreamSynchronize(h->st));
+    }
+    return SCLMD_OK;
+}
+
+int sclmd_md_run(sclmd_md *h, int64_t nsteps, float *elapsed_ms) {
+    SCLMD_REQUIRE(h && nsteps >= 0, "sclmd_md_run: bad arguments");
+    if (!h->have_dyn) {
+        set_error("sclmd_md_run: no dynamical matrix set (md.py:469 'no driver, no md')");
+        return SCLMD_ERR_STATE;
+    }
+    SCLMD_CUDA(cudaSetDevice(h->device));
+    SCLMD_CUDA(cudaEventRecord(h->ev0, h->st));
+    for (int64_t s = 0; s < nsteps; ++s)
+        if (int e = h->step()) return e;
+    SCLMD_CUDA(cudaEventRecord(h->ev1, h->st));
+    SCLMD_CUDA(cudaStreamSynchronize(h->st));
+    if (elapsed_ms) SCLMD_CUDA(cudaEventElapsedTime(elapsed_ms, h->ev0, h->ev1));
+    return SCLMD_OK;
+}
+
+static int get_slots(sclmd_md *h, const double *dev, double *host) {  // device [nmd][ntraj] -> host [ntraj][nmd]
+    std::vector<double> tmp((size_t)h->nmd * h->ntraj);
+    SCLMD_CUDA(cudaMemcpy(tmp.data(), dev, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < h->nmd; ++k)
+        for (int tr = 0; tr < h->ntraj; ++tr) host[(size_t)tr * h->nmd + k] = tmp[(size_t)k * h->ntraj + tr];
+    return SCLMD_OK;
+}
+
+int sclmd_md_get_current(sclmd_md *h, int bath, double *cur) {
+    if (int e = check_bath(h, bath, "sclmd_md_get_current")) return e;
+    SCLMD_REQUIRE(cur, "sclmd_md_get_current: NULL buffer");
+    SCLMD_CUDA(cudaSetDevice(h->device));
+    return get_slots(h, h->baths[bath]->cur.p, cur);
+}
+
+int sclmd_md_get_etot(sclmd_md *h, double *etot) {
+    SCLMD_REQUIRE(h && etot, "sclmd_md_get_etot: NULL argument");
+    SCLMD_CUDA(cudaSetDevice(h->device));
+    return get_slots(h, h->etot.p, etot);
+}
+
+int sclmd_md_get_current_sums(sclmd_md *h, int bath, double *sums) {
+    if (int e = check_bath(h, bath, "sclmd_md_get_current_sums")) return e;
+    SCLMD_REQUIRE(sums, "sclmd_md_get_current_sums: NULL buffer");
+    SCLMD_CUDA(cudaSetDevice(h->device));
+    k_sum_slots<<<cdiv(h->ntraj, 128), 128, 0, h->st>>>(h->baths[bath]->cur.p, h->nmd, h->ntraj, h->scratch.p);
+    SCLMD_CUDA(cudaGetLastError());
+    ++h->launches;
+    SCLMD_CUDA(cudaMemcpyAsync(sums, h->scratch.p, h->ntraj * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    SCLMD_CUDA(cudaStreamSynchronize(h->st));
+    return SCLMD_OK;
+}
+
+int64_t sclmd_md_launch_count(sclmd_md *h) { return h ? h->launches : -1; }
+
+int sclmd_md_time_tail(sclmd_md *h, int bath, int reps, float *avg_ms) {
+    if (int e = check_bath(h, bath, "sclmd_md_time_tail")) return e;
+    SCLMD_REQUIRE(reps > 0 && avg_ms, "sclmd_md_time_tail: bad arguments");
+    SCLMD_CUDA(cudaSetDevice(h->device));
+    Bath &b = *h->baths[bath];
+    SCLMD_REQUIRE(b.ml > 1, "sclmd_md_time_tail: bath %d is time-local (no history tail)", bath);
+    // tailp is scratch between steps only in the sense that re-running with the same head is idempotent
+    long long head = (h->t - 1) % b.ml;
+    if (head < 0) head += b.ml;
+    if (int e = h->tail(b, (int)head)) return e;  // warm-up
+    SCLMD_CUDA(cudaEventRecord(h->ev0, h->st));
+    for (int r = 0; r < reps; ++r)
+        if (int e = h->tail(b, (int)head)) return e;
+    SCLMD_CUDA(cudaEventRecord(h->ev1, h->st));
+    SCLMD_CUDA(cudaStreamSynchronize(h->st));
+    float ms = 0;
+    SCLMD_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    *avg_ms = ms / reps;
+    return SCLMD_OK;
+}
+
+int sclmd_md_time_potforce(sclmd_md *h, int reps, float *avg_ms) {
+    SCLMD_REQUIRE(h && reps > 0 && avg_ms, "sclmd_md_time_potforce: bad arguments");
+    SCLMD_CUDA(cudaSetDevice(h->device));
+    if (int e = h->potforce(h->q.p, h->Gn.p)) return e;
+    SCLMD_CUDA(cudaEventRecord(h->ev0, h->st));
+    for (int r = 0; r < reps; ++r)
+        if (int e = h->potforce(h->q.p, h->Gn.p)) return e;
+    SCLMD_CUDA(cudaEventRecord(h->ev1, h->st));
+    SCLMD_CUDA(cudaStreamSynchronize(h->st));
+    float ms = 0;
+    SCLMD_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    *avg_ms = ms / reps;
+    return SCLMD_OK;
+}
+
+}  // extern "C"

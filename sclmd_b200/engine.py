@@ -1,0 +1,138 @@
+"""Thin object wrapper over the sclmd_md_* C ABI (include/sclmd_b200.h).
+
+`MDEngine` is what sclmd_b200.md.md drives; tests and bench.py use it directly
+when they need raw access (host buffers in, host buffers out)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import as_f64, as_i32, check, dptr, iptr
+
+KERNEL_FULL, KERNEL_DIAG = 0, 1
+
+
+class MDEngine:
+    def __init__(self, nph, ntraj, dt, nmd, device=0):
+        self.nph, self.ntraj, self.dt, self.nmd, self.device = int(nph), int(ntraj), float(dt), int(nmd), int(device)
+        self._h = C.c_void_p()
+        self._baths = []  # (nc, ml)
+        check(_lib.lib().sclmd_md_create(self.nph, self.ntraj, self.dt, self.nmd, self.device, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            _lib.lib().sclmd_md_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- problem definition
+    def set_dyn(self, K):
+        K = as_f64(K, (self.nph, self.nph))
+        check(_lib.lib().sclmd_md_set_dyn(self._h, dptr(K)))
+
+    def set_constraint(self, idx):
+        idx = as_i32(idx)
+        check(_lib.lib().sclmd_md_set_constraint(self._h, iptr(idx), len(idx)))
+
+    def add_bath(self, cids, kernel, Mq=None, Mp=None):
+        """kernel: [ml,nc,nc] (full) or [ml,nc] (diagonal)."""
+        cids = as_i32(cids)
+        nc = len(cids)
+        kernel = as_f64(kernel)
+        if kernel.ndim == 3 and kernel.shape[1:] == (nc, nc):
+            kind = KERNEL_FULL
+        elif kernel.ndim == 2 and kernel.shape[1] == nc:
+            kind = KERNEL_DIAG
+        else:
+            raise ValueError("kernel must be [ml,%d,%d] or [ml,%d], got %s" % (nc, nc, nc, kernel.shape))
+        ml = kernel.shape[0]
+        Mq = None if Mq is None else as_f64(Mq, (nc, nc))
+        Mp = None if Mp is None else as_f64(Mp, (nc, nc))
+        out = C.c_int32(-1)
+        check(_lib.lib().sclmd_md_add_bath(self._h, iptr(cids), nc, ml, dptr(kernel), kind, dptr(Mq), dptr(Mp), C.byref(out)))
+        self._baths.append((nc, ml))
+        return out.value
+
+    # ---- data movement
+    def set_noise(self, bath, noise, traj0=0):
+        nc, _ = self._baths[bath]
+        noise = as_f64(noise)
+        if noise.ndim == 2:
+            noise = noise[None]
+        if noise.shape[1:] != (self.nmd, nc):
+            raise ValueError("noise must be [ntraj,%d,%d], got %s" % (self.nmd, nc, noise.shape))
+        noise = np.ascontiguousarray(noise)
+        check(_lib.lib().sclmd_md_set_noise(self._h, bath, traj0, noise.shape[0], dptr(noise)))
+
+    def get_noise(self, bath, traj0=0, ntraj=None):
+        nc, _ = self._baths[bath]
+        n = self.ntraj - traj0 if ntraj is None else ntraj
+        out = np.empty((n, self.nmd, nc))
+        check(_lib.lib().sclmd_md_get_noise(self._h, bath, traj0, n, dptr(out)))
+        return out
+
+    def set_state(self, q=None, p=None, t=-1):
+        q = None if q is None else as_f64(np.broadcast_to(q, (self.ntraj, self.nph)))
+        p = None if p is None else as_f64(np.broadcast_to(p, (self.ntraj, self.nph)))
+        check(_lib.lib().sclmd_md_set_state(self._h, dptr(q), dptr(p), int(t)))
+
+    def get_state(self):
+        q = np.empty((self.ntraj, self.nph))
+        p = np.empty((self.ntraj, self.nph))
+        t = C.c_int64(0)
+        check(_lib.lib().sclmd_md_get_state(self._h, dptr(q), dptr(p), C.byref(t)))
+        return q, p, t.value
+
+    def reset_history(self):
+        check(_lib.lib().sclmd_md_reset_history(self._h))
+
+    def get_history(self, bath):
+        nc, ml = self._baths[bath]
+        out = np.empty((self.ntraj, ml, nc))
+        check(_lib.lib().sclmd_md_get_history(self._h, bath, dptr(out)))
+        return out
+
+    def set_history(self, bath, phis):
+        nc, ml = self._baths[bath]
+        phis = as_f64(phis, (self.ntraj, ml, nc))
+        check(_lib.lib().sclmd_md_set_history(self._h, bath, dptr(phis)))
+
+    # ---- stepping / observables
+    def run(self, nsteps):
+        """advance every trajectory by nsteps; returns device milliseconds (CUDA events)."""
+        ms = C.c_float(0)
+        check(_lib.lib().sclmd_md_run(self._h, int(nsteps), C.byref(ms)))
+        return ms.value
+
+    def current(self, bath):
+        out = np.empty((self.ntraj, self.nmd))
+        check(_lib.lib().sclmd_md_get_current(self._h, bath, dptr(out)))
+        return out
+
+    def etot(self):
+        out = np.empty((self.ntraj, self.nmd))
+        check(_lib.lib().sclmd_md_get_etot(self._h, dptr(out)))
+        return out
+
+    def current_sums(self, bath):
+        out = np.empty(self.ntraj)
+        check(_lib.lib().sclmd_md_get_current_sums(self._h, bath, dptr(out)))
+        return out
+
+    def launch_count(self):
+        return int(_lib.lib().sclmd_md_launch_count(self._h))
+
+    def time_tail(self, bath, reps=5):
+        ms = C.c_float(0)
+        check(_lib.lib().sclmd_md_time_tail(self._h, bath, reps, C.byref(ms)))
+        return ms.value
+
+    def time_potforce(self, reps=5):
+        ms = C.c_float(0)
+        check(_lib.lib().sclmd_md_time_potforce(self._h, reps, C.byref(ms)))
+        return ms.value

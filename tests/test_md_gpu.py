@@ -1,0 +1,162 @@
+"""Parity of the CUDA ensemble integrator (through the C ABI) against the reference's
+golden trajectories and the CPU oracle.  Tolerance (north_star): <= 1e-10 relative per
+step on q,p given identical injected noise; <= 1e-8 on ensemble observables."""
+import os
+
+import numpy as np
+import pytest
+
+import problems as P
+from oracle import sclmd_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL_STEP = 1e-10
+TOL_OBS = 1e-8
+
+
+def relerr(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def bath_args(c, b):
+    """(kernel, Mq, Mp) exactly as sclmd_b200.baths hands them to the engine."""
+    if c["kinds"][b] == "ph":
+        return c["kern"][b], None, None
+    e = c["e"]
+    sym = lambda a: None if a is None else 0.5 * (a + a.T)
+    asym = lambda a: None if a is None else 0.5 * (a - a.T)
+    nc = len(c["cids"][b])
+    z = np.zeros((nc, nc))
+    exim = z if e["exim"][b] is None else asym(e["exim"][b])
+    zeta1 = z if e["zeta1"][b] is None else sym(e["zeta1"][b])
+    zeta2 = z if e["zeta2"][b] is None else asym(e["zeta2"][b])
+    kern = np.array([sym(e["efric"][b])])
+    if exim.any() and zeta1.any() and zeta2.any():        # baths.py:233
+        return kern, e["bias"][b] * (exim - zeta1), -e["bias"][b] * zeta2
+    return kern, None, None
+
+
+@pytest.mark.parametrize("name", list(P.MD_CASES))
+def test_golden_trajectories(name, golden_dir):
+    from sclmd_b200.engine import MDEngine
+    c = P.MD_CASES[name]()
+    g = np.load(os.path.join(golden_dir, "md_%s.npz" % name))
+    K = P.psd_project(c["K"])
+    ntraj = 3
+    eng = MDEngine(K.shape[0], ntraj, c["dt"], c["nmd"])
+    eng.set_dyn(K)
+    if c["cons"] is not None:
+        eng.set_constraint([i for grp in c["cons"] for i in grp])
+    for b in range(len(c["cids"])):
+        kern, Mq, Mp = bath_args(c, b)
+        eng.add_bath(c["cids"][b], kern, Mq, Mp)
+        eng.set_noise(b, np.stack([0.5 * c["noise"][b], c["noise"][b], -c["noise"][b]]))
+    eng.set_state(g["q0"], g["p0"], 0)
+    n = int(g["nsteps"])
+    full = g["q"].shape[0] == n
+    for s in range(n):
+        eng.run(1)
+        if full or s == n - 1:
+            q, p, t = eng.get_state()
+            k = s if full else 0
+            assert t == s + 1
+            assert relerr(q[1], g["q"][k]) < TOL_STEP, (name, s)
+            assert relerr(p[1], g["p"][k]) < TOL_STEP, (name, s)
+    for b in range(len(c["cids"])):
+        assert relerr(eng.current(b)[1], g["cur"][b]) < TOL_OBS
+        assert relerr(eng.current_sums(b)[1], g["cur"][b].sum()) < TOL_OBS
+    assert relerr(eng.etot()[1], g["etot"]) < TOL_STEP
+    eng.close()
+
+
+@pytest.mark.parametrize("kind,ml,nc,ntraj,nsteps", [
+    ("diag", 300, 30, 7, 330),      # ring wraps, T=4 tiles with a remainder, several splits
+    ("diag", 2, 6, 1, 9),           # shortest memory, single trajectory
+    ("diag", 1500, 150, 9, 40),     # C1-sized bath, long memory
+    ("full", 40, 30, 5, 90),        # split-K full-kernel tail
+    ("full", 2, 7, 2, 11),          # odd nc -> padded rows
+])
+def test_memory_kernels_vs_oracle(kind, ml, nc, ntraj, nsteps):
+    from sclmd_b200.engine import MDEngine
+    natoms = max(12, (2 * nc + 8) // 3 + 2)
+    nph = 3 * natoms
+    dt, nmd = 0.25 / 0.658, 64
+    K = P.psd_project(P.spring_chain_dyn(natoms, seed=5))
+    cons = [list(range(0, 3)), list(range(nph - 3, nph))]
+    cids = [list(range(3, 3 + nc)), list(range(nph - 3 - nc, nph - 3))]
+    eng = MDEngine(nph, ntraj, dt, nmd)
+    ens = O.EnsembleMD(K, dt, nmd, ntraj, cons)
+    eng.set_dyn(K)
+    eng.set_constraint([i for grp in cons for i in grp])
+    for b in range(2):
+        kern = P.diag_kernel(ml, nc, dt, 50 + b) if kind == "diag" else P.full_kernel(ml, nc, dt, 50 + b)
+        nz = P.injected_noise(ntraj, nmd, nc, seed=60 + b)
+        eng.add_bath(cids[b], kern)
+        eng.set_noise(b, nz)
+        ens.add_bath(cids[b], kern, nz)
+    rng = np.random.default_rng(7)
+    q0, p0 = 0.05 * rng.standard_normal((ntraj, nph)), 0.02 * rng.standard_normal((ntraj, nph))
+    eng.set_state(q0, p0, 0)
+    ens.q[:], ens.p[:] = q0, p0
+    done = 0
+    for chunk in (1, 2, nsteps - 3):
+        eng.run(chunk)
+        ens.run(chunk)
+        done += chunk
+        q, p, t = eng.get_state()
+        assert t == done
+        assert relerr(q, ens.q) < TOL_STEP and relerr(p, ens.p) < TOL_STEP, (kind, ml, done)
+    for b in range(2):
+        assert relerr(eng.current(b), ens.baths[b]["cur"]) < TOL_OBS
+        # history read-back in the reference's order (row 0 newest): bit-exact indexing
+        h = eng.get_history(b)
+        want = np.stack([ens.baths[b]["ring"][:, (done - 1 - i) % ml, :] for i in range(ml)], axis=1)
+        assert relerr(h, want) < TOL_STEP
+    assert relerr(eng.etot(), ens.etot) < TOL_STEP
+    eng.close()
+
+
+def test_history_roundtrip_and_restart():
+    """state + history saved from one engine and loaded into another continue identically
+    (md.py:552-562 restart semantics)."""
+    from sclmd_b200.engine import MDEngine
+    nph, nc, ml, ntraj, dt, nmd = 36, 9, 17, 4, 0.3, 32
+    K = P.psd_project(P.spring_chain_dyn(12, seed=3))
+    kern = P.diag_kernel(ml, nc, dt, 1)
+    nz = P.injected_noise(ntraj, nmd, nc, seed=2)
+
+    def mk():
+        e = MDEngine(nph, ntraj, dt, nmd)
+        e.set_dyn(K)
+        e.add_bath(list(range(nc)), kern)
+        e.set_noise(0, nz)
+        return e
+    a = mk()
+    a.set_state(np.full((ntraj, nph), 0.01), np.zeros((ntraj, nph)), 0)
+    a.run(25)
+    q, p, t = a.get_state()
+    b = mk()
+    b.set_state(q, p, t)
+    b.set_history(0, a.get_history(0))
+    a.run(20)
+    b.run(20)
+    qa, pa, _ = a.get_state()
+    qb, pb, _ = b.get_state()
+    assert relerr(qb, qa) < 1e-13 and relerr(pb, pa) < 1e-13
+    a.close()
+    b.close()
+
+
+def test_errors_are_reported_not_fatal():
+    from sclmd_b200.engine import MDEngine
+    from sclmd_b200._lib import SclmdError
+    e = MDEngine(12, 2, 0.3, 8)
+    with pytest.raises(SclmdError):
+        e.run(1)                                   # no dynamical matrix: "no driver, no md"
+    with pytest.raises(SclmdError):
+        e.add_bath([0, 1, 99], np.zeros((1, 3)))   # dof out of range
+    with pytest.raises(SclmdError):
+        e.add_bath([0, 0], np.zeros((1, 2)))       # duplicate dof
+    e.close()
