@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py -- QTB-MD trajectory-steps/s (and NEGF w-points/s) on N B200s of one node.
+
+Workload (BASELINE.json configs[4] per-GPU share, weak scaling): synthetic 3000-dof harmonic
+junction, two phonon baths of 300 dofs with 4096-step diagonal memory kernels, nmd=8192,
+1024 independent noise realisations per GPU.  One "step" = one velocity-Verlet step of every
+trajectory on the GPU (md.vv, sclmd/md.py:367-411).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...            # the reference algorithm on host cores
+
+Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import problems as P  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c5_diag", choices=["c5_diag", "c5_full", "c2"])
+    ap.add_argument("--ntraj-per-gpu", type=int, default=None)
+    ap.add_argument("--cpu-steps", type=int, default=4, help="steps of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the secondary workloads (C2 MD, NEGF)")
+    return ap.parse_args()
+
+
+WORKLOADS = {
+    # name: natoms, nc per bath, ml, nmd, dt, default ntraj/GPU, kernel kind, constraints
+    "c5_diag": dict(natoms=1000, nc=300, ml=4096, nmd=8192, dt=0.25 / 0.658, ntraj=1024, kind="diag", fixed=0),
+    "c5_full": dict(natoms=1000, nc=300, ml=4096, nmd=8192, dt=0.25 / 0.658, ntraj=256, kind="full", fixed=0),
+    "c2": dict(natoms=201, nc=150, ml=1, nmd=4096, dt=0.25 / 0.658, ntraj=1024, kind="diag", fixed=60),
+}
+
+
+def build_problem(w):
+    """K (PSD-projected as md.setDyn does), bath dof lists, kernels."""
+    nph = 3 * w["natoms"]
+    K = P.psd_project(P.spring_chain_dyn(w["natoms"], seed=5))
+    f = w["fixed"]
+    cids = [list(range(f, f + w["nc"])), list(range(nph - f - w["nc"], nph - f))]
+    cons = list(range(0, f)) + list(range(nph - f, nph)) if f else []
+    if w["ml"] == 1:
+        damp = 100 / 0.658211814201041                       # examples/runmd.py:44-47: efric = I/damp
+        kern = [np.full((1, w["nc"]), 1.0 / damp) for _ in range(2)]
+    elif w["kind"] == "diag":
+        kern = [P.diag_kernel(w["ml"], w["nc"], w["dt"], seed=50 + b) for b in range(2)]
+    else:
+        kern = [P.full_kernel(w["ml"], w["nc"], w["dt"], seed=50 + b) for b in range(2)]
+    return nph, K, cids, cons, kern
+
+
+def algorithmic_bytes_per_traj_step(w):
+    """history tail + ring write + noise row + q,p read/write + cur."""
+    nph = 3 * w["natoms"]
+    b = 0
+    for _ in range(2):
+        b += 8 * w["nc"] * (w["ml"] - 1) + 8 * w["nc"] + 8 * w["nc"]
+    return b + 32 * nph + 8 * 2
+
+
+class ClockSampler(threading.Thread):
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = []
+        reasons = set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                out["sm_max_mhz"] = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if sm:
+            hot = sorted(sm)[len(sm) // 2:]           # samples under load dominate the upper half
+            out["sm_mhz"] = float(np.median(hot))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def pinned(shape):
+    import torch
+    return torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy()
+
+
+def host_cores():
+    info = {"cpu_count": os.cpu_count()}
+    try:
+        from threadpoolctl import threadpool_info
+        blas = [t for t in threadpool_info() if t.get("user_api") == "blas"]
+        if blas:
+            info["blas_threads"] = blas[0].get("num_threads")
+            info["blas"] = "%s %s" % (blas[0].get("internal_api"), blas[0].get("version"))
+    except Exception:
+        pass
+    return info
+
+
+def reference_steps(w, nsteps, warm):
+    """The reference's algorithm (literal restatement oracle.LiteralMD: 3 force evaluations per step, physical
+    history shift, ml matvecs per evaluation; md.py:367-474) on the host cores, ONE trajectory of this workload."""
+    from oracle import sclmd_oracle as O     # bench.py may time the oracle as the CPU baseline
+    nph, K, cids, cons, kern = build_problem(w)
+    rng = np.random.default_rng(7)
+    baths = []
+    for b in range(2):
+        k = kern[b]
+        if k.ndim == 2:                       # the reference only knows [ml,nc,nc] kernels
+            full = np.zeros((k.shape[0], w["nc"], w["nc"]))
+            idx = np.arange(w["nc"])
+            full[:, idx, idx] = k
+            k = full
+        baths.append(O.Bath("ph", cids[b], k, 0.01 * rng.standard_normal((w["nmd"], w["nc"])), w["dt"], w["nmd"]))
+    m = O.LiteralMD(K, w["dt"], w["nmd"], baths, [cons] if cons else None)
+    m.q, m.p = 0.05 * rng.standard_normal(nph), 0.02 * rng.standard_normal(nph)
+    for c in cons:
+        m.q[c] = m.p[c] = 0.0
+    for _ in range(warm):
+        m.vv()
+    t0 = time.perf_counter()
+    for _ in range(nsteps):
+        m.vv()
+    return (time.perf_counter() - t0) / nsteps
+
+
+def run_reference(args, w, rank):
+    if rank != 0:
+        return
+    sec = reference_steps(w, args.steps, args.warmup)
+    cores = host_cores()
+    v = 1.0 / sec
+    line = {"impl": "reference", "metric": "qtb_md_trajectory_steps_per_s", "value": v, "unit": "trajectory-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, w, 1),
+            "cpu_baseline": {"value": v, "unit": "trajectory-steps/s", "cores": cores.get("blas_threads") or cores["cpu_count"],
+                             "kind": "port", "sample": "1 trajectory x %d steps of the workload (reference algorithm, NumPy/BLAS); host %s"
+                             % (args.steps, cores)},
+            "e2e": {"value": v, "unit": "trajectory-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, w, ntraj_total):
+    return {"workload": "%s: synthetic %d-dof harmonic junction, 2 phonon baths x %d dofs, %s memory kernels ml=%d, nmd=%d, "
+                        "%d trajectories/GPU (BASELINE.json configs[4] per-GPU share)" %
+                        (args.workload, 3 * w["natoms"], w["nc"], w["kind"], w["ml"], w["nmd"], w["ntraj"]),
+            "nph": 3 * w["natoms"], "nc": w["nc"], "ml": w["ml"], "nmd": w["nmd"], "ntraj_total": ntraj_total,
+            "parallelism": "trajectory-sharded x%d, no data-path collective; one all-reduce of heat-current sums" % args.gpus,
+            "l2": "per-step working set (history rings %.1f GB/GPU) >> 126 MB L2" %
+                  (2 * w["ntraj"] * w["ml"] * w["nc"] * 8 / 1e9)}
+
+
+def make_engine(w, device, ntraj):
+    from sclmd_b200.engine import MDEngine
+    nph, K, cids, cons, kern = build_problem(w)
+    eng = MDEngine(nph, ntraj, w["dt"], w["nmd"], device=device)
+    eng.set_dyn(K)
+    if cons:
+        eng.set_constraint(cons)
+    for b in range(2):
+        eng.add_bath(cids[b], kern[b])
+    return eng, nph
+
+
+def fill_noise(eng, w, ntraj, seed):
+    """synthetic N(0, sigma^2) noise table: a pinned host block of 32 time slabs tiled over nmd."""
+    rng = np.random.default_rng(seed)
+    nblk = min(32, w["nmd"])
+    blocks = []
+    for b in range(2):
+        blk = pinned((nblk, ntraj, w["nc"]))
+        blk[...] = 0.01 * rng.standard_normal(blk.shape)
+        for s0 in range(0, w["nmd"], nblk):
+            eng.set_noise_rows(b, s0, blk[:min(nblk, w["nmd"] - s0)])
+        blocks.append(blk)
+    return blocks
+
+
+def main():
+    args = parse()
+    w = dict(WORKLOADS[args.workload])
+    if args.ntraj_per_gpu:
+        w["ntraj"] = args.ntraj_per_gpu
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, w, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from sclmd_b200 import build as _b
+    if rank == 0:
+        _b.build()
+    if world > 1:
+        dist.barrier()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ntraj = w["ntraj"]
+    eng, nph = make_engine(w, local, ntraj)
+    blocks = fill_noise(eng, w, ntraj, seed=1000 + rank)
+    rng = np.random.default_rng(2000 + rank)
+    eng.set_state(0.05 * rng.standard_normal((ntraj, nph)), 0.02 * rng.standard_normal((ntraj, nph)), 0)
+    K, W = args.steps, max(args.warmup, 3)
+
+    # ---------------- device-resident throughput (`value`)
+    eng.run(W)
+    eng.set_profiling(True)
+    l0 = eng.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    t_wall = time.perf_counter()
+    ms = eng.run(K)                                          # CUDA events on the engine's stream
+    sums = np.array([eng.current_sums(b).sum() for b in range(2)] + [float(ntraj)])
+    ar_ms = 0.0
+    if world > 1:                                            # the one collective of the path: heat-current sums
+        tsum = torch.from_numpy(sums).cuda()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.all_reduce(tsum)
+        e1.record()
+        torch.cuda.synchronize()
+        ar_ms = e0.elapsed_time(e1)
+        sums = tsum.cpu().numpy()
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall) * 1e3
+    launches = eng.launch_count() - l0
+    prof = eng.profile()
+    eng.set_profiling(False)
+    clocks = sampler.stop() if rank == 0 else None
+    tot = torch.tensor([ms + ar_ms, float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = tot.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tot.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms_total, launches_total = float(mx[0]), int(sm[1])
+    else:
+        ms_total, launches_total = float(tot[0]), int(tot[1])
+    value = ntraj * world * K / (ms_total * 1e-3)
+
+    # ---------------- end to end through the C ABI with host buffers (`e2e`)
+    obs = pinned((3, ntraj))
+    _, _, t_now = eng.get_state()
+    h2d = sum(blk[0:1].nbytes for blk in blocks)
+    d2h = obs.nbytes
+    for s in range(2):                                       # warm
+        for b in range(2):
+            eng.set_noise_rows(b, (t_now + 1) % w["nmd"], blocks[b][s % 32:s % 32 + 1])
+        eng.run(1)
+        eng.step_observables(t_now % w["nmd"], obs)
+        t_now += 1
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(K):
+        for b in range(2):                                   # this step's new input: noise row t+1 of every bath
+            eng.set_noise_rows(b, (t_now + 1) % w["nmd"], blocks[b][s % 32:s % 32 + 1])
+        eng.run(1)
+        eng.step_observables(t_now % w["nmd"], obs)          # this step's result: etot and heat currents
+        t_now += 1
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = ntraj * world * K / float(te[0])
+
+    if rank != 0:
+        eng.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel
+    peak, peak_src = peaks()
+    roof = None
+    if prof["tail_launches"]:
+        per_launch_ms = prof["tail_ms"] / prof["tail_launches"]
+        alg = 8.0 * w["nc"] * (w["ml"] - 1) * ntraj           # 8*nc*(ml-1) B per trajectory-step per bath
+        ach = alg / (per_launch_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r01_tail_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        roof = {"kernel": "k_tail_diag<4>" if w["kind"] == "diag" else "dgemm_nt_seg_kernel (full-kernel tail)",
+                "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": per_launch_ms,
+                "launches_timed": prof["tail_launches"], "share_of_step": prof["tail_ms"] / ms,
+                "potforce_share_of_step": prof["potforce_ms"] / ms,
+                "step_algorithmic_GBs": algorithmic_bytes_per_traj_step(w) * ntraj * K / (ms * 1e-3) / 1e9}
+    line = {"metric": "qtb_md_trajectory_steps_per_s", "value": value, "unit": "trajectory-steps/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, w, ntraj * world),
+            "clocks": clocks, "e2e": {"value": e2e_value, "unit": "trajectory-steps/s", "h2d_bytes_per_step": h2d,
+                                      "d2h_bytes_per_step": d2h, "api": "sclmd_md_set_noise_rows + sclmd_md_run(1) + "
+                                      "sclmd_md_get_step_observables per step, pinned host buffers"},
+            "gpu_launches": launches_total, "roofline": roof, "wall_ms_timed_region": wall_ms, "allreduce_ms": ar_ms,
+            "heat_current_mean": [float(sums[b] / sums[2] / w["nmd"]) for b in range(2)]}
+    eng.close()
+
+    # ---------------- CPU baseline (reported, not the target): rank 0, N=1 only
+    if world == 1 and not args.no_cpu_baseline:
+        sec = reference_steps(w, args.cpu_steps, 1)
+        cores = host_cores()
+        line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "trajectory-steps/s",
+                                "cores": cores.get("blas_threads") or cores["cpu_count"], "kind": "port",
+                                "sample": "1 trajectory x %d steps of the same workload, reference algorithm "
+                                          "(oracle.LiteralMD, NumPy/BLAS); host %s" % (args.cpu_steps, cores)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -74,6 +74,10 @@ int sclmd_md_add_bath(sclmd_md *h, const int32_t *cids, int nc, int ml, const do
 int sclmd_md_set_noise(sclmd_md *h, int bath, int traj0, int ntraj_sel, const double *noise);
 int sclmd_md_get_noise(sclmd_md *h, int bath, int traj0, int ntraj_sel, double *noise);
 
+/* streaming form of the same table: rows[nslab][ntraj][nc] for time slabs
+ * [slab0, slab0+nslab) mod nmd (host buffers may be pinned; one async copy per piece) */
+int sclmd_md_set_noise_rows(sclmd_md *h, int bath, int slab0, int nslab, const double *rows);
+
 /* md.p, md.q, md.t (md.py:372,411): q,p are [ntraj][nph]; NULL pointers are skipped */
 int sclmd_md_set_state(sclmd_md *h, const double *q, const double *p, int64_t t);
 int sclmd_md_get_state(sclmd_md *h, double *q, double *p, int64_t *t);
@@ -94,6 +98,16 @@ int sclmd_md_get_etot(sclmd_md *h, double *etot);
 /* per-bath sum over the nmd slots of cur for each trajectory (np.mean(cur)*nmd, md.py:663):
  * sums[ntraj] -- the payload of the multi-GPU all-reduce */
 int sclmd_md_get_current_sums(sclmd_md *h, int bath, double *sums);
+
+/* etot and every bath's cur recorded at time slab `slab` (md.py:383,397):
+ * out[1+nbaths][ntraj] = etot, cur_0, cur_1, ... */
+int sclmd_md_get_step_observables(sclmd_md *h, int slab, double *out);
+
+/* per-kernel timing with CUDA events on the handle's stream around every history-tail and
+ * potential-force launch of subsequent sclmd_md_run calls; totals since it was switched on */
+int sclmd_md_set_profiling(sclmd_md *h, int on);
+int sclmd_md_get_profile(sclmd_md *h, double *tail_ms, int64_t *tail_launches, double *potforce_ms,
+                         int64_t *potforce_launches);
 
 /* instrumentation: kernels launched by this handle so far; name/time of the dominant kernel */
 int64_t sclmd_md_launch_count(sclmd_md *h);

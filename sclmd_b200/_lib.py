@@ -38,6 +38,10 @@ _PROTOS = {
     "sclmd_md_add_bath": (C.c_int, [C.c_void_p, c_int32_p, C.c_int, C.c_int, c_double_p, C.c_int, c_double_p, c_double_p, c_int32_p]),
     "sclmd_md_set_noise": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p]),
     "sclmd_md_get_noise": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p]),
+    "sclmd_md_set_noise_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p]),
+    "sclmd_md_get_step_observables": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
+    "sclmd_md_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "sclmd_md_get_profile": (C.c_int, [C.c_void_p, c_double_p, c_int64_p, c_double_p, c_int64_p]),
     "sclmd_md_set_state": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int64]),
     "sclmd_md_get_state": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_int64_p]),
     "sclmd_md_reset_history": (C.c_int, [C.c_void_p]),

@@ -255,6 +255,42 @@ struct sclmd_md {
     bool has_cons = false;
     std::vector<std::unique_ptr<Bath>> baths;
     int64_t launches = 0;
+    // optional per-kernel timing (CUDA events on `st` around every tail / potential-force launch)
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<int> ev_kind;  // 0 = tail, 1 = potforce; events come in (start, stop) pairs
+    size_t ev_used = 0;
+    double prof_ms[2] = {0, 0};
+    long long prof_n[2] = {0, 0};
+
+    void prof_begin(int kind) {
+        if (!profiling) return;
+        if (ev_used + 2 > ev_pool.size()) {
+            for (int i = 0; i < 2; ++i) {
+                cudaEvent_t e;
+                cudaEventCreate(&e);
+                ev_pool.push_back(e);
+            }
+        }
+        ev_kind.push_back(kind);
+        cudaEventRecord(ev_pool[ev_used], st);
+    }
+    void prof_end() {
+        if (!profiling) return;
+        cudaEventRecord(ev_pool[ev_used + 1], st);
+        ev_used += 2;
+    }
+    void prof_collect() {  // call after the stream is synchronised
+        for (size_t i = 0; i + 1 < ev_used; i += 2) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, ev_pool[i], ev_pool[i + 1]) == cudaSuccess) {
+                prof_ms[ev_kind[i / 2]] += ms;
+                prof_n[ev_kind[i / 2]] += 1;
+            }
+        }
+        ev_used = 0;
+        ev_kind.clear();
+    }
 
     BathSet view() const {
         BathSet s;
@@ -282,7 +318,9 @@ struct sclmd_md {
         g.A = qsrc; g.lda = ld; g.a_seg_stride = 0; g.a_head = 0; g.a_mod = 0;
         g.B = K.p; g.ldb = ld; g.b_seg_stride = 0; g.b_seg0 = 0;
         g.C = dst; g.ldc = ld; g.c_split_stride = 0; g.alpha = 1.0;
+        prof_begin(1);
         SCLMD_CUDA(launch_dgemm(g, 1, st));
+        prof_end();
         ++launches;
         return 0;
     }
@@ -299,6 +337,7 @@ struct sclmd_md {
     }
     int tail(Bath &b, int head) {  // partial tails from the ring with p_t already pushed at slot `head`
         if (b.ml <= 1) return 0;
+        prof_begin(0);
         if (b.kind == SCLMD_KERNEL_DIAG) {
             const int cp_total = b.ncp / 2;
             const int cpt = std::min(cp_total, 256);
@@ -322,6 +361,7 @@ struct sclmd_md {
             g.C = b.tailp.p; g.ldc = b.ncp; g.c_split_stride = (long long)ntraj * b.ncp; g.alpha = dt;
             SCLMD_CUDA(launch_dgemm(g, b.nsplit, st));
         }
+        prof_end();
         ++launches;
         return 0;
     }
@@ -610,6 +650,57 @@ int sclmd_md_run(sclmd_md *h, int64_t nsteps, float *elapsed_ms) {
     SCLMD_CUDA(cudaEventRecord(h->ev1, h->st));
     SCLMD_CUDA(cudaStreamSynchronize(h->st));
     if (elapsed_ms) SCLMD_CUDA(cudaEventElapsedTime(elapsed_ms, h->ev0, h->ev1));
+    h->prof_collect();
+    return SCLMD_OK;
+}
+
+int sclmd_md_set_profiling(sclmd_md *h, int on) {
+    SCLMD_REQUIRE(h, "sclmd_md_set_profiling: NULL handle");
+    h->profiling = on != 0;
+    h->prof_ms[0] = h->prof_ms[1] = 0;
+    h->prof_n[0] = h->prof_n[1] = 0;
+    return SCLMD_OK;
+}
+
+int sclmd_md_get_profile(sclmd_md *h, double *tail_ms, int64_t *tail_launches, double *potforce_ms, int64_t *potforce_launches) {
+    SCLMD_REQUIRE(h, "sclmd_md_get_profile: NULL handle");
+    if (tail_ms) *tail_ms = h->prof_ms[0];
+    if (tail_launches) *tail_launches = h->prof_n[0];
+    if (potforce_ms) *potforce_ms = h->prof_ms[1];
+    if (potforce_launches) *potforce_launches = h->prof_n[1];
+    return SCLMD_OK;
+}
+
+// rows[nslab][ntraj][nc] (time-major, as the device table) for time slabs [slab0, slab0+nslab) mod nmd
+int sclmd_md_set_noise_rows(sclmd_md *h, int bath, int slab0, int nslab, const double *rows) {
+    if (int e = check_bath(h, bath, "sclmd_md_set_noise_rows")) return e;
+    SCLMD_REQUIRE(rows && nslab > 0 && nslab <= h->nmd && slab0 >= 0 && slab0 < h->nmd, "sclmd_md_set_noise_rows: bad slab range");
+    SCLMD_CUDA(cudaSetDevice(h->device));
+    Bath &b = *h->baths[bath];
+    const size_t rowsz = (size_t)h->ntraj;
+    int done = 0;
+    while (done < nslab) {  // at most two pieces (wrap at nmd)
+        const int s = (slab0 + done) % h->nmd;
+        const int n = std::min(nslab - done, h->nmd - s);
+        SCLMD_CUDA(cudaMemcpy2DAsync(b.noise.p + (size_t)s * rowsz * b.ncp, b.ncp * sizeof(double),
+                                     rows + (size_t)done * rowsz * b.nc, b.nc * sizeof(double), b.nc * sizeof(double),
+                                     (size_t)n * rowsz, cudaMemcpyHostToDevice, h->st));
+        done += n;
+    }
+    SCLMD_CUDA(cudaStreamSynchronize(h->st));
+    return SCLMD_OK;
+}
+
+// observables recorded at time slab `slab` (= t % nmd of that step): out[(1+nbaths)][ntraj] = etot, cur_0, cur_1, ...
+int sclmd_md_get_step_observables(sclmd_md *h, int slab, double *out) {
+    SCLMD_REQUIRE(h && out && slab >= 0 && slab < h->nmd, "sclmd_md_get_step_observables: bad arguments");
+    SCLMD_CUDA(cudaSetDevice(h->device));
+    const size_t n = (size_t)h->ntraj;
+    SCLMD_CUDA(cudaMemcpyAsync(out, h->etot.p + (size_t)slab * n, n * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    for (size_t b = 0; b < h->baths.size(); ++b)
+        SCLMD_CUDA(cudaMemcpyAsync(out + (b + 1) * n, h->baths[b]->cur.p + (size_t)slab * n, n * sizeof(double),
+                                   cudaMemcpyDeviceToHost, h->st));
+    SCLMD_CUDA(cudaStreamSynchronize(h->st));
     return SCLMD_OK;
 }
 

@@ -76,6 +76,28 @@ class MDEngine:
         check(_lib.lib().sclmd_md_get_noise(self._h, bath, traj0, n, dptr(out)))
         return out
 
+    def set_noise_rows(self, bath, slab0, rows):
+        """rows: [nslab, ntraj, nc] time-major (may live in pinned host memory)."""
+        nc, _ = self._baths[bath]
+        if rows.dtype != np.float64 or not rows.flags.c_contiguous or rows.shape[1:] != (self.ntraj, nc):
+            raise ValueError("rows must be C-contiguous float64 [nslab,%d,%d]" % (self.ntraj, nc))
+        check(_lib.lib().sclmd_md_set_noise_rows(self._h, bath, int(slab0), rows.shape[0], dptr(rows)))
+
+    def step_observables(self, slab, out=None):
+        if out is None:
+            out = np.empty((1 + len(self._baths), self.ntraj))
+        check(_lib.lib().sclmd_md_get_step_observables(self._h, int(slab), dptr(out)))
+        return out
+
+    def set_profiling(self, on=True):
+        check(_lib.lib().sclmd_md_set_profiling(self._h, 1 if on else 0))
+
+    def profile(self):
+        a, b = C.c_double(0), C.c_double(0)
+        na, nb = C.c_int64(0), C.c_int64(0)
+        check(_lib.lib().sclmd_md_get_profile(self._h, C.byref(a), C.byref(na), C.byref(b), C.byref(nb)))
+        return dict(tail_ms=a.value, tail_launches=na.value, potforce_ms=b.value, potforce_launches=nb.value)
+
     def set_state(self, q=None, p=None, t=-1):
         q = None if q is None else as_f64(np.broadcast_to(q, (self.ntraj, self.nph)))
         p = None if p is None else as_f64(np.broadcast_to(p, (self.ntraj, self.nph)))
