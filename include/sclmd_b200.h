@@ -115,6 +115,72 @@ int64_t sclmd_md_launch_count(sclmd_md *h);
 int sclmd_md_time_tail(sclmd_md *h, int bath, int reps, float *avg_ms);
 int sclmd_md_time_potforce(sclmd_md *h, int reps, float *avg_ms);
 
+/* --------------------------------------------------------------- noise ---
+ * Coloured-noise generation for an ensemble: replaces noise.phnoise / noise.enoise
+ * (sclmd/noise.py:50-100, 149-206), vargau (273-305) and myfft.iFourier1D
+ * (functions.py:36-53).
+ *
+ * A plan holds, for every frequency w_i = 2 pi i/(dt nmd), i = 0..nmd/2, the factor
+ *   L_i = V sqrt(clamp+(lambda))   of   A_i = hermitianize( sum_m (cre+i cim)[i][m] basis[idx[i][m]] )
+ * computed on the device (one-sided Jacobi).  The host supplies the scalar weights:
+ *   phnoise: basis = gamma grid, two terms from flinterp (functions.py:117-134) times
+ *            (dt nmd) equ(w) (noise.py:77-78);   enoise: basis = {efric, exip, exim} with
+ *            the weights of noise.py:174-185.  idx < 0 marks an unused term. */
+typedef struct sclmd_noise_plan sclmd_noise_plan;
+int sclmd_noise_plan_create(int device, int nmd, double dt, int nc, int nbasis, const double *basis,
+                            int nterm, const int32_t *idx, const double *cre, const double *cim,
+                            sclmd_noise_plan **out);
+int sclmd_noise_plan_destroy(sclmd_noise_plan *pl);
+int sclmd_noise_plan_dims(sclmd_noise_plan *pl, int *nmd, int *nc);
+int sclmd_noise_plan_is_complex(sclmd_noise_plan *pl);
+/* L[nmd/2+1][nc][nc] (interleaved complex if the plan is complex); set_factors injects e.g. the
+ * reference's own eigen-factors for deterministic parity runs */
+int sclmd_noise_plan_get_factors(sclmd_noise_plan *pl, double *L);
+int sclmd_noise_plan_set_factors(sclmd_noise_plan *pl, const double *L, int is_complex);
+/* x_i = L_i xi_i, mirror to negative frequencies (noise.py:87-94), series = Re FFT/(dt nmd)
+ * (functions.py:51-53, baths.py:191,408).  xi: injected standard normals [ntraj][nmd/2+1][nc], or
+ * NULL -> Philox4x32-10 + Box-Muller with counter (i, k, traj0+traj) and key seed.
+ * out: [ntraj][nmd][nc] */
+int sclmd_noise_plan_generate(sclmd_noise_plan *pl, int ntraj, const double *xi, uint64_t seed,
+                              int64_t traj0, double *out);
+/* same, straight into a device table laid out [nmd][ntraj_total][ncp_table] (used by
+ * sclmd_md_generate_noise; `table` is a DEVICE pointer) */
+int sclmd_noise_plan_generate_into(sclmd_noise_plan *pl, int ntraj, uint64_t seed, int64_t traj0,
+                                   double *table, int ntraj_total, int ncp_table, int traj_offset);
+int64_t sclmd_noise_plan_launch_count(sclmd_noise_plan *pl);
+/* bath.gnoi() for every trajectory of an MD handle, no host round trip (baths.py:176-192,397-409) */
+int sclmd_md_generate_noise(sclmd_md *h, int bath, sclmd_noise_plan *plan, uint64_t seed, int64_t traj0);
+
+/* baths.gamt, eta_ad == 0 branch (baths.py:35-42):
+ *   out[nt][m] = 2*mean_i( giT[m][i]*cos(wl_i*tl_t) )*wl[nw-1]/pi
+ * giT[m][nw] = flinterp(wl_i, gwl, gam) flattened over the nc*nc (or nc) matrix entries and
+ * transposed by the host (the interpolation indices are host-side, functions.py:117-143). */
+int sclmd_gamt(int device, int nt, int nw, int m, const double *tl, const double *wl,
+               const double *giT, double *out);
+
+/* ---------------------------------------------------------------- NEGF ---
+ * bpt.tm over a frequency list (negf.py:104-119, 206-208, 240-242) for
+ * diagonal lead self-energies Sigma = -i w/damp on the bath dofs
+ * (negf.py:153-157):  T(w) = Re Tr[G Gamma_L G^dagger Gamma_R].
+ *   K[n*n] reduced dynamical matrix (fixed dofs removed), idxL/idxR reduced indices */
+int sclmd_bpt_tm(int device, int n, const double *K, const int32_t *idxL, int nL,
+                 const int32_t *idxR, int nR, double damp, const double *omegas, int nw,
+                 double *tm_out);
+/* bpt.ps without bias (negf.py:232): -2 w^2 nB Tr Im G[sel,sel]; nb[nw] = bosedist(w,T) */
+int sclmd_bpt_ps(int device, int n, const double *K, const int32_t *idxL, int nL,
+                 const int32_t *idxR, int nR, double damp, const double *omegas, const double *nb,
+                 int nw, const int32_t *sel, int nsel, double *ps_out);
+
+/* sig.selfenergy / sig.getse (selfenergy.py:105-140, 153-166): Sancho-Rubio decimation.
+ *   K00,K11,K01,K10: [m*m]; direction 'L' or 'R'; se_out: [nw][m][m] interleaved complex;
+ *   iters_out (may be NULL): [nw] decimation iterations */
+int sclmd_sig_selfenergy(int device, int m, const double *K00, const double *K11, const double *K01,
+                         const double *K10, double eta, char direction, const double *omegas, int nw,
+                         double *se_out, int32_t *iters_out);
+/* sig.tm / sig.gettm (selfenergy.py:145-151, 168-178) */
+int sclmd_sig_tm(int device, int m, const double *K00, const double *K11, const double *K01,
+                 const double *K10, double eta, const double *omegas, int nw, double *tm_out);
+
 #ifdef __cplusplus
 }
 #endif

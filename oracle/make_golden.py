@@ -70,6 +70,9 @@ def build_reference_md(c):
         if c["q0"] is None:
             np.random.seed(c["ic_seed"])
             m.initialise()
+            np.random.seed(c["ic_seed"])
+            oq, op = O.initialise(m.hw, m.U, c["T"], c["cons"], np.random.rand)
+            assert relerr(oq, m.q) < 1e-13 and relerr(op, m.p) < 1e-13, "oracle.initialise differs from md.initialise"
         else:
             m.initialise()
             m.q, m.p = c["q0"].copy(), c["p0"].copy()

@@ -258,6 +258,24 @@ def apply_constraint(f, constr):
     return nf
 
 
+def initialise(hw, Umat, T, constraint, rand):
+    """md.py:308-326: random-phase normal-mode displacement / velocity; `rand()` stands for
+    np.random.rand().  Returns (q, p)."""
+    dis = np.zeros(len(hw))
+    vel = np.zeros(len(hw))
+    for i in range(len(hw)):
+        if hw[i] < 0.01:
+            am = 0.0
+        else:
+            am = ((bose(hw[i], T) + 0.5) * 2.0 / hw[i]) ** 0.5
+        r = rand()
+        dis = dis + Umat[:, i] * am * np.cos(2. * np.pi * r)
+        vel = vel - hw[i] * Umat[:, i] * am * np.sin(2. * np.pi * r)
+        dis = apply_constraint(dis, constraint)
+        vel = apply_constraint(vel, constraint)
+    return dis, vel
+
+
 class LiteralMD:
     """Literal single-trajectory restatement of md.vv/force/potforce (md.py:367-474),
     including the physical history shift (functions.py:146-153) and the sameq

@@ -54,6 +54,21 @@ _PROTOS = {
     "sclmd_md_launch_count": (C.c_int64, [C.c_void_p]),
     "sclmd_md_time_tail": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p]),
     "sclmd_md_time_potforce": (C.c_int, [C.c_void_p, C.c_int, c_float_p]),
+    "sclmd_noise_plan_create": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, c_double_p, C.c_int, c_int32_p, c_double_p, c_double_p, C.POINTER(C.c_void_p)]),
+    "sclmd_noise_plan_destroy": (C.c_int, [C.c_void_p]),
+    "sclmd_noise_plan_dims": (C.c_int, [C.c_void_p, c_int32_p, c_int32_p]),
+    "sclmd_noise_plan_is_complex": (C.c_int, [C.c_void_p]),
+    "sclmd_noise_plan_get_factors": (C.c_int, [C.c_void_p, c_double_p]),
+    "sclmd_noise_plan_set_factors": (C.c_int, [C.c_void_p, c_double_p, C.c_int]),
+    "sclmd_noise_plan_generate": (C.c_int, [C.c_void_p, C.c_int, c_double_p, C.c_uint64, C.c_int64, c_double_p]),
+    "sclmd_noise_plan_generate_into": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "sclmd_noise_plan_launch_count": (C.c_int64, [C.c_void_p]),
+    "sclmd_md_generate_noise": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_int64]),
+    "sclmd_gamt": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p]),
+    "sclmd_bpt_tm": (C.c_int, [C.c_int, C.c_int, c_double_p, c_int32_p, C.c_int, c_int32_p, C.c_int, C.c_double, c_double_p, C.c_int, c_double_p]),
+    "sclmd_bpt_ps": (C.c_int, [C.c_int, C.c_int, c_double_p, c_int32_p, C.c_int, c_int32_p, C.c_int, C.c_double, c_double_p, c_double_p, C.c_int, c_int32_p, C.c_int, c_double_p]),
+    "sclmd_sig_selfenergy": (C.c_int, [C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p, C.c_double, C.c_char, c_double_p, C.c_int, c_double_p, c_int32_p]),
+    "sclmd_sig_tm": (C.c_int, [C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p, C.c_double, c_double_p, C.c_int, c_double_p]),
 }
 
 _lib = None

@@ -739,6 +739,20 @@ int sclmd_md_get_current_sums(sclmd_md *h, int bath, double *sums) {
 
 int64_t sclmd_md_launch_count(sclmd_md *h) { return h ? h->launches : -1; }
 
+// bath.gnoi() for the whole ensemble (baths.py:176-192, 397-409): fills the device noise table from a
+// noise plan, trajectory k using the Philox stream of global trajectory traj0+k.  No host round trip.
+int sclmd_md_generate_noise(sclmd_md *h, int bath, sclmd_noise_plan *plan, uint64_t seed, int64_t traj0) {
+    if (int e = check_bath(h, bath, "sclmd_md_generate_noise")) return e;
+    SCLMD_REQUIRE(plan, "sclmd_md_generate_noise: NULL plan");
+    Bath &b = *h->baths[bath];
+    int pn = 0, pc = 0;
+    if (int e = sclmd_noise_plan_dims(plan, &pn, &pc)) return e;
+    SCLMD_REQUIRE(pn == h->nmd && pc == b.nc, "sclmd_md_generate_noise: plan is for nmd=%d nc=%d, bath needs nmd=%d nc=%d", pn, pc, h->nmd, b.nc);
+    SCLMD_CUDA(cudaSetDevice(h->device));
+    SCLMD_CUDA(cudaStreamSynchronize(h->st));
+    return sclmd_noise_plan_generate_into(plan, h->ntraj, seed, traj0, b.noise.p, h->ntraj, b.ncp, 0);
+}
+
 int sclmd_md_time_tail(sclmd_md *h, int bath, int reps, float *avg_ms) {
     if (int e = check_bath(h, bath, "sclmd_md_time_tail")) return e;
     SCLMD_REQUIRE(reps > 0 && avg_ms, "sclmd_md_time_tail: bad arguments");

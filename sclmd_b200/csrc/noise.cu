@@ -1,0 +1,779 @@
+// Quantum coloured-noise generation for an ensemble (replaces noise.phnoise / noise.enoise /
+// noise.vargau / myfft.iFourier1D; sclmd/noise.py:50-100,149-206,273-305, functions.py:36-53).
+//
+//   1. covariance  A_w = sum_m (cre + i cim)[w][m] * basis[idx[w][m]], hermitianised
+//      (phnoise: two neighbouring gamma-grid nodes from flinterp, functions.py:117-134;
+//       enoise : efric, exip, exim with the Bose weights of noise.py:172-185)
+//   2. factor      L_w = V sqrt(clamp+(lambda))  -- one-sided Jacobi, one CTA per frequency
+//      (same clamp as vargau: eigenvalues <= 0 contribute nothing, noise.py:299-303)
+//   3. draws       xi ~ N(0,1) from Philox4x32-10 + Box-Muller, counter = (w, k, trajectory)
+//   4. x_w = L_w xi_w  as a batched DMMA GEMM over frequencies
+//   5. mirror to negative frequencies (noise.py:87-94) and Fourier transform with in-house
+//      Stockham radix-2/3/4/5 kernels (no cuFFT); two real-output series share one complex
+//      transform.  series = Re(FFT)/(dt*nmd)  (functions.py:51-53, baths.py:191,408)
+#include <algorithm>
+#include <cmath>
+#include <memory>
+
+#include "common.cuh"
+#include "dgemm.cuh"
+
+using namespace sclmd;
+
+namespace {
+
+// ------------------------------------------------------------------ Philox4x32-10
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+__device__ __forceinline__ double philox_normal(uint64_t seed, uint32_t w, uint32_t k, uint64_t traj) {
+    uint32_t c[4] = {w, k, (uint32_t)traj, (uint32_t)(traj >> 32)};
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        philox_round(c, k0, k1);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    const uint64_t a = ((uint64_t)c[0] << 32) | c[1], b = ((uint64_t)c[2] << 32) | c[3];
+    const double u1 = ((double)(a >> 11) + 0.5) * (1.0 / 9007199254740992.0);  // (0,1)
+    const double u2 = ((double)(b >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+
+// xi[w][traj][ncp] (pads zero)
+__global__ void k_fill_xi(double *__restrict__ xi, int nw, int ntraj, int nc, int ncp, uint64_t seed, long long traj0) {
+    const size_t n = (size_t)nw * ntraj * ncp;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(e % ncp);
+        const size_t r = e / ncp;
+        const int tr = (int)(r % ntraj), w = (int)(r / ntraj);
+        xi[e] = k < nc ? philox_normal(seed, (uint32_t)w, (uint32_t)k, (uint64_t)(traj0 + tr)) : 0.0;
+    }
+}
+// injected draws: host layout [ntraj][nw][nc] -> [w][traj][ncp]
+__global__ void k_scatter_xi(const double *__restrict__ src, double *__restrict__ xi, int nw, int ntraj, int nc, int ncp) {
+    const size_t n = (size_t)nw * ntraj * ncp;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(e % ncp);
+        const size_t r = e / ncp;
+        const int tr = (int)(r % ntraj), w = (int)(r / ntraj);
+        xi[e] = k < nc ? src[((size_t)tr * nw + w) * nc + k] : 0.0;
+    }
+}
+
+// ------------------------------------------------------------------ covariance + Jacobi factor
+// G: column-major n x n (complex: interleaved), lives in shared or global memory.
+template <bool CPLX>
+__device__ void jacobi_onesided(double *G, int n, double normF2, int *flag) {
+    constexpr int E = CPLX ? 2 : 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int m = n + (n & 1);  // players (a dummy if n is odd)
+    const double floor2 = 1e-28 * normF2;
+    const double tol = 8.9e-16 * sqrt((double)n);   // rounding level of an n-term dot product
+    for (int sweep = 0; sweep < 40; ++sweep) {
+        if (threadIdx.x == 0) *flag = 0;
+        __syncthreads();
+        for (int r = 0; r < m - 1; ++r) {
+            for (int k = warp; k < m / 2; k += nwarps) {
+                int p = (r + k) % (m - 1);
+                int q = k == 0 ? m - 1 : (r - k + m - 1) % (m - 1);
+                if (p >= n || q >= n) continue;
+                if (p > q) { const int t = p; p = q; q = t; }
+                double *gp = G + (size_t)p * n * E, *gq = G + (size_t)q * n * E;
+                double a = 0, b = 0, cr = 0, ci = 0;
+                for (int i = lane; i < n; i += 32) {
+                    if (CPLX) {
+                        const double pr = gp[2 * i], pi = gp[2 * i + 1], qr = gq[2 * i], qi = gq[2 * i + 1];
+                        a += pr * pr + pi * pi;
+                        b += qr * qr + qi * qi;
+                        cr += pr * qr + pi * qi;   // conj(gp) * gq
+                        ci += pr * qi - pi * qr;
+                    } else {
+                        const double pv = gp[i], qv = gq[i];
+                        a += pv * pv; b += qv * qv; cr += pv * qv;
+                    }
+                }
+                a = warp_sum(a); b = warp_sum(b); cr = warp_sum(cr);
+                if (CPLX) ci = warp_sum(ci);
+                const double gabs = CPLX ? sqrt(cr * cr + ci * ci) : fabs(cr);
+                if (gabs <= tol * sqrt(a * b) || gabs <= floor2) continue;
+                if (lane == 0) *flag = 1;
+                const double zeta = (b - a) / (2.0 * gabs);
+                const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+                // phase: gq~ = e^{-i phi} gq with gamma = |gamma| e^{i phi}
+                const double er = CPLX ? cr / gabs : (cr >= 0 ? 1.0 : -1.0), ei = CPLX ? -ci / gabs : 0.0;
+                for (int i = lane; i < n; i += 32) {
+                    if (CPLX) {
+                        const double pr = gp[2 * i], pi = gp[2 * i + 1], qr0 = gq[2 * i], qi0 = gq[2 * i + 1];
+                        const double qr = qr0 * er - qi0 * ei, qi = qr0 * ei + qi0 * er;
+                        gp[2 * i] = c * pr - s * qr; gp[2 * i + 1] = c * pi - s * qi;
+                        gq[2 * i] = s * pr + c * qr; gq[2 * i + 1] = s * pi + c * qi;
+                    } else {
+                        const double pv = gp[i], qv = gq[i] * er;
+                        gp[i] = c * pv - s * qv;
+                        gq[i] = s * pv + c * qv;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        const int any = *flag;
+        __syncthreads();
+        if (!any) break;
+    }
+}
+
+// One CTA per matrix.  A_w assembled from the basis, copied into G (shared if it fits, else the
+// global scratch), rotated to orthogonal columns g_k = lambda_k v_k; then
+//   lambda_k = g_k^H A g_k / |g_k|^2,   L[c][k] = g_k[c]/sqrt(lambda_k) if lambda_k > 0 else 0.
+// Output L as real rows [nc][ncp] (+ an imaginary block [nc][ncp] after it when CPLX).
+template <bool CPLX>
+__global__ void __launch_bounds__(512) k_factor(const double *__restrict__ basis, int nc, int ncp, int nterm,
+                                                 const int *__restrict__ idx, const double *__restrict__ cre,
+                                                 const double *__restrict__ cim, double *__restrict__ Aglob,
+                                                 double *__restrict__ Gglob, int use_smem, double *__restrict__ L,
+                                                 double *__restrict__ evals) {
+    constexpr int E = CPLX ? 2 : 1;
+    extern __shared__ double sm[];
+    __shared__ double red[32];
+    __shared__ int flag;
+    const int w = blockIdx.x, n = nc;
+    const size_t nn = (size_t)n * n * E;
+    double *A = Aglob + (size_t)w * nn;                 // column-major copy of the hermitianised covariance
+    double *G = use_smem ? sm : Gglob + (size_t)w * nn;
+    double nf = 0.0;
+    for (size_t e = threadIdx.x; e < (size_t)n * n; e += blockDim.x) {
+        const int i = (int)(e % n), j = (int)(e / n);   // element (i,j), column-major
+        double ar = 0, ai = 0;
+        for (int m = 0; m < nterm; ++m) {
+            const int bi = idx[w * nterm + m];
+            if (bi < 0) continue;
+            const double *B = basis + (size_t)bi * n * n;
+            const double bij = B[(size_t)i * n + j], bji = B[(size_t)j * n + i];
+            const double r = cre[w * nterm + m], im = CPLX ? cim[w * nterm + m] : 0.0;
+            // 0.5*(a_ij + conj(a_ji)) with a = (r + i im) * B   (functions.py:198-200)
+            ar += 0.5 * r * (bij + bji);
+            ai += 0.5 * im * (bij - bji);
+        }
+        if (CPLX) {
+            A[2 * e] = ar; A[2 * e + 1] = ai; G[2 * e] = ar; G[2 * e + 1] = ai;
+            nf += ar * ar + ai * ai;
+        } else {
+            A[e] = ar; G[e] = ar;
+            nf += ar * ar;
+        }
+    }
+    nf = block_sum(nf, red);
+    if (threadIdx.x == 0) red[0] = nf;
+    __syncthreads();
+    nf = red[0];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    double *Lw = L + (size_t)w * n * ncp * E;
+    // attempt 0: rotate A itself (keeps tiny eigenvalues relatively accurate; exact for PSD input).
+    // If A has eigenvalue pairs +-lambda the columns of A V need not be eigenvectors: detected by the
+    // residual below, and attempt 1 repeats the rotation on the positive definite A + |A|_F I.
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if (attempt == 1) {
+            const double sigma = sqrt(nf);
+            for (size_t e = threadIdx.x; e < (size_t)n * n; e += blockDim.x) {
+                const int i = (int)(e % n), j = (int)(e / n);
+                if (CPLX) { G[2 * e] = A[2 * e] + (i == j ? sigma : 0.0); G[2 * e + 1] = A[2 * e + 1]; }
+                else G[e] = A[e] + (i == j ? sigma : 0.0);
+            }
+            __syncthreads();
+        }
+        if (nf > 0.0) jacobi_onesided<CPLX>(G, n, attempt ? 4.0 * nf * n : nf, &flag);
+        __syncthreads();
+        if (threadIdx.x == 0) flag = 0;
+        __syncthreads();
+        for (int k = warp; k < n; k += nwarps) {
+            const double *g = G + (size_t)k * n * E;
+            double num = 0, den = 0, w2 = 0;
+            for (int i = lane; i < n; i += 32) {
+                // (A g)_i = sum_j A_ij g_j ; A Hermitian, column-major: A_ij = conj(A_ji) -> read column i
+                double sr = 0, si = 0;
+                const double *acol = A + (size_t)i * n * E;
+                for (int j = 0; j < n; ++j) {
+                    if (CPLX) {
+                        const double ar = acol[2 * j], ai = -acol[2 * j + 1];
+                        sr += ar * g[2 * j] - ai * g[2 * j + 1];
+                        si += ar * g[2 * j + 1] + ai * g[2 * j];
+                    } else {
+                        sr += acol[j] * g[j];
+                    }
+                }
+                if (CPLX) {
+                    num += g[2 * i] * sr + g[2 * i + 1] * si;
+                    den += g[2 * i] * g[2 * i] + g[2 * i + 1] * g[2 * i + 1];
+                } else {
+                    num += g[i] * sr;
+                    den += g[i] * g[i];
+                }
+                w2 += sr * sr + si * si;
+            }
+            num = warp_sum(num); den = warp_sum(den); w2 = warp_sum(w2);
+            const double lam = den > 0 ? num / den : 0.0;
+            // |A v - lam v|^2 = |A g|^2/|g|^2 - lam^2 ; an eigenvector has this at rounding level
+            const double res2 = den > 0 ? w2 / den - lam * lam : 0.0;
+            if (attempt == 0 && res2 > 1e-20 * nf && lane == 0) flag = 1;
+            const double sc = (lam > 0 && den > 0) ? sqrt(lam / den) : 0.0;   // v_k sqrt(lam) = g_k/|g_k| sqrt(lam)
+            if (lane == 0 && evals) evals[(size_t)w * n + k] = lam;
+            for (int i = lane; i < n; i += 32) {
+                if (CPLX) {
+                    Lw[(size_t)i * ncp + k] = g[2 * i] * sc;
+                    Lw[(size_t)(n + i) * ncp + k] = g[2 * i + 1] * sc;
+                } else {
+                    Lw[(size_t)i * ncp + k] = g[i] * sc;
+                }
+            }
+        }
+        __syncthreads();
+        if (!flag) break;
+        __syncthreads();
+    }
+}
+
+// single-basis shortcut: A_w = c_w * B  =>  L_w = V diag(sqrt(max(c_w*lambda, 0)))
+// L0 holds g_k/sqrt(|lambda_k|)-style data?  No: we pass V (unit eigenvectors) and lambda explicitly.
+__global__ void k_scale_factor(const double *__restrict__ V, const double *__restrict__ lam, const double *__restrict__ cw,
+                               int nc, int ncp, double *__restrict__ L) {
+    const int w = blockIdx.x;
+    const double c = cw[w];
+    for (int e = threadIdx.x; e < nc * ncp; e += blockDim.x) {
+        const int k = e % ncp;
+        double v = 0.0;
+        if (k < nc) {
+            const double s = c * lam[k];
+            v = s > 0 ? V[e] * sqrt(s) : 0.0;
+        }
+        L[(size_t)w * nc * ncp + e] = v;
+    }
+}
+// V[c][k] = L1[c][k] / sqrt(lambda_k) where L1 is the factor of B itself (lambda_k > 0), for lambda_k < 0 we
+// need the eigenvector too (c_w may be negative): recover from the factor of -B.
+__global__ void k_unit_vectors(const double *__restrict__ Lpos, const double *__restrict__ Lneg, const double *__restrict__ lpos,
+                               const double *__restrict__ lneg, int nc, int ncp, double *__restrict__ V, double *__restrict__ lam) {
+    // columns of Lpos with lpos>0 are eigenvectors of B with eigenvalue lpos; columns of Lneg (factor of -B)
+    // with lneg>0 are eigenvectors of B with eigenvalue -lneg.  Pack both sets (at most nc non-null in total).
+    __shared__ int map[1024];
+    __shared__ int cnt;
+    if (threadIdx.x == 0) {
+        int c = 0;
+        for (int k = 0; k < nc && c < nc; ++k) if (lpos[k] > 0) map[c++] = k;
+        for (int k = 0; k < nc && c < nc; ++k) if (lneg[k] > 0) map[c++] = -(k + 1);
+        cnt = c;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nc * ncp; e += blockDim.x) {
+        const int i = e / ncp, k = e % ncp;
+        double v = 0.0;
+        if (k < cnt) {
+            const int src = map[k];
+            v = src >= 0 ? Lpos[(size_t)i * ncp + src] / sqrt(lpos[src]) : Lneg[(size_t)i * ncp + (-src - 1)] / sqrt(lneg[-src - 1]);
+        }
+        V[e] = v;
+    }
+    for (int k = threadIdx.x; k < nc; k += blockDim.x) {
+        double l = 0.0;
+        if (k < cnt) l = map[k] >= 0 ? lpos[map[k]] : -lneg[-map[k] - 1];
+        lam[k] = l;
+    }
+}
+
+// ------------------------------------------------------------------ FFT (Stockham autosort, radix 2/3/4/5)
+struct FftPlan {
+    int n, npass, radix[24];
+};
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+template <int R>
+__device__ __forceinline__ void dft_small(double2 (&v)[R]) {
+    if (R == 2) {
+        const double2 a = v[0], b = v[1];
+        v[0] = make_double2(a.x + b.x, a.y + b.y);
+        v[1] = make_double2(a.x - b.x, a.y - b.y);
+    } else if (R == 4) {  // forward (exp(-i...)): multiply by -i = (y, -x)
+        const double2 a = make_double2(v[0].x + v[2].x, v[0].y + v[2].y), b = make_double2(v[0].x - v[2].x, v[0].y - v[2].y);
+        const double2 c = make_double2(v[1].x + v[3].x, v[1].y + v[3].y), d = make_double2(v[1].x - v[3].x, v[1].y - v[3].y);
+        v[0] = make_double2(a.x + c.x, a.y + c.y);
+        v[2] = make_double2(a.x - c.x, a.y - c.y);
+        v[1] = make_double2(b.x + d.y, b.y - d.x);
+        v[3] = make_double2(b.x - d.y, b.y + d.x);
+    } else {
+        double2 o[R];
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+            double2 s = v[0];
+#pragma unroll
+            for (int j = 1; j < R; ++j) {
+                double sn, cs;
+                sincospi(-2.0 * ((m * j) % R) / R, &sn, &cs);
+                s.x += v[j].x * cs - v[j].y * sn;
+                s.y += v[j].x * sn + v[j].y * cs;
+            }
+            o[m] = s;
+        }
+#pragma unroll
+        for (int m = 0; m < R; ++m) v[m] = o[m];
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void stockham_pass(const double2 *__restrict__ in, double2 *__restrict__ out, int n, int ns, int batch) {
+    const int per = n / R;
+    for (int e = threadIdx.x; e < per * batch; e += blockDim.x) {
+        const int f = e / per, j = e % per;
+        const int k = j % ns;
+        const double2 *src = in + (size_t)f * n;
+        double2 *dst = out + (size_t)f * n;
+        double2 v[R];
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+            v[m] = src[j + m * per];
+            if (m > 0 && k > 0) {
+                double sn, cs;
+                sincospi(-2.0 * (double)(m * k) / (double)(ns * R), &sn, &cs);
+                v[m] = cmul(v[m], make_double2(cs, sn));
+            }
+        }
+        dft_small<R>(v);
+        const int j0 = (j - k) * R + k;
+#pragma unroll
+        for (int m = 0; m < R; ++m) dst[j0 + m * ns] = v[m];
+    }
+}
+
+// in-place over two ping-pong buffers; returns the buffer holding the result (natural order)
+__device__ double2 *fft_smem(double2 *a, double2 *b, const FftPlan &pl, int batch) {
+    int ns = 1;
+    for (int p = 0; p < pl.npass; ++p) {
+        const int R = pl.radix[p];
+        if (R == 4) stockham_pass<4>(a, b, pl.n, ns, batch);
+        else if (R == 2) stockham_pass<2>(a, b, pl.n, ns, batch);
+        else if (R == 5) stockham_pass<5>(a, b, pl.n, ns, batch);
+        else stockham_pass<3>(a, b, pl.n, ns, batch);
+        ns *= R;
+        __syncthreads();
+        double2 *t = a; a = b; b = t;
+    }
+    return a;
+}
+
+// value of the mirrored, column-packed spectrum Z[k] = Xa[k] + i Xb[k] (noise.py:87-94):
+//   X[k] = x_k (k < h),  conj(x_{N-k}) (k >= h)     with x stored as [w][traj][ncx] (re block, then im block)
+__device__ __forceinline__ double2 load_Z(const double *__restrict__ X, int k, int N, int h, size_t wstride, size_t off, int imoff,
+                                          bool has_b) {
+    const bool mir = k >= h;
+    const int w = mir ? N - k : k;
+    const double *r = X + (size_t)w * wstride + off;
+    double ar = r[0], br = has_b ? r[1] : 0.0, ai = 0.0, bi = 0.0;
+    if (imoff) {
+        ai = r[imoff];
+        bi = has_b ? r[imoff + 1] : 0.0;
+    }
+    if (mir) { ai = -ai; bi = -bi; }
+    // bins 0 and N/2 are unpaired: their imaginary parts only feed Im(series), which the
+    // reference discards (np.real, baths.py:191,408); dropping them makes both packed transforms real
+    if (w == 0 || k == h) { ai = 0.0; bi = 0.0; }
+    return make_double2(ar - bi, ai + br);   // (ar + i ai) + i (br + i bi)
+}
+
+// N fits one CTA: one (trajectory, column pair) per CTA.
+__global__ void __launch_bounds__(256) k_fft_direct(const double *__restrict__ X, FftPlan pl, int ntraj_chunk, int nc, int ncp, int ncx,
+                                                     int imoff, double scale, double *__restrict__ out, size_t out_tstride,
+                                                     size_t out_nstride) {
+    extern __shared__ double2 fs[];
+    const int N = pl.n, h = N / 2;
+    const int pair = blockIdx.x, tr = blockIdx.y;
+    const int c0 = 2 * pair;
+    const bool has_b = c0 + 1 < nc;
+    double2 *a = fs, *b = fs + N;
+    const size_t wstride = (size_t)ntraj_chunk * ncx, off = (size_t)tr * ncx + c0;
+    for (int k = threadIdx.x; k < N; k += blockDim.x) a[k] = load_Z(X, k, N, h, wstride, off, imoff, has_b);
+    __syncthreads();
+    double2 *y = fft_smem(a, b, pl, 1);
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        double *o = out + (size_t)n * out_nstride + (size_t)tr * out_tstride + c0;
+        o[0] = y[n].x * scale;
+        if (has_b) o[1] = y[n].y * scale;
+    }
+}
+
+// four-step, N = N1*N2:  step 1 = N2 transforms of length N1 over stride-N2 data (+ twiddle), tile of k2 per CTA
+__global__ void __launch_bounds__(256) k_fft_step1(const double *__restrict__ X, FftPlan p1, int N, int N2, int tile, int ntraj_chunk,
+                                                    int nc, int ncx, int imoff, double2 *__restrict__ scratch) {
+    extern __shared__ double2 fs[];
+    const int N1 = p1.n, h = N / 2;
+    const int pair = blockIdx.x, tr = blockIdx.y, k20 = blockIdx.z * tile;
+    const int nt = min(tile, N2 - k20);
+    const int c0 = 2 * pair;
+    const bool has_b = c0 + 1 < nc;
+    double2 *a = fs, *b = fs + (size_t)tile * N1;
+    const size_t wstride = (size_t)ntraj_chunk * ncx, off = (size_t)tr * ncx + c0;
+    for (int e = threadIdx.x; e < nt * N1; e += blockDim.x) {
+        const int f = e % nt, k1 = e / nt;     // consecutive threads -> consecutive k2 (adjacent frequencies)
+        a[(size_t)f * N1 + k1] = load_Z(X, k1 * N2 + k20 + f, N, h, wstride, off, imoff, has_b);
+    }
+    __syncthreads();
+    double2 *y = fft_smem(a, b, p1, nt);
+    double2 *S = scratch + ((size_t)tr * gridDim.x + pair) * N;   // [n1][k2]
+    for (int e = threadIdx.x; e < nt * N1; e += blockDim.x) {
+        const int f = e % nt, n1 = e / nt;
+        double sn, cs;
+        sincospi(-2.0 * (double)((long long)n1 * (k20 + f) % N) / (double)N, &sn, &cs);
+        S[(size_t)n1 * N2 + k20 + f] = cmul(y[(size_t)f * N1 + n1], make_double2(cs, sn));
+    }
+}
+// step 2 = N1 transforms of length N2 over contiguous rows; Y[n1 + N1*n2]
+__global__ void __launch_bounds__(256) k_fft_step2(const double2 *__restrict__ scratch, FftPlan p2, int N, int N1, int tile, int nc,
+                                                    double scale, double *__restrict__ out, size_t out_tstride, size_t out_nstride) {
+    extern __shared__ double2 fs[];
+    const int N2 = p2.n;
+    const int pair = blockIdx.x, tr = blockIdx.y, n10 = blockIdx.z * tile;
+    const int nt = min(tile, N1 - n10);
+    const int c0 = 2 * pair;
+    const bool has_b = c0 + 1 < nc;
+    double2 *a = fs, *b = fs + (size_t)tile * N2;
+    const double2 *S = scratch + ((size_t)tr * gridDim.x + pair) * N + (size_t)n10 * N2;
+    for (int e = threadIdx.x; e < nt * N2; e += blockDim.x) a[e] = S[e];
+    __syncthreads();
+    double2 *y = fft_smem(a, b, p2, nt);
+    for (int e = threadIdx.x; e < nt * N2; e += blockDim.x) {
+        const int f = e % nt, n2 = e / nt;
+        const int n = n10 + f + N1 * n2;
+        double *o = out + (size_t)n * out_nstride + (size_t)tr * out_tstride + c0;
+        const double2 v = y[(size_t)f * N2 + n2];
+        o[0] = v.x * scale;
+        if (has_b) o[1] = v.y * scale;
+    }
+}
+
+bool make_fft_plan(int n, FftPlan &pl) {
+    pl.n = n;
+    pl.npass = 0;
+    int m = n;
+    while (m % 4 == 0) { pl.radix[pl.npass++] = 4; m /= 4; }
+    while (m % 2 == 0) { pl.radix[pl.npass++] = 2; m /= 2; }
+    while (m % 5 == 0) { pl.radix[pl.npass++] = 5; m /= 5; }
+    while (m % 3 == 0) { pl.radix[pl.npass++] = 3; m /= 3; }
+    return m == 1 && pl.npass <= 24;
+}
+
+// gamt (baths.py:35-42): C[t][i] = cos(wl_i * tl_t)
+__global__ void k_cos_table(const double *__restrict__ tl, const double *__restrict__ wl, int nt, int nw, int nwp, double *__restrict__ C) {
+    const size_t n = (size_t)nt * nwp;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(e % nwp), t = (int)(e / nwp);
+        C[e] = i < nw ? cos(wl[i] * tl[t]) : 0.0;
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ plan
+struct sclmd_noise_plan {
+    int device = 0, nmd = 0, nw = 0, nc = 0, ncp = 0, cplx = 0, nsm = 148;
+    double dt = 0;
+    cudaStream_t st = nullptr;
+    DevBuf<double> L;      // [nw][nc*(1+cplx)][ncp]
+    DevBuf<double> evals;  // [nw][nc]
+    int64_t launches = 0;
+};
+
+namespace {
+
+int factor_batch(sclmd_noise_plan *pl, int nw, int nbasis, const double *basis_h, int nterm, const int *idx_h, const double *cre_h,
+                 const double *cim_h, bool cplx, double *Ldst, double *evdst) {
+    const int nc = pl->nc, ncp = pl->ncp, E = cplx ? 2 : 1;
+    DevBuf<double> basis, cre, cim, A, G;
+    DevBuf<int> idx;
+    SCLMD_CUDA(basis.alloc((size_t)nbasis * nc * nc));
+    SCLMD_CUDA(cre.alloc((size_t)nw * nterm));
+    SCLMD_CUDA(cim.alloc((size_t)nw * nterm));
+    SCLMD_CUDA(idx.alloc((size_t)nw * nterm));
+    SCLMD_CUDA(cudaMemcpy(basis.p, basis_h, basis.n * sizeof(double), cudaMemcpyHostToDevice));
+    SCLMD_CUDA(cudaMemcpy(cre.p, cre_h, cre.n * sizeof(double), cudaMemcpyHostToDevice));
+    if (cim_h) SCLMD_CUDA(cudaMemcpy(cim.p, cim_h, cim.n * sizeof(double), cudaMemcpyHostToDevice));
+    SCLMD_CUDA(cudaMemcpy(idx.p, idx_h, idx.n * sizeof(int), cudaMemcpyHostToDevice));
+    const size_t nn = (size_t)nc * nc * E;
+    const size_t smem = nn * sizeof(double);
+    const int use_smem = smem <= 200 * 1024;
+    // frequencies are processed in slabs so the scratch (A, and G when it does not fit in smem) stays bounded
+    const int slab = (int)std::max<size_t>(1, std::min<size_t>(nw, ((size_t)2 << 30) / (nn * sizeof(double) * (use_smem ? 1 : 2))));
+    SCLMD_CUDA(A.alloc(nn * slab));
+    if (!use_smem) SCLMD_CUDA(G.alloc(nn * slab));
+    auto kern = cplx ? k_factor<true> : k_factor<false>;
+    if (use_smem) SCLMD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int threads = nc >= 64 ? 512 : 128;
+    for (int w0 = 0; w0 < nw; w0 += slab) {
+        const int cnt = std::min(slab, nw - w0);
+        kern<<<cnt, threads, use_smem ? smem : 0, pl->st>>>(basis.p, nc, ncp, nterm, idx.p + (size_t)w0 * nterm, cre.p + (size_t)w0 * nterm,
+                                                         cim.p + (size_t)w0 * nterm, A.p, G.p, use_smem,
+                                                         Ldst + (size_t)w0 * nc * E * ncp, evdst ? evdst + (size_t)w0 * nc : nullptr);
+        SCLMD_CUDA(cudaGetLastError());
+        ++pl->launches;
+    }
+    SCLMD_CUDA(cudaStreamSynchronize(pl->st));
+    return 0;
+}
+
+// series for `ntraj` trajectories written to out[(n*out_nstride) + traj*out_tstride + c]
+int generate(sclmd_noise_plan *pl, int ntraj, const double *xi_host, uint64_t seed, long long traj0, double *out, size_t out_tstride,
+             size_t out_nstride, cudaStream_t st) {
+    const int nw = pl->nw, nc = pl->nc, ncp = pl->ncp, N = pl->nmd, E = pl->cplx ? 2 : 1;
+    const int ncx = ncp * E;                 // x row: real block [ncp] then imaginary block [ncp]
+    const int imoff = pl->cplx ? ncp : 0;
+    FftPlan full, p1, p2;
+    int N1 = 0, N2 = 0;
+    const size_t smem_direct = (size_t)2 * N * sizeof(double2);
+    const bool direct = make_fft_plan(N, full) && smem_direct <= 200 * 1024;
+    if (!direct) {
+        // balanced 5-smooth split N = N1*N2, both transforms small enough to tile several per CTA
+        if (!make_fft_plan(N, full)) {
+            set_error("noise: nmd=%d is not of the form 2^a 3^b 5^c (needed by the in-house FFT)", N);
+            return SCLMD_ERR_ARG;
+        }
+        int best = 1;
+        for (int d = 1; (long long)d * d <= N; ++d)
+            if (N % d == 0) best = d;
+        N1 = best; N2 = N / best;
+        if (!make_fft_plan(N1, p1) || !make_fft_plan(N2, p2) || (size_t)2 * N2 * sizeof(double2) > 200 * 1024) {
+            set_error("noise: cannot split nmd=%d for the four-step FFT", N);
+            return SCLMD_ERR_ARG;
+        }
+    }
+    const int npair = (nc + 1) / 2;
+    // trajectory chunk bounded by ~3 GB of scratch
+    const size_t per_traj = (size_t)nw * (ncp + ncx) * sizeof(double) + (direct ? 0 : (size_t)npair * N * sizeof(double2));
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>(ntraj, ((size_t)3 << 30) / per_traj));
+    DevBuf<double> xi, X, xih;
+    DevBuf<double2> scratch;
+    SCLMD_CUDA(xi.alloc((size_t)nw * chunk * ncp));
+    SCLMD_CUDA(X.alloc((size_t)nw * chunk * ncx));
+    if (!direct) SCLMD_CUDA(scratch.alloc((size_t)chunk * npair * N));
+    const double scale = 1.0 / (pl->dt * N);   // dw/2pi (functions.py:51)
+    for (int t0 = 0; t0 < ntraj; t0 += chunk) {
+        const int cnt = std::min(chunk, ntraj - t0);
+        const size_t nel = (size_t)nw * cnt * ncp;
+        const int blocks = (int)std::min<size_t>((nel + 255) / 256, (size_t)pl->nsm * 16);
+        if (xi_host) {
+            SCLMD_CUDA(xih.alloc((size_t)cnt * nw * nc));
+            SCLMD_CUDA(cudaMemcpyAsync(xih.p, xi_host + (size_t)t0 * nw * nc, (size_t)cnt * nw * nc * sizeof(double), cudaMemcpyHostToDevice, st));
+            k_scatter_xi<<<blocks, 256, 0, st>>>(xih.p, xi.p, nw, cnt, nc, ncp);
+        } else {
+            k_fill_xi<<<blocks, 256, 0, st>>>(xi.p, nw, cnt, nc, ncp, seed, traj0 + t0);
+        }
+        SCLMD_CUDA(cudaGetLastError());
+        // X[w] (cnt x ncx) = xi[w] (cnt x ncp) . L[w]^T   -- batched over w through gridDim.z
+        GemmArgs g{};
+        g.M = cnt; g.N = nc * E; g.Kseg = ncp; g.nseg = nw; g.segs_per_split = 1;
+        g.A = xi.p; g.lda = ncp; g.a_seg_stride = (long long)cnt * ncp; g.a_mod = 0;
+        g.B = pl->L.p; g.ldb = ncp; g.b_seg_stride = (long long)nc * E * ncp; g.b_seg0 = 0;
+        g.C = X.p; g.ldc = ncx; g.c_split_stride = (long long)cnt * ncx; g.alpha = 1.0;
+        for (int w0 = 0; w0 < nw; w0 += 32768) {   // gridDim.z limit
+            const int wc = std::min(32768, nw - w0);
+            g.nseg = wc;
+            g.A = xi.p + (size_t)w0 * cnt * ncp;
+            g.N = nc;
+            g.B = pl->L.p + (size_t)w0 * nc * E * ncp; g.C = X.p + (size_t)w0 * cnt * ncx;
+            SCLMD_CUDA(launch_dgemm(g, wc, st));
+            ++pl->launches;
+            if (pl->cplx) {   // imaginary rows of L -> imaginary block [ncp, ncp+nc) of x
+                g.B += (size_t)nc * ncp; g.C += ncp;
+                SCLMD_CUDA(launch_dgemm(g, wc, st));
+                ++pl->launches;
+            }
+        }
+        double *o = out + (size_t)t0 * out_tstride;
+        if (direct) {
+            SCLMD_CUDA(cudaFuncSetAttribute(k_fft_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_direct));
+            k_fft_direct<<<dim3(npair, cnt), 256, smem_direct, st>>>(X.p, full, cnt, nc, ncp, ncx, imoff, scale, o, out_tstride, out_nstride);
+            SCLMD_CUDA(cudaGetLastError());
+            pl->launches += 2;
+        } else {
+            const int tile1 = std::max(1, std::min(N2, 2048 / N1)), tile2 = std::max(1, std::min(N1, 2048 / N2));
+            const size_t sm1 = (size_t)2 * tile1 * N1 * sizeof(double2), sm2 = (size_t)2 * tile2 * N2 * sizeof(double2);
+            SCLMD_CUDA(cudaFuncSetAttribute(k_fft_step1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+            SCLMD_CUDA(cudaFuncSetAttribute(k_fft_step2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+            k_fft_step1<<<dim3(npair, cnt, cdiv(N2, tile1)), 256, sm1, st>>>(X.p, p1, N, N2, tile1, cnt, nc, ncx, imoff, scratch.p);
+            SCLMD_CUDA(cudaGetLastError());
+            k_fft_step2<<<dim3(npair, cnt, cdiv(N1, tile2)), 256, sm2, st>>>(scratch.p, p2, N, N1, tile2, nc, scale, o, out_tstride, out_nstride);
+            SCLMD_CUDA(cudaGetLastError());
+            pl->launches += 3;
+        }
+        SCLMD_CUDA(cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sclmd_noise_plan_create(int device, int nmd, double dt, int nc, int nbasis, const double *basis, int nterm, const int32_t *idx,
+                            const double *cre, const double *cim, sclmd_noise_plan **out) {
+    SCLMD_REQUIRE(out, "sclmd_noise_plan_create: out is NULL");
+    *out = nullptr;
+    SCLMD_REQUIRE(nmd > 0 && nmd % 2 == 0, "MyFFT.iFourier1D: array length error! (nmd must be even, noise.py:64,93)");
+    SCLMD_REQUIRE(nc > 0 && nc <= 1024 && dt > 0, "sclmd_noise_plan_create: bad nc/dt");
+    SCLMD_REQUIRE(nbasis > 0 && basis && nterm > 0 && nterm <= 4 && idx && cre, "sclmd_noise_plan_create: bad basis/terms");
+    if (int e = select_device(device)) return e;
+    std::unique_ptr<sclmd_noise_plan> pl(new sclmd_noise_plan());
+    pl->device = device; pl->nmd = nmd; pl->dt = dt; pl->nc = nc; pl->ncp = round_up(nc, 2); pl->nw = nmd / 2 + 1;
+    pl->nsm = sm_count(device);
+    const int nw = pl->nw;
+    bool cplx = false;
+    if (cim)
+        for (size_t i = 0; i < (size_t)nw * nterm; ++i)
+            if (cim[i] != 0.0 && idx[i] >= 0) { cplx = true; break; }
+    pl->cplx = cplx;
+    for (size_t i = 0; i < (size_t)nw * nterm; ++i)
+        SCLMD_REQUIRE(idx[i] < nbasis, "sclmd_noise_plan_create: basis index out of range");
+    SCLMD_CUDA(cudaStreamCreateWithFlags(&pl->st, cudaStreamNonBlocking));
+    const int E = cplx ? 2 : 1;
+    SCLMD_CUDA(pl->L.alloc((size_t)nw * nc * E * pl->ncp));
+    SCLMD_CUDA(pl->evals.alloc((size_t)nw * nc));
+    // single real basis matrix for every frequency: factor once, scale per frequency
+    bool single = !cplx;
+    int b0 = -1;
+    std::vector<double> cw(nw, 0.0);
+    for (int w = 0; w < nw && single; ++w)
+        for (int m = 0; m < nterm; ++m) {
+            const int bi = idx[w * nterm + m];
+            if (bi < 0 || cre[w * nterm + m] == 0.0) continue;
+            if (b0 < 0) b0 = bi;
+            if (bi != b0) { single = false; break; }
+            cw[w] += cre[w * nterm + m];
+        }
+    if (single && b0 >= 0 && nw > 2) {
+        const int one_idx[2] = {0, 0};
+        const double cpos[2] = {1.0, -1.0};
+        DevBuf<double> L2, ev2, V, lam, cwd;
+        SCLMD_CUDA(L2.alloc((size_t)2 * nc * pl->ncp)); SCLMD_CUDA(ev2.alloc((size_t)2 * nc));
+        SCLMD_CUDA(V.alloc((size_t)nc * pl->ncp)); SCLMD_CUDA(lam.alloc(nc)); SCLMD_CUDA(cwd.alloc(nw));
+        if (int e = factor_batch(pl.get(), 2, 1, basis + (size_t)b0 * nc * nc, 1, one_idx, cpos, nullptr, false, L2.p, ev2.p)) return e;
+        k_unit_vectors<<<1, 256, 0, pl->st>>>(L2.p, L2.p + (size_t)nc * pl->ncp, ev2.p, ev2.p + nc, nc, pl->ncp, V.p, lam.p);
+        SCLMD_CUDA(cudaGetLastError());
+        SCLMD_CUDA(cudaMemcpyAsync(cwd.p, cw.data(), nw * sizeof(double), cudaMemcpyHostToDevice, pl->st));
+        k_scale_factor<<<nw, 256, 0, pl->st>>>(V.p, lam.p, cwd.p, nc, pl->ncp, pl->L.p);
+        SCLMD_CUDA(cudaGetLastError());
+        SCLMD_CUDA(cudaStreamSynchronize(pl->st));
+        pl->launches += 2;
+    } else {
+        if (int e = factor_batch(pl.get(), nw, nbasis, basis, nterm, idx, cre, cim, cplx, pl->L.p, pl->evals.p)) return e;
+    }
+    *out = pl.release();
+    return SCLMD_OK;
+}
+
+int sclmd_noise_plan_destroy(sclmd_noise_plan *pl) {
+    if (!pl) return SCLMD_OK;
+    cudaSetDevice(pl->device);
+    if (pl->st) { cudaStreamSynchronize(pl->st); cudaStreamDestroy(pl->st); }
+    delete pl;
+    return SCLMD_OK;
+}
+
+int sclmd_noise_plan_is_complex(sclmd_noise_plan *pl) { return pl ? pl->cplx : SCLMD_ERR_ARG; }
+
+// L: [nw][nc][nc] real, or interleaved complex when the plan is complex
+int sclmd_noise_plan_get_factors(sclmd_noise_plan *pl, double *L) {
+    SCLMD_REQUIRE(pl && L, "sclmd_noise_plan_get_factors: NULL argument");
+    SCLMD_CUDA(cudaSetDevice(pl->device));
+    const int nc = pl->nc, ncp = pl->ncp, E = pl->cplx ? 2 : 1;
+    std::vector<double> tmp(pl->L.n);
+    SCLMD_CUDA(cudaMemcpy(tmp.data(), pl->L.p, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int w = 0; w < pl->nw; ++w)
+        for (int i = 0; i < nc; ++i)
+            for (int k = 0; k < nc; ++k) {
+                const double *b = tmp.data() + (size_t)w * nc * E * ncp;
+                if (E == 1) L[((size_t)w * nc + i) * nc + k] = b[(size_t)i * ncp + k];
+                else {
+                    L[(((size_t)w * nc + i) * nc + k) * 2] = b[(size_t)i * ncp + k];
+                    L[(((size_t)w * nc + i) * nc + k) * 2 + 1] = b[(size_t)(nc + i) * ncp + k];
+                }
+            }
+    return SCLMD_OK;
+}
+
+// inject factors (e.g. the reference's own V sqrt(lambda+)) for deterministic parity runs
+int sclmd_noise_plan_set_factors(sclmd_noise_plan *pl, const double *L, int is_complex) {
+    SCLMD_REQUIRE(pl && L, "sclmd_noise_plan_set_factors: NULL argument");
+    SCLMD_CUDA(cudaSetDevice(pl->device));
+    const int nc = pl->nc, ncp = pl->ncp, E = is_complex ? 2 : 1;
+    pl->cplx = is_complex ? 1 : 0;
+    SCLMD_CUDA(pl->L.alloc((size_t)pl->nw * nc * E * ncp));
+    std::vector<double> tmp(pl->L.n, 0.0);
+    for (int w = 0; w < pl->nw; ++w)
+        for (int i = 0; i < nc; ++i)
+            for (int k = 0; k < nc; ++k) {
+                double *b = tmp.data() + (size_t)w * nc * E * ncp;
+                if (E == 1) b[(size_t)i * ncp + k] = L[((size_t)w * nc + i) * nc + k];
+                else {
+                    b[(size_t)i * ncp + k] = L[(((size_t)w * nc + i) * nc + k) * 2];
+                    b[(size_t)(nc + i) * ncp + k] = L[(((size_t)w * nc + i) * nc + k) * 2 + 1];
+                }
+            }
+    SCLMD_CUDA(cudaMemcpy(pl->L.p, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return SCLMD_OK;
+}
+
+int sclmd_noise_plan_generate(sclmd_noise_plan *pl, int ntraj, const double *xi, uint64_t seed, int64_t traj0, double *out) {
+    SCLMD_REQUIRE(pl && out && ntraj > 0, "sclmd_noise_plan_generate: bad arguments");
+    SCLMD_CUDA(cudaSetDevice(pl->device));
+    DevBuf<double> o;   // [ntraj][nmd][nc]
+    SCLMD_CUDA(o.alloc((size_t)ntraj * pl->nmd * pl->nc));
+    if (int e = generate(pl, ntraj, xi, seed, traj0, o.p, (size_t)pl->nmd * pl->nc, (size_t)pl->nc, pl->st)) return e;
+    SCLMD_CUDA(cudaMemcpy(out, o.p, o.n * sizeof(double), cudaMemcpyDeviceToHost));
+    return SCLMD_OK;
+}
+
+int64_t sclmd_noise_plan_launch_count(sclmd_noise_plan *pl) { return pl ? pl->launches : -1; }
+
+// device-to-device variant used by md.cu: writes into a [nmd][ntraj_total][ncp] table
+int sclmd_noise_plan_generate_into(sclmd_noise_plan *pl, int ntraj, uint64_t seed, int64_t traj0, double *table, int ntraj_total,
+                                   int ncp_table, int traj_offset) {
+    SCLMD_REQUIRE(pl && table, "sclmd_noise_plan_generate_into: bad arguments");
+    SCLMD_CUDA(cudaSetDevice(pl->device));
+    return generate(pl, ntraj, nullptr, seed, traj0, table + (size_t)traj_offset * ncp_table, (size_t)ncp_table,
+                    (size_t)ntraj_total * ncp_table, pl->st);
+}
+
+int sclmd_noise_plan_dims(sclmd_noise_plan *pl, int *nmd, int *nc) {
+    SCLMD_REQUIRE(pl, "sclmd_noise_plan_dims: NULL plan");
+    if (nmd) *nmd = pl->nmd;
+    if (nc) *nc = pl->nc;
+    return SCLMD_OK;
+}
+
+int sclmd_gamt(int device, int nt, int nw, int m, const double *tl, const double *wl, const double *giT, double *out) {
+    SCLMD_REQUIRE(nt > 0 && nw > 0 && m > 0 && tl && wl && giT && out, "sclmd_gamt: bad arguments");
+    if (int e = select_device(device)) return e;
+    const int nwp = round_up(nw, 2);
+    DevBuf<double> dtl, dwl, C, B, O;
+    SCLMD_CUDA(dtl.alloc(nt)); SCLMD_CUDA(dwl.alloc(nw)); SCLMD_CUDA(C.alloc((size_t)nt * nwp));
+    const int mp = round_up(m, 2);
+    SCLMD_CUDA(B.alloc((size_t)m * nwp)); SCLMD_CUDA(O.alloc((size_t)nt * mp));
+    SCLMD_CUDA(cudaMemcpy(dtl.p, tl, nt * sizeof(double), cudaMemcpyHostToDevice));
+    SCLMD_CUDA(cudaMemcpy(dwl.p, wl, nw * sizeof(double), cudaMemcpyHostToDevice));
+    SCLMD_CUDA(cudaMemcpy2D(B.p, nwp * sizeof(double), giT, nw * sizeof(double), nw * sizeof(double), m, cudaMemcpyHostToDevice));
+    k_cos_table<<<std::min(4096, cdiv(nt * nwp, 256)), 256>>>(dtl.p, dwl.p, nt, nw, nwp, C.p);
+    SCLMD_CUDA(cudaGetLastError());
+    GemmArgs g{};
+    g.M = nt; g.N = m; g.Kseg = nwp; g.nseg = 1; g.segs_per_split = 1;
+    g.A = C.p; g.lda = nwp; g.B = B.p; g.ldb = nwp; g.C = O.p; g.ldc = mp;
+    g.alpha = 2.0 / nw * wl[nw - 1] / 3.14159265358979323846;   // 2*mean(...)*wl[-1]/pi
+    SCLMD_CUDA(launch_dgemm(g, 1, 0));
+    SCLMD_CUDA(cudaDeviceSynchronize());
+    SCLMD_CUDA(cudaMemcpy2D(out, m * sizeof(double), O.p, mp * sizeof(double), m * sizeof(double), nt, cudaMemcpyDeviceToHost));
+    return SCLMD_OK;
+}
+
+}  // extern "C"

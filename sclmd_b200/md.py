@@ -1,0 +1,475 @@
+"""Generalized-Langevin molecular dynamics with the reference's class `md`
+(sclmd/md.py:17-794): same constructor, setters, `Run()`, `vv()`, output files.
+
+The time loop runs on the device for `ntraj` independent noise realisations at once
+(optional constructor argument, default 1 = the reference's behaviour); trajectories are
+reported as the reference's "runs" so `tools.calHF` / `tools.calTC` work unchanged.
+Host code here only does set-up (md.setDyn, md.initialise) and file output."""
+import os
+import sys
+import time
+
+import numpy as np
+from numpy import linalg as LA
+
+from . import units as U
+from .engine import MDEngine
+from .functions import bose, chkShape, mdot, symmetrize
+
+
+class md:
+    def __init__(self, dt, nmd, T, syslist=None, axyz=None, dyn=None, nstart=0, nstop=1, npie=1, md2ang=0.06466,
+                 ntraj=1, device=0):
+        self.nstart, self.nstop = nstart, nstop
+        self.dt, self.nmd = dt, nmd
+        self.T = T
+        self.npie = npie
+        self.ntraj, self.device = int(ntraj), int(device)
+        self.saveall = self.savep = self.saveq = self.rmnc = False
+        self.nstep = None
+        self.pforce = None
+        self.constraint = None
+        self.atomlist = None
+        self.SetXyz(axyz)
+        if syslist is not None:
+            if len(syslist) > self.nta or min(syslist) < 0 or max(syslist) > self.nta - 1:
+                print("syslist out of range")
+                sys.exit(0)
+            self.syslist = np.array(syslist, dtype='int')
+            self.na = len(syslist)
+            self.nph = 3 * len(syslist)
+        elif axyz is not None:
+            self.syslist = np.array(range(len(axyz)), dtype='int')
+            self.na = len(self.syslist)
+            self.nph = 3 * len(self.syslist)
+        else:
+            self.syslist = self.na = self.nph = None
+        self.ml = 1
+        self.cf = 0
+        self.t = 0
+        self.p = []
+        self.q = []
+        self.pinit = []
+        self.qinit = []
+        self.baths = []
+        self.fhis = []
+        self.fbaths = []
+        self.etot = np.zeros(nmd)
+        self.initranvel = True
+        self._eng = None
+        self._eng_sig = None
+        self._noise_seen = {}
+        self.setDyn(dyn)
+        self.md2ang = md2ang
+        self.mass = []
+        if self.els is not None:
+            self.get_atommass()
+            if len(self.mass) != len(self.els):
+                print("Wrong setting in els or mass")
+                sys.exit(0)
+            self.conv = self.md2ang * np.array([3 * [1.0 / np.sqrt(mass)] for mass in self.mass]).flatten()
+
+    # ------------------------------------------------------------ set-up (host, as in the reference)
+    def get_atommass(self):
+        for atomsname in self.els:
+            if atomsname in U.AtomicMassTable:
+                self.mass.append(U.AtomicMassTable[atomsname])
+
+    def info(self):
+        print("--------------------------------------------")
+        print("Basis information of the MD simulation:")
+        print("System atom number:" + str(self.na))
+        print("MD time step:" + str(self.dt))
+        print("MD number of steps:" + str(self.nmd))
+        print("MD memory kernel length:" + str(self.ml))
+        print("Number of baths attached:" + str(len(self.baths)))
+        print("Trajectories advanced together on the device:" + str(self.ntraj))
+
+    def ResetSavepq(self):
+        if self.savep and self.nmd is not None and self.nph is not None:
+            self.ps = np.zeros((self.nmd, self.nph))
+        if self.saveq and self.nmd is not None and self.nph is not None:
+            self.qs = np.zeros((self.nmd, self.nph))
+
+    def energy(self):
+        """kinetic energy (md.py:161-165)"""
+        return 0.5 * np.sum(np.asarray(self.p) ** 2, axis=-1)
+
+    def AddBath(self, bath):
+        """md.py:167-183"""
+        if self.dt != bath.dt:
+            print("md.AddBath: md time step dt not consistent")
+            sys.exit()
+        if self.nmd != bath.nmd:
+            print("md.AddBath: number of md steps nmd not consistent")
+            sys.exit()
+        self.baths.append(bath)
+        if bath.ml > self.ml:
+            self.ml = bath.ml
+        self.fbaths.append(np.zeros(self.nph))
+        bath._md = self
+        bath._index = len(self.baths) - 1
+        bath.device = self.device
+        self._eng_sig = None
+
+    def AddPowerSection(self, atomlist):
+        self.atomlist = atomlist
+        self.poweratomlist = np.empty((len(self.atomlist), self.nmd, 2))
+
+    def AddConstr(self, constr):
+        self.constraint = constr
+        self._eng_sig = None
+
+    def CalPowerSpec(self, cal=True):
+        self.savep = cal
+        self.power = np.empty((self.nmd, 2))
+
+    def CalAveStruct(self, cal=True):
+        self.saveq = cal
+
+    def SaveAll(self, save=True):
+        self.saveall = save
+
+    def Savep(self, save=True):
+        self.savep = save
+
+    def Saveq(self, save=True):
+        self.saveq = save
+
+    def SaveTraj(self, nstep=100):
+        self.nstep = nstep
+
+    def RemoveNC(self, rmnc=True):
+        self.rmnc = rmnc
+
+    def SetT(self, T):
+        self.T = T
+
+    def SetMD(self, dt, nmd):
+        self.dt, self.nmd = dt, nmd
+        self.etot = np.zeros(nmd)
+        self._eng_sig = None
+
+    def noranvel(self, rf=False):
+        self.initranvel = rf
+
+    def SetXyz(self, axyz):
+        if axyz is not None:
+            self.xyz = np.array([a[1:] for a in axyz], dtype='d').flatten()
+            self.els = [a[0] for a in axyz]
+            self.nta = len(axyz)
+        else:
+            self.xyz = self.els = self.nta = None
+
+    def SetSyslist(self, syslist):
+        self.syslist = np.array(syslist)
+        self.na = len(syslist)
+        self.nph = 3 * len(syslist)
+        if self.xyz is not None and len(self.syslist) > self.nta:
+            print("md.SetSyslist:system atom number larger than total atom number")
+            sys.exit()
+
+    def setDyn(self, dyn=None):
+        """md.py:250-292: symmetrise, clip negative eigenvalues, REBUILD dyn = U diag(av) U^T."""
+        if dyn is None:
+            self.dyn = None
+            self.hw = [1.0]
+            self.U = None
+            return
+        ndyn = np.array(dyn)
+        n = chkShape(ndyn)
+        if self.nph is not None and self.nph != n:
+            print("md.setDyn: the dimension of dynamical matrix is wrong")
+            sys.exit(0)
+        self.nph = n
+        self.dyn = symmetrize(ndyn)
+        av, au = LA.eigh(self.dyn)
+        if min(av) < 0:
+            print("md.setDyn: " + str(int(np.sum(av < 0))) + " negative frequencies removed")
+            av = np.where(av < 0, 0.0, av)
+        self.hw = np.sqrt(av)
+        self.U = np.array(au)
+        self.dyn = mdot(self.U, np.diag(np.array(av)), np.transpose(self.U))
+        self._eng_sig = None
+
+    def initialise(self):
+        """md.py:294-338: random-phase normal-mode displacements/velocities, one phase set per
+        trajectory (trajectory 0 consumes np.random exactly like the reference)."""
+        self.t = 0
+        shape = (self.nph,) if self.ntraj == 1 else (self.ntraj, self.nph)
+        if self.dyn is None or not self.initranvel:
+            if self.dyn is not None:
+                np.random.rand(len(self.hw))       # the reference draws the phases even when it discards them
+            self.p, self.q = np.zeros(shape), np.zeros(shape)
+        else:
+            av, au = np.asarray(self.hw), self.U
+            am = np.zeros(len(av))
+            ok = av >= 0.01                          # md.py:317: no motion in slow modes
+            am[ok] = np.array([((bose(a, self.T) + 0.5) * 2.0 / a) ** 0.5 for a in av[ok]])
+            r = np.random.rand(self.ntraj, len(av))
+            dis = (am * np.cos(2. * np.pi * r)) @ au.T
+            vel = -(av * am * np.sin(2. * np.pi * r)) @ au.T
+            dis, vel = ApplyConstraint(dis, self.constraint), ApplyConstraint(vel, self.constraint)
+            self.p, self.q = vel.reshape(shape), dis.reshape(shape)
+        self.pinit, self.qinit = self.p, self.q
+        self._state_dirty = True
+
+    def ResetHis(self):
+        """md.py:340-349"""
+        if self.nph is None or self.ml is None:
+            print("self.nph and self.ml are not set")
+            sys.exit()
+        self._ensure_engine()
+        self._eng.reset_history()
+
+    # ------------------------------------------------------------ device plumbing
+    def _signature(self):
+        return (self.nph, self.ntraj, self.dt, self.nmd, len(self.baths), id(self.dyn),
+                tuple(id(b.kernel) for b in self.baths), id(self.constraint))
+
+    def _ensure_engine(self):
+        if self.pforce is not None:
+            raise NotImplementedError("force drivers other than the harmonic dynamical matrix (md.AddPotential) are outside "
+                                      "the device hot path of this build (SURVEY.md section 8b)")
+        if self.dyn is None:
+            print("no driver, no md")
+            sys.exit()
+        sig = self._signature()
+        if self._eng is not None and sig == self._eng_sig:
+            return
+        if self._eng is not None:
+            self._eng.close()
+        eng = MDEngine(self.nph, self.ntraj, self.dt, self.nmd, self.device)
+        eng.set_dyn(self.dyn)
+        if self.constraint is not None:
+            eng.set_constraint(np.concatenate([np.asarray(list(c), dtype=np.int32) for c in self.constraint]))
+        for b in self.baths:
+            if b.kernel is None:
+                raise RuntimeError("bath kernel is not set: call phbath.gmem() before running (the reference's Run() "
+                                   "never does, md.py:493)")
+            mq, mp = b._engine_extra()
+            eng.add_bath(b.cids, b._engine_kernel(), mq, mp)
+        self._eng, self._eng_sig = eng, sig
+        self._noise_seen = {}
+        self._state_dirty = True
+
+    def _push(self):
+        """host attributes -> device (state if it was reassigned, injected noise if it changed)"""
+        if getattr(self, "_state_dirty", True) or getattr(self, "_last_p", None) is not self.p or getattr(self, "_last_q", None) is not self.q:
+            self._eng.set_state(np.asarray(self.q, dtype=float).reshape(self.ntraj, self.nph),
+                                np.asarray(self.p, dtype=float).reshape(self.ntraj, self.nph), int(self.t))
+            self._state_dirty = False
+        for i, b in enumerate(self.baths):
+            if b._noise is not None and self._noise_seen.get(i) != b._noise_version:
+                nz = np.asarray(b._noise, dtype=float)
+                if nz.ndim == 2:
+                    nz = np.broadcast_to(nz, (self.ntraj,) + nz.shape)
+                self._eng.set_noise(i, nz)
+                self._noise_seen[i] = b._noise_version
+
+    def _pull(self):
+        q, p, t = self._eng.get_state()
+        shape = (self.nph,) if self.ntraj == 1 else (self.ntraj, self.nph)
+        self.q, self.p, self.t = q.reshape(shape), p.reshape(shape), t
+        self._last_p, self._last_q = self.p, self.q
+
+    def _device_noise(self, bath):
+        """called by bath.gnoi(): fill the device table for every trajectory, no host round trip"""
+        self._ensure_engine()
+        bath._generate_device_noise(self._eng, bath._index, 0)
+        bath._noise_version += 1
+        self._noise_seen[bath._index] = bath._noise_version
+        if self.ntraj == 1:
+            bath._noise = self._eng.get_noise(bath._index)[0]
+        else:
+            bath._noise = None
+        return True
+
+    def get_noise(self, bath_index, traj0=0, ntraj=None):
+        """device noise table of one bath: [ntraj, nmd, nc]"""
+        self._ensure_engine()
+        return self._eng.get_noise(bath_index, traj0, ntraj)
+
+    def _collect(self):
+        """bath.cur / md.etot from the device (md.py:383,397)"""
+        et = self._eng.etot()
+        self.etot = et[0] if self.ntraj == 1 else et
+        for i, b in enumerate(self.baths):
+            c = self._eng.current(i)
+            b.cur = c[0] if self.ntraj == 1 else c
+
+    @property
+    def phis(self):
+        """md.py:346: [ml, nph] history of p (row 0 newest), rebuilt from the per-bath device rings;
+        entries outside the bath dofs are never read by any bath and are reported as 0."""
+        self._ensure_engine()
+        out = np.zeros((self.ntraj, self.ml, self.nph))
+        for i, b in enumerate(self.baths):
+            h = self._eng.get_history(i)
+            out[:, :b.ml, b.cids] = h
+        return out[0] if self.ntraj == 1 else out
+
+    # ------------------------------------------------------------ time stepping
+    def vv(self, id=0):
+        """one velocity-Verlet step of every trajectory (md.py:367-411), on the device"""
+        self._ensure_engine()
+        self._push()
+        t = int(self.t)
+        if self.savep:
+            self.ps[t % self.nmd] = np.asarray(self.p).reshape(self.ntraj, self.nph)[0]
+        if self.saveq:
+            self.qs[t % self.nmd] = np.asarray(self.q).reshape(self.ntraj, self.nph)[0]
+        self._eng.run(1)
+        self._pull()
+        self._collect()
+
+    def steps(self, n):
+        """n steps without host round trips in between (the bulk path used by Run)"""
+        self._ensure_engine()
+        self._push()
+        ms = self._eng.run(n)
+        self._pull()
+        return ms
+
+    def force(self, t, p, q, id=0):
+        raise NotImplementedError("md.force is fused into the device time step; use vv()/Run()")
+
+    def potforce(self, q):
+        raise NotImplementedError("md.potforce is fused into the device time step; use vv()/Run()")
+
+    def AddPotential(self, pint):
+        """md.py:481-485 -- accepted for API parity; external force drivers are out of scope (raises at run time)"""
+        self.pforce = pint
+
+    def Run(self):
+        """md.py:493-682: nstop-nstart runs of nmd steps in npie pieces; noise regenerated per run;
+        kappa.* files per run.  With ntraj > 1 trajectory k of run j is reported as run j*ntraj+k."""
+        self.initialise()
+        self.ResetHis()
+        self.info()
+        for j in range(self.nstart, self.nstop):
+            print("\n" + "MD run: " + str(j))
+            fn, fnm = "MD" + str(j) + ".npz", "MD" + str(j - 1) + ".npz"
+            ipie = -1
+            if os.path.isfile(fn):
+                ck = np.load(fn)
+                ipie = int(ck["ipie"])
+                if ipie + 1 == self.npie:
+                    print("finished run")
+                    self.t = int(ck["t"])
+                    continue
+                print("unfinished run: reading resume information")
+                self._restore(ck, with_noise=True)
+            else:
+                print("new run")
+                if os.path.isfile(fnm):
+                    print("reading history from previous run")
+                    self._restore(np.load(fnm), with_noise=False)
+                elif j != self.nstart and j != 0:
+                    print("no previous nc file exists")
+                    sys.exit()
+                for b in self.baths:
+                    b.gnoi()
+                self.ResetSavepq()
+            per = int(self.nmd / self.npie)
+            trajfile = open('trajectories' + "." + str(self.T) + "." + "run" + str(j) + '.ani', 'w')
+            slow = self.savep or self.saveq or self.nstep is not None
+            for i in range(ipie + 1, self.npie):
+                if slow:
+                    for _ in range(per):
+                        self.vv(j)
+                        if self.nstep is not None and ((self.t - 1) == 0 or (self.t - 1) % self.nstep == 0):
+                            self._write_frame(trajfile)
+                else:
+                    self.steps(per)
+                self._collect()
+                self.dump(i, j)
+            trajfile.close()
+            if self.savep:
+                power = np.copy(self.power)
+                self.GetPower()
+                self.power = (power * (j - self.nstart) + self.power) / float(j - self.nstart + 1)
+                with open("power." + str(self.T) + "." + "run" + str(j) + ".dat", "w") as f:
+                    for ni in range(len(self.power)):
+                        if self.power[ni, 0] < 1.5 * max(self.hw):
+                            f.write("%f     %f \n" % (self.power[ni, 0], self.power[ni, 1]))
+                        else:
+                            break
+            # heat current (md.py:658-664)
+            for ii, b in enumerate(self.baths):
+                cur = np.asarray(b.cur).reshape(self.ntraj, self.nmd)
+                for k in range(self.ntraj):
+                    run = j if self.ntraj == 1 else j * self.ntraj + k
+                    with open("kappa." + str(self.T) + "." + "bath" + str(ii) + ".run" + str(run) + ".dat", "w") as fk:
+                        fk.write("%i %f    %f \n" % (run, self.T, np.mean(cur[k]) * U.curcof))
+            if self.saveq:
+                with open("avestructure." + str(self.T) + "." + "run" + str(j) + ".dat", "w") as f:
+                    ave = self.conv * (self.qs.mean(axis=0)) + self.xyz
+                    f.write(str(len(self.els)) + '\n' + "average structure" + '\n')
+                    for ip in range(len(self.els)):
+                        f.write(str(self.els[ip]) + '    ' + str(ave[ip * 3]) + '   ' + str(ave[ip * 3 + 1]) + '   ' + str(ave[ip * 3 + 2]) + '\n')
+            if self.rmnc and os.path.exists(fnm):
+                os.remove(fnm)
+
+    def mean_currents(self):
+        """[nbaths] ensemble- and time-averaged heat current * curcof (what the kappa files hold),
+        summed on the device; the multi-GPU all-reduce payload (sum, count)."""
+        self._ensure_engine()
+        sums = np.array([self._eng.current_sums(i).sum() for i in range(len(self.baths))])
+        return sums / (self.ntraj * self.nmd) * U.curcof, sums, self.ntraj * self.nmd
+
+    def _write_frame(self, trajfile):
+        q = np.asarray(self.q).reshape(self.ntraj, self.nph)[0]
+        trajfile.write(str(len(self.els)) + '\n' + str(self.t - 1) + '\n')
+        structure = self.xyz + self.conv * q
+        for ip in range(len(self.els)):
+            trajfile.write(str(self.els[ip]) + '    ' + str(structure[ip * 3]) + '   ' + str(structure[ip * 3 + 1]) + '   ' +
+                           str(structure[ip * 3 + 2]) + '\n')
+
+    def GetPower(self):
+        """md.py:351-360 (post-processing; 'next' row of the scope table)"""
+        from .tools import powerspecp
+        self.power = powerspecp(self.ps, self.dt, self.nmd)
+        if self.atomlist is not None:
+            for layers in range(len(self.atomlist)):
+                self.poweratomlist[layers] = powerspecp(self.ps[:, self.atomlist[layers]], self.dt, self.nmd)
+
+    # ------------------------------------------------------------ checkpoint (md.py:684-745; .npz instead of NetCDF)
+    def dump(self, ipie, id):
+        out = dict(p=np.asarray(self.p), q=np.asarray(self.q), t=int(self.t), ipie=int(ipie), energy=np.asarray(self.etot))
+        for i in range(len(self.baths)):
+            out["phis%d" % i] = self._eng.get_history(i)
+            if self.saveall and self.ntraj == 1 and self.baths[i]._noise is not None:
+                out["noise%d" % i] = self.baths[i]._noise
+        if self.savep:
+            out["power"] = self.power
+            if self.saveall:
+                out["ps"] = self.ps
+        if self.saveq and self.saveall:
+            out["qs"] = self.qs
+        np.savez("MD" + str(id) + ".npz", **out)
+
+    def _restore(self, ck, with_noise):
+        self.p, self.q, self.t = ck["p"], ck["q"], int(ck["t"])
+        self._ensure_engine()
+        self._state_dirty = True
+        self._push()
+        for i, b in enumerate(self.baths):
+            key = "phis%d" % i
+            if key in ck and ck[key].shape == (self.ntraj, b.ml, b.nc):
+                self._eng.set_history(i, ck[key])
+            if with_noise:
+                if "noise%d" % i not in ck:
+                    print("saveall savep & saveq need to be set true to continue")
+                    sys.exit(0)
+                b.noise = ck["noise%d" % i]
+
+
+def ApplyConstraint(f, constr=None):
+    """md.py:782-794"""
+    if constr is None:
+        return f
+    nf = np.array(f) * 1.0
+    for c in constr:
+        nf[..., np.asarray(list(c), dtype=int)] = 0
+    return nf

@@ -1,0 +1,127 @@
+"""Ballistic phonon transport by NEGF with the reference's class `bpt` (sclmd/negf.py:8-277).
+The frequency sweeps (gettm, getps) run on the device; LAMMPS is optional: pass the dynamical
+matrix as `dynmatfile=<path or ndarray>` together with `natoms=`."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import as_f64, as_i32, check, dptr, iptr
+
+
+class bpt:
+    def __init__(self, infile, maxomega, damp, dofatomofbath, dofatomfixed=[[], []], dynmatfile=None, num=1000,
+                 natoms=None, device=0):
+        self.rpc = 6.582119569e-4     # reduced Planck constant, eV*ps
+        self.bc = 8.617333262e-5      # Boltzmann constant, eV/K
+        self.damp = damp              # ps
+        self.maxomega = maxomega / self.rpc
+        self.intnum = num
+        self.dofatomfixed = [list(dofatomfixed[0]), list(dofatomfixed[1])]
+        self.isbias = False
+        self.dofatomofbias = []
+        self.dofatomofbath = [list(dofatomofbath[0]), list(dofatomofbath[1])]
+        self.dynmatfile = dynmatfile
+        self.device = device
+        self.natoms = natoms
+        self.getdynmat(infile)
+
+    def setbias(self, bias, bdamp=None, chiplus=None, chiminus=None, dofatomofbias=[]):
+        raise NotImplementedError("bpt.setbias: the biased self-energies (negf.py:162-193) are not part of this build yet")
+
+    def getdynmat(self, infile):
+        """negf.py:39-102 without the LAMMPS dependency: the dynamical matrix comes from
+        `dynmatfile` (text file as written by LAMMPS `dynamical_matrix`, or an ndarray)."""
+        if self.dynmatfile is None:
+            raise RuntimeError("bpt: computing the dynamical matrix needs LAMMPS (negf.py:40-63), which is outside this "
+                               "build; pass dynmatfile=<file or ndarray>")
+        if isinstance(self.dynmatfile, np.ndarray):
+            dyn = np.array(self.dynmatfile, dtype=float)
+        else:
+            dat = np.loadtxt(self.dynmatfile)
+            dynlen = int(3 * np.sqrt(len(dat) / 3))
+            dyn = dat.reshape((dynlen, dynlen))
+        if self.natoms is None:
+            self.natoms = dyn.shape[0] // 3
+        if dyn.shape[0] != self.natoms * 3:
+            raise ValueError('System DOF test failed after load dynmat, check again')
+        dyn = (dyn + dyn.transpose()) / 2
+        fixed = list(self.dofatomfixed[0]) + list(self.dofatomfixed[1])
+        dyn = np.delete(np.delete(dyn, fixed, axis=0), fixed, axis=1)
+        self.dynmat = np.ascontiguousarray(dyn)
+        if self.natoms * 3 != len(self.dofatomfixed[0]) + len(self.dofatomfixed[1]) + len(self.dynmat):
+            raise ValueError('System DOF test failed, check again')
+        eigvals, self.eigvecs = np.linalg.eigh(self.dynmat)
+        self.omegas = [np.sqrt(v) * self.rpc if v > 0 else -np.sqrt(-v) * self.rpc for v in eigvals]
+
+    def _reduced(self, dofs):
+        """negf.py:195-204: bath dofs are in the unreduced 3N numbering; the leading fixed block is removed"""
+        idx = np.asarray(list(dofs), dtype=np.int64) - len(self.dofatomfixed[0])
+        if len(idx) and (idx.min() < 0 or idx.max() >= len(self.dynmat)):
+            raise ValueError('System DOF test failed, check again')
+        return as_i32(idx)
+
+    def bosedist(self, omega, T):
+        """negf.py:217-226"""
+        if abs(T) < 1e-30:
+            return 1 / (np.exp(self.rpc * omega * np.iinfo(np.int32).max) - 1)
+        elif abs(omega / T) < 1e-30:
+            return np.iinfo(np.int32).max
+        return 1 / (np.exp(self.rpc * omega / self.bc / T) - 1)
+
+    def tm_sweep(self, omegas):
+        """T(w) for an array of frequencies (ps^-1) on the device (negf.py:240-242 for each)"""
+        om = as_f64(omegas)
+        iL, iR = self._reduced(self.dofatomofbath[0]), self._reduced(self.dofatomofbath[1])
+        out = np.empty(len(om))
+        check(_lib.lib().sclmd_bpt_tm(self.device, len(self.dynmat), dptr(self.dynmat), iptr(iL), len(iL), iptr(iR), len(iR),
+                                      float(self.damp), dptr(om), len(om), dptr(out)))
+        return out
+
+    def tm(self, omega):
+        return float(self.tm_sweep(np.array([omega], dtype=float))[0])
+
+    def gettm(self, vector=False):
+        """negf.py:104-119"""
+        x = np.linspace(0, self.maxomega, self.intnum + 1)
+        self.tmnumber = np.array(np.column_stack((x, self.tm_sweep(x))))
+        np.savetxt('transmission.dat', np.column_stack((self.tmnumber[:, 0] * self.rpc, self.tmnumber[:, 1])))
+
+    def ps_sweep(self, omegas, T, atomlist):
+        om = as_f64(omegas)
+        sel = self._reduced(atomlist)
+        iL, iR = self._reduced(self.dofatomofbath[0]), self._reduced(self.dofatomofbath[1])
+        with np.errstate(all="ignore"):
+            nb = np.array([float(self.bosedist(w, T)) for w in om])
+        out = np.empty(len(om))
+        check(_lib.lib().sclmd_bpt_ps(self.device, len(self.dynmat), dptr(self.dynmat), iptr(iL), len(iL), iptr(iR), len(iR),
+                                      float(self.damp), dptr(om), dptr(nb), len(om), iptr(sel), len(sel), dptr(out)))
+        return out
+
+    def ps(self, omega, T, atomlist):
+        """negf.py:228-232 (unbiased)"""
+        return float(self.ps_sweep(np.array([omega], dtype=float), T, atomlist)[0])
+
+    def getps(self, T, maxomega, intnum, atomlist=None, filename=None, vector=False, omegalist=None):
+        """negf.py:121-150"""
+        if atomlist is None:
+            atomlist = np.array(range(0, len(self.dynmat))) + len(self.dofatomfixed[0])
+        x2 = np.sort(omegalist) / self.rpc if omegalist is not None else np.linspace(0, maxomega / self.rpc, intnum + 1)
+        self.psnumber = np.array(np.column_stack((x2, self.ps_sweep(x2, T, atomlist))))
+        name = 'powerspectrum.' + (str(filename) + '.' if filename is not None else '') + str(T) + '.dat'
+        np.savetxt(name, np.column_stack((self.psnumber[:, 0] * self.rpc, self.psnumber[:, 1])))
+
+    def thermalcurrent(self, T, delta):
+        """negf.py:245-270: trapezoid over the stored transmission, nW"""
+        n = len(self.tmnumber[:, 0]) - 1
+        if n != self.intnum:
+            raise ValueError('Error in number of omega')
+        arr = np.array([self.rpc * w / 2 / np.pi * t * (self.bosedist(w, T * (1 + 0.5 * delta)) - self.bosedist(w, T * (1 - 0.5 * delta)))
+                        for w, t in self.tmnumber])
+        return (float(self.tmnumber[-1, 0] - self.tmnumber[0, 0]) / n / 2.) * (2 * arr.sum() - arr[0] - arr[-1]) * 1.60217662 * 1e2
+
+    def thermalconductance(self, T, delta):
+        return self.thermalcurrent(T, delta) / (T * delta)
+
+    def thermalconductivity(self, T, delta, L, A):
+        return self.thermalconductance(T, delta) * L / A * 10

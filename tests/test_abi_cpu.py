@@ -55,3 +55,14 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "from oracle" not in txt and "import oracle" not in txt and "sclmd_oracle" not in txt, f
+
+
+def test_error_codes_map_to_reference_exceptions():
+    """sig.sgf raises ValueError after 100 decimation iterations (selfenergy.py:127-130):
+    SCLMD_ERR_NOCONV surfaces as a ValueError subclass; everything else as SclmdError."""
+    from sclmd_b200 import _lib
+    with pytest.raises(ValueError):
+        _lib.check(-4)
+    with pytest.raises(_lib.SclmdError):
+        _lib.check(-1)
+    assert _lib.check(0) == 0

@@ -1,0 +1,90 @@
+"""NEGF transmission / power spectrum and surface self-energy sweeps on the device vs the
+reference's golden numbers and the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+import problems as P
+from oracle import sclmd_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def relerr(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def test_bpt_golden(golden_dir, tmp_path, monkeypatch):
+    from sclmd_b200.negf import bpt
+    monkeypatch.chdir(tmp_path)
+    g = np.load(os.path.join(golden_dir, "bpt.npz"))
+    K = P.spring_chain_dyn(12, seed=80) / O.RPC ** 2
+    fixed = [list(range(0, 3)), list(range(33, 36))]
+    bath = [list(range(3, 12)), list(range(24, 33))]
+    b = bpt(None, 0.25, 0.1, bath, fixed, dynmatfile=K, num=20)
+    b.gettm()
+    assert np.array_equal(b.tmnumber[:, 0], g["tm"][:, 0])          # frequency grid bit-exact
+    assert relerr(b.tmnumber[:, 1], g["tm"][:, 1]) < 1e-8
+    assert os.path.exists("transmission.dat")
+    b.getps(300.0, 0.25, 20)
+    assert relerr(b.psnumber[1:, 1], g["ps"][1:, 1]) < 1e-8
+    kap = np.array([b.thermalconductance(T, 0.1) for T in (100.0, 300.0, 900.0)])
+    assert relerr(kap, g["kappa"]) < 1e-8
+    assert abs(b.tm(0.0)) < 1e-20                                      # Gamma ~ w -> T(0) = 0
+
+
+def test_bpt_config3_shape_vs_oracle():
+    """n = 483 (examples/runnegf.py shape): Gamma on 150 + 150 dofs, several panels, pivoting"""
+    from sclmd_b200.negf import bpt
+    natoms = 201
+    K = P.spring_chain_dyn(natoms, seed=14) / O.RPC ** 2
+    fixed = [list(range(0, 60)), list(range(543, 603))]
+    bath = [list(range(60, 210)), list(range(393, 543))]
+    b = bpt(None, 0.25, 0.1, bath, fixed, dynmatfile=K, num=1000)
+    om = np.array([0.0, 3.7, 41.3, 97.0, 150.2, 233.3, 301.9])
+    got = b.tm_sweep(om)
+    iL, iR = O.bpt_reduce_index(bath[0], 60), O.bpt_reduce_index(bath[1], 60)
+    want = np.array([O.bpt_tm(b.dynmat, w, 0.1, iL, iR) for w in om])
+    assert np.max(np.abs(got - want)) < 1e-8 * max(1.0, np.abs(want).max())
+    sel = list(range(60 + 150, 60 + 333))
+    ps = b.ps_sweep(om[1:4], 300.0, sel)
+    wantps = np.array([O.bpt_ps_nobias(b.dynmat, w, 300.0, 0.1, iL, iR, np.array(sel) - 60) for w in om[1:4]])
+    assert relerr(ps, wantps) < 1e-8
+
+
+def test_sig_golden(golden_dir, tmp_path, monkeypatch):
+    from sclmd_b200.selfenergy import sig
+    monkeypatch.chdir(tmp_path)
+    g = np.load(os.path.join(golden_dir, "sig.npz"))
+    K00, K11, K01 = P.chain_blocks(4, seed=81)
+    full = np.zeros((8, 8))
+    full[:4, :4], full[4:, 4:], full[:4, 4:], full[4:, :4] = K00, K11, K01, K01.T
+    s = sig(None, 0.06, range(0, 4), range(4, 8), dynmatfile=full, num=8, eta=2e-3)
+    assert np.array_equal(s.ep, g["ep"])
+    seL = s.getse('L')
+    assert relerr(s.dos, g["dosL"]) < 1e-9
+    seR = s.getse('R')
+    assert relerr(seL, g["seL"]) < 1e-10 and relerr(seR, g["seR"]) < 1e-10
+    s.gettm()
+    assert relerr(s.tmnumber[:, 1], g["tm"][:, 1]) < 1e-8
+    its = np.array([O.sig_sgf(K00, K11, s.K01, s.K10, w, s.eta, "R")[1] for w in s.ep])
+    assert np.array_equal(s.iterations, its)                            # same iteration counts as the reference loop
+
+
+def test_sig_24x24_vs_oracle():
+    from sclmd_b200.selfenergy import sig
+    m = 24
+    K00, K11, K01 = P.chain_blocks(m, seed=5, k2=0.08)
+    full = np.zeros((2 * m, 2 * m))
+    full[:m, :m], full[m:, m:], full[:m, m:], full[m:, :m] = K00, K11, K01, K01.T
+    s = sig(None, 0.06, range(0, m), range(m, 2 * m), dynmatfile=full, num=40, eta=1e-3)
+    om = s.ep[[0, 3, 11, 25, 40]]
+    se = s.selfenergy_sweep(om, 'R')
+    want = np.array([O.sig_selfenergy(K00, K11, s.K01, s.K10, w, s.eta, "R") for w in om])
+    assert relerr(se, want) < 1e-9
+    tm = s.tm_sweep(om)
+    wtm = np.array([O.sig_tm(K00, K11, s.K01, s.K10, w, s.eta) for w in om])
+    assert np.max(np.abs(tm - wtm)) < 1e-8 * max(1.0, np.abs(wtm).max())
+    assert np.array_equal(s.iterations, np.array([O.sig_sgf(K00, K11, s.K01, s.K10, w, s.eta, 'R')[1] for w in om]))

@@ -1,0 +1,164 @@
+"""Coloured-noise generation on the device vs the reference's golden series and the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+import problems as P
+from oracle import sclmd_oracle as O
+
+pytestmark = pytest.mark.gpu
+DT = 0.25 / 0.658
+
+
+def relerr(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def indexed_draws(av, stream):
+    """the reference consumes one normal per strictly positive eigenvalue, in order (noise.py:299-303)"""
+    xi = np.zeros(av.shape)
+    k = 0
+    for i in range(av.shape[0]):
+        for j in range(av.shape[1]):
+            if av[i, j] > 0:
+                xi[i, j] = stream[k]
+                k += 1
+    return xi, k
+
+
+def test_golden_series_with_reference_eigenvectors(golden_dir):
+    """deterministic parity: the reference's own eigen-factors + its own normal draws -> its own series"""
+    from sclmd_b200 import noise as N
+    g = np.load(os.path.join(golden_dir, "noise.npz"))
+    z = np.random.default_rng(60).standard_normal(4096)
+    nmd = 32
+    gwl, gam = P.gamma_grid(7, 4, 61, wmax=0.3)
+    plan = N.ph_plan(gam, gwl, 300.0, float(g["phcut"]), DT, nmd)
+    L = g["ph_au"] * np.sqrt(np.where(g["ph_av"] > 0, g["ph_av"], 0.0))[:, None, :]
+    plan.set_factors(L)
+    xi, used = indexed_draws(g["ph_av"], z)
+    assert used == int(g["used_ph"])
+    out = plan.generate(1, xi=xi[None])[0]
+    assert relerr(out, np.real(g["ph"])) < 1e-12
+    plan.close()
+    efric, exim, exip = P.psd(3, 62, 0.05), P.antisym(3, 63, 0.01), P.sym(3, 64, 0.01)
+    plan = N.e_plan(efric, exim, exip, 0.2, 300.0, 2.0, DT, nmd, False, False)
+    assert plan.is_complex
+    L = g["e_au"] * np.sqrt(np.where(g["e_av"] > 0, g["e_av"], 0.0))[:, None, :]
+    plan.set_factors(L)
+    xi, used = indexed_draws(g["e_av"], z[1000:])
+    assert used == int(g["used_e"])
+    out = plan.generate(1, xi=xi[None])[0]
+    assert relerr(out, np.real(g["en"])) < 1e-12
+    plan.close()
+
+
+@pytest.mark.parametrize("nc,ngw,nmd", [(4, 7, 32), (9, 5, 64), (150, 3, 8), (170, 3, 6)])
+def test_device_factor_reproduces_clamped_covariance(nc, ngw, nmd):
+    """L L^H == clamp+(A(w)) for every frequency (noise.py:82-84 + vargau clamp)"""
+    from sclmd_b200 import noise as N
+    gwl, gam = P.gamma_grid(ngw, nc, 5, wmax=0.3)
+    gam = gam - 0.004 * np.eye(nc)[None] * (np.arange(ngw) % 2)[:, None, None]      # make some nodes indefinite
+    phcut = 0.8 * np.pi / DT
+    plan = N.ph_plan(gam, gwl, 300.0, phcut, DT, nmd)
+    L = plan.factors()
+    for i in range(nmd // 2 + 1):
+        A = O.ph_covariance(i, gam, gwl, 300.0, phcut, DT, nmd)
+        ev, evec = np.linalg.eigh(A)
+        want = (evec * np.where(ev > 0, ev, 0.0)) @ evec.T
+        scale = max(np.abs(A).max(), 1e-300)
+        assert np.abs(L[i] @ L[i].T - want).max() / scale < 1e-11, i
+    plan.close()
+
+
+def test_complex_factor_and_single_basis_shortcut():
+    from sclmd_b200 import noise as N
+    nc, nmd = 12, 16
+    efric, exim, exip = P.psd(nc, 1, 0.05), P.antisym(nc, 2, 0.02), P.sym(nc, 3, 0.02)
+    plan = N.e_plan(efric, exim, exip, 0.3, 300.0, 2.0, DT, nmd, False, False)
+    L = plan.factors()
+    for i in range(nmd // 2 + 1):
+        A = O.e_covariance(i, efric, exim, exip, 0.3, 300.0, 2.0, DT, nmd, False, False)
+        ev, evec = np.linalg.eigh(A)
+        want = (evec * np.where(ev > 0, ev, 0.0)) @ evec.conj().T
+        assert np.abs(L[i] @ L[i].conj().T - want).max() / max(np.abs(A).max(), 1e-300) < 1e-11, i
+    plan.close()
+    # efric only -> one eigendecomposition scaled per frequency, including an indefinite efric
+    ef = P.sym(nc, 4, 0.05)
+    plan = N.e_plan(ef, np.zeros((nc, nc)), np.zeros((nc, nc)), 0.0, 300.0, 2.0, DT, nmd)
+    L = plan.factors()
+    for i in range(nmd // 2 + 1):
+        A = O.e_covariance(i, ef, np.zeros((nc, nc)), np.zeros((nc, nc)), 0.0, 300.0, 2.0, DT, nmd)
+        ev, evec = np.linalg.eigh(A)
+        want = (evec * np.where(ev > 0, ev, 0.0)) @ evec.T
+        assert np.abs(L[i] @ L[i].T - want).max() / max(np.abs(A).max(), 1e-300) < 1e-11, i
+    plan.close()
+
+
+@pytest.mark.parametrize("nmd,nc,cplx", [(64, 5, False), (4096, 6, False), (8192, 4, False), (2000, 3, True),
+                                         (20000, 2, False), (8192, 3, True)])
+def test_transform_pipeline_vs_oracle(nmd, nc, cplx):
+    """x = L xi, mirror, FFT/(dt nmd), real part -- against numpy with the SAME factors and draws;
+    covers the in-shared-memory transform, the four-step path, radix 5 and odd column counts"""
+    from sclmd_b200 import noise as N
+    ntraj = 3
+    if cplx:
+        plan = N.e_plan(P.psd(nc, 1, 0.05), P.antisym(nc, 2, 0.02), P.sym(nc, 3, 0.02), 0.3, 300.0, 2.0, DT, nmd, False, False)
+    else:
+        gwl, gam = P.gamma_grid(4, nc, 8, wmax=0.3)
+        plan = N.ph_plan(gam, gwl, 300.0, 2.0, DT, nmd)
+    L = plan.factors()
+    xi = np.random.default_rng(3).standard_normal((ntraj, nmd // 2 + 1, nc))
+    out = plan.generate(ntraj, xi=xi)
+    for k in range(ntraj):
+        want = O.noise_from_factors(L, xi[k], DT, nmd)
+        assert relerr(out[k], want) < 1e-11, k
+    plan.close()
+
+
+def test_philox_draws_are_standard_normal_and_reproducible():
+    from sclmd_b200 import noise as N
+    nc, nmd, ntraj = 8, 4096, 16
+    gam = np.array([np.eye(nc) * 0.01])
+    plan = N.ph_plan(gam, np.array([0.0]), 300.0, 10.0, DT, nmd, classical=True)
+    a = plan.generate(ntraj, seed=11)
+    b = plan.generate(ntraj, seed=11)
+    c = plan.generate(ntraj, seed=12)
+    d = plan.generate(4, seed=11, traj0=4)
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+    assert np.array_equal(a[4:8], d)                       # counter = global trajectory index
+    # classical white spectrum: A = dt nmd 2 kB T gamma ; series variance per sample = sum_w |x_w|^2 (2-sided)/(dt nmd)^2
+    var_expected = 2 * O.KB * 300.0 * 0.01 / DT * (2 * (nmd // 2 - 1) + 2) / nmd
+    v = a.var()
+    assert abs(v / var_expected - 1) < 0.03
+    # real spectrum -> even series, exactly as the reference produces (noise.py:82-94)
+    assert relerr(a[:, 1:, :], a[:, :0:-1, :]) < 1e-10
+    # different trajectories and dofs are uncorrelated
+    flat = a.reshape(ntraj, -1)
+    cc = np.corrcoef(flat)
+    assert np.abs(cc - np.eye(ntraj)).max() < 0.05
+    plan.close()
+
+
+def test_gamt_vs_reference_golden(golden_dir):
+    from sclmd_b200.baths import gamt
+    g = np.load(os.path.join(golden_dir, "scalars.npz"))
+    gwl, gam = P.gamma_grid(6, 3, 70, wmax=0.25)
+    wl = [0.3 * i / 40 for i in range(40)]
+    tl = [0.38 * i for i in range(9)]
+    assert relerr(gamt(tl, wl, gwl, gam, 0), g["gamt0"]) < 1e-12
+    # diagonal gamma, odd sizes
+    out = gamt(tl[:5], wl[:33], gwl, gam[:, :1, :1], 0)
+    assert relerr(out, O.gamt(tl[:5], wl[:33], gwl, gam[:, :1, :1], 0)) < 1e-12
+
+
+def test_odd_nmd_is_rejected():
+    from sclmd_b200 import noise as N
+    from sclmd_b200._lib import SclmdError
+    with pytest.raises(SclmdError):
+        N.ph_plan(np.array([np.eye(2)]), np.array([0.0]), 300.0, 1.0, DT, 33)
+    plan = N.ph_plan(np.array([np.eye(2)]), np.array([0.0]), 300.0, 1.0, DT, 2 * 7 * 11 * 13)   # not of the form 2^a 3^b 5^c
+    with pytest.raises(SclmdError):
+        plan.generate(1, seed=1)
