@@ -210,18 +210,60 @@ def make_engine(w, device, ntraj):
     return eng, nph
 
 
-def fill_noise(eng, w, ntraj, seed):
-    """synthetic N(0, sigma^2) noise table: a pinned host block of 32 time slabs tiled over nmd."""
+def fill_noise(eng, w, ntraj, seed, traj0):
+    """Quantum coloured noise for every trajectory, generated ON THE DEVICE straight into the noise tables
+    (Philox -> per-frequency factor -> in-house FFT; sclmd_md_generate_noise).  Bath temperatures T(1 +- delta/2),
+    Debye-like friction spectrum.  Also returns a pinned host block of 32 time slabs per bath for the e2e leg."""
+    import ctypes as C
+    from sclmd_b200 import _lib, noise as N
     rng = np.random.default_rng(seed)
+    t0 = time.perf_counter()
+    for b in range(2):
+        gam = np.array([np.eye(w["nc"]) * 0.05 * np.pi / 6.0])
+        plan = N.ph_plan(gam, np.array([0.0]), 300.0 * (1.05 if b == 0 else 0.95), 0.5, w["dt"], w["nmd"], device=eng.device)
+        _lib.check(_lib.lib().sclmd_md_generate_noise(eng._h, b, plan._h, C.c_uint64(seed), int(traj0)))
+        plan.close()
+    gen_s = time.perf_counter() - t0
     nblk = min(32, w["nmd"])
     blocks = []
     for b in range(2):
         blk = pinned((nblk, ntraj, w["nc"]))
         blk[...] = 0.01 * rng.standard_normal(blk.shape)
-        for s0 in range(0, w["nmd"], nblk):
-            eng.set_noise_rows(b, s0, blk[:min(nblk, w["nmd"] - s0)])
         blocks.append(blk)
-    return blocks
+    return blocks, gen_s
+
+
+def negf_also(rank, world, local, barrier):
+    """NEGF transmission sweep of the config-3 shape (n = 483, Gamma on 150 + 150 dofs, damp = 0.1 ps) with the
+    frequency grid sharded over the ranks (weak scaling: 2960 points per GPU); host buffers in and out."""
+    from sclmd_b200.negf import bpt
+    from sclmd_b200 import parallel as PAR
+    RPC = 6.582119569e-4
+    K = P.spring_chain_dyn(201, seed=14) / RPC ** 2
+    b = bpt(None, 0.25, 0.1, [list(range(60, 210)), list(range(393, 543))], [list(range(0, 60)), list(range(543, 603))],
+            dynmatfile=K, num=1000, device=local)
+    per = 2960
+    om = np.linspace(0, 0.25 / RPC, per * world + 1)
+    lo, hi = PAR.shard_range(len(om), rank, world)
+    b.tm_sweep(om[lo:lo + 296])
+    barrier()
+    t0 = time.perf_counter()
+    tm = b.tm_sweep(om[lo:hi])
+    full = PAR.gather_blocks(tm, len(om))
+    barrier()
+    dt = time.perf_counter() - t0
+    dt = dt if world == 1 else max_over_ranks(dt)
+    flops = ((8 / 3) * 483 ** 3 + 8 * 483 ** 2 * 150) * len(om)
+    return {"metric": "negf_omega_points_per_s", "value": len(om) / dt, "unit": "omega-points/s", "n": 483, "n_omega": len(om),
+            "fp64_tflops_algorithmic": flops / dt / 1e12, "transmission_checksum": float(np.sum(full))}
+
+
+def max_over_ranks(x):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
 
 
 def main():
@@ -254,7 +296,7 @@ def main():
 
     ntraj = w["ntraj"]
     eng, nph = make_engine(w, local, ntraj)
-    blocks = fill_noise(eng, w, ntraj, seed=1000 + rank)
+    blocks, noise_gen_s = fill_noise(eng, w, ntraj, seed=1000, traj0=rank * ntraj)
     rng = np.random.default_rng(2000 + rank)
     eng.set_state(0.05 * rng.standard_normal((ntraj, nph)), 0.02 * rng.standard_normal((ntraj, nph)), 0)
     K, W = args.steps, max(args.warmup, 3)
@@ -324,8 +366,11 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = ntraj * world * K / float(te[0])
 
+    eng.close()
+    also = None
+    if not args.no_also:
+        also = negf_also(rank, world, local, barrier)
     if rank != 0:
-        eng.close()
         if world > 1:
             dist.destroy_process_group()
         return
@@ -354,8 +399,8 @@ def main():
                                       "d2h_bytes_per_step": d2h, "api": "sclmd_md_set_noise_rows + sclmd_md_run(1) + "
                                       "sclmd_md_get_step_observables per step, pinned host buffers"},
             "gpu_launches": launches_total, "roofline": roof, "wall_ms_timed_region": wall_ms, "allreduce_ms": ar_ms,
-            "heat_current_mean": [float(sums[b] / sums[2] / w["nmd"]) for b in range(2)]}
-    eng.close()
+            "heat_current_mean": [float(sums[b] / sums[2] / w["nmd"]) for b in range(2)],
+            "noise_generation_s": noise_gen_s, "also": also}
 
     # ---------------- CPU baseline (reported, not the target): rank 0, N=1 only
     if world == 1 and not args.no_cpu_baseline:
