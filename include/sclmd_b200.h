@@ -109,6 +109,17 @@ int sclmd_md_set_profiling(sclmd_md *h, int on);
 int sclmd_md_get_profile(sclmd_md *h, double *tail_ms, int64_t *tail_launches, double *potforce_ms,
                          int64_t *potforce_launches);
 
+/* 1 (default): the FP64-bound K.q GEMM runs on a second stream concurrently with the HBM-bound
+ * history-tail kernels; 0: everything on one stream */
+int sclmd_md_set_overlap(sclmd_md *h, int on);
+
+/* 1 (default): diagonal-kernel baths with ml >= 128 stream their history ring from HBM once per 16 steps
+ * (time-blocked far/near tails, same flops, same results to rounding); 0: one full ring pass per step -- the
+ * direct single-tail algorithm on which the HBM roofline of SURVEY.md section 8d is defined */
+int sclmd_md_set_tail_block(sclmd_md *h, int on);
+/* ms[4], n[4] since profiling was switched on: 0 direct tail, 1 potential force, 2 far pass, 3 near pass */
+int sclmd_md_get_profile_all(sclmd_md *h, double *ms, int64_t *n);
+
 /* instrumentation: kernels launched by this handle so far; name/time of the dominant kernel */
 int64_t sclmd_md_launch_count(sclmd_md *h);
 /* time `reps` launches of the history-tail kernel of `bath` alone (CUDA events): avg ms */

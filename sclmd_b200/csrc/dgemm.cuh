@@ -17,6 +17,7 @@ namespace sclmd {
 
 struct GemmArgs {
     int M, N, Kseg, nseg, segs_per_split;
+    int Ktot;  // > 0: the segments are consecutive K-slices of ONE operand pair; slice s covers [s*Kseg, min(Ktot,(s+1)*Kseg))
     const double *A;
     long long lda, a_seg_stride;
     int a_head, a_mod;  // a_mod > 0: ring addressing slot = (a_head - seg) mod a_mod
@@ -75,6 +76,7 @@ dgemm_nt_seg_kernel(const GemmArgs g) {
     auto load_tile = [&](int it, int stage) {
         const int seg = seg_begin + it / ktiles;
         const int k0 = (it % ktiles) * BK;
+        const int kvalid = g.Ktot > 0 ? min(g.Kseg, g.Ktot - seg * g.Kseg) : g.Kseg;
         long long aoff, boff;
         if (g.a_mod > 0) {
             int slot = (g.a_head - seg) % g.a_mod;
@@ -91,7 +93,7 @@ dgemm_nt_seg_kernel(const GemmArgs g) {
         for (int c = tid; c < BM * CPR; c += THREADS) {
             const int r = c / CPR, kc = (c % CPR) * 2;
             const int gr = min(m0 + r, g.M - 1);
-            const int rem = g.Kseg - (k0 + kc);
+            const int rem = kvalid - (k0 + kc);
             const int nb = rem >= 2 ? 16 : (rem == 1 ? 8 : 0);
             const double *src = g.A + aoff + (long long)gr * g.lda + (nb ? k0 + kc : 0);
             cp_async16_zfill(as + r * LDS + kc, src, nb);
@@ -100,7 +102,7 @@ dgemm_nt_seg_kernel(const GemmArgs g) {
         for (int c = tid; c < BN * CPR; c += THREADS) {
             const int r = c / CPR, kc = (c % CPR) * 2;
             const int gr = min(n0 + r, g.N - 1);
-            const int rem = g.Kseg - (k0 + kc);
+            const int rem = kvalid - (k0 + kc);
             const int nb = rem >= 2 ? 16 : (rem == 1 ? 8 : 0);
             const double *src = g.B + boff + (long long)gr * g.ldb + (nb ? k0 + kc : 0);
             cp_async16_zfill(bs + r * LDS + kc, src, nb);
@@ -179,10 +181,42 @@ inline cudaError_t launch_dgemm_cfg(const GemmArgs &g, int nsplit, cudaStream_t 
 
 // Tile choice: big tiles when the problem fills the machine, small ones for skinny M (few
 // trajectories) so that more CTAs exist.
-inline cudaError_t launch_dgemm(const GemmArgs &g, int nsplit, cudaStream_t st) {
-    if (g.M > 64) return launch_dgemm_cfg<128, 128, 64, 32, 3>(g, nsplit, st);
-    if (g.M > 16) return launch_dgemm_cfg<64, 64, 32, 32, 4>(g, nsplit, st);
+inline cudaError_t launch_dgemm(const GemmArgs &g, int nsplit, cudaStream_t st, int force_cfg = -1) {
+    const int cfg = force_cfg >= 0 ? force_cfg : (g.M > 64 ? 0 : (g.M > 16 ? 1 : 2));
+    if (cfg == 0) return launch_dgemm_cfg<128, 128, 64, 32, 3>(g, nsplit, st);
+    if (cfg == 1) return launch_dgemm_cfg<64, 64, 32, 32, 4>(g, nsplit, st);
     return launch_dgemm_cfg<16, 128, 16, 32, 4>(g, nsplit, st);
+}
+
+// Split-K plan for a single big product C = A.B^T on `sms` SMs: pick the tile config and the number of K-slices
+// that minimise  rounds x per-unit work  (wave quantisation: 192 tiles of 128x128 on 148 SMs waste 35 %).
+// Each slice writes its own partial C; consumers add the slices in a fixed order (deterministic).
+struct SplitPlan {
+    int cfg, nsplit, kseg;
+};
+inline SplitPlan plan_split_k(int M, int N, int K, int sms, int max_split) {
+    SplitPlan best{M > 64 ? 0 : (M > 16 ? 1 : 2), 1, K};
+    double best_cost = 1e300;
+    const int bm[3] = {128, 64, 16}, bn[3] = {128, 64, 128}, per_sm[3] = {1, 3, 4};
+    const double eff[3] = {1.0, 0.80, 0.45};
+    for (int c = 0; c < 3; ++c) {
+        if (c == 0 && M <= 64) continue;
+        if (c == 2 && M > 16) continue;
+        for (int ns = 1; ns <= max_split; ++ns) {
+            const int kseg = round_up(cdiv(K, ns), 16);
+            if (ns > 1 && kseg < 192) break;
+            const int real_ns = cdiv(K, kseg);
+            const long long units = (long long)cdiv(M, bm[c]) * cdiv(N, bn[c]) * real_ns;
+            const long long slots = (long long)sms * per_sm[c];
+            const double rounds = (double)((units + slots - 1) / slots);
+            const double cost = rounds * per_sm[c] * bm[c] * bn[c] * (double)kseg / eff[c] + 2e5 * real_ns;
+            if (cost < best_cost) {
+                best_cost = cost;
+                best = SplitPlan{c, real_ns, kseg};
+            }
+        }
+    }
+    return best;
 }
 #endif
 

@@ -49,7 +49,10 @@ struct Bath {
     bool has_lin = false, has_extra = false;
     double c0 = 1.0;
     DevBuf<int> cids, inv;
-    DevBuf<double> kern, W, ring, xq, lin, tailp, noise, cur;
+    DevBuf<double> kern, W, ring, xq, lin, tailp, noise, cur, far;
+    bool blocked = false;     // time-blocked tails (diagonal kernel, long memory)
+    int far_nsplit = 1;
+    long long far_t0 = -1;    // block start the far tails in `far` belong to
 };
 
 // ---------------------------------------------------------------- kernels
@@ -68,8 +71,8 @@ __device__ __forceinline__ double bath_force(const BathDev &b, int traj, int ntr
 // evaluation A (md.py:383-398): etot, ring push, f_A, p_half, q_next, heat current
 __global__ void __launch_bounds__(256) k_phase_a(BathSet bs, int nph, int ld, int ntraj, int nmd, long long t, double dt,
                                                   const double *__restrict__ q, const double *__restrict__ p,
-                                                  const double *__restrict__ G, double *__restrict__ phalf,
-                                                  double *__restrict__ qn, double *__restrict__ etot) {
+                                                  const double *__restrict__ G, int gsplit, size_t gstride,
+                                                  double *__restrict__ phalf, double *__restrict__ qn, double *__restrict__ etot) {
     __shared__ double red[32];
     const int traj = blockIdx.x;
     const size_t row = (size_t)traj * ld;
@@ -79,7 +82,9 @@ __global__ void __launch_bounds__(256) k_phase_a(BathSet bs, int nph, int ld, in
     for (int b = 0; b < MAXB; ++b) cur[b] = 0.0;
     for (int i = threadIdx.x; i < nph; i += blockDim.x) {
         const double pi = p[row + i], qi = q[row + i];
-        double f = -G[row + i];
+        double gsum = G[row + i];
+        for (int z = 1; z < gsplit; ++z) gsum += G[(size_t)z * gstride + row + i];   // K-slices of K.q, fixed order
+        double f = -gsum;
 #pragma unroll
         for (int b = 0; b < MAXB; ++b) {
             if (b < bs.nb) {
@@ -111,14 +116,16 @@ __global__ void __launch_bounds__(256) k_phase_a(BathSet bs, int nph, int ld, in
 // constraint (md.py:407-408) and commits q.
 __global__ void __launch_bounds__(256) k_phase_bc(BathSet bs, int nph, int ld, int ntraj, int nmd, long long t, double dt,
                                                    const double *__restrict__ x, const double *__restrict__ phalf,
-                                                   const double *__restrict__ Gn, double *__restrict__ pout,
+                                                   const double *__restrict__ Gn, int gsplit, size_t gstride, double *__restrict__ pout,
                                                    const double *__restrict__ qn, double *__restrict__ qout,
                                                    const unsigned char *__restrict__ cons, int final, int fused) {
     const int traj = blockIdx.x;
     const size_t row = (size_t)traj * ld;
     const int slab = (int)((t + 1) % nmd);
     for (int i = threadIdx.x; i < nph; i += blockDim.x) {
-        const double ph = phalf[row + i], g = Gn[row + i];
+        const double ph = phalf[row + i];
+        double g = Gn[row + i];
+        for (int z = 1; z < gsplit; ++z) g += Gn[(size_t)z * gstride + row + i];
         double xi = fused ? ph : x[row + i];
         double pnew = 0.0;
         const int reps = fused ? 2 : 1;  // all baths time-local & diagonal: B and C in registers
@@ -232,6 +239,184 @@ __global__ void __launch_bounds__(512) k_tail_diag(const double *__restrict__ ri
     }
 }
 
+// ---- time-blocked history tails (diagonal kernels, long memory) -------------------------------------
+// The friction tail of step t = t0 + s (t0 = block start, s < TB)
+//   S'(t) = dt sum_{j=1}^{ml-1} k[j] p_{t+1-j}  =  Near_s + Far_s
+//   Near_s = dt sum_{j=1}^{s+1}  k[j] p_{t0+s+1-j}            (p_{t0} .. p_{t0+s}: at most TB fresh ring rows)
+//   Far_s  = dt sum_{d>=0}       k[s+2+d] p_{t0-1-d}          (everything older than the block start)
+// All TB far tails of a block are produced by ONE pass over the ring (each loaded p feeds TB accumulators), so
+// the ring is streamed from HBM once per TB steps instead of once per step; the flops are unchanged.
+// kern is zero-padded past row ml-1, which also retires the ring slots that are younger than the block start.
+constexpr int TB = 16;
+
+template <int T>
+__global__ void __launch_bounds__(256, 1) k_tail_far(const double *__restrict__ ring, const double *__restrict__ kern,
+                                                      double *__restrict__ out, int ntraj, int ml, int ncp, int base,
+                                                      int ages_per_split, int ct, double dt) {
+    const int c = blockIdx.z * ct + threadIdx.x;
+    if ((int)threadIdx.x >= ct || c >= ncp) return;
+    const int traj0 = blockIdx.x * T;
+    const int d_lo = blockIdx.y * ages_per_split, d_hi = min(d_lo + ages_per_split, ml);
+    double acc[T][TB];
+#pragma unroll
+    for (int k = 0; k < T; ++k)
+#pragma unroll
+        for (int s2 = 0; s2 < TB; ++s2) acc[k][s2] = 0.0;
+    const size_t tstride = (size_t)ml * ncp;
+    const double *rb[T];
+#pragma unroll
+    for (int k = 0; k < T; ++k) rb[k] = ring + (size_t)min(traj0 + k, ntraj - 1) * tstride + c;
+    for (int d0 = d_lo; d0 < d_hi; d0 += TB) {
+        double kw[2 * TB - 1];
+#pragma unroll
+        for (int i = 0; i < 2 * TB - 1; ++i) kw[i] = kern[(size_t)(d0 + 2 + i) * ncp + c];
+        int slot = (base - d0) % ml;
+        if (slot < 0) slot += ml;
+#pragma unroll
+        for (int u = 0; u < TB; ++u) {
+            double pv[T];
+#pragma unroll
+            for (int k = 0; k < T; ++k) {
+                double v;
+                asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(rb[k] + (size_t)slot * ncp));
+                pv[k] = v;
+            }
+#pragma unroll
+            for (int s2 = 0; s2 < TB; ++s2)
+#pragma unroll
+                for (int k = 0; k < T; ++k) acc[k][s2] = fma(kw[u + s2], pv[k], acc[k][s2]);
+            slot = slot == 0 ? ml - 1 : slot - 1;
+        }
+    }
+#pragma unroll
+    for (int s2 = 0; s2 < TB; ++s2)
+#pragma unroll
+        for (int k = 0; k < T; ++k)
+            if (traj0 + k < ntraj) out[(((size_t)blockIdx.y * TB + s2) * ntraj + traj0 + k) * ncp + c] = dt * acc[k][s2];
+}
+
+// TMA-staged variant (ncp <= 320): one elected thread streams contiguous 16-row ring chunks of T trajectories into
+// shared memory with cp.async.bulk (SASS UBLKCP) against an mbarrier, two stages deep, while all warps run the
+// 16x16 Toeplitz update of the previous chunk out of shared memory.  Age u of a chunk sits in smem row 15-u.
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity));
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(dst)),
+                 "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+
+template <int T>
+__global__ void __launch_bounds__(320, 1) k_tail_far_tma(const double *__restrict__ ring, const double *__restrict__ kern,
+                                                          double *__restrict__ out, int ntraj, int ml, int ncp, int base,
+                                                          int ages_per_split, double dt) {
+    extern __shared__ __align__(128) double stage_mem[];   // [2][T][TB][ncp]
+    __shared__ __align__(8) uint64_t full[2];
+    const int c = threadIdx.x;
+    const int traj0 = blockIdx.x * T;
+    const int d_lo = blockIdx.y * ages_per_split, d_hi = min(d_lo + ages_per_split, ml);
+    const int nchunk = (d_hi - d_lo + TB - 1) / TB;
+    const size_t tstride = (size_t)ml * ncp, stage_elems = (size_t)T * TB * ncp;
+    const unsigned rowbytes = (unsigned)ncp * 8u;
+
+    auto issue = [&](int ch) {   // one thread: ring rows of chunk ch -> stage ch&1
+        double *dst = stage_mem + (size_t)(ch & 1) * stage_elems;
+        uint64_t *bar = &full[ch & 1];
+        mbar_expect_tx(bar, (unsigned)(T * TB) * rowbytes);
+        int lo = (base - (d_lo + ch * TB) - (TB - 1)) % ml;
+        if (lo < 0) lo += ml;
+        const int n1 = min(TB, ml - lo);           // rows lo .. lo+n1-1, then (wrap) rows 0 .. TB-n1-1
+#pragma unroll
+        for (int k = 0; k < T; ++k) {
+            const double *src = ring + (size_t)min(traj0 + k, ntraj - 1) * tstride;
+            bulk_g2s(dst + (size_t)k * TB * ncp, src + (size_t)lo * ncp, (unsigned)n1 * rowbytes, bar);
+            if (n1 < TB) bulk_g2s(dst + ((size_t)k * TB + n1) * ncp, src, (unsigned)(TB - n1) * rowbytes, bar);
+        }
+    };
+
+    if (threadIdx.x == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        issue(0);
+        if (nchunk > 1) issue(1);
+    }
+    const bool active = c < ncp;
+    const int cc = active ? c : 0;
+    double acc[T][TB];
+#pragma unroll
+    for (int k = 0; k < T; ++k)
+#pragma unroll
+        for (int s2 = 0; s2 < TB; ++s2) acc[k][s2] = 0.0;
+    double kw[2 * TB - 1];
+#pragma unroll
+    for (int i = 0; i < 2 * TB - 1; ++i) kw[i] = kern[(size_t)(d_lo + 2 + i) * ncp + cc];
+    for (int ch = 0; ch < nchunk; ++ch) {
+        const int d0 = d_lo + ch * TB;
+        double knew[TB];   // the 16 kernel rows the next chunk adds to the sliding window (prefetched under the math)
+#pragma unroll
+        for (int i = 0; i < TB; ++i) knew[i] = kern[(size_t)(d0 + 2 + 2 * TB - 1 + i) * ncp + cc];
+        mbar_wait(&full[ch & 1], (unsigned)((ch >> 1) & 1));
+        const double *sp = stage_mem + (size_t)(ch & 1) * stage_elems + cc;
+#pragma unroll
+        for (int u = 0; u < TB; ++u) {
+            double pv[T];
+#pragma unroll
+            for (int k = 0; k < T; ++k) pv[k] = sp[((size_t)k * TB + (TB - 1 - u)) * ncp];
+#pragma unroll
+            for (int s2 = 0; s2 < TB; ++s2)
+#pragma unroll
+                for (int k = 0; k < T; ++k) acc[k][s2] = fma(kw[u + s2], pv[k], acc[k][s2]);
+        }
+#pragma unroll
+        for (int i = 0; i < TB - 1; ++i) kw[i] = kw[i + TB];
+#pragma unroll
+        for (int i = 0; i < TB; ++i) kw[TB - 1 + i] = knew[i];
+        __syncthreads();                            // everyone is done with this stage
+        if (threadIdx.x == 0 && ch + 2 < nchunk) issue(ch + 2);
+    }
+    if (active) {
+#pragma unroll
+        for (int s2 = 0; s2 < TB; ++s2)
+#pragma unroll
+            for (int k = 0; k < T; ++k)
+                if (traj0 + k < ntraj) out[(((size_t)blockIdx.y * TB + s2) * ntraj + traj0 + k) * ncp + c] = dt * acc[k][s2];
+    }
+}
+
+// tail[traj][c] = Near_s + sum_z Far[z][s]   (written where the phase kernels expect a single partial)
+__global__ void __launch_bounds__(256) k_tail_near(const double *__restrict__ ring, const double *__restrict__ kern,
+                                                    const double *__restrict__ far, double *__restrict__ out, int ntraj, int ml,
+                                                    int ncp, int head, int s, int nsplit, double dt) {
+    const int traj = blockIdx.x;
+    const double *r = ring + (size_t)traj * ml * ncp;
+    for (int c = threadIdx.x; c < ncp; c += blockDim.x) {
+        double acc = 0.0;
+        int slot = head;
+        for (int j = 1; j <= s + 1; ++j) {
+            acc = fma(kern[(size_t)j * ncp + c], r[(size_t)slot * ncp + c], acc);
+            slot = slot == 0 ? ml - 1 : slot - 1;
+        }
+        double f = 0.0;
+        for (int z = 0; z < nsplit; ++z) f += far[(((size_t)z * TB + s) * ntraj + traj) * ncp + c];
+        out[(size_t)traj * ncp + c] = dt * acc + f;
+    }
+}
+
 __global__ void k_sum_slots(const double *__restrict__ cur, int nmd, int ntraj, double *__restrict__ sums) {
     const int traj = blockIdx.x * blockDim.x + threadIdx.x;
     if (traj >= ntraj) return;
@@ -248,8 +433,9 @@ struct sclmd_md {
     double dt = 0;
     long long t = 0;
     bool g_valid = false, have_dyn = false;
-    cudaStream_t st = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t st = nullptr, st2 = nullptr;   // st2: the FP64-bound K.q GEMM overlaps the HBM-bound history tails
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evG = nullptr;
+    bool overlap = true;
     DevBuf<double> K, q, p, G, Gn, phalf, p1, qn, etot, scratch;
     DevBuf<unsigned char> cons;
     bool has_cons = false;
@@ -259,12 +445,15 @@ struct sclmd_md {
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;
     std::vector<int> ev_kind;  // 0 = tail, 1 = potforce; events come in (start, stop) pairs
-    size_t ev_used = 0;
-    double prof_ms[2] = {0, 0};
-    long long prof_n[2] = {0, 0};
+    size_t ev_used = 0, ev_open = 0;
+    double prof_ms[4] = {0, 0, 0, 0};   // 0 direct tail, 1 potforce, 2 far pass, 3 near
+    long long prof_n[4] = {0, 0, 0, 0};
+    bool tail_block = true, far_tma = true;
+    SplitPlan gplan{0, 1, 0};
 
-    void prof_begin(int kind) {
+    void prof_begin(int kind, cudaStream_t stream = nullptr) {
         if (!profiling) return;
+        if (!stream) stream = st;
         if (ev_used + 2 > ev_pool.size()) {
             for (int i = 0; i < 2; ++i) {
                 cudaEvent_t e;
@@ -273,12 +462,13 @@ struct sclmd_md {
             }
         }
         ev_kind.push_back(kind);
-        cudaEventRecord(ev_pool[ev_used], st);
-    }
-    void prof_end() {
-        if (!profiling) return;
-        cudaEventRecord(ev_pool[ev_used + 1], st);
+        cudaEventRecord(ev_pool[ev_used], stream);
+        ev_open = ev_used;
         ev_used += 2;
+    }
+    void prof_end(cudaStream_t stream = nullptr) {
+        if (!profiling) return;
+        cudaEventRecord(ev_pool[ev_open + 1], stream ? stream : st);
     }
     void prof_collect() {  // call after the stream is synchronised
         for (size_t i = 0; i + 1 < ev_used; i += 2) {
@@ -299,7 +489,7 @@ struct sclmd_md {
         for (int i = 0; i < s.nb; ++i) {
             const Bath &b = *baths[i];
             BathDev &d = s.b[i];
-            d.nc = b.nc; d.ncp = b.ncp; d.ml = b.ml; d.nsplit = b.nsplit;
+            d.nc = b.nc; d.ncp = b.ncp; d.ml = b.ml; d.nsplit = (b.blocked && tail_block) ? 1 : b.nsplit;
             d.diag = b.kind == SCLMD_KERNEL_DIAG;
             d.has_lin = b.has_lin; d.use_tail = b.ml > 1; d.c0 = b.c0;
             d.inv = b.inv.p; d.cids = b.cids.p; d.k0 = b.kern.p; d.noise = b.noise.p;
@@ -312,15 +502,16 @@ struct sclmd_md {
         return false;
     }
 
-    int potforce(const double *qsrc, double *dst) {  // dst = qsrc . K^T   (md.py:467, sign applied by consumers)
+    int potforce(const double *qsrc, double *dst, cudaStream_t stream = nullptr) {  // dst = qsrc . K^T   (md.py:467, sign applied by consumers)
+        if (!stream) stream = st;
         GemmArgs g{};
-        g.M = ntraj; g.N = nph; g.Kseg = ld; g.nseg = 1; g.segs_per_split = 1;
-        g.A = qsrc; g.lda = ld; g.a_seg_stride = 0; g.a_head = 0; g.a_mod = 0;
-        g.B = K.p; g.ldb = ld; g.b_seg_stride = 0; g.b_seg0 = 0;
-        g.C = dst; g.ldc = ld; g.c_split_stride = 0; g.alpha = 1.0;
-        prof_begin(1);
-        SCLMD_CUDA(launch_dgemm(g, 1, st));
-        prof_end();
+        g.M = ntraj; g.N = nph; g.Kseg = gplan.kseg; g.nseg = gplan.nsplit; g.segs_per_split = 1; g.Ktot = ld;
+        g.A = qsrc; g.lda = ld; g.a_seg_stride = gplan.kseg; g.a_head = 0; g.a_mod = 0;
+        g.B = K.p; g.ldb = ld; g.b_seg_stride = gplan.kseg; g.b_seg0 = 0;
+        g.C = dst; g.ldc = ld; g.c_split_stride = (long long)ntraj * ld; g.alpha = 1.0;
+        prof_begin(1, stream);
+        SCLMD_CUDA(launch_dgemm(g, gplan.nsplit, stream, gplan.cfg));
+        prof_end(stream);
         ++launches;
         return 0;
     }
@@ -335,7 +526,7 @@ struct sclmd_md {
         launches += 2;
         return 0;
     }
-    int tail(Bath &b, int head) {  // partial tails from the ring with p_t already pushed at slot `head`
+    int tail_direct(Bath &b, int head) {  // partial tails from the ring with p_t already pushed at slot `head`
         if (b.ml <= 1) return 0;
         prof_begin(0);
         if (b.kind == SCLMD_KERNEL_DIAG) {
@@ -366,6 +557,46 @@ struct sclmd_md {
         return 0;
     }
 
+    // friction tail S'(tt) of step tt (ring already holds p_tt)
+    int tail_step(Bath &b, long long tt) {
+        if (b.ml <= 1) return 0;
+        auto fmod_ll = [](long long a, long long m) { long long r = a % m; return r < 0 ? r + m : r; };
+        if (!(b.blocked && tail_block)) return tail_direct(b, (int)fmod_ll(tt, b.ml));
+        const long long t0 = tt - fmod_ll(tt, TB);
+        const int T = ntraj >= 4 ? 4 : 1;
+        if (b.far_t0 != t0) {
+            const int base = (int)fmod_ll(t0 - 1, b.ml);
+            const int ntiles = cdiv(b.ncp, 256), ct = cdiv(b.ncp, ntiles);
+            const int aps = round_up(cdiv(b.ml, b.far_nsplit), TB);
+            dim3 grid(cdiv(ntraj, T), b.far_nsplit, ntiles);
+            prof_begin(2);
+            if (b.ncp <= 320 && ntraj >= 2 && far_tma) {
+                const size_t sm = (size_t)2 * 2 * TB * b.ncp * sizeof(double);
+                static bool cfg = false;
+                if (!cfg) {
+                    SCLMD_CUDA(cudaFuncSetAttribute(k_tail_far_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                    cfg = true;
+                }
+                k_tail_far_tma<2><<<dim3(cdiv(ntraj, 2), b.far_nsplit), round_up(b.ncp, 32), sm, st>>>(b.ring.p, b.kern.p, b.far.p, ntraj,
+                                                                                                  b.ml, b.ncp, base, aps, dt);
+            } else if (T == 4)
+                k_tail_far<4><<<grid, round_up(ct, 32), 0, st>>>(b.ring.p, b.kern.p, b.far.p, ntraj, b.ml, b.ncp, base, aps, ct, dt);
+            else
+                k_tail_far<1><<<grid, round_up(ct, 32), 0, st>>>(b.ring.p, b.kern.p, b.far.p, ntraj, b.ml, b.ncp, base, aps, ct, dt);
+            prof_end();
+            SCLMD_CUDA(cudaGetLastError());
+            b.far_t0 = t0;
+            ++launches;
+        }
+        prof_begin(3);
+        k_tail_near<<<ntraj, 256, 0, st>>>(b.ring.p, b.kern.p, b.far.p, b.tailp.p, ntraj, b.ml, b.ncp, (int)fmod_ll(tt, b.ml), (int)(tt - t0),
+                                           b.far_nsplit, dt);
+        prof_end();
+        SCLMD_CUDA(cudaGetLastError());
+        ++launches;
+        return 0;
+    }
+
     int step() {
         BathSet bs = view();
         const bool lin = any_lin();
@@ -376,24 +607,35 @@ struct sclmd_md {
         if (lin)
             for (auto &b : baths)
                 if (b->has_lin) if (int e = bath_lin(*b, p.p, q.p)) return e;
-        k_phase_a<<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, q.p, p.p, G.p, phalf.p, qn.p, etot.p);
+        k_phase_a<<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, q.p, p.p, G.p, gplan.nsplit, (size_t)ntraj * ld, phalf.p, qn.p, etot.p);
         SCLMD_CUDA(cudaGetLastError());
         ++launches;
-        for (auto &b : baths) if (int e = tail(*b, (int)(t % b->ml))) return e;
-        if (int e = potforce(qn.p, Gn.p)) return e;
+        bool any_tail = false;
+        for (auto &b : baths) any_tail |= b->ml > 1;
+        if (overlap && any_tail) {   // GEMM on st2 first (1 CTA/SM leaves room for the tail CTAs), tails on st
+            SCLMD_CUDA(cudaEventRecord(evA, st));
+            SCLMD_CUDA(cudaStreamWaitEvent(st2, evA, 0));
+            if (int e = potforce(qn.p, Gn.p, st2)) return e;
+            SCLMD_CUDA(cudaEventRecord(evG, st2));
+            for (auto &b : baths) if (int e = tail_step(*b, t)) return e;
+            SCLMD_CUDA(cudaStreamWaitEvent(st, evG, 0));
+        } else {
+            for (auto &b : baths) if (int e = tail_step(*b, t)) return e;
+            if (int e = potforce(qn.p, Gn.p)) return e;
+        }
         const unsigned char *cm = has_cons ? cons.p : nullptr;
         if (!lin) {
-            k_phase_bc<<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, nullptr, phalf.p, Gn.p, p.p, qn.p, q.p, cm, 1, 1);
+            k_phase_bc<<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, nullptr, phalf.p, Gn.p, gplan.nsplit, (size_t)ntraj * ld, p.p, qn.p, q.p, cm, 1, 1);
             SCLMD_CUDA(cudaGetLastError());
             ++launches;
         } else {
             for (auto &b : baths)
                 if (b->has_lin) if (int e = bath_lin(*b, phalf.p, qn.p)) return e;
-            k_phase_bc<<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, phalf.p, phalf.p, Gn.p, p1.p, qn.p, q.p, cm, 0, 0);
+            k_phase_bc<<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, phalf.p, phalf.p, Gn.p, gplan.nsplit, (size_t)ntraj * ld, p1.p, qn.p, q.p, cm, 0, 0);
             SCLMD_CUDA(cudaGetLastError());
             for (auto &b : baths)
                 if (b->has_lin) if (int e = bath_lin(*b, p1.p, qn.p)) return e;
-            k_phase_bc<<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, p1.p, phalf.p, Gn.p, p.p, qn.p, q.p, cm, 1, 0);
+            k_phase_bc<<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, p1.p, phalf.p, Gn.p, gplan.nsplit, (size_t)ntraj * ld, p.p, qn.p, q.p, cm, 1, 0);
             SCLMD_CUDA(cudaGetLastError());
             launches += 2;
         }
@@ -419,11 +661,16 @@ int sclmd_md_create(int nph, int ntraj, double dt, int nmd, int device, sclmd_md
     h->nph = nph; h->ld = round_up(nph, 2); h->ntraj = ntraj; h->nmd = nmd; h->dt = dt; h->device = device;
     h->nsm = sm_count(device);
     SCLMD_CUDA(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+    SCLMD_CUDA(cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking));
+    SCLMD_CUDA(cudaEventCreateWithFlags(&h->evA, cudaEventDisableTiming));
+    SCLMD_CUDA(cudaEventCreateWithFlags(&h->evG, cudaEventDisableTiming));
     SCLMD_CUDA(cudaEventCreate(&h->ev0));
     SCLMD_CUDA(cudaEventCreate(&h->ev1));
     const size_t n = (size_t)ntraj * h->ld;
     SCLMD_CUDA(h->K.alloc((size_t)nph * h->ld));
-    SCLMD_CUDA(h->q.alloc(n)); SCLMD_CUDA(h->p.alloc(n)); SCLMD_CUDA(h->G.alloc(n)); SCLMD_CUDA(h->Gn.alloc(n));
+    h->gplan = plan_split_k(ntraj, nph, h->ld, h->nsm, 4);
+    SCLMD_CUDA(h->q.alloc(n)); SCLMD_CUDA(h->p.alloc(n));
+    SCLMD_CUDA(h->G.alloc(n * h->gplan.nsplit)); SCLMD_CUDA(h->Gn.alloc(n * h->gplan.nsplit));
     SCLMD_CUDA(h->phalf.alloc(n)); SCLMD_CUDA(h->p1.alloc(n)); SCLMD_CUDA(h->qn.alloc(n));
     SCLMD_CUDA(h->etot.alloc((size_t)nmd * ntraj));
     SCLMD_CUDA(h->cons.alloc(nph));
@@ -438,6 +685,9 @@ int sclmd_md_destroy(sclmd_md *h) {
     if (h->st) cudaStreamSynchronize(h->st);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->evA) cudaEventDestroy(h->evA);
+    if (h->evG) cudaEventDestroy(h->evG);
+    if (h->st2) cudaStreamDestroy(h->st2);
     if (h->st) cudaStreamDestroy(h->st);
     delete h;
     return SCLMD_OK;
@@ -492,7 +742,7 @@ int sclmd_md_add_bath(sclmd_md *h, const int32_t *cids, int nc, int ml, const do
     SCLMD_CUDA(cudaMemcpy(b->inv.p, inv.data(), h->nph * sizeof(int), cudaMemcpyHostToDevice));
     // kernel
     if (kernel_kind == SCLMD_KERNEL_DIAG) {
-        SCLMD_CUDA(b->kern.alloc((size_t)(ml + 1) * ncp));
+        SCLMD_CUDA(b->kern.alloc((size_t)(ml + 5 * TB + 2) * ncp));   // rows >= ml stay 0 (branch-free drop-out / far-tail padding)
         SCLMD_CUDA(cudaMemcpy2D(b->kern.p, ncp * sizeof(double), kernel, nc * sizeof(double), nc * sizeof(double), ml, cudaMemcpyHostToDevice));
     } else {
         SCLMD_CUDA(b->kern.alloc((size_t)ml * nc * ncp));
@@ -522,6 +772,12 @@ int sclmd_md_add_bath(sclmd_md *h, const int32_t *cids, int nc, int ml, const do
         int want = kernel_kind == SCLMD_KERNEL_DIAG ? 4 * h->nsm : 2 * h->nsm;
         b->nsplit = std::max(1, std::min({cdiv(want, tiles), 32, std::max(1, (ml - 1) / 64)}));
         SCLMD_CUDA(b->tailp.alloc((size_t)b->nsplit * ntraj * ncp));
+        if (kernel_kind == SCLMD_KERNEL_DIAG && ml >= 8 * TB) {
+            b->blocked = true;
+            const int ctas = cdiv(ntraj, ntraj >= 4 ? 4 : 1) * cdiv(ncp, 256);
+            b->far_nsplit = std::max(1, std::min({cdiv(4 * h->nsm, ctas), 16, ml / (4 * TB)}));
+            SCLMD_CUDA(b->far.alloc((size_t)b->far_nsplit * TB * ntraj * ncp));
+        }
     }
     SCLMD_CUDA(b->noise.alloc((size_t)h->nmd * ntraj * ncp));
     SCLMD_CUDA(b->cur.alloc((size_t)h->nmd * ntraj));
@@ -570,7 +826,10 @@ int sclmd_md_set_state(sclmd_md *h, const double *q, const double *p, int64_t t)
     if (q) SCLMD_CUDA(cudaMemcpy2DAsync(h->q.p, pitch, q, w, w, h->ntraj, cudaMemcpyHostToDevice, h->st));
     if (p) SCLMD_CUDA(cudaMemcpy2DAsync(h->p.p, pitch, p, w, w, h->ntraj, cudaMemcpyHostToDevice, h->st));
     SCLMD_CUDA(cudaStreamSynchronize(h->st));
-    if (t >= 0) h->t = t;
+    if (t >= 0 && t != h->t) {
+        h->t = t;
+        for (auto &b : h->baths) b->far_t0 = -1;
+    }
     if (q) h->g_valid = false;
     return SCLMD_OK;
 }
@@ -592,6 +851,7 @@ int sclmd_md_reset_history(sclmd_md *h) {
     for (auto &b : h->baths) {
         SCLMD_CUDA(cudaMemsetAsync(b->ring.p, 0, b->ring.n * sizeof(double), h->st));
         if (b->tailp.p) SCLMD_CUDA(cudaMemsetAsync(b->tailp.p, 0, b->tailp.n * sizeof(double), h->st));
+        b->far_t0 = -1;
     }
     SCLMD_CUDA(cudaStreamSynchronize(h->st));
     return SCLMD_OK;
@@ -629,11 +889,25 @@ int sclmd_md_set_history(sclmd_md *h, int bath, const double *phis) {
     SCLMD_CUDA(cudaMemcpy(b.ring.p, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice));
     // the tail for evaluation A of the next step: ring as if p_{t-1} had just been pushed
     if (b.ml > 1) {
-        long long head = (h->t - 1) % b.ml;
-        if (head < 0) head += b.ml;
-        if (int e = h->tail(b, (int)head)) return e;
+        b.far_t0 = -1;
+        if (int e = h->tail_step(b, h->t - 1)) return e;
         SCLMD_CUDA(cudaStreamSynchronize(h->st));
     }
+    return SCLMD_OK;
+}
+
+// 1 (default): diagonal-kernel baths with ml >= 128 stream their ring once per 16 steps (time-blocked far/near tails);
+// 0: one full ring pass per step (the direct single-tail algorithm the HBM roofline of SURVEY 8d is defined on)
+int sclmd_md_set_tail_block(sclmd_md *h, int on) {
+    SCLMD_REQUIRE(h, "sclmd_md_set_tail_block: NULL handle");
+    SCLMD_CUDA(cudaSetDevice(h->device));
+    h->tail_block = on != 0;
+    h->far_tma = on != 2;    // 2 = time-blocked with the plain-load far kernel (for A/B measurements)
+    for (auto &b : h->baths) {   // the partial-tail layout differs between the modes: rebuild S'(t-1)
+        b->far_t0 = -1;
+        if (b->ml > 1) if (int e = h->tail_step(*b, h->t - 1)) return e;
+    }
+    SCLMD_CUDA(cudaStreamSynchronize(h->st));
     return SCLMD_OK;
 }
 
@@ -654,11 +928,17 @@ int sclmd_md_run(sclmd_md *h, int64_t nsteps, float *elapsed_ms) {
     return SCLMD_OK;
 }
 
+// 1 (default): run the K.q GEMM on a second stream concurrently with the history tails; 0: single stream
+int sclmd_md_set_overlap(sclmd_md *h, int on) {
+    SCLMD_REQUIRE(h, "sclmd_md_set_overlap: NULL handle");
+    h->overlap = on != 0;
+    return SCLMD_OK;
+}
+
 int sclmd_md_set_profiling(sclmd_md *h, int on) {
     SCLMD_REQUIRE(h, "sclmd_md_set_profiling: NULL handle");
     h->profiling = on != 0;
-    h->prof_ms[0] = h->prof_ms[1] = 0;
-    h->prof_n[0] = h->prof_n[1] = 0;
+    for (int i = 0; i < 4; ++i) { h->prof_ms[i] = 0; h->prof_n[i] = 0; }
     return SCLMD_OK;
 }
 
@@ -668,6 +948,13 @@ int sclmd_md_get_profile(sclmd_md *h, double *tail_ms, int64_t *tail_launches, d
     if (tail_launches) *tail_launches = h->prof_n[0];
     if (potforce_ms) *potforce_ms = h->prof_ms[1];
     if (potforce_launches) *potforce_launches = h->prof_n[1];
+    return SCLMD_OK;
+}
+
+// ms[4], n[4]: 0 = direct history tail, 1 = potential force (when on the main stream), 2 = time-blocked far pass, 3 = near pass
+int sclmd_md_get_profile_all(sclmd_md *h, double *ms, int64_t *n) {
+    SCLMD_REQUIRE(h && ms && n, "sclmd_md_get_profile_all: NULL argument");
+    for (int i = 0; i < 4; ++i) { ms[i] = h->prof_ms[i]; n[i] = h->prof_n[i]; }
     return SCLMD_OK;
 }
 
@@ -762,15 +1049,18 @@ int sclmd_md_time_tail(sclmd_md *h, int bath, int reps, float *avg_ms) {
     // tailp is scratch between steps only in the sense that re-running with the same head is idempotent
     long long head = (h->t - 1) % b.ml;
     if (head < 0) head += b.ml;
-    if (int e = h->tail(b, (int)head)) return e;  // warm-up
+    if (int e = h->tail_direct(b, (int)head)) return e;  // warm-up
     SCLMD_CUDA(cudaEventRecord(h->ev0, h->st));
     for (int r = 0; r < reps; ++r)
-        if (int e = h->tail(b, (int)head)) return e;
+        if (int e = h->tail_direct(b, (int)head)) return e;
     SCLMD_CUDA(cudaEventRecord(h->ev1, h->st));
     SCLMD_CUDA(cudaStreamSynchronize(h->st));
     float ms = 0;
     SCLMD_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     *avg_ms = ms / reps;
+    b.far_t0 = -1;   // restore the tail in the handle's own mode
+    if (int e = h->tail_step(b, h->t - 1)) return e;
+    SCLMD_CUDA(cudaStreamSynchronize(h->st));
     return SCLMD_OK;
 }
 

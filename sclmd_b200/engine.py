@@ -89,6 +89,19 @@ class MDEngine:
         check(_lib.lib().sclmd_md_get_step_observables(self._h, int(slab), dptr(out)))
         return out
 
+    def set_overlap(self, on=True):
+        check(_lib.lib().sclmd_md_set_overlap(self._h, 1 if on else 0))
+
+    def set_tail_block(self, on=True):
+        check(_lib.lib().sclmd_md_set_tail_block(self._h, int(on)))
+
+    def profile_all(self):
+        ms = np.zeros(4)
+        n = np.zeros(4, dtype=np.int64)
+        check(_lib.lib().sclmd_md_get_profile_all(self._h, dptr(ms), n.ctypes.data_as(_lib.c_int64_p)))
+        names = ("tail_direct", "potforce", "tail_far", "tail_near")
+        return {k: dict(ms=float(ms[i]), launches=int(n[i])) for i, k in enumerate(names)}
+
     def set_profiling(self, on=True):
         check(_lib.lib().sclmd_md_set_profiling(self._h, 1 if on else 0))
 

@@ -118,6 +118,61 @@ def test_memory_kernels_vs_oracle(kind, ml, nc, ntraj, nsteps):
     eng.close()
 
 
+@pytest.mark.parametrize("ml,nc,ntraj", [(200, 22, 5), (4096, 12, 4), (131, 7, 1)])
+def test_time_blocked_tails_equal_direct_tails(ml, nc, ntraj):
+    """the 16-step time-blocked far/near split of the friction tail is the same sum in another order:
+    both modes against the oracle, with a mode switch and run() calls that end mid-block"""
+    from sclmd_b200.engine import MDEngine
+    natoms = 12
+    nph, dt, nmd = 3 * natoms, 0.25 / 0.658, 64
+    K = P.psd_project(P.spring_chain_dyn(natoms, seed=9))
+    kern = P.diag_kernel(ml, nc, dt, 4, tau=400.0)          # slowly decaying memory: old history matters
+    nz = P.injected_noise(ntraj, nmd, nc, seed=5)
+    rng = np.random.default_rng(1)
+    q0, p0 = 0.05 * rng.standard_normal((ntraj, nph)), 0.02 * rng.standard_normal((ntraj, nph))
+    ens = O.EnsembleMD(K, dt, nmd, ntraj, None)
+    ens.add_bath(list(range(nc)), kern, nz)
+    ens.q[:], ens.p[:] = q0, p0
+    engs = []
+    for mode in (1, 0):
+        e = MDEngine(nph, ntraj, dt, nmd)
+        e.set_dyn(K)
+        e.add_bath(list(range(nc)), kern)
+        e.set_noise(0, nz)
+        e.set_tail_block(mode)
+        e.set_state(q0, p0, 0)
+        engs.append(e)
+    done = 0
+    for chunk in (5, 16, 1, 27, 40):
+        ens.run(chunk)
+        done += chunk
+        for e in engs:
+            e.run(chunk)
+            q, p, t = e.get_state()
+            assert t == done and relerr(q, ens.q) < TOL_STEP and relerr(p, ens.p) < TOL_STEP, (ml, done)
+    engs[0].set_tail_block(0)        # switch modes in the middle of a block
+    engs[1].set_tail_block(1)
+    ens.run(23)
+    for e in engs:
+        e.run(23)
+        q, p, _ = e.get_state()
+        assert relerr(q, ens.q) < TOL_STEP and relerr(p, ens.p) < TOL_STEP
+    # restart into a fresh blocked engine at a time that is not a block boundary
+    q, p, t = engs[0].get_state()
+    f = MDEngine(nph, ntraj, dt, nmd)
+    f.set_dyn(K)
+    f.add_bath(list(range(nc)), kern)
+    f.set_noise(0, nz)
+    f.set_state(q, p, t)
+    f.set_history(0, engs[0].get_history(0))
+    ens.run(19)
+    f.run(19)
+    qf, pf, _ = f.get_state()
+    assert relerr(qf, ens.q) < TOL_STEP and relerr(pf, ens.p) < TOL_STEP
+    for e in engs + [f]:
+        e.close()
+
+
 def test_history_roundtrip_and_restart():
     """state + history saved from one engine and loaded into another continue identically
     (md.py:552-562 restart semantics)."""
