@@ -13,6 +13,7 @@
 // Layout: augmented matrix W = [M | E] column-major, planar complex (real plane, imaginary
 // plane), one scratch slot per resident CTA; CTAs loop over frequencies (persistent grid).
 #include <algorithm>
+#include <cstdlib>
 #include <memory>
 
 #include "common.cuh"
@@ -24,9 +25,10 @@ namespace {
 constexpr int NB = 16;    // panel width
 constexpr int CW = 64;    // column chunk of the trailing update
 constexpr int NT = 256;   // threads per CTA
+constexpr int UW = CW + 4; // padded row of the U chunk in shared memory (conflict-free DMMA fragment loads)
 
 struct LuArgs {
-    int n, ld, nrhs, ncols, nw, mode;   // mode 0 = tm, 1 = ps
+    int n, np, ld, lw, nrhs, ncols, nw, mode;   // mode 0 = tm, 1 = ps; ld: panel leading dim (smem), lw: leading dim of W
     const double *K;                     // [n][n] row-major (symmetric)
     const double *sig_mask;              // [n] number of leads touching each dof (0/1/2)
     const int *rhs;                      // [nrhs] unit-vector index of every right-hand side
@@ -38,6 +40,7 @@ struct LuArgs {
     double *W;                           // [grid][2][ncols*ld]
     double *out;                         // [nw]
     int *status;                         // [nw] 0 ok, 1 singular pivot
+    long long *timing;                   // optional [8] cycle counters of CTA 0 (build, panel, trsm, update, backsub, observable)
 };
 
 __device__ __forceinline__ void cfma_sub(double &cr, double &ci, double ar, double ai, double br, double bi) {
@@ -46,47 +49,83 @@ __device__ __forceinline__ void cfma_sub(double &cr, double &ci, double ar, doub
     ci = fma(-ar, bi, ci); ci = fma(-ai, br, ci);
 }
 
-// C[rows r0..r1) x cols [c0, c0+cw)  -=  P[rows][0..kb) . U[0..kb)[cols]
-//   P planar in smem with leading dim pld (row index relative to prow0), U planar in smem [kb][CW]
-__device__ __forceinline__ void rank_update(double *__restrict__ Wre, double *__restrict__ Wim, int ld, int r0, int r1, int c0, int cw,
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// C[rows r0..r1) x cols [c0, c0+cw)  -=  P[rows][0..NB) . U[0..NB)[cols]      (complex, planar; W row-major, leading dim lw)
+//   P in smem: Pre/Pim[kk*pld + (row - prow0)], columns kk >= kb are zero;  U in smem: Ure/Uim[kk*UW + col], rows >= kb zero.
+// FP64 tensor path: the complex product is four real DMMA.8x8x4 per fragment pair
+//   Re += Pre.Ure + (-Pim).Uim ,  Im += Pre.Uim + Pim.Ure.
+// 8 warps = 2 row groups (32 rows) x 4 column groups (16 columns): one pass covers 64 rows x 64 columns.
+// The C tile is fetched into registers BEFORE the DMMA loop (it does not depend on it): every lane has 16 independent
+// 16-byte loads per plane in flight while the tensor pipe works, so the update streams W at memory speed.
+__device__ __forceinline__ void rank_update(double *__restrict__ Wre, double *__restrict__ Wim, int lw, int r0, int r1, int c0, int cw,
                                             const double *__restrict__ Pre, const double *__restrict__ Pim, int pld, int prow0,
-                                            const double *__restrict__ Ure, const double *__restrict__ Uim, int kb) {
-    const int rg = threadIdx.x % 16, cg = threadIdx.x / 16;   // 16 row groups x 16 column groups, 4x4 tiles
-    const int cbase = cg * 4;
-    if (cbase >= cw) return;
-    for (int rb = r0 + rg * 4; rb < r1; rb += 64) {
-        double ar[4][4], ai[4][4];
+                                            const double *__restrict__ Ure, const double *__restrict__ Uim) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wr = warp & 1, wc = warp >> 1;
+    const int fr = lane >> 2, fk = lane & 3;
+    if (wc * 16 >= cw) return;
+    for (int rb = r0 + wr * 32; rb < r1; rb += 64) {
+        double2 cre[4][2], cim[4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int row = min(rb + i * 8 + fr, r1 - 1);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int col = min(wc * 16 + j * 8 + 2 * fk, CW - 2);      // c0, lw even -> 16-byte aligned pair
+                const size_t o = (size_t)row * lw + c0 + col;
+                cre[i][j] = *reinterpret_cast<const double2 *>(Wre + o);
+                cim[i][j] = *reinterpret_cast<const double2 *>(Wim + o);
+            }
+        }
+        double are[4][2][2], aim[4][2][2];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) ar[i][j] = ai[i][j] = 0.0;
-        for (int kk = 0; kk < kb; ++kk) {
-            double pr[4], pi[4], ur[4], ui[4];
+            for (int j = 0; j < 2; ++j) are[i][j][0] = are[i][j][1] = aim[i][j][0] = aim[i][j][1] = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < NB; kk += 4) {
+            double pr[4], pi[4], pn[4], ur[2], ui[2];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int r = min(rb + i, r1 - 1) - prow0;
-                pr[i] = Pre[kk * pld + r];
-                pi[i] = Pim[kk * pld + r];
+                const int r = min(rb + i * 8 + fr, r1 - 1) - prow0;
+                pr[i] = Pre[(kk + fk) * pld + r];
+                pi[i] = Pim[(kk + fk) * pld + r];
+                pn[i] = -pi[i];
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                ur[j] = Ure[kk * CW + cbase + j];
-                ui[j] = Uim[kk * CW + cbase + j];
+            for (int j = 0; j < 2; ++j) {
+                ur[j] = Ure[(kk + fk) * UW + wc * 16 + j * 8 + fr];
+                ui[j] = Uim[(kk + fk) * UW + wc * 16 + j * 8 + fr];
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) cfma_sub(ar[i][j], ai[i][j], pr[i], pi[i], ur[j], ui[j]);
+                for (int j = 0; j < 2; ++j) {
+                    dmma(are[i][j][0], are[i][j][1], pr[i], ur[j]);
+                    dmma(are[i][j][0], are[i][j][1], pn[i], ui[j]);
+                    dmma(aim[i][j][0], aim[i][j][1], pr[i], ui[j]);
+                    dmma(aim[i][j][0], aim[i][j][1], pi[i], ur[j]);
+                }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (cbase + j >= cw) continue;
-            const size_t col = (size_t)(c0 + cbase + j) * ld;
+        for (int i = 0; i < 4; ++i) {
+            const int row = rb + i * 8 + fr;
+            if (row >= r1) continue;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (rb + i >= r1) continue;
-                Wre[col + rb + i] += ar[i][j];
-                Wim[col + rb + i] += ai[i][j];
+            for (int j = 0; j < 2; ++j) {
+                const int col = wc * 16 + j * 8 + 2 * fk;
+                if (col >= cw) continue;
+                const size_t o = (size_t)row * lw + c0 + col;
+                if (col + 1 < cw) {
+                    *reinterpret_cast<double2 *>(Wre + o) = make_double2(cre[i][j].x - are[i][j][0], cre[i][j].y - are[i][j][1]);
+                    *reinterpret_cast<double2 *>(Wim + o) = make_double2(cim[i][j].x - aim[i][j][0], cim[i][j].y - aim[i][j][1]);
+                } else {
+                    Wre[o] = cre[i][j].x - are[i][j][0];
+                    Wim[o] = cim[i][j].x - aim[i][j][0];
+                }
             }
         }
     }
@@ -94,44 +133,65 @@ __device__ __forceinline__ void rank_update(double *__restrict__ Wre, double *__
 
 __global__ void __launch_bounds__(NT) k_bpt_lu(const LuArgs a) {
     extern __shared__ double sm[];
-    const int n = a.n, ld = a.ld, ncols = a.ncols;
+    // working dimension n is even (a decoupled identity dof pads an odd system): every chunk start k0+kb and the first
+    // right-hand-side column are then even, which keeps the 16-byte tile accesses of the update aligned
+    const int nl = a.n, n = a.np, ld = a.ld, lw = a.lw, ncols = a.ncols;
     double *Pre = sm, *Pim = Pre + (size_t)NB * ld;           // panel [NB][ld] (column kk contiguous over rows)
-    double *Ure = Pim + (size_t)NB * ld, *Uim = Ure + NB * CW;  // chunk [NB][CW]
-    double *red = Uim + NB * CW;                                // [64]
+    double *Ure = Pim + (size_t)NB * ld, *Uim = Ure + NB * UW;  // chunk [NB][UW]
+    double *red = Uim + NB * UW;                                // [64]
     __shared__ int piv[NB];
-    __shared__ int s_arg;
+    __shared__ int sw_dst[2 * NB], sw_src[2 * NB], sw_n;   // net effect of the panel's row interchanges on the touched rows
     __shared__ int s_bad;
-    double *Wre = a.W + (size_t)blockIdx.x * 2 * (size_t)ncols * ld, *Wim = Wre + (size_t)ncols * ld;
+    // W = [M | E] row-major, planar: row swaps, the U12 solve and the tile traffic of the update are all coalesced
+    double *Wre = a.W + (size_t)blockIdx.x * 2 * (size_t)n * lw, *Wim = Wre + (size_t)n * lw;
 
+    long long tacc[6] = {0, 0, 0, 0, 0, 0}, tlast = clock64();
+#define TICK(k) do { if (a.timing && blockIdx.x == 0 && threadIdx.x == 0) { const long long _n = clock64(); tacc[k] += _n - tlast; tlast = _n; } } while (0)
     for (int iw = blockIdx.x; iw < a.nw; iw += gridDim.x) {
         const double w = a.omegas[iw];
+        TICK(5);
         // (w + i eps)^2 = w^2 - eps^2 + 2 i w eps ;  Sigma_ii = -i w/damp * mask_i  ->  M_ii += i w/damp * mask_i
         const double zr = w * w - a.eps * a.eps, zi = 2.0 * w * a.eps, sg = w / a.damp;
         __syncthreads();
         if (threadIdx.x == 0) s_bad = 0;
-        for (size_t e = threadIdx.x; e < (size_t)n * n; e += NT) {
-            const int i = (int)(e % n), j = (int)(e / n);
-            Wre[(size_t)j * ld + i] = (i == j ? zr : 0.0) - a.K[(size_t)i * n + j];
-            Wim[(size_t)j * ld + i] = i == j ? zi + sg * a.sig_mask[i] : 0.0;
-        }
-        for (size_t e = threadIdx.x; e < (size_t)a.nrhs * n; e += NT) {
-            const int i = (int)(e % n), c = (int)(e / n);
-            Wre[(size_t)(n + c) * ld + i] = a.rhs[c] == i ? 1.0 : 0.0;
-            Wim[(size_t)(n + c) * ld + i] = 0.0;
+        for (int i = threadIdx.x >> 5; i < n; i += NT / 32) {          // warp per row, lanes over columns: coalesced, 4-deep ILP
+            const double *krow = a.K + (size_t)min(i, nl - 1) * nl;
+            double *wre = Wre + (size_t)i * lw, *wim = Wim + (size_t)i * lw;
+            for (int j0 = threadIdx.x & 31; j0 < ncols; j0 += 128) {
+                double v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + 32 * u;
+                    v[u] = (j < nl && i < nl) ? krow[j] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + 32 * u;
+                    if (j < n) {
+                        wre[j] = (i == j ? (i < nl ? zr : 1.0) : 0.0) - v[u];
+                        wim[j] = (i == j && i < nl) ? zi + sg * a.sig_mask[i] : 0.0;
+                    } else if (j < ncols) {
+                        wre[j] = a.rhs[j - n] == i ? 1.0 : 0.0;
+                        wim[j] = 0.0;
+                    }
+                }
+            }
         }
         __syncthreads();
 
+        TICK(0);
         // ---------------- blocked LU, right-hand sides carried as columns n..ncols
         for (int k0 = 0; k0 < n; k0 += NB) {
             const int kb = min(NB, n - k0), m = n - k0;
-            for (int e = threadIdx.x; e < kb * m; e += NT) {
-                const int kk = e / m, i = e % m;
-                Pre[kk * ld + i] = Wre[(size_t)(k0 + kk) * ld + k0 + i];
-                Pim[kk * ld + i] = Wim[(size_t)(k0 + kk) * ld + k0 + i];
+            for (int e = threadIdx.x; e < NB * m; e += NT) {
+                const int kk = e % NB, i = e / NB;
+                const bool ok = kk < kb;
+                Pre[kk * ld + i] = ok ? Wre[(size_t)(k0 + i) * lw + k0 + kk] : 0.0;
+                Pim[kk * ld + i] = ok ? Wim[(size_t)(k0 + i) * lw + k0 + kk] : 0.0;
             }
             __syncthreads();
             for (int j = 0; j < kb; ++j) {
-                // pivot: max |re|+|im| over rows j..m (izamax convention)
+                // pivot: max |re|+|im| over rows j..m (izamax convention), ties -> smallest row
                 double best = -1.0;
                 int arg = j;
                 for (int i = j + threadIdx.x; i < m; i += NT) {
@@ -144,20 +204,20 @@ __global__ void __launch_bounds__(NT) k_bpt_lu(const LuArgs a) {
                     const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
                     if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
                 }
-                if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = best; red[32 + (threadIdx.x >> 5)] = (double)arg; }
+                double *cand = red + (j & 1) * 32;       // double-buffered: no barrier needed before the next column's writes
+                if ((threadIdx.x & 31) == 0) { cand[threadIdx.x >> 5] = best; cand[16 + (threadIdx.x >> 5)] = (double)arg; }
                 __syncthreads();
+                best = cand[0];
+                arg = (int)cand[16];
+#pragma unroll
+                for (int q = 1; q < NT / 32; ++q)
+                    if (cand[q] > best || (cand[q] == best && (int)cand[16 + q] < arg)) { best = cand[q]; arg = (int)cand[16 + q]; }
+                const int r = arg;                        // every thread derives the same pivot
                 if (threadIdx.x == 0) {
-                    double b = red[0];
-                    int ar = (int)red[32];
-                    for (int q = 1; q < NT / 32; ++q)
-                        if (red[q] > b || (red[q] == b && (int)red[32 + q] < ar)) { b = red[q]; ar = (int)red[32 + q]; }
-                    piv[j] = ar;
-                    s_arg = ar;
-                    if (!(b > 0.0)) s_bad = 1;
+                    piv[j] = r;
+                    if (!(best > 0.0)) s_bad = 1;
                 }
-                __syncthreads();
-                const int r = s_arg;
-                if (r != j && threadIdx.x < kb) {
+                if (r != j && threadIdx.x < NB) {         // swap rows j <-> r of the panel (all NB columns)
                     const int kk = threadIdx.x;
                     double t = Pre[kk * ld + j]; Pre[kk * ld + j] = Pre[kk * ld + r]; Pre[kk * ld + r] = t;
                     t = Pim[kk * ld + j]; Pim[kk * ld + j] = Pim[kk * ld + r]; Pim[kk * ld + r] = t;
@@ -166,131 +226,179 @@ __global__ void __launch_bounds__(NT) k_bpt_lu(const LuArgs a) {
                 const double dr = Pre[j * ld + j], di = Pim[j * ld + j];
                 const double dn = dr * dr + di * di;
                 const double ir = dr / dn, ii = -di / dn;    // 1/pivot
-                __syncthreads();
+                // scale column j and apply the rank-1 update to the rest of the panel; a thread owns whole rows and
+                // first gathers its row into registers so the shared-memory round trips overlap
                 for (int i = j + 1 + threadIdx.x; i < m; i += NT) {
-                    const double xr = Pre[j * ld + i], xi = Pim[j * ld + i];
-                    Pre[j * ld + i] = xr * ir - xi * ii;
-                    Pim[j * ld + i] = xr * ii + xi * ir;
-                }
-                __syncthreads();
-                const int rem = kb - 1 - j, below = m - 1 - j;
-                for (int e = threadIdx.x; e < rem * below; e += NT) {
-                    const int jj = j + 1 + e / below, i = j + 1 + e % below;
-                    double cr = Pre[jj * ld + i], ci = Pim[jj * ld + i];
-                    cfma_sub(cr, ci, Pre[j * ld + i], Pim[j * ld + i], Pre[jj * ld + j], Pim[jj * ld + j]);
-                    Pre[jj * ld + i] = cr;
-                    Pim[jj * ld + i] = ci;
+                    double vr[NB], vi[NB];
+#pragma unroll
+                    for (int jj = 0; jj < NB; ++jj) {
+                        vr[jj] = Pre[jj * ld + i];
+                        vi[jj] = Pim[jj * ld + i];
+                    }
+                    double lr = 0.0, li = 0.0;
+#pragma unroll
+                    for (int jj = 0; jj < NB; ++jj)
+                        if (jj == j) { lr = vr[jj] * ir - vi[jj] * ii; li = vr[jj] * ii + vi[jj] * ir; }
+#pragma unroll
+                    for (int jj = 0; jj < NB; ++jj) {
+                        if (jj == j) {
+                            Pre[jj * ld + i] = lr;
+                            Pim[jj * ld + i] = li;
+                        } else if (jj > j && jj < kb) {
+                            cfma_sub(vr[jj], vi[jj], lr, li, Pre[jj * ld + j], Pim[jj * ld + j]);
+                            Pre[jj * ld + i] = vr[jj];
+                            Pim[jj * ld + i] = vi[jj];
+                        }
+                    }
                 }
                 __syncthreads();
             }
-            // panel back to W (U11 / L11 / L21 needed by the back substitution and nothing else)
             for (int e = threadIdx.x; e < kb * m; e += NT) {
-                const int kk = e / m, i = e % m;
-                Wre[(size_t)(k0 + kk) * ld + k0 + i] = Pre[kk * ld + i];
-                Wim[(size_t)(k0 + kk) * ld + k0 + i] = Pim[kk * ld + i];
-            }
-            // remaining columns in chunks: row swaps, U12 = L11^-1 A12, then A22 -= L21 U12
-            for (int c0 = k0 + kb; c0 < ncols; c0 += CW) {
-                const int cw = min(CW, ncols - c0);
-                __syncthreads();
-                if (threadIdx.x < cw) {
-                    const size_t col = (size_t)(c0 + threadIdx.x) * ld + k0;
-                    for (int jj = 0; jj < kb; ++jj) {
-                        const int r = piv[jj];
-                        if (r != jj) {
-                            double t = Wre[col + jj]; Wre[col + jj] = Wre[col + r]; Wre[col + r] = t;
-                            t = Wim[col + jj]; Wim[col + jj] = Wim[col + r]; Wim[col + r] = t;
-                        }
-                    }
-                    double ur[NB], ui[NB];
-#pragma unroll
-                    for (int jj = 0; jj < NB; ++jj) {
-                        ur[jj] = jj < kb ? Wre[col + jj] : 0.0;
-                        ui[jj] = jj < kb ? Wim[col + jj] : 0.0;
-                    }
-#pragma unroll
-                    for (int jj = 0; jj < NB; ++jj) {
-#pragma unroll
-                        for (int i2 = 0; i2 < NB; ++i2)
-                            if (i2 > jj && i2 < kb && jj < kb) cfma_sub(ur[i2], ui[i2], Pre[jj * ld + i2], Pim[jj * ld + i2], ur[jj], ui[jj]);
-                    }
-#pragma unroll
-                    for (int jj = 0; jj < NB; ++jj) {
-                        if (jj < kb) {
-                            Wre[col + jj] = ur[jj];
-                            Wim[col + jj] = ui[jj];
-                        }
-                        Ure[jj * CW + threadIdx.x] = ur[jj];
-                        Uim[jj * CW + threadIdx.x] = ui[jj];
-                    }
-                }
-                __syncthreads();
-                rank_update(Wre, Wim, ld, k0 + kb, n, c0, cw, Pre, Pim, ld, k0, Ure, Uim, kb);
+                const int kk = e % kb, i = e / kb;
+                Wre[(size_t)(k0 + i) * lw + k0 + kk] = Pre[kk * ld + i];
+                Wim[(size_t)(k0 + i) * lw + k0 + kk] = Pim[kk * ld + i];
             }
             __syncthreads();
+            TICK(1);
+            // net row permutation of this panel (LAPACK laswp without the 16 dependent round trips): touched rows are the
+            // kb top rows plus the distinct pivot rows below them; sw_src[t] = original row that ends up in row sw_dst[t]
+            if (threadIdx.x == 0) {
+                int nt = kb;
+                for (int t = 0; t < kb; ++t) sw_dst[t] = sw_src[t] = t;
+                for (int jj = 0; jj < kb; ++jj) {
+                    const int r = piv[jj];
+                    int pos = -1;
+                    for (int t = 0; t < nt; ++t) if (sw_dst[t] == r) { pos = t; break; }
+                    if (pos < 0) { pos = nt++; sw_dst[pos] = sw_src[pos] = r; }
+                    const int tmp = sw_src[jj]; sw_src[jj] = sw_src[pos]; sw_src[pos] = tmp;
+                }
+                sw_n = nt;
+            }
+            __syncthreads();
+            // every remaining column (thread per column, coalesced across the warp): interchanges, then U12 = L11^-1 A12
+            for (int c = k0 + kb + threadIdx.x; c < ncols; c += NT) {
+                double *wre = Wre + (size_t)k0 * lw + c, *wim = Wim + (size_t)k0 * lw + c;
+                const int nt = sw_n;
+                double vr[2 * NB], vi[2 * NB];
+#pragma unroll
+                for (int t = 0; t < 2 * NB; ++t) {
+                    if (t < nt) {
+                        vr[t] = wre[(size_t)sw_src[t] * lw];
+                        vi[t] = wim[(size_t)sw_src[t] * lw];
+                    } else {
+                        vr[t] = vi[t] = 0.0;
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < 2 * NB; ++t)     // displaced rows below the panel
+                    if (t >= kb && t < nt && sw_dst[t] != sw_src[t]) { wre[(size_t)sw_dst[t] * lw] = vr[t]; wim[(size_t)sw_dst[t] * lw] = vi[t]; }
+                double ur[NB], ui[NB];
+#pragma unroll
+                for (int jj = 0; jj < NB; ++jj) {
+                    ur[jj] = jj < kb ? vr[jj] : 0.0;
+                    ui[jj] = jj < kb ? vi[jj] : 0.0;
+                }
+#pragma unroll
+                for (int jj = 0; jj < NB; ++jj) {
+#pragma unroll
+                    for (int i2 = 0; i2 < NB; ++i2)
+                        if (i2 > jj && i2 < kb && jj < kb) cfma_sub(ur[i2], ui[i2], Pre[jj * ld + i2], Pim[jj * ld + i2], ur[jj], ui[jj]);
+                }
+#pragma unroll
+                for (int jj = 0; jj < NB; ++jj)
+                    if (jj < kb) {
+                        wre[(size_t)jj * lw] = ur[jj];
+                        wim[(size_t)jj * lw] = ui[jj];
+                    }
+            }
+            __syncthreads();
+            TICK(2);
+            // trailing update in column chunks: A22 -= L21 U12 (also advances the carried right-hand sides)
+            for (int c0 = k0 + kb; c0 < ncols; c0 += CW) {
+                const int cw = min(CW, ncols - c0);
+                for (int e = threadIdx.x; e < NB * CW; e += NT) {
+                    const int cc = e % CW, jj = e / CW;
+                    const bool ok = cc < cw && jj < kb;
+                    Ure[jj * UW + cc] = ok ? Wre[(size_t)(k0 + jj) * lw + c0 + cc] : 0.0;
+                    Uim[jj * UW + cc] = ok ? Wim[(size_t)(k0 + jj) * lw + c0 + cc] : 0.0;
+                }
+                __syncthreads();
+                rank_update(Wre, Wim, lw, k0 + kb, n, c0, cw, Pre, Pim, ld, k0, Ure, Uim);
+                __syncthreads();
+            }
+            TICK(3);
         }
 
         // ---------------- back substitution on the right-hand sides, bottom block first, down to row_stop
         const int last = ((n - 1) / NB) * NB;
         for (int k0 = last; k0 >= 0 && k0 + NB > a.row_stop; k0 -= NB) {
             const int kb = min(NB, n - k0);
-            // U[0:k0+kb, k0:k0+kb] -> panel buffer (rows relative to 0)
+            // U[rlo:k0+kb, k0:k0+kb] -> panel buffer (rows relative to 0; only the rows still needed)
             const int rows = k0 + kb;
-            for (int e = threadIdx.x; e < kb * rows; e += NT) {
-                const int kk = e / rows, i = e % rows;
-                Pre[kk * ld + i] = Wre[(size_t)(k0 + kk) * ld + i];
-                Pim[kk * ld + i] = Wim[(size_t)(k0 + kk) * ld + i];
-            }
             const int rlo = max(0, (a.row_stop / NB) * NB);
-            for (int c0 = n; c0 < ncols; c0 += CW) {
-                const int cw = min(CW, ncols - c0);
-                __syncthreads();
-                if (threadIdx.x < cw) {
-                    const size_t col = (size_t)(c0 + threadIdx.x) * ld + k0;
-                    double xr[NB], xi[NB];
-#pragma unroll
-                    for (int jj = 0; jj < NB; ++jj) {
-                        xr[jj] = jj < kb ? Wre[col + jj] : 0.0;
-                        xi[jj] = jj < kb ? Wim[col + jj] : 0.0;
-                    }
-#pragma unroll
-                    for (int jj = NB - 1; jj >= 0; --jj) {
-                        if (jj < kb) {
-                            const double dr = Pre[jj * ld + k0 + jj], di = Pim[jj * ld + k0 + jj];
-                            const double dn = dr * dr + di * di;
-                            const double tr = (xr[jj] * dr + xi[jj] * di) / dn, ti = (xi[jj] * dr - xr[jj] * di) / dn;
-                            xr[jj] = tr; xi[jj] = ti;
-#pragma unroll
-                            for (int i2 = 0; i2 < NB; ++i2)
-                                if (i2 < jj) cfma_sub(xr[i2], xi[i2], Pre[jj * ld + k0 + i2], Pim[jj * ld + k0 + i2], tr, ti);
-                        }
-                    }
-#pragma unroll
-                    for (int jj = 0; jj < NB; ++jj) {
-                        if (jj < kb) {
-                            Wre[col + jj] = xr[jj];
-                            Wim[col + jj] = xi[jj];
-                        }
-                        Ure[jj * CW + threadIdx.x] = xr[jj];
-                        Uim[jj * CW + threadIdx.x] = xi[jj];
-                    }
-                }
-                __syncthreads();
-                if (k0 > rlo) rank_update(Wre, Wim, ld, rlo, k0, c0, cw, Pre, Pim, ld, 0, Ure, Uim, kb);
+            const int nr = rows - rlo;
+            for (int e = threadIdx.x; e < NB * nr; e += NT) {
+                const int kk = e % NB, i = rlo + e / NB;
+                const bool ok = kk < kb;
+                Pre[kk * ld + i] = ok ? Wre[(size_t)i * lw + k0 + kk] : 0.0;
+                Pim[kk * ld + i] = ok ? Wim[(size_t)i * lw + k0 + kk] : 0.0;
             }
             __syncthreads();
+            for (int c = n + threadIdx.x; c < ncols; c += NT) {    // X1 = U11^-1 Y1, thread per right-hand side
+                double *wre = Wre + (size_t)k0 * lw + c, *wim = Wim + (size_t)k0 * lw + c;
+                double xr[NB], xi[NB];
+#pragma unroll
+                for (int jj = 0; jj < NB; ++jj) {
+                    xr[jj] = jj < kb ? wre[(size_t)jj * lw] : 0.0;
+                    xi[jj] = jj < kb ? wim[(size_t)jj * lw] : 0.0;
+                }
+#pragma unroll
+                for (int jj = NB - 1; jj >= 0; --jj) {
+                    if (jj < kb) {
+                        const double dr = Pre[jj * ld + k0 + jj], di = Pim[jj * ld + k0 + jj];
+                        const double dn = dr * dr + di * di;
+                        const double tr = (xr[jj] * dr + xi[jj] * di) / dn, ti = (xi[jj] * dr - xr[jj] * di) / dn;
+                        xr[jj] = tr; xi[jj] = ti;
+#pragma unroll
+                        for (int i2 = 0; i2 < NB; ++i2)
+                            if (i2 < jj) cfma_sub(xr[i2], xi[i2], Pre[jj * ld + k0 + i2], Pim[jj * ld + k0 + i2], tr, ti);
+                    }
+                }
+#pragma unroll
+                for (int jj = 0; jj < NB; ++jj)
+                    if (jj < kb) {
+                        wre[(size_t)jj * lw] = xr[jj];
+                        wim[(size_t)jj * lw] = xi[jj];
+                    }
+            }
+            __syncthreads();
+            if (k0 > rlo) {
+                for (int c0 = n; c0 < ncols; c0 += CW) {           // Y_above -= U_above,blk X1
+                    const int cw = min(CW, ncols - c0);
+                    for (int e = threadIdx.x; e < NB * CW; e += NT) {
+                        const int cc = e % CW, jj = e / CW;
+                        const bool ok = cc < cw && jj < kb;
+                        Ure[jj * UW + cc] = ok ? Wre[(size_t)(k0 + jj) * lw + c0 + cc] : 0.0;
+                        Uim[jj * UW + cc] = ok ? Wim[(size_t)(k0 + jj) * lw + c0 + cc] : 0.0;
+                    }
+                    __syncthreads();
+                    rank_update(Wre, Wim, lw, rlo, k0, c0, cw, Pre, Pim, ld, 0, Ure, Uim);
+                    __syncthreads();
+                }
+            }
         }
 
+        TICK(4);
         // ---------------- observable
         double acc = 0.0;
         if (a.mode == 0) {
             for (int e = threadIdx.x; e < a.nrows * a.nrhs; e += NT) {
-                const int i = a.rows[e % a.nrows], c = e / a.nrows;
-                const double xr = Wre[(size_t)(n + c) * ld + i], xi = Wim[(size_t)(n + c) * ld + i];
+                const int c = e % a.nrhs, i = a.rows[e / a.nrhs];
+                const double xr = Wre[(size_t)i * lw + n + c], xi = Wim[(size_t)i * lw + n + c];
                 acc += xr * xr + xi * xi;
             }
         } else {
-            for (int c = threadIdx.x; c < a.nrhs; c += NT) acc += Wim[(size_t)(n + c) * ld + a.rhs[c]];
+            for (int c = threadIdx.x; c < a.nrhs; c += NT) acc += Wim[(size_t)a.rhs[c] * lw + n + c];
         }
         acc = block_sum(acc, red);
         if (threadIdx.x == 0) {
@@ -300,6 +408,9 @@ __global__ void __launch_bounds__(NT) k_bpt_lu(const LuArgs a) {
         }
         __syncthreads();
     }
+    if (a.timing && blockIdx.x == 0 && threadIdx.x == 0)
+        for (int k = 0; k < 6; ++k) a.timing[k] = tacc[k];
+#undef TICK
 }
 
 int run_lu(int device, int n, const double *K, const int32_t *idxL, int nL, const int32_t *idxR, int nR, double damp,
@@ -329,15 +440,18 @@ int run_lu(int device, int n, const double *K, const int32_t *idxL, int nL, cons
         row_stop = *std::min_element(rows.begin(), rows.end());
     }
     LuArgs a{};
-    a.n = n; a.ld = round_up(n, 4); a.nrhs = (int)rhs.size(); a.ncols = n + a.nrhs; a.nw = nw; a.mode = mode;
+    a.n = n; a.np = n + (n & 1); a.nrhs = (int)rhs.size(); a.ld = round_up(a.np, 16) + 4;   // ld % 16 == 4: conflict-free 64-bit DMMA fragment loads from the panel
+    if (a.ld - 16 >= a.np) a.ld -= 16;
+    a.ncols = a.np + a.nrhs; a.nw = nw; a.mode = mode;
+    a.lw = round_up(a.ncols + CW, 2);   // slack of one chunk: the update prefetches whole 64-column tiles
     a.nrows = (int)rows.size(); a.row_stop = row_stop; a.damp = damp; a.eps = 1e-9;
-    const size_t smem = ((size_t)2 * NB * a.ld + 2 * NB * CW + 64) * sizeof(double);
+    const size_t smem = ((size_t)2 * NB * a.ld + 2 * NB * UW + 64) * sizeof(double);
     SCLMD_REQUIRE(smem <= 220 * 1024, "bpt: n=%d too large for the shared-memory panel (max ~850)", n);
     const int grid = std::min(nw, 2 * sm_count(device));
     DevBuf<double> dK, dmask, dom, dwt, W, dout;
     DevBuf<int> drhs, drows, dstat;
     SCLMD_CUDA(dK.alloc((size_t)n * n)); SCLMD_CUDA(dmask.alloc(n)); SCLMD_CUDA(dom.alloc(nw)); SCLMD_CUDA(dwt.alloc(nw));
-    SCLMD_CUDA(W.alloc((size_t)grid * 2 * a.ncols * a.ld)); SCLMD_CUDA(dout.alloc(nw));
+    SCLMD_CUDA(W.alloc((size_t)grid * 2 * a.np * a.lw)); SCLMD_CUDA(dout.alloc(nw));
     SCLMD_CUDA(drhs.alloc(rhs.size())); SCLMD_CUDA(drows.alloc(rows.size())); SCLMD_CUDA(dstat.alloc(nw));
     SCLMD_CUDA(cudaMemcpy(dK.p, K, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice));
     SCLMD_CUDA(cudaMemcpy(dmask.p, mask.data(), n * sizeof(double), cudaMemcpyHostToDevice));
@@ -347,11 +461,29 @@ int run_lu(int device, int n, const double *K, const int32_t *idxL, int nL, cons
     SCLMD_CUDA(cudaMemcpy(drows.p, rows.data(), rows.size() * sizeof(int), cudaMemcpyHostToDevice));
     a.K = dK.p; a.sig_mask = dmask.p; a.rhs = drhs.p; a.rows = drows.p; a.omegas = dom.p; a.weight = dwt.p;
     a.W = W.p; a.out = dout.p; a.status = dstat.p;
+    DevBuf<long long> dtim;
+    const bool want_timing = getenv("SCLMD_BPT_TIMING") != nullptr;
+    if (want_timing) { SCLMD_CUDA(dtim.alloc(8)); a.timing = dtim.p; }
     SCLMD_CUDA(cudaFuncSetAttribute(k_bpt_lu, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEvent_t e0, e1;
+    SCLMD_CUDA(cudaEventCreate(&e0));
+    SCLMD_CUDA(cudaEventCreate(&e1));
+    SCLMD_CUDA(cudaEventRecord(e0));
     k_bpt_lu<<<grid, NT, smem>>>(a);
     SCLMD_CUDA(cudaGetLastError());
+    SCLMD_CUDA(cudaEventRecord(e1));
     SCLMD_CUDA(cudaDeviceSynchronize());
+    float kms = 0;
+    SCLMD_CUDA(cudaEventElapsedTime(&kms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (want_timing) fprintf(stderr, "[bpt] kernel %.3f ms for %d frequencies on %d CTAs (%.0f omega/s device-only)\n", kms, nw, grid, nw / (kms * 1e-3));
     SCLMD_CUDA(cudaMemcpy(out, dout.p, nw * sizeof(double), cudaMemcpyDeviceToHost));
+    if (want_timing) {
+        long long t[8];
+        SCLMD_CUDA(cudaMemcpy(t, dtim.p, sizeof(t), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[bpt timing, CTA 0 cycles] build %lld panel %lld swap+trsm %lld update %lld backsub %lld observable+loop %lld\n", t[0], t[1], t[2], t[3], t[4], t[5]);
+    }
     std::vector<int> st(nw);
     SCLMD_CUDA(cudaMemcpy(st.data(), dstat.p, nw * sizeof(int), cudaMemcpyDeviceToHost));
     for (int i = 0; i < nw; ++i)

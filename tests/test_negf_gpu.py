@@ -54,6 +54,22 @@ def test_bpt_config3_shape_vs_oracle():
     assert relerr(ps, wantps) < 1e-8
 
 
+def test_bpt_large_system_fallback_panel():
+    """n = 654 (config-4 size) exceeds the register-resident panel (n <= 512): shared-memory panel path"""
+    from sclmd_b200.negf import bpt
+    natoms = 242
+    K = P.spring_chain_dyn(natoms, seed=15) / O.RPC ** 2
+    fixed = [list(range(0, 24)), list(range(678, 726))]
+    bath = [list(range(24, 144)), list(range(558, 678))]
+    b = bpt(None, 0.25, 0.1, bath, fixed, dynmatfile=K, num=10)
+    assert len(b.dynmat) == 654
+    om = np.array([5.0, 120.7, 290.1])
+    got = b.tm_sweep(om)
+    iL, iR = O.bpt_reduce_index(bath[0], 24), O.bpt_reduce_index(bath[1], 24)
+    want = np.array([O.bpt_tm(b.dynmat, w, 0.1, iL, iR) for w in om])
+    assert np.max(np.abs(got - want)) < 1e-8 * max(1.0, np.abs(want).max())
+
+
 def test_sig_golden(golden_dir, tmp_path, monkeypatch):
     from sclmd_b200.selfenergy import sig
     monkeypatch.chdir(tmp_path)
