@@ -72,6 +72,7 @@ __device__ __forceinline__ double bath_force(const BathDev &b, int traj, int ntr
 __global__ void __launch_bounds__(256) k_phase_a(BathSet bs, int nph, int ld, int ntraj, int nmd, long long t, double dt,
                                                   const double *__restrict__ q, const double *__restrict__ p,
                                                   const double *__restrict__ G, int gsplit, size_t gstride,
+                                                  const double *__restrict__ Dcorr,
                                                   double *__restrict__ phalf, double *__restrict__ qn, double *__restrict__ etot) {
     __shared__ double red[32];
     const int traj = blockIdx.x;
@@ -84,6 +85,7 @@ __global__ void __launch_bounds__(256) k_phase_a(BathSet bs, int nph, int ld, in
         const double pi = p[row + i], qi = q[row + i];
         double gsum = G[row + i];
         for (int z = 1; z < gsplit; ++z) gsum += G[(size_t)z * gstride + row + i];   // K-slices of K.q, fixed order
+        if (Dcorr) gsum -= Dcorr[row + i];   // K.constrain(q') = K.q' - K[:,c].q'[c]
         double f = -gsum;
 #pragma unroll
         for (int b = 0; b < MAXB; ++b) {
@@ -417,6 +419,17 @@ __global__ void __launch_bounds__(256) k_tail_near(const double *__restrict__ ri
     }
 }
 
+// Kc[i][k] = K[i][cons_k]  (columns of K that multiply the constrained dofs)
+__global__ void k_gather_kc(const double *__restrict__ K, int nph, int ld, const int *__restrict__ cidx, int ncons, int ldc, double *__restrict__ Kc) {
+    const int i = blockIdx.x;
+    for (int k = threadIdx.x; k < ncons; k += blockDim.x) Kc[(size_t)i * ldc + k] = K[(size_t)i * ld + cidx[k]];
+}
+// qc[traj][k] = q'[traj][cons_k]  (values the constraint is about to zero)
+__global__ void k_gather_qc(const double *__restrict__ qn, int ld, const int *__restrict__ cidx, int ncons, int ldc, double *__restrict__ qc) {
+    const int traj = blockIdx.x;
+    for (int k = threadIdx.x; k < ncons; k += blockDim.x) qc[(size_t)traj * ldc + k] = qn[(size_t)traj * ld + cidx[k]];
+}
+
 __global__ void k_sum_slots(const double *__restrict__ cur, int nmd, int ntraj, double *__restrict__ sums) {
     const int traj = blockIdx.x * blockDim.x + threadIdx.x;
     if (traj >= ntraj) return;
@@ -438,7 +451,10 @@ struct sclmd_md {
     bool overlap = true;
     DevBuf<double> K, q, p, G, Gn, phalf, p1, qn, etot, scratch;
     DevBuf<unsigned char> cons;
-    bool has_cons = false;
+    bool has_cons = false, d_valid = false, kc_valid = false, use_corr = false;
+    int ncons = 0, ldcons = 0;
+    DevBuf<int> cidx;
+    DevBuf<double> Kc, qc, Dc;   // constraint correction: D = q'[cons] . K[:,cons]^T
     std::vector<std::unique_ptr<Bath>> baths;
     int64_t launches = 0;
     // optional per-kernel timing (CUDA events on `st` around every tail / potential-force launch)
@@ -449,7 +465,7 @@ struct sclmd_md {
     double prof_ms[4] = {0, 0, 0, 0};   // 0 direct tail, 1 potforce, 2 far pass, 3 near
     long long prof_n[4] = {0, 0, 0, 0};
     bool tail_block = true, far_tma = true;
-    SplitPlan gplan{0, 1, 0};
+    SplitPlan gplan{0, 1, 0}, cplan{0, 1, 0};
 
     void prof_begin(int kind, cudaStream_t stream = nullptr) {
         if (!profiling) return;
@@ -603,11 +619,13 @@ struct sclmd_md {
         if (!g_valid) {
             if (int e = potforce(q.p, G.p)) return e;
             g_valid = true;
+            d_valid = false;
         }
         if (lin)
             for (auto &b : baths)
                 if (b->has_lin) if (int e = bath_lin(*b, p.p, q.p)) return e;
-        k_phase_a<<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, q.p, p.p, G.p, gplan.nsplit, (size_t)ntraj * ld, phalf.p, qn.p, etot.p);
+        k_phase_a<<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, q.p, p.p, G.p, gplan.nsplit, (size_t)ntraj * ld, d_valid ? Dc.p : nullptr, phalf.p, qn.p, etot.p);
+        d_valid = false;
         SCLMD_CUDA(cudaGetLastError());
         ++launches;
         bool any_tail = false;
@@ -624,6 +642,11 @@ struct sclmd_md {
             if (int e = potforce(qn.p, Gn.p)) return e;
         }
         const unsigned char *cm = has_cons ? cons.p : nullptr;
+        if (has_cons && use_corr) {
+            k_gather_qc<<<ntraj, 128, 0, st>>>(qn.p, ld, cidx.p, ncons, ldcons, qc.p);
+            SCLMD_CUDA(cudaGetLastError());
+            ++launches;
+        }
         if (!lin) {
             k_phase_bc<<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, nullptr, phalf.p, Gn.p, gplan.nsplit, (size_t)ntraj * ld, p.p, qn.p, q.p, cm, 1, 1);
             SCLMD_CUDA(cudaGetLastError());
@@ -639,8 +662,24 @@ struct sclmd_md {
             SCLMD_CUDA(cudaGetLastError());
             launches += 2;
         }
-        if (has_cons) {
-            g_valid = false;  // q_{t+1} = constrain(q') != q'  -> K.q must be re-evaluated (md.py:449 cache miss)
+        if (has_cons && use_corr) {
+            // q_{t+1} = constrain(q') != q' (md.py:407-408), so the reference's force cache misses (md.py:449) and K.q is
+            // evaluated again.  Here: K.q_{t+1} = K.q' - K[:,cons].q'[cons], a GEMM over the constrained columns only.
+            if (!kc_valid) {
+                k_gather_kc<<<nph, 128, 0, st>>>(K.p, nph, ld, cidx.p, ncons, ldcons, Kc.p);
+                SCLMD_CUDA(cudaGetLastError());
+                kc_valid = true;
+                ++launches;
+            }
+            GemmArgs g{};
+            g.M = ntraj; g.N = nph; g.Kseg = ldcons; g.nseg = 1; g.segs_per_split = 1;
+            g.A = qc.p; g.lda = ldcons; g.B = Kc.p; g.ldb = ldcons; g.C = Dc.p; g.ldc = ld; g.alpha = 1.0;
+            SCLMD_CUDA(launch_dgemm(g, 1, st, cplan.cfg));
+            ++launches;
+            d_valid = true;
+            std::swap(G.p, Gn.p);
+        } else if (has_cons) {
+            g_valid = false;
         } else {
             std::swap(G.p, Gn.p);
         }
@@ -701,6 +740,8 @@ int sclmd_md_set_dyn(sclmd_md *h, const double *K) {
     SCLMD_CUDA(cudaStreamSynchronize(h->st));
     h->have_dyn = true;
     h->g_valid = false;
+    h->kc_valid = false;
+    h->d_valid = false;
     return SCLMD_OK;
 }
 
@@ -714,6 +755,22 @@ int sclmd_md_set_constraint(sclmd_md *h, const int32_t *idx, int n) {
     }
     SCLMD_CUDA(cudaMemcpy(h->cons.p, m.data(), h->nph, cudaMemcpyHostToDevice));
     h->has_cons = n > 0;
+    std::vector<int> uniq;
+    for (int i = 0; i < h->nph; ++i) if (m[i]) uniq.push_back(i);
+    h->ncons = (int)uniq.size();
+    h->ldcons = round_up(std::max(h->ncons, 2), 2);
+    h->use_corr = h->has_cons && 2 * h->ncons <= h->nph;   // cheaper than a second full K.q
+    h->kc_valid = false;
+    h->d_valid = false;
+    h->g_valid = false;
+    if (h->use_corr) {
+        SCLMD_CUDA(h->cidx.alloc(h->ncons));
+        SCLMD_CUDA(cudaMemcpy(h->cidx.p, uniq.data(), h->ncons * sizeof(int), cudaMemcpyHostToDevice));
+        SCLMD_CUDA(h->Kc.alloc((size_t)h->nph * h->ldcons));
+        SCLMD_CUDA(h->qc.alloc((size_t)h->ntraj * h->ldcons));
+        SCLMD_CUDA(h->Dc.alloc((size_t)h->ntraj * h->ld));
+        h->cplan = plan_split_k(h->ntraj, h->nph, h->ldcons, h->nsm, 1);
+    }
     return SCLMD_OK;
 }
 
@@ -830,7 +887,7 @@ int sclmd_md_set_state(sclmd_md *h, const double *q, const double *p, int64_t t)
         h->t = t;
         for (auto &b : h->baths) b->far_t0 = -1;
     }
-    if (q) h->g_valid = false;
+    if (q) { h->g_valid = false; h->d_valid = false; }
     return SCLMD_OK;
 }
 
