@@ -74,8 +74,9 @@ int sclmd_md_add_bath(sclmd_md *h, const int32_t *cids, int nc, int ml, const do
 int sclmd_md_set_noise(sclmd_md *h, int bath, int traj0, int ntraj_sel, const double *noise);
 int sclmd_md_get_noise(sclmd_md *h, int bath, int traj0, int ntraj_sel, double *noise);
 
-/* streaming form of the same table: rows[nslab][ntraj][nc] for time slabs
- * [slab0, slab0+nslab) mod nmd (host buffers may be pinned; one async copy per piece) */
+/* streaming form of the same table: rows[nslab][ntraj][nc] for time slabs [slab0, slab0+nslab) mod nmd.
+ * ASYNCHRONOUS (copy stream): the upload overlaps the step in flight, the next sclmd_md_run orders itself
+ * after it; `rows` must stay valid until the next synchronising call.  Use pinned host memory. */
 int sclmd_md_set_noise_rows(sclmd_md *h, int bath, int slab0, int nslab, const double *rows);
 
 /* md.p, md.q, md.t (md.py:372,411): q,p are [ntraj][nph]; NULL pointers are skipped */
@@ -88,8 +89,9 @@ int sclmd_md_reset_history(sclmd_md *h);
 int sclmd_md_get_history(sclmd_md *h, int bath, double *phis);
 int sclmd_md_set_history(sclmd_md *h, int bath, const double *phis);
 
-/* `nsteps` calls of md.vv (md.py:367-411) for every trajectory.  elapsed_ms (may be
- * NULL) receives the device time measured with CUDA events on the handle's stream. */
+/* `nsteps` calls of md.vv (md.py:367-411) for every trajectory.  With elapsed_ms != NULL the call
+ * synchronises and returns the device time measured with CUDA events on the handle's stream; with
+ * elapsed_ms == NULL it only enqueues the work (every sclmd_md_get_* synchronises). */
 int sclmd_md_run(sclmd_md *h, int64_t nsteps, float *elapsed_ms);
 
 /* bath.cur (md.py:397) and md.etot (md.py:383): [ntraj][nmd], index t % nmd */

@@ -16,6 +16,7 @@
 //   cur_b,etot  [nmd][ntraj]
 //   tailp_b     [nsplit_b][ntraj][ncp_b]   partial tails, summed in fixed order by consumers
 #include <algorithm>
+#include <cstdlib>
 #include <memory>
 
 #include "common.cuh"
@@ -319,12 +320,12 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
                  : "memory");
 }
 
-template <int T>
+template <int T, int STAGES>
 __global__ void __launch_bounds__(320, 1) k_tail_far_tma(const double *__restrict__ ring, const double *__restrict__ kern,
                                                           double *__restrict__ out, int ntraj, int ml, int ncp, int base,
                                                           int ages_per_split, double dt) {
-    extern __shared__ __align__(128) double stage_mem[];   // [2][T][TB][ncp]
-    __shared__ __align__(8) uint64_t full[2];
+    extern __shared__ __align__(128) double stage_mem[];   // [STAGES][T][TB][ncp]
+    __shared__ __align__(8) uint64_t full[STAGES];
     const int c = threadIdx.x;
     const int traj0 = blockIdx.x * T;
     const int d_lo = blockIdx.y * ages_per_split, d_hi = min(d_lo + ages_per_split, ml);
@@ -332,9 +333,9 @@ __global__ void __launch_bounds__(320, 1) k_tail_far_tma(const double *__restric
     const size_t tstride = (size_t)ml * ncp, stage_elems = (size_t)T * TB * ncp;
     const unsigned rowbytes = (unsigned)ncp * 8u;
 
-    auto issue = [&](int ch) {   // one thread: ring rows of chunk ch -> stage ch&1
-        double *dst = stage_mem + (size_t)(ch & 1) * stage_elems;
-        uint64_t *bar = &full[ch & 1];
+    auto issue = [&](int ch) {   // one thread: ring rows of chunk ch -> stage ch % STAGES
+        double *dst = stage_mem + (size_t)(ch % STAGES) * stage_elems;
+        uint64_t *bar = &full[ch % STAGES];
         mbar_expect_tx(bar, (unsigned)(T * TB) * rowbytes);
         int lo = (base - (d_lo + ch * TB) - (TB - 1)) % ml;
         if (lo < 0) lo += ml;
@@ -348,14 +349,15 @@ __global__ void __launch_bounds__(320, 1) k_tail_far_tma(const double *__restric
     };
 
     if (threadIdx.x == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
+#pragma unroll
+        for (int i = 0; i < STAGES; ++i) mbar_init(&full[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        issue(0);
-        if (nchunk > 1) issue(1);
+#pragma unroll
+        for (int i = 0; i < STAGES; ++i)
+            if (i < nchunk) issue(i);
     }
     const bool active = c < ncp;
     const int cc = active ? c : 0;
@@ -372,8 +374,8 @@ __global__ void __launch_bounds__(320, 1) k_tail_far_tma(const double *__restric
         double knew[TB];   // the 16 kernel rows the next chunk adds to the sliding window (prefetched under the math)
 #pragma unroll
         for (int i = 0; i < TB; ++i) knew[i] = kern[(size_t)(d0 + 2 + 2 * TB - 1 + i) * ncp + cc];
-        mbar_wait(&full[ch & 1], (unsigned)((ch >> 1) & 1));
-        const double *sp = stage_mem + (size_t)(ch & 1) * stage_elems + cc;
+        mbar_wait(&full[ch % STAGES], (unsigned)((ch / STAGES) & 1));
+        const double *sp = stage_mem + (size_t)(ch % STAGES) * stage_elems + cc;
 #pragma unroll
         for (int u = 0; u < TB; ++u) {
             double pv[T];
@@ -389,7 +391,7 @@ __global__ void __launch_bounds__(320, 1) k_tail_far_tma(const double *__restric
 #pragma unroll
         for (int i = 0; i < TB; ++i) kw[TB - 1 + i] = knew[i];
         __syncthreads();                            // everyone is done with this stage
-        if (threadIdx.x == 0 && ch + 2 < nchunk) issue(ch + 2);
+        if (threadIdx.x == 0 && ch + STAGES < nchunk) issue(ch + STAGES);
     }
     if (active) {
 #pragma unroll
@@ -446,6 +448,9 @@ struct sclmd_md {
     double dt = 0;
     long long t = 0;
     bool g_valid = false, have_dyn = false;
+    cudaStream_t stc = nullptr;                  // copy stream: streamed noise rows overlap the running step
+    cudaEvent_t evN = nullptr;
+    bool noise_pending = false;
     cudaStream_t st = nullptr, st2 = nullptr;   // st2: the FP64-bound K.q GEMM overlaps the HBM-bound history tails
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evG = nullptr;
     bool overlap = true;
@@ -587,14 +592,14 @@ struct sclmd_md {
             dim3 grid(cdiv(ntraj, T), b.far_nsplit, ntiles);
             prof_begin(2);
             if (b.ncp <= 320 && ntraj >= 2 && far_tma) {
-                const size_t sm = (size_t)2 * 2 * TB * b.ncp * sizeof(double);
                 static bool cfg = false;
                 if (!cfg) {
-                    SCLMD_CUDA(cudaFuncSetAttribute(k_tail_far_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                    SCLMD_CUDA(cudaFuncSetAttribute(k_tail_far_tma<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
                     cfg = true;
                 }
-                k_tail_far_tma<2><<<dim3(cdiv(ntraj, 2), b.far_nsplit), round_up(b.ncp, 32), sm, st>>>(b.ring.p, b.kern.p, b.far.p, ntraj,
-                                                                                                  b.ml, b.ncp, base, aps, dt);
+                const size_t sm = (size_t)2 * 2 * TB * b.ncp * sizeof(double);
+                k_tail_far_tma<2, 2><<<dim3(cdiv(ntraj, 2), b.far_nsplit), round_up(b.ncp, 32), sm, st>>>(b.ring.p, b.kern.p, b.far.p, ntraj,
+                                                                                                     b.ml, b.ncp, base, aps, dt);
             } else if (T == 4)
                 k_tail_far<4><<<grid, round_up(ct, 32), 0, st>>>(b.ring.p, b.kern.p, b.far.p, ntraj, b.ml, b.ncp, base, aps, ct, dt);
             else
@@ -640,6 +645,10 @@ struct sclmd_md {
         } else {
             for (auto &b : baths) if (int e = tail_step(*b, t)) return e;
             if (int e = potforce(qn.p, Gn.p)) return e;
+        }
+        if (noise_pending) {   // rows streamed by sclmd_md_set_noise_rows: evaluations B, C read slab t+1
+            SCLMD_CUDA(cudaStreamWaitEvent(st, evN, 0));
+            noise_pending = false;
         }
         const unsigned char *cm = has_cons ? cons.p : nullptr;
         if (has_cons && use_corr) {
@@ -701,6 +710,8 @@ int sclmd_md_create(int nph, int ntraj, double dt, int nmd, int device, sclmd_md
     h->nsm = sm_count(device);
     SCLMD_CUDA(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
     SCLMD_CUDA(cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking));
+    SCLMD_CUDA(cudaStreamCreateWithFlags(&h->stc, cudaStreamNonBlocking));
+    SCLMD_CUDA(cudaEventCreateWithFlags(&h->evN, cudaEventDisableTiming));
     SCLMD_CUDA(cudaEventCreateWithFlags(&h->evA, cudaEventDisableTiming));
     SCLMD_CUDA(cudaEventCreateWithFlags(&h->evG, cudaEventDisableTiming));
     SCLMD_CUDA(cudaEventCreate(&h->ev0));
@@ -726,6 +737,8 @@ int sclmd_md_destroy(sclmd_md *h) {
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->evA) cudaEventDestroy(h->evA);
     if (h->evG) cudaEventDestroy(h->evG);
+    if (h->evN) cudaEventDestroy(h->evN);
+    if (h->stc) cudaStreamDestroy(h->stc);
     if (h->st2) cudaStreamDestroy(h->st2);
     if (h->st) cudaStreamDestroy(h->st);
     delete h;
@@ -979,6 +992,7 @@ int sclmd_md_run(sclmd_md *h, int64_t nsteps, float *elapsed_ms) {
     for (int64_t s = 0; s < nsteps; ++s)
         if (int e = h->step()) return e;
     SCLMD_CUDA(cudaEventRecord(h->ev1, h->st));
+    if (!elapsed_ms && !h->profiling) return SCLMD_OK;   // asynchronous: the next sclmd_md_get_* synchronises
     SCLMD_CUDA(cudaStreamSynchronize(h->st));
     if (elapsed_ms) SCLMD_CUDA(cudaEventElapsedTime(elapsed_ms, h->ev0, h->ev1));
     h->prof_collect();
@@ -1022,16 +1036,20 @@ int sclmd_md_set_noise_rows(sclmd_md *h, int bath, int slab0, int nslab, const d
     SCLMD_CUDA(cudaSetDevice(h->device));
     Bath &b = *h->baths[bath];
     const size_t rowsz = (size_t)h->ntraj;
+    // ASYNCHRONOUS on the handle's copy stream: the upload overlaps the step that is running; the next
+    // sclmd_md_run orders itself after it.  `rows` must stay valid until the next synchronising call
+    // (sclmd_md_run with elapsed_ms != NULL, any sclmd_md_get_*).  Pinned host memory makes it a true DMA.
     int done = 0;
     while (done < nslab) {  // at most two pieces (wrap at nmd)
         const int s = (slab0 + done) % h->nmd;
         const int n = std::min(nslab - done, h->nmd - s);
         SCLMD_CUDA(cudaMemcpy2DAsync(b.noise.p + (size_t)s * rowsz * b.ncp, b.ncp * sizeof(double),
                                      rows + (size_t)done * rowsz * b.nc, b.nc * sizeof(double), b.nc * sizeof(double),
-                                     (size_t)n * rowsz, cudaMemcpyHostToDevice, h->st));
+                                     (size_t)n * rowsz, cudaMemcpyHostToDevice, h->stc));
         done += n;
     }
-    SCLMD_CUDA(cudaStreamSynchronize(h->st));
+    SCLMD_CUDA(cudaEventRecord(h->evN, h->stc));
+    h->noise_pending = true;
     return SCLMD_OK;
 }
 

@@ -144,6 +144,10 @@ class MDEngine:
         check(_lib.lib().sclmd_md_run(self._h, int(nsteps), C.byref(ms)))
         return ms.value
 
+    def run_async(self, nsteps):
+        """enqueue nsteps without waiting; any getter synchronises"""
+        check(_lib.lib().sclmd_md_run(self._h, int(nsteps), None))
+
     def current(self, bath):
         out = np.empty((self.ntraj, self.nmd))
         check(_lib.lib().sclmd_md_get_current(self._h, bath, dptr(out)))

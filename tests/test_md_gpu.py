@@ -173,6 +173,43 @@ def test_time_blocked_tails_equal_direct_tails(ml, nc, ntraj):
         e.close()
 
 
+def test_streamed_noise_rows_and_async_steps_match_resident_table():
+    """the end-to-end path of bench.py: per step, noise row t+1 uploaded from the host (asynchronously), one
+    asynchronous step, observables read back -- identical to running on a resident noise table"""
+    from sclmd_b200.engine import MDEngine
+    nph, nc, ml, ntraj, dt, nmd = 36, 8, 150, 5, 0.3, 16
+    K = P.psd_project(P.spring_chain_dyn(12, seed=3))
+    kern = P.diag_kernel(ml, nc, dt, 1)
+    nz = P.injected_noise(ntraj, nmd, nc, seed=2)
+
+    def mk():
+        e = MDEngine(nph, ntraj, dt, nmd)
+        e.set_dyn(K)
+        e.set_constraint([0, 1, 2])
+        e.add_bath(list(range(3, 3 + nc)), kern)
+        e.set_state(np.full((ntraj, nph), 0.01), np.zeros((ntraj, nph)), 0)
+        return e
+    a, b = mk(), mk()
+    a.set_noise(0, nz)
+    rows = np.ascontiguousarray(nz.transpose(1, 0, 2))           # [nmd, ntraj, nc] time-major
+    b.set_noise_rows(0, 0, rows[0:1])
+    nsteps = 40                                                  # > nmd: the table wraps
+    obs_b = []
+    for t in range(nsteps):
+        b.set_noise_rows(0, (t + 1) % nmd, rows[(t + 1) % nmd:(t + 1) % nmd + 1])
+        b.run_async(1)
+        obs_b.append(b.step_observables(t % nmd).copy())
+    a.run(nsteps)
+    qa, pa, ta = a.get_state()
+    qb, pb, tb = b.get_state()
+    assert ta == tb == nsteps and np.array_equal(qa, qb) and np.array_equal(pa, pb)
+    et, cur = a.etot(), a.current(0)
+    for t in range(nsteps - nmd, nsteps):
+        assert np.array_equal(obs_b[t][0], et[:, t % nmd]) and np.array_equal(obs_b[t][1], cur[:, t % nmd])
+    a.close()
+    b.close()
+
+
 def test_history_roundtrip_and_restart():
     """state + history saved from one engine and loaded into another continue identically
     (md.py:552-562 restart semantics)."""
