@@ -419,7 +419,15 @@ def main():
                       "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_ring, "avg_launch_ms": per,
                       "launches_timed": pa["tail_far"]["launches"], "share_of_step": pa["tail_far"]["ms"] / ms,
                       "fp64_tflops": 2.0 * 16 * w["nc"] * w["ml"] * ntraj / (per * 1e-3) / 1e12})
-    if pa["tail_direct"]["launches"]:
+    if pa["tail_direct"]["launches"] and w["kind"] == "full":
+        per = pa["tail_direct"]["ms"] / pa["tail_direct"]["launches"]
+        fl = 2.0 * (w["ml"] - 1) * w["nc"] * w["nc"] * ntraj
+        cands.append({"kernel": "dgemm_nt_seg_kernel (full memory-kernel tail over the history ring, DMMA.8x8x4, split-K)", "bound": "tensor",
+                      "achieved": fl / (per * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fl / (per * 1e-3) / 1e12 / fp64_peak,
+                      "traffic": None, "peak_source": "measured live: FP64 DMMA.8x8x4 chain probe (sclmd_probe_fp64)",
+                      "algorithmic_flops_per_launch": fl, "avg_launch_ms": per, "launches_timed": pa["tail_direct"]["launches"],
+                      "share_of_step": pa["tail_direct"]["ms"] / ms})
+    elif pa["tail_direct"]["launches"]:
         per = pa["tail_direct"]["ms"] / pa["tail_direct"]["launches"]
         cands.append({"kernel": "k_tail_diag<4> (direct history pass, every step)", "bound": "hbm",
                       "achieved": alg_ring / (per * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
