@@ -170,6 +170,13 @@ int sclmd_md_generate_noise(sclmd_md *h, int bath, sclmd_noise_plan *plan, uint6
  * transposed by the host (the interpolation indices are host-side, functions.py:117-143). */
 int sclmd_gamt(int device, int nt, int nw, int m, const double *tl, const double *wl,
                const double *giT, double *out);
+/* general form: out[nt][m] = alpha * sum_i c(tl_t, wl_i) giT[m][i] with
+ *   c = cos(w t)                                                   (eta == 0)
+ *   c = e^{-eta t}(w^2 cos wt + w eta sin wt)/(w^2 + eta^2)        (eta != 0: half of the bracket of baths.py:48-49)
+ * used for gamt with artificial damping (baths.py:43-50, alpha = 2 wl[-1]/(pi nw)) and for the re-derived
+ * gamma(w) = dt sum_t kernel(t) cos(w t) of phbath.gmem (baths.py:437-445, alpha = dt) */
+int sclmd_cos_transform(int device, int nt, int nw, int m, const double *tl, const double *wl,
+                        const double *giT, double eta, double alpha, double *out);
 
 /* ---------------------------------------------------------------- NEGF ---
  * bpt.tm over a frequency list (negf.py:104-119, 206-208, 240-242) for
@@ -183,6 +190,22 @@ int sclmd_bpt_tm(int device, int n, const double *K, const int32_t *idxL, int nL
 int sclmd_bpt_ps(int device, int n, const double *K, const int32_t *idxL, int nL,
                  const int32_t *idxR, int nR, double damp, const double *omegas, const double *nb,
                  int nw, const int32_t *sel, int nsel, double *ps_out);
+
+/* bpt with a biased electron bath (bpt.setbias, negf.py:27-37): Sigma_b^r = -i w bdamp - bias chiminus on the contiguous
+ * dof block [b0, b0+nb) (negf.py:162-172; reduced numbering), bias in angular units (eV/hbar, as bpt stores it).
+ * bdamp, chiplus, chiminus: [nb*nb]. */
+int sclmd_bpt_tm_bias(int device, int n, const double *K, const int32_t *idxL, int nL,
+                      const int32_t *idxR, int nR, double damp, int b0, int nb, const double *bdamp,
+                      const double *chiplus, const double *chiminus, double bias, const double *omegas,
+                      int nw, double *tm_out);
+/* bpt.ps with bias (negf.py:234-236): w^2 Re Tr[(G^r Sigma^K G^a)[sel,sel]] with Sigma^K = totalkselfenergy
+ * (negf.py:177-193) = kd[w] on the lead dofs + kr1[w] bdamp + kr2[w] chiplus + i ki[w] chiminus on the bias block;
+ * the per-frequency weights carry the Bose factors (bosedist edge cases stay on the host side). */
+int sclmd_bpt_ps_bias(int device, int n, const double *K, const int32_t *idxL, int nL,
+                      const int32_t *idxR, int nR, double damp, int b0, int nb, const double *bdamp,
+                      const double *chiplus, const double *chiminus, double bias, const double *omegas,
+                      const double *kd, const double *kr1, const double *kr2, const double *ki, int nw,
+                      const int32_t *sel, int nsel, double *ps_out);
 
 /* sig.selfenergy / sig.getse (selfenergy.py:105-140, 153-166): Sancho-Rubio decimation.
  *   K00,K11,K01,K10: [m*m]; direction 'L' or 'R'; se_out: [nw][m][m] interleaved complex;

@@ -249,6 +249,7 @@ def run_negf_cases():
         b.getps(300.0, 0.25, 20)
         os.chdir(cwd)
     kap = np.array([b.thermalconductance(T, 0.1) for T in (100.0, 300.0, 900.0)])
+    tm0, ps0 = np.array(b.tmnumber), np.array(b.psnumber)
     Kr = b.dynmat
     iL, iR = O.bpt_reduce_index(bath[0], 3), O.bpt_reduce_index(bath[1], 3)
     otm = np.array([O.bpt_tm(Kr, w, 0.1, iL, iR) for w in b.tmnumber[:, 0]])
@@ -256,7 +257,23 @@ def run_negf_cases():
     okap = np.array([O.thermalcurrent(b.tmnumber, T, 0.1) / (T * 0.1) for T in (100.0, 300.0, 900.0)])
     print("bpt            tm %.2e  ps %.2e  kappa %.2e" % (relerr(otm, b.tmnumber[:, 1]), relerr(ops[1:], b.psnumber[1:, 1]), relerr(okap, kap)))
     assert relerr(otm, b.tmnumber[:, 1]) < 1e-9 and relerr(okap, kap) < 1e-9
-    np.savez_compressed(os.path.join(GOLD, "bpt.npz"), tm=b.tmnumber, ps=b.psnumber, kappa=kap)
+    # biased electron bath on the 6 centre dofs 15..20 (unreduced), bias 0.6 eV  (examples/current-induced/runnegf.py:43-61)
+    bd, cp, cm = P.psd(6, 82, 2.0), P.sym(6, 83, 1.5), P.antisym(6, 84, 1.5)
+    b.setbias(0.6, bdamp=bd, chiplus=cp, chiminus=cm, dofatomofbias=list(range(15, 21)))
+    with refshim.quiet():
+        cwd = os.getcwd()
+        os.chdir("/tmp")
+        b.getps(300.0, 0.25, 20, atomlist=list(range(15, 21)), filename="bias")
+        psb = np.array(b.psnumber)
+        b.gettm()
+        tmb = np.array(b.tmnumber)
+        os.chdir(cwd)
+    with np.errstate(all="ignore"):
+        opsb = np.array([O.bpt_ps_bias(Kr, w, 300.0, 0.1, iL, iR, 12, bd, cp, cm, 0.6 / O.RPC, np.arange(12, 18)) for w in psb[:, 0]])
+        otmb = np.array([O.bpt_tm_bias(Kr, w, 300.0, 0.1, iL, iR, 12, bd, cp, cm, 0.6 / O.RPC) for w in tmb[:, 0]])
+    print("bpt (bias)     ps %.2e  tm %.2e" % (relerr(opsb[1:], psb[1:, 1]), relerr(otmb, tmb[:, 1])))
+    assert relerr(opsb[1:], psb[1:, 1]) < 1e-9 and relerr(otmb, tmb[:, 1]) < 1e-9
+    np.savez_compressed(os.path.join(GOLD, "bpt.npz"), tm=tm0, ps=ps0, kappa=kap, ps_bias=psb, tm_bias=tmb)
     # sig
     m = 4
     K00, K11, K01 = P.chain_blocks(m, seed=81)

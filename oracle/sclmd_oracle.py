@@ -495,6 +495,47 @@ def bpt_ps_nobias(K, omega, T, damp, idxL, idxR, sel):
     return float(-2 * omega ** 2 * bosedist(omega, T) * np.trace(np.imag(G[sel][:, sel])))
 
 
+def bpt_bias_matrices(K, omega, T, damp, idxL, idxR, b0, bdamp, chiplus, chiminus, bias):
+    """negf.py:153-193, 206-212 with a biased block on dofs [b0, b0+nb): returns (G^r, Sigma^K_total, G^a).
+    `bias` is in angular units (bias_eV / rpc), as bpt.setbias stores it."""
+    n = K.shape[0]
+    nb = len(bdamp)
+    sl = np.zeros((n, n), dtype=complex)
+    sr = np.zeros((n, n), dtype=complex)
+    sl[idxL, idxL] = -1j * omega / damp
+    sr[idxR, idxR] = -1j * omega / damp
+    sb = np.zeros((n, n), dtype=complex)
+    blk = slice(b0, b0 + nb)
+    sb[blk, blk] = -1j * omega * np.asarray(bdamp) - bias * np.asarray(chiminus)
+    z2 = (omega + 1e-9j) ** 2 * np.identity(n)
+    Gr = np.linalg.inv(z2 - K - sl - sr - sb)
+    Ga = np.linalg.inv(z2 - K - sl.conj().T - sr.conj().T - sb.conj().T)
+    with np.errstate(all="ignore"):
+        n0 = bosedist(omega, T)
+        semat = np.zeros((n, n), dtype=complex)
+        semat[blk, blk] = ((np.asarray(chiplus) - 1j * np.asarray(chiminus)) * (omega + bias) * (2 * bosedist(omega + bias, T) - 2 * n0)
+                           + (np.asarray(chiplus) + 1j * np.asarray(chiminus)) * (omega - bias) * (2 * bosedist(omega - bias, T) - 2 * n0)) / 2
+        sk = -2 * np.imag(sl) * n0 + -2 * np.imag(sr) * n0 + (1j * sb) * 2 * n0 + semat
+    return Gr, sk, Ga
+
+
+def bpt_ps_bias(K, omega, T, damp, idxL, idxR, b0, bdamp, chiplus, chiminus, bias, sel):
+    """negf.py:236."""
+    Gr, sk, Ga = bpt_bias_matrices(K, omega, T, damp, idxL, idxR, b0, bdamp, chiplus, chiminus, bias)
+    return float(omega ** 2 * np.trace(np.real((Gr @ sk @ Ga)[sel][:, sel])))
+
+
+def bpt_tm_bias(K, omega, T, damp, idxL, idxR, b0, bdamp, chiplus, chiminus, bias):
+    """negf.py:240-242 with retargf including the bias self-energy."""
+    Gr, _, _ = bpt_bias_matrices(K, omega, T, damp, idxL, idxR, b0, bdamp, chiplus, chiminus, bias)
+    n = K.shape[0]
+    gl = np.zeros(n)
+    gr = np.zeros(n)
+    gl[idxL] = -2.0 * omega / damp
+    gr[idxR] = -2.0 * omega / damp
+    return float(np.real(np.trace(Gr @ np.diag(gl) @ Gr.conj().T @ np.diag(gr))))
+
+
 def thermalcurrent(tmnumber, T, delta):
     """negf.py:245-270 trapezoid, nW."""
     n = len(tmnumber) - 1

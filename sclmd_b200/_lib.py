@@ -67,9 +67,12 @@ _PROTOS = {
     "sclmd_noise_plan_generate_into": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "sclmd_noise_plan_launch_count": (C.c_int64, [C.c_void_p]),
     "sclmd_md_generate_noise": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_int64]),
+    "sclmd_cos_transform": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, C.c_double, C.c_double, c_double_p]),
     "sclmd_gamt": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p]),
     "sclmd_bpt_tm": (C.c_int, [C.c_int, C.c_int, c_double_p, c_int32_p, C.c_int, c_int32_p, C.c_int, C.c_double, c_double_p, C.c_int, c_double_p]),
     "sclmd_bpt_ps": (C.c_int, [C.c_int, C.c_int, c_double_p, c_int32_p, C.c_int, c_int32_p, C.c_int, C.c_double, c_double_p, c_double_p, C.c_int, c_int32_p, C.c_int, c_double_p]),
+    "sclmd_bpt_tm_bias": (C.c_int, [C.c_int, C.c_int, c_double_p, c_int32_p, C.c_int, c_int32_p, C.c_int, C.c_double, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, C.c_double, c_double_p, C.c_int, c_double_p]),
+    "sclmd_bpt_ps_bias": (C.c_int, [C.c_int, C.c_int, c_double_p, c_int32_p, C.c_int, c_int32_p, C.c_int, C.c_double, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, C.c_double, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, C.c_int, c_int32_p, C.c_int, c_double_p]),
     "sclmd_sig_selfenergy": (C.c_int, [C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p, C.c_double, C.c_char, c_double_p, C.c_int, c_double_p, c_int32_p]),
     "sclmd_sig_tm": (C.c_int, [C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p, C.c_double, c_double_p, C.c_int, c_double_p]),
 }

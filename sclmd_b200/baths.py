@@ -19,10 +19,7 @@ def gamt(tl, wl, gwl, gam, eta_ad=0, device=0):
     """baths.py:19-52: gamma(w) -> gamma(t) by direct cosine transform on the wl grid.
 
     kernel[k] = 2*mean_i[ flinterp(wl_i, gwl, gam) cos(wl_i t_k) ] * wl[-1]/pi    (eta_ad == 0)."""
-    if eta_ad != 0:
-        raise NotImplementedError("gamt: the artificial-damping branch (eta_ad != 0, baths.py:43-50) is not ported; "
-                                  "it is outside the hot path (SURVEY.md section 8a, a11)")
-    print("eta=0")
+    print("eta=0" if eta_ad == 0 else "eta!=0")
     gam = as_f64(gam)
     wl = as_f64(wl)
     tl = as_f64(tl)
@@ -35,7 +32,11 @@ def gamt(tl, wl, gwl, gam, eta_ad=0, device=0):
         gi[i] = g2[i0] if i0 == i1 else g2[i0] + wt * (g2[i0] - g2[i1])
     giT = np.ascontiguousarray(gi.T)
     out = np.empty((len(tl), m))
-    check(_lib.lib().sclmd_gamt(device, len(tl), len(wl), m, dptr(tl), dptr(wl), dptr(giT), dptr(out)))
+    if eta_ad == 0:
+        check(_lib.lib().sclmd_gamt(device, len(tl), len(wl), m, dptr(tl), dptr(wl), dptr(giT), dptr(out)))
+    else:   # baths.py:43-50: mean over the two damped exponentials = 2 * table; times wl[-1]/pi
+        alpha = 2.0 / len(wl) * wl[-1] / np.pi
+        check(_lib.lib().sclmd_cos_transform(device, len(tl), len(wl), m, dptr(tl), dptr(wl), dptr(giT), float(eta_ad), alpha, dptr(out)))
     return out.reshape((len(tl),) + shape)
 
 
@@ -266,6 +267,16 @@ class phbath(_BathBase):
         else:
             tl = [self.dt * i for i in range(self.ml)]
             self.kernel = np.real(gamt(tl, self.wl, self.gwl, self.gamma, self.eta_ad, self.device))
+            if self.eta_ad != 0:
+                # baths.py:429-445: gamma is re-derived from the damped kernel, gamma(w_i) = dt sum_t kernel(t) cos(w_i t)
+                k2 = np.ascontiguousarray(self.kernel.reshape(self.ml, -1).T)
+                gw = as_f64(self.gwl)
+                tt = as_f64(tl)
+                out = np.empty((len(gw), k2.shape[0]))
+                check(_lib.lib().sclmd_cos_transform(self.device, len(gw), len(tt), k2.shape[0], dptr(gw), dptr(tt), dptr(k2), 0.0,
+                                                     float(self.dt), dptr(out)))
+                self.gammaOld = self.gamma
+                self.gamma = out.reshape((len(gw),) + self.kernel.shape[1:])
 
     def _engine_extra(self):
         return None, None

@@ -40,6 +40,13 @@ struct LuArgs {
     double *W;                           // [grid][2][ncols*ld]
     double *out;                         // [nw]
     int *status;                         // [nw] 0 ok, 1 singular pivot
+    // optional dense self-energy block of a biased electron bath on dofs [b0, b0+nb) (negf.py:162-190):
+    //   Sigma_b^r = -i w bdamp - bias chiminus ;  Sigma^K_b = kr1 bdamp + kr2 chiplus + i ki chiminus (per-frequency scalars)
+    int b0, nb;
+    const double *bdamp, *chiplus, *chiminus;   // [nb][nb]
+    double bias;
+    const double *kd, *kr1, *kr2, *ki;          // [nw] Keldysh weights (mode 2)
+    double *Xs;                                 // [grid][2][np][nrhs] first-pass solution (mode 2)
     long long *timing;                   // optional [8] cycle counters of CTA 0 (build, panel, trsm, update, backsub, observable)
 };
 
@@ -154,6 +161,13 @@ __global__ void __launch_bounds__(NT) k_bpt_lu(const LuArgs a) {
         const double zr = w * w - a.eps * a.eps, zi = 2.0 * w * a.eps, sg = w / a.damp;
         __syncthreads();
         if (threadIdx.x == 0) s_bad = 0;
+        // mode 2 (biased power spectrum, negf.py:236) needs G^a[:,sel] and G^r[sel,:]: two factorisations per frequency,
+        //   pass 0: M^a = z^2 - K - Sigma^r-dagger            (advanced; negf.py:210-212 keeps the +i eps of z)
+        //   pass 1: (M^r)^T                                   (rows of G^r are columns of its transpose)
+        const int npass = a.mode == 2 ? 2 : 1;
+        for (int pass = 0; pass < npass; ++pass) {
+        const double sgn = (a.mode == 2 && pass == 0) ? -1.0 : 1.0;
+        const bool tblk = a.mode == 2;
         for (int i = threadIdx.x >> 5; i < n; i += NT / 32) {          // warp per row, lanes over columns: coalesced, 4-deep ILP
             const double *krow = a.K + (size_t)min(i, nl - 1) * nl;
             double *wre = Wre + (size_t)i * lw, *wim = Wim + (size_t)i * lw;
@@ -168,8 +182,15 @@ __global__ void __launch_bounds__(NT) k_bpt_lu(const LuArgs a) {
                 for (int u = 0; u < 4; ++u) {
                     const int j = j0 + 32 * u;
                     if (j < n) {
-                        wre[j] = (i == j ? (i < nl ? zr : 1.0) : 0.0) - v[u];
-                        wim[j] = (i == j && i < nl) ? zi + sg * a.sig_mask[i] : 0.0;
+                        double mr = (i == j ? (i < nl ? zr : 1.0) : 0.0) - v[u];
+                        double mi = (i == j && i < nl) ? zi + sgn * sg * a.sig_mask[i] : 0.0;
+                        if (a.nb > 0 && i >= a.b0 && i < a.b0 + a.nb && j >= a.b0 && j < a.b0 + a.nb) {
+                            const int bi = tblk ? j - a.b0 : i - a.b0, bj = tblk ? i - a.b0 : j - a.b0;
+                            mr += a.bias * a.chiminus[bi * a.nb + bj];          // M -= Sigma_b :  +bias chi-  and  +i w bdamp
+                            mi += sgn * w * a.bdamp[bi * a.nb + bj];
+                        }
+                        wre[j] = mr;
+                        wim[j] = mi;
                     } else if (j < ncols) {
                         wre[j] = a.rhs[j - n] == i ? 1.0 : 0.0;
                         wim[j] = 0.0;
@@ -388,10 +409,41 @@ __global__ void __launch_bounds__(NT) k_bpt_lu(const LuArgs a) {
             }
         }
 
+        if (a.mode == 2 && pass == 0) {     // keep G^a[:,sel] while the second factorisation runs
+            double *xr = a.Xs + (size_t)blockIdx.x * 2 * n * a.nrhs, *xi = xr + (size_t)n * a.nrhs;
+            for (int e = threadIdx.x; e < n * a.nrhs; e += NT) {
+                const int c = e % a.nrhs, i = e / a.nrhs;
+                xr[e] = Wre[(size_t)i * lw + n + c];
+                xi[e] = Wim[(size_t)i * lw + n + c];
+            }
+            __syncthreads();
+        }
+        }   // pass
         TICK(4);
         // ---------------- observable
         double acc = 0.0;
-        if (a.mode == 0) {
+        if (a.mode == 2) {
+            // w^2 Re sum_c [G^r Sigma^K G^a]_cc  with  Z[a,c] = G^r[sel_c,a] (pass 1) and X[b,c] = G^a[b,sel_c] (pass 0)
+            const double *xr = a.Xs + (size_t)blockIdx.x * 2 * n * a.nrhs, *xi = xr + (size_t)n * a.nrhs;
+            const double kd = a.kd[iw], kr1 = a.kr1[iw], kr2 = a.kr2[iw], ki = a.ki[iw];
+            for (int e = threadIdx.x; e < nl * a.nrhs; e += NT) {          // diagonal lead part: kd * mask_a
+                const int c = e % a.nrhs, i = e / a.nrhs;
+                const double m = a.sig_mask[i];
+                if (m != 0.0) {
+                    const double zr2 = Wre[(size_t)i * lw + n + c], zi2 = Wim[(size_t)i * lw + n + c];
+                    acc += kd * m * (zr2 * xr[(size_t)i * a.nrhs + c] - zi2 * xi[(size_t)i * a.nrhs + c]);
+                }
+            }
+            for (int e = threadIdx.x; e < a.nb * a.nb * a.nrhs; e += NT) { // dense bias block
+                const int c = e % a.nrhs, ab = e / a.nrhs, ia = ab / a.nb, ib = ab % a.nb;
+                const double skr = kr1 * a.bdamp[ab] + kr2 * a.chiplus[ab], ski = ki * a.chiminus[ab];
+                const size_t ra = (size_t)(a.b0 + ia) * lw + n + c, rb = (size_t)(a.b0 + ib) * a.nrhs + c;
+                const double zr2 = Wre[ra], zi2 = Wim[ra], xr2 = xr[rb], xi2 = xi[rb];
+                // Re[ z * sk * x ]
+                const double tr = skr * xr2 - ski * xi2, ti = skr * xi2 + ski * xr2;
+                acc += zr2 * tr - zi2 * ti;
+            }
+        } else if (a.mode == 0) {
             for (int e = threadIdx.x; e < a.nrows * a.nrhs; e += NT) {
                 const int c = e % a.nrhs, i = a.rows[e / a.nrhs];
                 const double xr = Wre[(size_t)i * lw + n + c], xi = Wim[(size_t)i * lw + n + c];
@@ -403,7 +455,7 @@ __global__ void __launch_bounds__(NT) k_bpt_lu(const LuArgs a) {
         acc = block_sum(acc, red);
         if (threadIdx.x == 0) {
             const double gam = 2.0 * w / a.damp;
-            a.out[iw] = a.mode == 0 ? gam * gam * acc : -2.0 * w * w * a.weight[iw] * acc;
+            a.out[iw] = a.mode == 0 ? gam * gam * acc : (a.mode == 1 ? -2.0 * w * w * a.weight[iw] * acc : w * w * acc);
             a.status[iw] = s_bad;
         }
         __syncthreads();
@@ -413,8 +465,16 @@ __global__ void __launch_bounds__(NT) k_bpt_lu(const LuArgs a) {
 #undef TICK
 }
 
+struct BiasBlock {
+    int b0 = 0, nb = 0;
+    const double *bdamp = nullptr, *chiplus = nullptr, *chiminus = nullptr;
+    double bias = 0.0;
+    const double *kd = nullptr, *kr1 = nullptr, *kr2 = nullptr, *ki = nullptr;
+};
+
 int run_lu(int device, int n, const double *K, const int32_t *idxL, int nL, const int32_t *idxR, int nR, double damp,
-           const double *omegas, int nw, int mode, const double *weight, const int32_t *sel, int nsel, double *out) {
+           const double *omegas, int nw, int mode, const double *weight, const int32_t *sel, int nsel, double *out,
+           const BiasBlock *bb = nullptr) {
     SCLMD_REQUIRE(n > 0 && K && idxL && idxR && nL > 0 && nR > 0 && omegas && nw > 0 && out && damp != 0.0, "bpt: bad arguments");
     if (int e = select_device(device)) return e;
     std::vector<double> mask(n, 0.0);
@@ -433,12 +493,20 @@ int run_lu(int device, int n, const double *K, const int32_t *idxL, int nL, cons
         rows.assign(idxR, idxR + nR);
         row_stop = *std::min_element(rows.begin(), rows.end());
     } else {
-        SCLMD_REQUIRE(sel && nsel > 0 && weight, "bpt.ps: empty selection");
+        SCLMD_REQUIRE(sel && nsel > 0 && (weight || mode == 2), "bpt.ps: empty selection");
         for (int i = 0; i < nsel; ++i) SCLMD_REQUIRE(sel[i] >= 0 && sel[i] < n, "bpt.ps: selected dof %d out of range", sel[i]);
         rhs.assign(sel, sel + nsel);
         rows = rhs;
         row_stop = *std::min_element(rows.begin(), rows.end());
+        if (mode == 2) {   // the Keldysh self-energy lives on the lead dofs and on the bias block: those rows of both solutions
+            row_stop = 0;
+            for (int i = 0; i < n; ++i) if (mask[i] != 0.0) { row_stop = i; break; }
+            if (bb && bb->nb > 0) row_stop = std::min(row_stop, bb->b0);
+        }
     }
+    if (bb && bb->nb > 0)
+        SCLMD_REQUIRE(bb->b0 >= 0 && bb->b0 + bb->nb <= n && bb->bdamp && bb->chiminus && bb->chiplus, "bpt: bad bias block");
+    SCLMD_REQUIRE(mode != 2 || (bb && bb->nb > 0 && bb->kd && bb->kr1 && bb->kr2 && bb->ki), "bpt.ps (biased): missing Keldysh weights");
     LuArgs a{};
     a.n = n; a.np = n + (n & 1); a.nrhs = (int)rhs.size(); a.ld = round_up(a.np, 16) + 4;   // ld % 16 == 4: conflict-free 64-bit DMMA fragment loads from the panel
     if (a.ld - 16 >= a.np) a.ld -= 16;
@@ -461,6 +529,25 @@ int run_lu(int device, int n, const double *K, const int32_t *idxL, int nL, cons
     SCLMD_CUDA(cudaMemcpy(drows.p, rows.data(), rows.size() * sizeof(int), cudaMemcpyHostToDevice));
     a.K = dK.p; a.sig_mask = dmask.p; a.rhs = drhs.p; a.rows = drows.p; a.omegas = dom.p; a.weight = dwt.p;
     a.W = W.p; a.out = dout.p; a.status = dstat.p;
+    DevBuf<double> dbd, dcp, dcm, dkw, dXs;
+    if (bb && bb->nb > 0) {
+        const size_t n2 = (size_t)bb->nb * bb->nb;
+        SCLMD_CUDA(dbd.alloc(n2)); SCLMD_CUDA(dcp.alloc(n2)); SCLMD_CUDA(dcm.alloc(n2));
+        SCLMD_CUDA(cudaMemcpy(dbd.p, bb->bdamp, n2 * sizeof(double), cudaMemcpyHostToDevice));
+        SCLMD_CUDA(cudaMemcpy(dcp.p, bb->chiplus, n2 * sizeof(double), cudaMemcpyHostToDevice));
+        SCLMD_CUDA(cudaMemcpy(dcm.p, bb->chiminus, n2 * sizeof(double), cudaMemcpyHostToDevice));
+        a.b0 = bb->b0; a.nb = bb->nb; a.bdamp = dbd.p; a.chiplus = dcp.p; a.chiminus = dcm.p; a.bias = bb->bias;
+        if (mode == 2) {
+            SCLMD_CUDA(dkw.alloc((size_t)4 * nw));
+            SCLMD_CUDA(cudaMemcpy(dkw.p, bb->kd, nw * sizeof(double), cudaMemcpyHostToDevice));
+            SCLMD_CUDA(cudaMemcpy(dkw.p + nw, bb->kr1, nw * sizeof(double), cudaMemcpyHostToDevice));
+            SCLMD_CUDA(cudaMemcpy(dkw.p + 2 * (size_t)nw, bb->kr2, nw * sizeof(double), cudaMemcpyHostToDevice));
+            SCLMD_CUDA(cudaMemcpy(dkw.p + 3 * (size_t)nw, bb->ki, nw * sizeof(double), cudaMemcpyHostToDevice));
+            a.kd = dkw.p; a.kr1 = dkw.p + nw; a.kr2 = dkw.p + 2 * (size_t)nw; a.ki = dkw.p + 3 * (size_t)nw;
+            SCLMD_CUDA(dXs.alloc((size_t)grid * 2 * a.np * a.nrhs));
+            a.Xs = dXs.p;
+        }
+    }
     DevBuf<long long> dtim;
     const bool want_timing = getenv("SCLMD_BPT_TIMING") != nullptr;
     if (want_timing) { SCLMD_CUDA(dtim.alloc(8)); a.timing = dtim.p; }
@@ -506,6 +593,28 @@ int sclmd_bpt_tm(int device, int n, const double *K, const int32_t *idxL, int nL
 int sclmd_bpt_ps(int device, int n, const double *K, const int32_t *idxL, int nL, const int32_t *idxR, int nR, double damp,
                  const double *omegas, const double *nb, int nw, const int32_t *sel, int nsel, double *ps_out) {
     return run_lu(device, n, K, idxL, nL, idxR, nR, damp, omegas, nw, 1, nb, sel, nsel, ps_out);
+}
+
+// bpt.tm with a biased electron bath attached (bpt.setbias, negf.py:27-37): G includes Sigma_b^r = -i w bdamp - bias chiminus
+// on the contiguous dof block [b0, b0+nb) (negf.py:162-172); bias in angular units (eV/hbar, as bpt stores it)
+int sclmd_bpt_tm_bias(int device, int n, const double *K, const int32_t *idxL, int nL, const int32_t *idxR, int nR, double damp,
+                      int b0, int nb, const double *bdamp, const double *chiplus, const double *chiminus, double bias,
+                      const double *omegas, int nw, double *tm_out) {
+    BiasBlock bb;
+    bb.b0 = b0; bb.nb = nb; bb.bdamp = bdamp; bb.chiplus = chiplus; bb.chiminus = chiminus; bb.bias = bias;
+    return run_lu(device, n, K, idxL, nL, idxR, nR, damp, omegas, nw, 0, nullptr, nullptr, 0, tm_out, &bb);
+}
+
+// bpt.ps with bias (negf.py:234-236): w^2 Re Tr[(G^r Sigma^K G^a)[sel,sel]], Sigma^K = totalkselfenergy (negf.py:177-193)
+//   = kd(w) on the lead dofs (kd = (2w/damp) n_B) + kr1 bdamp + kr2 chiplus + i ki chiminus on the bias block
+int sclmd_bpt_ps_bias(int device, int n, const double *K, const int32_t *idxL, int nL, const int32_t *idxR, int nR, double damp,
+                      int b0, int nb, const double *bdamp, const double *chiplus, const double *chiminus, double bias,
+                      const double *omegas, const double *kd, const double *kr1, const double *kr2, const double *ki, int nw,
+                      const int32_t *sel, int nsel, double *ps_out) {
+    BiasBlock bb;
+    bb.b0 = b0; bb.nb = nb; bb.bdamp = bdamp; bb.chiplus = chiplus; bb.chiminus = chiminus; bb.bias = bias;
+    bb.kd = kd; bb.kr1 = kr1; bb.kr2 = kr2; bb.ki = ki;
+    return run_lu(device, n, K, idxL, nL, idxR, nR, damp, omegas, nw, 2, nullptr, sel, nsel, ps_out, &bb);
 }
 
 }  // extern "C"

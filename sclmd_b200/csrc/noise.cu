@@ -466,12 +466,21 @@ bool make_fft_plan(int n, FftPlan &pl) {
     return m == 1 && pl.npass <= 24;
 }
 
-// gamt (baths.py:35-42): C[t][i] = cos(wl_i * tl_t)
-__global__ void k_cos_table(const double *__restrict__ tl, const double *__restrict__ wl, int nt, int nw, int nwp, double *__restrict__ C) {
+// gamt (baths.py:35-50): C[t][i] = cos(w_i t)                                                    (eta == 0, baths.py:40)
+//                       or  Re[ w/(w - i eta) e^{-i w t - eta t} + w/(w + i eta) e^{+i w t - eta t} ]/2   (eta != 0, baths.py:48-49)
+//                         = e^{-eta t} (w^2 cos wt + w eta sin wt)/(w^2 + eta^2)
+__global__ void k_cos_table(const double *__restrict__ tl, const double *__restrict__ wl, int nt, int nw, int nwp, double eta,
+                            double *__restrict__ C) {
     const size_t n = (size_t)nt * nwp;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
         const int i = (int)(e % nwp), t = (int)(e / nwp);
-        C[e] = i < nw ? cos(wl[i] * tl[t]) : 0.0;
+        double v = 0.0;
+        if (i < nw) {
+            const double w = wl[i], tt = tl[t];
+            if (eta == 0.0) v = cos(w * tt);
+            else v = exp(-eta * tt) * (w * w * cos(w * tt) + w * eta * sin(w * tt)) / (w * w + eta * eta);
+        }
+        C[e] = v;
     }
 }
 
@@ -753,8 +762,10 @@ int sclmd_noise_plan_dims(sclmd_noise_plan *pl, int *nmd, int *nc) {
     return SCLMD_OK;
 }
 
-int sclmd_gamt(int device, int nt, int nw, int m, const double *tl, const double *wl, const double *giT, double *out) {
-    SCLMD_REQUIRE(nt > 0 && nw > 0 && m > 0 && tl && wl && giT && out, "sclmd_gamt: bad arguments");
+// out[nt][m] = alpha * sum_i table(tl_t, wl_i; eta) * giT[m][i]
+int sclmd_cos_transform(int device, int nt, int nw, int m, const double *tl, const double *wl, const double *giT, double eta,
+                        double alpha, double *out) {
+    SCLMD_REQUIRE(nt > 0 && nw > 0 && m > 0 && tl && wl && giT && out, "sclmd_cos_transform: bad arguments");
     if (int e = select_device(device)) return e;
     const int nwp = round_up(nw, 2);
     DevBuf<double> dtl, dwl, C, B, O;
@@ -764,16 +775,21 @@ int sclmd_gamt(int device, int nt, int nw, int m, const double *tl, const double
     SCLMD_CUDA(cudaMemcpy(dtl.p, tl, nt * sizeof(double), cudaMemcpyHostToDevice));
     SCLMD_CUDA(cudaMemcpy(dwl.p, wl, nw * sizeof(double), cudaMemcpyHostToDevice));
     SCLMD_CUDA(cudaMemcpy2D(B.p, nwp * sizeof(double), giT, nw * sizeof(double), nw * sizeof(double), m, cudaMemcpyHostToDevice));
-    k_cos_table<<<std::min(4096, cdiv(nt * nwp, 256)), 256>>>(dtl.p, dwl.p, nt, nw, nwp, C.p);
+    k_cos_table<<<std::min(4096, cdiv(nt * nwp, 256)), 256>>>(dtl.p, dwl.p, nt, nw, nwp, eta, C.p);
     SCLMD_CUDA(cudaGetLastError());
     GemmArgs g{};
     g.M = nt; g.N = m; g.Kseg = nwp; g.nseg = 1; g.segs_per_split = 1;
     g.A = C.p; g.lda = nwp; g.B = B.p; g.ldb = nwp; g.C = O.p; g.ldc = mp;
-    g.alpha = 2.0 / nw * wl[nw - 1] / 3.14159265358979323846;   // 2*mean(...)*wl[-1]/pi
+    g.alpha = alpha;
     SCLMD_CUDA(launch_dgemm(g, 1, 0));
     SCLMD_CUDA(cudaDeviceSynchronize());
     SCLMD_CUDA(cudaMemcpy2D(out, m * sizeof(double), O.p, mp * sizeof(double), m * sizeof(double), nt, cudaMemcpyDeviceToHost));
     return SCLMD_OK;
+}
+
+int sclmd_gamt(int device, int nt, int nw, int m, const double *tl, const double *wl, const double *giT, double *out) {
+    SCLMD_REQUIRE(nw > 0 && wl, "sclmd_gamt: bad arguments");
+    return sclmd_cos_transform(device, nt, nw, m, tl, wl, giT, 0.0, 2.0 / nw * wl[nw - 1] / 3.14159265358979323846, out);   // 2*mean(...)*wl[-1]/pi
 }
 
 }  // extern "C"

@@ -27,7 +27,39 @@ class bpt:
         self.getdynmat(infile)
 
     def setbias(self, bias, bdamp=None, chiplus=None, chiminus=None, dofatomofbias=[]):
-        raise NotImplementedError("bpt.setbias: the biased self-energies (negf.py:162-193) are not part of this build yet")
+        """negf.py:27-37: attach a biased electron bath on the contiguous block dofatomofbias[0]..dofatomofbias[-1]"""
+        np.seterr(divide='ignore', invalid='ignore')
+        self.isbias = True
+        self.bias = bias / self.rpc
+        self.biasgamma = bdamp
+        self.chiplus = chiplus
+        self.chiminus = chiminus
+        self.dofatomofbias = list(dofatomofbias)
+        if len(self.biasgamma) != len(self.chiminus) or len(self.biasgamma) != len(self.chiplus) or \
+                len(self.biasgamma) != len(self.dofatomofbias):
+            raise ValueError('Bias parameters not set correctly')
+
+    def _bias_block(self):
+        t1, t2 = self.dofatomofbias[0], self.dofatomofbias[-1] + 1          # negf.py:165-166
+        b0 = t1 - len(self.dofatomfixed[0])
+        nb = t2 - t1
+        mats = [as_f64(np.ascontiguousarray(m), (nb, nb)) for m in (self.biasgamma, self.chiplus, self.chiminus)]
+        return b0, nb, mats
+
+    def _keldysh_weights(self, om, T):
+        """per-frequency scalars of totalkselfenergy (negf.py:177-193), Bose factors evaluated with bpt.bosedist"""
+        kd, kr1, kr2, ki = (np.zeros(len(om)) for _ in range(4))
+        b = self.bias
+        with np.errstate(all="ignore"):
+            for i, w in enumerate(om):
+                n0 = float(self.bosedist(w, T))
+                cp = (w + b) * (2 * float(self.bosedist(w + b, T)) - 2 * n0)
+                cm = (w - b) * (2 * float(self.bosedist(w - b, T)) - 2 * n0)
+                kd[i] = 2.0 * w / self.damp * n0
+                kr1[i] = w * 2 * n0
+                kr2[i] = (cp + cm) / 2
+                ki[i] = -b * 2 * n0 + (cm - cp) / 2
+        return kd, kr1, kr2, ki
 
     def getdynmat(self, infile):
         """negf.py:39-102 without the LAMMPS dependency: the dynamical matrix comes from
@@ -74,6 +106,12 @@ class bpt:
         om = as_f64(omegas)
         iL, iR = self._reduced(self.dofatomofbath[0]), self._reduced(self.dofatomofbath[1])
         out = np.empty(len(om))
+        if self.isbias:
+            b0, nb, (bd, cp, cm) = self._bias_block()
+            check(_lib.lib().sclmd_bpt_tm_bias(self.device, len(self.dynmat), dptr(self.dynmat), iptr(iL), len(iL), iptr(iR), len(iR),
+                                               float(self.damp), b0, nb, dptr(bd), dptr(cp), dptr(cm), float(self.bias), dptr(om),
+                                               len(om), dptr(out)))
+            return out
         check(_lib.lib().sclmd_bpt_tm(self.device, len(self.dynmat), dptr(self.dynmat), iptr(iL), len(iL), iptr(iR), len(iR),
                                       float(self.damp), dptr(om), len(om), dptr(out)))
         return out
@@ -91,15 +129,22 @@ class bpt:
         om = as_f64(omegas)
         sel = self._reduced(atomlist)
         iL, iR = self._reduced(self.dofatomofbath[0]), self._reduced(self.dofatomofbath[1])
+        out = np.empty(len(om))
+        if self.isbias:   # negf.py:234-236
+            b0, nbk, (bd, cp, cm) = self._bias_block()
+            kd, kr1, kr2, ki = self._keldysh_weights(om, T)
+            check(_lib.lib().sclmd_bpt_ps_bias(self.device, len(self.dynmat), dptr(self.dynmat), iptr(iL), len(iL), iptr(iR), len(iR),
+                                               float(self.damp), b0, nbk, dptr(bd), dptr(cp), dptr(cm), float(self.bias), dptr(om),
+                                               dptr(kd), dptr(kr1), dptr(kr2), dptr(ki), len(om), iptr(sel), len(sel), dptr(out)))
+            return out
         with np.errstate(all="ignore"):
             nb = np.array([float(self.bosedist(w, T)) for w in om])
-        out = np.empty(len(om))
         check(_lib.lib().sclmd_bpt_ps(self.device, len(self.dynmat), dptr(self.dynmat), iptr(iL), len(iL), iptr(iR), len(iR),
                                       float(self.damp), dptr(om), dptr(nb), len(om), iptr(sel), len(sel), dptr(out)))
         return out
 
     def ps(self, omega, T, atomlist):
-        """negf.py:228-232 (unbiased)"""
+        """negf.py:228-238"""
         return float(self.ps_sweep(np.array([omega], dtype=float), T, atomlist)[0])
 
     def getps(self, T, maxomega, intnum, atomlist=None, filename=None, vector=False, omegalist=None):

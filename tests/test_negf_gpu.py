@@ -35,6 +35,32 @@ def test_bpt_golden(golden_dir, tmp_path, monkeypatch):
     assert abs(b.tm(0.0)) < 1e-20                                      # Gamma ~ w -> T(0) = 0
 
 
+def test_bpt_with_biased_electron_bath(golden_dir, tmp_path, monkeypatch):
+    """bpt.setbias + getps/gettm (examples/current-induced/runnegf.py flow) against the reference's golden numbers"""
+    from sclmd_b200.negf import bpt
+    monkeypatch.chdir(tmp_path)
+    g = np.load(os.path.join(golden_dir, "bpt.npz"))
+    K = P.spring_chain_dyn(12, seed=80) / O.RPC ** 2
+    fixed = [list(range(0, 3)), list(range(33, 36))]
+    bath = [list(range(3, 12)), list(range(24, 33))]
+    b = bpt(None, 0.25, 0.1, bath, fixed, dynmatfile=K, num=20)
+    bd, cp, cm = P.psd(6, 82, 2.0), P.sym(6, 83, 1.5), P.antisym(6, 84, 1.5)
+    with pytest.raises(ValueError):
+        b.setbias(0.6, bdamp=bd, chiplus=cp, chiminus=cm, dofatomofbias=list(range(15, 20)))
+    b.setbias(0.6, bdamp=bd, chiplus=cp, chiminus=cm, dofatomofbias=list(range(15, 21)))
+    b.getps(300.0, 0.25, 20, atomlist=list(range(15, 21)), filename="bias")
+    assert relerr(b.psnumber[1:, 1], g["ps_bias"][1:, 1]) < 1e-8
+    b.gettm()
+    assert relerr(b.tmnumber[:, 1], g["tm_bias"][:, 1]) < 1e-8
+    # zero bias keeps the block damping but no nonequilibrium terms
+    b.setbias(0.0, bdamp=bd, chiplus=cp, chiminus=cm, dofatomofbias=list(range(15, 21)))
+    om = np.array([17.0, 88.0, 250.0])
+    got = b.ps_sweep(om, 300.0, list(range(15, 21)))
+    iL, iR = O.bpt_reduce_index(bath[0], 3), O.bpt_reduce_index(bath[1], 3)
+    want = np.array([O.bpt_ps_bias(b.dynmat, w, 300.0, 0.1, iL, iR, 12, bd, cp, cm, 0.0, np.arange(12, 18)) for w in om])
+    assert relerr(got, want) < 1e-8
+
+
 def test_bpt_config3_shape_vs_oracle():
     """n = 483 (examples/runnegf.py shape): Gamma on 150 + 150 dofs, several panels, pivoting"""
     from sclmd_b200.negf import bpt

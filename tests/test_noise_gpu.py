@@ -149,9 +149,26 @@ def test_gamt_vs_reference_golden(golden_dir):
     wl = [0.3 * i / 40 for i in range(40)]
     tl = [0.38 * i for i in range(9)]
     assert relerr(gamt(tl, wl, gwl, gam, 0), g["gamt0"]) < 1e-12
+    assert relerr(gamt(tl, wl, gwl, gam, 0.01), g["gamt1"]) < 1e-12      # artificial damping branch (baths.py:43-50)
     # diagonal gamma, odd sizes
     out = gamt(tl[:5], wl[:33], gwl, gam[:, :1, :1], 0)
     assert relerr(out, O.gamt(tl[:5], wl[:33], gwl, gam[:, :1, :1], 0)) < 1e-12
+
+
+def test_gmem_with_artificial_damping_rederives_gamma():
+    """phbath.gmem with eta_ad != 0 (baths.py:429-445) against the reference formula evaluated with numpy"""
+    from sclmd_b200.baths import phbath
+    gwl, gam = P.gamma_grid(6, 3, 70, wmax=0.25)
+    b = phbath(300.0, [0, 1, 2], 0.06, 40, DT, 64, ml=9, gamma=gam, gwl=gwl, eta_ad=0.01)
+    b.gmem()
+    tl = [DT * i for i in range(9)]
+    kern = O.gamt(tl, b.wl, gwl, gam, 0.01)
+    assert relerr(b.kernel, kern) < 1e-12
+    want = np.zeros(gam.shape)
+    for i in range(len(gwl)):
+        for it in range(9):
+            want[i] += DT * kern[it] * np.cos(gwl[i] * tl[it])
+    assert relerr(b.gamma, want) < 1e-12 and relerr(b.gammaOld, gam) == 0
 
 
 def test_odd_nmd_is_rejected():

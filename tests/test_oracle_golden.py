@@ -143,6 +143,12 @@ def test_bpt(golden_dir):
     assert relerr(ps[1:], g["ps"][1:, 1]) < 1e-9
     kap = np.array([O.thermalcurrent(g["tm"], T, 0.1) / (T * 0.1) for T in (100.0, 300.0, 900.0)])
     assert relerr(kap, g["kappa"]) < 1e-12
+    # biased electron bath on the centre block (negf.py:162-193, 234-236)
+    bd, cp, cm = P.psd(6, 82, 2.0), P.sym(6, 83, 1.5), P.antisym(6, 84, 1.5)
+    with np.errstate(all="ignore"):
+        psb = np.array([O.bpt_ps_bias(Kr, w, 300.0, 0.1, iL, iR, 12, bd, cp, cm, 0.6 / O.RPC, np.arange(12, 18)) for w in g["ps_bias"][:, 0]])
+        tmb = np.array([O.bpt_tm_bias(Kr, w, 300.0, 0.1, iL, iR, 12, bd, cp, cm, 0.6 / O.RPC) for w in g["tm_bias"][:, 0]])
+    assert relerr(psb[1:], g["ps_bias"][1:, 1]) < 1e-9 and relerr(tmb, g["tm_bias"][:, 1]) < 1e-9
 
 
 def test_sig(golden_dir):
