@@ -178,6 +178,9 @@ int sclmd_gamt(int device, int nt, int nw, int m, const double *tl, const double
 int sclmd_cos_transform(int device, int nt, int nw, int m, const double *tl, const double *wl,
                         const double *giT, double eta, double alpha, double *out);
 
+/* The frequency sweeps keep their device workspace (batch buffers, streams) between calls; this frees it. */
+int sclmd_release_workspace(void);
+
 /* ---------------------------------------------------------------- NEGF ---
  * bpt.tm over a frequency list (negf.py:104-119, 206-208, 240-242) for
  * diagonal lead self-energies Sigma = -i w/damp on the bath dofs

@@ -1,20 +1,37 @@
-// Ballistic phonon transmission sweeps (replaces bpt.retargf / bpt.tm / bpt.ps / bpt.gettm,
-// sclmd/negf.py:104-119,153-157,206-208,228-242).
+// Ballistic phonon transmission sweeps (replaces bpt.retargf / bpt.advangf / bpt.tm / bpt.ps / bpt.gettm / bpt.getps,
+// sclmd/negf.py:104-150,153-193,206-212,228-242).
 //
-// For every frequency one CTA factorises  M(w) = (w + 1e-9 i)^2 I - K - Sigma_L(w) - Sigma_R(w)
-// (Sigma = -i w/damp on the bath dofs, negf.py:153-157) by blocked LU with partial pivoting and
-// carries the right-hand sides along as extra columns, so the trailing update also performs the
-// forward substitution.  Only the rows of G = M^-1 that the observable needs are back-substituted:
-//   tm :  T = Re Tr[G Gamma_L G^dagger Gamma_R] = (2w/damp)^2 sum_{i in R, j in L} |G_ij|^2
-//         (Gamma = -i(Sigma - Sigma^dagger) is diagonal, negf.py:214-215)  -> columns L, rows R
-//   ps :  -2 w^2 n_B Tr Im G[sel,sel]  (negf.py:232)                       -> columns sel, rows sel
+// For every frequency  M(w) = (w + 1e-9 i)^2 I - K - Sigma_L(w) - Sigma_R(w) [- Sigma_bias(w)]  is factorised by blocked LU with
+// partial pivoting, the right-hand sides (unit vectors) ride along as extra columns so the trailing update also performs the
+// forward substitution, and only the rows of G = M^-1 that the observable needs are back-substituted:
+//   tm :  T = Re Tr[G Gamma_L G^dagger Gamma_R] = (2w/damp)^2 sum_{i in R, j in L} |G_ij|^2   (Gamma diagonal, negf.py:214-215)
+//   ps :  -2 w^2 n_B Tr Im G[sel,sel]  (negf.py:232)   /   w^2 Re Tr[(G^r Sigma^K G^a)[sel,sel]]  (negf.py:236, two factorisations)
 // The reference forms two full inverses and three dense n^3 products per frequency instead.
 //
-// Layout: augmented matrix W = [M | E] column-major, planar complex (real plane, imaginary
-// plane), one scratch slot per resident CTA; CTAs loop over frequencies (persistent grid).
+// B200 design.  A rank-k update of an HBM-resident matrix moves 32 bytes per 8k flops, so k = 16 needs ~9 TB/s at the FP64 peak
+// and is HBM-bound; the factorisation is therefore organised as a BATCH of frequencies moving in lock step through
+//   k_build      M(w) and the unit columns, one pass over W
+//   k_panel      16-column sub-panel, one CTA per frequency, rows held in REGISTERS, implicit partial pivoting
+//                (rows stay with their thread; one barrier per column), pivot rows placed by the write-back
+//                and - thread per column - the swaps / U rows of the other columns of the current 64-column block
+//   k_block_trsm once per 64-column block, thread per column right of it: replay of the sub-panels' net row permutations and
+//                U12 = L11^-1 A12 (64 rows)
+//   k_gemm       complex rank-16 (panel columns of the block) / rank-64 (trailing matrix) update on the FP64 tensor pipe
+//                (4 real DMMA.8x8x4 per complex fragment pair), 64x64 tiles, whole K slab in shared memory
+//   k_backsub    thread per right-hand side, rows >= row_stop only
+//   k_observe    reduction to one number per frequency
+// with several batches in flight on separate streams so that the latency-bound kernels of one batch fill the tails of another.
+// The dofs are re-ordered [not needed | right-hand-side dofs | rows needed]: the unit columns are then zero in every row above
+// their own dof, and a 64x64 update tile whose U12 slab is exactly zero is skipped (bit-identical result, ~1/3 fewer flops).
+//
+// Layout: W = [M | E] row-major, planar complex (real plane, imaginary plane), nrp x lw doubles per plane (rows padded to 64,
+// columns to 64, pads zero), one slot per frequency of a batch.
 #include <algorithm>
+#include <climits>
 #include <cstdlib>
 #include <memory>
+#include <mutex>
+#include <numeric>
 
 #include "common.cuh"
 
@@ -22,32 +39,36 @@ using namespace sclmd;
 
 namespace {
 
-constexpr int NB = 16;    // panel width
-constexpr int CW = 64;    // column chunk of the trailing update
-constexpr int NT = 256;   // threads per CTA
-constexpr int UW = CW + 4; // padded row of the U chunk in shared memory (conflict-free DMMA fragment loads)
+constexpr int TS = 64;        // outer block (rank of the trailing update) and GEMM tile edge
+constexpr int NBMAX = 16;     // widest sub-panel
+constexpr int SWS = 8 + 4 * NBMAX;   // ints per swap record: [0] count, [8..) src rows, [8+2*NBMAX..) dst rows
+constexpr int MAXSUB = TS / 8;       // sub-panels per 64-column block (8- or 16-wide): one swap record each, per frequency
+constexpr int LDS_T = TS + 4; // padded shared-memory row (== 4 mod 16 doubles: conflict-free 64-bit DMMA fragment loads)
+constexpr int GK = 16, GSTG = 3, GLDA = GK + 4;                 // k_gemm: slab depth, ring stages, leading dim of the A slab
+constexpr int GSTAGE = 2 * TS * GLDA + 2 * GK * LDS_T;          // doubles per stage: Are | Aim | Bre | Bim
+constexpr size_t GEMM_SMEM = (size_t)GSTG * GSTAGE * sizeof(double);
 
-struct LuArgs {
-    int n, np, ld, lw, nrhs, ncols, nw, mode;   // mode 0 = tm, 1 = ps; ld: panel leading dim (smem), lw: leading dim of W
-    const double *K;                     // [n][n] row-major (symmetric)
-    const double *sig_mask;              // [n] number of leads touching each dof (0/1/2)
-    const int *rhs;                      // [nrhs] unit-vector index of every right-hand side
-    const int *rows;                     // tm: [nrows] rows R ; ps: unused (rows == rhs)
-    int nrows, row_stop;
-    double damp, eps;                    // eps = 1e-9 broadening
-    const double *omegas;                // [nw]
-    const double *weight;                // ps: n_B(w) per frequency; tm: unused
-    double *W;                           // [grid][2][ncols*ld]
-    double *out;                         // [nw]
-    int *status;                         // [nw] 0 ok, 1 singular pivot
-    // optional dense self-energy block of a biased electron bath on dofs [b0, b0+nb) (negf.py:162-190):
-    //   Sigma_b^r = -i w bdamp - bias chiminus ;  Sigma^K_b = kr1 bdamp + kr2 chiplus + i ki chiminus (per-frequency scalars)
-    int b0, nb;
+struct Geo {
+    int nl;      // logical dimension
+    int np;      // even working dimension (an identity dof pads an odd system)
+    int nrp;     // rows allocated (multiple of 64, plus one spare tile: update tiles start at any multiple of 8)
+    int lw;      // leading dimension (multiple of 64)
+    int nrhs, ncols;
+    size_t plane;    // nrp * lw
+};
+
+struct Problem {
+    const double *K;          // [nl][nl] permuted
+    const double *mask;       // [nl] number of leads on each dof
+    const int *rhs;           // [nrhs] row index of the 1 in every unit column
+    const int *rows;          // [nrows] rows of G entering the tm observable
+    int nrows;
+    const int *bmap;          // [nl] index inside the bias block or -1
+    const int *bpos;          // [nb] row of every bias-block dof
+    int nb;
     const double *bdamp, *chiplus, *chiminus;   // [nb][nb]
-    double bias;
-    const double *kd, *kr1, *kr2, *ki;          // [nw] Keldysh weights (mode 2)
-    double *Xs;                                 // [grid][2][np][nrhs] first-pass solution (mode 2)
-    long long *timing;                   // optional [8] cycle counters of CTA 0 (build, panel, trsm, update, backsub, observable)
+    double bias, damp, eps;
+    const double *omegas, *weight, *kd, *kr1, *kr2, *ki;   // per frequency
 };
 
 __device__ __forceinline__ void cfma_sub(double &cr, double &ci, double ar, double ai, double br, double bi) {
@@ -60,409 +81,558 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// C[rows r0..r1) x cols [c0, c0+cw)  -=  P[rows][0..NB) . U[0..NB)[cols]      (complex, planar; W row-major, leading dim lw)
-//   P in smem: Pre/Pim[kk*pld + (row - prow0)], columns kk >= kb are zero;  U in smem: Ure/Uim[kk*UW + col], rows >= kb zero.
-// FP64 tensor path: the complex product is four real DMMA.8x8x4 per fragment pair
-//   Re += Pre.Ure + (-Pim).Uim ,  Im += Pre.Uim + Pim.Ure.
-// 8 warps = 2 row groups (32 rows) x 4 column groups (16 columns): one pass covers 64 rows x 64 columns.
-// The C tile is fetched into registers BEFORE the DMMA loop (it does not depend on it): every lane has 16 independent
-// 16-byte loads per plane in flight while the tensor pipe works, so the update streams W at memory speed.
-__device__ __forceinline__ void rank_update(double *__restrict__ Wre, double *__restrict__ Wim, int lw, int r0, int r1, int c0, int cw,
-                                            const double *__restrict__ Pre, const double *__restrict__ Pim, int pld, int prow0,
-                                            const double *__restrict__ Ure, const double *__restrict__ Uim) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int wr = warp & 1, wc = warp >> 1;
-    const int fr = lane >> 2, fk = lane & 3;
-    if (wc * 16 >= cw) return;
-    for (int rb = r0 + wr * 32; rb < r1; rb += 64) {
-        double2 cre[4][2], cim[4][2];
+// ------------------------------------------------------------------------------------------------ build
+// grid (nrp, batch): one row of W per CTA.  sgn = -1 builds the advanced matrix (Sigma^r-dagger), tblk transposes the bias block
+// (mode 2: pass 0 = M^a, pass 1 = (M^r)^T; negf.py:210-212 keeps the +i eps of z in advangf).
+__global__ void __launch_bounds__(128) k_build(Geo g, Problem p, double *W, int w0, double sgn, int tblk) {
+    const int i = blockIdx.x, b = blockIdx.y;
+    const double w = p.omegas[w0 + b];
+    const double zr = w * w - p.eps * p.eps, zi = 2.0 * w * p.eps, sg = w / p.damp;
+    double *wre = W + (size_t)b * 2 * g.plane + (size_t)i * g.lw, *wim = wre + g.plane;
+    const int bi0 = (i < g.nl && p.nb > 0) ? p.bmap[i] : -1;
+    for (int j = threadIdx.x; j < g.lw; j += blockDim.x) {
+        double mr = 0.0, mi = 0.0;
+        if (i < g.np && j < g.np) {
+            if (i < g.nl && j < g.nl) {
+                mr = -p.K[(size_t)i * g.nl + j];
+                if (i == j) { mr += zr; mi = zi + sgn * sg * p.mask[i]; }
+                if (bi0 >= 0) {
+                    const int bj0 = p.bmap[j];
+                    if (bj0 >= 0) {
+                        const int bi = tblk ? bj0 : bi0, bj = tblk ? bi0 : bj0;
+                        mr += p.bias * p.chiminus[bi * p.nb + bj];      // M -= Sigma_b :  +bias chi-  and  +i w bdamp
+                        mi += sgn * w * p.bdamp[bi * p.nb + bj];
+                    }
+                }
+            } else if (i == j) {
+                mr = 1.0;
+            }
+        } else if (i < g.np && j < g.ncols) {
+            mr = p.rhs[j - g.np] == i ? 1.0 : 0.0;
+        }
+        wre[j] = mr;
+        wim[j] = mi;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ sub-panel
+// One CTA per frequency factorises columns [kk, kk+kb) over rows [kk, np).  Thread t owns rows kk + t + r*256 (r < RPT) in
+// registers.  Implicit pivoting: rows never move during the factorisation; a chosen row is frozen (it becomes a row of U), the
+// winner of each warp publishes its row next to its magnitude, so one barrier per column suffices.  The write-back places
+// pivot j at row kk+j and moves the unchosen top rows into the vacated slots; the same net permutation is recorded for
+// k_block_trsm.  Pivot rule: max |re|+|im| (izamax), ties to the smallest row.
+template <int NT, int RPT, int NBW>
+__global__ void __launch_bounds__(NT, 1) k_panel(Geo g, double *W, int *swp, int *status, int w0, int k0, int kk, int kb, int rend, int sub) {
+    constexpr int NWARP = NT / 32;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m = g.np - kk, lw = g.lw;
+    double *wre = W + (size_t)b * 2 * g.plane, *wim = wre + g.plane;
+    __shared__ double c_best[2][NWARP];
+    __shared__ int c_arg[2][NWARP];
+    __shared__ double c_row[2][NWARP][2][NBW];
+    __shared__ int s_piv[NBW], s_topdest[NBW], s_bad;
+    __shared__ int s_src[2 * NBW], s_dst[2 * NBW], s_n;
+    __shared__ double s_lr[NBW][NBW + 1], s_li[NBW][NBW + 1];      // L11 (final row order) for the in-block U rows
+
+    double ar[RPT][NBW], ai[RPT][NBW];
+    int ord[RPT];
+    bool live[RPT];      // valid row, not yet chosen as a pivot
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int row = min(rb + i * 8 + fr, r1 - 1);
+    for (int r = 0; r < RPT; ++r) {
+        const int rel = tid + r * NT;
+        live[r] = rel < m;
+        ord[r] = -1;
+        const size_t o = (size_t)(kk + min(rel, m - 1)) * lw + kk;
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int col = min(wc * 16 + j * 8 + 2 * fk, CW - 2);      // c0, lw even -> 16-byte aligned pair
-                const size_t o = (size_t)row * lw + c0 + col;
-                cre[i][j] = *reinterpret_cast<const double2 *>(Wre + o);
-                cim[i][j] = *reinterpret_cast<const double2 *>(Wim + o);
+        for (int jj = 0; jj < NBW; jj += 2) {
+            double2 vr = make_double2(0.0, 0.0), vi = vr;
+            if (live[r] && jj < kb) {          // kb is even: a pair is inside or outside the panel as a whole
+                vr = *reinterpret_cast<const double2 *>(wre + o + jj);
+                vi = *reinterpret_cast<const double2 *>(wim + o + jj);
+            }
+            ar[r][jj] = vr.x; ar[r][jj + 1] = vr.y;
+            ai[r][jj] = vi.x; ai[r][jj + 1] = vi.y;
+        }
+    }
+    if (tid == 0) s_bad = 0;
+
+#pragma unroll
+    for (int j = 0; j < NBW; ++j) {
+        if (j < kb) {
+            double best = -1.0;
+            int arg = INT_MAX;
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) {
+                const double v = fabs(ar[r][j]) + fabs(ai[r][j]);
+                if (live[r] && v > best) { best = v; arg = tid + r * NT; }
+            }
+            const double mybest = best;
+            const int myarg = arg;
+            {   // warp arg-max with three redux.sync: non-negative doubles order like their bit patterns (a NaN wins and is
+                // reported as a singular pivot below); ties go to the smallest row
+                const long long key = __double_as_longlong(best);          // -1.0 (no live row) is negative
+                const int hi = (int)(key >> 32);
+                const int mh = __reduce_max_sync(0xffffffffu, hi);
+                const unsigned lo = hi == mh ? (unsigned)(key & 0xffffffffll) : 0u;
+                const unsigned ml = __reduce_max_sync(0xffffffffu, lo);
+                const bool top = hi == mh && lo == ml && mh >= 0;
+                arg = __reduce_min_sync(0xffffffffu, top ? myarg : INT_MAX);
+                best = __longlong_as_double(((long long)mh << 32) | (long long)ml);
+            }
+            const int buf = j & 1;
+            if (arg == myarg && mybest >= 0.0) {      // this lane holds the warp's candidate: publish the rest of its row
+#pragma unroll
+                for (int r = 0; r < RPT; ++r)
+                    if (tid + r * NT == arg) {
+#pragma unroll
+                        for (int jj = j; jj < NBW; ++jj) {
+                            c_row[buf][warp][0][jj] = ar[r][jj];
+                            c_row[buf][warp][1][jj] = ai[r][jj];
+                        }
+                    }
+            }
+            if (lane == 0) { c_best[buf][warp] = best; c_arg[buf][warp] = arg; }
+            __syncthreads();
+            double wbest = c_best[buf][0];
+            int warg = c_arg[buf][0], ww = 0;
+#pragma unroll
+            for (int q = 1; q < NWARP; ++q) {
+                const double qb = c_best[buf][q];
+                const int qa = c_arg[buf][q];
+                if (qb > wbest || (qb == wbest && qa < warg)) { wbest = qb; warg = qa; ww = q; }
+            }
+            if (tid == 0) {
+                s_piv[j] = warg == INT_MAX ? j : warg;
+                if (!(wbest > 0.0)) s_bad = 1;
+            }
+            const double dr = c_row[buf][ww][0][j], di = c_row[buf][ww][1][j];
+            const double rn = 1.0 / (dr * dr + di * di);
+            const double ir = dr * rn, ii = -di * rn;          // 1 / pivot
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) {
+                if (!live[r]) continue;
+                if (tid + r * NT == warg) {
+                    live[r] = false;
+                    ord[r] = j;
+                } else {
+                    const double lr = ar[r][j] * ir - ai[r][j] * ii, li = ar[r][j] * ii + ai[r][j] * ir;
+                    ar[r][j] = lr;
+                    ai[r][j] = li;
+#pragma unroll
+                    for (int jj = j + 1; jj < NBW; ++jj)
+                        cfma_sub(ar[r][jj], ai[r][jj], lr, li, c_row[buf][ww][0][jj], c_row[buf][ww][1][jj]);
+                }
             }
         }
-        double are[4][2][2], aim[4][2][2];
+    }
+
+    // net row permutation: pivot j -> row kk+j ; unchosen top rows -> the vacated slots (any order is a valid LU as long as
+    // every remaining column follows the same permutation)
+    if (tid == 0) {
+        bool chosen[NBW];
+        int vac[NBW], nv = 0, q = 0;
+        for (int t = 0; t < NBW; ++t) chosen[t] = false;
+        for (int j = 0; j < kb; ++j) {
+            if (s_piv[j] < kb) chosen[s_piv[j]] = true;
+            else vac[nv++] = s_piv[j];
+        }
+        int cnt = kb;
+        for (int t = 0; t < kb; ++t) {
+            s_src[t] = kk + s_piv[t];
+            s_dst[t] = kk + t;
+            s_topdest[t] = -1;
+            if (!chosen[t]) {
+                s_topdest[t] = vac[q];
+                s_src[cnt] = kk + t;
+                s_dst[cnt] = kk + vac[q];
+                ++cnt;
+                ++q;
+            }
+        }
+        s_n = cnt;
+        if (s_bad) status[w0 + b] = 1;
+    }
+    __syncthreads();
+    if (tid < 2 * NBW) {          // the record k_block_trsm replays on the columns right of the block
+        int *rec = swp + ((size_t)b * MAXSUB + sub) * SWS;
+        if (tid == 0) rec[0] = s_n;
+        rec[8 + tid] = tid < s_n ? s_src[tid] : 0;
+        rec[8 + 2 * NBMAX + tid] = tid < s_n ? s_dst[tid] : 0;
+    }
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+    for (int r = 0; r < RPT; ++r) {
+        const int rel = tid + r * NT;
+        if (rel >= m) continue;
+        const int dest = ord[r] >= 0 ? ord[r] : (rel < kb ? s_topdest[rel] : rel);
+        const size_t o = (size_t)(kk + dest) * lw + kk;
 #pragma unroll
-            for (int j = 0; j < 2; ++j) are[i][j][0] = are[i][j][1] = aim[i][j][0] = aim[i][j][1] = 0.0;
+        for (int jj = 0; jj < NBW; jj += 2)
+            if (jj < kb) {
+                *reinterpret_cast<double2 *>(wre + o + jj) = make_double2(ar[r][jj], ar[r][jj + 1]);
+                *reinterpret_cast<double2 *>(wim + o + jj) = make_double2(ai[r][jj], ai[r][jj + 1]);
+            }
+        if (dest < kb) {
 #pragma unroll
-        for (int kk = 0; kk < NB; kk += 4) {
-            double pr[4], pi[4], pn[4], ur[2], ui[2];
+            for (int jj = 0; jj < NBW; ++jj) { s_lr[dest][jj] = ar[r][jj]; s_li[dest][jj] = ai[r][jj]; }
+        }
+    }
+    __syncthreads();
+    // the other columns of this 64-column block, thread per column: columns [k0, kk) (L of the earlier sub-panels) follow the
+    // row permutation; columns [kk+kb, rend) also get their U rows  U = L11^-1 A  (rows [kk, kk+kb)); k_gemm then updates
+    // them below.  Columns right of the block are handled once per block by k_block_trsm.
+    const int nleft = kk - k0, nside = nleft + (rend - kk - kb);
+    if (tid < nside) {
+        const int c = tid < nleft ? k0 + tid : kk + kb + (tid - nleft);
+        const int nt = s_n;
+        double vr[2 * NBW], vi[2 * NBW];
+#pragma unroll
+        for (int t = 0; t < 2 * NBW; ++t) {
+            vr[t] = vi[t] = 0.0;
+            if (t < nt) {
+                vr[t] = wre[(size_t)s_src[t] * lw + c];
+                vi[t] = wim[(size_t)s_src[t] * lw + c];
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 2 * NBW; ++t)
+            if (t >= kb && t < nt) {
+                wre[(size_t)s_dst[t] * lw + c] = vr[t];
+                wim[(size_t)s_dst[t] * lw + c] = vi[t];
+            }
+        if (tid >= nleft) {
+#pragma unroll
+            for (int jj = 0; jj < NBW; ++jj)
+#pragma unroll
+                for (int i2 = jj + 1; i2 < NBW; ++i2)
+                    if (i2 < kb) cfma_sub(vr[i2], vi[i2], s_lr[i2][jj], s_li[i2][jj], vr[jj], vi[jj]);
+        }
+#pragma unroll
+        for (int t = 0; t < NBW; ++t)
+            if (t < kb) {
+                wre[(size_t)(kk + t) * lw + c] = vr[t];
+                wim[(size_t)(kk + t) * lw + c] = vi[t];
+            }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ block row swaps + U12
+// Once per 64-column block, thread per column right of the block (c >= rend): replay the net row permutation of every
+// sub-panel, then  U_j = L_jj^-1 (A_j - sum_{t<j} L_jt U_t)  (left-looking over the sub-panels; the thread re-reads its own
+// earlier U rows from W).  L (64x64, strictly lower, final row order) sits in shared memory.
+template <int NBW>
+__global__ void __launch_bounds__(128) k_block_trsm(Geo g, double *W, const int *swp, int k0, int rend) {
+    extern __shared__ double sm[];
+    constexpr int LDL = TS + 1;
+    double *Lr = sm, *Li = Lr + TS * LDL;
+    __shared__ int s_src[MAXSUB][2 * NBW], s_dst[MAXSUB][2 * NBW], s_n[MAXSUB];
+    const int b = blockIdx.y, lw = g.lw, nblk = rend - k0, nsub = (nblk + NBW - 1) / NBW;
+    double *wre = W + (size_t)b * 2 * g.plane, *wim = wre + g.plane;
+    for (int e = threadIdx.x; e < nblk * nblk; e += blockDim.x) {
+        const int jj = e % nblk, i = e / nblk;
+        Lr[i * LDL + jj] = jj < i ? wre[(size_t)(k0 + i) * lw + k0 + jj] : 0.0;
+        Li[i * LDL + jj] = jj < i ? wim[(size_t)(k0 + i) * lw + k0 + jj] : 0.0;
+    }
+    for (int e = threadIdx.x; e < nsub * 2 * NBW; e += blockDim.x) {
+        const int t = e % (2 * NBW), j = e / (2 * NBW);
+        const int *rec = swp + ((size_t)b * MAXSUB + j) * SWS;
+        s_src[j][t] = rec[8 + t];
+        s_dst[j][t] = rec[8 + 2 * NBMAX + t];
+        if (t == 0) s_n[j] = rec[0];
+    }
+    __syncthreads();
+    const int c = rend + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= g.ncols) return;
+    bool seen = false;          // unit columns: nothing to do while every touched entry is still exactly zero
+    for (int j = 0; j < nsub; ++j) {
+        const int kk = k0 + j * NBW, kb = min(NBW, rend - kk), nt = s_n[j];
+        double vr[2 * NBW], vi[2 * NBW];
+        bool nz = false;
+#pragma unroll
+        for (int t = 0; t < 2 * NBW; ++t) {
+            vr[t] = vi[t] = 0.0;
+            if (t < nt) {
+                vr[t] = wre[(size_t)s_src[j][t] * lw + c];
+                vi[t] = wim[(size_t)s_src[j][t] * lw + c];
+                nz |= (vr[t] != 0.0) | (vi[t] != 0.0);
+            }
+        }
+        if (!nz && !seen) continue;
+        seen = true;
+#pragma unroll
+        for (int t = 0; t < 2 * NBW; ++t)     // displaced rows below the sub-panel's top block
+            if (t >= kb && t < nt) {
+                wre[(size_t)s_dst[j][t] * lw + c] = vr[t];
+                wim[(size_t)s_dst[j][t] * lw + c] = vi[t];
+            }
+        for (int kx0 = 0; kx0 < j * NBW; kx0 += 4) {          // pending contributions of the earlier U rows of this block
+            double ur[4], ui[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                ur[u] = wre[(size_t)(k0 + kx0 + u) * lw + c];
+                ui[u] = wim[(size_t)(k0 + kx0 + u) * lw + c];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int i = 0; i < NBW; ++i)
+                    if (i < kb) cfma_sub(vr[i], vi[i], Lr[(j * NBW + i) * LDL + kx0 + u], Li[(j * NBW + i) * LDL + kx0 + u], ur[u], ui[u]);
+        }
+#pragma unroll
+        for (int jj = 0; jj < NBW; ++jj)
+#pragma unroll
+            for (int i2 = jj + 1; i2 < NBW; ++i2)
+                if (i2 < kb)
+                    cfma_sub(vr[i2], vi[i2], Lr[(j * NBW + i2) * LDL + j * NBW + jj], Li[(j * NBW + i2) * LDL + j * NBW + jj], vr[jj], vi[jj]);
+#pragma unroll
+        for (int t = 0; t < NBW; ++t)
+            if (t < kb) {
+                wre[(size_t)(kk + t) * lw + c] = vr[t];
+                wim[(size_t)(kk + t) * lw + c] = vi[t];
+            }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ rank-K update
+// C[r0 + 64 by .. , c0 + 64 bx ..) -= A B  with  A = W[rows, ka:ka+K]  (L21)  and  B = W[ka:ka+K, cols]  (U12), K <= 64, complex planar.
+// 8 warps = 2 row groups (32 rows) x 4 column groups (16 columns); the C tile is the accumulator itself:
+//   Re += (-Ar) Br + Ai Bi ,  Im += (-Ar) Bi + (-Ai) Br      (four real DMMA.8x8x4 per fragment pair)
+// The K range is cut into 16-deep slabs moved by 16-byte cp.async through a 3-stage shared-memory ring (A as [row][k], B as
+// [k][col], both padded to a leading dimension == 4 mod 16 doubles: conflict-free 64-bit fragment loads), so the loads of the
+// next slabs and of the C tile overlap the tensor work.  Tiles in the unit-column region whose B slab is exactly zero leave C
+// unchanged and return early.
+__device__ __forceinline__ void cp_async16(double *dst, const double *src, bool pred) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
+    const int nbytes = pred ? 16 : 0;      // src-size 0: the 16 bytes are zero-filled, nothing is read
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(src), "r"(nbytes) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 2) k_gemm(Geo g, double *W, int r0, int c0, int c1, int ka, int K) {
+    extern __shared__ double sm[];
+    const int b = blockIdx.z, lw = g.lw;
+    const int tr = r0 + TS * blockIdx.y, tc = c0 + TS * blockIdx.x;
+    double *wre = W + (size_t)b * 2 * g.plane, *wim = wre + g.plane;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wr = warp & 1, wc = warp >> 1, fr = lane >> 2, fk = lane & 3;
+
+    if (tc >= g.np) {       // unit columns: skip slabs that are still exactly zero
+        int any = 0;
+        for (int e = tid; e < K * (TS / 2); e += 256) {
+            const int k = e / (TS / 2), cp = (e % (TS / 2)) * 2;
+            if (tc + cp < c1) {
+                const double2 a = *reinterpret_cast<const double2 *>(wre + (size_t)(ka + k) * lw + tc + cp);
+                const double2 c = *reinterpret_cast<const double2 *>(wim + (size_t)(ka + k) * lw + tc + cp);
+                any |= (a.x != 0.0) | (a.y != 0.0) | (c.x != 0.0) | (c.y != 0.0);
+            }
+        }
+        if (!__syncthreads_or(any)) return;
+    }
+
+    const int nslab = (K + GK - 1) / GK;
+    auto issue = [&](int slab) {
+        double *st = sm + (size_t)(slab % GSTG) * GSTAGE;
+        const int kc = slab * GK;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {          // A: 2 planes x 64 rows x 8 chunks
+            const int e = tid + u * 256, pl = e >> 9, r = (e >> 3) & 63, kp = (e & 7) * 2;
+            const bool ok = kc + kp < K;
+            const double *src = (pl ? wim : wre) + (size_t)(tr + r) * lw + ka + (ok ? kc + kp : 0);
+            cp_async16(st + pl * (TS * GLDA) + r * GLDA + kp, src, ok);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {          // B: 2 planes x 16 k x 32 chunks
+            const int e = tid + u * 256, pl = e >> 9, k = (e >> 5) & 15, cp = (e & 31) * 2;
+            const bool ok = kc + k < K && tc + cp < c1;
+            const double *src = (pl ? wim : wre) + (size_t)(ka + (ok ? kc + k : 0)) * lw + (ok ? tc + cp : tc);
+            cp_async16(st + 2 * (TS * GLDA) + pl * (GK * LDS_T) + k * LDS_T + cp, src, ok);
+        }
+    };
+#pragma unroll
+    for (int s0 = 0; s0 < GSTG - 1; ++s0) {
+        if (s0 < nslab) issue(s0);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+
+    double2 cre[4][2], cim[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int row = tr + wr * 32 + i * 8 + fr, col = tc + wc * 16 + j * 8 + 2 * fk;
+            cre[i][j] = cim[i][j] = make_double2(0.0, 0.0);
+            if (col < c1) {
+                cre[i][j] = *reinterpret_cast<const double2 *>(wre + (size_t)row * lw + col);
+                cim[i][j] = *reinterpret_cast<const double2 *>(wim + (size_t)row * lw + col);
+            }
+        }
+
+    for (int sl = 0; sl < nslab; ++sl) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(GSTG - 2) : "memory");
+        __syncthreads();          // slab sl has landed for everyone, and everyone is done with the stage refilled next
+        if (sl + GSTG - 1 < nslab) issue(sl + GSTG - 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const double *Ar = sm + (size_t)(sl % GSTG) * GSTAGE, *Ai = Ar + TS * GLDA, *Br = Ai + TS * GLDA, *Bi = Br + GK * LDS_T;
+#pragma unroll
+        for (int k4 = 0; k4 < GK; k4 += 4) {
+            double nar[4], pai[4], nai[4], br[2], bi[2];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int r = min(rb + i * 8 + fr, r1 - 1) - prow0;
-                pr[i] = Pre[(kk + fk) * pld + r];
-                pi[i] = Pim[(kk + fk) * pld + r];
-                pn[i] = -pi[i];
+                const int o = (wr * 32 + i * 8 + fr) * GLDA + k4 + fk;
+                nar[i] = -Ar[o];
+                pai[i] = Ai[o];
+                nai[i] = -pai[i];
             }
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                ur[j] = Ure[(kk + fk) * UW + wc * 16 + j * 8 + fr];
-                ui[j] = Uim[(kk + fk) * UW + wc * 16 + j * 8 + fr];
+                const int o = (k4 + fk) * LDS_T + wc * 16 + j * 8 + fr;
+                br[j] = Br[o];
+                bi[j] = Bi[o];
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    dmma(are[i][j][0], are[i][j][1], pr[i], ur[j]);
-                    dmma(are[i][j][0], are[i][j][1], pn[i], ui[j]);
-                    dmma(aim[i][j][0], aim[i][j][1], pr[i], ui[j]);
-                    dmma(aim[i][j][0], aim[i][j][1], pi[i], ur[j]);
+                    dmma(cre[i][j].x, cre[i][j].y, nar[i], br[j]);
+                    dmma(cre[i][j].x, cre[i][j].y, pai[i], bi[j]);
+                    dmma(cim[i][j].x, cim[i][j].y, nar[i], bi[j]);
+                    dmma(cim[i][j].x, cim[i][j].y, nai[i], br[j]);
                 }
         }
+    }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int row = rb + i * 8 + fr;
-            if (row >= r1) continue;
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int col = wc * 16 + j * 8 + 2 * fk;
-                if (col >= cw) continue;
-                const size_t o = (size_t)row * lw + c0 + col;
-                if (col + 1 < cw) {
-                    *reinterpret_cast<double2 *>(Wre + o) = make_double2(cre[i][j].x - are[i][j][0], cre[i][j].y - are[i][j][1]);
-                    *reinterpret_cast<double2 *>(Wim + o) = make_double2(cim[i][j].x - aim[i][j][0], cim[i][j].y - aim[i][j][1]);
-                } else {
-                    Wre[o] = cre[i][j].x - are[i][j][0];
-                    Wim[o] = cim[i][j].x - aim[i][j][0];
+        for (int j = 0; j < 2; ++j) {
+            const int row = tr + wr * 32 + i * 8 + fr, col = tc + wc * 16 + j * 8 + 2 * fk;
+            if (col < c1) {
+                *reinterpret_cast<double2 *>(wre + (size_t)row * lw + col) = cre[i][j];
+                *reinterpret_cast<double2 *>(wim + (size_t)row * lw + col) = cim[i][j];
+            }
+        }
+}
+
+// ------------------------------------------------------------------------------------------------ back substitution
+// One CTA per frequency, thread per right-hand side, 16-row blocks from the bottom up to row_stop.  The U rows of a block are
+// staged in shared memory (every thread multiplies them with its own solution column, which it re-reads from W).
+constexpr int BSK = 128;
+__global__ void __launch_bounds__(256) k_backsub(Geo g, double *W, int row_stop) {
+    const int b = blockIdx.x, lw = g.lw, np = g.np;
+    double *wre = W + (size_t)b * 2 * g.plane, *wim = wre + g.plane;
+    __shared__ double Ur[16][BSK + 1], Ui[16][BSK + 1];
+    const int last = ((np - 1) / 16) * 16;
+    for (int cb = 0; cb < g.nrhs; cb += blockDim.x) {
+        const int c = cb + threadIdx.x;
+        const bool act = c < g.nrhs;
+        const int col = np + min(c, g.nrhs - 1);
+        for (int k0 = last; k0 >= 0 && k0 + 16 > row_stop; k0 -= 16) {
+            const int kb = min(16, np - k0);
+            double xr[16], xi[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                xr[i] = xi[i] = 0.0;
+                if (i < kb) {
+                    xr[i] = wre[(size_t)(k0 + i) * lw + col];
+                    xi[i] = wim[(size_t)(k0 + i) * lw + col];
                 }
+            }
+            for (int kc = k0 + kb; kc < np; kc += BSK) {
+                const int kn = min(BSK, np - kc);
+                __syncthreads();
+                for (int e = threadIdx.x; e < 16 * kn; e += blockDim.x) {
+                    const int kk = e % kn, i = e / kn;
+                    const bool ok = i < kb;
+                    Ur[i][kk] = ok ? wre[(size_t)(k0 + i) * lw + kc + kk] : 0.0;
+                    Ui[i][kk] = ok ? wim[(size_t)(k0 + i) * lw + kc + kk] : 0.0;
+                }
+                __syncthreads();
+                for (int kk = 0; kk < kn; ++kk) {
+                    const double sr = wre[(size_t)(kc + kk) * lw + col], si = wim[(size_t)(kc + kk) * lw + col];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) cfma_sub(xr[i], xi[i], Ur[i][kk], Ui[i][kk], sr, si);
+                }
+            }
+            __syncthreads();
+            for (int e = threadIdx.x; e < 16 * 16; e += blockDim.x) {
+                const int kk = e % 16, i = e / 16;
+                const bool ok = i < kb && kk < kb;
+                Ur[i][kk] = ok ? wre[(size_t)(k0 + i) * lw + k0 + kk] : (i == kk ? 1.0 : 0.0);
+                Ui[i][kk] = ok ? wim[(size_t)(k0 + i) * lw + k0 + kk] : 0.0;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int jj = 15; jj >= 0; --jj) {
+                const double dr = Ur[jj][jj], di = Ui[jj][jj];
+                const double dn = dr * dr + di * di;
+                const double tr = (xr[jj] * dr + xi[jj] * di) / dn, ti = (xi[jj] * dr - xr[jj] * di) / dn;
+                xr[jj] = tr; xi[jj] = ti;
+#pragma unroll
+                for (int i2 = 0; i2 < 16; ++i2)
+                    if (i2 < jj) cfma_sub(xr[i2], xi[i2], Ur[i2][jj], Ui[i2][jj], tr, ti);
+            }
+            if (act) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (i < kb) {
+                        wre[(size_t)(k0 + i) * lw + col] = xr[i];
+                        wim[(size_t)(k0 + i) * lw + col] = xi[i];
+                    }
             }
         }
     }
 }
 
-__global__ void __launch_bounds__(NT) k_bpt_lu(const LuArgs a) {
-    extern __shared__ double sm[];
-    // working dimension n is even (a decoupled identity dof pads an odd system): every chunk start k0+kb and the first
-    // right-hand-side column are then even, which keeps the 16-byte tile accesses of the update aligned
-    const int nl = a.n, n = a.np, ld = a.ld, lw = a.lw, ncols = a.ncols;
-    double *Pre = sm, *Pim = Pre + (size_t)NB * ld;           // panel [NB][ld] (column kk contiguous over rows)
-    double *Ure = Pim + (size_t)NB * ld, *Uim = Ure + NB * UW;  // chunk [NB][UW]
-    double *red = Uim + NB * UW;                                // [64]
-    __shared__ int piv[NB];
-    __shared__ int sw_dst[2 * NB], sw_src[2 * NB], sw_n;   // net effect of the panel's row interchanges on the touched rows
-    __shared__ int s_bad;
-    // W = [M | E] row-major, planar: row swaps, the U12 solve and the tile traffic of the update are all coalesced
-    double *Wre = a.W + (size_t)blockIdx.x * 2 * (size_t)n * lw, *Wim = Wre + (size_t)n * lw;
-
-    long long tacc[6] = {0, 0, 0, 0, 0, 0}, tlast = clock64();
-#define TICK(k) do { if (a.timing && blockIdx.x == 0 && threadIdx.x == 0) { const long long _n = clock64(); tacc[k] += _n - tlast; tlast = _n; } } while (0)
-    for (int iw = blockIdx.x; iw < a.nw; iw += gridDim.x) {
-        const double w = a.omegas[iw];
-        TICK(5);
-        // (w + i eps)^2 = w^2 - eps^2 + 2 i w eps ;  Sigma_ii = -i w/damp * mask_i  ->  M_ii += i w/damp * mask_i
-        const double zr = w * w - a.eps * a.eps, zi = 2.0 * w * a.eps, sg = w / a.damp;
-        __syncthreads();
-        if (threadIdx.x == 0) s_bad = 0;
-        // mode 2 (biased power spectrum, negf.py:236) needs G^a[:,sel] and G^r[sel,:]: two factorisations per frequency,
-        //   pass 0: M^a = z^2 - K - Sigma^r-dagger            (advanced; negf.py:210-212 keeps the +i eps of z)
-        //   pass 1: (M^r)^T                                   (rows of G^r are columns of its transpose)
-        const int npass = a.mode == 2 ? 2 : 1;
-        for (int pass = 0; pass < npass; ++pass) {
-        const double sgn = (a.mode == 2 && pass == 0) ? -1.0 : 1.0;
-        const bool tblk = a.mode == 2;
-        for (int i = threadIdx.x >> 5; i < n; i += NT / 32) {          // warp per row, lanes over columns: coalesced, 4-deep ILP
-            const double *krow = a.K + (size_t)min(i, nl - 1) * nl;
-            double *wre = Wre + (size_t)i * lw, *wim = Wim + (size_t)i * lw;
-            for (int j0 = threadIdx.x & 31; j0 < ncols; j0 += 128) {
-                double v[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int j = j0 + 32 * u;
-                    v[u] = (j < nl && i < nl) ? krow[j] : 0.0;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int j = j0 + 32 * u;
-                    if (j < n) {
-                        double mr = (i == j ? (i < nl ? zr : 1.0) : 0.0) - v[u];
-                        double mi = (i == j && i < nl) ? zi + sgn * sg * a.sig_mask[i] : 0.0;
-                        if (a.nb > 0 && i >= a.b0 && i < a.b0 + a.nb && j >= a.b0 && j < a.b0 + a.nb) {
-                            const int bi = tblk ? j - a.b0 : i - a.b0, bj = tblk ? i - a.b0 : j - a.b0;
-                            mr += a.bias * a.chiminus[bi * a.nb + bj];          // M -= Sigma_b :  +bias chi-  and  +i w bdamp
-                            mi += sgn * w * a.bdamp[bi * a.nb + bj];
-                        }
-                        wre[j] = mr;
-                        wim[j] = mi;
-                    } else if (j < ncols) {
-                        wre[j] = a.rhs[j - n] == i ? 1.0 : 0.0;
-                        wim[j] = 0.0;
-                    }
-                }
-            }
-        }
-        __syncthreads();
-
-        TICK(0);
-        // ---------------- blocked LU, right-hand sides carried as columns n..ncols
-        for (int k0 = 0; k0 < n; k0 += NB) {
-            const int kb = min(NB, n - k0), m = n - k0;
-            for (int e = threadIdx.x; e < NB * m; e += NT) {
-                const int kk = e % NB, i = e / NB;
-                const bool ok = kk < kb;
-                Pre[kk * ld + i] = ok ? Wre[(size_t)(k0 + i) * lw + k0 + kk] : 0.0;
-                Pim[kk * ld + i] = ok ? Wim[(size_t)(k0 + i) * lw + k0 + kk] : 0.0;
-            }
-            __syncthreads();
-            for (int j = 0; j < kb; ++j) {
-                // pivot: max |re|+|im| over rows j..m (izamax convention), ties -> smallest row
-                double best = -1.0;
-                int arg = j;
-                for (int i = j + threadIdx.x; i < m; i += NT) {
-                    const double v = fabs(Pre[j * ld + i]) + fabs(Pim[j * ld + i]);
-                    if (v > best) { best = v; arg = i; }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-                    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
-                    if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
-                }
-                double *cand = red + (j & 1) * 32;       // double-buffered: no barrier needed before the next column's writes
-                if ((threadIdx.x & 31) == 0) { cand[threadIdx.x >> 5] = best; cand[16 + (threadIdx.x >> 5)] = (double)arg; }
-                __syncthreads();
-                best = cand[0];
-                arg = (int)cand[16];
-#pragma unroll
-                for (int q = 1; q < NT / 32; ++q)
-                    if (cand[q] > best || (cand[q] == best && (int)cand[16 + q] < arg)) { best = cand[q]; arg = (int)cand[16 + q]; }
-                const int r = arg;                        // every thread derives the same pivot
-                if (threadIdx.x == 0) {
-                    piv[j] = r;
-                    if (!(best > 0.0)) s_bad = 1;
-                }
-                if (r != j && threadIdx.x < NB) {         // swap rows j <-> r of the panel (all NB columns)
-                    const int kk = threadIdx.x;
-                    double t = Pre[kk * ld + j]; Pre[kk * ld + j] = Pre[kk * ld + r]; Pre[kk * ld + r] = t;
-                    t = Pim[kk * ld + j]; Pim[kk * ld + j] = Pim[kk * ld + r]; Pim[kk * ld + r] = t;
-                }
-                __syncthreads();
-                const double dr = Pre[j * ld + j], di = Pim[j * ld + j];
-                const double dn = dr * dr + di * di;
-                const double ir = dr / dn, ii = -di / dn;    // 1/pivot
-                // scale column j and apply the rank-1 update to the rest of the panel; a thread owns whole rows and
-                // first gathers its row into registers so the shared-memory round trips overlap
-                for (int i = j + 1 + threadIdx.x; i < m; i += NT) {
-                    double vr[NB], vi[NB];
-#pragma unroll
-                    for (int jj = 0; jj < NB; ++jj) {
-                        vr[jj] = Pre[jj * ld + i];
-                        vi[jj] = Pim[jj * ld + i];
-                    }
-                    double lr = 0.0, li = 0.0;
-#pragma unroll
-                    for (int jj = 0; jj < NB; ++jj)
-                        if (jj == j) { lr = vr[jj] * ir - vi[jj] * ii; li = vr[jj] * ii + vi[jj] * ir; }
-#pragma unroll
-                    for (int jj = 0; jj < NB; ++jj) {
-                        if (jj == j) {
-                            Pre[jj * ld + i] = lr;
-                            Pim[jj * ld + i] = li;
-                        } else if (jj > j && jj < kb) {
-                            cfma_sub(vr[jj], vi[jj], lr, li, Pre[jj * ld + j], Pim[jj * ld + j]);
-                            Pre[jj * ld + i] = vr[jj];
-                            Pim[jj * ld + i] = vi[jj];
-                        }
-                    }
-                }
-                __syncthreads();
-            }
-            for (int e = threadIdx.x; e < kb * m; e += NT) {
-                const int kk = e % kb, i = e / kb;
-                Wre[(size_t)(k0 + i) * lw + k0 + kk] = Pre[kk * ld + i];
-                Wim[(size_t)(k0 + i) * lw + k0 + kk] = Pim[kk * ld + i];
-            }
-            __syncthreads();
-            TICK(1);
-            // net row permutation of this panel (LAPACK laswp without the 16 dependent round trips): touched rows are the
-            // kb top rows plus the distinct pivot rows below them; sw_src[t] = original row that ends up in row sw_dst[t]
-            if (threadIdx.x == 0) {
-                int nt = kb;
-                for (int t = 0; t < kb; ++t) sw_dst[t] = sw_src[t] = t;
-                for (int jj = 0; jj < kb; ++jj) {
-                    const int r = piv[jj];
-                    int pos = -1;
-                    for (int t = 0; t < nt; ++t) if (sw_dst[t] == r) { pos = t; break; }
-                    if (pos < 0) { pos = nt++; sw_dst[pos] = sw_src[pos] = r; }
-                    const int tmp = sw_src[jj]; sw_src[jj] = sw_src[pos]; sw_src[pos] = tmp;
-                }
-                sw_n = nt;
-            }
-            __syncthreads();
-            // every remaining column (thread per column, coalesced across the warp): interchanges, then U12 = L11^-1 A12
-            for (int c = k0 + kb + threadIdx.x; c < ncols; c += NT) {
-                double *wre = Wre + (size_t)k0 * lw + c, *wim = Wim + (size_t)k0 * lw + c;
-                const int nt = sw_n;
-                double vr[2 * NB], vi[2 * NB];
-#pragma unroll
-                for (int t = 0; t < 2 * NB; ++t) {
-                    if (t < nt) {
-                        vr[t] = wre[(size_t)sw_src[t] * lw];
-                        vi[t] = wim[(size_t)sw_src[t] * lw];
-                    } else {
-                        vr[t] = vi[t] = 0.0;
-                    }
-                }
-#pragma unroll
-                for (int t = 0; t < 2 * NB; ++t)     // displaced rows below the panel
-                    if (t >= kb && t < nt && sw_dst[t] != sw_src[t]) { wre[(size_t)sw_dst[t] * lw] = vr[t]; wim[(size_t)sw_dst[t] * lw] = vi[t]; }
-                double ur[NB], ui[NB];
-#pragma unroll
-                for (int jj = 0; jj < NB; ++jj) {
-                    ur[jj] = jj < kb ? vr[jj] : 0.0;
-                    ui[jj] = jj < kb ? vi[jj] : 0.0;
-                }
-#pragma unroll
-                for (int jj = 0; jj < NB; ++jj) {
-#pragma unroll
-                    for (int i2 = 0; i2 < NB; ++i2)
-                        if (i2 > jj && i2 < kb && jj < kb) cfma_sub(ur[i2], ui[i2], Pre[jj * ld + i2], Pim[jj * ld + i2], ur[jj], ui[jj]);
-                }
-#pragma unroll
-                for (int jj = 0; jj < NB; ++jj)
-                    if (jj < kb) {
-                        wre[(size_t)jj * lw] = ur[jj];
-                        wim[(size_t)jj * lw] = ui[jj];
-                    }
-            }
-            __syncthreads();
-            TICK(2);
-            // trailing update in column chunks: A22 -= L21 U12 (also advances the carried right-hand sides)
-            for (int c0 = k0 + kb; c0 < ncols; c0 += CW) {
-                const int cw = min(CW, ncols - c0);
-                for (int e = threadIdx.x; e < NB * CW; e += NT) {
-                    const int cc = e % CW, jj = e / CW;
-                    const bool ok = cc < cw && jj < kb;
-                    Ure[jj * UW + cc] = ok ? Wre[(size_t)(k0 + jj) * lw + c0 + cc] : 0.0;
-                    Uim[jj * UW + cc] = ok ? Wim[(size_t)(k0 + jj) * lw + c0 + cc] : 0.0;
-                }
-                __syncthreads();
-                rank_update(Wre, Wim, lw, k0 + kb, n, c0, cw, Pre, Pim, ld, k0, Ure, Uim);
-                __syncthreads();
-            }
-            TICK(3);
-        }
-
-        // ---------------- back substitution on the right-hand sides, bottom block first, down to row_stop
-        const int last = ((n - 1) / NB) * NB;
-        for (int k0 = last; k0 >= 0 && k0 + NB > a.row_stop; k0 -= NB) {
-            const int kb = min(NB, n - k0);
-            // U[rlo:k0+kb, k0:k0+kb] -> panel buffer (rows relative to 0; only the rows still needed)
-            const int rows = k0 + kb;
-            const int rlo = max(0, (a.row_stop / NB) * NB);
-            const int nr = rows - rlo;
-            for (int e = threadIdx.x; e < NB * nr; e += NT) {
-                const int kk = e % NB, i = rlo + e / NB;
-                const bool ok = kk < kb;
-                Pre[kk * ld + i] = ok ? Wre[(size_t)i * lw + k0 + kk] : 0.0;
-                Pim[kk * ld + i] = ok ? Wim[(size_t)i * lw + k0 + kk] : 0.0;
-            }
-            __syncthreads();
-            for (int c = n + threadIdx.x; c < ncols; c += NT) {    // X1 = U11^-1 Y1, thread per right-hand side
-                double *wre = Wre + (size_t)k0 * lw + c, *wim = Wim + (size_t)k0 * lw + c;
-                double xr[NB], xi[NB];
-#pragma unroll
-                for (int jj = 0; jj < NB; ++jj) {
-                    xr[jj] = jj < kb ? wre[(size_t)jj * lw] : 0.0;
-                    xi[jj] = jj < kb ? wim[(size_t)jj * lw] : 0.0;
-                }
-#pragma unroll
-                for (int jj = NB - 1; jj >= 0; --jj) {
-                    if (jj < kb) {
-                        const double dr = Pre[jj * ld + k0 + jj], di = Pim[jj * ld + k0 + jj];
-                        const double dn = dr * dr + di * di;
-                        const double tr = (xr[jj] * dr + xi[jj] * di) / dn, ti = (xi[jj] * dr - xr[jj] * di) / dn;
-                        xr[jj] = tr; xi[jj] = ti;
-#pragma unroll
-                        for (int i2 = 0; i2 < NB; ++i2)
-                            if (i2 < jj) cfma_sub(xr[i2], xi[i2], Pre[jj * ld + k0 + i2], Pim[jj * ld + k0 + i2], tr, ti);
-                    }
-                }
-#pragma unroll
-                for (int jj = 0; jj < NB; ++jj)
-                    if (jj < kb) {
-                        wre[(size_t)jj * lw] = xr[jj];
-                        wim[(size_t)jj * lw] = xi[jj];
-                    }
-            }
-            __syncthreads();
-            if (k0 > rlo) {
-                for (int c0 = n; c0 < ncols; c0 += CW) {           // Y_above -= U_above,blk X1
-                    const int cw = min(CW, ncols - c0);
-                    for (int e = threadIdx.x; e < NB * CW; e += NT) {
-                        const int cc = e % CW, jj = e / CW;
-                        const bool ok = cc < cw && jj < kb;
-                        Ure[jj * UW + cc] = ok ? Wre[(size_t)(k0 + jj) * lw + c0 + cc] : 0.0;
-                        Uim[jj * UW + cc] = ok ? Wim[(size_t)(k0 + jj) * lw + c0 + cc] : 0.0;
-                    }
-                    __syncthreads();
-                    rank_update(Wre, Wim, lw, rlo, k0, c0, cw, Pre, Pim, ld, 0, Ure, Uim);
-                    __syncthreads();
-                }
-            }
-        }
-
-        if (a.mode == 2 && pass == 0) {     // keep G^a[:,sel] while the second factorisation runs
-            double *xr = a.Xs + (size_t)blockIdx.x * 2 * n * a.nrhs, *xi = xr + (size_t)n * a.nrhs;
-            for (int e = threadIdx.x; e < n * a.nrhs; e += NT) {
-                const int c = e % a.nrhs, i = e / a.nrhs;
-                xr[e] = Wre[(size_t)i * lw + n + c];
-                xi[e] = Wim[(size_t)i * lw + n + c];
-            }
-            __syncthreads();
-        }
-        }   // pass
-        TICK(4);
-        // ---------------- observable
-        double acc = 0.0;
-        if (a.mode == 2) {
-            // w^2 Re sum_c [G^r Sigma^K G^a]_cc  with  Z[a,c] = G^r[sel_c,a] (pass 1) and X[b,c] = G^a[b,sel_c] (pass 0)
-            const double *xr = a.Xs + (size_t)blockIdx.x * 2 * n * a.nrhs, *xi = xr + (size_t)n * a.nrhs;
-            const double kd = a.kd[iw], kr1 = a.kr1[iw], kr2 = a.kr2[iw], ki = a.ki[iw];
-            for (int e = threadIdx.x; e < nl * a.nrhs; e += NT) {          // diagonal lead part: kd * mask_a
-                const int c = e % a.nrhs, i = e / a.nrhs;
-                const double m = a.sig_mask[i];
-                if (m != 0.0) {
-                    const double zr2 = Wre[(size_t)i * lw + n + c], zi2 = Wim[(size_t)i * lw + n + c];
-                    acc += kd * m * (zr2 * xr[(size_t)i * a.nrhs + c] - zi2 * xi[(size_t)i * a.nrhs + c]);
-                }
-            }
-            for (int e = threadIdx.x; e < a.nb * a.nb * a.nrhs; e += NT) { // dense bias block
-                const int c = e % a.nrhs, ab = e / a.nrhs, ia = ab / a.nb, ib = ab % a.nb;
-                const double skr = kr1 * a.bdamp[ab] + kr2 * a.chiplus[ab], ski = ki * a.chiminus[ab];
-                const size_t ra = (size_t)(a.b0 + ia) * lw + n + c, rb = (size_t)(a.b0 + ib) * a.nrhs + c;
-                const double zr2 = Wre[ra], zi2 = Wim[ra], xr2 = xr[rb], xi2 = xi[rb];
-                // Re[ z * sk * x ]
-                const double tr = skr * xr2 - ski * xi2, ti = skr * xi2 + ski * xr2;
-                acc += zr2 * tr - zi2 * ti;
-            }
-        } else if (a.mode == 0) {
-            for (int e = threadIdx.x; e < a.nrows * a.nrhs; e += NT) {
-                const int c = e % a.nrhs, i = a.rows[e / a.nrhs];
-                const double xr = Wre[(size_t)i * lw + n + c], xi = Wim[(size_t)i * lw + n + c];
-                acc += xr * xr + xi * xi;
-            }
-        } else {
-            for (int c = threadIdx.x; c < a.nrhs; c += NT) acc += Wim[(size_t)a.rhs[c] * lw + n + c];
-        }
-        acc = block_sum(acc, red);
-        if (threadIdx.x == 0) {
-            const double gam = 2.0 * w / a.damp;
-            a.out[iw] = a.mode == 0 ? gam * gam * acc : (a.mode == 1 ? -2.0 * w * w * a.weight[iw] * acc : w * w * acc);
-            a.status[iw] = s_bad;
-        }
-        __syncthreads();
+// keep G^a[:,sel] (pass 0 of the biased power spectrum) while the second factorisation runs
+__global__ void k_save(Geo g, const double *W, double *Xs) {
+    const int b = blockIdx.y;
+    const double *wre = W + (size_t)b * 2 * g.plane, *wim = wre + g.plane;
+    double *xr = Xs + (size_t)b * 2 * g.np * g.nrhs, *xi = xr + (size_t)g.np * g.nrhs;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < g.np * g.nrhs; e += gridDim.x * blockDim.x) {
+        const int c = e % g.nrhs, i = e / g.nrhs;
+        xr[e] = wre[(size_t)i * g.lw + g.np + c];
+        xi[e] = wim[(size_t)i * g.lw + g.np + c];
     }
-    if (a.timing && blockIdx.x == 0 && threadIdx.x == 0)
-        for (int k = 0; k < 6; ++k) a.timing[k] = tacc[k];
-#undef TICK
+}
+
+// ------------------------------------------------------------------------------------------------ observable
+__global__ void __launch_bounds__(256) k_observe(Geo g, Problem p, const double *W, const double *Xs, double *out, int w0, int mode) {
+    __shared__ double red[32];
+    const int b = blockIdx.x, iw = w0 + b, lw = g.lw, n = g.np;
+    const double *wre = W + (size_t)b * 2 * g.plane, *wim = wre + g.plane;
+    const double w = p.omegas[iw];
+    double acc = 0.0;
+    if (mode == 2) {
+        // w^2 Re sum_c [G^r Sigma^K G^a]_cc  with  Z[a,c] = G^r[sel_c,a] (pass 1, in W) and X[b,c] = G^a[b,sel_c] (pass 0, in Xs)
+        const double *xr = Xs + (size_t)b * 2 * n * g.nrhs, *xi = xr + (size_t)n * g.nrhs;
+        const double kd = p.kd[iw], kr1 = p.kr1[iw], kr2 = p.kr2[iw], ki = p.ki[iw];
+        for (int e = threadIdx.x; e < g.nl * g.nrhs; e += blockDim.x) {          // diagonal lead part: kd * mask_a
+            const int c = e % g.nrhs, i = e / g.nrhs;
+            const double m = p.mask[i];
+            if (m != 0.0) {
+                const double zr2 = wre[(size_t)i * lw + n + c], zi2 = wim[(size_t)i * lw + n + c];
+                acc += kd * m * (zr2 * xr[(size_t)i * g.nrhs + c] - zi2 * xi[(size_t)i * g.nrhs + c]);
+            }
+        }
+        for (int e = threadIdx.x; e < p.nb * p.nb * g.nrhs; e += blockDim.x) { // dense bias block
+            const int c = e % g.nrhs, ab = e / g.nrhs, ia = ab / p.nb, ib = ab % p.nb;
+            const double skr = kr1 * p.bdamp[ab] + kr2 * p.chiplus[ab], ski = ki * p.chiminus[ab];
+            const size_t ra = (size_t)p.bpos[ia] * lw + n + c, rb = (size_t)p.bpos[ib] * g.nrhs + c;
+            const double zr2 = wre[ra], zi2 = wim[ra], xr2 = xr[rb], xi2 = xi[rb];
+            const double tr = skr * xr2 - ski * xi2, ti = skr * xi2 + ski * xr2;     // Re[ z * sk * x ]
+            acc += zr2 * tr - zi2 * ti;
+        }
+    } else if (mode == 0) {
+        for (int e = threadIdx.x; e < p.nrows * g.nrhs; e += blockDim.x) {
+            const int c = e % g.nrhs, i = p.rows[e / g.nrhs];
+            const double xr = wre[(size_t)i * lw + n + c], xi = wim[(size_t)i * lw + n + c];
+            acc += xr * xr + xi * xi;
+        }
+    } else {
+        for (int c = threadIdx.x; c < g.nrhs; c += blockDim.x) acc += wim[(size_t)p.rhs[c] * lw + n + c];
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) {
+        const double gam = 2.0 * w / p.damp;
+        out[iw] = mode == 0 ? gam * gam * acc : (mode == 1 ? -2.0 * w * w * p.weight[iw] * acc : w * w * acc);
+    }
 }
 
 struct BiasBlock {
@@ -472,10 +642,84 @@ struct BiasBlock {
     const double *kd = nullptr, *kr1 = nullptr, *kr2 = nullptr, *ki = nullptr;
 };
 
+// Per-device workspace kept between calls (cudaMalloc of several GB costs more than a whole sweep): grow-only raw buffers and
+// the streams of the batch slots; released by sclmd_release_workspace().  One sweep at a time per process (g_ws_mutex).
+struct RawBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    cudaError_t reserve(size_t want) {
+        if (want <= bytes) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) bytes = want; else p = nullptr;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+struct StreamSlot {
+    cudaStream_t st = nullptr;
+    RawBuf W, Xs, swp;
+};
+struct Workspace {
+    int device = -1;
+    StreamSlot slot[3];
+    void release() {
+        for (auto &s : slot) {
+            s.W.release(); s.Xs.release(); s.swp.release();
+            if (s.st) cudaStreamDestroy(s.st);
+            s.st = nullptr;
+        }
+    }
+};
+std::mutex g_ws_mutex;
+std::vector<std::unique_ptr<Workspace>> g_ws;
+
+Workspace &workspace(int device) {
+    for (auto &w : g_ws) if (w->device == device) return *w;
+    g_ws.emplace_back(new Workspace());
+    g_ws.back()->device = device;
+    return *g_ws.back();
+}
+
+// enqueue the factorisation + solve of one batch (nbat frequencies starting at w0) on slot s
+cudaError_t enqueue_lu(const Geo &g, const Problem &p, StreamSlot &s, int *status, int w0, int nbat, int row_stop, double sgn, int tblk) {
+    cudaStream_t st = s.st;
+    double *W = static_cast<double *>(s.W.p);
+    int *swp = static_cast<int *>(s.swp.p);
+    k_build<<<dim3(g.nrp, nbat), 128, 0, st>>>(g, p, W, w0, sgn, tblk);
+    const size_t gsm = GEMM_SMEM, tsm = (size_t)2 * TS * (TS + 1) * sizeof(double);
+    for (int k0 = 0; k0 < g.np; k0 += TS) {
+        const int rend = std::min(k0 + TS, g.np);
+        const int nbw = g.np - k0 > 512 ? 8 : 16;       // rows per thread x columns must fit the register file
+        int sub = 0;
+        for (int kk = k0; kk < rend; kk += nbw, ++sub) {
+            const int m = g.np - kk, kb = std::min(nbw, rend - kk);
+            if (nbw == 8) k_panel<256, 4, 8><<<nbat, 256, 0, st>>>(g, W, swp, status, w0, k0, kk, kb, rend, sub);
+            else if (m > 256) k_panel<256, 2, 16><<<nbat, 256, 0, st>>>(g, W, swp, status, w0, k0, kk, kb, rend, sub);
+            else if (m > 128) k_panel<128, 2, 16><<<nbat, 128, 0, st>>>(g, W, swp, status, w0, k0, kk, kb, rend, sub);
+            else k_panel<64, 2, 16><<<nbat, 64, 0, st>>>(g, W, swp, status, w0, k0, kk, kb, rend, sub);
+            // the remaining panel columns of this block, every row below the sub-panel: rank-kb update
+            if (kk + kb < rend)
+                k_gemm<<<dim3(1, cdiv(g.np - (kk + kb), TS), nbat), 256, gsm, st>>>(g, W, kk + kb, kk + kb, rend, kk, kb);
+        }
+        if (g.ncols > rend) {
+            const dim3 tg(cdiv(g.ncols - rend, 128), nbat);
+            if (nbw == 8) k_block_trsm<8><<<tg, 128, tsm, st>>>(g, W, swp, k0, rend);
+            else k_block_trsm<16><<<tg, 128, tsm, st>>>(g, W, swp, k0, rend);
+        }
+        if (rend < g.np)       // trailing matrix and carried right-hand sides: rank-64 update
+            k_gemm<<<dim3(cdiv(g.ncols - rend, TS), cdiv(g.np - rend, TS), nbat), 256, gsm, st>>>(g, W, rend, rend, g.ncols, k0, rend - k0);
+    }
+    k_backsub<<<nbat, std::min(256, round_up(g.nrhs, 32)), 0, st>>>(g, W, row_stop);
+    return cudaGetLastError();
+}
+
 int run_lu(int device, int n, const double *K, const int32_t *idxL, int nL, const int32_t *idxR, int nR, double damp,
            const double *omegas, int nw, int mode, const double *weight, const int32_t *sel, int nsel, double *out,
            const BiasBlock *bb = nullptr) {
     SCLMD_REQUIRE(n > 0 && K && idxL && idxR && nL > 0 && nR > 0 && omegas && nw > 0 && out && damp != 0.0, "bpt: bad arguments");
+    SCLMD_REQUIRE(n <= 1024, "bpt: n=%d exceeds the register-resident panel (n <= 1024)", n);
     if (int e = select_device(device)) return e;
     std::vector<double> mask(n, 0.0);
     for (int i = 0; i < nL; ++i) {
@@ -486,95 +730,144 @@ int run_lu(int device, int n, const double *K, const int32_t *idxL, int nL, cons
         SCLMD_REQUIRE(idxR[i] >= 0 && idxR[i] < n, "bpt: right bath dof %d out of range", idxR[i]);
         mask[idxR[i]] += 1.0;
     }
-    std::vector<int> rhs, rows;
-    int row_stop = 0;
-    if (mode == 0) {
-        rhs.assign(idxL, idxL + nL);
-        rows.assign(idxR, idxR + nR);
-        row_stop = *std::min_element(rows.begin(), rows.end());
-    } else {
-        SCLMD_REQUIRE(sel && nsel > 0 && (weight || mode == 2), "bpt.ps: empty selection");
-        for (int i = 0; i < nsel; ++i) SCLMD_REQUIRE(sel[i] >= 0 && sel[i] < n, "bpt.ps: selected dof %d out of range", sel[i]);
-        rhs.assign(sel, sel + nsel);
-        rows = rhs;
-        row_stop = *std::min_element(rows.begin(), rows.end());
-        if (mode == 2) {   // the Keldysh self-energy lives on the lead dofs and on the bias block: those rows of both solutions
-            row_stop = 0;
-            for (int i = 0; i < n; ++i) if (mask[i] != 0.0) { row_stop = i; break; }
-            if (bb && bb->nb > 0) row_stop = std::min(row_stop, bb->b0);
-        }
-    }
     if (bb && bb->nb > 0)
         SCLMD_REQUIRE(bb->b0 >= 0 && bb->b0 + bb->nb <= n && bb->bdamp && bb->chiminus && bb->chiplus, "bpt: bad bias block");
     SCLMD_REQUIRE(mode != 2 || (bb && bb->nb > 0 && bb->kd && bb->kr1 && bb->kr2 && bb->ki), "bpt.ps (biased): missing Keldysh weights");
-    LuArgs a{};
-    a.n = n; a.np = n + (n & 1); a.nrhs = (int)rhs.size(); a.ld = round_up(a.np, 16) + 4;   // ld % 16 == 4: conflict-free 64-bit DMMA fragment loads from the panel
-    if (a.ld - 16 >= a.np) a.ld -= 16;
-    a.ncols = a.np + a.nrhs; a.nw = nw; a.mode = mode;
-    a.lw = round_up(a.ncols + CW, 2);   // slack of one chunk: the update prefetches whole 64-column tiles
-    a.nrows = (int)rows.size(); a.row_stop = row_stop; a.damp = damp; a.eps = 1e-9;
-    const size_t smem = ((size_t)2 * NB * a.ld + 2 * NB * UW + 64) * sizeof(double);
-    SCLMD_REQUIRE(smem <= 220 * 1024, "bpt: n=%d too large for the shared-memory panel (max ~850)", n);
-    const int grid = std::min(nw, 2 * sm_count(device));
-    DevBuf<double> dK, dmask, dom, dwt, W, dout;
-    DevBuf<int> drhs, drows, dstat;
+    const int nb = bb ? bb->nb : 0, b0 = bb ? bb->b0 : 0;
+    // right-hand sides and the rows of the solution the observable reads (original numbering)
+    std::vector<int> rhs_o, rows_o;
+    if (mode == 0) {
+        rhs_o.assign(idxL, idxL + nL);
+        rows_o.assign(idxR, idxR + nR);
+    } else {
+        SCLMD_REQUIRE(sel && nsel > 0 && (weight || mode == 2), "bpt.ps: empty selection");
+        for (int i = 0; i < nsel; ++i) SCLMD_REQUIRE(sel[i] >= 0 && sel[i] < n, "bpt.ps: selected dof %d out of range", sel[i]);
+        rhs_o.assign(sel, sel + nsel);
+        rows_o = rhs_o;
+        if (mode == 2) {   // the Keldysh self-energy lives on the lead dofs and on the bias block: those rows of both solutions
+            rows_o.clear();
+            for (int i = 0; i < n; ++i)
+                if (mask[i] != 0.0 || (i >= b0 && i < b0 + nb)) rows_o.push_back(i);
+        }
+    }
+    // ordering [neither | right-hand-side dofs | needed rows]: unit columns stay zero above their dof, back substitution is short
+    std::vector<int> key(n, 0), order(n), pos(n);
+    for (int d : rhs_o) key[d] = std::max(key[d], 1);
+    for (int d : rows_o) key[d] = 2;
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
+    for (int i = 0; i < n; ++i) pos[order[i]] = i;
+    std::vector<double> Kp((size_t)n * n), maskp(n);
+    std::vector<int> bmap(n, -1), bpos(std::max(nb, 1), 0);
+    for (int i = 0; i < n; ++i) {
+        const double *src = K + (size_t)order[i] * n;
+        double *dst = Kp.data() + (size_t)i * n;
+        for (int j = 0; j < n; ++j) dst[j] = src[order[j]];
+        maskp[i] = mask[order[i]];
+        if (order[i] >= b0 && order[i] < b0 + nb) { bmap[i] = order[i] - b0; bpos[order[i] - b0] = i; }
+    }
+    std::vector<int> rhs(rhs_o.size()), rows(rows_o.size());
+    for (size_t i = 0; i < rhs_o.size(); ++i) rhs[i] = pos[rhs_o[i]];
+    for (size_t i = 0; i < rows_o.size(); ++i) rows[i] = pos[rows_o[i]];
+    const int row_stop = *std::min_element(rows.begin(), rows.end());
+
+    Geo g{};
+    g.nl = n; g.np = n + (n & 1); g.nrhs = (int)rhs.size(); g.ncols = g.np + g.nrhs;
+    g.nrp = round_up(g.np, TS) + TS; g.lw = round_up(g.ncols, TS); g.plane = (size_t)g.nrp * g.lw;
+
+    // batches: several in flight on separate streams; slot memory bounded
+    const int sms = sm_count(device);
+    const size_t per_w = 2 * g.plane * sizeof(double);
+    int bmax = 4 * sms;
+    while (bmax > 8 && (size_t)bmax * per_w * 3 > ((size_t)24 << 30)) bmax /= 2;
+    const int nbatch = cdiv(nw, bmax), bsz = cdiv(nw, nbatch);
+    const int nslots = std::min(3, nbatch);
+
+    DevBuf<double> dK, dmask, dom, dwt, dout, dbd, dcp, dcm, dkw;
+    DevBuf<int> drhs, drows, dstat, dbmap, dbpos;
     SCLMD_CUDA(dK.alloc((size_t)n * n)); SCLMD_CUDA(dmask.alloc(n)); SCLMD_CUDA(dom.alloc(nw)); SCLMD_CUDA(dwt.alloc(nw));
-    SCLMD_CUDA(W.alloc((size_t)grid * 2 * a.np * a.lw)); SCLMD_CUDA(dout.alloc(nw));
-    SCLMD_CUDA(drhs.alloc(rhs.size())); SCLMD_CUDA(drows.alloc(rows.size())); SCLMD_CUDA(dstat.alloc(nw));
-    SCLMD_CUDA(cudaMemcpy(dK.p, K, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice));
-    SCLMD_CUDA(cudaMemcpy(dmask.p, mask.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    SCLMD_CUDA(dout.alloc(nw)); SCLMD_CUDA(drhs.alloc(rhs.size())); SCLMD_CUDA(drows.alloc(rows.size())); SCLMD_CUDA(dstat.alloc(nw));
+    SCLMD_CUDA(dbmap.alloc(n)); SCLMD_CUDA(dbpos.alloc(bpos.size()));
+    SCLMD_CUDA(cudaMemcpy(dK.p, Kp.data(), (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice));
+    SCLMD_CUDA(cudaMemcpy(dmask.p, maskp.data(), n * sizeof(double), cudaMemcpyHostToDevice));
     SCLMD_CUDA(cudaMemcpy(dom.p, omegas, nw * sizeof(double), cudaMemcpyHostToDevice));
     if (weight) SCLMD_CUDA(cudaMemcpy(dwt.p, weight, nw * sizeof(double), cudaMemcpyHostToDevice));
     SCLMD_CUDA(cudaMemcpy(drhs.p, rhs.data(), rhs.size() * sizeof(int), cudaMemcpyHostToDevice));
     SCLMD_CUDA(cudaMemcpy(drows.p, rows.data(), rows.size() * sizeof(int), cudaMemcpyHostToDevice));
-    a.K = dK.p; a.sig_mask = dmask.p; a.rhs = drhs.p; a.rows = drows.p; a.omegas = dom.p; a.weight = dwt.p;
-    a.W = W.p; a.out = dout.p; a.status = dstat.p;
-    DevBuf<double> dbd, dcp, dcm, dkw, dXs;
-    if (bb && bb->nb > 0) {
-        const size_t n2 = (size_t)bb->nb * bb->nb;
+    SCLMD_CUDA(cudaMemcpy(dbmap.p, bmap.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+    SCLMD_CUDA(cudaMemcpy(dbpos.p, bpos.data(), bpos.size() * sizeof(int), cudaMemcpyHostToDevice));
+    Problem p{};
+    p.K = dK.p; p.mask = dmask.p; p.rhs = drhs.p; p.rows = drows.p; p.nrows = (int)rows.size(); p.bmap = dbmap.p; p.bpos = dbpos.p;
+    p.nb = nb; p.damp = damp; p.eps = 1e-9; p.omegas = dom.p; p.weight = dwt.p;
+    if (nb > 0) {
+        const size_t n2 = (size_t)nb * nb;
         SCLMD_CUDA(dbd.alloc(n2)); SCLMD_CUDA(dcp.alloc(n2)); SCLMD_CUDA(dcm.alloc(n2));
         SCLMD_CUDA(cudaMemcpy(dbd.p, bb->bdamp, n2 * sizeof(double), cudaMemcpyHostToDevice));
         SCLMD_CUDA(cudaMemcpy(dcp.p, bb->chiplus, n2 * sizeof(double), cudaMemcpyHostToDevice));
         SCLMD_CUDA(cudaMemcpy(dcm.p, bb->chiminus, n2 * sizeof(double), cudaMemcpyHostToDevice));
-        a.b0 = bb->b0; a.nb = bb->nb; a.bdamp = dbd.p; a.chiplus = dcp.p; a.chiminus = dcm.p; a.bias = bb->bias;
+        p.bdamp = dbd.p; p.chiplus = dcp.p; p.chiminus = dcm.p; p.bias = bb->bias;
         if (mode == 2) {
             SCLMD_CUDA(dkw.alloc((size_t)4 * nw));
-            SCLMD_CUDA(cudaMemcpy(dkw.p, bb->kd, nw * sizeof(double), cudaMemcpyHostToDevice));
-            SCLMD_CUDA(cudaMemcpy(dkw.p + nw, bb->kr1, nw * sizeof(double), cudaMemcpyHostToDevice));
-            SCLMD_CUDA(cudaMemcpy(dkw.p + 2 * (size_t)nw, bb->kr2, nw * sizeof(double), cudaMemcpyHostToDevice));
-            SCLMD_CUDA(cudaMemcpy(dkw.p + 3 * (size_t)nw, bb->ki, nw * sizeof(double), cudaMemcpyHostToDevice));
-            a.kd = dkw.p; a.kr1 = dkw.p + nw; a.kr2 = dkw.p + 2 * (size_t)nw; a.ki = dkw.p + 3 * (size_t)nw;
-            SCLMD_CUDA(dXs.alloc((size_t)grid * 2 * a.np * a.nrhs));
-            a.Xs = dXs.p;
+            const double *src[4] = {bb->kd, bb->kr1, bb->kr2, bb->ki};
+            for (int q = 0; q < 4; ++q) SCLMD_CUDA(cudaMemcpy(dkw.p + (size_t)q * nw, src[q], nw * sizeof(double), cudaMemcpyHostToDevice));
+            p.kd = dkw.p; p.kr1 = dkw.p + nw; p.kr2 = dkw.p + 2 * (size_t)nw; p.ki = dkw.p + 3 * (size_t)nw;
         }
     }
-    DevBuf<long long> dtim;
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    Workspace &ws = workspace(device);
+    StreamSlot *slots = ws.slot;
+    for (int s = 0; s < nslots; ++s) {
+        if (!slots[s].st) SCLMD_CUDA(cudaStreamCreateWithFlags(&slots[s].st, cudaStreamNonBlocking));
+        SCLMD_CUDA(slots[s].W.reserve((size_t)bsz * 2 * g.plane * sizeof(double)));       // k_build writes every element
+        SCLMD_CUDA(slots[s].swp.reserve((size_t)bsz * MAXSUB * SWS * sizeof(int)));
+        if (mode == 2) SCLMD_CUDA(slots[s].Xs.reserve((size_t)bsz * 2 * g.np * g.nrhs * sizeof(double)));
+    }
+    SCLMD_CUDA(cudaFuncSetAttribute(k_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+    SCLMD_CUDA(cudaFuncSetAttribute(k_block_trsm<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)2 * TS * (TS + 1) * sizeof(double))));
+    SCLMD_CUDA(cudaFuncSetAttribute(k_block_trsm<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)2 * TS * (TS + 1) * sizeof(double))));
+
     const bool want_timing = getenv("SCLMD_BPT_TIMING") != nullptr;
-    if (want_timing) { SCLMD_CUDA(dtim.alloc(8)); a.timing = dtim.p; }
-    SCLMD_CUDA(cudaFuncSetAttribute(k_bpt_lu, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEvent_t e0, e1;
     SCLMD_CUDA(cudaEventCreate(&e0));
     SCLMD_CUDA(cudaEventCreate(&e1));
-    SCLMD_CUDA(cudaEventRecord(e0));
-    k_bpt_lu<<<grid, NT, smem>>>(a);
-    SCLMD_CUDA(cudaGetLastError());
-    SCLMD_CUDA(cudaEventRecord(e1));
+    SCLMD_CUDA(cudaDeviceSynchronize());
+    SCLMD_CUDA(cudaEventRecord(e0, slots[0].st));
+    for (int ib = 0; ib < nbatch; ++ib) {
+        StreamSlot &s = slots[ib % nslots];
+        const int w0 = ib * bsz, nbat = std::min(bsz, nw - w0);
+        if (nbat <= 0) break;
+        if (mode == 2) {
+            SCLMD_CUDA(enqueue_lu(g, p, s, dstat.p, w0, nbat, row_stop, -1.0, 1));
+            k_save<<<dim3(cdiv(g.np * g.nrhs, 256), nbat), 256, 0, s.st>>>(g, static_cast<const double *>(s.W.p), static_cast<double *>(s.Xs.p));
+            SCLMD_CUDA(enqueue_lu(g, p, s, dstat.p, w0, nbat, row_stop, 1.0, 1));
+        } else {
+            SCLMD_CUDA(enqueue_lu(g, p, s, dstat.p, w0, nbat, row_stop, 1.0, 0));
+        }
+        k_observe<<<nbat, 256, 0, s.st>>>(g, p, static_cast<const double *>(s.W.p), static_cast<const double *>(s.Xs.p), dout.p, w0, mode);
+        SCLMD_CUDA(cudaGetLastError());
+    }
+    // the end marker waits for every slot
+    for (int s = 1; s < nslots; ++s) {
+        cudaEvent_t ev;
+        SCLMD_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        SCLMD_CUDA(cudaEventRecord(ev, slots[s].st));
+        SCLMD_CUDA(cudaStreamWaitEvent(slots[0].st, ev, 0));
+        SCLMD_CUDA(cudaEventDestroy(ev));
+    }
+    SCLMD_CUDA(cudaEventRecord(e1, slots[0].st));
     SCLMD_CUDA(cudaDeviceSynchronize());
     float kms = 0;
     SCLMD_CUDA(cudaEventElapsedTime(&kms, e0, e1));
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    if (want_timing) fprintf(stderr, "[bpt] kernel %.3f ms for %d frequencies on %d CTAs (%.0f omega/s device-only)\n", kms, nw, grid, nw / (kms * 1e-3));
+    if (want_timing)
+        fprintf(stderr, "[bpt] device %.3f ms for %d frequencies in %d batches of %d on %d streams (%.0f omega/s device-only)\n", kms, nw,
+                nbatch, bsz, nslots, nw / (kms * 1e-3));
     SCLMD_CUDA(cudaMemcpy(out, dout.p, nw * sizeof(double), cudaMemcpyDeviceToHost));
-    if (want_timing) {
-        long long t[8];
-        SCLMD_CUDA(cudaMemcpy(t, dtim.p, sizeof(t), cudaMemcpyDeviceToHost));
-        fprintf(stderr, "[bpt timing, CTA 0 cycles] build %lld panel %lld swap+trsm %lld update %lld backsub %lld observable+loop %lld\n", t[0], t[1], t[2], t[3], t[4], t[5]);
-    }
-    std::vector<int> st(nw);
-    SCLMD_CUDA(cudaMemcpy(st.data(), dstat.p, nw * sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<int> stv(nw);
+    SCLMD_CUDA(cudaMemcpy(stv.data(), dstat.p, nw * sizeof(int), cudaMemcpyDeviceToHost));
     for (int i = 0; i < nw; ++i)
-        if (st[i]) {
+        if (stv[i]) {
             set_error("bpt: singular matrix at omega[%d]=%g (numpy.linalg.LinAlgError in the reference)", i, omegas[i]);
             return SCLMD_ERR_STATE;
         }
@@ -584,6 +877,16 @@ int run_lu(int device, int n, const double *K, const int32_t *idxL, int nL, cons
 }  // namespace
 
 extern "C" {
+
+// frees the device workspace the sweeps keep between calls
+int sclmd_release_workspace(void) {
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    for (auto &w : g_ws) {
+        if (cudaSetDevice(w->device) == cudaSuccess) w->release();
+    }
+    g_ws.clear();
+    return SCLMD_OK;
+}
 
 int sclmd_bpt_tm(int device, int n, const double *K, const int32_t *idxL, int nL, const int32_t *idxR, int nR, double damp,
                  const double *omegas, int nw, double *tm_out) {
