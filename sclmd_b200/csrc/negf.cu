@@ -10,22 +10,24 @@
 //
 // B200 design.  A rank-k update of an HBM-resident matrix moves 32 bytes per 8k flops, so k = 16 needs ~9 TB/s at the FP64 peak
 // and is HBM-bound; the factorisation is therefore organised as a BATCH of frequencies moving in lock step through
-//   k_build      M(w) and the unit columns, one pass over W
-//   k_panel      16-column sub-panel, one CTA per frequency, rows held in REGISTERS, implicit partial pivoting
-//                (rows stay with their thread; one barrier per column), pivot rows placed by the write-back
-//                and - thread per column - the swaps / U rows of the other columns of the current 64-column block
-//   k_block_trsm once per 64-column block, thread per column right of it: replay of the sub-panels' net row permutations and
-//                U12 = L11^-1 A12 (64 rows)
-//   k_gemm       complex rank-16 (panel columns of the block) / rank-64 (trailing matrix) update on the FP64 tensor pipe
-//                (4 real DMMA.8x8x4 per complex fragment pair), 64x64 tiles, whole K slab in shared memory
-//   k_backsub    thread per right-hand side, rows >= row_stop only
-//   k_observe    reduction to one number per frequency
+//   k_build       M(w) and the unit columns, one pass over W
+//   k_panel       16-column sub-panel, one CTA per frequency, rows held in REGISTERS, one barrier per column; then - thread per
+//                 column - the U rows of the other columns of the current 64-column block
+//   k_block_trsm  once per 64-column block, persistent CTA per frequency over 32-column chunks right of the block:
+//                 U12 = L11^-1 A12 (64 rows) with the in-block updates on the FP64 tensor pipe, next chunk prefetched in registers
+//   k_gemm        complex rank-16 (panel columns of the block) / rank-64 (trailing matrix) update on the FP64 tensor pipe
+//                 (4 real DMMA.8x8x4 per complex fragment pair), 64x64 tiles, K slabs through a 3-stage cp.async ring
+//   k_backsub     thread per right-hand side, rows >= row_stop only
+//   k_observe     reduction to one number per frequency
 // with several batches in flight on separate streams so that the latency-bound kernels of one batch fill the tails of another.
+// Pivoting is IMPLICIT over the whole factorisation: no row of W ever moves.  Every frequency carries an index list
+// act[position] -> physical row; choosing a pivot permutes 16-32 entries of that list (pivot j to position kk+j, the displaced
+// entries into the vacated positions) and every kernel addresses rows through it.
 // The dofs are re-ordered [not needed | right-hand-side dofs | rows needed]: the unit columns are then zero in every row above
 // their own dof, and a 64x64 update tile whose U12 slab is exactly zero is skipped (bit-identical result, ~1/3 fewer flops).
 //
-// Layout: W = [M | E] row-major, planar complex (real plane, imaginary plane), nrp x lw doubles per plane (rows padded to 64,
-// columns to 64, pads zero), one slot per frequency of a batch.
+// Layout: W = [M | E] row-major, planar complex (real plane, imaginary plane), nrp x lw doubles per plane (rows padded to 64
+// plus one spare tile, columns to 64, pads zero), one slot per frequency of a batch.
 #include <algorithm>
 #include <climits>
 #include <cstdlib>
@@ -40,13 +42,12 @@ using namespace sclmd;
 namespace {
 
 constexpr int TS = 64;        // outer block (rank of the trailing update) and GEMM tile edge
-constexpr int NBMAX = 16;     // widest sub-panel
-constexpr int SWS = 8 + 4 * NBMAX;   // ints per swap record: [0] count, [8..) src rows, [8+2*NBMAX..) dst rows
-constexpr int MAXSUB = TS / 8;       // sub-panels per 64-column block (8- or 16-wide): one swap record each, per frequency
 constexpr int LDS_T = TS + 4; // padded shared-memory row (== 4 mod 16 doubles: conflict-free 64-bit DMMA fragment loads)
 constexpr int GK = 16, GSTG = 3, GLDA = GK + 4;                 // k_gemm: slab depth, ring stages, leading dim of the A slab
 constexpr int GSTAGE = 2 * TS * GLDA + 2 * GK * LDS_T;          // doubles per stage: Are | Aim | Bre | Bim
 constexpr size_t GEMM_SMEM = (size_t)GSTG * GSTAGE * sizeof(double);
+constexpr int TC = 32, LDT = TC + 4;                            // k_block_trsm: columns per chunk, leading dim of the chunk tile
+constexpr size_t TRSM_SMEM = (size_t)(2 * TS * LDS_T + 2 * TS * LDT) * sizeof(double);
 
 struct Geo {
     int nl;      // logical dimension
@@ -84,8 +85,9 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
 // ------------------------------------------------------------------------------------------------ build
 // grid (nrp, batch): one row of W per CTA.  sgn = -1 builds the advanced matrix (Sigma^r-dagger), tblk transposes the bias block
 // (mode 2: pass 0 = M^a, pass 1 = (M^r)^T; negf.py:210-212 keeps the +i eps of z in advangf).
-__global__ void __launch_bounds__(128) k_build(Geo g, Problem p, double *W, int w0, double sgn, int tblk) {
+__global__ void __launch_bounds__(128) k_build(Geo g, Problem p, double *W, int *act, int w0, double sgn, int tblk) {
     const int i = blockIdx.x, b = blockIdx.y;
+    if (threadIdx.x == 0) act[(size_t)b * g.nrp + i] = i;
     const double w = p.omegas[w0 + b];
     const double zr = w * w - p.eps * p.eps, zi = 2.0 * w * p.eps, sg = w / p.damp;
     double *wre = W + (size_t)b * 2 * g.plane + (size_t)i * g.lw, *wim = wre + g.plane;
@@ -116,39 +118,44 @@ __global__ void __launch_bounds__(128) k_build(Geo g, Problem p, double *W, int 
 }
 
 // ------------------------------------------------------------------------------------------------ sub-panel
-// One CTA per frequency factorises columns [kk, kk+kb) over rows [kk, np).  Thread t owns rows kk + t + r*256 (r < RPT) in
-// registers.  Implicit pivoting: rows never move during the factorisation; a chosen row is frozen (it becomes a row of U), the
-// winner of each warp publishes its row next to its magnitude, so one barrier per column suffices.  The write-back places
-// pivot j at row kk+j and moves the unchosen top rows into the vacated slots; the same net permutation is recorded for
-// k_block_trsm.  Pivot rule: max |re|+|im| (izamax), ties to the smallest row.
+// One CTA per frequency factorises columns [kk, kk+kb) over the rows at positions [kk, np).  Thread t owns positions
+// kk + t + r*NT (r < RPT) in registers.  A chosen row is frozen (it becomes a row of U), the winner of each warp publishes its
+// row next to its magnitude, so one barrier per column suffices.  Afterwards the index list is permuted (pivot j to position
+// kk+j, unchosen top entries into the vacated positions); the rows themselves are written back where they came from.
+// Pivot rule: max |re|+|im| (izamax), ties to the smallest position.
 template <int NT, int RPT, int NBW>
-__global__ void __launch_bounds__(NT, 1) k_panel(Geo g, double *W, int *swp, int *status, int w0, int k0, int kk, int kb, int rend, int sub) {
+__global__ void __launch_bounds__(NT, RPT == 1 ? 512 / NT : 1) k_panel(Geo g, double *W, int *act, int *status, int w0, int kk, int kb, int rend) {
     constexpr int NWARP = NT / 32;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m = g.np - kk, lw = g.lw;
     double *wre = W + (size_t)b * 2 * g.plane, *wim = wre + g.plane;
+    int *actb = act + (size_t)b * g.nrp;
     __shared__ double c_best[2][NWARP];
     __shared__ int c_arg[2][NWARP];
     __shared__ double c_row[2][NWARP][2][NBW];
-    __shared__ int s_piv[NBW], s_topdest[NBW], s_bad;
-    __shared__ int s_src[2 * NBW], s_dst[2 * NBW], s_n;
-    __shared__ double s_lr[NBW][NBW + 1], s_li[NBW][NBW + 1];      // L11 (final row order) for the in-block U rows
+    __shared__ int s_piv[NBW], s_bad;
+    __shared__ int s_src[2 * NBW], s_dst[2 * NBW], s_n, s_phys[NBW];
+    __shared__ double s_lr[NBW][NBW + 1], s_li[NBW][NBW + 1];      // L11 in pivot order for the U rows of the side columns
 
     double ar[RPT][NBW], ai[RPT][NBW];
     int ord[RPT];
+    size_t off[RPT];
     bool live[RPT];      // valid row, not yet chosen as a pivot
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
         const int rel = tid + r * NT;
         live[r] = rel < m;
         ord[r] = -1;
-        const size_t o = (size_t)(kk + min(rel, m - 1)) * lw + kk;
+        off[r] = (size_t)actb[kk + min(rel, m - 1)] * lw + kk;
+    }
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
 #pragma unroll
         for (int jj = 0; jj < NBW; jj += 2) {
             double2 vr = make_double2(0.0, 0.0), vi = vr;
             if (live[r] && jj < kb) {          // kb is even: a pair is inside or outside the panel as a whole
-                vr = *reinterpret_cast<const double2 *>(wre + o + jj);
-                vi = *reinterpret_cast<const double2 *>(wim + o + jj);
+                vr = *reinterpret_cast<const double2 *>(wre + off[r] + jj);
+                vi = *reinterpret_cast<const double2 *>(wim + off[r] + jj);
             }
             ar[r][jj] = vr.x; ar[r][jj + 1] = vr.y;
             ai[r][jj] = vi.x; ai[r][jj + 1] = vi.y;
@@ -169,7 +176,7 @@ __global__ void __launch_bounds__(NT, 1) k_panel(Geo g, double *W, int *swp, int
             const double mybest = best;
             const int myarg = arg;
             {   // warp arg-max with three redux.sync: non-negative doubles order like their bit patterns (a NaN wins and is
-                // reported as a singular pivot below); ties go to the smallest row
+                // reported as a singular pivot below); ties go to the smallest position
                 const long long key = __double_as_longlong(best);          // -1.0 (no live row) is negative
                 const int hi = (int)(key >> 32);
                 const int mh = __reduce_max_sync(0xffffffffu, hi);
@@ -206,7 +213,7 @@ __global__ void __launch_bounds__(NT, 1) k_panel(Geo g, double *W, int *swp, int
                 if (!(wbest > 0.0)) s_bad = 1;
             }
             const double dr = c_row[buf][ww][0][j], di = c_row[buf][ww][1][j];
-            const double rn = 1.0 / (dr * dr + di * di);
+            const double rn = __drcp_rn(dr * dr + di * di);
             const double ir = dr * rn, ii = -di * rn;          // 1 / pivot
 #pragma unroll
             for (int r = 0; r < RPT; ++r) {
@@ -226,169 +233,214 @@ __global__ void __launch_bounds__(NT, 1) k_panel(Geo g, double *W, int *swp, int
         }
     }
 
-    // net row permutation: pivot j -> row kk+j ; unchosen top rows -> the vacated slots (any order is a valid LU as long as
-    // every remaining column follows the same permutation)
-    if (tid == 0) {
-        bool chosen[NBW];
-        int vac[NBW], nv = 0, q = 0;
-        for (int t = 0; t < NBW; ++t) chosen[t] = false;
-        for (int j = 0; j < kb; ++j) {
-            if (s_piv[j] < kb) chosen[s_piv[j]] = true;
-            else vac[nv++] = s_piv[j];
+    // permutation of the index list: pivot j -> position kk+j ; unchosen top entries -> the vacated positions (warp 0, ballots)
+    __syncthreads();
+    if (warp == 0) {
+        const int pj = lane < kb ? s_piv[lane] : INT_MAX;                     // lane j: relative position of pivot j
+        const unsigned chosen = __reduce_or_sync(0xffffffffu, pj < kb ? 1u << pj : 0u);   // top positions taken as pivots
+        const unsigned below = __ballot_sync(0xffffffffu, lane < kb && pj >= kb);         // pivots that vacate a lower position
+        const bool loose = lane < kb && !((chosen >> lane) & 1u);            // top entry that must move down
+        const unsigned loosem = __ballot_sync(0xffffffffu, loose);
+        const int q = __popc(loosem & ((1u << lane) - 1u));
+        const int vl = __fns(below, 0, q + 1);                                // lane of the q-th vacating pivot
+        const int vpos = __shfl_sync(0xffffffffu, pj, loose ? (vl & 31) : 0);
+        if (lane < kb) {
+            s_src[lane] = kk + pj;
+            s_dst[lane] = kk + lane;
         }
-        int cnt = kb;
-        for (int t = 0; t < kb; ++t) {
-            s_src[t] = kk + s_piv[t];
-            s_dst[t] = kk + t;
-            s_topdest[t] = -1;
-            if (!chosen[t]) {
-                s_topdest[t] = vac[q];
-                s_src[cnt] = kk + t;
-                s_dst[cnt] = kk + vac[q];
-                ++cnt;
-                ++q;
-            }
+        if (loose) {
+            s_src[kb + q] = kk + lane;
+            s_dst[kb + q] = kk + vpos;
         }
-        s_n = cnt;
-        if (s_bad) status[w0 + b] = 1;
+        if (lane == 0) {
+            s_n = kb + __popc(below);
+            if (s_bad) status[w0 + b] = 1;
+        }
     }
     __syncthreads();
-    if (tid < 2 * NBW) {          // the record k_block_trsm replays on the columns right of the block
-        int *rec = swp + ((size_t)b * MAXSUB + sub) * SWS;
-        if (tid == 0) rec[0] = s_n;
-        rec[8 + tid] = tid < s_n ? s_src[tid] : 0;
-        rec[8 + 2 * NBMAX + tid] = tid < s_n ? s_dst[tid] : 0;
-    }
+    int moved = 0;
+    if (tid < s_n) moved = actb[s_src[tid]];
 #pragma unroll
-    for (int r = 0; r < RPT; ++r) {
-        const int rel = tid + r * NT;
-        if (rel >= m) continue;
-        const int dest = ord[r] >= 0 ? ord[r] : (rel < kb ? s_topdest[rel] : rel);
-        const size_t o = (size_t)(kk + dest) * lw + kk;
+    for (int r = 0; r < RPT; ++r) {          // rows go back where they came from (L below the pivots, U in the pivot rows)
+        if (tid + r * NT >= m) continue;
 #pragma unroll
         for (int jj = 0; jj < NBW; jj += 2)
             if (jj < kb) {
-                *reinterpret_cast<double2 *>(wre + o + jj) = make_double2(ar[r][jj], ar[r][jj + 1]);
-                *reinterpret_cast<double2 *>(wim + o + jj) = make_double2(ai[r][jj], ai[r][jj + 1]);
+                *reinterpret_cast<double2 *>(wre + off[r] + jj) = make_double2(ar[r][jj], ar[r][jj + 1]);
+                *reinterpret_cast<double2 *>(wim + off[r] + jj) = make_double2(ai[r][jj], ai[r][jj + 1]);
             }
-        if (dest < kb) {
+        if (ord[r] >= 0) {
 #pragma unroll
-            for (int jj = 0; jj < NBW; ++jj) { s_lr[dest][jj] = ar[r][jj]; s_li[dest][jj] = ai[r][jj]; }
+            for (int jj = 0; jj < NBW; ++jj) { s_lr[ord[r]][jj] = ar[r][jj]; s_li[ord[r]][jj] = ai[r][jj]; }
         }
     }
     __syncthreads();
-    // the other columns of this 64-column block, thread per column: columns [k0, kk) (L of the earlier sub-panels) follow the
-    // row permutation; columns [kk+kb, rend) also get their U rows  U = L11^-1 A  (rows [kk, kk+kb)); k_gemm then updates
-    // them below.  Columns right of the block are handled once per block by k_block_trsm.
-    const int nleft = kk - k0, nside = nleft + (rend - kk - kb);
+    if (tid < s_n) {
+        actb[s_dst[tid]] = moved;
+        if (tid < kb) s_phys[tid] = moved;
+    }
+    __syncthreads();
+    // the remaining panel columns [kk+kb, rend) of this 64-column block, thread per column: U = L11^-1 A on the pivot rows
+    // (k_gemm then updates them below).  Columns right of the block are handled once per block by k_block_trsm.
+    const int nside = rend - kk - kb;
     if (tid < nside) {
-        const int c = tid < nleft ? k0 + tid : kk + kb + (tid - nleft);
-        const int nt = s_n;
-        double vr[2 * NBW], vi[2 * NBW];
+        const int c = kk + kb + tid;
+        double vr[NBW], vi[NBW];
 #pragma unroll
-        for (int t = 0; t < 2 * NBW; ++t) {
+        for (int t = 0; t < NBW; ++t) {
             vr[t] = vi[t] = 0.0;
-            if (t < nt) {
-                vr[t] = wre[(size_t)s_src[t] * lw + c];
-                vi[t] = wim[(size_t)s_src[t] * lw + c];
-            }
-        }
-#pragma unroll
-        for (int t = 0; t < 2 * NBW; ++t)
-            if (t >= kb && t < nt) {
-                wre[(size_t)s_dst[t] * lw + c] = vr[t];
-                wim[(size_t)s_dst[t] * lw + c] = vi[t];
-            }
-        if (tid >= nleft) {
-#pragma unroll
-            for (int jj = 0; jj < NBW; ++jj)
-#pragma unroll
-                for (int i2 = jj + 1; i2 < NBW; ++i2)
-                    if (i2 < kb) cfma_sub(vr[i2], vi[i2], s_lr[i2][jj], s_li[i2][jj], vr[jj], vi[jj]);
-        }
-#pragma unroll
-        for (int t = 0; t < NBW; ++t)
             if (t < kb) {
-                wre[(size_t)(kk + t) * lw + c] = vr[t];
-                wim[(size_t)(kk + t) * lw + c] = vi[t];
+                vr[t] = wre[(size_t)s_phys[t] * lw + c];
+                vi[t] = wim[(size_t)s_phys[t] * lw + c];
             }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------ block row swaps + U12
-// Once per 64-column block, thread per column right of the block (c >= rend): replay the net row permutation of every
-// sub-panel, then  U_j = L_jj^-1 (A_j - sum_{t<j} L_jt U_t)  (left-looking over the sub-panels; the thread re-reads its own
-// earlier U rows from W).  L (64x64, strictly lower, final row order) sits in shared memory.
-template <int NBW>
-__global__ void __launch_bounds__(128) k_block_trsm(Geo g, double *W, const int *swp, int k0, int rend) {
-    extern __shared__ double sm[];
-    constexpr int LDL = TS + 1;
-    double *Lr = sm, *Li = Lr + TS * LDL;
-    __shared__ int s_src[MAXSUB][2 * NBW], s_dst[MAXSUB][2 * NBW], s_n[MAXSUB];
-    const int b = blockIdx.y, lw = g.lw, nblk = rend - k0, nsub = (nblk + NBW - 1) / NBW;
-    double *wre = W + (size_t)b * 2 * g.plane, *wim = wre + g.plane;
-    for (int e = threadIdx.x; e < nblk * nblk; e += blockDim.x) {
-        const int jj = e % nblk, i = e / nblk;
-        Lr[i * LDL + jj] = jj < i ? wre[(size_t)(k0 + i) * lw + k0 + jj] : 0.0;
-        Li[i * LDL + jj] = jj < i ? wim[(size_t)(k0 + i) * lw + k0 + jj] : 0.0;
-    }
-    for (int e = threadIdx.x; e < nsub * 2 * NBW; e += blockDim.x) {
-        const int t = e % (2 * NBW), j = e / (2 * NBW);
-        const int *rec = swp + ((size_t)b * MAXSUB + j) * SWS;
-        s_src[j][t] = rec[8 + t];
-        s_dst[j][t] = rec[8 + 2 * NBMAX + t];
-        if (t == 0) s_n[j] = rec[0];
-    }
-    __syncthreads();
-    const int c = rend + blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= g.ncols) return;
-    bool seen = false;          // unit columns: nothing to do while every touched entry is still exactly zero
-    for (int j = 0; j < nsub; ++j) {
-        const int kk = k0 + j * NBW, kb = min(NBW, rend - kk), nt = s_n[j];
-        double vr[2 * NBW], vi[2 * NBW];
-        bool nz = false;
-#pragma unroll
-        for (int t = 0; t < 2 * NBW; ++t) {
-            vr[t] = vi[t] = 0.0;
-            if (t < nt) {
-                vr[t] = wre[(size_t)s_src[j][t] * lw + c];
-                vi[t] = wim[(size_t)s_src[j][t] * lw + c];
-                nz |= (vr[t] != 0.0) | (vi[t] != 0.0);
-            }
-        }
-        if (!nz && !seen) continue;
-        seen = true;
-#pragma unroll
-        for (int t = 0; t < 2 * NBW; ++t)     // displaced rows below the sub-panel's top block
-            if (t >= kb && t < nt) {
-                wre[(size_t)s_dst[j][t] * lw + c] = vr[t];
-                wim[(size_t)s_dst[j][t] * lw + c] = vi[t];
-            }
-        for (int kx0 = 0; kx0 < j * NBW; kx0 += 4) {          // pending contributions of the earlier U rows of this block
-            double ur[4], ui[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                ur[u] = wre[(size_t)(k0 + kx0 + u) * lw + c];
-                ui[u] = wim[(size_t)(k0 + kx0 + u) * lw + c];
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-#pragma unroll
-                for (int i = 0; i < NBW; ++i)
-                    if (i < kb) cfma_sub(vr[i], vi[i], Lr[(j * NBW + i) * LDL + kx0 + u], Li[(j * NBW + i) * LDL + kx0 + u], ur[u], ui[u]);
         }
 #pragma unroll
         for (int jj = 0; jj < NBW; ++jj)
 #pragma unroll
             for (int i2 = jj + 1; i2 < NBW; ++i2)
-                if (i2 < kb)
-                    cfma_sub(vr[i2], vi[i2], Lr[(j * NBW + i2) * LDL + j * NBW + jj], Li[(j * NBW + i2) * LDL + j * NBW + jj], vr[jj], vi[jj]);
+                if (i2 < kb) cfma_sub(vr[i2], vi[i2], s_lr[i2][jj], s_li[i2][jj], vr[jj], vi[jj]);
 #pragma unroll
         for (int t = 0; t < NBW; ++t)
             if (t < kb) {
-                wre[(size_t)(kk + t) * lw + c] = vr[t];
-                wim[(size_t)(kk + t) * lw + c] = vi[t];
+                wre[(size_t)s_phys[t] * lw + c] = vr[t];
+                wim[(size_t)s_phys[t] * lw + c] = vi[t];
             }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ U12 of a 64-column block
+// Persistent CTA per frequency over 32-column chunks right of the block (c >= rend).  L (64x64, strictly lower, pivot order)
+// sits in shared memory as the DMMA A operand; a chunk (64 pivot rows x 32 columns) is staged in shared memory as the B / C
+// operand.  Per sub-panel: U_j = inv(L_jj) T_j, then  T_below -= L_below U_j, both on the tensor pipe (the diagonal blocks are
+// inverted once per CTA).  The next chunk is prefetched into registers meanwhile; chunks that are still exactly zero are skipped.
+template <int NBW>
+__global__ void __launch_bounds__(256, 2) k_block_trsm(Geo g, double *W, const int *act, int *flags, int k0, int rend) {
+    extern __shared__ double sm[];
+    double *Lr = sm, *Li = Lr + TS * LDS_T, *Tr = Li + TS * LDS_T, *Ti = Tr + TS * LDT;
+    __shared__ int s_row[TS];
+    const int b = blockIdx.x, lw = g.lw, nblk = rend - k0, nsub = (nblk + NBW - 1) / NBW;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, fr = lane >> 2, fk = lane & 3;
+    double *wre = W + (size_t)b * 2 * g.plane, *wim = wre + g.plane;
+    const int *actb = act + (size_t)b * g.nrp;
+    if (tid < TS) s_row[tid] = actb[k0 + min(tid, nblk - 1)];
+    __syncthreads();
+    for (int e = tid; e < TS * TS; e += 256) {
+        const int kx = e % TS, i = e / TS;
+        const bool ok = i < nblk && kx < i;
+        Lr[i * LDS_T + kx] = ok ? wre[(size_t)s_row[i] * lw + k0 + kx] : 0.0;
+        Li[i * LDS_T + kx] = ok ? wim[(size_t)s_row[i] * lw + k0 + kx] : 0.0;
+    }
+    __syncthreads();
+    // the diagonal blocks are replaced by their inverses (unit lower triangular, NBW x NBW): the solve of a sub-panel's rows
+    // becomes a DMMA product that all warps share.  Thread (j, c) builds column c of inv(L_jj) by forward substitution.
+    {
+        const int j = tid / NBW, c = tid % NBW, jb = j * NBW;
+        double xr[NBW], xi[NBW];
+        if (tid < nsub * NBW) {
+#pragma unroll
+            for (int i = 0; i < NBW; ++i) { xr[i] = i == c ? 1.0 : 0.0; xi[i] = 0.0; }
+#pragma unroll
+            for (int jj = 0; jj < NBW; ++jj)
+#pragma unroll
+                for (int i2 = jj + 1; i2 < NBW; ++i2)
+                    cfma_sub(xr[i2], xi[i2], Lr[(jb + i2) * LDS_T + jb + jj], Li[(jb + i2) * LDS_T + jb + jj], xr[jj], xi[jj]);
+        }
+        __syncthreads();
+        if (tid < nsub * NBW) {
+#pragma unroll
+            for (int i = 0; i < NBW; ++i) {
+                Lr[(jb + i) * LDS_T + jb + c] = xr[i];
+                Li[(jb + i) * LDS_T + jb + c] = xi[i];
+            }
+        }
+    }
+    const int nchunk = (g.ncols - rend + TC - 1) / TC;
+    double2 cur[8], nxt[8];
+    auto fetch = [&](int ch, double2 (&buf)[8]) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = tid + u * 256, pl = e >> 10, row = (e >> 4) & 63, col = rend + ch * TC + (e & 15) * 2;
+            buf[u] = make_double2(0.0, 0.0);
+            if (row < nblk && col < g.ncols) buf[u] = *reinterpret_cast<const double2 *>((pl ? wim : wre) + (size_t)s_row[row] * lw + col);
+        }
+    };
+    fetch(0, cur);
+    for (int ch = 0; ch < nchunk; ++ch) {
+        int any = 0;
+        __syncthreads();          // L staged (first pass) / previous chunk written back
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = tid + u * 256, pl = e >> 10, row = (e >> 4) & 63, cp = (e & 15) * 2;
+            *reinterpret_cast<double2 *>((pl ? Ti : Tr) + row * LDT + cp) = cur[u];
+            any |= (cur[u].x != 0.0) | (cur[u].y != 0.0);
+        }
+        any = __syncthreads_or(any);
+        if (tid == 0) flags[(size_t)b * (g.lw / TC) + ch] = any;          // k_gemm skips update tiles whose U12 chunks are all zero
+        if (ch + 1 < nchunk) fetch(ch + 1, nxt);
+        if (any) {
+            for (int j = 0; j < nsub; ++j) {
+                const int jb = j * NBW, kb = min(NBW, nblk - jb);
+                if (warp < TC / 8) {      // U_j = inv(L_jj) T_j : warp w owns the 8-column fragment w (reads its inputs, then writes)
+                    const int cbase = warp * 8;
+                    double ur[NBW / 4], ui[NBW / 4];
+#pragma unroll
+                    for (int k4 = 0; k4 < NBW; k4 += 4) {
+                        ur[k4 / 4] = Tr[(jb + k4 + fk) * LDT + cbase + fr];
+                        ui[k4 / 4] = Ti[(jb + k4 + fk) * LDT + cbase + fr];
+                    }
+                    double2 yr[NBW / 8], yi[NBW / 8];
+#pragma unroll
+                    for (int mf = 0; mf < NBW / 8; ++mf) {
+                        yr[mf] = yi[mf] = make_double2(0.0, 0.0);
+#pragma unroll
+                        for (int k4 = 0; k4 < NBW; k4 += 4) {
+                            const double alr = Lr[(jb + mf * 8 + fr) * LDS_T + jb + k4 + fk], ali = Li[(jb + mf * 8 + fr) * LDS_T + jb + k4 + fk];
+                            dmma(yr[mf].x, yr[mf].y, alr, ur[k4 / 4]);
+                            dmma(yr[mf].x, yr[mf].y, -ali, ui[k4 / 4]);
+                            dmma(yi[mf].x, yi[mf].y, alr, ui[k4 / 4]);
+                            dmma(yi[mf].x, yi[mf].y, ali, ur[k4 / 4]);
+                        }
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int mf = 0; mf < NBW / 8; ++mf) {
+                        *reinterpret_cast<double2 *>(Tr + (jb + mf * 8 + fr) * LDT + cbase + 2 * fk) = yr[mf];
+                        *reinterpret_cast<double2 *>(Ti + (jb + mf * 8 + fr) * LDT + cbase + 2 * fk) = yi[mf];
+                    }
+                }
+                __syncthreads();
+                // rows below inside the block: (nblk - jb - kb) rows in 8-row fragments x 4 column fragments over the 8 warps
+                const int rb0 = jb + kb, nmf = (nblk - rb0 + 7) / 8;
+                for (int q = warp; q < nmf * (TC / 8); q += 8) {
+                    const int rbase = rb0 + (q / (TC / 8)) * 8, cbase = (q % (TC / 8)) * 8;
+                    double2 cr = *reinterpret_cast<const double2 *>(Tr + (rbase + fr) * LDT + cbase + 2 * fk);
+                    double2 ci = *reinterpret_cast<const double2 *>(Ti + (rbase + fr) * LDT + cbase + 2 * fk);
+#pragma unroll
+                    for (int k4 = 0; k4 < NBW; k4 += 4) {
+                        if (k4 < kb) {
+                            const double alr = Lr[(rbase + fr) * LDS_T + jb + k4 + fk], ali = Li[(rbase + fr) * LDS_T + jb + k4 + fk];
+                            const double ur = Tr[(jb + k4 + fk) * LDT + cbase + fr], ui = Ti[(jb + k4 + fk) * LDT + cbase + fr];
+                            dmma(cr.x, cr.y, -alr, ur);
+                            dmma(cr.x, cr.y, ali, ui);
+                            dmma(ci.x, ci.y, -alr, ui);
+                            dmma(ci.x, ci.y, -ali, ur);
+                        }
+                    }
+                    *reinterpret_cast<double2 *>(Tr + (rbase + fr) * LDT + cbase + 2 * fk) = cr;
+                    *reinterpret_cast<double2 *>(Ti + (rbase + fr) * LDT + cbase + 2 * fk) = ci;
+                }
+                __syncthreads();
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = tid + u * 256, pl = e >> 10, row = (e >> 4) & 63, cp = (e & 15) * 2, col = rend + ch * TC + cp;
+                if (row < nblk && col < g.ncols)
+                    *reinterpret_cast<double2 *>((pl ? wim : wre) + (size_t)s_row[row] * lw + col) =
+                        *reinterpret_cast<const double2 *>((pl ? Ti : Tr) + row * LDT + cp);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
     }
 }
 
@@ -406,26 +458,25 @@ __device__ __forceinline__ void cp_async16(double *dst, const double *src, bool 
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(src), "r"(nbytes) : "memory");
 }
 
-__global__ void __launch_bounds__(256, 2) k_gemm(Geo g, double *W, int r0, int c0, int c1, int ka, int K) {
+__global__ void __launch_bounds__(256, 2) k_gemm(Geo g, double *W, const int *act, const int *flags, int r0, int c0, int c1, int ka, int K) {
     extern __shared__ double sm[];
+    __shared__ int s_ra[TS], s_rb[TS];          // physical rows of the C / A tile and of the B slab
     const int b = blockIdx.z, lw = g.lw;
     const int tr = r0 + TS * blockIdx.y, tc = c0 + TS * blockIdx.x;
     double *wre = W + (size_t)b * 2 * g.plane, *wim = wre + g.plane;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wr = warp & 1, wc = warp >> 1, fr = lane >> 2, fk = lane & 3;
-
-    if (tc >= g.np) {       // unit columns: skip slabs that are still exactly zero
-        int any = 0;
-        for (int e = tid; e < K * (TS / 2); e += 256) {
-            const int k = e / (TS / 2), cp = (e % (TS / 2)) * 2;
-            if (tc + cp < c1) {
-                const double2 a = *reinterpret_cast<const double2 *>(wre + (size_t)(ka + k) * lw + tc + cp);
-                const double2 c = *reinterpret_cast<const double2 *>(wim + (size_t)(ka + k) * lw + tc + cp);
-                any |= (a.x != 0.0) | (a.y != 0.0) | (c.x != 0.0) | (c.y != 0.0);
-            }
-        }
-        if (!__syncthreads_or(any)) return;
+    if (flags && tc >= g.np) {       // unit columns: skip tiles whose U12 slab is still exactly zero (recorded by k_block_trsm)
+        const int ch = (tc - c0) / TC, nch = (g.ncols - c0 + TC - 1) / TC;
+        const int *fl = flags + (size_t)b * (g.lw / TC);
+        if (!(fl[ch] | (ch + 1 < nch ? fl[ch + 1] : 0))) return;
     }
+    {
+        const int *actb = act + (size_t)b * g.nrp;
+        if (tid < TS) s_ra[tid] = actb[tr + tid];
+        else if (tid < 2 * TS) s_rb[tid - TS] = actb[ka + min(tid - TS, K - 1)];
+    }
+    __syncthreads();
 
     const int nslab = (K + GK - 1) / GK;
     auto issue = [&](int slab) {
@@ -435,14 +486,14 @@ __global__ void __launch_bounds__(256, 2) k_gemm(Geo g, double *W, int r0, int c
         for (int u = 0; u < 4; ++u) {          // A: 2 planes x 64 rows x 8 chunks
             const int e = tid + u * 256, pl = e >> 9, r = (e >> 3) & 63, kp = (e & 7) * 2;
             const bool ok = kc + kp < K;
-            const double *src = (pl ? wim : wre) + (size_t)(tr + r) * lw + ka + (ok ? kc + kp : 0);
+            const double *src = (pl ? wim : wre) + (size_t)s_ra[r] * lw + ka + (ok ? kc + kp : 0);
             cp_async16(st + pl * (TS * GLDA) + r * GLDA + kp, src, ok);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {          // B: 2 planes x 16 k x 32 chunks
             const int e = tid + u * 256, pl = e >> 9, k = (e >> 5) & 15, cp = (e & 31) * 2;
             const bool ok = kc + k < K && tc + cp < c1;
-            const double *src = (pl ? wim : wre) + (size_t)(ka + (ok ? kc + k : 0)) * lw + (ok ? tc + cp : tc);
+            const double *src = (pl ? wim : wre) + (size_t)s_rb[ok ? kc + k : 0] * lw + (ok ? tc + cp : tc);
             cp_async16(st + 2 * (TS * GLDA) + pl * (GK * LDS_T) + k * LDS_T + cp, src, ok);
         }
     };
@@ -457,7 +508,7 @@ __global__ void __launch_bounds__(256, 2) k_gemm(Geo g, double *W, int r0, int c
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            const int row = tr + wr * 32 + i * 8 + fr, col = tc + wc * 16 + j * 8 + 2 * fk;
+            const int row = s_ra[wr * 32 + i * 8 + fr], col = tc + wc * 16 + j * 8 + 2 * fk;
             cre[i][j] = cim[i][j] = make_double2(0.0, 0.0);
             if (col < c1) {
                 cre[i][j] = *reinterpret_cast<const double2 *>(wre + (size_t)row * lw + col);
@@ -502,7 +553,7 @@ __global__ void __launch_bounds__(256, 2) k_gemm(Geo g, double *W, int r0, int c
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            const int row = tr + wr * 32 + i * 8 + fr, col = tc + wc * 16 + j * 8 + 2 * fk;
+            const int row = s_ra[wr * 32 + i * 8 + fr], col = tc + wc * 16 + j * 8 + 2 * fk;
             if (col < c1) {
                 *reinterpret_cast<double2 *>(wre + (size_t)row * lw + col) = cre[i][j];
                 *reinterpret_cast<double2 *>(wim + (size_t)row * lw + col) = cim[i][j];
@@ -514,14 +565,17 @@ __global__ void __launch_bounds__(256, 2) k_gemm(Geo g, double *W, int r0, int c
 // One CTA per frequency, thread per right-hand side, 16-row blocks from the bottom up to row_stop.  The U rows of a block are
 // staged in shared memory (every thread multiplies them with its own solution column, which it re-reads from W).
 constexpr int BSK = 128;
-__global__ void __launch_bounds__(256) k_backsub(Geo g, double *W, int row_stop) {
+__global__ void __launch_bounds__(256) k_backsub(Geo g, double *W, const int *act, int row_stop) {
     const int b = blockIdx.x, lw = g.lw, np = g.np;
     double *wre = W + (size_t)b * 2 * g.plane, *wim = wre + g.plane;
     __shared__ double Ur[16][BSK + 1], Ui[16][BSK + 1];
+    __shared__ int s_act[1024];
+    for (int i = threadIdx.x; i < np; i += blockDim.x) s_act[i] = act[(size_t)b * g.nrp + i];
+    __syncthreads();
     const int last = ((np - 1) / 16) * 16;
     for (int cb = 0; cb < g.nrhs; cb += blockDim.x) {
         const int c = cb + threadIdx.x;
-        const bool act = c < g.nrhs;
+        const bool actv = c < g.nrhs;
         const int col = np + min(c, g.nrhs - 1);
         for (int k0 = last; k0 >= 0 && k0 + 16 > row_stop; k0 -= 16) {
             const int kb = min(16, np - k0);
@@ -530,8 +584,8 @@ __global__ void __launch_bounds__(256) k_backsub(Geo g, double *W, int row_stop)
             for (int i = 0; i < 16; ++i) {
                 xr[i] = xi[i] = 0.0;
                 if (i < kb) {
-                    xr[i] = wre[(size_t)(k0 + i) * lw + col];
-                    xi[i] = wim[(size_t)(k0 + i) * lw + col];
+                    xr[i] = wre[(size_t)s_act[k0 + i] * lw + col];
+                    xi[i] = wim[(size_t)s_act[k0 + i] * lw + col];
                 }
             }
             for (int kc = k0 + kb; kc < np; kc += BSK) {
@@ -540,22 +594,32 @@ __global__ void __launch_bounds__(256) k_backsub(Geo g, double *W, int row_stop)
                 for (int e = threadIdx.x; e < 16 * kn; e += blockDim.x) {
                     const int kk = e % kn, i = e / kn;
                     const bool ok = i < kb;
-                    Ur[i][kk] = ok ? wre[(size_t)(k0 + i) * lw + kc + kk] : 0.0;
-                    Ui[i][kk] = ok ? wim[(size_t)(k0 + i) * lw + kc + kk] : 0.0;
+                    Ur[i][kk] = ok ? wre[(size_t)s_act[k0 + min(i, kb - 1)] * lw + kc + kk] : 0.0;
+                    Ui[i][kk] = ok ? wim[(size_t)s_act[k0 + min(i, kb - 1)] * lw + kc + kk] : 0.0;
                 }
                 __syncthreads();
-                for (int kk = 0; kk < kn; ++kk) {
-                    const double sr = wre[(size_t)(kc + kk) * lw + col], si = wim[(size_t)(kc + kk) * lw + col];
+                for (int kk = 0; kk < kn; kk += 4) {
+                    double sr[4], si[4];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) cfma_sub(xr[i], xi[i], Ur[i][kk], Ui[i][kk], sr, si);
+                    for (int u = 0; u < 4; ++u) {
+                        const int kx = min(kk + u, kn - 1);
+                        sr[u] = wre[(size_t)s_act[kc + kx] * lw + col];
+                        si[u] = wim[(size_t)s_act[kc + kx] * lw + col];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (kk + u < kn) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) cfma_sub(xr[i], xi[i], Ur[i][kk + u], Ui[i][kk + u], sr[u], si[u]);
+                        }
                 }
             }
             __syncthreads();
             for (int e = threadIdx.x; e < 16 * 16; e += blockDim.x) {
                 const int kk = e % 16, i = e / 16;
                 const bool ok = i < kb && kk < kb;
-                Ur[i][kk] = ok ? wre[(size_t)(k0 + i) * lw + k0 + kk] : (i == kk ? 1.0 : 0.0);
-                Ui[i][kk] = ok ? wim[(size_t)(k0 + i) * lw + k0 + kk] : 0.0;
+                Ur[i][kk] = ok ? wre[(size_t)s_act[k0 + min(i, kb - 1)] * lw + k0 + kk] : (i == kk ? 1.0 : 0.0);
+                Ui[i][kk] = ok ? wim[(size_t)s_act[k0 + min(i, kb - 1)] * lw + k0 + kk] : 0.0;
             }
             __syncthreads();
 #pragma unroll
@@ -568,35 +632,38 @@ __global__ void __launch_bounds__(256) k_backsub(Geo g, double *W, int row_stop)
                 for (int i2 = 0; i2 < 16; ++i2)
                     if (i2 < jj) cfma_sub(xr[i2], xi[i2], Ur[i2][jj], Ui[i2][jj], tr, ti);
             }
-            if (act) {
+            if (actv) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
                     if (i < kb) {
-                        wre[(size_t)(k0 + i) * lw + col] = xr[i];
-                        wim[(size_t)(k0 + i) * lw + col] = xi[i];
+                        wre[(size_t)s_act[k0 + i] * lw + col] = xr[i];
+                        wim[(size_t)s_act[k0 + i] * lw + col] = xi[i];
                     }
             }
         }
     }
 }
 
-// keep G^a[:,sel] (pass 0 of the biased power spectrum) while the second factorisation runs
-__global__ void k_save(Geo g, const double *W, double *Xs) {
+// keep G^a[:,sel] (pass 0 of the biased power spectrum) while the second factorisation runs; Xs is indexed by position
+__global__ void k_save(Geo g, const double *W, const int *act, double *Xs) {
     const int b = blockIdx.y;
     const double *wre = W + (size_t)b * 2 * g.plane, *wim = wre + g.plane;
+    const int *actb = act + (size_t)b * g.nrp;
     double *xr = Xs + (size_t)b * 2 * g.np * g.nrhs, *xi = xr + (size_t)g.np * g.nrhs;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < g.np * g.nrhs; e += gridDim.x * blockDim.x) {
         const int c = e % g.nrhs, i = e / g.nrhs;
-        xr[e] = wre[(size_t)i * g.lw + g.np + c];
-        xi[e] = wim[(size_t)i * g.lw + g.np + c];
+        xr[e] = wre[(size_t)actb[i] * g.lw + g.np + c];
+        xi[e] = wim[(size_t)actb[i] * g.lw + g.np + c];
     }
 }
 
 // ------------------------------------------------------------------------------------------------ observable
-__global__ void __launch_bounds__(256) k_observe(Geo g, Problem p, const double *W, const double *Xs, double *out, int w0, int mode) {
+__global__ void __launch_bounds__(256) k_observe(Geo g, Problem p, const double *W, const int *act, const double *Xs, double *out, int w0,
+                                                 int mode) {
     __shared__ double red[32];
     const int b = blockIdx.x, iw = w0 + b, lw = g.lw, n = g.np;
     const double *wre = W + (size_t)b * 2 * g.plane, *wim = wre + g.plane;
+    const int *actb = act + (size_t)b * g.nrp;
     const double w = p.omegas[iw];
     double acc = 0.0;
     if (mode == 2) {
@@ -607,26 +674,26 @@ __global__ void __launch_bounds__(256) k_observe(Geo g, Problem p, const double 
             const int c = e % g.nrhs, i = e / g.nrhs;
             const double m = p.mask[i];
             if (m != 0.0) {
-                const double zr2 = wre[(size_t)i * lw + n + c], zi2 = wim[(size_t)i * lw + n + c];
-                acc += kd * m * (zr2 * xr[(size_t)i * g.nrhs + c] - zi2 * xi[(size_t)i * g.nrhs + c]);
+                const size_t o = (size_t)actb[i] * lw + n + c;
+                acc += kd * m * (wre[o] * xr[(size_t)i * g.nrhs + c] - wim[o] * xi[(size_t)i * g.nrhs + c]);
             }
         }
         for (int e = threadIdx.x; e < p.nb * p.nb * g.nrhs; e += blockDim.x) { // dense bias block
             const int c = e % g.nrhs, ab = e / g.nrhs, ia = ab / p.nb, ib = ab % p.nb;
             const double skr = kr1 * p.bdamp[ab] + kr2 * p.chiplus[ab], ski = ki * p.chiminus[ab];
-            const size_t ra = (size_t)p.bpos[ia] * lw + n + c, rb = (size_t)p.bpos[ib] * g.nrhs + c;
+            const size_t ra = (size_t)actb[p.bpos[ia]] * lw + n + c, rb = (size_t)p.bpos[ib] * g.nrhs + c;
             const double zr2 = wre[ra], zi2 = wim[ra], xr2 = xr[rb], xi2 = xi[rb];
             const double tr = skr * xr2 - ski * xi2, ti = skr * xi2 + ski * xr2;     // Re[ z * sk * x ]
             acc += zr2 * tr - zi2 * ti;
         }
     } else if (mode == 0) {
         for (int e = threadIdx.x; e < p.nrows * g.nrhs; e += blockDim.x) {
-            const int c = e % g.nrhs, i = p.rows[e / g.nrhs];
+            const int c = e % g.nrhs, i = actb[p.rows[e / g.nrhs]];
             const double xr = wre[(size_t)i * lw + n + c], xi = wim[(size_t)i * lw + n + c];
             acc += xr * xr + xi * xi;
         }
     } else {
-        for (int c = threadIdx.x; c < g.nrhs; c += blockDim.x) acc += wim[(size_t)p.rhs[c] * lw + n + c];
+        for (int c = threadIdx.x; c < g.nrhs; c += blockDim.x) acc += wim[(size_t)actb[p.rhs[c]] * lw + n + c];
     }
     acc = block_sum(acc, red);
     if (threadIdx.x == 0) {
@@ -659,14 +726,14 @@ struct RawBuf {
 };
 struct StreamSlot {
     cudaStream_t st = nullptr;
-    RawBuf W, Xs, swp;
+    RawBuf W, Xs, act, flags;
 };
 struct Workspace {
     int device = -1;
     StreamSlot slot[3];
     void release() {
         for (auto &s : slot) {
-            s.W.release(); s.Xs.release(); s.swp.release();
+            s.W.release(); s.Xs.release(); s.act.release(); s.flags.release();
             if (s.st) cudaStreamDestroy(s.st);
             s.st = nullptr;
         }
@@ -686,32 +753,30 @@ Workspace &workspace(int device) {
 cudaError_t enqueue_lu(const Geo &g, const Problem &p, StreamSlot &s, int *status, int w0, int nbat, int row_stop, double sgn, int tblk) {
     cudaStream_t st = s.st;
     double *W = static_cast<double *>(s.W.p);
-    int *swp = static_cast<int *>(s.swp.p);
-    k_build<<<dim3(g.nrp, nbat), 128, 0, st>>>(g, p, W, w0, sgn, tblk);
-    const size_t gsm = GEMM_SMEM, tsm = (size_t)2 * TS * (TS + 1) * sizeof(double);
-    for (int k0 = 0; k0 < g.np; k0 += TS) {
+    int *act = static_cast<int *>(s.act.p), *flags = static_cast<int *>(s.flags.p);
+    k_build<<<dim3(g.nrp, nbat), 128, 0, st>>>(g, p, W, act, w0, sgn, tblk);
+    for (int k0 = 0; k0 < g.np; k0 += TS) {       // (blocks start on multiples of 64: tiles stay 512-byte aligned)
         const int rend = std::min(k0 + TS, g.np);
         const int nbw = g.np - k0 > 512 ? 8 : 16;       // rows per thread x columns must fit the register file
-        int sub = 0;
-        for (int kk = k0; kk < rend; kk += nbw, ++sub) {
+        for (int kk = k0; kk < rend; kk += nbw) {
             const int m = g.np - kk, kb = std::min(nbw, rend - kk);
-            if (nbw == 8) k_panel<256, 4, 8><<<nbat, 256, 0, st>>>(g, W, swp, status, w0, k0, kk, kb, rend, sub);
-            else if (m > 256) k_panel<256, 2, 16><<<nbat, 256, 0, st>>>(g, W, swp, status, w0, k0, kk, kb, rend, sub);
-            else if (m > 128) k_panel<128, 2, 16><<<nbat, 128, 0, st>>>(g, W, swp, status, w0, k0, kk, kb, rend, sub);
-            else k_panel<64, 2, 16><<<nbat, 64, 0, st>>>(g, W, swp, status, w0, k0, kk, kb, rend, sub);
+            if (nbw == 8) k_panel<512, 2, 8><<<nbat, 512, 0, st>>>(g, W, act, status, w0, kk, kb, rend);
+            else if (m > 256) k_panel<256, 2, 16><<<nbat, 256, 0, st>>>(g, W, act, status, w0, kk, kb, rend);
+            else if (m > 128) k_panel<256, 1, 16><<<nbat, 256, 0, st>>>(g, W, act, status, w0, kk, kb, rend);
+            else if (m > 64) k_panel<128, 1, 16><<<nbat, 128, 0, st>>>(g, W, act, status, w0, kk, kb, rend);
+            else k_panel<64, 1, 16><<<nbat, 64, 0, st>>>(g, W, act, status, w0, kk, kb, rend);
             // the remaining panel columns of this block, every row below the sub-panel: rank-kb update
             if (kk + kb < rend)
-                k_gemm<<<dim3(1, cdiv(g.np - (kk + kb), TS), nbat), 256, gsm, st>>>(g, W, kk + kb, kk + kb, rend, kk, kb);
+                k_gemm<<<dim3(1, cdiv(g.np - (kk + kb), TS), nbat), 256, GEMM_SMEM, st>>>(g, W, act, nullptr, kk + kb, kk + kb, rend, kk, kb);
         }
         if (g.ncols > rend) {
-            const dim3 tg(cdiv(g.ncols - rend, 128), nbat);
-            if (nbw == 8) k_block_trsm<8><<<tg, 128, tsm, st>>>(g, W, swp, k0, rend);
-            else k_block_trsm<16><<<tg, 128, tsm, st>>>(g, W, swp, k0, rend);
+            if (nbw == 8) k_block_trsm<8><<<nbat, 256, TRSM_SMEM, st>>>(g, W, act, flags, k0, rend);
+            else k_block_trsm<16><<<nbat, 256, TRSM_SMEM, st>>>(g, W, act, flags, k0, rend);
         }
         if (rend < g.np)       // trailing matrix and carried right-hand sides: rank-64 update
-            k_gemm<<<dim3(cdiv(g.ncols - rend, TS), cdiv(g.np - rend, TS), nbat), 256, gsm, st>>>(g, W, rend, rend, g.ncols, k0, rend - k0);
+            k_gemm<<<dim3(cdiv(g.ncols - rend, TS), cdiv(g.np - rend, TS), nbat), 256, GEMM_SMEM, st>>>(g, W, act, flags, rend, rend, g.ncols, k0, rend - k0);
     }
-    k_backsub<<<nbat, std::min(256, round_up(g.nrhs, 32)), 0, st>>>(g, W, row_stop);
+    k_backsub<<<nbat, std::min(256, round_up(g.nrhs, 32)), 0, st>>>(g, W, act, row_stop);
     return cudaGetLastError();
 }
 
@@ -819,12 +884,13 @@ int run_lu(int device, int n, const double *K, const int32_t *idxL, int nL, cons
     for (int s = 0; s < nslots; ++s) {
         if (!slots[s].st) SCLMD_CUDA(cudaStreamCreateWithFlags(&slots[s].st, cudaStreamNonBlocking));
         SCLMD_CUDA(slots[s].W.reserve((size_t)bsz * 2 * g.plane * sizeof(double)));       // k_build writes every element
-        SCLMD_CUDA(slots[s].swp.reserve((size_t)bsz * MAXSUB * SWS * sizeof(int)));
+        SCLMD_CUDA(slots[s].act.reserve((size_t)bsz * g.nrp * sizeof(int)));
+        SCLMD_CUDA(slots[s].flags.reserve((size_t)bsz * (g.lw / TC) * sizeof(int)));
         if (mode == 2) SCLMD_CUDA(slots[s].Xs.reserve((size_t)bsz * 2 * g.np * g.nrhs * sizeof(double)));
     }
     SCLMD_CUDA(cudaFuncSetAttribute(k_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-    SCLMD_CUDA(cudaFuncSetAttribute(k_block_trsm<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)2 * TS * (TS + 1) * sizeof(double))));
-    SCLMD_CUDA(cudaFuncSetAttribute(k_block_trsm<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)2 * TS * (TS + 1) * sizeof(double))));
+    SCLMD_CUDA(cudaFuncSetAttribute(k_block_trsm<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSM_SMEM));
+    SCLMD_CUDA(cudaFuncSetAttribute(k_block_trsm<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSM_SMEM));
 
     const bool want_timing = getenv("SCLMD_BPT_TIMING") != nullptr;
     cudaEvent_t e0, e1;
@@ -838,12 +904,12 @@ int run_lu(int device, int n, const double *K, const int32_t *idxL, int nL, cons
         if (nbat <= 0) break;
         if (mode == 2) {
             SCLMD_CUDA(enqueue_lu(g, p, s, dstat.p, w0, nbat, row_stop, -1.0, 1));
-            k_save<<<dim3(cdiv(g.np * g.nrhs, 256), nbat), 256, 0, s.st>>>(g, static_cast<const double *>(s.W.p), static_cast<double *>(s.Xs.p));
+            k_save<<<dim3(cdiv(g.np * g.nrhs, 256), nbat), 256, 0, s.st>>>(g, static_cast<const double *>(s.W.p), static_cast<const int *>(s.act.p), static_cast<double *>(s.Xs.p));
             SCLMD_CUDA(enqueue_lu(g, p, s, dstat.p, w0, nbat, row_stop, 1.0, 1));
         } else {
             SCLMD_CUDA(enqueue_lu(g, p, s, dstat.p, w0, nbat, row_stop, 1.0, 0));
         }
-        k_observe<<<nbat, 256, 0, s.st>>>(g, p, static_cast<const double *>(s.W.p), static_cast<const double *>(s.Xs.p), dout.p, w0, mode);
+        k_observe<<<nbat, 256, 0, s.st>>>(g, p, static_cast<const double *>(s.W.p), static_cast<const int *>(s.act.p), static_cast<const double *>(s.Xs.p), dout.p, w0, mode);
         SCLMD_CUDA(cudaGetLastError());
     }
     // the end marker waits for every slot
