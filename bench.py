@@ -234,19 +234,24 @@ def fill_noise(eng, w, ntraj, seed, traj0):
     return blocks, gen_s
 
 
-def negf_also(rank, world, local, barrier):
-    """NEGF transmission sweep of the config-3 shape (n = 483, Gamma on 150 + 150 dofs, damp = 0.1 ps) with the
-    frequency grid sharded over the ranks (weak scaling: 2960 points per GPU); host buffers in and out."""
+def negf_also(rank, world, local, barrier, fp64_peak_tflops=None):
+    """NEGF transmission sweep of BASELINE.json configs[2] (runnegf.py shape: n = 483, Gamma on 150 + 150 dofs, damp = 0.1 ps,
+    10^5 frequencies over 8 GPUs) with the frequency grid sharded over the ranks (weak scaling: 12500 points per GPU); host
+    buffers in and out.  A second, profiled pass (one stream, CUDA events around every launch) gives the roofline of its
+    dominant kernel, the rank-64 trailing update on the FP64 tensor pipe."""
+    import ctypes as C
+    from sclmd_b200 import _lib
     from sclmd_b200.negf import bpt
     from sclmd_b200 import parallel as PAR
     RPC = 6.582119569e-4
     K = P.spring_chain_dyn(201, seed=14) / RPC ** 2
     b = bpt(None, 0.25, 0.1, [list(range(60, 210)), list(range(393, 543))], [list(range(0, 60)), list(range(543, 603))],
             dynmatfile=K, num=1000, device=local)
-    per = 2960
+    per = 12500
     om = np.linspace(0, 0.25 / RPC, per * world + 1)
     lo, hi = PAR.shard_range(len(om), rank, world)
-    b.tm_sweep(om[lo:lo + 296])
+    b.tm_sweep(om[lo:lo + 1184])
+    b.tm_sweep(om[lo:lo + 1184])
     barrier()
     t0 = time.perf_counter()
     tm = b.tm_sweep(om[lo:hi])
@@ -255,13 +260,42 @@ def negf_also(rank, world, local, barrier):
     barrier()
     dt = time.perf_counter() - t0
     sweep_s = t1 - t0
+    L = _lib.lib()
+    dev_ms = C.c_double(0.0)
+    _lib.check(L.sclmd_bpt_get_profile(None, None, None, C.byref(dev_ms)))
+    device_s = dev_ms.value * 1e-3
     if world > 1:
-        dt, sweep_s = max_over_ranks(dt), max_over_ranks(sweep_s)
-    flops = ((8 / 3) * 483 ** 3 + 8 * 483 ** 2 * 150) * len(om)
-    return {"metric": "negf_omega_points_per_s", "value": len(om) / dt, "unit": "omega-points/s", "n": 483, "n_omega": len(om),
-            "fp64_tflops_algorithmic": flops / dt / 1e12, "transmission_checksum": float(np.sum(full)),
-            "sweep_s_max_over_ranks": sweep_s, "total_s_incl_allgather": dt,
-            "config": "config-3 shape: n=483, Gamma on 150+150 dofs, damp=0.1 ps, %d omega per GPU, blocks sharded + all-gather" % per}
+        dt, sweep_s, device_s = max_over_ranks(dt), max_over_ranks(sweep_s), max_over_ranks(device_s)
+    flops_w = (8 / 3) * 483 ** 3 + 8 * 483 ** 2 * 150          # one complex LU + n_R solves per frequency
+    out = {"metric": "negf_omega_points_per_s", "value": len(om) / dt, "unit": "omega-points/s", "n": 483, "n_omega": len(om),
+           "fp64_tflops_algorithmic": flops_w * len(om) / dt / 1e12, "transmission_checksum": float(np.sum(full)),
+           "sweep_s_max_over_ranks": sweep_s, "device_s_max_over_ranks": device_s, "total_s_incl_allgather": dt,
+           "device_only_omega_points_per_s": len(om) / device_s if device_s > 0 else None,
+           "algorithmic_flops_per_omega": flops_w,
+           "config": "BASELINE configs[2] shape: n=483, Gamma on 150+150 dofs, damp=0.1 ps, %d omega per GPU (10^5 over 8 GPUs), "
+                     "blocks sharded + all-gather; host buffers in and out" % per}
+    if rank == 0:
+        nprof = 2960
+        _lib.check(L.sclmd_bpt_set_profiling(1))
+        b.tm_sweep(om[lo:lo + nprof])
+        ms = (C.c_double * 7)()
+        n = (C.c_int64 * 7)()
+        gf = C.c_double(0.0)
+        _lib.check(L.sclmd_bpt_get_profile(ms, n, C.byref(gf), C.byref(dev_ms)))
+        _lib.check(L.sclmd_bpt_set_profiling(0))
+        names = ["k_build", "k_panel", "k_gemm (rank-16, panel columns)", "k_block_trsm", "k_gemm (rank-64 trailing update)", "k_backsub", "k_observe"]
+        tot = sum(ms)
+        peak = fp64_peak_tflops or 37.1
+        ach = gf.value / (ms[4] * 1e-3) / 1e12 if ms[4] > 0 else None
+        out["roofline"] = {
+            "kernel": "k_gemm (complex rank-64 trailing update, 4 real DMMA.8x8x4 per fragment pair)", "bound": "tensor",
+            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if ach else None, "traffic": None,
+            "peak_source": "measured live: FP64 DMMA.8x8x4 chain probe (sclmd_probe_fp64)",
+            "flops_per_launch": gf.value / max(1, n[4]), "avg_launch_ms": ms[4] / max(1, n[4]), "launches_timed": int(n[4]),
+            "share_of_sweep": ms[4] / tot if tot > 0 else None, "sample": "%d frequencies, one stream, event pair per launch" % nprof,
+            "kernel_ms": {names[i]: ms[i] for i in range(7)}, "kernel_launches": {names[i]: int(n[i]) for i in range(7)},
+            "whole_sweep_algorithmic_frac_of_peak": (flops_w * nprof / (tot * 1e-3) / 1e12) / peak if tot > 0 else None}
+    return out
 
 
 def max_over_ranks(x):
@@ -393,7 +427,7 @@ def main():
     eng.close()
     also = None
     if not args.no_also:
-        also = negf_also(rank, world, local, barrier)
+        also = negf_also(rank, world, local, barrier, probe["dmma_tflops"])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

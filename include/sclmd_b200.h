@@ -180,6 +180,10 @@ int sclmd_cos_transform(int device, int nt, int nw, int m, const double *tl, con
 
 /* The frequency sweeps keep their device workspace (batch buffers, streams) between calls; this frees it. */
 int sclmd_release_workspace(void);
+/* Per-kernel-class CUDA-event timing of the bpt sweeps (build, panel, rank-16 update, block trsm, rank-64 update, back
+ * substitution, observable): ms[7], n[7], flops executed by the rank-64 update, device time of the last sweep. */
+int sclmd_bpt_set_profiling(int on);
+int sclmd_bpt_get_profile(double *ms, int64_t *n, double *gemm_flops, double *last_device_ms);
 
 /* ---------------------------------------------------------------- NEGF ---
  * bpt.tm over a frequency list (negf.py:104-119, 206-208, 240-242) for

@@ -70,6 +70,8 @@ _PROTOS = {
     "sclmd_cos_transform": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, C.c_double, C.c_double, c_double_p]),
     "sclmd_gamt": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p]),
     "sclmd_release_workspace": (C.c_int, []),
+    "sclmd_bpt_set_profiling": (C.c_int, [C.c_int]),
+    "sclmd_bpt_get_profile": (C.c_int, [c_double_p, c_int64_p, c_double_p, c_double_p]),
     "sclmd_bpt_tm": (C.c_int, [C.c_int, C.c_int, c_double_p, c_int32_p, C.c_int, c_int32_p, C.c_int, C.c_double, c_double_p, C.c_int, c_double_p]),
     "sclmd_bpt_ps": (C.c_int, [C.c_int, C.c_int, c_double_p, c_int32_p, C.c_int, c_int32_p, C.c_int, C.c_double, c_double_p, c_double_p, C.c_int, c_int32_p, C.c_int, c_double_p]),
     "sclmd_bpt_tm_bias": (C.c_int, [C.c_int, C.c_int, c_double_p, c_int32_p, C.c_int, c_int32_p, C.c_int, C.c_double, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, C.c_double, c_double_p, C.c_int, c_double_p]),

@@ -458,7 +458,8 @@ __device__ __forceinline__ void cp_async16(double *dst, const double *src, bool 
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(src), "r"(nbytes) : "memory");
 }
 
-__global__ void __launch_bounds__(256, 2) k_gemm(Geo g, double *W, const int *act, const int *flags, int r0, int c0, int c1, int ka, int K) {
+__global__ void __launch_bounds__(256, 2) k_gemm(Geo g, double *W, const int *act, const int *flags, unsigned long long *tiles, int r0, int c0,
+                                                 int c1, int ka, int K) {
     extern __shared__ double sm[];
     __shared__ int s_ra[TS], s_rb[TS];          // physical rows of the C / A tile and of the B slab
     const int b = blockIdx.z, lw = g.lw;
@@ -471,6 +472,7 @@ __global__ void __launch_bounds__(256, 2) k_gemm(Geo g, double *W, const int *ac
         const int *fl = flags + (size_t)b * (g.lw / TC);
         if (!(fl[ch] | (ch + 1 < nch ? fl[ch + 1] : 0))) return;
     }
+    if (tiles && threadIdx.x == 0) atomicAdd(tiles, 1ull);
     {
         const int *actb = act + (size_t)b * g.nrp;
         if (tid < TS) s_ra[tid] = actb[tr + tid];
@@ -731,14 +733,47 @@ struct StreamSlot {
 struct Workspace {
     int device = -1;
     StreamSlot slot[3];
+    RawBuf arena;
     void release() {
         for (auto &s : slot) {
             s.W.release(); s.Xs.release(); s.act.release(); s.flags.release();
             if (s.st) cudaStreamDestroy(s.st);
             s.st = nullptr;
         }
+        arena.release();
     }
 };
+// Optional per-kernel-class timing (sclmd_bpt_set_profiling): one stream, a CUDA event pair around every launch.
+// classes: 0 build, 1 panel, 2 panel-column update (k_gemm, rank 16), 3 block trsm, 4 trailing update (k_gemm, rank 64),
+//          5 back substitution, 6 observable/save
+constexpr int NPROF = 7;
+struct Prof {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;      // pairs
+    std::vector<int> kind;
+    double ms[NPROF] = {0};
+    long long n[NPROF] = {0};
+    double last_device_ms = 0.0;
+    unsigned long long tiles = 0;     // rank-64 update tiles that ran the tensor loop (zero tiles return early)
+    double gemm_flops = 0.0;
+    void begin(int k, cudaStream_t st) {
+        if (!on) return;
+        cudaEvent_t a, b;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, st);
+        ev.push_back(a); ev.push_back(b); kind.push_back(k);
+    }
+    void end(cudaStream_t st) { if (on) cudaEventRecord(ev.back(), st); }
+    void collect() {
+        for (size_t i = 0; i < kind.size(); ++i) {
+            float t = 0;
+            if (cudaEventElapsedTime(&t, ev[2 * i], ev[2 * i + 1]) == cudaSuccess) { ms[kind[i]] += t; n[kind[i]]++; }
+            cudaEventDestroy(ev[2 * i]); cudaEventDestroy(ev[2 * i + 1]);
+        }
+        ev.clear(); kind.clear();
+    }
+};
+Prof g_prof;
 std::mutex g_ws_mutex;
 std::vector<std::unique_ptr<Workspace>> g_ws;
 
@@ -750,33 +785,49 @@ Workspace &workspace(int device) {
 }
 
 // enqueue the factorisation + solve of one batch (nbat frequencies starting at w0) on slot s
-cudaError_t enqueue_lu(const Geo &g, const Problem &p, StreamSlot &s, int *status, int w0, int nbat, int row_stop, double sgn, int tblk) {
+cudaError_t enqueue_lu(const Geo &g, const Problem &p, StreamSlot &s, int *status, int w0, int nbat, int row_stop, double sgn, int tblk,
+                       unsigned long long *tiles) {
+    Prof &pf = g_prof;
     cudaStream_t st = s.st;
     double *W = static_cast<double *>(s.W.p);
     int *act = static_cast<int *>(s.act.p), *flags = static_cast<int *>(s.flags.p);
+    pf.begin(0, st);
     k_build<<<dim3(g.nrp, nbat), 128, 0, st>>>(g, p, W, act, w0, sgn, tblk);
+    pf.end(st);
     for (int k0 = 0; k0 < g.np; k0 += TS) {       // (blocks start on multiples of 64: tiles stay 512-byte aligned)
         const int rend = std::min(k0 + TS, g.np);
         const int nbw = g.np - k0 > 512 ? 8 : 16;       // rows per thread x columns must fit the register file
         for (int kk = k0; kk < rend; kk += nbw) {
             const int m = g.np - kk, kb = std::min(nbw, rend - kk);
+            pf.begin(1, st);
             if (nbw == 8) k_panel<512, 2, 8><<<nbat, 512, 0, st>>>(g, W, act, status, w0, kk, kb, rend);
             else if (m > 256) k_panel<256, 2, 16><<<nbat, 256, 0, st>>>(g, W, act, status, w0, kk, kb, rend);
             else if (m > 128) k_panel<256, 1, 16><<<nbat, 256, 0, st>>>(g, W, act, status, w0, kk, kb, rend);
             else if (m > 64) k_panel<128, 1, 16><<<nbat, 128, 0, st>>>(g, W, act, status, w0, kk, kb, rend);
             else k_panel<64, 1, 16><<<nbat, 64, 0, st>>>(g, W, act, status, w0, kk, kb, rend);
+            pf.end(st);
             // the remaining panel columns of this block, every row below the sub-panel: rank-kb update
-            if (kk + kb < rend)
-                k_gemm<<<dim3(1, cdiv(g.np - (kk + kb), TS), nbat), 256, GEMM_SMEM, st>>>(g, W, act, nullptr, kk + kb, kk + kb, rend, kk, kb);
+            if (kk + kb < rend) {
+                pf.begin(2, st);
+                k_gemm<<<dim3(1, cdiv(g.np - (kk + kb), TS), nbat), 256, GEMM_SMEM, st>>>(g, W, act, nullptr, nullptr, kk + kb, kk + kb, rend, kk, kb);
+                pf.end(st);
+            }
         }
         if (g.ncols > rend) {
+            pf.begin(3, st);
             if (nbw == 8) k_block_trsm<8><<<nbat, 256, TRSM_SMEM, st>>>(g, W, act, flags, k0, rend);
             else k_block_trsm<16><<<nbat, 256, TRSM_SMEM, st>>>(g, W, act, flags, k0, rend);
+            pf.end(st);
         }
-        if (rend < g.np)       // trailing matrix and carried right-hand sides: rank-64 update
-            k_gemm<<<dim3(cdiv(g.ncols - rend, TS), cdiv(g.np - rend, TS), nbat), 256, GEMM_SMEM, st>>>(g, W, act, flags, rend, rend, g.ncols, k0, rend - k0);
+        if (rend < g.np) {     // trailing matrix and carried right-hand sides: rank-64 update
+            pf.begin(4, st);
+            k_gemm<<<dim3(cdiv(g.ncols - rend, TS), cdiv(g.np - rend, TS), nbat), 256, GEMM_SMEM, st>>>(g, W, act, flags, tiles, rend, rend, g.ncols, k0, rend - k0);
+            pf.end(st);
+        }
     }
+    pf.begin(5, st);
     k_backsub<<<nbat, std::min(256, round_up(g.nrhs, 32)), 0, st>>>(g, W, act, row_stop);
+    pf.end(st);
     return cudaGetLastError();
 }
 
@@ -846,41 +897,47 @@ int run_lu(int device, int n, const double *K, const int32_t *idxL, int nL, cons
     int bmax = 4 * sms;
     while (bmax > 8 && (size_t)bmax * per_w * 3 > ((size_t)24 << 30)) bmax /= 2;
     const int nbatch = cdiv(nw, bmax), bsz = cdiv(nw, nbatch);
-    const int nslots = std::min(3, nbatch);
+    const int nslots = g_prof.on ? 1 : std::min(3, nbatch);
 
-    DevBuf<double> dK, dmask, dom, dwt, dout, dbd, dcp, dcm, dkw;
-    DevBuf<int> drhs, drows, dstat, dbmap, dbpos;
-    SCLMD_CUDA(dK.alloc((size_t)n * n)); SCLMD_CUDA(dmask.alloc(n)); SCLMD_CUDA(dom.alloc(nw)); SCLMD_CUDA(dwt.alloc(nw));
-    SCLMD_CUDA(dout.alloc(nw)); SCLMD_CUDA(drhs.alloc(rhs.size())); SCLMD_CUDA(drows.alloc(rows.size())); SCLMD_CUDA(dstat.alloc(nw));
-    SCLMD_CUDA(dbmap.alloc(n)); SCLMD_CUDA(dbpos.alloc(bpos.size()));
-    SCLMD_CUDA(cudaMemcpy(dK.p, Kp.data(), (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice));
-    SCLMD_CUDA(cudaMemcpy(dmask.p, maskp.data(), n * sizeof(double), cudaMemcpyHostToDevice));
-    SCLMD_CUDA(cudaMemcpy(dom.p, omegas, nw * sizeof(double), cudaMemcpyHostToDevice));
-    if (weight) SCLMD_CUDA(cudaMemcpy(dwt.p, weight, nw * sizeof(double), cudaMemcpyHostToDevice));
-    SCLMD_CUDA(cudaMemcpy(drhs.p, rhs.data(), rhs.size() * sizeof(int), cudaMemcpyHostToDevice));
-    SCLMD_CUDA(cudaMemcpy(drows.p, rows.data(), rows.size() * sizeof(int), cudaMemcpyHostToDevice));
-    SCLMD_CUDA(cudaMemcpy(dbmap.p, bmap.data(), n * sizeof(int), cudaMemcpyHostToDevice));
-    SCLMD_CUDA(cudaMemcpy(dbpos.p, bpos.data(), bpos.size() * sizeof(int), cudaMemcpyHostToDevice));
-    Problem p{};
-    p.K = dK.p; p.mask = dmask.p; p.rhs = drhs.p; p.rows = drows.p; p.nrows = (int)rows.size(); p.bmap = dbmap.p; p.bpos = dbpos.p;
-    p.nb = nb; p.damp = damp; p.eps = 1e-9; p.omegas = dom.p; p.weight = dwt.p;
-    if (nb > 0) {
-        const size_t n2 = (size_t)nb * nb;
-        SCLMD_CUDA(dbd.alloc(n2)); SCLMD_CUDA(dcp.alloc(n2)); SCLMD_CUDA(dcm.alloc(n2));
-        SCLMD_CUDA(cudaMemcpy(dbd.p, bb->bdamp, n2 * sizeof(double), cudaMemcpyHostToDevice));
-        SCLMD_CUDA(cudaMemcpy(dcp.p, bb->chiplus, n2 * sizeof(double), cudaMemcpyHostToDevice));
-        SCLMD_CUDA(cudaMemcpy(dcm.p, bb->chiminus, n2 * sizeof(double), cudaMemcpyHostToDevice));
-        p.bdamp = dbd.p; p.chiplus = dcp.p; p.chiminus = dcm.p; p.bias = bb->bias;
-        if (mode == 2) {
-            SCLMD_CUDA(dkw.alloc((size_t)4 * nw));
-            const double *src[4] = {bb->kd, bb->kr1, bb->kr2, bb->ki};
-            for (int q = 0; q < 4; ++q) SCLMD_CUDA(cudaMemcpy(dkw.p + (size_t)q * nw, src[q], nw * sizeof(double), cudaMemcpyHostToDevice));
-            p.kd = dkw.p; p.kr1 = dkw.p + nw; p.kr2 = dkw.p + 2 * (size_t)nw; p.ki = dkw.p + 3 * (size_t)nw;
-        }
-    }
     std::lock_guard<std::mutex> lock(g_ws_mutex);
     Workspace &ws = workspace(device);
     StreamSlot *slots = ws.slot;
+    // the per-call device arrays come out of one cached arena (no cudaMalloc / cudaFree per sweep)
+    const size_t nb2 = (size_t)nb * nb;
+    const size_t arena_bytes = sizeof(double) * ((size_t)n * n + n + 7 * (size_t)nw + 3 * nb2) +
+                               sizeof(int) * (rhs.size() + rows.size() + (size_t)nw + n + bpos.size()) + 256 * 24;
+    SCLMD_CUDA(ws.arena.reserve(arena_bytes));
+    char *cursor = static_cast<char *>(ws.arena.p);
+    auto take = [&](size_t bytes) { char *r = cursor; cursor += (bytes + 255) / 256 * 256; return static_cast<void *>(r); };
+    auto take_d = [&](size_t cnt) { return static_cast<double *>(take(cnt * sizeof(double))); };
+    auto take_i = [&](size_t cnt) { return static_cast<int *>(take(cnt * sizeof(int))); };
+    double *dK = take_d((size_t)n * n), *dmask = take_d(n), *dom = take_d(nw), *dwt = take_d(nw), *dout = take_d(nw);
+    int *drhs = take_i(rhs.size()), *drows = take_i(rows.size()), *dstat = take_i(nw), *dbmap = take_i(n), *dbpos = take_i(bpos.size());
+    SCLMD_CUDA(cudaMemcpy(dK, Kp.data(), (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice));
+    SCLMD_CUDA(cudaMemcpy(dmask, maskp.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    SCLMD_CUDA(cudaMemcpy(dom, omegas, nw * sizeof(double), cudaMemcpyHostToDevice));
+    if (weight) SCLMD_CUDA(cudaMemcpy(dwt, weight, nw * sizeof(double), cudaMemcpyHostToDevice));
+    SCLMD_CUDA(cudaMemcpy(drhs, rhs.data(), rhs.size() * sizeof(int), cudaMemcpyHostToDevice));
+    SCLMD_CUDA(cudaMemcpy(drows, rows.data(), rows.size() * sizeof(int), cudaMemcpyHostToDevice));
+    SCLMD_CUDA(cudaMemcpy(dbmap, bmap.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+    SCLMD_CUDA(cudaMemcpy(dbpos, bpos.data(), bpos.size() * sizeof(int), cudaMemcpyHostToDevice));
+    SCLMD_CUDA(cudaMemset(dstat, 0, nw * sizeof(int)));
+    Problem p{};
+    p.K = dK; p.mask = dmask; p.rhs = drhs; p.rows = drows; p.nrows = (int)rows.size(); p.bmap = dbmap; p.bpos = dbpos;
+    p.nb = nb; p.damp = damp; p.eps = 1e-9; p.omegas = dom; p.weight = dwt;
+    if (nb > 0) {
+        double *dbd = take_d(nb2), *dcp = take_d(nb2), *dcm = take_d(nb2);
+        SCLMD_CUDA(cudaMemcpy(dbd, bb->bdamp, nb2 * sizeof(double), cudaMemcpyHostToDevice));
+        SCLMD_CUDA(cudaMemcpy(dcp, bb->chiplus, nb2 * sizeof(double), cudaMemcpyHostToDevice));
+        SCLMD_CUDA(cudaMemcpy(dcm, bb->chiminus, nb2 * sizeof(double), cudaMemcpyHostToDevice));
+        p.bdamp = dbd; p.chiplus = dcp; p.chiminus = dcm; p.bias = bb->bias;
+        if (mode == 2) {
+            double *dkw = take_d((size_t)4 * nw);
+            const double *src[4] = {bb->kd, bb->kr1, bb->kr2, bb->ki};
+            for (int q = 0; q < 4; ++q) SCLMD_CUDA(cudaMemcpy(dkw + (size_t)q * nw, src[q], nw * sizeof(double), cudaMemcpyHostToDevice));
+            p.kd = dkw; p.kr1 = dkw + nw; p.kr2 = dkw + 2 * (size_t)nw; p.ki = dkw + 3 * (size_t)nw;
+        }
+    }
     for (int s = 0; s < nslots; ++s) {
         if (!slots[s].st) SCLMD_CUDA(cudaStreamCreateWithFlags(&slots[s].st, cudaStreamNonBlocking));
         SCLMD_CUDA(slots[s].W.reserve((size_t)bsz * 2 * g.plane * sizeof(double)));       // k_build writes every element
@@ -892,6 +949,8 @@ int run_lu(int device, int n, const double *K, const int32_t *idxL, int nL, cons
     SCLMD_CUDA(cudaFuncSetAttribute(k_block_trsm<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSM_SMEM));
     SCLMD_CUDA(cudaFuncSetAttribute(k_block_trsm<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSM_SMEM));
 
+    DevBuf<unsigned long long> dtiles;
+    if (g_prof.on) SCLMD_CUDA(dtiles.alloc(1));
     const bool want_timing = getenv("SCLMD_BPT_TIMING") != nullptr;
     cudaEvent_t e0, e1;
     SCLMD_CUDA(cudaEventCreate(&e0));
@@ -903,13 +962,15 @@ int run_lu(int device, int n, const double *K, const int32_t *idxL, int nL, cons
         const int w0 = ib * bsz, nbat = std::min(bsz, nw - w0);
         if (nbat <= 0) break;
         if (mode == 2) {
-            SCLMD_CUDA(enqueue_lu(g, p, s, dstat.p, w0, nbat, row_stop, -1.0, 1));
+            SCLMD_CUDA(enqueue_lu(g, p, s, dstat, w0, nbat, row_stop, -1.0, 1, dtiles.p));
             k_save<<<dim3(cdiv(g.np * g.nrhs, 256), nbat), 256, 0, s.st>>>(g, static_cast<const double *>(s.W.p), static_cast<const int *>(s.act.p), static_cast<double *>(s.Xs.p));
-            SCLMD_CUDA(enqueue_lu(g, p, s, dstat.p, w0, nbat, row_stop, 1.0, 1));
+            SCLMD_CUDA(enqueue_lu(g, p, s, dstat, w0, nbat, row_stop, 1.0, 1, dtiles.p));
         } else {
-            SCLMD_CUDA(enqueue_lu(g, p, s, dstat.p, w0, nbat, row_stop, 1.0, 0));
+            SCLMD_CUDA(enqueue_lu(g, p, s, dstat, w0, nbat, row_stop, 1.0, 0, dtiles.p));
         }
-        k_observe<<<nbat, 256, 0, s.st>>>(g, p, static_cast<const double *>(s.W.p), static_cast<const int *>(s.act.p), static_cast<const double *>(s.Xs.p), dout.p, w0, mode);
+        g_prof.begin(6, s.st);
+        k_observe<<<nbat, 256, 0, s.st>>>(g, p, static_cast<const double *>(s.W.p), static_cast<const int *>(s.act.p), static_cast<const double *>(s.Xs.p), dout, w0, mode);
+        g_prof.end(s.st);
         SCLMD_CUDA(cudaGetLastError());
     }
     // the end marker waits for every slot
@@ -926,12 +987,20 @@ int run_lu(int device, int n, const double *K, const int32_t *idxL, int nL, cons
     SCLMD_CUDA(cudaEventElapsedTime(&kms, e0, e1));
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    g_prof.last_device_ms = kms;
+    if (g_prof.on) {
+        g_prof.collect();
+        unsigned long long t = 0;
+        SCLMD_CUDA(cudaMemcpy(&t, dtiles.p, sizeof(t), cudaMemcpyDeviceToHost));
+        g_prof.tiles += t;
+        g_prof.gemm_flops += (double)t * 8.0 * TS * TS * TS;      // full 64-deep tiles (the last block of an n that is not a multiple of 64 is shallower)
+    }
     if (want_timing)
         fprintf(stderr, "[bpt] device %.3f ms for %d frequencies in %d batches of %d on %d streams (%.0f omega/s device-only)\n", kms, nw,
                 nbatch, bsz, nslots, nw / (kms * 1e-3));
-    SCLMD_CUDA(cudaMemcpy(out, dout.p, nw * sizeof(double), cudaMemcpyDeviceToHost));
+    SCLMD_CUDA(cudaMemcpy(out, dout, nw * sizeof(double), cudaMemcpyDeviceToHost));
     std::vector<int> stv(nw);
-    SCLMD_CUDA(cudaMemcpy(stv.data(), dstat.p, nw * sizeof(int), cudaMemcpyDeviceToHost));
+    SCLMD_CUDA(cudaMemcpy(stv.data(), dstat, nw * sizeof(int), cudaMemcpyDeviceToHost));
     for (int i = 0; i < nw; ++i)
         if (stv[i]) {
             set_error("bpt: singular matrix at omega[%d]=%g (numpy.linalg.LinAlgError in the reference)", i, omegas[i]);
@@ -943,6 +1012,27 @@ int run_lu(int device, int n, const double *K, const int32_t *idxL, int nL, cons
 }  // namespace
 
 extern "C" {
+
+// per-kernel-class timing of the bpt sweeps (one stream, event pair per launch); switching it on resets the totals
+int sclmd_bpt_set_profiling(int on) {
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    g_prof = Prof();
+    g_prof.on = on != 0;
+    return SCLMD_OK;
+}
+
+// ms[7], n[7]: build, panel, rank-16 panel-column update, block trsm, rank-64 trailing update, back substitution, observable;
+// gemm_flops: flops executed by the rank-64 update tiles; last_device_ms: device time of the most recent sweep (always kept)
+int sclmd_bpt_get_profile(double *ms, int64_t *n, double *gemm_flops, double *last_device_ms) {
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    for (int i = 0; i < NPROF; ++i) {
+        if (ms) ms[i] = g_prof.ms[i];
+        if (n) n[i] = g_prof.n[i];
+    }
+    if (gemm_flops) *gemm_flops = g_prof.gemm_flops;
+    if (last_device_ms) *last_device_ms = g_prof.last_device_ms;
+    return SCLMD_OK;
+}
 
 // frees the device workspace the sweeps keep between calls
 int sclmd_release_workspace(void) {
