@@ -73,6 +73,18 @@ dgemm_nt_seg_kernel(const GemmArgs g) {
     const int ktiles = (g.Kseg + BK - 1) / BK;
     const int niter = max(0, seg_end - seg_begin) * ktiles;
 
+    // per-thread invariants of the tile loads: a thread always copies the same 16-byte column chunk (kc) of rows
+    // r0 + u * RSTEP, so the row offsets are computed once and an iteration only adds the K offset
+    constexpr int CPR = BK / 2;                 // 16-byte chunks per row
+    static_assert(THREADS % CPR == 0, "thread count must be a multiple of the chunks per row");
+    constexpr int RSTEP = THREADS / CPR, NA = (BM + RSTEP - 1) / RSTEP, NB_ = (BN + RSTEP - 1) / RSTEP;
+    const int kc = (tid % CPR) * 2, r0 = tid / CPR;
+    long long a_off[NA], b_off[NB_];
+#pragma unroll
+    for (int u = 0; u < NA; ++u) a_off[u] = (long long)min(m0 + r0 + u * RSTEP, g.M - 1) * g.lda + kc;
+#pragma unroll
+    for (int u = 0; u < NB_; ++u) b_off[u] = (long long)min(n0 + r0 + u * RSTEP, g.N - 1) * g.ldb + kc;
+
     auto load_tile = [&](int it, int stage) {
         const int seg = seg_begin + it / ktiles;
         const int k0 = (it % ktiles) * BK;
@@ -86,27 +98,18 @@ dgemm_nt_seg_kernel(const GemmArgs g) {
             aoff = (long long)seg * g.a_seg_stride;
         }
         boff = (long long)(g.b_seg0 + seg) * g.b_seg_stride;
-        double *as = As + (size_t)stage * BM * LDS;
-        double *bs = Bs + (size_t)stage * BN * LDS;
-        constexpr int CPR = BK / 2;  // 16-byte chunks per row
+        const int rem = kvalid - (k0 + kc);
+        const int nb = rem >= 2 ? 16 : (rem == 1 ? 8 : 0);
+        const long long kofs = nb ? k0 : -kc;      // nothing is read when nb == 0; keep the address inside the row
+        double *as = As + (size_t)stage * BM * LDS + r0 * LDS + kc;
+        double *bs = Bs + (size_t)stage * BN * LDS + r0 * LDS + kc;
+        const double *ag = g.A + aoff + kofs, *bg = g.B + boff + kofs;
 #pragma unroll
-        for (int c = tid; c < BM * CPR; c += THREADS) {
-            const int r = c / CPR, kc = (c % CPR) * 2;
-            const int gr = min(m0 + r, g.M - 1);
-            const int rem = kvalid - (k0 + kc);
-            const int nb = rem >= 2 ? 16 : (rem == 1 ? 8 : 0);
-            const double *src = g.A + aoff + (long long)gr * g.lda + (nb ? k0 + kc : 0);
-            cp_async16_zfill(as + r * LDS + kc, src, nb);
-        }
+        for (int u = 0; u < NA; ++u)
+            if (BM % RSTEP == 0 || r0 + u * RSTEP < BM) cp_async16_zfill(as + u * RSTEP * LDS, ag + a_off[u], nb);
 #pragma unroll
-        for (int c = tid; c < BN * CPR; c += THREADS) {
-            const int r = c / CPR, kc = (c % CPR) * 2;
-            const int gr = min(n0 + r, g.N - 1);
-            const int rem = kvalid - (k0 + kc);
-            const int nb = rem >= 2 ? 16 : (rem == 1 ? 8 : 0);
-            const double *src = g.B + boff + (long long)gr * g.ldb + (nb ? k0 + kc : 0);
-            cp_async16_zfill(bs + r * LDS + kc, src, nb);
-        }
+        for (int u = 0; u < NB_; ++u)
+            if (BN % RSTEP == 0 || r0 + u * RSTEP < BN) cp_async16_zfill(bs + u * RSTEP * LDS, bg + b_off[u], nb);
     };
 
     double acc[FM][FN][2];
@@ -124,11 +127,10 @@ dgemm_nt_seg_kernel(const GemmArgs g) {
     for (int it = 0; it < niter; ++it) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
-        {   // prefetch tile it+STAGES-1 into the stage consumed at iteration it-1
-            const int nx = it + STAGES - 1;
-            if (nx < niter) load_tile(nx, nx % STAGES);
-            cp_async_commit();
-        }
+        // The prefetch of tile it+STAGES-1 (into the stage consumed at iteration it-1) is issued by warp w after its k-step
+        // (w mod 4): right after the barrier every warp would otherwise run the same address arithmetic at the same time and
+        // the tensor pipe would idle; staggered, some warp of every scheduler is always issuing DMMAs.
+        const int nx = it + STAGES - 1;
         const double *as = As + (size_t)(it % STAGES) * BM * LDS + (wm + frow) * LDS + fcol;
         const double *bs = Bs + (size_t)(it % STAGES) * BN * LDS + (wn + frow) * LDS + fcol;
 #pragma unroll
@@ -142,6 +144,10 @@ dgemm_nt_seg_kernel(const GemmArgs g) {
             for (int i = 0; i < FM; ++i)
 #pragma unroll
                 for (int j = 0; j < FN; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            if (kk / 4 == (((warp & 3) + 2 * (warp >> 2)) & 3)) {
+                if (nx < niter) load_tile(nx, nx % STAGES);
+                cp_async_commit();
+            }
         }
     }
     cp_async_wait<0>();

@@ -521,8 +521,6 @@ __global__ void __launch_bounds__(256, 2) k_gemm(Geo g, double *W, const int *ac
     for (int sl = 0; sl < nslab; ++sl) {
         asm volatile("cp.async.wait_group %0;" ::"n"(GSTG - 2) : "memory");
         __syncthreads();          // slab sl has landed for everyone, and everyone is done with the stage refilled next
-        if (sl + GSTG - 1 < nslab) issue(sl + GSTG - 1);
-        asm volatile("cp.async.commit_group;" ::: "memory");
         const double *Ar = sm + (size_t)(sl % GSTG) * GSTAGE, *Ai = Ar + TS * GLDA, *Br = Ai + TS * GLDA, *Bi = Br + GK * LDS_T;
 #pragma unroll
         for (int k4 = 0; k4 < GK; k4 += 4) {
@@ -549,6 +547,12 @@ __global__ void __launch_bounds__(256, 2) k_gemm(Geo g, double *W, const int *ac
                     dmma(cim[i][j].x, cim[i][j].y, nar[i], bi[j]);
                     dmma(cim[i][j].x, cim[i][j].y, nai[i], br[j]);
                 }
+            // the refill of the stage freed by the barrier is issued by warp w after its k-step (w mod 4): staggered, some warp
+            // of every scheduler is always issuing DMMAs while another does the address arithmetic
+            if (k4 / 4 == (((warp & 3) + 2 * (warp >> 2)) & 3)) {
+                if (sl + GSTG - 1 < nslab) issue(sl + GSTG - 1);
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            }
         }
     }
 #pragma unroll
