@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <memory>
+#include <type_traits>
 
 #include "common.cuh"
 #include "dgemm.cuh"
@@ -402,6 +403,111 @@ __global__ void __launch_bounds__(320, 1) k_tail_far_tma(const double *__restric
     }
 }
 
+// Warp-specialised variant: one producer warp keeps NST small stages (SR ring rows of T trajectories each) in flight with
+// cp.async.bulk against full/empty mbarrier pairs while the consumer warps run the Toeplitz update; a stage is handed back
+// as soon as its SR rows are consumed, so ~7/8 of the staging memory is always in flight (the two-stage kernel above has at
+// most half in flight and is bound by the bulk-copy latency: 3.2 us per 77 KB stage against 1.3 us of math).
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+template <int T, int SR, int NST>
+__global__ void __launch_bounds__(352, 1) k_tail_far_ws(const double *__restrict__ ring, const double *__restrict__ kern,
+                                                         double *__restrict__ out, int ntraj, int ml, int ncp, int base,
+                                                         int ages_per_split, double dt) {
+    static_assert(TB % SR == 0, "stage rows must divide the time block");
+    extern __shared__ __align__(128) double stage_mem[];   // [NST][T][SR][ncp]
+    __shared__ __align__(8) uint64_t full[NST], empty[NST];
+    const int ncons = blockDim.x - 32;                      // consumer threads (whole warps), then one producer warp
+    const int traj0 = blockIdx.x * T;
+    const int d_lo = blockIdx.y * ages_per_split, d_hi = min(d_lo + ages_per_split, ml);
+    const int nchunk = (d_hi - d_lo + TB - 1) / TB, nsub = nchunk * (TB / SR);
+    const size_t tstride = (size_t)ml * ncp, stage_elems = (size_t)T * SR * ncp;
+    const unsigned rowbytes = (unsigned)ncp * 8u;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < NST; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], (unsigned)(ncons / 32));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if ((int)threadIdx.x >= ncons) {                        // ---- producer warp (one elected lane)
+        if ((int)threadIdx.x == ncons) {
+            for (int sc = 0; sc < nsub; ++sc) {
+                const int st = sc % NST;
+                if (sc >= NST) mbar_wait(&empty[st], (unsigned)(((sc / NST) - 1) & 1));
+                double *dst = stage_mem + (size_t)st * stage_elems;
+                mbar_expect_tx(&full[st], (unsigned)(T * SR) * rowbytes);
+                int lo = (base - (d_lo + sc * SR) - (SR - 1)) % ml;
+                if (lo < 0) lo += ml;
+                const int n1 = min(SR, ml - lo);            // rows lo .. lo+n1-1, then (wrap) rows 0 .. SR-n1-1
+#pragma unroll
+                for (int k = 0; k < T; ++k) {
+                    const double *src = ring + (size_t)min(traj0 + k, ntraj - 1) * tstride;
+                    bulk_g2s(dst + (size_t)k * SR * ncp, src + (size_t)lo * ncp, (unsigned)n1 * rowbytes, &full[st]);
+                    if (n1 < SR) bulk_g2s(dst + ((size_t)k * SR + n1) * ncp, src, (unsigned)(SR - n1) * rowbytes, &full[st]);
+                }
+            }
+        }
+        return;
+    }
+    const int c = threadIdx.x;                              // ---- consumers: thread per column
+    const bool active = c < ncp;
+    const int cc = active ? c : 0;
+    double acc[T][TB];
+#pragma unroll
+    for (int k = 0; k < T; ++k)
+#pragma unroll
+        for (int s2 = 0; s2 < TB; ++s2) acc[k][s2] = 0.0;
+    // kernel window as a 32-entry circular register file: in a chunk of phase PH the logical entry kw[i] (i < 31) lives in
+    // W[(16 PH + i) & 31].  The 16 entries the next chunk adds are loaded straight into the slots that die during this chunk
+    // (4 per consumed stage, one stage later than their last use), so the window never shifts and needs no staging copy.
+    double W[32];
+#pragma unroll
+    for (int i = 0; i < 2 * TB - 1; ++i) W[i] = kern[(size_t)(d_lo + 2 + i) * ncp + cc];
+    W[31] = 0.0;
+    auto chunk = [&](auto ph, int ch) {
+        constexpr int O = decltype(ph)::value * TB;
+        const double *knext = kern + (size_t)(d_lo + (ch + 1) * TB + 2) * ncp + cc;     // logical entry i of the next chunk: knext[i * ncp]
+#pragma unroll
+        for (int q = 0; q < TB / SR; ++q) {
+            const int sc = ch * (TB / SR) + q, st = sc % NST;
+            mbar_wait(&full[st], (unsigned)((sc / NST) & 1));
+            const double *sp = stage_mem + (size_t)st * stage_elems + cc;
+#pragma unroll
+            for (int u = 0; u < SR; ++u) {
+                double pv[T];
+#pragma unroll
+                for (int k = 0; k < T; ++k) pv[k] = sp[((size_t)k * SR + (SR - 1 - u)) * ncp];
+#pragma unroll
+                for (int s2 = 0; s2 < TB; ++s2)
+#pragma unroll
+                    for (int k = 0; k < T; ++k) acc[k][s2] = fma(W[(O + q * SR + u + s2) & 31], pv[k], acc[k][s2]);
+            }
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[st]);     // this warp is done with the stage
+            // slots O + q SR .. O + q SR + SR-1 are dead now: they receive the next chunk's logical entries 16 + q SR + j
+#pragma unroll
+            for (int j = 0; j < SR; ++j)
+                if (q * SR + j + TB < 2 * TB - 1) W[(O + q * SR + j) & 31] = knext[(size_t)(TB + q * SR + j) * ncp];
+            if (q == 0) W[(O + 31) & 31] = knext[(size_t)(TB - 1) * ncp];      // the slot this chunk never used
+        }
+    };
+    for (int ch = 0; ch < nchunk; ch += 2) {
+        chunk(std::integral_constant<int, 0>{}, ch);
+        if (ch + 1 < nchunk) chunk(std::integral_constant<int, 1>{}, ch + 1);
+    }
+    if (active) {
+#pragma unroll
+        for (int s2 = 0; s2 < TB; ++s2)
+#pragma unroll
+            for (int k = 0; k < T; ++k)
+                if (traj0 + k < ntraj) out[(((size_t)blockIdx.y * TB + s2) * ntraj + traj0 + k) * ncp + c] = dt * acc[k][s2];
+    }
+}
+
 // tail[traj][c] = Near_s + sum_z Far[z][s]   (written where the phase kernels expect a single partial)
 __global__ void __launch_bounds__(256) k_tail_near(const double *__restrict__ ring, const double *__restrict__ kern,
                                                     const double *__restrict__ far, double *__restrict__ out, int ntraj, int ml,
@@ -469,7 +575,7 @@ struct sclmd_md {
     size_t ev_used = 0, ev_open = 0;
     double prof_ms[4] = {0, 0, 0, 0};   // 0 direct tail, 1 potforce, 2 far pass, 3 near
     long long prof_n[4] = {0, 0, 0, 0};
-    bool tail_block = true, far_tma = true;
+    bool tail_block = true, far_tma = true, far_ws = true;
     SplitPlan gplan{0, 1, 0}, cplan{0, 1, 0};
 
     void prof_begin(int kind, cudaStream_t stream = nullptr) {
@@ -595,11 +701,16 @@ struct sclmd_md {
                 static bool cfg = false;
                 if (!cfg) {
                     SCLMD_CUDA(cudaFuncSetAttribute(k_tail_far_tma<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+                    SCLMD_CUDA(cudaFuncSetAttribute(k_tail_far_ws<2, 4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
                     cfg = true;
                 }
-                const size_t sm = (size_t)2 * 2 * TB * b.ncp * sizeof(double);
-                k_tail_far_tma<2, 2><<<dim3(cdiv(ntraj, 2), b.far_nsplit), round_up(b.ncp, 32), sm, st>>>(b.ring.p, b.kern.p, b.far.p, ntraj,
-                                                                                                     b.ml, b.ncp, base, aps, dt);
+                const size_t sm = (size_t)2 * 2 * TB * b.ncp * sizeof(double);     // = 8 stages x 2 trajectories x 4 rows
+                if (far_ws)
+                    k_tail_far_ws<2, 4, 8><<<dim3(cdiv(ntraj, 2), b.far_nsplit), round_up(b.ncp, 32) + 32, sm, st>>>(b.ring.p, b.kern.p, b.far.p,
+                                                                                                                 ntraj, b.ml, b.ncp, base, aps, dt);
+                else
+                    k_tail_far_tma<2, 2><<<dim3(cdiv(ntraj, 2), b.far_nsplit), round_up(b.ncp, 32), sm, st>>>(b.ring.p, b.kern.p, b.far.p, ntraj,
+                                                                                                         b.ml, b.ncp, base, aps, dt);
             } else if (T == 4)
                 k_tail_far<4><<<grid, round_up(ct, 32), 0, st>>>(b.ring.p, b.kern.p, b.far.p, ntraj, b.ml, b.ncp, base, aps, ct, dt);
             else
@@ -973,6 +1084,7 @@ int sclmd_md_set_tail_block(sclmd_md *h, int on) {
     SCLMD_CUDA(cudaSetDevice(h->device));
     h->tail_block = on != 0;
     h->far_tma = on != 2;    // 2 = time-blocked with the plain-load far kernel (for A/B measurements)
+    h->far_ws = on != 3;     // 3 = time-blocked with the two-stage TMA kernel (no producer warp)
     for (auto &b : h->baths) {   // the partial-tail layout differs between the modes: rebuild S'(t-1)
         b->far_t0 = -1;
         if (b->ml > 1) if (int e = h->tail_step(*b, h->t - 1)) return e;
