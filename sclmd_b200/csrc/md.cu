@@ -71,7 +71,8 @@ __device__ __forceinline__ double bath_force(const BathDev &b, int traj, int ntr
 }
 
 // evaluation A (md.py:383-398): etot, ring push, f_A, p_half, q_next, heat current
-__global__ void __launch_bounds__(256) k_phase_a(BathSet bs, int nph, int ld, int ntraj, int nmd, long long t, double dt,
+template <int NBATH>      // baths the per-element loop is unrolled for (register pressure: 128 registers at 8, 1/4 occupancy)
+__global__ void __launch_bounds__(256, NBATH <= 2 ? 4 : 1) k_phase_a(BathSet bs, int nph, int ld, int ntraj, int nmd, long long t, double dt,
                                                   const double *__restrict__ q, const double *__restrict__ p,
                                                   const double *__restrict__ G, int gsplit, size_t gstride,
                                                   const double *__restrict__ Dcorr,
@@ -80,9 +81,9 @@ __global__ void __launch_bounds__(256) k_phase_a(BathSet bs, int nph, int ld, in
     const int traj = blockIdx.x;
     const size_t row = (size_t)traj * ld;
     const int slab = (int)(t % nmd);
-    double ke = 0.0, cur[MAXB];
+    double ke = 0.0, cur[NBATH];
 #pragma unroll
-    for (int b = 0; b < MAXB; ++b) cur[b] = 0.0;
+    for (int b = 0; b < NBATH; ++b) cur[b] = 0.0;
     for (int i = threadIdx.x; i < nph; i += blockDim.x) {
         const double pi = p[row + i], qi = q[row + i];
         double gsum = G[row + i];
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(256) k_phase_a(BathSet bs, int nph, int ld, in
         if (Dcorr) gsum -= Dcorr[row + i];   // K.constrain(q') = K.q' - K[:,c].q'[c]
         double f = -gsum;
 #pragma unroll
-        for (int b = 0; b < MAXB; ++b) {
+        for (int b = 0; b < NBATH; ++b) {
             if (b < bs.nb) {
                 const int a = bs.b[b].inv[i];
                 if (a >= 0) {
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(256) k_phase_a(BathSet bs, int nph, int ld, in
     ke = block_sum(ke, red);
     if (threadIdx.x == 0) etot[(size_t)slab * ntraj + traj] = ke;
 #pragma unroll
-    for (int b = 0; b < MAXB; ++b) {
+    for (int b = 0; b < NBATH; ++b) {
         if (b < bs.nb) {
             const double c = block_sum(cur[b], red);
             if (threadIdx.x == 0) bs.b[b].cur[(size_t)slab * ntraj + traj] = c;
@@ -118,7 +119,8 @@ __global__ void __launch_bounds__(256) k_phase_a(BathSet bs, int nph, int ld, in
 
 // evaluation B or C (md.py:401-404): pout = phalf + dt/2 * F(t+1; x, qn); `final` applies the
 // constraint (md.py:407-408) and commits q.
-__global__ void __launch_bounds__(256) k_phase_bc(BathSet bs, int nph, int ld, int ntraj, int nmd, long long t, double dt,
+template <int NBATH>
+__global__ void __launch_bounds__(256, NBATH <= 2 ? 4 : 1) k_phase_bc(BathSet bs, int nph, int ld, int ntraj, int nmd, long long t, double dt,
                                                    const double *__restrict__ x, const double *__restrict__ phalf,
                                                    const double *__restrict__ Gn, int gsplit, size_t gstride, double *__restrict__ pout,
                                                    const double *__restrict__ qn, double *__restrict__ qout,
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(256) k_phase_bc(BathSet bs, int nph, int ld, i
         for (int r = 0; r < reps; ++r) {
             double f = -g;
 #pragma unroll
-            for (int b = 0; b < MAXB; ++b) {
+            for (int b = 0; b < NBATH; ++b) {
                 if (b < bs.nb) {
                     const int a = bs.b[b].inv[i];
                     if (a >= 0) f += bath_force(bs.b[b], traj, ntraj, a, slab, xi);
@@ -740,7 +742,11 @@ struct sclmd_md {
         if (lin)
             for (auto &b : baths)
                 if (b->has_lin) if (int e = bath_lin(*b, p.p, q.p)) return e;
-        k_phase_a<<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, q.p, p.p, G.p, gplan.nsplit, (size_t)ntraj * ld, d_valid ? Dc.p : nullptr, phalf.p, qn.p, etot.p);
+        {
+            const double *dc = d_valid ? Dc.p : nullptr;
+            if (bs.nb <= 2) k_phase_a<2><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, q.p, p.p, G.p, gplan.nsplit, (size_t)ntraj * ld, dc, phalf.p, qn.p, etot.p);
+            else k_phase_a<MAXB><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, q.p, p.p, G.p, gplan.nsplit, (size_t)ntraj * ld, dc, phalf.p, qn.p, etot.p);
+        }
         d_valid = false;
         SCLMD_CUDA(cudaGetLastError());
         ++launches;
@@ -768,17 +774,20 @@ struct sclmd_md {
             ++launches;
         }
         if (!lin) {
-            k_phase_bc<<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, nullptr, phalf.p, Gn.p, gplan.nsplit, (size_t)ntraj * ld, p.p, qn.p, q.p, cm, 1, 1);
+            if (bs.nb <= 2) k_phase_bc<2><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, nullptr, phalf.p, Gn.p, gplan.nsplit, (size_t)ntraj * ld, p.p, qn.p, q.p, cm, 1, 1);
+            else k_phase_bc<MAXB><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, nullptr, phalf.p, Gn.p, gplan.nsplit, (size_t)ntraj * ld, p.p, qn.p, q.p, cm, 1, 1);
             SCLMD_CUDA(cudaGetLastError());
             ++launches;
         } else {
             for (auto &b : baths)
                 if (b->has_lin) if (int e = bath_lin(*b, phalf.p, qn.p)) return e;
-            k_phase_bc<<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, phalf.p, phalf.p, Gn.p, gplan.nsplit, (size_t)ntraj * ld, p1.p, qn.p, q.p, cm, 0, 0);
+            if (bs.nb <= 2) k_phase_bc<2><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, phalf.p, phalf.p, Gn.p, gplan.nsplit, (size_t)ntraj * ld, p1.p, qn.p, q.p, cm, 0, 0);
+            else k_phase_bc<MAXB><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, phalf.p, phalf.p, Gn.p, gplan.nsplit, (size_t)ntraj * ld, p1.p, qn.p, q.p, cm, 0, 0);
             SCLMD_CUDA(cudaGetLastError());
             for (auto &b : baths)
                 if (b->has_lin) if (int e = bath_lin(*b, p1.p, qn.p)) return e;
-            k_phase_bc<<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, p1.p, phalf.p, Gn.p, gplan.nsplit, (size_t)ntraj * ld, p.p, qn.p, q.p, cm, 1, 0);
+            if (bs.nb <= 2) k_phase_bc<2><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, p1.p, phalf.p, Gn.p, gplan.nsplit, (size_t)ntraj * ld, p.p, qn.p, q.p, cm, 1, 0);
+            else k_phase_bc<MAXB><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, p1.p, phalf.p, Gn.p, gplan.nsplit, (size_t)ntraj * ld, p.p, qn.p, q.p, cm, 1, 0);
             SCLMD_CUDA(cudaGetLastError());
             launches += 2;
         }
