@@ -102,7 +102,10 @@ int sclmd_md_get_etot(sclmd_md *h, double *etot);
 int sclmd_md_get_current_sums(sclmd_md *h, int bath, double *sums);
 
 /* etot and every bath's cur recorded at time slab `slab` (md.py:383,397):
- * out[1+nbaths][ntraj] = etot, cur_0, cur_1, ... */
+ * out[1+nbaths][ntraj] = etot, cur_0, cur_1, ...
+ * For the slab of the most recent step the call returns as soon as that step's first kernel (evaluation A, which
+ * produces these numbers) has finished -- the rest of the step keeps running while the caller prepares the next one;
+ * any other slab waits for all queued work.  Rows given to sclmd_md_set_noise_rows may be reused after it returns. */
 int sclmd_md_get_step_observables(sclmd_md *h, int slab, double *out);
 
 /* per-kernel timing with CUDA events on the handle's stream around every history-tail and

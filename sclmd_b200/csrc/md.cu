@@ -557,7 +557,9 @@ struct sclmd_md {
     long long t = 0;
     bool g_valid = false, have_dyn = false;
     cudaStream_t stc = nullptr;                  // copy stream: streamed noise rows overlap the running step
-    cudaEvent_t evN = nullptr;
+    cudaEvent_t evN = nullptr, evObs = nullptr;   // evObs: the observables of slab obs_slab (etot, currents) have been written
+    cudaStream_t str = nullptr;                   // read-back stream of sclmd_md_get_step_observables
+    long long obs_slab = -1;
     bool noise_pending = false;
     cudaStream_t st = nullptr, st2 = nullptr;   // st2: the FP64-bound K.q GEMM overlaps the HBM-bound history tails
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evG = nullptr;
@@ -746,6 +748,8 @@ struct sclmd_md {
             const double *dc = d_valid ? Dc.p : nullptr;
             if (bs.nb <= 2) k_phase_a<2><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, q.p, p.p, G.p, gplan.nsplit, (size_t)ntraj * ld, dc, phalf.p, qn.p, etot.p);
             else k_phase_a<MAXB><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, q.p, p.p, G.p, gplan.nsplit, (size_t)ntraj * ld, dc, phalf.p, qn.p, etot.p);
+            SCLMD_CUDA(cudaEventRecord(evObs, st));      // evaluation A wrote etot / currents of this slab
+            obs_slab = t % nmd;
         }
         d_valid = false;
         SCLMD_CUDA(cudaGetLastError());
@@ -832,6 +836,8 @@ int sclmd_md_create(int nph, int ntraj, double dt, int nmd, int device, sclmd_md
     SCLMD_CUDA(cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking));
     SCLMD_CUDA(cudaStreamCreateWithFlags(&h->stc, cudaStreamNonBlocking));
     SCLMD_CUDA(cudaEventCreateWithFlags(&h->evN, cudaEventDisableTiming));
+    SCLMD_CUDA(cudaEventCreateWithFlags(&h->evObs, cudaEventDisableTiming));
+    SCLMD_CUDA(cudaStreamCreateWithFlags(&h->str, cudaStreamNonBlocking));
     SCLMD_CUDA(cudaEventCreateWithFlags(&h->evA, cudaEventDisableTiming));
     SCLMD_CUDA(cudaEventCreateWithFlags(&h->evG, cudaEventDisableTiming));
     SCLMD_CUDA(cudaEventCreate(&h->ev0));
@@ -858,6 +864,8 @@ int sclmd_md_destroy(sclmd_md *h) {
     if (h->evA) cudaEventDestroy(h->evA);
     if (h->evG) cudaEventDestroy(h->evG);
     if (h->evN) cudaEventDestroy(h->evN);
+    if (h->evObs) cudaEventDestroy(h->evObs);
+    if (h->str) cudaStreamDestroy(h->str);
     if (h->stc) cudaStreamDestroy(h->stc);
     if (h->st2) cudaStreamDestroy(h->st2);
     if (h->st) cudaStreamDestroy(h->st);
@@ -1179,11 +1187,18 @@ int sclmd_md_get_step_observables(sclmd_md *h, int slab, double *out) {
     SCLMD_REQUIRE(h && out && slab >= 0 && slab < h->nmd, "sclmd_md_get_step_observables: bad arguments");
     SCLMD_CUDA(cudaSetDevice(h->device));
     const size_t n = (size_t)h->ntraj;
-    SCLMD_CUDA(cudaMemcpyAsync(out, h->etot.p + (size_t)slab * n, n * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    // The observables of a step are produced by its first kernel (evaluation A).  For the slab of the latest step the
+    // read-back only waits for that kernel (event), on its own stream, so the rest of the step keeps running while the host
+    // already prepares the next one; any other slab takes the fully synchronising path.
+    const bool latest = (long long)slab == h->obs_slab;
+    cudaStream_t s = latest ? h->str : h->st;
+    if (latest) SCLMD_CUDA(cudaStreamWaitEvent(h->str, h->evObs, 0));
+    SCLMD_CUDA(cudaMemcpyAsync(out, h->etot.p + (size_t)slab * n, n * sizeof(double), cudaMemcpyDeviceToHost, s));
     for (size_t b = 0; b < h->baths.size(); ++b)
         SCLMD_CUDA(cudaMemcpyAsync(out + (b + 1) * n, h->baths[b]->cur.p + (size_t)slab * n, n * sizeof(double),
-                                   cudaMemcpyDeviceToHost, h->st));
-    SCLMD_CUDA(cudaStreamSynchronize(h->st));
+                                   cudaMemcpyDeviceToHost, s));
+    SCLMD_CUDA(cudaStreamSynchronize(s));
+    SCLMD_CUDA(cudaStreamSynchronize(h->stc));      // rows handed to sclmd_md_set_noise_rows have been consumed by the DMA
     return SCLMD_OK;
 }
 
