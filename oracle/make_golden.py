@@ -294,12 +294,65 @@ def run_negf_cases():
     np.savez_compressed(os.path.join(GOLD, "sig.npz"), seL=seL, seR=seR, dosL=dosL, dosR=dosR, tm=s.tmnumber, ep=s.ep, eta=s.eta)
 
 
+# -------------------------------------------------------------- config 4 (current-induced example)
+def extract_c4_lambda():
+    """The reference reads examples/current-induced/grapheneLambda-r-0.3-ver2.nc with netCDF4 (rundp.py:10,76-77), which is
+    not installed here; the product's own HDF5 walker (sclmd_b200/myio.py) reads the same file.  The five 36x36 matrices the
+    example uses are stored as a fixture so that the GPU box (no reference tree) can rebuild the case."""
+    from sclmd_b200.myio import read_nc_variables
+    v = read_nc_variables(os.path.join(refshim.REFERENCE_ROOT, "examples", "current-induced", "grapheneLambda-r-0.3-ver2.nc"))
+    lam = {k: np.array(v[k]) for k in ("eta_r", "xim_r", "xip_r", "zeta1_r", "zeta2_r")}
+    assert all(a.shape == (36, 36) for a in lam.values())
+    assert np.abs(lam["eta_r"] - lam["eta_r"].T).max() < 1e-18 and np.abs(lam["xim_r"] + lam["xim_r"].T).max() < 1e-18
+    assert np.abs(lam["xip_r"] - lam["xip_r"].T).max() < 1e-18
+    np.savez_compressed(os.path.join(GOLD, "c4_lambda.npz"), **lam)
+    print("c4_lambda      eta_r max %.3e  xim_r max %.3e  xip_r max %.3e" %
+          (np.abs(lam["eta_r"]).max(), np.abs(lam["xim_r"]).max(), np.abs(lam["xip_r"]).max()))
+
+
+def run_c4_noise_case():
+    """enoise of the biased junction bath of rundp.py:76-77 (bias 1.0, wmax 2.0, zpmotion False) with the example's matrices:
+    complex Hermitian covariances, eigensystems captured from the reference, draws injected"""
+    lam = P.c4_lambda()
+    dt, nmd, T = 0.5 / 0.658, 16, 300.0
+    z = np.random.default_rng(66).standard_normal(4096)
+    captured = []
+    real_eigh = np.linalg.eigh
+
+    def cap_eigh(a):
+        av, au = real_eigh(a)
+        captured.append((np.array(av), np.array(au)))
+        return av, au
+    rnoise.LA.eigh = cap_eigh
+    saved = np.random.normal
+    np.random.normal = Stream(z)
+    with refshim.quiet():
+        en = rnoise.enoise(lam["eta_r"], lam["xim_r"], lam["xip_r"], 1.0, T, 2.0, dt, nmd, False, False)
+    used = np.random.normal.k
+    np.random.normal = saved
+    rnoise.LA.eigh = real_eigh
+    it = iter(captured)
+    s = Stream(z)
+    x = [O.vargau(*next(it), lambda sc: s(0.0, sc)) for _ in range(nmd // 2 + 1)]
+    oen = O.spectrum_to_series(np.array(x), dt, nmd)
+    ec = 0.0
+    for i, (av, au) in enumerate(captured):
+        ec = max(ec, np.max(np.abs((au * av) @ au.conj().T - O.e_covariance(i, lam["eta_r"], lam["xim_r"], lam["xip_r"], 1.0, T, 2.0, dt, nmd,
+                                                                              False, False))))
+    print("noise c4       e %.2e  covariance abs err %.2e  draws %d" % (relerr(oen, en), ec, used))
+    assert relerr(oen, en) < 1e-12 and ec < 1e-18
+    np.savez_compressed(os.path.join(GOLD, "noise_c4.npz"), en=en, e_av=np.array([a for a, _ in captured]),
+                        e_au=np.array([u for _, u in captured]), used=used)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
+    extract_c4_lambda()
     for name, fn in (("ph_full", md_case_ph_full), ("ph_local", md_case_ph_local), ("e_extra", md_case_e_extra),
-                     ("c1_shape", md_case_c1_shape)):
+                     ("c1_shape", md_case_c1_shape), ("c4_shape", P.md_case_c4_shape)):
         run_md_case(name, fn())
     run_noise_cases()
+    run_c4_noise_case()
     run_scalar_cases()
     run_negf_cases()
     print("golden fixtures written to", GOLD)

@@ -65,3 +65,22 @@ def powerspecp(ps, dt, nmd):
     psw = np.fft.ifft(pst, axis=1) * (2. * np.pi / dw)
     psw = np.real(np.transpose(psw * np.conjugate(psw)))
     return np.array([[i * dw, np.sum(psw[i]) / dt / nmd] for i in range(nmd)])
+
+
+def phbath_from_sig(s, direction, T, cats, nw, dt, nmd, ml, mcof=2.0, debye=None, eta_ad=0, classical=False, zpmotion=True):
+    """The step BEFORE the hot path: a `sig` lead self-energy sweep (selfenergy.py:153-166, frequencies in ps^-1, Sigma in
+    ps^-2) becomes the `phbath(sig=..., gwl=...)` of an MD run (baths.py:294,322-327,375-395), whose energies are in eV:
+    hbar w -> rpc * w and Sigma -> rpc^2 * Sigma with rpc = 6.582119569e-4 eV ps.  `debye` defaults to the end of the
+    self-energy grid divided by `mcof`, so that the kernel transform (`gmem` -> `gamt`) and the noise cutoff
+    (wmax = mcof * debye, baths.py:305-308,408) cover exactly the tabulated range.  Call `.gmem()` on the result before
+    stepping, as with the reference (md.Run never does, baths.py:412)."""
+    from .baths import phbath
+    se = np.asarray(s.getse(direction))                 # device sweep; also writes densityofstates_<direction>.dat
+    gwl = np.asarray(s.ep, dtype=float) * s.rpc
+    sig_md = se * s.rpc ** 2
+    if len(cats) != se.shape[1]:
+        raise ValueError("phbath_from_sig: %d bath dofs but the self-energy is %dx%d" % (len(cats), se.shape[1], se.shape[2]))
+    if debye is None:
+        debye = float(gwl[-1]) / mcof
+    return phbath(T, cats, debye, nw, dt, nmd, ml=ml, mcof=mcof, sig=sig_md, gwl=gwl, eta_ad=eta_ad, classical=classical,
+                  zpmotion=zpmotion)

@@ -168,4 +168,34 @@ def md_case_c1_shape():
                 q0=None, p0=None, kinds=["e", "e"], T=300.0, ic_seed=77)
 
 
-MD_CASES = dict(ph_full=md_case_ph_full, ph_local=md_case_ph_local, e_extra=md_case_e_extra, c1_shape=md_case_c1_shape)
+def c4_lambda():
+    """The 36x36 electron-phonon matrices of the reference's current-induced example (eta_r, xim_r, xip_r, zeta1_r,
+    zeta2_r of examples/current-induced/grapheneLambda-r-0.3-ver2.nc), extracted into a fixture by oracle/make_golden.py
+    with sclmd_b200.myio (the reference tree does not exist on the GPU box)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c4_lambda.npz"))
+    return {k: np.array(g[k]) for k in g.files}
+
+
+def md_case_c4_shape():
+    """config-4 shape (examples/current-induced/rundp.py:51-79): 242 atoms, nph = 726, 24 + 48 fixed dofs, two electron
+    baths on 120 dofs each with efric = I/damp, and a biased electron bath (bias = 1.0) on the 36 junction dofs with the
+    example's own friction / non-conservative / Berry matrices; zeta1 = zeta2 = None as in the script, so the
+    baths.py:233 quirk applies; dt = 0.5/0.658; zero initial conditions (noranvel); harmonic force constants."""
+    natoms, dt, nmd, nsteps = 242, 0.5 / 0.658, 32, 12
+    K = spring_chain_dyn(natoms, seed=15)
+    cons = [list(range(0 * 3, (7 + 1) * 3)), list(range(226 * 3, (241 + 1) * 3))]
+    cid = [list(range(8 * 3, (47 + 1) * 3)), list(range(186 * 3, (225 + 1) * 3)), list(range(111 * 3, (122 + 1) * 3))]
+    damp = 100 / 0.658211814201041
+    lam = c4_lambda()
+    e = dict(efric=[np.identity(120) / damp, np.identity(120) / damp, lam["eta_r"]],
+             exim=[None, None, lam["xim_r"]], exip=[None, None, lam["xip_r"]],
+             zeta1=[None] * 3, zeta2=[None] * 3, bias=[0.0, 0.0, 1.0])
+    noise = [injected_noise(1, nmd, len(cid[b]), seed=44 + b, sigma=0.003)[0] for b in range(3)]
+    n = 3 * natoms
+    return dict(K=K, dt=dt, nmd=nmd, nsteps=nsteps, cons=cons, cids=cid, noise=noise, e=e,
+                q0=np.zeros(n), p0=np.zeros(n), kinds=["e", "e", "e"], T=300.0)
+
+
+MD_CASES = dict(ph_full=md_case_ph_full, ph_local=md_case_ph_local, e_extra=md_case_e_extra, c1_shape=md_case_c1_shape,
+                c4_shape=md_case_c4_shape)

@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 import problems as P
+from oracle import sclmd_oracle as O
 
 pytestmark = pytest.mark.gpu
 
@@ -130,3 +131,48 @@ def test_equipartition_with_classical_white_baths():
     m._collect()
     ke = np.asarray(m.etot)[:, nmd // 4:].mean()          # 0.5 sum_i p_i^2
     assert abs(2 * ke / 18 / (U.kb * T) - 1) < 0.05
+
+
+def test_sig_to_phbath_pipeline(tmp_path, monkeypatch):
+    """runsig.py -> phbath(sig=..., gwl=...) -> gmem -> an MD step: lead self-energy sweep on the device,
+    unit conversion ps^-2 -> eV^2, gamma(w) = -Im Sigma/w, memory kernel by the device cosine transform; every stage
+    against the oracle restatement of the reference's formulas"""
+    from sclmd_b200.selfenergy import sig
+    from sclmd_b200.tools import phbath_from_sig
+    from sclmd_b200.md import md
+    monkeypatch.chdir(tmp_path)
+    m, dt, nmd, ml = 6, 0.25 / 0.658, 32, 24
+    K00, K11, K01 = P.chain_blocks(m, seed=7, k2=0.1)
+    full = np.zeros((2 * m, 2 * m))
+    full[:m, :m], full[m:, m:], full[:m, m:], full[m:, :m] = K00, K11, K01, K01.T
+    s = sig(None, 0.06, range(0, m), range(m, 2 * m), dynmatfile=full, num=60, eta=2e-3)
+    cats = list(range(3, 3 + m))
+    b = phbath_from_sig(s, 'R', 300.0, cats, nw=80, dt=dt, nmd=nmd, ml=ml)
+    assert os.path.exists('densityofstates_R.dat')
+    # oracle: the same chain of formulas (selfenergy.py:133-143, baths.py:375-395, baths.py:19-52)
+    rpc = O.RPC
+    se = np.array([O.sig_selfenergy(K00, K11, s.K01, s.K10, w, s.eta, 'R') for w in s.ep])
+    gwl = s.ep * rpc
+    gam = O.ggamma(se * rpc ** 2, gwl)
+    assert relerr(b.gamma, gam) < 1e-9
+    ev = np.linalg.eigvalsh(0.5 * (gam[5:] + np.transpose(gam[5:], (0, 2, 1))))
+    assert ev.min() > -1e-6 * np.abs(ev).max()                 # a lead self-energy damps: gamma(w) is positive semidefinite
+    assert abs(b.wmax - gwl[-1]) < 1e-15 * gwl[-1]
+    b.gmem()
+    want = O.gamt([dt * i for i in range(ml)], b.wl, gwl, gam)
+    assert b.kernel.shape == (ml, m, m) and relerr(b.kernel, want) < 1e-10
+    # the bath drives an ensemble step through the reference-shaped md class
+    natoms = 6
+    Kd = P.psd_project(P.spring_chain_dyn(natoms, seed=21))
+    mdrun = md(dt, nmd, 300.0, axyz=[["C", float(i), 0.0, 0.0] for i in range(natoms)], dyn=Kd, ntraj=3)
+    b.noise = P.injected_noise(3, nmd, m, seed=9)
+    mdrun.AddBath(b)
+    mdrun.noranvel()
+    mdrun.initialise()
+    mdrun.ResetHis()
+    ens = O.EnsembleMD(np.array(mdrun.dyn), dt, nmd, 3, None)
+    ens.add_bath(cats, want, P.injected_noise(3, nmd, m, seed=9))
+    for _ in range(10):
+        mdrun.vv(0)
+        ens.step()
+    assert relerr(mdrun.q, ens.q) < 1e-9 and relerr(mdrun.p, ens.p) < 1e-9

@@ -179,3 +179,28 @@ def test_odd_nmd_is_rejected():
     plan = N.ph_plan(np.array([np.eye(2)]), np.array([0.0]), 300.0, 1.0, DT, 2 * 7 * 11 * 13)   # not of the form 2^a 3^b 5^c
     with pytest.raises(SclmdError):
         plan.generate(1, seed=1)
+
+
+def test_config4_junction_bath_with_example_matrices(golden_dir):
+    """biased electron bath of examples/current-induced/rundp.py:76-77 (36x36 eta_r / xim_r / xip_r, bias 1.0, wmax 2.0,
+    zpmotion False): the reference's series from its own eigen-factors and draws, and the device's own factors"""
+    from sclmd_b200 import noise as N
+    g = np.load(os.path.join(golden_dir, "noise_c4.npz"))
+    lam = P.c4_lambda()
+    dt, nmd = 0.5 / 0.658, 16
+    z = np.random.default_rng(66).standard_normal(4096)
+    plan = N.e_plan(lam["eta_r"], lam["xim_r"], lam["xip_r"], 1.0, 300.0, 2.0, dt, nmd, False, False)
+    assert plan.is_complex
+    Ldev = plan.factors()
+    for i in range(nmd // 2 + 1):
+        A = O.e_covariance(i, lam["eta_r"], lam["xim_r"], lam["xip_r"], 1.0, 300.0, 2.0, dt, nmd, False, False)
+        ev, evec = np.linalg.eigh(A)
+        want = (evec * np.where(ev > 0, ev, 0.0)) @ evec.conj().T
+        assert np.abs(Ldev[i] @ Ldev[i].conj().T - want).max() / max(np.abs(A).max(), 1e-300) < 1e-10, i
+    L = g["e_au"] * np.sqrt(np.where(g["e_av"] > 0, g["e_av"], 0.0))[:, None, :]
+    plan.set_factors(L)
+    xi, used = indexed_draws(g["e_av"], z)
+    assert used == int(g["used"])
+    out = plan.generate(1, xi=xi[None])[0]
+    assert relerr(out, np.real(g["en"])) < 1e-12
+    plan.close()

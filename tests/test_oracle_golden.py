@@ -163,3 +163,43 @@ def test_sig(golden_dir):
     assert relerr(tm, g["tm"][:, 1]) < 1e-8
     # physics KAT: a perfect chain transmits one channel per dof inside the band
     assert 3.9 < tm[3] < 4.0001
+
+
+def test_noise_replay_config4_matrices(golden_dir):
+    """enoise of the biased junction bath of the current-induced example (rundp.py:76-77) with its own 36x36 matrices:
+    the oracle rebuilds the reference's series from the captured eigensystems and its covariance restatement matches"""
+    g = np.load(os.path.join(golden_dir, "noise_c4.npz"))
+    lam = P.c4_lambda()
+    dt, nmd = 0.5 / 0.658, 16
+    z = np.random.default_rng(66).standard_normal(4096)
+    k = [0]
+
+    def draw(scale):
+        v = scale * z[k[0]]
+        k[0] += 1
+        return v
+    x = [O.vargau(g["e_av"][i], g["e_au"][i], draw) for i in range(nmd // 2 + 1)]
+    en = O.spectrum_to_series(np.array(x), dt, nmd)
+    assert k[0] == int(g["used"]) and relerr(en, g["en"]) < 1e-12
+    for i in range(nmd // 2 + 1):
+        A = O.e_covariance(i, lam["eta_r"], lam["xim_r"], lam["xip_r"], 1.0, 300.0, 2.0, dt, nmd, False, False)
+        assert np.max(np.abs((g["e_au"][i] * g["e_av"][i]) @ g["e_au"][i].conj().T - A)) < 1e-18
+
+
+def test_netcdf4_reader_against_fixture(golden_dir):
+    """sclmd_b200.myio reads the reference's NetCDF-4 (HDF5) example file without netCDF4 / h5py; the fixture the GPU box
+    uses is what it read.  Needs the reference tree (this container only)."""
+    path = "/root/reference/examples/current-induced/grapheneLambda-r-0.3-ver2.nc"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    from sclmd_b200 import myio
+    v = myio.read_nc_variables(path)
+    lam = P.c4_lambda()
+    for k in ("eta_r", "xim_r", "xip_r", "zeta1_r", "zeta2_r"):
+        assert v[k].shape == (36, 36) and np.array_equal(v[k], lam[k])
+    assert v["hw"].shape == (36,) and v["U"].shape == (36, 36) and v["blist"].shape == (400,)
+    assert abs(np.abs(v["U"] @ v["U"].T - np.eye(36)).max()) < 1e-10           # the mode matrix it ships is orthogonal
+    ds = myio.Dataset(path, "r")                                                 # the access pattern of rundp.py:10,76
+    assert np.array_equal(ds["eta_r"][:], lam["eta_r"])
+    with pytest.raises(ValueError):
+        myio.read_nc_variables(__file__)
