@@ -664,8 +664,8 @@ __global__ void k_save(Geo g, const double *W, const int *act, double *Xs) {
 }
 
 // ------------------------------------------------------------------------------------------------ observable
-__global__ void __launch_bounds__(256) k_observe(Geo g, Problem p, const double *W, const int *act, const double *Xs, double *out, int w0,
-                                                 int mode) {
+__global__ void __launch_bounds__(256) k_observe(Geo g, Problem p, const double *W, const int *act, const double *Xs, double *out, int *status,
+                                                 int w0, int mode) {
     __shared__ double red[32];
     const int b = blockIdx.x, iw = w0 + b, lw = g.lw, n = g.np;
     const double *wre = W + (size_t)b * 2 * g.plane, *wim = wre + g.plane;
@@ -705,6 +705,7 @@ __global__ void __launch_bounds__(256) k_observe(Geo g, Problem p, const double 
     if (threadIdx.x == 0) {
         const double gam = 2.0 * w / p.damp;
         out[iw] = mode == 0 ? gam * gam * acc : (mode == 1 ? -2.0 * w * w * p.weight[iw] * acc : w * w * acc);
+        if (!isfinite(acc)) status[iw] = 1;      // a zero / NaN pivot somewhere upstream: reported as a singular matrix
     }
 }
 
@@ -973,7 +974,7 @@ int run_lu(int device, int n, const double *K, const int32_t *idxL, int nL, cons
             SCLMD_CUDA(enqueue_lu(g, p, s, dstat, w0, nbat, row_stop, 1.0, 0, dtiles.p));
         }
         g_prof.begin(6, s.st);
-        k_observe<<<nbat, 256, 0, s.st>>>(g, p, static_cast<const double *>(s.W.p), static_cast<const int *>(s.act.p), static_cast<const double *>(s.Xs.p), dout, w0, mode);
+        k_observe<<<nbat, 256, 0, s.st>>>(g, p, static_cast<const double *>(s.W.p), static_cast<const int *>(s.act.p), static_cast<const double *>(s.Xs.p), dout, dstat, w0, mode);
         g_prof.end(s.st);
         SCLMD_CUDA(cudaGetLastError());
     }

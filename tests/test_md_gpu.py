@@ -252,3 +252,53 @@ def test_errors_are_reported_not_fatal():
     with pytest.raises(SclmdError):
         e.add_bath([0, 0], np.zeros((1, 2)))       # duplicate dof
     e.close()
+
+
+def test_config5_shape_full_size_vs_oracle():
+    """BASELINE configs[4] per-trajectory shape at full size (3000 dofs, 2 baths x 300 dofs, diagonal 4096-step memory kernels) with a
+    random pre-existing history, so that the whole memory matters from the first step: both history-tail modes (time-blocked with the
+    warp-specialised ring pass, and direct) against the oracle across block boundaries and mid-block run() calls"""
+    from sclmd_b200.engine import MDEngine
+    natoms, nc, ml, ntraj, nmd = 1000, 300, 4096, 4, 64
+    nph, dt = 3 * natoms, 0.25 / 0.658
+    K = P.spring_chain_dyn(natoms, seed=5)
+    cids = [list(range(0, nc)), list(range(nph - nc, nph))]
+    kern = [P.diag_kernel(ml, nc, dt, 30 + b, tau=600.0) for b in range(2)]
+    nz = [P.injected_noise(ntraj, nmd, nc, seed=40 + b) for b in range(2)]
+    rng = np.random.default_rng(50)
+    q0, p0 = 0.05 * rng.standard_normal((ntraj, nph)), 0.02 * rng.standard_normal((ntraj, nph))
+    hist = [0.02 * rng.standard_normal((ntraj, ml, nc)) for _ in range(2)]      # phis[i] = p_{t-1-i}[cids]
+    ens = O.EnsembleMD(K, dt, nmd, ntraj, None)
+    for b in range(2):
+        ens.add_bath(cids[b], kern[b], nz[b])
+        ens.baths[b]["ring"][:, (-1 - np.arange(ml)) % ml, :] = hist[b]
+    ens.q[:], ens.p[:] = q0, p0
+    ens.t = -1
+    for b in ens.baths:
+        b["tail"] = ens._tail(b)             # S(0) = dt sum_j k[j] p_{-j}
+    ens.t = 0
+    engs = []
+    for mode in (1, 0):
+        e = MDEngine(nph, ntraj, dt, nmd)
+        e.set_dyn(K)
+        for b in range(2):
+            e.add_bath(cids[b], kern[b])
+            e.set_noise(b, nz[b])
+        e.set_tail_block(mode)
+        e.set_state(q0, p0, 0)
+        for b in range(2):
+            e.set_history(b, hist[b])
+        engs.append(e)
+    done = 0
+    for chunk in (20, 17):
+        ens.run(chunk)
+        done += chunk
+        for e in engs:
+            e.run(chunk)
+            q, p, t = e.get_state()
+            assert t == done and relerr(q, ens.q) < TOL_STEP and relerr(p, ens.p) < TOL_STEP, done
+    for b in range(2):
+        cur = engs[0].current(b)
+        assert relerr(cur[:, :done], ens.baths[b]["cur"][:, :done]) < 1e-8
+    for e in engs:
+        e.close()

@@ -130,3 +130,39 @@ def test_sig_24x24_vs_oracle():
     wtm = np.array([O.sig_tm(K00, K11, s.K01, s.K10, w, s.eta) for w in om])
     assert np.max(np.abs(tm - wtm)) < 1e-8 * max(1.0, np.abs(wtm).max())
     assert np.array_equal(s.iterations, np.array([O.sig_sgf(K00, K11, s.K01, s.K10, w, s.eta, 'R')[1] for w in om]))
+
+
+def test_bpt_config3_full_sweep_properties():
+    """size-independent properties at the full config-3 shape (n = 483, a few thousand frequencies, several batches and streams):
+    reciprocity T_LR(w) = T_RL(w) (the two sweeps factorise differently ordered matrices), 0 <= T <= number of channels,
+    batching invariance (any sub-range of the grid gives the same numbers), and agreement with the oracle on a sample"""
+    from sclmd_b200.negf import bpt
+    natoms = 201
+    K = P.spring_chain_dyn(natoms, seed=14) / O.RPC ** 2
+    fixed = [list(range(0, 60)), list(range(543, 603))]
+    bath = [list(range(60, 210)), list(range(393, 543))]
+    b = bpt(None, 0.25, 0.1, bath, fixed, dynmatfile=K, num=1000)
+    om = np.linspace(0.0, 0.25 / O.RPC, 1500)
+    t_lr = b.tm_sweep(om)
+    b2 = bpt(None, 0.25, 0.1, [bath[1], bath[0]], fixed, dynmatfile=K, num=1000)
+    t_rl = b2.tm_sweep(om)
+    scale = max(1.0, np.abs(t_lr).max())
+    assert np.max(np.abs(t_lr - t_rl)) < 1e-8 * scale
+    assert t_lr.min() > -1e-10 and t_lr.max() <= 150.0 + 1e-9 and t_lr[0] == 0.0
+    sub = b.tm_sweep(om[700:713])
+    assert np.max(np.abs(sub - t_lr[700:713])) < 1e-10 * scale
+    iL, iR = O.bpt_reduce_index(bath[0], 60), O.bpt_reduce_index(bath[1], 60)
+    for k in (1, 333, 901, 1499):
+        want = O.bpt_tm(b.dynmat, om[k], 0.1, iL, iR)
+        assert abs(t_lr[k] - want) < 1e-8 * max(1.0, abs(want)), k
+
+
+def test_bpt_singular_matrix_is_reported():
+    """numpy.linalg.LinAlgError in the reference (negf.py:208): a structurally singular M(w) must come back as an error"""
+    from sclmd_b200.negf import bpt
+    from sclmd_b200._lib import SclmdError
+    K = np.zeros((36, 36))
+    K[17, 17] = -(1e-9 * 1e-9)                               # at w = 0, z^2 = -(1e-9)^2: row 17 of M = z^2 - K is exactly zero
+    b = bpt(None, 0.25, 0.1, [list(range(3, 12)), list(range(24, 33))], [list(range(0, 3)), list(range(33, 36))], dynmatfile=K, num=4)
+    with pytest.raises(SclmdError):
+        b.tm_sweep(np.array([0.0]))
