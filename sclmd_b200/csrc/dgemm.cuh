@@ -191,6 +191,7 @@ inline cudaError_t launch_dgemm(const GemmArgs &g, int nsplit, cudaStream_t st, 
     const int cfg = force_cfg >= 0 ? force_cfg : (g.M > 64 ? 0 : (g.M > 16 ? 1 : 2));
     // 128x128 tiles, 32-deep K slabs (half the barriers of 16-deep ones: 29.6 -> 31.0 TFLOP/s on the K.q shape), 3 stages = 221 KB
     if (cfg == 0) return launch_dgemm_cfg<128, 128, 64, 32, 3, 32>(g, nsplit, st);
+    if (cfg == 3) return launch_dgemm_cfg<128, 64, 32, 32, 3, 16>(g, nsplit, st);      // narrow N: 64-wide tiles, 2 CTAs/SM
     if (cfg == 1) return launch_dgemm_cfg<64, 64, 32, 32, 4>(g, nsplit, st);
     return launch_dgemm_cfg<16, 128, 16, 32, 4>(g, nsplit, st);
 }
@@ -201,6 +202,18 @@ inline cudaError_t launch_dgemm(const GemmArgs &g, int nsplit, cudaStream_t st, 
 struct SplitPlan {
     int cfg, nsplit, kseg;
 };
+// number of K-splits (<= max_split) that fills whole waves best: `tiles` output tiles, `slots` CTAs resident on the device
+inline int wave_fit_splits(int tiles, int slots, int max_split) {
+    int best = 1;
+    double best_eff = 0.0;
+    for (int ns = 1; ns <= max_split; ++ns) {
+        const long long units = (long long)tiles * ns;
+        const long long rounds = (units + slots - 1) / slots;
+        const double eff = (double)units / (double)(rounds * slots);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = ns; }
+    }
+    return best;
+}
 inline SplitPlan plan_split_k(int M, int N, int K, int sms, int max_split) {
     SplitPlan best{M > 64 ? 0 : (M > 16 ? 1 : 2), 1, K};
     double best_cost = 1e300;

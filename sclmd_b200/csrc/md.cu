@@ -47,7 +47,7 @@ struct BathSet {
 };
 
 struct Bath {
-    int nc = 0, ncp = 0, ml = 1, kind = 0, nsplit = 1, Kw = 0;
+    int nc = 0, ncp = 0, ml = 1, kind = 0, nsplit = 1, Kw = 0, gemm_cfg = -1;
     bool has_lin = false, has_extra = false;
     double c0 = 1.0;
     DevBuf<int> cids, inv;
@@ -681,7 +681,7 @@ struct sclmd_md {
             g.A = b.ring.p; g.lda = (long long)b.ml * b.ncp; g.a_seg_stride = b.ncp; g.a_head = head; g.a_mod = b.ml;
             g.B = b.kern.p; g.ldb = b.ncp; g.b_seg_stride = (long long)b.nc * b.ncp; g.b_seg0 = 1;
             g.C = b.tailp.p; g.ldc = b.ncp; g.c_split_stride = (long long)ntraj * b.ncp; g.alpha = dt;
-            SCLMD_CUDA(launch_dgemm(g, b.nsplit, st));
+            SCLMD_CUDA(launch_dgemm(g, b.nsplit, st, b.gemm_cfg));
         }
         prof_end();
         ++launches;
@@ -969,6 +969,14 @@ int sclmd_md_add_bath(sclmd_md *h, const int32_t *cids, int nc, int ml, const do
                                                       : cdiv(ntraj, 128) * cdiv(nc, 128);
         int want = kernel_kind == SCLMD_KERNEL_DIAG ? 4 * h->nsm : 2 * h->nsm;
         b->nsplit = std::max(1, std::min({cdiv(want, tiles), 32, std::max(1, (ml - 1) / 64)}));
+        if (kernel_kind == SCLMD_KERNEL_FULL && ntraj > 64) {
+            // ring-segment GEMM [ntraj x nc] with a very deep K: 64-wide tiles when 128-wide ones would be mostly padding, and a
+            // split count that fills whole waves (6 tiles x 32 splits on 148 SMs ran two waves at 65 %)
+            const bool narrow = round_up(nc, 128) - nc >= 64;
+            b->gemm_cfg = narrow ? 3 : 0;
+            tiles = cdiv(ntraj, 128) * cdiv(nc, narrow ? 64 : 128);
+            b->nsplit = wave_fit_splits(tiles, h->nsm * (narrow ? 2 : 1), std::max(1, std::min(64, (ml - 1) / 64)));
+        }
         SCLMD_CUDA(b->tailp.alloc((size_t)b->nsplit * ntraj * ncp));
         if (kernel_kind == SCLMD_KERNEL_DIAG && ml >= 8 * TB) {
             b->blocked = true;
