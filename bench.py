@@ -466,7 +466,7 @@ def main():
                       "share_of_step": pa["potforce"]["ms"] / ms})
     if pa["tail_far"]["launches"]:
         per = pa["tail_far"]["ms"] / pa["tail_far"]["launches"]
-        cands.append({"kernel": "k_tail_far_ws<2,4,8> (time-blocked history pass, 16 steps per ring pass; producer warp + 8 TMA stages)", "bound": "hbm",
+        cands.append({"kernel": "k_tail_far_ws<2,8,5> (time-blocked history pass, 16 steps per ring pass; producer warp + 5 TMA stages of 8 ring rows)", "bound": "hbm",
                       "achieved": alg_ring / (per * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                       "frac": alg_ring / (per * 1e-3) / 1e9 / hbm_peak, "traffic": (traffic or {}).get("far_dram_bytes_per_launch"),
                       "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_ring, "avg_launch_ms": per,

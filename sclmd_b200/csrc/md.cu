@@ -407,8 +407,9 @@ __global__ void __launch_bounds__(320, 1) k_tail_far_tma(const double *__restric
 
 // Warp-specialised variant: one producer warp keeps NST small stages (SR ring rows of T trajectories each) in flight with
 // cp.async.bulk against full/empty mbarrier pairs while the consumer warps run the Toeplitz update; a stage is handed back
-// as soon as its SR rows are consumed, so ~7/8 of the staging memory is always in flight (the two-stage kernel above has at
-// most half in flight and is bound by the bulk-copy latency: 3.2 us per 77 KB stage against 1.3 us of math).
+// as soon as its SR rows are consumed, so (NST-1)/NST of the staging memory is always in flight (the two-stage kernel above
+// has at most half in flight and is bound by the bulk-copy latency: 3.2 us per 77 KB stage against 1.3 us of math).
+// Measured at C5 (ms per ring pass): 2 x 16 rows 2.93 | 16 x 2 rows 2.92 | 8 x 4 rows 2.42-2.62 | 4 x 8 rows 2.39 | 5 x 8 rows 2.19.
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
@@ -705,12 +706,13 @@ struct sclmd_md {
                 static bool cfg = false;
                 if (!cfg) {
                     SCLMD_CUDA(cudaFuncSetAttribute(k_tail_far_tma<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-                    SCLMD_CUDA(cudaFuncSetAttribute(k_tail_far_ws<2, 4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+                    SCLMD_CUDA(cudaFuncSetAttribute(k_tail_far_ws<2, 8, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
                     cfg = true;
                 }
-                const size_t sm = (size_t)2 * 2 * TB * b.ncp * sizeof(double);     // = 8 stages x 2 trajectories x 4 rows
+                const size_t sm = (size_t)2 * 2 * TB * b.ncp * sizeof(double);     // two stages x 2 trajectories x 16 rows
+                const size_t smws = (size_t)5 * 2 * 8 * b.ncp * sizeof(double);    // five stages x 2 trajectories x 8 rows
                 if (far_ws)
-                    k_tail_far_ws<2, 4, 8><<<dim3(cdiv(ntraj, 2), b.far_nsplit), round_up(b.ncp, 32) + 32, sm, st>>>(b.ring.p, b.kern.p, b.far.p,
+                    k_tail_far_ws<2, 8, 5><<<dim3(cdiv(ntraj, 2), b.far_nsplit), round_up(b.ncp, 32) + 32, smws, st>>>(b.ring.p, b.kern.p, b.far.p,
                                                                                                                  ntraj, b.ml, b.ncp, base, aps, dt);
                 else
                     k_tail_far_tma<2, 2><<<dim3(cdiv(ntraj, 2), b.far_nsplit), round_up(b.ncp, 32), sm, st>>>(b.ring.p, b.kern.p, b.far.p, ntraj,
