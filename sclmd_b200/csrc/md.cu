@@ -120,13 +120,15 @@ __global__ void __launch_bounds__(256, NBATH <= 2 ? 4 : 1) k_phase_a(BathSet bs,
 // evaluation B or C (md.py:401-404): pout = phalf + dt/2 * F(t+1; x, qn); `final` applies the
 // constraint (md.py:407-408) and commits q.
 template <int NBATH>
-__global__ void __launch_bounds__(256, NBATH <= 2 ? 4 : 1) k_phase_bc(BathSet bs, int nph, int ld, int ntraj, int nmd, long long t, double dt,
+__global__ void __launch_bounds__(256, NBATH <= 2 ? 4 : 1) k_phase_bc(BathSet bs, int nph, int ld, int ntraj, int nmd, long long t,
+                                                                      const long long *__restrict__ tptr, double dt,
                                                    const double *__restrict__ x, const double *__restrict__ phalf,
                                                    const double *__restrict__ Gn, int gsplit, size_t gstride, double *__restrict__ pout,
                                                    const double *__restrict__ qn, double *__restrict__ qout,
                                                    const unsigned char *__restrict__ cons, int final, int fused) {
     const int traj = blockIdx.x;
     const size_t row = (size_t)traj * ld;
+    if (tptr) t = *tptr;                    // captured in a CUDA graph: the step counter lives on the device
     const int slab = (int)((t + 1) % nmd);
     for (int i = threadIdx.x; i < nph; i += blockDim.x) {
         const double ph = phalf[row + i];
@@ -158,6 +160,10 @@ __global__ void __launch_bounds__(256, NBATH <= 2 ? 4 : 1) k_phase_bc(BathSet bs
         pout[row + i] = pnew;
     }
 }
+
+// device-resident step counter of the graph-captured part of a step
+__global__ void k_set_t(long long *t, long long v) { *t = v; }
+__global__ void k_advance_t(long long *t) { *t += 1; }
 
 // xq[traj] = [ x[cids] | q[cids] ]  (operand of the time-local matrix product, baths.py:236-249)
 __global__ void k_gather_xq(const int *__restrict__ cids, int nc, int ncp, int Kw, int ld,
@@ -582,6 +588,20 @@ struct sclmd_md {
     long long prof_n[4] = {0, 0, 0, 0};
     bool tail_block = true, far_tma = true, far_ws = true;
     SplitPlan gplan{0, 1, 0}, cplan{0, 1, 0};
+    // Steps without history tails (every bath ml == 1: the reference's shipped examples) are launch-bound for small systems:
+    // everything after evaluation A is captured once per G/Gn role into a CUDA graph and replayed; the step counter the
+    // captured kernels need lives on the device (d_t).
+    bool use_graphs = true, dt_synced = false;
+    cudaGraphExec_t gexec[2] = {nullptr, nullptr};
+    int gnodes[2] = {0, 0}, gpar = 0;
+    DevBuf<long long> d_t;
+    void drop_graphs() {
+        for (int i = 0; i < 2; ++i) {
+            if (gexec[i]) cudaGraphExecDestroy(gexec[i]);
+            gexec[i] = nullptr;
+        }
+        dt_synced = false;
+    }
 
     void prof_begin(int kind, cudaStream_t stream = nullptr) {
         if (!profiling) return;
@@ -735,6 +755,57 @@ struct sclmd_md {
         return 0;
     }
 
+    // everything of a step after evaluation A and the history tails: K.q', evaluations B and C, constraint correction.
+    // `tptr` != nullptr: enqueue for CUDA-graph capture (the step counter is read from the device).
+    int enqueue_rest(const BathSet &bs, bool lin, const long long *tptr) {
+        const unsigned char *cm = has_cons ? cons.p : nullptr;
+        const size_t gs = (size_t)ntraj * ld;
+        if (has_cons && use_corr) {
+            k_gather_qc<<<ntraj, 128, 0, st>>>(qn.p, ld, cidx.p, ncons, ldcons, qc.p);
+            SCLMD_CUDA(cudaGetLastError());
+            ++launches;
+        }
+        auto bc = [&](const double *x, double *pout, int final, int fused) -> cudaError_t {
+            if (bs.nb <= 2) k_phase_bc<2><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, tptr, dt, x, phalf.p, Gn.p, gplan.nsplit, gs, pout, qn.p, q.p, cm, final, fused);
+            else k_phase_bc<MAXB><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, tptr, dt, x, phalf.p, Gn.p, gplan.nsplit, gs, pout, qn.p, q.p, cm, final, fused);
+            ++launches;
+            return cudaGetLastError();
+        };
+        if (!lin) {
+            SCLMD_CUDA(bc(nullptr, p.p, 1, 1));
+        } else {
+            for (auto &b : baths)
+                if (b->has_lin) if (int e = bath_lin(*b, phalf.p, qn.p)) return e;
+            SCLMD_CUDA(bc(phalf.p, p1.p, 0, 0));
+            for (auto &b : baths)
+                if (b->has_lin) if (int e = bath_lin(*b, p1.p, qn.p)) return e;
+            SCLMD_CUDA(bc(p1.p, p.p, 1, 0));
+        }
+        if (has_cons && use_corr) {
+            // q_{t+1} = constrain(q') != q' (md.py:407-408), so the reference's force cache misses (md.py:449) and K.q is
+            // evaluated again.  Here: K.q_{t+1} = K.q' - K[:,cons].q'[cons], a GEMM over the constrained columns only.
+            GemmArgs g{};
+            g.M = ntraj; g.N = nph; g.Kseg = ldcons; g.nseg = 1; g.segs_per_split = 1;
+            g.A = qc.p; g.lda = ldcons; g.B = Kc.p; g.ldb = ldcons; g.C = Dc.p; g.ldc = ld; g.alpha = 1.0;
+            SCLMD_CUDA(launch_dgemm(g, 1, st, cplan.cfg));
+            ++launches;
+        }
+        return 0;
+    }
+    void finish_step() {      // host-side state after a step
+        if (has_cons && use_corr) {
+            d_valid = true;
+            std::swap(G.p, Gn.p);
+            gpar ^= 1;
+        } else if (has_cons) {
+            g_valid = false;
+        } else {
+            std::swap(G.p, Gn.p);
+            gpar ^= 1;
+        }
+        ++t;
+    }
+
     int step() {
         BathSet bs = view();
         const bool lin = any_lin();
@@ -758,6 +829,55 @@ struct sclmd_md {
         ++launches;
         bool any_tail = false;
         for (auto &b : baths) any_tail |= b->ml > 1;
+        if (has_cons && use_corr && !kc_valid) {
+            k_gather_kc<<<nph, 128, 0, st>>>(K.p, nph, ld, cidx.p, ncons, ldcons, Kc.p);
+            SCLMD_CUDA(cudaGetLastError());
+            kc_valid = true;
+            ++launches;
+        }
+        if (use_graphs && !any_tail && !profiling) {
+            // ---- graph path: K.q' + B + C + correction replayed as one launch
+            if (noise_pending) {
+                SCLMD_CUDA(cudaStreamWaitEvent(st, evN, 0));
+                noise_pending = false;
+            }
+            if (!dt_synced) {
+                k_set_t<<<1, 1, 0, st>>>(d_t.p, t);
+                SCLMD_CUDA(cudaGetLastError());
+                dt_synced = true;
+            }
+            if (!gexec[gpar]) {
+                const int64_t l0 = launches;
+                SCLMD_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                int e = potforce(qn.p, Gn.p);
+                if (!e) e = enqueue_rest(bs, lin, d_t.p);
+                if (!e) {
+                    k_advance_t<<<1, 1, 0, st>>>(d_t.p);
+                    if (cudaGetLastError() != cudaSuccess) e = SCLMD_ERR_CUDA;
+                }
+                cudaGraph_t graph = nullptr;
+                const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+                if (e || ce != cudaSuccess) {
+                    if (graph) cudaGraphDestroy(graph);
+                    if (!e) set_error("cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
+                    return e ? e : SCLMD_ERR_CUDA;
+                }
+                const cudaError_t ie = cudaGraphInstantiate(&gexec[gpar], graph, 0);
+                cudaGraphDestroy(graph);
+                if (ie != cudaSuccess) {
+                    gexec[gpar] = nullptr;
+                    set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+                    return SCLMD_ERR_CUDA;
+                }
+                gnodes[gpar] = (int)(launches - l0);
+                launches = l0;
+            }
+            SCLMD_CUDA(cudaGraphLaunch(gexec[gpar], st));
+            launches += gnodes[gpar];
+            finish_step();
+            return 0;
+        }
+        dt_synced = false;
         if (overlap && any_tail) {   // GEMM on st2 first (1 CTA/SM leaves room for the tail CTAs), tails on st
             SCLMD_CUDA(cudaEventRecord(evA, st));
             SCLMD_CUDA(cudaStreamWaitEvent(st2, evA, 0));
@@ -773,52 +893,8 @@ struct sclmd_md {
             SCLMD_CUDA(cudaStreamWaitEvent(st, evN, 0));
             noise_pending = false;
         }
-        const unsigned char *cm = has_cons ? cons.p : nullptr;
-        if (has_cons && use_corr) {
-            k_gather_qc<<<ntraj, 128, 0, st>>>(qn.p, ld, cidx.p, ncons, ldcons, qc.p);
-            SCLMD_CUDA(cudaGetLastError());
-            ++launches;
-        }
-        if (!lin) {
-            if (bs.nb <= 2) k_phase_bc<2><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, nullptr, phalf.p, Gn.p, gplan.nsplit, (size_t)ntraj * ld, p.p, qn.p, q.p, cm, 1, 1);
-            else k_phase_bc<MAXB><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, nullptr, phalf.p, Gn.p, gplan.nsplit, (size_t)ntraj * ld, p.p, qn.p, q.p, cm, 1, 1);
-            SCLMD_CUDA(cudaGetLastError());
-            ++launches;
-        } else {
-            for (auto &b : baths)
-                if (b->has_lin) if (int e = bath_lin(*b, phalf.p, qn.p)) return e;
-            if (bs.nb <= 2) k_phase_bc<2><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, phalf.p, phalf.p, Gn.p, gplan.nsplit, (size_t)ntraj * ld, p1.p, qn.p, q.p, cm, 0, 0);
-            else k_phase_bc<MAXB><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, phalf.p, phalf.p, Gn.p, gplan.nsplit, (size_t)ntraj * ld, p1.p, qn.p, q.p, cm, 0, 0);
-            SCLMD_CUDA(cudaGetLastError());
-            for (auto &b : baths)
-                if (b->has_lin) if (int e = bath_lin(*b, p1.p, qn.p)) return e;
-            if (bs.nb <= 2) k_phase_bc<2><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, p1.p, phalf.p, Gn.p, gplan.nsplit, (size_t)ntraj * ld, p.p, qn.p, q.p, cm, 1, 0);
-            else k_phase_bc<MAXB><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, p1.p, phalf.p, Gn.p, gplan.nsplit, (size_t)ntraj * ld, p.p, qn.p, q.p, cm, 1, 0);
-            SCLMD_CUDA(cudaGetLastError());
-            launches += 2;
-        }
-        if (has_cons && use_corr) {
-            // q_{t+1} = constrain(q') != q' (md.py:407-408), so the reference's force cache misses (md.py:449) and K.q is
-            // evaluated again.  Here: K.q_{t+1} = K.q' - K[:,cons].q'[cons], a GEMM over the constrained columns only.
-            if (!kc_valid) {
-                k_gather_kc<<<nph, 128, 0, st>>>(K.p, nph, ld, cidx.p, ncons, ldcons, Kc.p);
-                SCLMD_CUDA(cudaGetLastError());
-                kc_valid = true;
-                ++launches;
-            }
-            GemmArgs g{};
-            g.M = ntraj; g.N = nph; g.Kseg = ldcons; g.nseg = 1; g.segs_per_split = 1;
-            g.A = qc.p; g.lda = ldcons; g.B = Kc.p; g.ldb = ldcons; g.C = Dc.p; g.ldc = ld; g.alpha = 1.0;
-            SCLMD_CUDA(launch_dgemm(g, 1, st, cplan.cfg));
-            ++launches;
-            d_valid = true;
-            std::swap(G.p, Gn.p);
-        } else if (has_cons) {
-            g_valid = false;
-        } else {
-            std::swap(G.p, Gn.p);
-        }
-        ++t;
+        if (int e = enqueue_rest(bs, lin, nullptr)) return e;
+        finish_step();
         return 0;
     }
 };
@@ -849,6 +925,8 @@ int sclmd_md_create(int nph, int ntraj, double dt, int nmd, int device, sclmd_md
     h->gplan = plan_split_k(ntraj, nph, h->ld, h->nsm, 4);
     SCLMD_CUDA(h->q.alloc(n)); SCLMD_CUDA(h->p.alloc(n));
     SCLMD_CUDA(h->G.alloc(n * h->gplan.nsplit)); SCLMD_CUDA(h->Gn.alloc(n * h->gplan.nsplit));
+    SCLMD_CUDA(h->d_t.alloc(1));
+    h->use_graphs = getenv("SCLMD_NO_GRAPH") == nullptr;
     SCLMD_CUDA(h->phalf.alloc(n)); SCLMD_CUDA(h->p1.alloc(n)); SCLMD_CUDA(h->qn.alloc(n));
     SCLMD_CUDA(h->etot.alloc((size_t)nmd * ntraj));
     SCLMD_CUDA(h->cons.alloc(nph));
@@ -861,6 +939,7 @@ int sclmd_md_destroy(sclmd_md *h) {
     if (!h) return SCLMD_OK;
     cudaSetDevice(h->device);
     if (h->st) cudaStreamSynchronize(h->st);
+    h->drop_graphs();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->evA) cudaEventDestroy(h->evA);
@@ -876,6 +955,7 @@ int sclmd_md_destroy(sclmd_md *h) {
 }
 
 int sclmd_md_set_dyn(sclmd_md *h, const double *K) {
+    if (h) h->drop_graphs();      // captured kernel arguments are about to change
     SCLMD_REQUIRE(h && K, "sclmd_md_set_dyn: NULL argument");
     SCLMD_CUDA(cudaSetDevice(h->device));
     SCLMD_CUDA(cudaMemcpy2DAsync(h->K.p, h->ld * sizeof(double), K, h->nph * sizeof(double), h->nph * sizeof(double), h->nph,
@@ -889,6 +969,7 @@ int sclmd_md_set_dyn(sclmd_md *h, const double *K) {
 }
 
 int sclmd_md_set_constraint(sclmd_md *h, const int32_t *idx, int n) {
+    if (h) h->drop_graphs();      // captured kernel arguments are about to change
     SCLMD_REQUIRE(h && (n == 0 || idx), "sclmd_md_set_constraint: NULL argument");
     SCLMD_CUDA(cudaSetDevice(h->device));
     std::vector<unsigned char> m(h->nph, 0);
@@ -919,6 +1000,7 @@ int sclmd_md_set_constraint(sclmd_md *h, const int32_t *idx, int n) {
 
 int sclmd_md_add_bath(sclmd_md *h, const int32_t *cids, int nc, int ml, const double *kernel, int kernel_kind,
                       const double *Mq, const double *Mp, int *bath_out) {
+    if (h) h->drop_graphs();      // captured kernel arguments are about to change
     SCLMD_REQUIRE(h && cids && kernel, "sclmd_md_add_bath: NULL argument");
     SCLMD_REQUIRE(nc > 0 && ml >= 1, "sclmd_md_add_bath: nc and ml must be positive");
     SCLMD_REQUIRE(kernel_kind == SCLMD_KERNEL_FULL || kernel_kind == SCLMD_KERNEL_DIAG, "sclmd_md_add_bath: bad kernel_kind");
@@ -1036,6 +1118,7 @@ int sclmd_md_set_state(sclmd_md *h, const double *q, const double *p, int64_t t)
     SCLMD_CUDA(cudaStreamSynchronize(h->st));
     if (t >= 0 && t != h->t) {
         h->t = t;
+        h->dt_synced = false;
         for (auto &b : h->baths) b->far_t0 = -1;
     }
     if (q) { h->g_valid = false; h->d_valid = false; }
