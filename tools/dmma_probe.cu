@@ -61,7 +61,50 @@ void run(const char *name, int ctas_per_sm, int iters) {
     printf("%-28s FMxFN=%dx%d ld=%d ctas/SM=%d : %.2f TFLOP/s\n", name, FM, FN, LD, ctas_per_sm, flops / (best * 1e-3) / 1e12);
     cudaFree(d);
 }
+// do DFMA and DMMA share the FP64 datapath?  even warps run a DFMA chain, odd warps a DMMA chain
+__global__ void __launch_bounds__(256) k_mixed(double *out, int iters, int mode) {
+    const int warp = threadIdx.x >> 5;
+    const bool use_dmma = mode == 1 || (mode == 2 && (warp & 1));
+    double acc[16][2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i][0] = acc[i][1] = threadIdx.x * 1e-3 + i;
+    const double a = 1.0000001, b = 1e-9;
+    if (use_dmma) {
+        for (int it = 0; it < iters; ++it)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dmma(acc[i][0], acc[i][1], a, b);
+    } else {
+        for (int it = 0; it < iters; ++it)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { acc[i][0] = fma(acc[i][0], a, b); acc[i][1] = fma(acc[i][1], a, b); }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[i][0] + acc[i][1];
+    if (s == 123.456) out[0] = s;
+}
+void run_mixed(int mode, const char *name) {
+    double *d; cudaMalloc(&d, 8);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int iters = 20000, blocks = 148 * 4;
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(e0);
+        k_mixed<<<blocks, 256>>>(d, iters, mode);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (rep && ms < best) best = ms;
+    }
+    // per warp per iteration: DFMA warps 32 lanes x 32 FMA; DMMA warps 16 x 256 FMA
+    const double dfma = 2.0 * 32 * 32, dm = 2.0 * 16 * 256;
+    const double per_iter_block = mode == 0 ? 8 * dfma : (mode == 1 ? 8 * dm : 4 * dfma + 4 * dm);
+    printf("%-34s : %.2f TFLOP/s  (%.3f ms)\n", name, per_iter_block * iters * blocks / (best * 1e-3) / 1e12, best);
+    cudaFree(d);
+}
 int main() {
+    run_mixed(0, "all warps DFMA");
+    run_mixed(1, "all warps DMMA");
+    run_mixed(2, "half DFMA + half DMMA");
     run<8, 4, 0>("64x32 warp tile, regs held", 1, 4000);
     run<8, 4, 1>("64x32 warp tile, LDS per k4", 1, 4000);
     run<8, 4, 1>("64x32 warp tile, LDS per k4", 2, 4000);
