@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--cpu-steps", type=int, default=4, help="steps of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary workloads (C2 MD, NEGF)")
+    ap.add_argument("--no-overlap", action="store_true", help="run the K.q GEMM on the same stream as the history-tail kernels (A/B measurement)")
     ap.add_argument("--tail-block", type=int, default=1, help="1: time-blocked history tails (default); 0: direct, one ring pass per step")
     return ap.parse_args()
 
@@ -345,6 +346,8 @@ def main():
     rng = np.random.default_rng(2000 + rank)
     eng.set_state(0.05 * rng.standard_normal((ntraj, nph)), 0.02 * rng.standard_normal((ntraj, nph)), 0)
     eng.set_tail_block(args.tail_block)
+    if args.no_overlap:
+        eng.set_overlap(False)
     K, W = args.steps, max(args.warmup, 3)
 
     # ---------------- device-resident throughput (`value`)

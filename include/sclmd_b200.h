@@ -173,6 +173,12 @@ int sclmd_md_generate_noise(sclmd_md *h, int bath, sclmd_noise_plan *plan, uint6
  * transposed by the host (the interpolation indices are host-side, functions.py:117-143). */
 int sclmd_gamt(int device, int nt, int nw, int m, const double *tl, const double *wl,
                const double *giT, double *out);
+/* functions.myfft (functions.py:11-53) and the power spectra built on it (functions.py:203-236): batched complex transform with the
+ * in-house radix-2/3/4/5 kernels, out[f][m] = scale * sum_k in[f][k] exp(sign * 2 pi i k m / n); planar [batch][n], im may be NULL.
+ * myfft.iFourier1D = sign -1, scale dw/2pi; myfft.Fourier1D = sign +1, scale (2pi/dw)/n. */
+int sclmd_fft(int device, int n, int batch, const double *re, const double *im, int sign, double scale, double *out_re,
+              double *out_im);
+
 /* general form: out[nt][m] = alpha * sum_i c(tl_t, wl_i) giT[m][i] with
  *   c = cos(w t)                                                   (eta == 0)
  *   c = e^{-eta t}(w^2 cos wt + w eta sin wt)/(w^2 + eta^2)        (eta != 0: half of the bracket of baths.py:48-49)

@@ -455,6 +455,65 @@ __global__ void __launch_bounds__(256) k_fft_step2(const double2 *__restrict__ s
     }
 }
 
+// ---- generic batched complex transform (functions.myfft, functions.py:11-53; power spectra, functions.py:203-236) ----
+// Y[f][m] = scale * sum_k X[f][k] exp(sgn * 2 pi i k m / N); planar input/output [batch][N] (im may be NULL).
+// sgn = +1 is computed as the conjugate of the forward transform of the conjugate.
+__device__ __forceinline__ double2 load_c(const double *__restrict__ re, const double *__restrict__ im, size_t i, double cj) {
+    return make_double2(re[i], im ? cj * im[i] : 0.0);
+}
+__global__ void __launch_bounds__(256) k_c2c_direct(const double *__restrict__ re, const double *__restrict__ im, FftPlan pl, double cj,
+                                                     double scale, double *__restrict__ ore, double *__restrict__ oim) {
+    extern __shared__ double2 fs[];
+    const int N = pl.n;
+    const size_t base = (size_t)blockIdx.x * N;
+    double2 *a = fs, *b = fs + N;
+    for (int k = threadIdx.x; k < N; k += blockDim.x) a[k] = load_c(re, im, base + k, cj);
+    __syncthreads();
+    double2 *y = fft_smem(a, b, pl, 1);
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        ore[base + n] = y[n].x * scale;
+        oim[base + n] = cj * y[n].y * scale;
+    }
+}
+__global__ void __launch_bounds__(256) k_c2c_step1(const double *__restrict__ re, const double *__restrict__ im, FftPlan p1, int N, int N2,
+                                                    int tile, double cj, double2 *__restrict__ scratch) {
+    extern __shared__ double2 fs[];
+    const int N1 = p1.n, k20 = blockIdx.y * tile, nt = min(tile, N2 - k20);
+    const size_t base = (size_t)blockIdx.x * N;
+    double2 *a = fs, *b = fs + (size_t)tile * N1;
+    for (int e = threadIdx.x; e < nt * N1; e += blockDim.x) {
+        const int f = e % nt, k1 = e / nt;
+        a[(size_t)f * N1 + k1] = load_c(re, im, base + (size_t)k1 * N2 + k20 + f, cj);
+    }
+    __syncthreads();
+    double2 *y = fft_smem(a, b, p1, nt);
+    double2 *S = scratch + base;   // [n1][k2]
+    for (int e = threadIdx.x; e < nt * N1; e += blockDim.x) {
+        const int f = e % nt, n1 = e / nt;
+        double sn, cs;
+        sincospi(-2.0 * (double)((long long)n1 * (k20 + f) % N) / (double)N, &sn, &cs);
+        S[(size_t)n1 * N2 + k20 + f] = cmul(y[(size_t)f * N1 + n1], make_double2(cs, sn));
+    }
+}
+__global__ void __launch_bounds__(256) k_c2c_step2(const double2 *__restrict__ scratch, FftPlan p2, int N, int N1, int tile, double cj,
+                                                    double scale, double *__restrict__ ore, double *__restrict__ oim) {
+    extern __shared__ double2 fs[];
+    const int N2 = p2.n, n10 = blockIdx.y * tile, nt = min(tile, N1 - n10);
+    const size_t base = (size_t)blockIdx.x * N;
+    double2 *a = fs, *b = fs + (size_t)tile * N2;
+    const double2 *S = scratch + base + (size_t)n10 * N2;
+    for (int e = threadIdx.x; e < nt * N2; e += blockDim.x) a[e] = S[e];
+    __syncthreads();
+    double2 *y = fft_smem(a, b, p2, nt);
+    for (int e = threadIdx.x; e < nt * N2; e += blockDim.x) {
+        const int f = e % nt, n2 = e / nt;
+        const size_t n = base + n10 + f + (size_t)N1 * n2;
+        const double2 v = y[(size_t)f * N2 + n2];
+        ore[n] = v.x * scale;
+        oim[n] = cj * v.y * scale;
+    }
+}
+
 bool make_fft_plan(int n, FftPlan &pl) {
     pl.n = n;
     pl.npass = 0;
@@ -763,6 +822,50 @@ int sclmd_noise_plan_dims(sclmd_noise_plan *pl, int *nmd, int *nc) {
 }
 
 // out[nt][m] = alpha * sum_i table(tl_t, wl_i; eta) * giT[m][i]
+// functions.myfft / numpy.fft with the reference's conventions left to the caller: out[f][m] = scale * sum_k in[f][k] exp(sign 2 pi i k m / n)
+int sclmd_fft(int device, int n, int batch, const double *re, const double *im, int sign, double scale, double *out_re, double *out_im) {
+    SCLMD_REQUIRE(n > 0 && batch > 0 && re && out_re && out_im && (sign == 1 || sign == -1), "sclmd_fft: bad arguments");
+    if (int e = select_device(device)) return e;
+    FftPlan full, p1, p2;
+    SCLMD_REQUIRE(make_fft_plan(n, full), "sclmd_fft: n=%d is not of the form 2^a 3^b 5^c (in-house radix-2/3/4/5 FFT)", n);
+    const size_t tot = (size_t)n * batch;
+    DevBuf<double> dre, dim, ore, oim;
+    SCLMD_CUDA(dre.alloc(tot)); SCLMD_CUDA(ore.alloc(tot)); SCLMD_CUDA(oim.alloc(tot));
+    SCLMD_CUDA(cudaMemcpy(dre.p, re, tot * sizeof(double), cudaMemcpyHostToDevice));
+    if (im) {
+        SCLMD_CUDA(dim.alloc(tot));
+        SCLMD_CUDA(cudaMemcpy(dim.p, im, tot * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    const double cj = sign < 0 ? 1.0 : -1.0;
+    const size_t smem_direct = (size_t)2 * n * sizeof(double2);
+    if (smem_direct <= 200 * 1024) {
+        SCLMD_CUDA(cudaFuncSetAttribute(k_c2c_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_direct));
+        k_c2c_direct<<<batch, 256, smem_direct>>>(dre.p, dim.p, full, cj, scale, ore.p, oim.p);
+        SCLMD_CUDA(cudaGetLastError());
+    } else {
+        int best = 1;
+        for (int d = 1; (long long)d * d <= n; ++d)
+            if (n % d == 0) best = d;
+        const int N1 = best, N2 = n / best;
+        SCLMD_REQUIRE(make_fft_plan(N1, p1) && make_fft_plan(N2, p2) && (size_t)2 * N2 * sizeof(double2) <= 200 * 1024,
+                      "sclmd_fft: cannot split n=%d for the four-step transform", n);
+        DevBuf<double2> scratch;
+        SCLMD_CUDA(scratch.alloc(tot));
+        const int tile1 = std::max(1, std::min(N2, 2048 / N1)), tile2 = std::max(1, std::min(N1, 2048 / N2));
+        const size_t sm1 = (size_t)2 * tile1 * N1 * sizeof(double2), sm2 = (size_t)2 * tile2 * N2 * sizeof(double2);
+        SCLMD_CUDA(cudaFuncSetAttribute(k_c2c_step1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+        SCLMD_CUDA(cudaFuncSetAttribute(k_c2c_step2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+        k_c2c_step1<<<dim3(batch, cdiv(N2, tile1)), 256, sm1>>>(dre.p, dim.p, p1, n, N2, tile1, cj, scratch.p);
+        SCLMD_CUDA(cudaGetLastError());
+        k_c2c_step2<<<dim3(batch, cdiv(N1, tile2)), 256, sm2>>>(scratch.p, p2, n, N1, tile2, cj, scale, ore.p, oim.p);
+        SCLMD_CUDA(cudaGetLastError());
+    }
+    SCLMD_CUDA(cudaDeviceSynchronize());
+    SCLMD_CUDA(cudaMemcpy(out_re, ore.p, tot * sizeof(double), cudaMemcpyDeviceToHost));
+    SCLMD_CUDA(cudaMemcpy(out_im, oim.p, tot * sizeof(double), cudaMemcpyDeviceToHost));
+    return SCLMD_OK;
+}
+
 int sclmd_cos_transform(int device, int nt, int nw, int m, const double *tl, const double *wl, const double *giT, double eta,
                         double alpha, double *out) {
     SCLMD_REQUIRE(nt > 0 && nw > 0 && m > 0 && tl && wl && giT && out, "sclmd_cos_transform: bad arguments");

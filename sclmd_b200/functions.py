@@ -10,6 +10,43 @@ from . import units as U
 np.seterr(over="ignore")
 
 
+def device_fft(a, sign, scale, device=0):
+    """out[..., m] = scale * sum_k a[..., k] exp(sign 2 pi i k m / n) along the last axis, on the device (sclmd_fft)"""
+    from . import _lib
+    a = np.asarray(a)
+    n = a.shape[-1]
+    re = np.ascontiguousarray(a.real, dtype=np.float64).reshape(-1, n)
+    im = np.ascontiguousarray(a.imag, dtype=np.float64).reshape(-1, n) if np.iscomplexobj(a) else None
+    ore, oim = np.empty_like(re), np.empty_like(re)
+    _lib.check(_lib.lib().sclmd_fft(int(device), int(n), int(re.shape[0]), _lib.dptr(re), _lib.dptr(im), int(sign), float(scale),
+                                    _lib.dptr(ore), _lib.dptr(oim)))
+    return (ore + 1j * oim).reshape(a.shape)
+
+
+class myfft:
+    """functions.py:11-53 with the transforms on the device (lengths of the form 2^a 3^b 5^c)."""
+
+    def __init__(self, dt, n, device=0):
+        self.dt = dt
+        self.N = n
+        self.dw = 2 * np.pi / dt / n
+        self.device = device
+
+    def Fourier1D(self, a):
+        """f(j) = dt sum_i f(i) e^(+I 2pi i j/N)  ==  numpy.fft.ifft(a) * 2 pi / dw"""
+        if len(a) != self.N:
+            print("MyFFT.Fourier1D: array length error!")
+            sys.exit(0)
+        return device_fft(np.asarray(a), +1, (2. * np.pi / self.dw) / self.N, self.device)
+
+    def iFourier1D(self, a):
+        """f(i) = dw/2pi sum_j f(j) e^(-I 2pi i j/N)  ==  numpy.fft.fft(a) * dw / 2 pi"""
+        if len(a) != self.N:
+            print("MyFFT.iFourier1D: array length error!")
+            sys.exit(0)
+        return device_fft(np.asarray(a), -1, self.dw / 2 / np.pi, self.device)
+
+
 def bose(w, T):
     """functions.py:80-99 (bose(0,T>0) = 0 by fiat; T == 0 branches)."""
     if T == 0.0:
@@ -89,6 +126,30 @@ def dagger(a):
 def hermitianize(a):
     aa = np.array(a)
     return 0.5 * (aa + dagger(aa))
+
+
+def powerspecq(qs, dt, nmd, device=0):
+    """functions.py:203-218: (dw i)^2 sum_dof |Fourier1D(q)|^2 / (dt nmd); the batched transform runs on the device"""
+    qst = np.transpose(np.array(qs))
+    if nmd != qst.shape[1]:
+        print("power: qs shape error!")
+        sys.exit()
+    dw = 2. * np.pi / dt / nmd
+    qsw = device_fft(qst, +1, (2. * np.pi / dw) / nmd, device)
+    tot = np.sum(np.real(qsw * np.conjugate(qsw)), axis=0)
+    return np.array([[i * dw, (dw * i) ** 2 * tot[i] / dt / nmd] for i in range(nmd)])
+
+
+def powerspecp(ps, dt, nmd, device=0):
+    """functions.py:221-236: sum_dof |Fourier1D(p)|^2 / (dt nmd); the batched transform runs on the device"""
+    pst = np.transpose(np.array(ps))
+    if nmd != pst.shape[1]:
+        print("power: ps shape error!")
+        sys.exit()
+    dw = 2. * np.pi / dt / nmd
+    psw = device_fft(pst, +1, (2. * np.pi / dw) / nmd, device)
+    tot = np.sum(np.real(psw * np.conjugate(psw)), axis=0)
+    return np.array([[i * dw, tot[i] / dt / nmd] for i in range(nmd)])
 
 
 def rpadleft(bs, b):

@@ -57,14 +57,9 @@ def calTC(delta, dlist=1, bathnum=2, L=None, A=None):
 
 
 def powerspecp(ps, dt, nmd):
-    """functions.py:221-236: sum_dof |Fourier1D(p)|^2 / (dt nmd)"""
-    pst = np.transpose(np.array(ps))
-    if nmd != pst.shape[1]:
-        raise ValueError("power: ps shape error!")
-    dw = 2. * np.pi / dt / nmd
-    psw = np.fft.ifft(pst, axis=1) * (2. * np.pi / dw)
-    psw = np.real(np.transpose(psw * np.conjugate(psw)))
-    return np.array([[i * dw, np.sum(psw[i]) / dt / nmd] for i in range(nmd)])
+    """functions.py:221-236 (kept importable from tools as md.GetPower expects): device transform, see functions.powerspecp"""
+    from .functions import powerspecp as _p
+    return _p(ps, dt, nmd)
 
 
 def phbath_from_sig(s, direction, T, cats, nw, dt, nmd, ml, mcof=2.0, debye=None, eta_ad=0, classical=False, zpmotion=True):

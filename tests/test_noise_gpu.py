@@ -204,3 +204,33 @@ def test_config4_junction_bath_with_example_matrices(golden_dir):
     out = plan.generate(1, xi=xi[None])[0]
     assert relerr(out, np.real(g["en"])) < 1e-12
     plan.close()
+
+
+@pytest.mark.parametrize("n", [8, 60, 1000, 4096, 6000, 8192, 20000])
+def test_myfft_and_power_spectrum_on_the_device(n):
+    """functions.myfft (functions.py:11-53) and powerspecp (functions.py:221-236) with the in-house radix-2/3/4/5 transform,
+    direct (n <= 6400) and four-step, against numpy.fft with the reference's normalisation"""
+    from sclmd_b200.functions import myfft, powerspecp, device_fft
+    rng = np.random.default_rng(n)
+    dt = 0.25 / 0.658
+    a = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    f = myfft(dt, n)
+    dw = 2 * np.pi / dt / n
+    assert relerr(f.iFourier1D(a), np.fft.fft(a) * dw / 2 / np.pi) < 1e-12
+    assert relerr(f.Fourier1D(a), np.fft.ifft(a) * 2 * np.pi / dw) < 1e-12
+    assert relerr(f.Fourier1D(f.iFourier1D(a)), a) < 1e-12                    # round trip
+    b = rng.standard_normal((3, n))                                            # real batched input
+    assert relerr(device_fft(b, -1, 1.0), np.fft.fft(b, axis=1)) < 1e-12
+    if n <= 4096:
+        ps = rng.standard_normal((n, 5))
+        want = np.fft.ifft(ps.T, axis=1) * (2 * np.pi / dw)
+        want = np.sum(np.real(want * np.conj(want)), axis=0) / dt / n
+        got = powerspecp(ps, dt, n)
+        assert np.array_equal(got[:, 0], np.arange(n) * dw) and relerr(got[:, 1], want) < 1e-11
+
+
+def test_fft_rejects_unsupported_lengths():
+    from sclmd_b200.functions import device_fft
+    from sclmd_b200._lib import SclmdError
+    with pytest.raises(SclmdError):
+        device_fft(np.ones(14), -1, 1.0)          # 7 is not a supported radix
