@@ -214,6 +214,13 @@ int sclmd_bpt_tm_bias(int device, int n, const double *K, const int32_t *idxL, i
                       const int32_t *idxR, int nR, double damp, int b0, int nb, const double *bdamp,
                       const double *chiplus, const double *chiminus, double bias, const double *omegas,
                       int nw, double *tm_out);
+/* bpt.retargf / bpt.advangf (negf.py:206-212): the full Green function, green_out[nw][n][n] complex (interleaved re, im);
+ * nb == 0: no bias block; advanced != 0: advanced self-energies (the +i eps of z is kept, as negf.py:212 does). */
+int sclmd_bpt_green(int device, int n, const double *K, const int32_t *idxL, int nL,
+                    const int32_t *idxR, int nR, double damp, int b0, int nb, const double *bdamp,
+                    const double *chiplus, const double *chiminus, double bias, const double *omegas, int nw,
+                    int advanced, double *green_out);
+
 /* bpt.ps with bias (negf.py:234-236): w^2 Re Tr[(G^r Sigma^K G^a)[sel,sel]] with Sigma^K = totalkselfenergy
  * (negf.py:177-193) = kd[w] on the lead dofs + kr1[w] bdamp + kr2[w] chiplus + i ki[w] chiminus on the bias block;
  * the per-frequency weights carry the Bose factors (bosedist edge cases stay on the host side). */

@@ -663,6 +663,21 @@ __global__ void k_save(Geo g, const double *W, const int *act, double *Xs) {
     }
 }
 
+// the full solution X = M^-1 (mode 3: bpt.retargf / bpt.advangf): out[b][i][j] = (re, im) of row i of unit column j
+__global__ void k_extract(Geo g, const double *W, const int *act, double *out, int *status, int w0) {
+    const int b = blockIdx.y, n = g.nl;
+    const double *wre = W + (size_t)b * 2 * g.plane, *wim = wre + g.plane;
+    const int *actb = act + (size_t)b * g.nrp;
+    double2 *o = reinterpret_cast<double2 *>(out) + (size_t)b * n * n;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n * n; e += gridDim.x * blockDim.x) {
+        const int j = e % n, i = e / n;
+        const size_t src = (size_t)actb[i] * g.lw + g.np + j;
+        const double2 v = make_double2(wre[src], wim[src]);
+        o[e] = v;
+        if (!isfinite(v.x) || !isfinite(v.y)) status[w0 + b] = 1;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ observable
 __global__ void __launch_bounds__(256) k_observe(Geo g, Problem p, const double *W, const int *act, const double *Xs, double *out, int *status,
                                                  int w0, int mode) {
@@ -838,7 +853,8 @@ cudaError_t enqueue_lu(const Geo &g, const Problem &p, StreamSlot &s, int *statu
 
 int run_lu(int device, int n, const double *K, const int32_t *idxL, int nL, const int32_t *idxR, int nR, double damp,
            const double *omegas, int nw, int mode, const double *weight, const int32_t *sel, int nsel, double *out,
-           const BiasBlock *bb = nullptr) {
+           const BiasBlock *bb = nullptr, int advanced = 0) {
+    // mode 0 transmission, 1 power spectrum, 2 biased power spectrum, 3 the full Green function (out = [nw][n][n] complex, interleaved)
     SCLMD_REQUIRE(n > 0 && K && idxL && idxR && nL > 0 && nR > 0 && omegas && nw > 0 && out && damp != 0.0, "bpt: bad arguments");
     SCLMD_REQUIRE(n <= 1024, "bpt: n=%d exceeds the register-resident panel (n <= 1024)", n);
     if (int e = select_device(device)) return e;
@@ -860,6 +876,10 @@ int run_lu(int device, int n, const double *K, const int32_t *idxL, int nL, cons
     if (mode == 0) {
         rhs_o.assign(idxL, idxL + nL);
         rows_o.assign(idxR, idxR + nR);
+    } else if (mode == 3) {
+        rhs_o.resize(n);
+        std::iota(rhs_o.begin(), rhs_o.end(), 0);
+        rows_o = rhs_o;
     } else {
         SCLMD_REQUIRE(sel && nsel > 0 && (weight || mode == 2), "bpt.ps: empty selection");
         for (int i = 0; i < nsel; ++i) SCLMD_REQUIRE(sel[i] >= 0 && sel[i] < n, "bpt.ps: selected dof %d out of range", sel[i]);
@@ -956,6 +976,11 @@ int run_lu(int device, int n, const double *K, const int32_t *idxL, int nL, cons
 
     DevBuf<unsigned long long> dtiles;
     if (g_prof.on) SCLMD_CUDA(dtiles.alloc(1));
+    DevBuf<double> dgreen;
+    if (mode == 3) {
+        SCLMD_REQUIRE((size_t)nw * n * n <= ((size_t)1 << 28), "bpt: %d full Green functions of order %d do not fit the output buffer; sweep in pieces", nw, n);
+        SCLMD_CUDA(dgreen.alloc((size_t)nw * n * n * 2));
+    }
     const bool want_timing = getenv("SCLMD_BPT_TIMING") != nullptr;
     cudaEvent_t e0, e1;
     SCLMD_CUDA(cudaEventCreate(&e0));
@@ -970,6 +995,12 @@ int run_lu(int device, int n, const double *K, const int32_t *idxL, int nL, cons
             SCLMD_CUDA(enqueue_lu(g, p, s, dstat, w0, nbat, row_stop, -1.0, 1, dtiles.p));
             k_save<<<dim3(cdiv(g.np * g.nrhs, 256), nbat), 256, 0, s.st>>>(g, static_cast<const double *>(s.W.p), static_cast<const int *>(s.act.p), static_cast<double *>(s.Xs.p));
             SCLMD_CUDA(enqueue_lu(g, p, s, dstat, w0, nbat, row_stop, 1.0, 1, dtiles.p));
+        } else if (mode == 3) {
+            SCLMD_CUDA(enqueue_lu(g, p, s, dstat, w0, nbat, row_stop, advanced ? -1.0 : 1.0, advanced ? 1 : 0, dtiles.p));
+            k_extract<<<dim3(cdiv(n * n, 256), nbat), 256, 0, s.st>>>(g, static_cast<const double *>(s.W.p), static_cast<const int *>(s.act.p),
+                                                                      dgreen.p + (size_t)w0 * n * n * 2, dstat, w0);
+            SCLMD_CUDA(cudaGetLastError());
+            continue;
         } else {
             SCLMD_CUDA(enqueue_lu(g, p, s, dstat, w0, nbat, row_stop, 1.0, 0, dtiles.p));
         }
@@ -1003,7 +1034,8 @@ int run_lu(int device, int n, const double *K, const int32_t *idxL, int nL, cons
     if (want_timing)
         fprintf(stderr, "[bpt] device %.3f ms for %d frequencies in %d batches of %d on %d streams (%.0f omega/s device-only)\n", kms, nw,
                 nbatch, bsz, nslots, nw / (kms * 1e-3));
-    SCLMD_CUDA(cudaMemcpy(out, dout, nw * sizeof(double), cudaMemcpyDeviceToHost));
+    if (mode == 3) SCLMD_CUDA(cudaMemcpy(out, dgreen.p, (size_t)nw * n * n * 2 * sizeof(double), cudaMemcpyDeviceToHost));
+    else SCLMD_CUDA(cudaMemcpy(out, dout, nw * sizeof(double), cudaMemcpyDeviceToHost));
     std::vector<int> stv(nw);
     SCLMD_CUDA(cudaMemcpy(stv.data(), dstat, nw * sizeof(int), cudaMemcpyDeviceToHost));
     for (int i = 0; i < nw; ++i)
@@ -1067,6 +1099,16 @@ int sclmd_bpt_tm_bias(int device, int n, const double *K, const int32_t *idxL, i
     BiasBlock bb;
     bb.b0 = b0; bb.nb = nb; bb.bdamp = bdamp; bb.chiplus = chiplus; bb.chiminus = chiminus; bb.bias = bias;
     return run_lu(device, n, K, idxL, nL, idxR, nR, damp, omegas, nw, 0, nullptr, nullptr, 0, tm_out, &bb);
+}
+
+// bpt.retargf / bpt.advangf (negf.py:206-212): the full Green function of every frequency, G[nw][n][n] complex (interleaved re, im);
+// nb == 0: no bias block.  advangf keeps the +i eps of z (negf.py:212) and takes the advanced self-energies.
+int sclmd_bpt_green(int device, int n, const double *K, const int32_t *idxL, int nL, const int32_t *idxR, int nR, double damp,
+                    int b0, int nb, const double *bdamp, const double *chiplus, const double *chiminus, double bias,
+                    const double *omegas, int nw, int advanced, double *green_out) {
+    BiasBlock bb;
+    bb.b0 = b0; bb.nb = nb; bb.bdamp = bdamp; bb.chiplus = chiplus; bb.chiminus = chiminus; bb.bias = bias;
+    return run_lu(device, n, K, idxL, nL, idxR, nR, damp, omegas, nw, 3, nullptr, nullptr, 0, green_out, nb > 0 ? &bb : nullptr, advanced);
 }
 
 // bpt.ps with bias (negf.py:234-236): w^2 Re Tr[(G^r Sigma^K G^a)[sel,sel]], Sigma^K = totalkselfenergy (negf.py:177-193)

@@ -101,6 +101,89 @@ class bpt:
             return np.iinfo(np.int32).max
         return 1 / (np.exp(self.rpc * omega / self.bc / T) - 1)
 
+    # ---- the reference's building blocks (negf.py:153-215).  The sweeps above never form these matrices; they are kept for
+    #      scripts that call them directly.  Self-energies are O(n^2) assembly on the host, Green functions come from the device.
+    def cleanse(self, semat):
+        """negf.py:195-204"""
+        semat = np.delete(semat, self.dofatomfixed[0], axis=0)
+        semat = np.delete(semat, self.dofatomfixed[0], axis=1)
+        semat = np.delete(semat, [dof - len(self.dofatomfixed[0]) for dof in self.dofatomfixed[1]], axis=0)
+        semat = np.delete(semat, [dof - len(self.dofatomfixed[0]) for dof in self.dofatomfixed[1]], axis=1)
+        if len(semat) != len(self.dynmat) or self.natoms * 3 != len(self.dofatomfixed[0]) + len(self.dofatomfixed[1]) + len(semat):
+            raise ValueError('System DOF test failed, check again')
+        return semat
+
+    def retarselfenergy(self, omega, dofatoms):
+        """negf.py:153-157"""
+        semat = np.zeros((self.natoms * 3, self.natoms * 3), dtype=np.complex128)
+        for dofatom in dofatoms:
+            semat[dofatom, dofatom] = -1j * omega / self.damp
+        return self.cleanse(semat)
+
+    def advanselfenergy(self, omega, dofatoms):
+        return self.retarselfenergy(omega, dofatoms).conjugate().transpose()
+
+    def retarbiasselfenergy(self, omega, dofatoms):
+        """negf.py:162-172"""
+        if self.isbias:
+            semat = np.zeros((self.natoms * 3, self.natoms * 3), dtype=np.complex128)
+            t1, t2 = dofatoms[0], dofatoms[-1] + 1
+            semat[t1:t2, t1:t2] = -1j * omega * np.asarray(self.biasgamma) - self.bias * np.asarray(self.chiminus)
+            return self.cleanse(semat)
+        return 0
+
+    def advanbiasselfenergy(self, omega, dofatoms):
+        r = self.retarbiasselfenergy(omega, dofatoms)
+        return r.conjugate().transpose() if self.isbias else 0
+
+    def kselfenergy(self, omega, T, dofatoms):
+        """negf.py:177-178"""
+        return -2 * np.imag(self.retarselfenergy(omega, dofatoms)) * self.bosedist(omega, T)
+
+    def kbiasselfenergy(self, omega, T, dofatoms):
+        """negf.py:180-190"""
+        if self.isbias:
+            semat = np.zeros((self.natoms * 3, self.natoms * 3), dtype=np.complex128)
+            t1, t2 = dofatoms[0], dofatoms[-1] + 1
+            cp, cm = np.asarray(self.chiplus), np.asarray(self.chiminus)
+            with np.errstate(all="ignore"):
+                semat[t1:t2, t1:t2] = ((cp - 1j * cm) * (omega + self.bias) * (2 * self.bosedist(omega + self.bias, T) - 2 * self.bosedist(omega, T))
+                                       + (cp + 1j * cm) * (omega - self.bias) * (2 * self.bosedist(omega - self.bias, T) - 2 * self.bosedist(omega, T))) / 2
+            return (1j * self.retarbiasselfenergy(omega, dofatoms)) * 2 * self.bosedist(omega, T) + self.cleanse(semat)
+        return 0
+
+    def totalkselfenergy(self, omega, T):
+        """negf.py:192-193"""
+        return (self.kselfenergy(omega, T, self.dofatomofbath[0]) + self.kselfenergy(omega, T, self.dofatomofbath[1])
+                + self.kbiasselfenergy(omega, T, self.dofatomofbias))
+
+    def gamma(self, Pi):
+        """negf.py:214-215"""
+        return -1j * (Pi - Pi.conjugate().transpose())
+
+    def green_sweep(self, omegas, advanced=False):
+        """full Green functions G(w) [len(omegas), n, n] from the device (batched LU with the identity as right-hand side)"""
+        om = as_f64(np.atleast_1d(omegas))
+        n = len(self.dynmat)
+        iL, iR = self._reduced(self.dofatomofbath[0]), self._reduced(self.dofatomofbath[1])
+        out = np.empty((len(om), n, n), dtype=np.complex128)
+        if self.isbias:
+            b0, nb, (bd, cp, cm) = self._bias_block()
+            args = (b0, nb, dptr(bd), dptr(cp), dptr(cm), float(self.bias))
+        else:
+            args = (0, 0, None, None, None, 0.0)
+        check(_lib.lib().sclmd_bpt_green(self.device, n, dptr(self.dynmat), iptr(iL), len(iL), iptr(iR), len(iR), float(self.damp), *args,
+                                         dptr(om), len(om), 1 if advanced else 0, out.ctypes.data_as(_lib.c_double_p)))
+        return out
+
+    def retargf(self, omega):
+        """negf.py:206-208"""
+        return self.green_sweep([omega])[0]
+
+    def advangf(self, omega):
+        """negf.py:210-212 (the +1e-9j of z is kept, as the reference does)"""
+        return self.green_sweep([omega], advanced=True)[0]
+
     def tm_sweep(self, omegas):
         """T(w) for an array of frequencies (ps^-1) on the device (negf.py:240-242 for each)"""
         om = as_f64(omegas)

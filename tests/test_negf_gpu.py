@@ -166,3 +166,38 @@ def test_bpt_singular_matrix_is_reported():
     b = bpt(None, 0.25, 0.1, [list(range(3, 12)), list(range(24, 33))], [list(range(0, 3)), list(range(33, 36))], dynmatfile=K, num=4)
     with pytest.raises(SclmdError):
         b.tm_sweep(np.array([0.0]))
+
+
+def test_bpt_green_functions_and_building_blocks():
+    """bpt.retargf / advangf from the device (full inverse through the batched LU) and the self-energy building blocks, against
+    numpy on the reference's formulas (negf.py:153-215), with and without the biased block"""
+    from sclmd_b200.negf import bpt
+    K = P.spring_chain_dyn(12, seed=80) / O.RPC ** 2
+    fixed = [list(range(0, 3)), list(range(33, 36))]
+    bath = [list(range(3, 12)), list(range(24, 33))]
+    b = bpt(None, 0.25, 0.1, bath, fixed, dynmatfile=K, num=20)
+    n = len(b.dynmat)
+
+    def ref_gf(w, adv):
+        sl, sr = b.retarselfenergy(w, bath[0]), b.retarselfenergy(w, bath[1])
+        sb = b.retarbiasselfenergy(w, b.dofatomofbias)
+        if adv:
+            sl, sr = sl.conj().T, sr.conj().T
+            sb = sb.conj().T if b.isbias else 0
+        return np.linalg.inv((w + 1e-9j) ** 2 * np.identity(n) - b.dynmat - sl - sr - sb)
+    for w in (3.0, 57.3, 211.0):
+        assert relerr(b.retargf(w), ref_gf(w, False)) < 1e-9
+        assert relerr(b.advangf(w), ref_gf(w, True)) < 1e-9
+    g = b.gamma(b.retarselfenergy(57.3, bath[0]))
+    assert np.allclose(np.diag(g)[:9], -2 * 57.3 / 0.1) and abs(g[12, 12]) == 0      # negf.py:214-215 with Sigma = -i w/damp
+    t = np.real(np.trace(b.retargf(57.3) @ g @ b.retargf(57.3).conj().T @ b.gamma(b.retarselfenergy(57.3, bath[1]))))
+    assert abs(t - b.tm(57.3)) < 1e-8 * max(1.0, abs(t))              # the reference's own tm formula (negf.py:240-242)
+    bd, cp, cm = P.psd(6, 82, 2.0), P.sym(6, 83, 1.5), P.antisym(6, 84, 1.5)
+    b.setbias(0.6, bdamp=bd, chiplus=cp, chiminus=cm, dofatomofbias=list(range(15, 21)))
+    for w in (17.0, 140.0):
+        gr, ga = b.retargf(w), b.advangf(w)
+        assert relerr(gr, ref_gf(w, False)) < 1e-9 and relerr(ga, ref_gf(w, True)) < 1e-9
+        want = w ** 2 * np.trace(np.real(np.linalg.multi_dot([gr, b.totalkselfenergy(w, 300.0), ga])[12:18][:, 12:18]))
+        assert abs(b.ps(w, 300.0, list(range(15, 21))) - want) < 1e-8 * abs(want)     # negf.py:236 from the building blocks
+    sweep = b.green_sweep(np.array([17.0, 140.0]))
+    assert sweep.shape == (2, n, n) and relerr(sweep[1], ref_gf(140.0, False)) < 1e-9
