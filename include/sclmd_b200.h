@@ -237,6 +237,9 @@ int sclmd_sig_selfenergy(int device, int m, const double *K00, const double *K11
                          const double *K10, double eta, char direction, const double *omegas, int nw,
                          double *se_out, int32_t *iters_out);
 /* sig.tm / sig.gettm (selfenergy.py:145-151, 168-178) */
+/* sig.retargf (selfenergy.py:145-147): green_out[nw][m][m] complex (interleaved re, im) */
+int sclmd_sig_green(int device, int m, const double *K00, const double *K11, const double *K01,
+                    const double *K10, double eta, const double *omegas, int nw, double *green_out);
 int sclmd_sig_tm(int device, int m, const double *K00, const double *K11, const double *K01,
                  const double *K10, double eta, const double *omegas, int nw, double *tm_out);
 

@@ -79,6 +79,7 @@ _PROTOS = {
     "sclmd_bpt_green": (C.c_int, [C.c_int, C.c_int, c_double_p, c_int32_p, C.c_int, c_int32_p, C.c_int, C.c_double, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, C.c_double, c_double_p, C.c_int, C.c_int, c_double_p]),
     "sclmd_bpt_ps_bias": (C.c_int, [C.c_int, C.c_int, c_double_p, c_int32_p, C.c_int, c_int32_p, C.c_int, C.c_double, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, C.c_double, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, C.c_int, c_int32_p, C.c_int, c_double_p]),
     "sclmd_sig_selfenergy": (C.c_int, [C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p, C.c_double, C.c_char, c_double_p, C.c_int, c_double_p, c_int32_p]),
+    "sclmd_sig_green": (C.c_int, [C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p, C.c_double, c_double_p, C.c_int, c_double_p]),
     "sclmd_sig_tm": (C.c_int, [C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p, C.c_double, c_double_p, C.c_int, c_double_p]),
 }
 

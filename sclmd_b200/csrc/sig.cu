@@ -190,6 +190,15 @@ __global__ void __launch_bounds__(ST) k_sig(const SigArgs a) {
             __syncthreads();
             const cplx z2 = {w * w - 1e-16, 2.0 * w * 1e-8};
             inv_shift(g, s, z2, m, aug, red, &ired, &bad);
+            if (a.mode == 2) {            // sig.retargf: the Green function itself
+                for (int i = threadIdx.x; i < mm2; i += blockDim.x) {
+                    a.se_out[((size_t)iw * mm2 + i) * 2] = g[i].x;
+                    a.se_out[((size_t)iw * mm2 + i) * 2 + 1] = g[i].y;
+                }
+                if (threadIdx.x == 0) a.status[iw] = notconv ? 1 : (bad ? 2 : 0);
+                __syncthreads();
+                continue;
+            }
             // Gamma = -i (Sigma - Sigma^dagger):  Gamma_ij = -i (S_ij - conj(S_ji))
             for (int i = threadIdx.x; i < mm2; i += blockDim.x) {
                 const int r = i / m, c = i % m;
@@ -228,7 +237,7 @@ int run_sig(int device, int m, const double *K00, const double *K11, const doubl
     const size_t mm2 = (size_t)m * m;
     SCLMD_CUDA(k00.alloc(mm2)); SCLMD_CUDA(k11.alloc(mm2)); SCLMD_CUDA(k01.alloc(mm2)); SCLMD_CUDA(k10.alloc(mm2));
     SCLMD_CUDA(dom.alloc(nw)); SCLMD_CUDA(dit.alloc((size_t)2 * nw)); SCLMD_CUDA(dst.alloc(nw));
-    if (mode == 0) SCLMD_CUDA(dse.alloc((size_t)nw * mm2 * 2));
+    if (mode != 1) SCLMD_CUDA(dse.alloc((size_t)nw * mm2 * 2));
     else SCLMD_CUDA(dtm.alloc(nw));
     SCLMD_CUDA(cudaMemcpy(k00.p, K00, mm2 * 8, cudaMemcpyHostToDevice));
     SCLMD_CUDA(cudaMemcpy(k11.p, K11, mm2 * 8, cudaMemcpyHostToDevice));
@@ -246,9 +255,9 @@ int run_sig(int device, int m, const double *K00, const double *K11, const doubl
     std::vector<int> st(nw), it((size_t)2 * nw);
     SCLMD_CUDA(cudaMemcpy(st.data(), dst.p, nw * sizeof(int), cudaMemcpyDeviceToHost));
     SCLMD_CUDA(cudaMemcpy(it.data(), dit.p, (size_t)2 * nw * sizeof(int), cudaMemcpyDeviceToHost));
-    if (mode == 0) {
+    if (mode != 1) {
         SCLMD_CUDA(cudaMemcpy(se_out, dse.p, (size_t)nw * mm2 * 2 * 8, cudaMemcpyDeviceToHost));
-        if (iters_out) memcpy(iters_out, it.data(), nw * sizeof(int));
+        if (iters_out && mode == 0) memcpy(iters_out, it.data(), nw * sizeof(int));
     } else {
         SCLMD_CUDA(cudaMemcpy(tm_out, dtm.p, nw * 8, cudaMemcpyDeviceToHost));
     }
@@ -274,6 +283,13 @@ int sclmd_sig_selfenergy(int device, int m, const double *K00, const double *K11
     SCLMD_REQUIRE(direction == 'R' || direction == 'L', "Wrong direction, should only be R or L");
     SCLMD_REQUIRE(se_out, "sclmd_sig_selfenergy: NULL output");
     return run_sig(device, m, K00, K11, K01, K10, eta, 0, direction == 'R', omegas, nw, se_out, nullptr, iters_out);
+}
+
+// sig.retargf (selfenergy.py:145-147): G(w) = inv((w + 1e-8 i)^2 - K00 - Sigma_L - Sigma_R), green_out[nw][m][m] complex (interleaved)
+int sclmd_sig_green(int device, int m, const double *K00, const double *K11, const double *K01, const double *K10, double eta,
+                    const double *omegas, int nw, double *green_out) {
+    SCLMD_REQUIRE(green_out, "sclmd_sig_green: NULL output");
+    return run_sig(device, m, K00, K11, K01, K10, eta, 2, 0, omegas, nw, green_out, nullptr, nullptr);
 }
 
 int sclmd_sig_tm(int device, int m, const double *K00, const double *K11, const double *K01, const double *K10, double eta,

@@ -80,6 +80,20 @@ class sig:
                                       len(om), dptr(out)))
         return out
 
+    def green_sweep(self, omegas):
+        """G(w) = inv((w + 1e-8 i)^2 - K00 - Sigma_L - Sigma_R) for every frequency, on the device"""
+        om = as_f64(np.atleast_1d(omegas))
+        m = len(self.K00)
+        k00, k11, k01, k10 = self._k()
+        out = np.empty((len(om), m, m), dtype=np.complex128)
+        check(_lib.lib().sclmd_sig_green(self.device, m, dptr(k00), dptr(k11), dptr(k01), dptr(k10), float(self.eta), dptr(om),
+                                         len(om), out.ctypes.data_as(_lib.c_double_p)))
+        return out
+
+    def retargf(self, omega):
+        """selfenergy.py:145-147"""
+        return self.green_sweep([omega])[0]
+
     def tm(self, omega):
         """selfenergy.py:149-151"""
         return float(self.tm_sweep(np.array([omega], dtype=float))[0])

@@ -130,6 +130,13 @@ def test_sig_24x24_vs_oracle():
     wtm = np.array([O.sig_tm(K00, K11, s.K01, s.K10, w, s.eta) for w in om])
     assert np.max(np.abs(tm - wtm)) < 1e-8 * max(1.0, np.abs(wtm).max())
     assert np.array_equal(s.iterations, np.array([O.sig_sgf(K00, K11, s.K01, s.K10, w, s.eta, 'R')[1] for w in om]))
+    # sig.retargf (selfenergy.py:145-147) from the device and the reference's own tm formula built on it (selfenergy.py:149-151)
+    w = float(om[2])
+    sl, sr = s.selfenergy(w, 'L'), s.selfenergy(w, 'R')
+    g = s.retargf(w)
+    assert relerr(g, np.linalg.inv((w + 1e-8j) ** 2 * np.identity(m) - K00 - sl - sr)) < 1e-9
+    t = np.real(np.trace(g @ s.gamma(sl) @ g.conj().T @ s.gamma(sr)))
+    assert abs(t - tm[2]) < 1e-8 * max(1.0, abs(t))
 
 
 def test_bpt_config3_full_sweep_properties():
