@@ -127,6 +127,10 @@ int sclmd_md_get_profile_all(sclmd_md *h, double *ms, int64_t *n);
 
 /* instrumentation: kernels launched by this handle so far; name/time of the dominant kernel */
 int64_t sclmd_md_launch_count(sclmd_md *h);
+/* C[M x N] = alpha * A[M x K] . B[N x K]^T on the device, host buffers in and out: the building block of the stand-alone force
+ * evaluations md.potforce / md.force / bath.bforce (md.py:413-474, baths.py:224-255,448-458) of the Python layer. */
+int sclmd_dgemm_nt(int device, int M, int N, int K, const double *A, const double *B, double alpha, double *C);
+
 /* time `reps` launches of the history-tail kernel of `bath` alone (CUDA events): avg ms */
 int sclmd_md_time_tail(sclmd_md *h, int bath, int reps, float *avg_ms);
 int sclmd_md_time_potforce(sclmd_md *h, int reps, float *avg_ms);

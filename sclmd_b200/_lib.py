@@ -55,6 +55,7 @@ _PROTOS = {
     "sclmd_md_get_etot": (C.c_int, [C.c_void_p, c_double_p]),
     "sclmd_md_get_current_sums": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
     "sclmd_md_launch_count": (C.c_int64, [C.c_void_p]),
+    "sclmd_dgemm_nt": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, C.c_double, c_double_p]),
     "sclmd_md_time_tail": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p]),
     "sclmd_md_time_potforce": (C.c_int, [C.c_void_p, C.c_int, c_float_p]),
     "sclmd_noise_plan_create": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, c_double_p, C.c_int, c_int32_p, c_double_p, c_double_p, C.POINTER(C.c_void_p)]),
@@ -131,6 +132,17 @@ def as_f64(a, shape=None):
 
 def as_i32(a):
     return np.ascontiguousarray(np.asarray(list(a) if not isinstance(a, np.ndarray) else a), dtype=np.int32)
+
+
+def dgemm_nt(A, B, alpha=1.0, device=0):
+    """alpha * A . B^T on the device (A [M,K], B [N,K] host arrays)"""
+    A = np.ascontiguousarray(np.atleast_2d(A), dtype=np.float64)
+    B = np.ascontiguousarray(np.atleast_2d(B), dtype=np.float64)
+    if A.shape[1] != B.shape[1]:
+        raise ValueError("dgemm_nt: inner dimensions differ")
+    out = np.empty((A.shape[0], B.shape[0]))
+    check(lib().sclmd_dgemm_nt(int(device), A.shape[0], B.shape[0], A.shape[1], dptr(A), dptr(B), float(alpha), dptr(out)))
+    return out
 
 
 def device_count():

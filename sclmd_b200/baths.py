@@ -57,9 +57,12 @@ class _BathBase:
         self._noise = None if value is None else np.asarray(value, dtype=float)
         self._noise_version += 1
 
-    def bforce(self, t, phis, qhis):
-        raise NotImplementedError("bforce is fused into the device time step (sclmd_b200/csrc/md.cu); "
-                                  "use md.vv()/md.Run(). There is no host-side force path.")
+    def _noise_row(self, t):
+        nz = self.noise
+        if nz is None:
+            raise RuntimeError("bforce: the bath has no host copy of its noise (generated on the device); set bath.noise or call gnoi()")
+        nz = np.asarray(nz)
+        return nz[t % self.nmd] if nz.ndim == 2 else nz[0, t % self.nmd]
 
     def _engine_kernel(self):
         """(kernel, Mq, Mp) for MDEngine.add_bath: diagonal storage when every kernel[j] is diagonal."""
@@ -142,6 +145,18 @@ class ebath(_BathBase):
         plan = self._plan(self.device)
         self.noise = plan.generate(1, int(np.random.randint(0, 2 ** 62)))[0]
         plan.close()
+
+    def bforce(self, t, phis, qhis):
+        """baths.py:224-255 as a stand-alone call (the time loop itself never calls it: the force is fused into the device step).
+        The matrix products run on the device (sclmd_dgemm_nt)."""
+        from .noise import mf
+        pc, qc = np.asarray(phis)[0][self.cids], np.asarray(qhis)[0][self.cids]
+        f = self._noise_row(t) - _lib.dgemm_nt(pc[None], np.asarray(self.efric, dtype=float), 1.0, self.device)[0]
+        ex = [np.asarray(m, dtype=float) if m is not None else None for m in (self.exim, self.zeta1, self.zeta2)]
+        if all(m is not None and np.any(m) for m in ex):            # baths.py:233: only if all three have a non-zero element
+            f = f + self.bias * _lib.dgemm_nt(qc[None], ex[0] - ex[1], 1.0, self.device)[0]
+            f = f - self.bias * _lib.dgemm_nt(pc[None], ex[2], 1.0, self.device)[0]
+        return mf(f, self.cids, len(np.asarray(phis)[0]))
 
     def _engine_extra(self):
         """baths.py:233: the exim / zeta1 / zeta2 forces act only if ALL THREE have a non-zero entry."""
@@ -277,6 +292,16 @@ class phbath(_BathBase):
                                                      float(self.dt), dptr(out)))
                 self.gammaOld = self.gamma
                 self.gamma = out.reshape((len(gw),) + self.kernel.shape[1:])
+
+    def bforce(self, t, phis, qhis):
+        """baths.py:448-458 as a stand-alone call: noise - sum_i kernel[i] . phis[i][cids] (* dt when ml > 1), contracted on the device"""
+        from .noise import mf
+        kern = np.asarray(self.kernel, dtype=float)
+        ml = kern.shape[0]
+        hist = np.asarray(phis)[:ml][:, self.cids].reshape(1, -1)                       # [1, ml*nc]
+        fric = _lib.dgemm_nt(hist, np.ascontiguousarray(kern.transpose(1, 0, 2)).reshape(self.nc, -1), 1.0, self.device)[0]
+        f = self._noise_row(t) - (fric * self.dt if ml > 1 else fric)
+        return mf(f, self.cids, len(np.asarray(phis)[0]))
 
     def _engine_extra(self):
         return None, None

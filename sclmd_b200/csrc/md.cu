@@ -1344,6 +1344,25 @@ int sclmd_md_generate_noise(sclmd_md *h, int bath, sclmd_noise_plan *plan, uint6
     return sclmd_noise_plan_generate_into(plan, h->ntraj, seed, traj0, b.noise.p, h->ntraj, b.ncp, 0);
 }
 
+// C[M x N] = alpha * A[M x K] . B[N x K]^T on the device with host buffers (the DMMA GEMM of dgemm.cuh).  The stand-alone force
+// evaluations of the reference-shaped classes (md.potforce, md.force, bath.bforce: md.py:413-474, baths.py:224-255,448-458) are built on it.
+int sclmd_dgemm_nt(int device, int M, int N, int K, const double *A, const double *B, double alpha, double *C) {
+    SCLMD_REQUIRE(M > 0 && N > 0 && K > 0 && A && B && C, "sclmd_dgemm_nt: bad arguments");
+    if (int e = select_device(device)) return e;
+    const int ldk = K + (K & 1), ldc = N + (N & 1);      // 16-byte aligned rows (pads are zero)
+    DevBuf<double> dA, dB, dC;
+    SCLMD_CUDA(dA.alloc((size_t)M * ldk)); SCLMD_CUDA(dB.alloc((size_t)N * ldk)); SCLMD_CUDA(dC.alloc((size_t)M * ldc));
+    SCLMD_CUDA(cudaMemcpy2D(dA.p, ldk * sizeof(double), A, K * sizeof(double), K * sizeof(double), M, cudaMemcpyHostToDevice));
+    SCLMD_CUDA(cudaMemcpy2D(dB.p, ldk * sizeof(double), B, K * sizeof(double), K * sizeof(double), N, cudaMemcpyHostToDevice));
+    GemmArgs g{};
+    g.M = M; g.N = N; g.Kseg = ldk; g.nseg = 1; g.segs_per_split = 1;
+    g.A = dA.p; g.lda = ldk; g.B = dB.p; g.ldb = ldk; g.C = dC.p; g.ldc = ldc; g.alpha = alpha;
+    SCLMD_CUDA(launch_dgemm(g, 1, nullptr));
+    SCLMD_CUDA(cudaDeviceSynchronize());
+    SCLMD_CUDA(cudaMemcpy2D(C, N * sizeof(double), dC.p, ldc * sizeof(double), N * sizeof(double), M, cudaMemcpyDeviceToHost));
+    return SCLMD_OK;
+}
+
 int sclmd_md_time_tail(sclmd_md *h, int bath, int reps, float *avg_ms) {
     if (int e = check_bath(h, bath, "sclmd_md_time_tail")) return e;
     SCLMD_REQUIRE(reps > 0 && avg_ms, "sclmd_md_time_tail: bad arguments");

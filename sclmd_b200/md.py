@@ -10,6 +10,8 @@ import sys
 import time
 
 import numpy as np
+
+from . import _lib
 from numpy import linalg as LA
 
 from . import units as U
@@ -332,10 +334,32 @@ class md:
         return ms
 
     def force(self, t, p, q, id=0):
-        raise NotImplementedError("md.force is fused into the device time step; use vv()/Run()")
+        """md.py:413-435 as a stand-alone evaluation for one trajectory (vv()/Run() never call it: the three force evaluations of a
+        step are fused into the device kernels).  Histories come from the device ring; products run on the device."""
+        from .functions import rpadleft
+        it = t + id
+        pf = self.potforce(q)
+        phis = np.asarray(self.phis)
+        phis = phis if phis.ndim == 2 else phis[0]
+        qhis = np.zeros_like(phis)
+        qhis[0] = np.asarray(q, dtype=float)            # only row 0 of the q history is ever read (baths.py:246-249)
+        if id != 0:                                     # md.py:426-431: id = 0 uses the stored history as it is
+            phis = rpadleft(phis, p)
+        for i in range(len(self.baths)):
+            self.fbaths[i] = self.baths[i].bforce(it, phis, qhis)
+            pf = pf + self.fbaths[i]
+        return pf
 
     def potforce(self, q):
-        raise NotImplementedError("md.potforce is fused into the device time step; use vv()/Run()")
+        """md.py:437-474, harmonic branch: f = -dyn . q on the device (one trajectory or [ntraj, nph])"""
+        if self.pforce is not None:
+            return self.pforce.force(q)
+        if self.dyn is None:
+            print("no driver, no md")
+            sys.exit()
+        q = np.asarray(q, dtype=float)
+        f = -_lib.dgemm_nt(q.reshape(-1, self.nph), np.asarray(self.dyn, dtype=float), 1.0, self.device)
+        return f[0] if q.ndim == 1 else f
 
     def AddPotential(self, pint):
         """md.py:481-485 -- accepted for API parity; external force drivers are out of scope (raises at run time)"""

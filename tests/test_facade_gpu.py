@@ -176,3 +176,48 @@ def test_sig_to_phbath_pipeline(tmp_path, monkeypatch):
         mdrun.vv(0)
         ens.step()
     assert relerr(mdrun.q, ens.q) < 1e-9 and relerr(mdrun.p, ens.p) < 1e-9
+
+
+def test_standalone_force_calls_match_the_oracle():
+    """md.potforce / md.force / bath.bforce as stand-alone calls (md.py:413-474, baths.py:224-255,448-458): device GEMMs behind the
+    reference's signatures, against the literal oracle restatement; the id = 1 evaluation at (p, q) is the one vv() performs"""
+    from sclmd_b200.md import md
+    from sclmd_b200.baths import ebath, phbath
+    c = P.md_case_e_extra()
+    natoms = c["K"].shape[0] // 3
+    m = md(c["dt"], c["nmd"], c["T"], axyz=[["C", float(i), 0.0, 0.0] for i in range(natoms)], dyn=c["K"])
+    e = c["e"]
+    baths = []
+    for b in range(2):
+        bb = ebath(c["cids"][b], c["T"], c["dt"], c["nmd"], wmax=1.0, nw=50, bias=e["bias"][b], efric=e["efric"][b], exim=e["exim"][b],
+                   exip=e["exip"][b], zeta1=e["zeta1"][b], zeta2=e["zeta2"][b])
+        bb.noise = c["noise"][b]
+        m.AddBath(bb)
+        baths.append(bb)
+    m.AddConstr(c["cons"])
+    m.initialise()
+    m.q, m.p = c["q0"].copy(), c["p0"].copy()
+    m.ResetHis()
+    K = np.array(m.dyn)
+    assert relerr(m.potforce(c["q0"]), -K @ c["q0"]) < 1e-12
+    obaths = [O.Bath("e", c["cids"][b], np.array(baths[b].kernel), c["noise"][b], c["dt"], c["nmd"], baths[b].bias, baths[b].exim,
+                     baths[b].zeta1, baths[b].zeta2) for b in range(2)]
+    lit = O.LiteralMD(K, c["dt"], c["nmd"], obaths, c["cons"])
+    lit.q, lit.p = c["q0"].copy(), c["p0"].copy()
+    for _ in range(5):
+        m.vv(0)
+        lit.vv()
+    q, p = np.array(m.q), np.array(m.p)
+    want = lit.force(lit.t, p, q, 1)
+    got = m.force(m.t, p, q, 1)
+    assert relerr(got, want) < 1e-10
+    # phonon bath with a full memory kernel: bforce against the definition
+    cp = P.md_case_ph_full()
+    pb = phbath(cp["T"], cp["cids"][0], 0.05, 10, cp["dt"], cp["nmd"], ml=cp["kern"][0].shape[0], gamma=P.gamma_grid(4, 6, 5)[1], gwl=P.gamma_grid(4, 6, 5)[0])
+    pb.kernel = cp["kern"][0]
+    pb.noise = cp["noise"][0]
+    rng = np.random.default_rng(3)
+    phis = rng.standard_normal((pb.kernel.shape[0], 30))
+    f = pb.bforce(7, phis, np.zeros_like(phis))
+    wantc = cp["noise"][0][7] - cp["dt"] * np.einsum("jab,jb->a", cp["kern"][0], phis[:, cp["cids"][0]])
+    assert relerr(f[cp["cids"][0]], wantc) < 1e-12 and np.count_nonzero(f) == 6
