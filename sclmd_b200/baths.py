@@ -10,6 +10,11 @@ from ._lib import as_f64, check, dptr
 from .functions import antisymmetrize, chkShape, flinterp_index, symmetrize
 
 
+def exlist(a, indices):
+    """baths.py:12-13"""
+    return a[indices]
+
+
 def _is_diagonal(m):
     m = np.asarray(m)
     return m.ndim == 2 and not np.any(m - np.diag(np.diagonal(m)))

@@ -10,6 +10,19 @@ from . import units as U
 np.seterr(over="ignore")
 
 
+def coth(x):
+    """functions.py:59-67"""
+    if x == 0.0:
+        print("coth:coth(0) is infinity")
+        sys.exit(0)
+    return np.cosh(x) / np.sinh(x)
+
+
+def xcoth(x):
+    """functions.py:70-77"""
+    return 1.0 if x == 0.0 else x * np.cosh(x) / np.sinh(x)
+
+
 def device_fft(a, sign, scale, device=0):
     """out[..., m] = scale * sum_k a[..., k] exp(sign 2 pi i k m / n) along the last axis, on the device (sclmd_fft)"""
     from . import _lib
@@ -150,6 +163,20 @@ def powerspecp(ps, dt, nmd, device=0):
     psw = device_fft(pst, +1, (2. * np.pi / dw) / nmd, device)
     tot = np.sum(np.real(psw * np.conjugate(psw)), axis=0)
     return np.array([[i * dw, tot[i] / dt / nmd] for i in range(nmd)])
+
+
+def mm(*args):
+    """functions.py:159-164: chained matrix product, every factor on the device (sclmd_dgemm_nt; real matrices)"""
+    from . import _lib
+    tmp = np.array(args[0], dtype=float)
+    for mat in args[1:]:
+        m = np.asarray(mat, dtype=float)
+        vec_l, vec_r = tmp.ndim == 1, m.ndim == 1
+        r = _lib.dgemm_nt(tmp.reshape(1, -1) if vec_l else tmp, m.reshape(1, -1) if vec_r else np.ascontiguousarray(m.T))
+        tmp = r.reshape(-1) if vec_l or vec_r else r
+        if vec_l and vec_r:
+            tmp = tmp[0]
+    return tmp
 
 
 def rpadleft(bs, b):

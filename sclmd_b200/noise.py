@@ -23,6 +23,46 @@ def equ(w, cut, T, classical=False, zpmotion=True):
     return 0.0
 
 
+def nonequm(w, bias, T, classical=False):
+    """noise.py:209-226"""
+    hw1, hw2, small = U.hbar * w - bias, U.hbar * w, 10e-20
+    if classical:
+        hw1 = small if hw1 == 0. else hw1
+        hw2 = small if hw2 == 0. else hw2
+        return 2.0 * hw1 * (U.kb * T / hw1 - U.kb * T / hw2)
+    return 2.0 * hw1 * (bose(hw1, T) - bose(hw2, T))
+
+
+def nonequp(w, bias, T, classical=False):
+    """noise.py:229-246"""
+    hw1, hw2, small = U.hbar * w + bias, U.hbar * w, 10e-20
+    if classical:
+        hw1 = small if hw1 == 0. else hw1
+        hw2 = small if hw2 == 0. else hw2
+        return 2.0 * hw1 * (U.kb * T / hw1 - U.kb * T / hw2)
+    return 2.0 * hw1 * (bose(hw1, T) - bose(hw2, T))
+
+
+def phnoisew(gamma, wl, T, phcut, classical=False, zpmotion=True):
+    """noise.py:28-46: the phonon noise spectrum equ(w) gamma(w) on the given grid (assembly only, no random numbers)"""
+    gamma = np.array(gamma)
+    return np.array([equ(wl[i], phcut, T, classical, zpmotion) * gamma[i] for i in range(len(wl))])
+
+
+def enoisew(wl, efric, exim, exip, bias, T, ecut, classical=False, zpmotion=True):
+    """noise.py:103-146: the Hermitian electron noise spectrum on the given grid (assembly only, no random numbers)"""
+    from .functions import hermitianize
+    efric, exim, exip = np.array(efric), np.array(exim), np.array(exip)
+    out = np.zeros((len(wl),) + efric.shape, dtype=complex)
+    for i, w in enumerate(wl):
+        aw = equ(w, ecut, T, classical, zpmotion)
+        awm = equ(U.hbar * w - bias, ecut, T, classical, zpmotion)
+        awp = equ(U.hbar * w + bias, ecut, T, classical, zpmotion)
+        amat = aw * efric + (-0.5 * aw * exip + 0.5 * awm * (exip + 1j * exim)) + (-0.5 * aw * exip + 0.5 * awp * (exip - 1j * exim))
+        out[i] = hermitianize(amat)
+    return out
+
+
 def mf(f, cats, lens):
     """noise.py:15-22 scatter (host helper kept for API parity)."""
     t = np.zeros(lens)
