@@ -252,7 +252,7 @@ def negf_also(rank, world, local, barrier, fp64_peak_tflops=None):
     om = np.linspace(0, 0.25 / RPC, per * world + 1)
     lo, hi = PAR.shard_range(len(om), rank, world)
     b.tm_sweep(om[lo:lo + 1184])
-    b.tm_sweep(om[lo:lo + 1184])
+    b.tm_sweep(om[lo:hi])                      # warm-up at full length (workspace sized, kernels loaded)
     barrier()
     t0 = time.perf_counter()
     tm = b.tm_sweep(om[lo:hi])

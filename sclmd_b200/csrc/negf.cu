@@ -931,7 +931,7 @@ int run_lu(int device, int n, const double *K, const int32_t *idxL, int nL, cons
     const size_t nb2 = (size_t)nb * nb;
     const size_t arena_bytes = sizeof(double) * ((size_t)n * n + n + 7 * (size_t)nw + 3 * nb2) +
                                sizeof(int) * (rhs.size() + rows.size() + (size_t)nw + n + bpos.size()) + 256 * 24;
-    SCLMD_CUDA(ws.arena.reserve(arena_bytes));
+    SCLMD_CUDA(ws.arena.reserve(((arena_bytes >> 24) + 1) << 24));      // 16 MB granules: sweeps of similar length reuse the arena
     char *cursor = static_cast<char *>(ws.arena.p);
     auto take = [&](size_t bytes) { char *r = cursor; cursor += (bytes + 255) / 256 * 256; return static_cast<void *>(r); };
     auto take_d = [&](size_t cnt) { return static_cast<double *>(take(cnt * sizeof(double))); };
