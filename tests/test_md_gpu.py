@@ -302,3 +302,52 @@ def test_config5_shape_full_size_vs_oracle():
         assert relerr(cur[:, :done], ens.baths[b]["cur"][:, :done]) < 1e-8
     for e in engs:
         e.close()
+
+
+@pytest.mark.parametrize("case", ["one_atom", "unsorted_cids", "overlapping_baths", "bath_on_every_dof", "no_bath", "nmd_wraps"])
+def test_edge_shapes_vs_oracle(case):
+    """smallest and ragged inputs: a single atom with a one-dof bath, bath dofs given out of order (baths.py:79-80 takes any index
+    list), two baths acting on the same dofs (their forces add, md.py:432-434), a bath covering every dof, no bath at all, and
+    more steps than nmd (slot indices wrap, md.py:383,397)"""
+    from sclmd_b200.engine import MDEngine
+    dt = 0.25 / 0.658
+    rng = np.random.default_rng(11)
+    if case == "one_atom":
+        natoms, nmd, ntraj, baths = 1, 8, 1, [([1], "diag", 1)]
+    elif case == "unsorted_cids":
+        natoms, nmd, ntraj, baths = 6, 16, 3, [([7, 3, 12, 4, 9], "full", 3), ([15, 14, 16], "diag", 4)]
+    elif case == "overlapping_baths":
+        natoms, nmd, ntraj, baths = 5, 16, 2, [([3, 4, 5, 6], "diag", 2), ([5, 6, 7], "full", 1)]
+    elif case == "bath_on_every_dof":
+        natoms, nmd, ntraj, baths = 4, 16, 5, [(list(range(12)), "full", 2)]
+    elif case == "no_bath":
+        natoms, nmd, ntraj, baths = 4, 8, 2, []
+    else:
+        natoms, nmd, ntraj, baths = 4, 6, 2, [([0, 1, 2], "diag", 5)]
+    nph = 3 * natoms
+    K = P.psd_project(P.spring_chain_dyn(max(natoms, 2), seed=2))[:nph, :nph]
+    K = 0.5 * (K + K.T)
+    eng = MDEngine(nph, ntraj, dt, nmd)
+    ens = O.EnsembleMD(K, dt, nmd, ntraj, None)
+    eng.set_dyn(K)
+    for b, (cids, kind, ml) in enumerate(baths):
+        nc = len(cids)
+        kern = P.diag_kernel(ml, nc, dt, 70 + b) if kind == "diag" else P.full_kernel(ml, nc, dt, 70 + b)
+        nz = P.injected_noise(ntraj, nmd, nc, seed=80 + b)
+        eng.add_bath(cids, kern)
+        eng.set_noise(b, nz)
+        ens.add_bath(cids, kern, nz)
+    q0, p0 = 0.05 * rng.standard_normal((ntraj, nph)), 0.02 * rng.standard_normal((ntraj, nph))
+    eng.set_state(q0, p0, 0)
+    ens.q[:], ens.p[:] = q0, p0
+    nsteps = 2 * nmd + 3
+    eng.run(nsteps)
+    ens.run(nsteps)
+    q, p, t = eng.get_state()
+    assert t == nsteps and relerr(q, ens.q) < TOL_STEP and relerr(p, ens.p) < TOL_STEP
+    assert relerr(eng.etot(), ens.etot) < TOL_STEP
+    for b in range(len(baths)):
+        assert relerr(eng.current(b), ens.baths[b]["cur"]) < TOL_OBS
+    eng.run(0)                                   # zero steps: a no-op
+    assert eng.get_state()[2] == nsteps
+    eng.close()

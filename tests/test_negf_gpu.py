@@ -208,3 +208,24 @@ def test_bpt_green_functions_and_building_blocks():
         assert abs(b.ps(w, 300.0, list(range(15, 21))) - want) < 1e-8 * abs(want)     # negf.py:236 from the building blocks
     sweep = b.green_sweep(np.array([17.0, 140.0]))
     assert sweep.shape == (2, n, n) and relerr(sweep[1], ref_gf(140.0, False)) < 1e-9
+
+
+@pytest.mark.parametrize("natoms,nfix,nb", [(4, 0, 1), (5, 3, 3), (7, 3, 2), (43, 3, 20)])
+def test_bpt_small_and_odd_systems(natoms, nfix, nb):
+    """smallest systems: n = 12 with one-dof leads, odd orders (the working matrix is padded by an identity dof), leads that are not
+    whole blocks, n = 123 (two 64-column blocks, a partial one)"""
+    from sclmd_b200.negf import bpt
+    K = P.spring_chain_dyn(natoms, seed=3) / O.RPC ** 2
+    n3 = 3 * natoms
+    fixed = [list(range(0, nfix)), list(range(n3 - nfix, n3))]
+    bath = [list(range(nfix, nfix + nb)), list(range(n3 - nfix - nb, n3 - nfix))]
+    b = bpt(None, 0.25, 0.1, bath, fixed, dynmatfile=K, num=10)
+    om = np.array([0.0, 1.3, 44.0, 171.0, 350.0])
+    got = b.tm_sweep(om)
+    iL, iR = O.bpt_reduce_index(bath[0], nfix), O.bpt_reduce_index(bath[1], nfix)
+    want = np.array([O.bpt_tm(b.dynmat, w, 0.1, iL, iR) for w in om])
+    assert np.max(np.abs(got - want)) < 1e-8 * max(1.0, np.abs(want).max())
+    sel = list(range(nfix + nb, nfix + nb + 2))
+    ps = b.ps_sweep(om[1:4], 300.0, sel)
+    wantps = np.array([O.bpt_ps_nobias(b.dynmat, w, 300.0, 0.1, iL, iR, np.array(sel) - nfix) for w in om[1:4]])
+    assert relerr(ps, wantps) < 1e-8
