@@ -522,6 +522,29 @@ def main():
         except Exception as exc:  # the headline line must not depend on the secondary workload
             line["also_md_config2"] = {"error": str(exc)[:200]}
 
+    # ---------------- BASELINE configs[0] shape: ONE trajectory of the same junction (the reference's own mode of operation)
+    if world == 1 and not args.no_also:
+        try:
+            w1 = dict(WORKLOADS["c2"])
+            e1, nph1 = make_engine(w1, local, 1)
+            r1 = np.random.default_rng(3)
+            for b in range(2):
+                e1.set_noise(b, 0.01 * r1.standard_normal((1, w1["nmd"], w1["nc"])))
+            e1.set_state(0.05 * r1.standard_normal((1, nph1)), 0.02 * r1.standard_normal((1, nph1)), 0)
+            e1.run(64)
+            ms1 = e1.run(4096)
+            e1.set_persistent(False)
+            e1.run(64)
+            ms1c = e1.run(1024)
+            e1.close()
+            line["also_md_config1"] = {"metric": "qtb_md_trajectory_steps_per_s", "value": 4096 / (ms1 * 1e-3), "unit": "trajectory-steps/s",
+                                       "us_per_step": ms1 / 4096 * 1e3, "steps": 4096,
+                                       "kernel": "k_md_persist (one cooperative launch per run, one grid barrier per step)",
+                                       "launch_chain_value": 1024 / (ms1c * 1e-3),
+                                       "config": "BASELINE configs[0] shape: 603-dof junction, 2 time-local baths x 150 dofs, fixed ends, 1 trajectory"}
+        except Exception as exc:
+            line["also_md_config1"] = {"error": str(exc)[:200]}
+
     # ---------------- CPU baseline (reported, not the target): rank 0, N=1 only
     if world == 1 and not args.no_cpu_baseline:
         sec = reference_steps(w, args.cpu_steps, 1)

@@ -117,6 +117,9 @@ int sclmd_md_get_profile(sclmd_md *h, double *tail_ms, int64_t *tail_launches, d
 /* 1 (default): the FP64-bound K.q GEMM runs on a second stream concurrently with the HBM-bound
  * history-tail kernels; 0: everything on one stream */
 int sclmd_md_set_overlap(sclmd_md *h, int on);
+/* 1 (default): sclmd_md_run of <= 2 trajectories of <= 1024 dofs whose baths are all time-local and diagonal (the reference's own
+ * example, examples/runmd.py) is ONE cooperative launch of a persistent kernel with one grid barrier per step; 0: per-step launches */
+int sclmd_md_set_persistent(sclmd_md *h, int on);
 
 /* 1 (default): diagonal-kernel baths with ml >= 128 stream their history ring from HBM once per 16 steps
  * (time-blocked far/near tails, same flops, same results to rounding); 0: one full ring pass per step -- the

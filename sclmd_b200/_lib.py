@@ -41,6 +41,7 @@ _PROTOS = {
     "sclmd_md_set_noise_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p]),
     "sclmd_md_get_step_observables": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
     "sclmd_md_set_overlap": (C.c_int, [C.c_void_p, C.c_int]),
+    "sclmd_md_set_persistent": (C.c_int, [C.c_void_p, C.c_int]),
     "sclmd_md_set_tail_block": (C.c_int, [C.c_void_p, C.c_int]),
     "sclmd_md_get_profile_all": (C.c_int, [C.c_void_p, c_double_p, c_int64_p]),
     "sclmd_md_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),

@@ -20,6 +20,8 @@
 #include <memory>
 #include <type_traits>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "dgemm.cuh"
 
@@ -159,6 +161,186 @@ __global__ void __launch_bounds__(256, NBATH <= 2 ? 4 : 1) k_phase_bc(BathSet bs
         }
         pout[row + i] = pnew;
     }
+}
+
+// ---- persistent step kernel for small systems -------------------------------------------------------------------------
+// A single trajectory (or a handful) of a few hundred dofs with time-local diagonal baths -- the reference's own example
+// (examples/runmd.py: 603 dofs, two ml = 1 baths) -- is latency-bound as a chain of launches (~50 us per step).  Here ONE
+// cooperative launch advances nsteps steps: every CTA keeps the whole state (q, p, K.q, p_half, q') of all trajectories in
+// shared memory and does the elementwise parts of a step redundantly (identical arithmetic, so identical values everywhere);
+// only the matrix-vector products K.q' and K.constrain(q') are distributed (warp per row of K, which stays in L2) and exchanged
+// through a double-buffered global vector with ONE grid-wide barrier per step.
+constexpr int PS_MAXT = 2;      // trajectories the persistent kernel keeps in registers
+struct PersistArgs {
+    BathSet bs;
+    int nph, ld, ntraj, nmd, has_cons;
+    long long t0, nsteps;
+    double dt;
+    const double *K;
+    double *q, *p, *G;             // state in / out; G = K.q of the current q (slice 0 of the handle's buffer)
+    const unsigned char *cons;
+    double *etot;
+    double *xbuf;                  // [2][2][ntraj][ld]: (K.q', K.constrain(q')) of the step, double-buffered over steps
+};
+
+// A thread owns the same <= PS_EPT elements of every trajectory for the whole run: their bath index, friction coefficient and
+// constraint flag sit in registers, and the noise row of step t+1 (needed by evaluations B, C and by evaluation A of the next
+// step) is requested before the matrix-vector product so that it arrives under it.
+constexpr int PS_EPT = 4;          // elements per thread: nph <= 1024
+template <int NBATH, int NT>
+__global__ void __launch_bounds__(256, 1) k_md_persist(const PersistArgs a) {
+    extern __shared__ double psm[];
+    __shared__ double red[32];
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    const int nph = a.nph, ld = a.ld;
+    double *sn = psm;                                   // q' of every trajectory: the operand of the matrix-vector product
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    const double dt = a.dt;
+    double q[NT][PS_EPT], p[NT][PS_EPT], g[NT][PS_EPT], nz[NT][PS_EPT][NBATH], kf[PS_EPT][NBATH];
+    int bc[PS_EPT][NBATH];
+    bool fix[PS_EPT];
+    const int slab0 = (int)(a.t0 % a.nmd);
+#pragma unroll
+    for (int j = 0; j < PS_EPT; ++j) {
+        const int i = tid + j * 256;
+        const bool ok = i < nph;
+        fix[j] = ok && a.has_cons && a.cons[i];
+#pragma unroll
+        for (int b = 0; b < NBATH; ++b) {
+            bc[j][b] = (ok && b < a.bs.nb) ? a.bs.b[b].inv[i] : -1;
+            kf[j][b] = bc[j][b] >= 0 ? a.bs.b[b].c0 * a.bs.b[b].k0[bc[j][b]] : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < NT; ++k) {
+            q[k][j] = ok ? a.q[(size_t)k * ld + i] : 0.0;
+            p[k][j] = ok ? a.p[(size_t)k * ld + i] : 0.0;
+            g[k][j] = ok ? a.G[(size_t)k * ld + i] : 0.0;
+#pragma unroll
+            for (int b = 0; b < NBATH; ++b)
+                nz[k][j][b] = bc[j][b] >= 0 ? a.bs.b[b].noise[((size_t)slab0 * NT + k) * a.bs.b[b].ncp + bc[j][b]] : 0.0;
+        }
+    }
+    for (long long s = 0; s < a.nsteps; ++s) {
+        const long long t = a.t0 + s;
+        const int slab = (int)(t % a.nmd), slab1 = (int)((t + 1) % a.nmd);
+        double ph[NT][PS_EPT], qn[NT][PS_EPT], n1[NT][PS_EPT][NBATH];
+        // ---- evaluation A (md.py:383-398), redundantly in every CTA; CTA 0 records the observables and pushes the history
+#pragma unroll
+        for (int k = 0; k < NT; ++k) {
+            double ke = 0.0, cur[NBATH];
+#pragma unroll
+            for (int b = 0; b < NBATH; ++b) cur[b] = 0.0;
+#pragma unroll
+            for (int j = 0; j < PS_EPT; ++j) {
+                const int i = tid + j * 256;
+                double f = -g[k][j];
+#pragma unroll
+                for (int b = 0; b < NBATH; ++b)
+                    if (bc[j][b] >= 0) {
+                        const double fb = nz[k][j][b] - kf[j][b] * p[k][j];
+                        cur[b] += fb * p[k][j];
+                        f += fb;
+                        if (blockIdx.x == 0)
+                            a.bs.b[b].ring[((size_t)k * a.bs.b[b].ml + (int)(t % a.bs.b[b].ml)) * a.bs.b[b].ncp + bc[j][b]] = p[k][j];
+                    }
+                ke += 0.5 * p[k][j] * p[k][j];
+                ph[k][j] = p[k][j] + f * dt / 2.0;
+                qn[k][j] = q[k][j] + p[k][j] * dt + f * dt * dt / 2.0;
+                if (i < nph) sn[(size_t)k * ld + i] = qn[k][j];
+                // the noise of step t+1: in flight during the matrix-vector product and the grid barrier
+#pragma unroll
+                for (int b = 0; b < NBATH; ++b)
+                    n1[k][j][b] = bc[j][b] >= 0 ? a.bs.b[b].noise[((size_t)slab1 * NT + k) * a.bs.b[b].ncp + bc[j][b]] : 0.0;
+            }
+            if (blockIdx.x == 0) {
+                ke = block_sum(ke, red);
+                if (tid == 0) a.etot[(size_t)slab * NT + k] = ke;
+#pragma unroll
+                for (int b = 0; b < NBATH; ++b)
+                    if (b < a.bs.nb) {
+                        const double c = block_sum(cur[b], red);
+                        if (tid == 0) a.bs.b[b].cur[(size_t)slab * NT + k] = c;
+                    }
+            }
+        }
+        __syncthreads();
+        // ---- K.q' and K.constrain(q'): warp per row, rows dealt round-robin over the grid
+        double *xb = a.xbuf + (size_t)(s & 1) * 2 * NT * ld;
+        for (int r = blockIdx.x * nwarp + warp; r < nph; r += gridDim.x * nwarp) {
+            const double *krow = a.K + (size_t)r * ld;
+            double acc[NT], accc[NT];
+#pragma unroll
+            for (int k = 0; k < NT; ++k) acc[k] = accc[k] = 0.0;
+            for (int c = lane; c < nph; c += 32) {
+                const double kv = krow[c];
+                const bool fx = a.has_cons && a.cons[c];
+#pragma unroll
+                for (int k = 0; k < NT; ++k) {
+                    const double x = sn[(size_t)k * ld + c];
+                    acc[k] = fma(kv, x, acc[k]);
+                    if (!fx) accc[k] = fma(kv, x, accc[k]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < NT; ++k) {
+                const double v = warp_sum(acc[k]), vc = warp_sum(accc[k]);
+                if (lane == 0) {
+                    xb[(size_t)k * ld + r] = v;
+                    xb[(size_t)(NT + k) * ld + r] = vc;
+                }
+            }
+        }
+        grid.sync();
+        // ---- evaluations B and C (md.py:401-404), constraint (md.py:407-408); K.q of the next step
+#pragma unroll
+        for (int k = 0; k < NT; ++k)
+#pragma unroll
+            for (int j = 0; j < PS_EPT; ++j) {
+                const int i = tid + j * 256;
+                if (i >= nph) continue;
+                const double gn = __ldcg(xb + (size_t)k * ld + i), gc = __ldcg(xb + (size_t)(NT + k) * ld + i);
+                double xi = ph[k][j], pnew = 0.0;
+#pragma unroll
+                for (int rep = 0; rep < 2; ++rep) {
+                    double f = -gn;
+#pragma unroll
+                    for (int b = 0; b < NBATH; ++b)
+                        if (bc[j][b] >= 0) f += n1[k][j][b] - kf[j][b] * xi;
+                    pnew = ph[k][j] + dt * f / 2.0;
+                    xi = pnew;
+                }
+                p[k][j] = fix[j] ? 0.0 : pnew;
+                q[k][j] = fix[j] ? 0.0 : qn[k][j];
+                g[k][j] = a.has_cons ? gc : gn;
+#pragma unroll
+                for (int b = 0; b < NBATH; ++b) nz[k][j][b] = n1[k][j][b];
+            }
+        __syncthreads();      // everyone is done with sn before the next evaluation A rewrites it
+    }
+    if (blockIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NT; ++k)
+#pragma unroll
+            for (int j = 0; j < PS_EPT; ++j) {
+                const int i = tid + j * 256;
+                if (i < nph) {
+                    a.q[(size_t)k * ld + i] = q[k][j];
+                    a.p[(size_t)k * ld + i] = p[k][j];
+                    a.G[(size_t)k * ld + i] = g[k][j];
+                }
+            }
+    }
+}
+
+// G[0] <- sum_z G[z] (- D): the persistent kernel works on one K.q vector per trajectory
+__global__ void k_fold_g(double *G, int nsplit, size_t n, const double *D) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    double v = G[e];
+    for (int z = 1; z < nsplit; ++z) v += G[(size_t)z * n + e];
+    if (D) v -= D[e];
+    G[e] = v;
 }
 
 // device-resident step counter of the graph-captured part of a step
@@ -792,6 +974,50 @@ struct sclmd_md {
         }
         return 0;
     }
+    // whole run(n) in one cooperative launch (k_md_persist): few trajectories, time-local diagonal baths, state fits shared memory
+    bool use_persist = true;
+    DevBuf<double> xbuf;
+    bool persist_ok() const {
+        if (!use_persist || profiling || ntraj > PS_MAXT || nph > 256 * PS_EPT || baths.size() > 2) return false;
+        for (auto &b : baths)
+            if (b->ml > 1 || b->has_lin || b->kind != SCLMD_KERNEL_DIAG) return false;
+        return true;
+    }
+    int run_persist(long long nsteps) {
+        BathSet bs = view();
+        if (!g_valid) {
+            if (int e = potforce(q.p, G.p)) return e;
+            g_valid = true;
+            d_valid = false;
+        }
+        const size_t n = (size_t)ntraj * ld;
+        if (gplan.nsplit > 1 || d_valid) {     // fold the K-slices (and a pending constraint correction) into slice 0
+            k_fold_g<<<cdiv((int)n, 256), 256, 0, st>>>(G.p, gplan.nsplit, n, d_valid ? Dc.p : nullptr);
+            SCLMD_CUDA(cudaGetLastError());
+            d_valid = false;
+        }
+        if (!xbuf.p) SCLMD_CUDA(xbuf.alloc(4 * n));
+        if (noise_pending) {
+            SCLMD_CUDA(cudaStreamWaitEvent(st, evN, 0));
+            noise_pending = false;
+        }
+        PersistArgs a{};
+        a.bs = bs; a.nph = nph; a.ld = ld; a.ntraj = ntraj; a.nmd = nmd; a.has_cons = has_cons ? 1 : 0;
+        a.t0 = t; a.nsteps = nsteps; a.dt = dt; a.K = K.p; a.q = q.p; a.p = p.p; a.G = G.p; a.cons = cons.p; a.etot = etot.p; a.xbuf = xbuf.p;
+        const size_t smem = n * sizeof(double);
+        const int grid = std::max(1, std::min(nsm, cdiv(nph, 8)));
+        void *args[] = {&a};
+        const void *fn = ntraj == 1 ? (const void *)k_md_persist<2, 1> : (const void *)k_md_persist<2, 2>;
+        SCLMD_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(256), args, smem, st));
+        ++launches;
+        t += nsteps;
+        dt_synced = false;
+        obs_slab = -1;               // every slab of the run is written by this one launch: read-backs take the synchronising path
+        if (gplan.nsplit > 1) {      // the step kernels add the K-slices of G: the other slices must read as zero
+            SCLMD_CUDA(cudaMemsetAsync(G.p + n, 0, (size_t)(gplan.nsplit - 1) * n * sizeof(double), st));
+        }
+        return 0;
+    }
     void finish_step() {      // host-side state after a step
         if (has_cons && use_corr) {
             d_valid = true;
@@ -927,6 +1153,7 @@ int sclmd_md_create(int nph, int ntraj, double dt, int nmd, int device, sclmd_md
     SCLMD_CUDA(h->G.alloc(n * h->gplan.nsplit)); SCLMD_CUDA(h->Gn.alloc(n * h->gplan.nsplit));
     SCLMD_CUDA(h->d_t.alloc(1));
     h->use_graphs = getenv("SCLMD_NO_GRAPH") == nullptr;
+    h->use_persist = getenv("SCLMD_NO_PERSIST") == nullptr;
     SCLMD_CUDA(h->phalf.alloc(n)); SCLMD_CUDA(h->p1.alloc(n)); SCLMD_CUDA(h->qn.alloc(n));
     SCLMD_CUDA(h->etot.alloc((size_t)nmd * ntraj));
     SCLMD_CUDA(h->cons.alloc(nph));
@@ -1211,8 +1438,12 @@ int sclmd_md_run(sclmd_md *h, int64_t nsteps, float *elapsed_ms) {
     }
     SCLMD_CUDA(cudaSetDevice(h->device));
     SCLMD_CUDA(cudaEventRecord(h->ev0, h->st));
-    for (int64_t s = 0; s < nsteps; ++s)
-        if (int e = h->step()) return e;
+    if (nsteps > 0 && h->persist_ok()) {
+        if (int e = h->run_persist(nsteps)) return e;
+    } else {
+        for (int64_t s = 0; s < nsteps; ++s)
+            if (int e = h->step()) return e;
+    }
     SCLMD_CUDA(cudaEventRecord(h->ev1, h->st));
     if (!elapsed_ms && !h->profiling) return SCLMD_OK;   // asynchronous: the next sclmd_md_get_* synchronises
     SCLMD_CUDA(cudaStreamSynchronize(h->st));
@@ -1225,6 +1456,14 @@ int sclmd_md_run(sclmd_md *h, int64_t nsteps, float *elapsed_ms) {
 int sclmd_md_set_overlap(sclmd_md *h, int on) {
     SCLMD_REQUIRE(h, "sclmd_md_set_overlap: NULL handle");
     h->overlap = on != 0;
+    return SCLMD_OK;
+}
+
+// 1 (default): runs of <= 2 trajectories of <= 1024 dofs with time-local diagonal baths use the persistent cooperative kernel
+// (one launch per sclmd_md_run, one grid barrier per step); 0: always the per-step launch chain
+int sclmd_md_set_persistent(sclmd_md *h, int on) {
+    SCLMD_REQUIRE(h, "sclmd_md_set_persistent: NULL handle");
+    h->use_persist = on != 0;
     return SCLMD_OK;
 }
 

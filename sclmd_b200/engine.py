@@ -89,6 +89,9 @@ class MDEngine:
         check(_lib.lib().sclmd_md_get_step_observables(self._h, int(slab), dptr(out)))
         return out
 
+    def set_persistent(self, on=True):
+        check(_lib.lib().sclmd_md_set_persistent(self._h, 1 if on else 0))
+
     def set_overlap(self, on=True):
         check(_lib.lib().sclmd_md_set_overlap(self._h, 1 if on else 0))
 

@@ -351,3 +351,61 @@ def test_edge_shapes_vs_oracle(case):
     eng.run(0)                                   # zero steps: a no-op
     assert eng.get_state()[2] == nsteps
     eng.close()
+
+
+@pytest.mark.parametrize("ntraj,cons", [(1, True), (2, True), (2, False)])
+def test_persistent_kernel_equals_launch_chain_and_oracle(ntraj, cons):
+    """the cooperative persistent kernel (one launch per run, one grid barrier per step; config-1 shape: 603 dofs, two ml = 1 baths,
+    fixed ends) against the per-step launch chain and the oracle: several run() calls, observables, a restart in between"""
+    from sclmd_b200.engine import MDEngine
+    c = P.md_case_c1_shape()
+    K = P.psd_project(c["K"])
+    nph, dt, nmd = K.shape[0], c["dt"], c["nmd"]
+    cn = c["cons"] if cons else None
+    kern = [np.array([np.diag(c["e"]["efric"][b])]) for b in range(2)]          # diagonal, ml = 1
+    nz = [P.injected_noise(ntraj, nmd, 150, seed=90 + b, sigma=0.003) for b in range(2)]
+    rng = np.random.default_rng(5)
+    q0, p0 = 0.05 * rng.standard_normal((ntraj, nph)), 0.02 * rng.standard_normal((ntraj, nph))
+    if cn:
+        for g in cn:
+            q0[:, g] = 0
+            p0[:, g] = 0
+    ens = O.EnsembleMD(K, dt, nmd, ntraj, cn)
+    engs = []
+    for persist in (True, False):
+        e = MDEngine(nph, ntraj, dt, nmd)
+        e.set_persistent(persist)
+        e.set_dyn(K)
+        if cn:
+            e.set_constraint([i for g in cn for i in g])
+        for b in range(2):
+            e.add_bath(c["cids"][b], kern[b])
+            e.set_noise(b, nz[b])
+        e.set_state(q0, p0, 0)
+        engs.append(e)
+    for b in range(2):
+        ens.add_bath(c["cids"][b], kern[b], nz[b])
+    ens.q[:], ens.p[:] = q0, p0
+    done = 0
+    for chunk in (1, 37, 90):            # 128 steps in total: the slot indices wrap (nmd = 64)
+        ens.run(chunk)
+        done += chunk
+        for e in engs:
+            e.run(chunk)
+            q, p, t = e.get_state()
+            assert t == done and relerr(q, ens.q) < TOL_STEP and relerr(p, ens.p) < TOL_STEP, (done,)
+    assert engs[0].launch_count() < 40 < engs[1].launch_count()                 # one launch per run() vs several per step
+    for e in engs:
+        assert relerr(e.etot(), ens.etot) < TOL_STEP
+        for b in range(2):
+            assert relerr(e.current(b), ens.baths[b]["cur"]) < TOL_OBS
+    # hand the state of the chain engine to the persistent one and continue: both agree
+    q, p, t = engs[1].get_state()
+    engs[0].set_state(q, p, t)
+    for e in engs:
+        e.run(11)
+    qa, pa, _ = engs[0].get_state()
+    qb, pb, _ = engs[1].get_state()
+    assert relerr(qa, qb) < 1e-12 and relerr(pa, pb) < 1e-12
+    for e in engs:
+        e.close()
