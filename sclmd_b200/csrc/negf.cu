@@ -575,9 +575,7 @@ __global__ void __launch_bounds__(256) k_backsub(Geo g, double *W, const int *ac
     const int b = blockIdx.x, lw = g.lw, np = g.np;
     double *wre = W + (size_t)b * 2 * g.plane, *wim = wre + g.plane;
     __shared__ double Ur[16][BSK + 1], Ui[16][BSK + 1];
-    __shared__ int s_act[1024];
-    for (int i = threadIdx.x; i < np; i += blockDim.x) s_act[i] = act[(size_t)b * g.nrp + i];
-    __syncthreads();
+    const int *s_act = act + (size_t)b * g.nrp;      // position -> physical row (read-only here: served from L1/L2)
     const int last = ((np - 1) / 16) * 16;
     for (int cb = 0; cb < g.nrhs; cb += blockDim.x) {
         const int c = cb + threadIdx.x;
@@ -816,11 +814,16 @@ cudaError_t enqueue_lu(const Geo &g, const Problem &p, StreamSlot &s, int *statu
     pf.end(st);
     for (int k0 = 0; k0 < g.np; k0 += TS) {       // (blocks start on multiples of 64: tiles stay 512-byte aligned)
         const int rend = std::min(k0 + TS, g.np);
-        const int nbw = g.np - k0 > 512 ? 8 : 16;       // rows per thread x columns must fit the register file
+        // rows per thread x sub-panel width is bounded by the register file (32 complex numbers per thread): the taller the
+        // panel, the narrower its sub-panels; k_block_trsm and the rank-64 update do not depend on that width
+        const int mh = g.np - k0;
+        const int nbw = mh > 2048 ? 2 : (mh > 1024 ? 4 : (mh > 512 ? 8 : 16));
         for (int kk = k0; kk < rend; kk += nbw) {
             const int m = g.np - kk, kb = std::min(nbw, rend - kk);
             pf.begin(1, st);
-            if (nbw == 8) k_panel<512, 2, 8><<<nbat, 512, 0, st>>>(g, W, act, status, w0, kk, kb, rend);
+            if (nbw == 2) k_panel<256, 16, 2><<<nbat, 256, 0, st>>>(g, W, act, status, w0, kk, kb, rend);
+            else if (nbw == 4) k_panel<256, 8, 4><<<nbat, 256, 0, st>>>(g, W, act, status, w0, kk, kb, rend);
+            else if (nbw == 8) k_panel<512, 2, 8><<<nbat, 512, 0, st>>>(g, W, act, status, w0, kk, kb, rend);
             else if (m > 256) k_panel<256, 2, 16><<<nbat, 256, 0, st>>>(g, W, act, status, w0, kk, kb, rend);
             else if (m > 128) k_panel<256, 1, 16><<<nbat, 256, 0, st>>>(g, W, act, status, w0, kk, kb, rend);
             else if (m > 64) k_panel<128, 1, 16><<<nbat, 128, 0, st>>>(g, W, act, status, w0, kk, kb, rend);
@@ -835,8 +838,7 @@ cudaError_t enqueue_lu(const Geo &g, const Problem &p, StreamSlot &s, int *statu
         }
         if (g.ncols > rend) {
             pf.begin(3, st);
-            if (nbw == 8) k_block_trsm<8><<<nbat, 256, TRSM_SMEM, st>>>(g, W, act, flags, k0, rend);
-            else k_block_trsm<16><<<nbat, 256, TRSM_SMEM, st>>>(g, W, act, flags, k0, rend);
+            k_block_trsm<16><<<nbat, 256, TRSM_SMEM, st>>>(g, W, act, flags, k0, rend);      // its own 16-row blocking of L11
             pf.end(st);
         }
         if (rend < g.np) {     // trailing matrix and carried right-hand sides: rank-64 update
@@ -856,7 +858,7 @@ int run_lu(int device, int n, const double *K, const int32_t *idxL, int nL, cons
            const BiasBlock *bb = nullptr, int advanced = 0) {
     // mode 0 transmission, 1 power spectrum, 2 biased power spectrum, 3 the full Green function (out = [nw][n][n] complex, interleaved)
     SCLMD_REQUIRE(n > 0 && K && idxL && idxR && nL > 0 && nR > 0 && omegas && nw > 0 && out && damp != 0.0, "bpt: bad arguments");
-    SCLMD_REQUIRE(n <= 1024, "bpt: n=%d exceeds the register-resident panel (n <= 1024)", n);
+    SCLMD_REQUIRE(n <= 4096, "bpt: n=%d exceeds the register-resident panel (n <= 4096)", n);
     if (int e = select_device(device)) return e;
     std::vector<double> mask(n, 0.0);
     for (int i = 0; i < nL; ++i) {
@@ -971,7 +973,6 @@ int run_lu(int device, int n, const double *K, const int32_t *idxL, int nL, cons
         if (mode == 2) SCLMD_CUDA(slots[s].Xs.reserve((size_t)bsz * 2 * g.np * g.nrhs * sizeof(double)));
     }
     SCLMD_CUDA(cudaFuncSetAttribute(k_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-    SCLMD_CUDA(cudaFuncSetAttribute(k_block_trsm<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSM_SMEM));
     SCLMD_CUDA(cudaFuncSetAttribute(k_block_trsm<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSM_SMEM));
 
     DevBuf<unsigned long long> dtiles;

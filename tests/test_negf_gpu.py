@@ -229,3 +229,20 @@ def test_bpt_small_and_odd_systems(natoms, nfix, nb):
     ps = b.ps_sweep(om[1:4], 300.0, sel)
     wantps = np.array([O.bpt_ps_nobias(b.dynmat, w, 300.0, 0.1, iL, iR, np.array(sel) - nfix) for w in om[1:4]])
     assert relerr(ps, wantps) < 1e-8
+
+
+@pytest.mark.parametrize("natoms", [401, 700])
+def test_bpt_systems_beyond_1024_dofs(natoms):
+    """n = 1197 and n = 2094: the tall sub-panels are factorised 4 resp. 2 columns at a time (rows per thread x width is bounded by
+    the register file); same pivoting, same result as the oracle's dense inverse"""
+    from sclmd_b200.negf import bpt
+    K = P.spring_chain_dyn(natoms, seed=16) / O.RPC ** 2
+    n3 = 3 * natoms
+    fixed = [list(range(0, 3)), list(range(n3 - 3, n3))]
+    bath = [list(range(3, 153)), list(range(n3 - 153, n3 - 3))]
+    b = bpt(None, 0.25, 0.1, bath, fixed, dynmatfile=K, num=10)
+    om = np.array([2.0, 87.0, 260.0])
+    got = b.tm_sweep(om)
+    iL, iR = O.bpt_reduce_index(bath[0], 3), O.bpt_reduce_index(bath[1], 3)
+    want = np.array([O.bpt_tm(b.dynmat, w, 0.1, iL, iR) for w in om])
+    assert np.max(np.abs(got - want)) < 1e-8 * max(1.0, np.abs(want).max())
