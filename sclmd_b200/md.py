@@ -373,14 +373,14 @@ class md:
         self.info()
         for j in range(self.nstart, self.nstop):
             print("\n" + "MD run: " + str(j))
-            fn, fnm = "MD" + str(j) + ".npz", "MD" + str(j - 1) + ".npz"
+            fn, fnm = "MD" + str(j) + ".nc", "MD" + str(j - 1) + ".nc"
             ipie = -1
             if os.path.isfile(fn):
-                ck = np.load(fn)
-                ipie = int(ck["ipie"])
+                ck = self._read_checkpoint(fn)
+                ipie = int(ck["ipie"][0])
                 if ipie + 1 == self.npie:
                     print("finished run")
-                    self.t = int(ck["t"])
+                    self.t = int(ck["t"][0])
                     continue
                 print("unfinished run: reading resume information")
                 self._restore(ck, with_noise=True)
@@ -388,7 +388,7 @@ class md:
                 print("new run")
                 if os.path.isfile(fnm):
                     print("reading history from previous run")
-                    self._restore(np.load(fnm), with_noise=False)
+                    self._restore(self._read_checkpoint(fnm), with_noise=False)
                 elif j != self.nstart and j != 0:
                     print("no previous nc file exists")
                     sys.exit()
@@ -458,30 +458,66 @@ class md:
             for layers in range(len(self.atomlist)):
                 self.poweratomlist[layers] = powerspecp(self.ps[:, self.atomlist[layers]], self.dt, self.nmd)
 
-    # ------------------------------------------------------------ checkpoint (md.py:684-745; .npz instead of NetCDF)
+    # ------------------------------------------------------------ checkpoint (md.py:684-745)
+    # MD<run>.nc in NetCDF classic format (scipy.io.netcdf_file; netCDF4 is not needed and reads it too) with the reference's
+    # variable names: energy, p, q, t, ipie, phis, qhis (+ noise<i>, power, ps, qs when saved).  Extras for the device engine:
+    # the per-bath history rings `ring<i>` [ntraj, ml_i, nc_i]; an ensemble adds a leading `ntraj` dimension to p, q, phis, energy.
     def dump(self, ipie, id):
-        out = dict(p=np.asarray(self.p), q=np.asarray(self.q), t=int(self.t), ipie=int(ipie), energy=np.asarray(self.etot))
-        for i in range(len(self.baths)):
-            out["phis%d" % i] = self._eng.get_history(i)
-            if self.saveall and self.ntraj == 1 and self.baths[i]._noise is not None:
-                out["noise%d" % i] = self.baths[i]._noise
+        from scipy.io import netcdf_file
+        f = netcdf_file("MD" + str(id) + ".nc", 'w')
+        f.title = 'Output from sclmd_b200.md'
+        f.createDimension('nph', self.nph)
+        f.createDimension('one', 1)
+        f.createDimension('two', 2)
+        f.createDimension('mem', self.ml)
+        f.createDimension('nmd', self.nmd)
+        f.createDimension('ntraj', self.ntraj)
+        lead = () if self.ntraj == 1 else ('ntraj',)
+
+        def put(name, arr, dims):
+            v = f.createVariable(name, 'd', dims)
+            v[:] = np.asarray(arr, dtype=float).reshape([f.dimensions[d] for d in dims])
+        put('energy', self.etot, lead + ('nmd',))
+        put('p', self.p, lead + ('nph',))
+        put('q', self.q, lead + ('nph',))
+        put('t', [float(self.t)], ('one',))
+        put('ipie', [float(ipie)], ('one',))
+        phis = np.asarray(self.phis)
+        put('phis', phis, lead + ('mem', 'nph'))
+        qhis = np.zeros_like(phis)                       # only its first row is ever read (baths.py:246-249), from the live q
+        put('qhis', qhis, lead + ('mem', 'nph'))
+        for i, b in enumerate(self.baths):
+            f.createDimension('n' + str(i), b.nc)
+            f.createDimension('m' + str(i), b.ml)
+            put('ring' + str(i), self._eng.get_history(i), ('ntraj', 'm' + str(i), 'n' + str(i)))
+            if self.saveall and self.ntraj == 1 and b._noise is not None:
+                put('noise' + str(i), np.asarray(b._noise).reshape(self.nmd, b.nc), ('nmd', 'n' + str(i)))
         if self.savep:
-            out["power"] = self.power
+            f.createDimension('npw', len(self.power))
+            put('power', self.power, ('npw', 'two'))
             if self.saveall:
-                out["ps"] = self.ps
+                put('ps', self.ps, ('nmd', 'nph'))
         if self.saveq and self.saveall:
-            out["qs"] = self.qs
-        np.savez("MD" + str(id) + ".npz", **out)
+            put('qs', self.qs, ('nmd', 'nph'))
+        f.close()
+
+    @staticmethod
+    def _read_checkpoint(fn):
+        from scipy.io import netcdf_file
+        with netcdf_file(fn, 'r', mmap=False) as f:
+            return {k: np.array(v[:], dtype=float) for k, v in f.variables.items()}
 
     def _restore(self, ck, with_noise):
-        self.p, self.q, self.t = ck["p"], ck["q"], int(ck["t"])
+        self.p, self.q, self.t = ck["p"], ck["q"], int(ck["t"][0])
         self._ensure_engine()
         self._state_dirty = True
         self._push()
         for i, b in enumerate(self.baths):
-            key = "phis%d" % i
+            key = "ring%d" % i
             if key in ck and ck[key].shape == (self.ntraj, b.ml, b.nc):
                 self._eng.set_history(i, ck[key])
+            elif "phis" in ck and self.ntraj == 1 and ck["phis"].shape[0] >= b.ml:      # a checkpoint in the reference's layout
+                self._eng.set_history(i, np.ascontiguousarray(ck["phis"][:b.ml][:, b.cids])[None])
             if with_noise:
                 if "noise%d" % i not in ck:
                     print("saveall savep & saveq need to be set true to continue")

@@ -221,3 +221,55 @@ def test_standalone_force_calls_match_the_oracle():
     f = pb.bforce(7, phis, np.zeros_like(phis))
     wantc = cp["noise"][0][7] - cp["dt"] * np.einsum("jab,jb->a", cp["kern"][0], phis[:, cp["cids"][0]])
     assert relerr(f[cp["cids"][0]], wantc) < 1e-12 and np.count_nonzero(f) == 6
+
+
+def test_checkpoint_is_netcdf_with_the_reference_variable_names(tmp_path, monkeypatch):
+    """md.dump (md.py:684-745): MD<run>.nc in NetCDF classic format with the reference's variable names and shapes (readable by the
+    reference's netCDF4-based ReadNetCDFVar), restored into a fresh object -- also from the reference's own layout (phis [mem, nph])"""
+    from scipy.io import netcdf_file
+    from sclmd_b200.md import md
+    from sclmd_b200.baths import phbath
+    monkeypatch.chdir(tmp_path)
+    c = P.md_case_ph_full()
+    natoms = c["K"].shape[0] // 3
+
+    def make(nstop):
+        m = md(c["dt"], c["nmd"], c["T"], axyz=axyz(natoms), dyn=c["K"], nstart=0, nstop=nstop)
+        for b in range(2):
+            gwl, g = P.gamma_grid(4, 6, 5)
+            bb = phbath(c["T"], c["cids"][b], 0.05, 10, c["dt"], c["nmd"], ml=c["kern"][b].shape[0], gamma=g, gwl=gwl)
+            bb.kernel = c["kern"][b]
+            bb.noise = c["noise"][b]
+            bb.gnoi = lambda: None
+            m.AddBath(bb)
+        m.AddConstr(c["cons"])
+        return m
+    m = make(1)
+    m.Run()
+    assert open("MD0.nc", "rb").read(3) == b"CDF"
+    with netcdf_file("MD0.nc", "r", mmap=False) as f:
+        v = {k: np.array(x[:], dtype=float) for k, x in f.variables.items()}
+    nph, ml = 3 * natoms, m.ml
+    assert v["p"].shape == (nph,) and v["q"].shape == (nph,) and v["t"].shape == (1,) and v["ipie"].shape == (1,)
+    assert v["phis"].shape == (ml, nph) and v["qhis"].shape == (ml, nph) and v["energy"].shape == (c["nmd"],)
+    assert int(v["t"][0]) == c["nmd"] and int(v["ipie"][0]) == 0
+    assert relerr(v["p"], m.p) == 0 and relerr(v["phis"], m.phis) == 0
+    for drop_rings in (False, True):
+        ck = dict(v)
+        if drop_rings:
+            ck = {k: a for k, a in ck.items() if not k.startswith("ring")}      # what a file written by the reference holds
+        m2 = make(1)
+        m2.initialise()
+        m2.ResetHis()
+        m2._restore(ck, with_noise=False)
+        assert m2.t == m.t and relerr(m2.q, m.q) == 0 and relerr(m2.p, m.p) == 0
+        assert relerr(m2.phis, m.phis) == 0
+        for _ in range(5):
+            m2.vv(0)
+        m3 = make(1)
+        m3.initialise()
+        m3.ResetHis()
+        m3._restore(dict(v), with_noise=False)
+        for _ in range(5):
+            m3.vv(0)
+        assert relerr(m2.q, m3.q) < 1e-13
