@@ -153,9 +153,14 @@ def _dataset(buf, addr):
 
 
 def read_nc_variables(filename):
-    """dict name -> ndarray of every contiguous numeric variable of a NetCDF-4 / HDF5 file (root group)"""
+    """dict name -> ndarray of every numeric variable of a NetCDF file: NetCDF-4 / HDF5 (contiguous datasets of the root group,
+    the walker above) or NetCDF classic (scipy.io.netcdf_file)"""
     with open(filename, 'rb') as f:
         buf = f.read()
+    if buf[:3] == b'CDF':
+        from scipy.io import netcdf_file
+        with netcdf_file(filename, 'r', mmap=False) as nf:
+            return {k: np.array(v[:], dtype=float if v.typecode() in 'fd' else None) for k, v in nf.variables.items()}
     if buf[:8] != b'\x89HDF\r\n\x1a\n':
         raise ValueError("%s is not an HDF5 / NetCDF-4 file" % filename)
     ver = buf[8]
@@ -194,6 +199,44 @@ class _Dataset:
 
 
 Dataset = _Dataset
+
+
+def ReadNetCDFVar(file, var):
+    """sclmd/myio.py:184-189, md.py ReadNetCDFVar"""
+    return read_nc_variables(file)[var]
+
+
+def WriteEPHNCfile(filename, wl, hw, U, DynMat, SigL, SigR, Friction, NC, NCP, zeta1, zeta2):
+    """sclmd/myio.py:138-171 in NetCDF classic format (same dimension and variable names; netCDF4 reads it)"""
+    from scipy.io import netcdf_file
+    SigL, SigR = np.asarray(SigL), np.asarray(SigR)
+    f = netcdf_file(filename, 'w')
+    f.createDimension('NPh', len(hw))
+    f.createDimension('NWl', len(wl))
+    f.createDimension('Nsl', len(SigL[0]))
+    f.createDimension('Nsr', len(SigR[0]))
+
+    def put(name, arr, dims, units):
+        v = f.createVariable(name, 'd', dims)
+        v[:] = np.asarray(arr, dtype=float)
+        v.units = units
+    put('Wlist', wl, ('NWl',), 'eV')
+    put('hw', hw, ('NPh',), 'eV')
+    put('U', U, ('NPh', 'NPh'), 'None')
+    put('DynMat', DynMat, ('NPh', 'NPh'), 'eV**2')
+    put('ReSigL', SigL.real, ('NWl', 'Nsl', 'Nsl'), 'eV**2')
+    put('ImSigL', SigL.imag, ('NWl', 'Nsl', 'Nsl'), 'eV**2')
+    put('ReSigR', SigR.real, ('NWl', 'Nsr', 'Nsr'), 'eV**2')
+    put('ImSigR', SigR.imag, ('NWl', 'Nsr', 'Nsr'), 'eV**2')
+    for name, arr in (('Friction', Friction), ('NC', NC), ('NCP', NCP), ('zeta1', zeta1), ('zeta2', zeta2)):
+        put(name, arr, ('NPh', 'NPh'), 'eV**2')
+    f.close()
+
+
+def ReadEPHNCFile(filename):
+    """sclmd/myio.py:80-106"""
+    e = ReadNewEPHNCFile(filename)
+    return e
 
 
 def ReadNewEPHNCFile(filename):

@@ -203,3 +203,20 @@ def test_netcdf4_reader_against_fixture(golden_dir):
     assert np.array_equal(ds["eta_r"][:], lam["eta_r"])
     with pytest.raises(ValueError):
         myio.read_nc_variables(__file__)
+
+
+def test_eph_file_round_trip(tmp_path):
+    """myio.WriteEPHNCfile / ReadNewEPHNCFile (myio.py:109-171): NetCDF classic on the way out, either flavour on the way in"""
+    from sclmd_b200 import myio
+    rng = np.random.default_rng(8)
+    n, nw, ns = 6, 5, 3
+    args = dict(wl=np.linspace(0, 0.2, nw), hw=rng.random(n), U=rng.standard_normal((n, n)), DynMat=P.sym(n, 1),
+                SigL=rng.standard_normal((nw, ns, ns)) + 1j * rng.standard_normal((nw, ns, ns)),
+                SigR=rng.standard_normal((nw, ns, ns)) + 1j * rng.standard_normal((nw, ns, ns)),
+                Friction=P.psd(n, 2), NC=P.antisym(n, 3), NCP=P.sym(n, 4), zeta1=P.sym(n, 5), zeta2=P.antisym(n, 6))
+    fn = str(tmp_path / "eph.nc")
+    myio.WriteEPHNCfile(fn, **args)
+    e = myio.ReadNewEPHNCFile(fn)
+    assert np.array_equal(e.wl, args["wl"]) and np.array_equal(e.DynMat, args["DynMat"]) and np.array_equal(e.SigL, args["SigL"])
+    assert np.array_equal(e.efric, args["Friction"]) and np.array_equal(e.xim, args["NC"]) and np.array_equal(e.zeta2, args["zeta2"])
+    assert np.array_equal(myio.ReadNetCDFVar(fn, "hw"), args["hw"])
