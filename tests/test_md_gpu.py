@@ -77,6 +77,8 @@ def test_golden_trajectories(name, golden_dir):
     ("diag", 1500, 150, 9, 40),     # C1-sized bath, long memory
     ("full", 40, 30, 5, 90),        # split-K full-kernel tail
     ("full", 2, 7, 2, 11),          # odd nc -> padded rows
+    ("full", 6, 30, 70, 12),        # > 64 trajectories, narrow output: 64-wide GEMM tiles with a wave-fitting split count
+    ("full", 3, 150, 130, 8),       # > 64 trajectories, wide output: 128-wide tiles
 ])
 def test_memory_kernels_vs_oracle(kind, ml, nc, ntraj, nsteps):
     from sclmd_b200.engine import MDEngine
