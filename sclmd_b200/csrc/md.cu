@@ -597,7 +597,8 @@ __global__ void __launch_bounds__(320, 1) k_tail_far_tma(const double *__restric
 // cp.async.bulk against full/empty mbarrier pairs while the consumer warps run the Toeplitz update; a stage is handed back
 // as soon as its SR rows are consumed, so (NST-1)/NST of the staging memory is always in flight (the two-stage kernel above
 // has at most half in flight and is bound by the bulk-copy latency: 3.2 us per 77 KB stage against 1.3 us of math).
-// Measured at C5 (ms per ring pass): 2 x 16 rows 2.93 | 16 x 2 rows 2.92 | 8 x 4 rows 2.42-2.62 | 4 x 8 rows 2.39 | 5 x 8 rows 2.19.
+// Measured at C5 (ms per ring pass): 2 x 16 rows 2.93 | 16 x 2 rows 2.92 | 8 x 4 rows 2.42-2.62 | 4 x 8 rows 2.39 | 5 x 8 rows 2.19;
+// one trajectory per CTA (10 x 8 or 5 x 16 rows) 2.7: the kernel-window loads are no longer shared by two trajectories.
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
