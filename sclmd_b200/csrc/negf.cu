@@ -602,16 +602,16 @@ __global__ void __launch_bounds__(256) k_backsub(Geo g, double *W, const int *ac
                     Ui[i][kk] = ok ? wim[(size_t)s_act[k0 + min(i, kb - 1)] * lw + kc + kk] : 0.0;
                 }
                 __syncthreads();
-                for (int kk = 0; kk < kn; kk += 4) {
-                    double sr[4], si[4];
+                for (int kk = 0; kk < kn; kk += 16) {       // 32 independent loads of the thread's own solution column in flight
+                    double sr[16], si[16];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
+                    for (int u = 0; u < 16; ++u) {
                         const int kx = min(kk + u, kn - 1);
                         sr[u] = wre[(size_t)s_act[kc + kx] * lw + col];
                         si[u] = wim[(size_t)s_act[kc + kx] * lw + col];
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u)
+                    for (int u = 0; u < 16; ++u)
                         if (kk + u < kn) {
 #pragma unroll
                             for (int i = 0; i < 16; ++i) cfma_sub(xr[i], xi[i], Ur[i][kk + u], Ui[i][kk + u], sr[u], si[u]);
