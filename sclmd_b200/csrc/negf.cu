@@ -17,7 +17,7 @@
 //                 U12 = L11^-1 A12 (64 rows) with the in-block updates on the FP64 tensor pipe, next chunk prefetched in registers
 //   k_gemm        complex rank-16 (panel columns of the block) / rank-64 (trailing matrix) update on the FP64 tensor pipe
 //                 (4 real DMMA.8x8x4 per complex fragment pair), 64x64 tiles, K slabs through a 3-stage cp.async ring
-//   k_backsub     thread per right-hand side, rows >= row_stop only
+//   k_block_trsm_upper + k_gemm   back substitution of the rows >= row_stop in 64-row blocks from the bottom, on the tensor pipe
 //   k_observe     reduction to one number per frequency
 // with several batches in flight on separate streams so that the latency-bound kernels of one batch fill the tails of another.
 // Pivoting is IMPLICIT over the whole factorisation: no row of W ever moves.  Every frequency carries an index list
@@ -444,6 +444,126 @@ __global__ void __launch_bounds__(256, 2) k_block_trsm(Geo g, double *W, const i
     }
 }
 
+// ------------------------------------------------------------------------------------------------ back substitution, one block
+// X_B = U_BB^-1 Y_B for the pivot rows at positions [b0, b1) (<= 64) and every right-hand side: the mirror image of
+// k_block_trsm (upper triangular, non-unit diagonal, sub-blocks from the bottom up).  U_BB sits in shared memory as the DMMA A
+// operand with its 16x16 diagonal blocks inverted once per CTA; the rows above inside the block are updated on the tensor pipe.
+// The rows above the block get  Y -= U[above, B] X_B  from k_gemm.
+__global__ void __launch_bounds__(256, 2) k_block_trsm_upper(Geo g, double *W, const int *act, int b0, int b1) {
+    extern __shared__ double sm[];
+    constexpr int NBW = 16;
+    double *Ur = sm, *Ui = Ur + TS * LDS_T, *Tr = Ui + TS * LDS_T, *Ti = Tr + TS * LDT;
+    __shared__ int s_row[TS];
+    const int b = blockIdx.x, lw = g.lw, nblk = b1 - b0, nsub = (nblk + NBW - 1) / NBW;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, fr = lane >> 2, fk = lane & 3;
+    double *wre = W + (size_t)b * 2 * g.plane, *wim = wre + g.plane;
+    const int *actb = act + (size_t)b * g.nrp;
+    if (tid < TS) s_row[tid] = actb[b0 + min(tid, nblk - 1)];
+    __syncthreads();
+    for (int e = tid; e < TS * TS; e += 256) {
+        const int kx = e % TS, i = e / TS;
+        const bool ok = i < nblk && kx < nblk && kx >= i;
+        Ur[i * LDS_T + kx] = ok ? wre[(size_t)s_row[i] * lw + b0 + kx] : (i == kx ? 1.0 : 0.0);   // identity beyond a partial block
+        Ui[i * LDS_T + kx] = ok ? wim[(size_t)s_row[i] * lw + b0 + kx] : 0.0;
+    }
+    __syncthreads();
+    {   // thread (j, c): column c of inv(U_jj) by back substitution; x_i = 0 below the diagonal
+        const int j = tid / NBW, c = tid % NBW, jb = j * NBW;
+        double xr[NBW], xi[NBW];
+        if (tid < nsub * NBW) {
+#pragma unroll
+            for (int i = NBW - 1; i >= 0; --i) {
+                double sr = i == c ? 1.0 : 0.0, si = 0.0;
+#pragma unroll
+                for (int k = i + 1; k < NBW; ++k)
+                    if (k <= c) cfma_sub(sr, si, Ur[(jb + i) * LDS_T + jb + k], Ui[(jb + i) * LDS_T + jb + k], xr[k], xi[k]);
+                const double dr = Ur[(jb + i) * LDS_T + jb + i], di = Ui[(jb + i) * LDS_T + jb + i];
+                const double rn = 1.0 / (dr * dr + di * di);
+                const bool on = i <= c;
+                xr[i] = on ? (sr * dr + si * di) * rn : 0.0;
+                xi[i] = on ? (si * dr - sr * di) * rn : 0.0;
+            }
+        }
+        __syncthreads();
+        if (tid < nsub * NBW) {
+#pragma unroll
+            for (int i = 0; i < NBW; ++i) {
+                Ur[(jb + i) * LDS_T + jb + c] = xr[i];
+                Ui[(jb + i) * LDS_T + jb + c] = xi[i];
+            }
+        }
+    }
+    const int nchunk = (g.nrhs + TC - 1) / TC;
+    for (int ch = 0; ch < nchunk; ++ch) {
+        __syncthreads();          // inverses staged (first pass) / previous chunk written back
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = tid + u * 256, pl = e >> 10, row = (e >> 4) & 63, cp = (e & 15) * 2, col = g.np + ch * TC + cp;
+            double2 v = make_double2(0.0, 0.0);
+            if (row < nblk && col < g.ncols) v = *reinterpret_cast<const double2 *>((pl ? wim : wre) + (size_t)s_row[row] * lw + col);
+            *reinterpret_cast<double2 *>((pl ? Ti : Tr) + row * LDT + cp) = v;
+        }
+        __syncthreads();
+        for (int j = nsub - 1; j >= 0; --j) {
+            const int jb = j * NBW;
+            if (warp < TC / 8) {      // X_j = inv(U_jj) T_j : warp w owns the 8-column fragment w (reads its inputs, then writes)
+                const int cbase = warp * 8;
+                double ur[NBW / 4], ui[NBW / 4];
+#pragma unroll
+                for (int k4 = 0; k4 < NBW; k4 += 4) {
+                    ur[k4 / 4] = Tr[(jb + k4 + fk) * LDT + cbase + fr];
+                    ui[k4 / 4] = Ti[(jb + k4 + fk) * LDT + cbase + fr];
+                }
+                double2 yr[NBW / 8], yi[NBW / 8];
+#pragma unroll
+                for (int mf = 0; mf < NBW / 8; ++mf) {
+                    yr[mf] = yi[mf] = make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int k4 = 0; k4 < NBW; k4 += 4) {
+                        const double alr = Ur[(jb + mf * 8 + fr) * LDS_T + jb + k4 + fk], ali = Ui[(jb + mf * 8 + fr) * LDS_T + jb + k4 + fk];
+                        dmma(yr[mf].x, yr[mf].y, alr, ur[k4 / 4]);
+                        dmma(yr[mf].x, yr[mf].y, -ali, ui[k4 / 4]);
+                        dmma(yi[mf].x, yi[mf].y, alr, ui[k4 / 4]);
+                        dmma(yi[mf].x, yi[mf].y, ali, ur[k4 / 4]);
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int mf = 0; mf < NBW / 8; ++mf) {
+                    *reinterpret_cast<double2 *>(Tr + (jb + mf * 8 + fr) * LDT + cbase + 2 * fk) = yr[mf];
+                    *reinterpret_cast<double2 *>(Ti + (jb + mf * 8 + fr) * LDT + cbase + 2 * fk) = yi[mf];
+                }
+            }
+            __syncthreads();
+            // rows above inside the block: jb rows in 8-row fragments x 4 column fragments over the 8 warps
+            for (int q = warp; q < (jb / 8) * (TC / 8); q += 8) {
+                const int rbase = (q / (TC / 8)) * 8, cbase = (q % (TC / 8)) * 8;
+                double2 cr = *reinterpret_cast<const double2 *>(Tr + (rbase + fr) * LDT + cbase + 2 * fk);
+                double2 ci = *reinterpret_cast<const double2 *>(Ti + (rbase + fr) * LDT + cbase + 2 * fk);
+#pragma unroll
+                for (int k4 = 0; k4 < NBW; k4 += 4) {
+                    const double alr = Ur[(rbase + fr) * LDS_T + jb + k4 + fk], ali = Ui[(rbase + fr) * LDS_T + jb + k4 + fk];
+                    const double xr = Tr[(jb + k4 + fk) * LDT + cbase + fr], xi = Ti[(jb + k4 + fk) * LDT + cbase + fr];
+                    dmma(cr.x, cr.y, -alr, xr);
+                    dmma(cr.x, cr.y, ali, xi);
+                    dmma(ci.x, ci.y, -alr, xi);
+                    dmma(ci.x, ci.y, -ali, xr);
+                }
+                *reinterpret_cast<double2 *>(Tr + (rbase + fr) * LDT + cbase + 2 * fk) = cr;
+                *reinterpret_cast<double2 *>(Ti + (rbase + fr) * LDT + cbase + 2 * fk) = ci;
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = tid + u * 256, pl = e >> 10, row = (e >> 4) & 63, cp = (e & 15) * 2, col = g.np + ch * TC + cp;
+            if (row < nblk && col < g.ncols)
+                *reinterpret_cast<double2 *>((pl ? wim : wre) + (size_t)s_row[row] * lw + col) =
+                    *reinterpret_cast<const double2 *>((pl ? Ti : Tr) + row * LDT + cp);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ rank-K update
 // C[r0 + 64 by .. , c0 + 64 bx ..) -= A B  with  A = W[rows, ka:ka+K]  (L21)  and  B = W[ka:ka+K, cols]  (U12), K <= 64, complex planar.
 // 8 warps = 2 row groups (32 rows) x 4 column groups (16 columns); the C tile is the accumulator itself:
@@ -565,87 +685,6 @@ __global__ void __launch_bounds__(256, 2) k_gemm(Geo g, double *W, const int *ac
                 *reinterpret_cast<double2 *>(wim + (size_t)row * lw + col) = cim[i][j];
             }
         }
-}
-
-// ------------------------------------------------------------------------------------------------ back substitution
-// One CTA per frequency, thread per right-hand side, 16-row blocks from the bottom up to row_stop.  The U rows of a block are
-// staged in shared memory (every thread multiplies them with its own solution column, which it re-reads from W).
-constexpr int BSK = 128;
-__global__ void __launch_bounds__(256) k_backsub(Geo g, double *W, const int *act, int row_stop) {
-    const int b = blockIdx.x, lw = g.lw, np = g.np;
-    double *wre = W + (size_t)b * 2 * g.plane, *wim = wre + g.plane;
-    __shared__ double Ur[16][BSK + 1], Ui[16][BSK + 1];
-    const int *s_act = act + (size_t)b * g.nrp;      // position -> physical row (read-only here: served from L1/L2)
-    const int last = ((np - 1) / 16) * 16;
-    for (int cb = 0; cb < g.nrhs; cb += blockDim.x) {
-        const int c = cb + threadIdx.x;
-        const bool actv = c < g.nrhs;
-        const int col = np + min(c, g.nrhs - 1);
-        for (int k0 = last; k0 >= 0 && k0 + 16 > row_stop; k0 -= 16) {
-            const int kb = min(16, np - k0);
-            double xr[16], xi[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                xr[i] = xi[i] = 0.0;
-                if (i < kb) {
-                    xr[i] = wre[(size_t)s_act[k0 + i] * lw + col];
-                    xi[i] = wim[(size_t)s_act[k0 + i] * lw + col];
-                }
-            }
-            for (int kc = k0 + kb; kc < np; kc += BSK) {
-                const int kn = min(BSK, np - kc);
-                __syncthreads();
-                for (int e = threadIdx.x; e < 16 * kn; e += blockDim.x) {
-                    const int kk = e % kn, i = e / kn;
-                    const bool ok = i < kb;
-                    Ur[i][kk] = ok ? wre[(size_t)s_act[k0 + min(i, kb - 1)] * lw + kc + kk] : 0.0;
-                    Ui[i][kk] = ok ? wim[(size_t)s_act[k0 + min(i, kb - 1)] * lw + kc + kk] : 0.0;
-                }
-                __syncthreads();
-                for (int kk = 0; kk < kn; kk += 16) {       // 32 independent loads of the thread's own solution column in flight
-                    double sr[16], si[16];
-#pragma unroll
-                    for (int u = 0; u < 16; ++u) {
-                        const int kx = min(kk + u, kn - 1);
-                        sr[u] = wre[(size_t)s_act[kc + kx] * lw + col];
-                        si[u] = wim[(size_t)s_act[kc + kx] * lw + col];
-                    }
-#pragma unroll
-                    for (int u = 0; u < 16; ++u)
-                        if (kk + u < kn) {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) cfma_sub(xr[i], xi[i], Ur[i][kk + u], Ui[i][kk + u], sr[u], si[u]);
-                        }
-                }
-            }
-            __syncthreads();
-            for (int e = threadIdx.x; e < 16 * 16; e += blockDim.x) {
-                const int kk = e % 16, i = e / 16;
-                const bool ok = i < kb && kk < kb;
-                Ur[i][kk] = ok ? wre[(size_t)s_act[k0 + min(i, kb - 1)] * lw + k0 + kk] : (i == kk ? 1.0 : 0.0);
-                Ui[i][kk] = ok ? wim[(size_t)s_act[k0 + min(i, kb - 1)] * lw + k0 + kk] : 0.0;
-            }
-            __syncthreads();
-#pragma unroll
-            for (int jj = 15; jj >= 0; --jj) {
-                const double dr = Ur[jj][jj], di = Ui[jj][jj];
-                const double dn = dr * dr + di * di;
-                const double tr = (xr[jj] * dr + xi[jj] * di) / dn, ti = (xi[jj] * dr - xr[jj] * di) / dn;
-                xr[jj] = tr; xi[jj] = ti;
-#pragma unroll
-                for (int i2 = 0; i2 < 16; ++i2)
-                    if (i2 < jj) cfma_sub(xr[i2], xi[i2], Ur[i2][jj], Ui[i2][jj], tr, ti);
-            }
-            if (actv) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    if (i < kb) {
-                        wre[(size_t)s_act[k0 + i] * lw + col] = xr[i];
-                        wim[(size_t)s_act[k0 + i] * lw + col] = xi[i];
-                    }
-            }
-        }
-    }
 }
 
 // keep G^a[:,sel] (pass 0 of the biased power spectrum) while the second factorisation runs; Xs is indexed by position
@@ -847,8 +886,16 @@ cudaError_t enqueue_lu(const Geo &g, const Problem &p, StreamSlot &s, int *statu
             pf.end(st);
         }
     }
+    // back substitution for the rows >= row_stop, 64-row blocks from the bottom: triangular solve of the block (k_block_trsm_upper),
+    // then the rows above it on the tensor pipe (k_gemm, rank = block height)
     pf.begin(5, st);
-    k_backsub<<<nbat, std::min(256, round_up(g.nrhs, 32)), 0, st>>>(g, W, act, row_stop);
+    const int rs = (row_stop / TS) * TS;
+    for (int b0 = ((g.np - 1) / TS) * TS; b0 >= rs; b0 -= TS) {
+        const int b1 = std::min(b0 + TS, g.np);
+        k_block_trsm_upper<<<nbat, 256, TRSM_SMEM, st>>>(g, W, act, b0, b1);
+        if (b0 > rs)
+            k_gemm<<<dim3(cdiv(g.nrhs, TS), (b0 - rs) / TS, nbat), 256, GEMM_SMEM, st>>>(g, W, act, nullptr, nullptr, rs, g.np, g.ncols, b0, b1 - b0);
+    }
     pf.end(st);
     return cudaGetLastError();
 }
@@ -974,6 +1021,7 @@ int run_lu(int device, int n, const double *K, const int32_t *idxL, int nL, cons
     }
     SCLMD_CUDA(cudaFuncSetAttribute(k_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
     SCLMD_CUDA(cudaFuncSetAttribute(k_block_trsm<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSM_SMEM));
+    SCLMD_CUDA(cudaFuncSetAttribute(k_block_trsm_upper, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSM_SMEM));
 
     DevBuf<unsigned long long> dtiles;
     if (g_prof.on) SCLMD_CUDA(dtiles.alloc(1));
