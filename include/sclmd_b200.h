@@ -121,6 +121,27 @@ int sclmd_md_set_overlap(sclmd_md *h, int on);
  * example, examples/runmd.py) is ONE cooperative launch of a persistent kernel with one grid barrier per step; 0: per-step launches */
 int sclmd_md_set_persistent(sclmd_md *h, int on);
 
+/* Force drivers (md.AddPotential, md.py:457-459, 481-485; protocol lammpsdriver.py:83-84): the potential force is a host callback.
+ * on = 1: the handle never multiplies by K; sclmd_md_run is refused and a step is the pair below.  Forces are the driver's own
+ * (mass-weighted, reference sign), [ntraj][nph].  Evaluations A, B, C of the bath forces, the history tails, the constraint and the
+ * observables stay on the device; the callback runs once per step (twice with constraints: q_{t+1} = constrain(q') != q', md.py:449).
+ *     if (sclmd_md_force_needed(h) == 1) sclmd_md_set_force(h, f(q_t));      first step, after set_state, with constraints
+ *     sclmd_md_step_begin(h, q_trial);   q_trial[ntraj][nph] = q' of md.py:392
+ *     sclmd_md_step_end(h, f(q_trial));  */
+int sclmd_md_set_external_force(sclmd_md *h, int on);
+int sclmd_md_force_needed(sclmd_md *h);
+int sclmd_md_set_force(sclmd_md *h, const double *f);
+int sclmd_md_step_begin(sclmd_md *h, double *q_trial);
+int sclmd_md_step_end(sclmd_md *h, const double *f_trial);
+
+/* md.f, md.fbaths, md.fhis (md.py:390-398, 403, 411).  on = 1: every step also stores the total force of evaluation C (md.f) and
+ * each bath's force of evaluation A (the one the heat current is built from, md.fhis) and of evaluation C (md.fbaths after vv);
+ * after a step   sclmd_md_get_force(h, f[ntraj][nph])   and
+ *                sclmd_md_get_bath_force(h, bath, evaluation (0 = A, 2 = C), fb[ntraj][nc])   return them. */
+int sclmd_md_set_force_output(sclmd_md *h, int on);
+int sclmd_md_get_force(sclmd_md *h, double *f);
+int sclmd_md_get_bath_force(sclmd_md *h, int bath, int evaluation, double *fb);
+
 /* 1 (default): diagonal-kernel baths with ml >= 128 stream their history ring from HBM once per 16 steps
  * (time-blocked far/near tails, same flops, same results to rounding); 0: one full ring pass per step -- the
  * direct single-tail algorithm on which the HBM roofline of SURVEY.md section 8d is defined */
@@ -243,10 +264,15 @@ int sclmd_bpt_ps_bias(int device, int n, const double *K, const int32_t *idxL, i
 int sclmd_sig_selfenergy(int device, int m, const double *K00, const double *K11, const double *K01,
                          const double *K10, double eta, char direction, const double *omegas, int nw,
                          double *se_out, int32_t *iters_out);
-/* sig.tm / sig.gettm (selfenergy.py:145-151, 168-178) */
+/* sig.sgf (selfenergy.py:105-131): the surface Green function of one lead after the decimation,
+ *   sgf_out[nw][m][m] complex (interleaved re, im); same arguments and errors as sclmd_sig_selfenergy */
+int sclmd_sig_sgf(int device, int m, const double *K00, const double *K11, const double *K01,
+                  const double *K10, double eta, char direction, const double *omegas, int nw,
+                  double *sgf_out, int32_t *iters_out);
 /* sig.retargf (selfenergy.py:145-147): green_out[nw][m][m] complex (interleaved re, im) */
 int sclmd_sig_green(int device, int m, const double *K00, const double *K11, const double *K01,
                     const double *K10, double eta, const double *omegas, int nw, double *green_out);
+/* sig.tm / sig.gettm (selfenergy.py:145-151, 168-178) */
 int sclmd_sig_tm(int device, int m, const double *K00, const double *K11, const double *K01,
                  const double *K10, double eta, const double *omegas, int nw, double *tm_out);
 

@@ -42,6 +42,14 @@ _PROTOS = {
     "sclmd_md_get_step_observables": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
     "sclmd_md_set_overlap": (C.c_int, [C.c_void_p, C.c_int]),
     "sclmd_md_set_persistent": (C.c_int, [C.c_void_p, C.c_int]),
+    "sclmd_md_set_force_output": (C.c_int, [C.c_void_p, C.c_int]),
+    "sclmd_md_get_force": (C.c_int, [C.c_void_p, c_double_p]),
+    "sclmd_md_get_bath_force": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p]),
+    "sclmd_md_set_external_force": (C.c_int, [C.c_void_p, C.c_int]),
+    "sclmd_md_force_needed": (C.c_int, [C.c_void_p]),
+    "sclmd_md_set_force": (C.c_int, [C.c_void_p, c_double_p]),
+    "sclmd_md_step_begin": (C.c_int, [C.c_void_p, c_double_p]),
+    "sclmd_md_step_end": (C.c_int, [C.c_void_p, c_double_p]),
     "sclmd_md_set_tail_block": (C.c_int, [C.c_void_p, C.c_int]),
     "sclmd_md_get_profile_all": (C.c_int, [C.c_void_p, c_double_p, c_int64_p]),
     "sclmd_md_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
@@ -81,6 +89,7 @@ _PROTOS = {
     "sclmd_bpt_green": (C.c_int, [C.c_int, C.c_int, c_double_p, c_int32_p, C.c_int, c_int32_p, C.c_int, C.c_double, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, C.c_double, c_double_p, C.c_int, C.c_int, c_double_p]),
     "sclmd_bpt_ps_bias": (C.c_int, [C.c_int, C.c_int, c_double_p, c_int32_p, C.c_int, c_int32_p, C.c_int, C.c_double, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, C.c_double, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, C.c_int, c_int32_p, C.c_int, c_double_p]),
     "sclmd_sig_selfenergy": (C.c_int, [C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p, C.c_double, C.c_char, c_double_p, C.c_int, c_double_p, c_int32_p]),
+    "sclmd_sig_sgf": (C.c_int, [C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p, C.c_double, C.c_char, c_double_p, C.c_int, c_double_p, c_int32_p]),
     "sclmd_sig_green": (C.c_int, [C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p, C.c_double, c_double_p, C.c_int, c_double_p]),
     "sclmd_sig_tm": (C.c_int, [C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p, C.c_double, c_double_p, C.c_int, c_double_p]),
 }

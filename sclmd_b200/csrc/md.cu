@@ -42,6 +42,7 @@ struct BathDev {  // POD view passed to kernels
     const double *lin;       // [ntraj][ncp]
     double *ring;            // [ntraj][ml][ncp]
     double *cur;             // [nmd][ntraj]
+    double *fa, *fc;         // [ntraj][ncp] bath force of evaluation A (md.fhis) / of evaluation C (md.fbaths after vv), or NULL
 };
 struct BathSet {
     int nb;
@@ -53,7 +54,7 @@ struct Bath {
     bool has_lin = false, has_extra = false;
     double c0 = 1.0;
     DevBuf<int> cids, inv;
-    DevBuf<double> kern, W, ring, xq, lin, tailp, noise, cur, far;
+    DevBuf<double> kern, W, ring, xq, lin, tailp, noise, cur, far, fa, fc;
     bool blocked = false;     // time-blocked tails (diagonal kernel, long memory)
     int far_nsplit = 1;
     long long far_t0 = -1;    // block start the far tails in `far` belong to
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(256, NBATH <= 2 ? 4 : 1) k_phase_a(BathSet bs,
                     const double fb = bath_force(bs.b[b], traj, ntraj, a, slab, pi);
                     cur[b] += fb * pi;
                     f += fb;
+                    if (bs.b[b].fa) bs.b[b].fa[(size_t)traj * bs.b[b].ncp + a] = fb;
                     bs.b[b].ring[((size_t)traj * bs.b[b].ml + (int)(t % bs.b[b].ml)) * bs.b[b].ncp + a] = pi;
                 }
             }
@@ -127,7 +129,8 @@ __global__ void __launch_bounds__(256, NBATH <= 2 ? 4 : 1) k_phase_bc(BathSet bs
                                                    const double *__restrict__ x, const double *__restrict__ phalf,
                                                    const double *__restrict__ Gn, int gsplit, size_t gstride, double *__restrict__ pout,
                                                    const double *__restrict__ qn, double *__restrict__ qout,
-                                                   const unsigned char *__restrict__ cons, int final, int fused) {
+                                                   const unsigned char *__restrict__ cons, int final, int fused,
+                                                   double *__restrict__ fout) {
     const int traj = blockIdx.x;
     const size_t row = (size_t)traj * ld;
     if (tptr) t = *tptr;                    // captured in a CUDA graph: the step counter lives on the device
@@ -137,15 +140,19 @@ __global__ void __launch_bounds__(256, NBATH <= 2 ? 4 : 1) k_phase_bc(BathSet bs
         double g = Gn[row + i];
         for (int z = 1; z < gsplit; ++z) g += Gn[(size_t)z * gstride + row + i];
         double xi = fused ? ph : x[row + i];
-        double pnew = 0.0;
+        double pnew = 0.0, f = 0.0;
         const int reps = fused ? 2 : 1;  // all baths time-local & diagonal: B and C in registers
         for (int r = 0; r < reps; ++r) {
-            double f = -g;
+            f = -g;
 #pragma unroll
             for (int b = 0; b < NBATH; ++b) {
                 if (b < bs.nb) {
                     const int a = bs.b[b].inv[i];
-                    if (a >= 0) f += bath_force(bs.b[b], traj, ntraj, a, slab, xi);
+                    if (a >= 0) {
+                        const double fb = bath_force(bs.b[b], traj, ntraj, a, slab, xi);
+                        f += fb;
+                        if (final && bs.b[b].fc) bs.b[b].fc[(size_t)traj * bs.b[b].ncp + a] = fb;   // the last evaluation wins
+                    }
                 }
             }
             pnew = ph + dt * f / 2.0;
@@ -158,6 +165,7 @@ __global__ void __launch_bounds__(256, NBATH <= 2 ? 4 : 1) k_phase_bc(BathSet bs
                 qv = 0.0;
             }
             qout[row + i] = qv;
+            if (fout) fout[row + i] = f;     // md.f: the force of evaluation C (md.py:403,411)
         }
         pout[row + i] = pnew;
     }
@@ -730,6 +738,11 @@ __global__ void k_gather_qc(const double *__restrict__ qn, int ld, const int *__
     for (int k = threadIdx.x; k < ncons; k += blockDim.x) qc[(size_t)traj * ldc + k] = qn[(size_t)traj * ld + cidx[k]];
 }
 
+__global__ void k_negate(double *__restrict__ x, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = -x[i];
+}
+
 __global__ void k_sum_slots(const double *__restrict__ cur, int nmd, int ntraj, double *__restrict__ sums) {
     const int traj = blockIdx.x * blockDim.x + threadIdx.x;
     if (traj >= ntraj) return;
@@ -757,6 +770,14 @@ struct sclmd_md {
     DevBuf<double> K, q, p, G, Gn, phalf, p1, qn, etot, scratch;
     DevBuf<unsigned char> cons;
     bool has_cons = false, d_valid = false, kc_valid = false, use_corr = false;
+    // md.AddPotential drivers (md.py:457-459, 481-485): the potential force comes from a host callback, one call per step
+    // (two with constraints); everything else of the step stays on the device (sclmd_md_step_begin / sclmd_md_step_end)
+    bool ext_force = false, ext_open = false;
+    // md.f / md.fbaths (md.py:390-398, 411): force of evaluation C and bath forces of evaluation A of the last step, on request
+    bool want_f = false;
+    long long f_step = -1;      // the step (value of t after it) fC / fa belong to
+    DevBuf<double> fC;
+    bool corr() const { return has_cons && use_corr && !ext_force; }
     int ncons = 0, ldcons = 0;
     DevBuf<int> cidx;
     DevBuf<double> Kc, qc, Dc;   // constraint correction: D = q'[cons] . K[:,cons]^T
@@ -829,6 +850,8 @@ struct sclmd_md {
             d.has_lin = b.has_lin; d.use_tail = b.ml > 1; d.c0 = b.c0;
             d.inv = b.inv.p; d.cids = b.cids.p; d.k0 = b.kern.p; d.noise = b.noise.p;
             d.tailp = b.tailp.p; d.lin = b.lin.p; d.ring = b.ring.p; d.cur = b.cur.p;
+            d.fa = want_f ? b.fa.p : nullptr;
+            d.fc = want_f ? b.fc.p : nullptr;
         }
         return s;
     }
@@ -943,14 +966,14 @@ struct sclmd_md {
     int enqueue_rest(const BathSet &bs, bool lin, const long long *tptr) {
         const unsigned char *cm = has_cons ? cons.p : nullptr;
         const size_t gs = (size_t)ntraj * ld;
-        if (has_cons && use_corr) {
+        if (corr()) {
             k_gather_qc<<<ntraj, 128, 0, st>>>(qn.p, ld, cidx.p, ncons, ldcons, qc.p);
             SCLMD_CUDA(cudaGetLastError());
             ++launches;
         }
         auto bc = [&](const double *x, double *pout, int final, int fused) -> cudaError_t {
-            if (bs.nb <= 2) k_phase_bc<2><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, tptr, dt, x, phalf.p, Gn.p, gplan.nsplit, gs, pout, qn.p, q.p, cm, final, fused);
-            else k_phase_bc<MAXB><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, tptr, dt, x, phalf.p, Gn.p, gplan.nsplit, gs, pout, qn.p, q.p, cm, final, fused);
+            if (bs.nb <= 2) k_phase_bc<2><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, tptr, dt, x, phalf.p, Gn.p, gplan.nsplit, gs, pout, qn.p, q.p, cm, final, fused, want_f ? fC.p : nullptr);
+            else k_phase_bc<MAXB><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, tptr, dt, x, phalf.p, Gn.p, gplan.nsplit, gs, pout, qn.p, q.p, cm, final, fused, want_f ? fC.p : nullptr);
             ++launches;
             return cudaGetLastError();
         };
@@ -964,7 +987,7 @@ struct sclmd_md {
                 if (b->has_lin) if (int e = bath_lin(*b, p1.p, qn.p)) return e;
             SCLMD_CUDA(bc(p1.p, p.p, 1, 0));
         }
-        if (has_cons && use_corr) {
+        if (corr()) {
             // q_{t+1} = constrain(q') != q' (md.py:407-408), so the reference's force cache misses (md.py:449) and K.q is
             // evaluated again.  Here: K.q_{t+1} = K.q' - K[:,cons].q'[cons], a GEMM over the constrained columns only.
             GemmArgs g{};
@@ -979,7 +1002,7 @@ struct sclmd_md {
     bool use_persist = true;
     DevBuf<double> xbuf;
     bool persist_ok() const {
-        if (!use_persist || profiling || ntraj > PS_MAXT || nph > 256 * PS_EPT || baths.size() > 2) return false;
+        if (!use_persist || ext_force || want_f || profiling || ntraj > PS_MAXT || nph > 256 * PS_EPT || baths.size() > 2) return false;
         for (auto &b : baths)
             if (b->ml > 1 || b->has_lin || b->kind != SCLMD_KERNEL_DIAG) return false;
         return true;
@@ -1020,7 +1043,7 @@ struct sclmd_md {
         return 0;
     }
     void finish_step() {      // host-side state after a step
-        if (has_cons && use_corr) {
+        if (corr()) {
             d_valid = true;
             std::swap(G.p, Gn.p);
             gpar ^= 1;
@@ -1031,6 +1054,50 @@ struct sclmd_md {
             gpar ^= 1;
         }
         ++t;
+        if (want_f) f_step = t;
+    }
+
+    // dst (K-slice 0) = -f, the other K-slices zero: the phase kernels add the slices and apply the sign themselves
+    int upload_force(double *dst, const double *f) {
+        const size_t n = (size_t)ntraj * ld, w = nph * sizeof(double);
+        SCLMD_CUDA(cudaMemcpy2DAsync(dst, ld * sizeof(double), f, w, w, ntraj, cudaMemcpyHostToDevice, st));
+        k_negate<<<cdiv((int)n, 256), 256, 0, st>>>(dst, n);
+        SCLMD_CUDA(cudaGetLastError());
+        ++launches;
+        if (gplan.nsplit > 1) SCLMD_CUDA(cudaMemsetAsync(dst + n, 0, (size_t)(gplan.nsplit - 1) * n * sizeof(double), st));
+        return 0;
+    }
+    // first half of a step with a host force driver: evaluation A, q' and the history tails; q' goes back to the caller
+    int ext_begin(double *q_trial) {
+        BathSet bs = view();
+        if (any_lin())
+            for (auto &b : baths)
+                if (b->has_lin) if (int e = bath_lin(*b, p.p, q.p)) return e;
+        if (bs.nb <= 2) k_phase_a<2><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, q.p, p.p, G.p, gplan.nsplit, (size_t)ntraj * ld, nullptr, phalf.p, qn.p, etot.p);
+        else k_phase_a<MAXB><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, q.p, p.p, G.p, gplan.nsplit, (size_t)ntraj * ld, nullptr, phalf.p, qn.p, etot.p);
+        SCLMD_CUDA(cudaGetLastError());
+        SCLMD_CUDA(cudaEventRecord(evObs, st));
+        obs_slab = t % nmd;
+        ++launches;
+        dt_synced = false;
+        for (auto &b : baths) if (int e = tail_step(*b, t)) return e;
+        const size_t w = nph * sizeof(double);
+        SCLMD_CUDA(cudaMemcpy2DAsync(q_trial, w, qn.p, ld * sizeof(double), w, ntraj, cudaMemcpyDeviceToHost, st));
+        SCLMD_CUDA(cudaStreamSynchronize(st));
+        ext_open = true;
+        return 0;
+    }
+    // second half: the driver's force at q' arrives, evaluations B and C, constraint
+    int ext_end(const double *f_trial) {
+        if (int e = upload_force(Gn.p, f_trial)) return e;
+        if (noise_pending) {
+            SCLMD_CUDA(cudaStreamWaitEvent(st, evN, 0));
+            noise_pending = false;
+        }
+        if (int e = enqueue_rest(view(), any_lin(), nullptr)) return e;
+        finish_step();
+        ext_open = false;
+        return 0;
     }
 
     int step() {
@@ -1056,7 +1123,7 @@ struct sclmd_md {
         ++launches;
         bool any_tail = false;
         for (auto &b : baths) any_tail |= b->ml > 1;
-        if (has_cons && use_corr && !kc_valid) {
+        if (corr() && !kc_valid) {
             k_gather_kc<<<nph, 128, 0, st>>>(K.p, nph, ld, cidx.p, ncons, ldcons, Kc.p);
             SCLMD_CUDA(cudaGetLastError());
             kc_valid = true;
@@ -1433,6 +1500,11 @@ int sclmd_md_set_tail_block(sclmd_md *h, int on) {
 
 int sclmd_md_run(sclmd_md *h, int64_t nsteps, float *elapsed_ms) {
     SCLMD_REQUIRE(h && nsteps >= 0, "sclmd_md_run: bad arguments");
+    if (h->ext_force) {
+        set_error("sclmd_md_run: the handle takes its potential force from the host (sclmd_md_set_external_force): "
+                  "step with sclmd_md_step_begin / sclmd_md_step_end");
+        return SCLMD_ERR_STATE;
+    }
     if (!h->have_dyn) {
         set_error("sclmd_md_run: no dynamical matrix set (md.py:469 'no driver, no md')");
         return SCLMD_ERR_STATE;
@@ -1450,6 +1522,102 @@ int sclmd_md_run(sclmd_md *h, int64_t nsteps, float *elapsed_ms) {
     SCLMD_CUDA(cudaStreamSynchronize(h->st));
     if (elapsed_ms) SCLMD_CUDA(cudaEventElapsedTime(elapsed_ms, h->ev0, h->ev1));
     h->prof_collect();
+    return SCLMD_OK;
+}
+
+// ---- force drivers (md.AddPotential, md.py:457-459, 481-485): potential force from a host callback
+// on = 1: the handle never multiplies by K; the caller supplies f(q) (reference sign: the force itself, mass-weighted,
+// [ntraj][nph]) through sclmd_md_set_force / sclmd_md_step_end.  Per step:
+//     if (sclmd_md_force_needed(h)) sclmd_md_set_force(h, f(q_t));         // first step, after set_state, or with constraints
+//     sclmd_md_step_begin(h, q_trial);  sclmd_md_step_end(h, f(q_trial));
+int sclmd_md_set_external_force(sclmd_md *h, int on) {
+    SCLMD_REQUIRE(h, "sclmd_md_set_external_force: NULL handle");
+    SCLMD_REQUIRE(!h->ext_open, "sclmd_md_set_external_force: a step is open (sclmd_md_step_end missing)");
+    h->drop_graphs();
+    h->ext_force = on != 0;
+    h->g_valid = false;
+    h->d_valid = false;
+    return SCLMD_OK;
+}
+
+int sclmd_md_force_needed(sclmd_md *h) {
+    SCLMD_REQUIRE(h, "sclmd_md_force_needed: NULL handle");
+    return (h->ext_force && !h->g_valid) ? 1 : 0;
+}
+
+int sclmd_md_set_force(sclmd_md *h, const double *f) {
+    SCLMD_REQUIRE(h && f, "sclmd_md_set_force: NULL argument");
+    SCLMD_REQUIRE(h->ext_force, "sclmd_md_set_force: the handle is not in external-force mode");
+    SCLMD_REQUIRE(!h->ext_open, "sclmd_md_set_force: a step is open (sclmd_md_step_end missing)");
+    SCLMD_CUDA(cudaSetDevice(h->device));
+    if (int e = h->upload_force(h->G.p, f)) return e;
+    SCLMD_CUDA(cudaStreamSynchronize(h->st));     // `f` may be reused by the caller
+    h->g_valid = true;
+    h->d_valid = false;
+    return SCLMD_OK;
+}
+
+int sclmd_md_step_begin(sclmd_md *h, double *q_trial) {
+    SCLMD_REQUIRE(h && q_trial, "sclmd_md_step_begin: NULL argument");
+    SCLMD_REQUIRE(h->ext_force, "sclmd_md_step_begin: the handle is not in external-force mode");
+    SCLMD_REQUIRE(!h->ext_open, "sclmd_md_step_begin: the previous step is still open (sclmd_md_step_end missing)");
+    if (!h->g_valid) {
+        set_error("sclmd_md_step_begin: the force at the current positions is missing (sclmd_md_set_force)");
+        return SCLMD_ERR_STATE;
+    }
+    SCLMD_CUDA(cudaSetDevice(h->device));
+    return h->ext_begin(q_trial);
+}
+
+int sclmd_md_step_end(sclmd_md *h, const double *f_trial) {
+    SCLMD_REQUIRE(h && f_trial, "sclmd_md_step_end: NULL argument");
+    SCLMD_REQUIRE(h->ext_force && h->ext_open, "sclmd_md_step_end: no open step (sclmd_md_step_begin first)");
+    SCLMD_CUDA(cudaSetDevice(h->device));
+    if (int e = h->ext_end(f_trial)) return e;
+    SCLMD_CUDA(cudaStreamSynchronize(h->st));     // `f_trial` may be reused by the caller
+    return SCLMD_OK;
+}
+
+// md.f, md.fbaths and md.fhis (md.py:390-398, 403, 411): on = 1 makes every step also store the total force of evaluation C
+// (md.f), each bath's force of evaluation C (md.fbaths after vv) and of evaluation A (the one the heat current is built from,
+// md.fhis); read them with the two getters after a step.
+int sclmd_md_set_force_output(sclmd_md *h, int on) {
+    SCLMD_REQUIRE(h, "sclmd_md_set_force_output: NULL handle");
+    SCLMD_CUDA(cudaSetDevice(h->device));
+    h->drop_graphs();
+    if (on) {
+        if (!h->fC.p) SCLMD_CUDA(h->fC.alloc((size_t)h->ntraj * h->ld));
+        for (auto &b : h->baths)
+            if (!b->fa.p) {
+                SCLMD_CUDA(b->fa.alloc((size_t)h->ntraj * b->ncp));
+                SCLMD_CUDA(b->fc.alloc((size_t)h->ntraj * b->ncp));
+            }
+    }
+    h->want_f = on != 0;
+    h->f_step = -1;
+    return SCLMD_OK;
+}
+
+int sclmd_md_get_force(sclmd_md *h, double *f) {
+    SCLMD_REQUIRE(h && f, "sclmd_md_get_force: NULL argument");
+    SCLMD_REQUIRE(h->want_f && h->f_step == h->t, "sclmd_md_get_force: no step since sclmd_md_set_force_output(h, 1) / set_state");
+    SCLMD_CUDA(cudaSetDevice(h->device));
+    const size_t w = h->nph * sizeof(double);
+    SCLMD_CUDA(cudaMemcpy2DAsync(f, w, h->fC.p, h->ld * sizeof(double), w, h->ntraj, cudaMemcpyDeviceToHost, h->st));
+    SCLMD_CUDA(cudaStreamSynchronize(h->st));
+    return SCLMD_OK;
+}
+
+int sclmd_md_get_bath_force(sclmd_md *h, int bath, int evaluation, double *fb) {
+    if (int e = check_bath(h, bath, "sclmd_md_get_bath_force")) return e;
+    SCLMD_REQUIRE(fb && (evaluation == 0 || evaluation == 2), "sclmd_md_get_bath_force: NULL buffer or evaluation not 0 (A) / 2 (C)");
+    SCLMD_REQUIRE(h->want_f && h->f_step == h->t && h->baths[bath]->fa.p,
+                  "sclmd_md_get_bath_force: no step since sclmd_md_set_force_output(h, 1) / set_state");
+    SCLMD_CUDA(cudaSetDevice(h->device));
+    Bath &b = *h->baths[bath];
+    const size_t w = b.nc * sizeof(double);
+    SCLMD_CUDA(cudaMemcpy2DAsync(fb, w, evaluation == 0 ? b.fa.p : b.fc.p, b.ncp * sizeof(double), w, h->ntraj, cudaMemcpyDeviceToHost, h->st));
+    SCLMD_CUDA(cudaStreamSynchronize(h->st));
     return SCLMD_OK;
 }
 

@@ -95,7 +95,7 @@ __device__ void inv_shift(cplx *Ainv, const cplx *S, cplx z, int m, cplx *aug, d
 }
 
 struct SigArgs {
-    int m, nw, mode;             // mode 0: self-energy of one lead; 1: transmission
+    int m, nw, mode;             // mode 0: self-energy of one lead; 1: transmission; 2: device Green function; 3: surface Green function of one lead
     const double *K00, *K11, *K01, *K10;
     double eta;
     int dirR;                    // mode 0: 1 = 'R', 0 = 'L'
@@ -162,8 +162,17 @@ __global__ void __launch_bounds__(ST) k_sig(const SigArgs a) {
         __syncthreads();
         const double w = a.omegas[iw];
         const cplx z = {w * w - a.eta * a.eta, 2.0 * w * a.eta};
-        if (a.mode == 0) {
+        if (a.mode == 0 || a.mode == 3) {
             const int it = sgf(a, a.dirR, z, s, e, al, g, t1, t2, t3, aug, red, &ired, &bad, &notconv);
+            if (a.mode == 3) {            // sig.sgf: the surface Green function itself
+                for (int i = threadIdx.x; i < mm2; i += blockDim.x) {
+                    a.se_out[((size_t)iw * mm2 + i) * 2] = g[i].x;
+                    a.se_out[((size_t)iw * mm2 + i) * 2 + 1] = g[i].y;
+                }
+                if (threadIdx.x == 0) { a.iters[iw] = it; a.status[iw] = notconv ? 1 : (bad ? 2 : 0); }
+                __syncthreads();
+                continue;
+            }
             // Sigma_R = K01 g K10 ; Sigma_L = K10 g K01 (selfenergy.py:133-140)
             const double *A = a.dirR ? a.K01 : a.K10, *B = a.dirR ? a.K10 : a.K01;
             for (int i = threadIdx.x; i < mm2; i += blockDim.x) { t1[i] = {A[i], 0.0}; t2[i] = {B[i], 0.0}; }
@@ -257,7 +266,7 @@ int run_sig(int device, int m, const double *K00, const double *K11, const doubl
     SCLMD_CUDA(cudaMemcpy(it.data(), dit.p, (size_t)2 * nw * sizeof(int), cudaMemcpyDeviceToHost));
     if (mode != 1) {
         SCLMD_CUDA(cudaMemcpy(se_out, dse.p, (size_t)nw * mm2 * 2 * 8, cudaMemcpyDeviceToHost));
-        if (iters_out && mode == 0) memcpy(iters_out, it.data(), nw * sizeof(int));
+        if (iters_out && (mode == 0 || mode == 3)) memcpy(iters_out, it.data(), nw * sizeof(int));
     } else {
         SCLMD_CUDA(cudaMemcpy(tm_out, dtm.p, nw * 8, cudaMemcpyDeviceToHost));
     }
@@ -283,6 +292,14 @@ int sclmd_sig_selfenergy(int device, int m, const double *K00, const double *K11
     SCLMD_REQUIRE(direction == 'R' || direction == 'L', "Wrong direction, should only be R or L");
     SCLMD_REQUIRE(se_out, "sclmd_sig_selfenergy: NULL output");
     return run_sig(device, m, K00, K11, K01, K10, eta, 0, direction == 'R', omegas, nw, se_out, nullptr, iters_out);
+}
+
+// sig.sgf (selfenergy.py:105-131): surface Green function inv((w + i eta)^2 - s) after the decimation, sgf_out[nw][m][m] complex
+int sclmd_sig_sgf(int device, int m, const double *K00, const double *K11, const double *K01, const double *K10, double eta,
+                  char direction, const double *omegas, int nw, double *sgf_out, int32_t *iters_out) {
+    SCLMD_REQUIRE(direction == 'R' || direction == 'L', "Wrong direction, should only be R or L");
+    SCLMD_REQUIRE(sgf_out, "sclmd_sig_sgf: NULL output");
+    return run_sig(device, m, K00, K11, K01, K10, eta, 3, direction == 'R', omegas, nw, sgf_out, nullptr, iters_out);
 }
 
 // sig.retargf (selfenergy.py:145-147): G(w) = inv((w + 1e-8 i)^2 - K00 - Sigma_L - Sigma_R), green_out[nw][m][m] complex (interleaved)

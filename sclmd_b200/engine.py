@@ -151,6 +151,41 @@ class MDEngine:
         """enqueue nsteps without waiting; any getter synchronises"""
         check(_lib.lib().sclmd_md_run(self._h, int(nsteps), None))
 
+    # ---- md.f / md.fbaths of the last step
+    def set_force_output(self, on=True):
+        check(_lib.lib().sclmd_md_set_force_output(self._h, 1 if on else 0))
+
+    def last_force(self):
+        out = np.empty((self.ntraj, self.nph))
+        check(_lib.lib().sclmd_md_get_force(self._h, dptr(out)))
+        return out
+
+    def last_bath_force(self, bath, evaluation=0):
+        """bath force of the last step at evaluation A (0) or C (2): [ntraj, nc]"""
+        out = np.empty((self.ntraj, self._baths[bath][0]))
+        check(_lib.lib().sclmd_md_get_bath_force(self._h, bath, evaluation, dptr(out)))
+        return out
+
+    # ---- force drivers (md.AddPotential): potential force from a host callback, everything else on the device
+    def set_external_force(self, on=True):
+        check(_lib.lib().sclmd_md_set_external_force(self._h, 1 if on else 0))
+
+    def step_with_driver(self, force, q_now=None):
+        """one step; `force(q[ntraj, nph]) -> f[ntraj, nph]` is the driver.  q_now: current positions (fetched if the force
+        at them is needed and they are not given)"""
+        L = _lib.lib()
+        need = L.sclmd_md_force_needed(self._h)
+        check(min(need, 0))
+        if need:
+            if q_now is None:
+                q_now = self.get_state()[0]
+            f0 = as_f64(force(np.asarray(q_now, dtype=float).reshape(self.ntraj, self.nph)), (self.ntraj, self.nph))
+            check(L.sclmd_md_set_force(self._h, dptr(f0)))
+        qt = np.empty((self.ntraj, self.nph))
+        check(L.sclmd_md_step_begin(self._h, dptr(qt)))
+        f1 = as_f64(force(qt), (self.ntraj, self.nph))
+        check(L.sclmd_md_step_end(self._h, dptr(f1)))
+
     def current(self, bath):
         out = np.empty((self.ntraj, self.nmd))
         check(_lib.lib().sclmd_md_get_current(self._h, bath, dptr(out)))

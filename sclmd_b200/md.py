@@ -226,14 +226,11 @@ class md:
 
     # ------------------------------------------------------------ device plumbing
     def _signature(self):
-        return (self.nph, self.ntraj, self.dt, self.nmd, len(self.baths), id(self.dyn),
+        return (self.nph, self.ntraj, self.dt, self.nmd, len(self.baths), id(self.dyn), id(self.pforce),
                 tuple(id(b.kernel) for b in self.baths), id(self.constraint))
 
     def _ensure_engine(self):
-        if self.pforce is not None:
-            raise NotImplementedError("force drivers other than the harmonic dynamical matrix (md.AddPotential) are outside "
-                                      "the device hot path of this build (SURVEY.md section 8b)")
-        if self.dyn is None:
+        if self.pforce is None and self.dyn is None:
             print("no driver, no md")
             sys.exit()
         sig = self._signature()
@@ -242,7 +239,12 @@ class md:
         if self._eng is not None:
             self._eng.close()
         eng = MDEngine(self.nph, self.ntraj, self.dt, self.nmd, self.device)
-        eng.set_dyn(self.dyn)
+        if self.pforce is not None:
+            # md.py:457-459: a force driver takes precedence over the dynamical matrix.  Its force is a host callback, one call per
+            # step (two with constraints); bath forces, history tails, integrator and observables stay on the device.
+            eng.set_external_force(True)
+        else:
+            eng.set_dyn(self.dyn)
         if self.constraint is not None:
             eng.set_constraint(np.concatenate([np.asarray(list(c), dtype=np.int32) for c in self.constraint]))
         for b in self.baths:
@@ -254,6 +256,7 @@ class md:
         self._eng, self._eng_sig = eng, sig
         self._noise_seen = {}
         self._state_dirty = True
+        self._force_out = False
 
     def _push(self):
         """host attributes -> device (state if it was reassigned, injected noise if it changed)"""
@@ -312,8 +315,29 @@ class md:
         return out[0] if self.ntraj == 1 else out
 
     # ------------------------------------------------------------ time stepping
+    def _driver_force(self, q):
+        """the force driver on every trajectory: driver.force(q[nph]) -> f[nph] (lammpsdriver.py:83-84)"""
+        q = np.asarray(q, dtype=float).reshape(self.ntraj, self.nph)
+        return np.stack([np.asarray(self.pforce.force(q[k]), dtype=float) for k in range(self.ntraj)])
+
+    def _set_force_output(self, on):
+        if self._force_out != on:
+            self._eng.set_force_output(on)
+            self._force_out = on
+
+    def _advance(self, n):
+        if self.pforce is None:
+            return self._eng.run(n)
+        import time as _time
+        t0 = _time.perf_counter()
+        for _ in range(n):
+            self._eng.step_with_driver(self._driver_force)
+        return (_time.perf_counter() - t0) * 1e3
+
     def vv(self, id=0):
-        """one velocity-Verlet step of every trajectory (md.py:367-411), on the device"""
+        """one velocity-Verlet step of every trajectory (md.py:367-411), on the device; also fills md.f (force of the last
+        evaluation, md.py:411), md.fbaths (bath forces of that evaluation) and, with SaveAll, md.fhis (bath forces of evaluation A, the
+        ones the heat current is built from, md.py:397-398)"""
         self._ensure_engine()
         self._push()
         t = int(self.t)
@@ -321,17 +345,44 @@ class md:
             self.ps[t % self.nmd] = np.asarray(self.p).reshape(self.ntraj, self.nph)[0]
         if self.saveq:
             self.qs[t % self.nmd] = np.asarray(self.q).reshape(self.ntraj, self.nph)[0]
-        self._eng.run(1)
+        if self.cf:                                       # md.py:378-379
+            q0 = np.asarray(self.q, dtype=float).reshape(self.ntraj, self.nph)[0]
+            self.cflist.append(np.asarray(self.forcedriver.force(q0)) - self.potforce_harmonic(q0))
+        self._set_force_output(True)
+        self._advance(1)
         self._pull()
         self._collect()
+        f = self._eng.last_force()
+        self.f = f[0] if self.ntraj == 1 else f
+        for i, b in enumerate(self.baths):
+            fb = np.zeros((self.ntraj, self.nph))
+            fb[:, b.cids] = self._eng.last_bath_force(i, 2)   # md.fbaths is overwritten by every evaluation: C is what remains
+            self.fbaths[i] = fb[0] if self.ntraj == 1 else fb
+            if self.saveall:                              # md.py:398 keeps them always; here only when they are dumped
+                while len(self.fhis) <= i:
+                    self.fhis.append(np.zeros((self.nmd, self.nph)))
+                self.fhis[i][t % self.nmd, b.cids] = self._eng.last_bath_force(i, 0)[0]
 
     def steps(self, n):
         """n steps without host round trips in between (the bulk path used by Run)"""
         self._ensure_engine()
         self._push()
-        ms = self._eng.run(n)
+        self._set_force_output(False)
+        ms = self._advance(n)
         self._pull()
         return ms
+
+    def CompareForce(self, forcedriver):
+        """md.py:362-365: every vv() records forcedriver.force(q) + dyn.q; Run() saves deltaforce.run<j>.npy"""
+        self.cf = 1
+        self.forcedriver = forcedriver
+        self.cflist = []
+
+    def potforce_harmonic(self, q):
+        """-dyn . q on the device, whatever driver is attached"""
+        q = np.asarray(q, dtype=float)
+        f = -_lib.dgemm_nt(q.reshape(-1, self.nph), np.asarray(self.dyn, dtype=float), 1.0, self.device)
+        return f[0] if q.ndim == 1 else f
 
     def force(self, t, p, q, id=0):
         """md.py:413-435 as a stand-alone evaluation for one trajectory (vv()/Run() never call it: the three force evaluations of a
@@ -357,13 +408,13 @@ class md:
         if self.dyn is None:
             print("no driver, no md")
             sys.exit()
-        q = np.asarray(q, dtype=float)
-        f = -_lib.dgemm_nt(q.reshape(-1, self.nph), np.asarray(self.dyn, dtype=float), 1.0, self.device)
-        return f[0] if q.ndim == 1 else f
+        return self.potforce_harmonic(q)
 
     def AddPotential(self, pint):
-        """md.py:481-485 -- accepted for API parity; external force drivers are out of scope (raises at run time)"""
+        """md.py:481-485: a force driver (`.force(q) -> f[nph]`, mass-weighted; lammpsdriver.py:83-84).  The driver runs on the
+        host, once per step; everything else of the step stays on the device (sclmd_md_step_begin / sclmd_md_step_end)."""
         self.pforce = pint
+        self._eng_sig = None
 
     def Run(self):
         """md.py:493-682: nstop-nstart runs of nmd steps in npie pieces; noise regenerated per run;
@@ -397,7 +448,7 @@ class md:
                 self.ResetSavepq()
             per = int(self.nmd / self.npie)
             trajfile = open('trajectories' + "." + str(self.T) + "." + "run" + str(j) + '.ani', 'w')
-            slow = self.savep or self.saveq or self.nstep is not None
+            slow = self.savep or self.saveq or self.cf or self.saveall or self.nstep is not None
             for i in range(ipie + 1, self.npie):
                 if slow:
                     for _ in range(per):
@@ -409,6 +460,9 @@ class md:
                 self._collect()
                 self.dump(i, j)
             trajfile.close()
+            if self.cf:                                   # md.py:599-602
+                np.save("deltaforce" + ".run" + str(j), np.array(self.cflist) / self.forcedriver.conv)
+                self.cflist = []
             if self.savep:
                 power = np.copy(self.power)
                 self.GetPower()
@@ -444,11 +498,12 @@ class md:
 
     def _write_frame(self, trajfile):
         q = np.asarray(self.q).reshape(self.ntraj, self.nph)[0]
+        fr = np.asarray(self.f).reshape(self.ntraj, self.nph)[0]        # md.py:594-595: element, position, force
         trajfile.write(str(len(self.els)) + '\n' + str(self.t - 1) + '\n')
         structure = self.xyz + self.conv * q
         for ip in range(len(self.els)):
             trajfile.write(str(self.els[ip]) + '    ' + str(structure[ip * 3]) + '   ' + str(structure[ip * 3 + 1]) + '   ' +
-                           str(structure[ip * 3 + 2]) + '\n')
+                           str(structure[ip * 3 + 2]) + '   ' + str(fr[ip * 3]) + '   ' + str(fr[ip * 3 + 1]) + '   ' + str(fr[ip * 3 + 2]) + '\n')
 
     def GetPower(self):
         """md.py:351-360 (post-processing; 'next' row of the scope table)"""
@@ -492,6 +547,8 @@ class md:
             put('ring' + str(i), self._eng.get_history(i), ('ntraj', 'm' + str(i), 'n' + str(i)))
             if self.saveall and self.ntraj == 1 and b._noise is not None:
                 put('noise' + str(i), np.asarray(b._noise).reshape(self.nmd, b.nc), ('nmd', 'n' + str(i)))
+            if self.saveall and i < len(self.fhis):       # md.py:713-714
+                put('fhis' + str(i), self.fhis[i], ('nmd', 'nph'))
         if self.savep:
             f.createDimension('npw', len(self.power))
             put('power', self.power, ('npw', 'two'))

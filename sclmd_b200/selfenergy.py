@@ -64,6 +64,25 @@ class sig:
         self.iterations = iters
         return out
 
+    def sgf_sweep(self, omegas, direction):
+        """surface Green function of one lead for every frequency (selfenergy.py:105-131 per frequency)"""
+        if direction not in ('R', 'L'):
+            raise ValueError('Wrong direction, should only be R or L')
+        om = as_f64(np.atleast_1d(omegas))
+        m = len(self.K00)
+        k00, k11, k01, k10 = self._k()
+        out = np.empty((len(om), m, m), dtype=np.complex128)
+        iters = np.zeros(len(om), dtype=np.int32)
+        check(_lib.lib().sclmd_sig_sgf(self.device, m, dptr(k00), dptr(k11), dptr(k01), dptr(k10), float(self.eta),
+                                       direction.encode(), dptr(om), len(om), out.ctypes.data_as(_lib.c_double_p),
+                                       iters.ctypes.data_as(_lib.c_int32_p)))
+        self.iterations = iters
+        return out
+
+    def sgf(self, omega, direction):
+        """selfenergy.py:105-131"""
+        return self.sgf_sweep([omega], direction)[0]
+
     def selfenergy(self, omega, direction):
         """selfenergy.py:133-140"""
         return self.selfenergy_sweep(np.array([omega], dtype=float), direction)[0]

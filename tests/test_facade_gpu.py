@@ -83,6 +83,86 @@ def test_reference_script_flow_reproduces_golden(name, golden_dir):
     assert relerr(m.etot, g["etot"]) < 1e-10
 
 
+class HarmonicDriver:
+    """a force driver in the reference's protocol (lammpsdriver.py:83-84): force(q) -> mass-weighted f[nph], relative to q = 0"""
+    conv = 1.0
+
+    def __init__(self, K):
+        self.K = np.array(K)
+        self.calls = 0
+
+    def force(self, q):
+        self.calls += 1
+        return -self.K @ np.asarray(q)
+
+
+@pytest.mark.parametrize("name", ["ph_full", "e_extra", "c1_shape"])
+def test_force_driver_reproduces_golden(name, golden_dir):
+    """md.AddPotential (md.py:457-459, 481-485): with a host force driver that returns -K.q the device step (bath forces, history
+    tails, integrator, constraint, observables on the device; the driver called once per step, twice with constraints) reproduces
+    the reference's golden trajectories of the harmonic runs"""
+    c = P.MD_CASES[name]()
+    g = np.load(os.path.join(golden_dir, "md_%s.npz" % name))
+    m, baths = build(c)
+    drv = HarmonicDriver(m.dyn)
+    m.AddPotential(drv)
+    m.initialise()
+    if c["q0"] is None:
+        m.q, m.p = g["q0"].copy(), g["p0"].copy()
+    else:
+        m.q, m.p = c["q0"].copy(), c["p0"].copy()
+    m.ResetHis()
+    n = int(g["nsteps"])
+    full = g["q"].shape[0] == n
+    half = n // 2
+    for s in range(half):                              # step by step ...
+        m.vv(0)
+        if full:
+            assert relerr(m.q, g["q"][s]) < 1e-10 and relerr(m.p, g["p"][s]) < 1e-10, (name, s)
+    m.steps(n - half)                                  # ... and in bulk
+    m._collect()
+    assert m.t == n
+    assert relerr(m.q, g["q"][-1]) < 1e-10 and relerr(m.p, g["p"][-1]) < 1e-10
+    for b, bb in enumerate(baths):
+        assert relerr(bb.cur, g["cur"][b]) < 1e-8
+    assert relerr(m.etot, g["etot"]) < 1e-10
+    assert drv.calls == (2 * n if c["cons"] is not None else n + 1)
+    # the engine refuses the K.q path while a driver is attached, and a half-open step
+    from sclmd_b200._lib import SclmdError
+    with pytest.raises(SclmdError):
+        m._eng.run(1)
+
+
+def test_compare_force_records_driver_minus_harmonic(tmp_path, monkeypatch):
+    """md.CompareForce (md.py:362-365, 378-379, 599-602): every step records forcedriver.force(q) + dyn.q; Run() saves them"""
+    monkeypatch.chdir(tmp_path)
+    c = P.md_case_ph_local()
+    m, baths = build(c)
+    for b in baths:
+        b.gnoi = lambda: None                          # keep the injected noise (Run() regenerates it otherwise)
+    K2 = 1.01 * np.array(m.dyn)
+    drv = HarmonicDriver(K2)
+    drv.conv = 2.0
+    m.CompareForce(drv)
+    m.noranvel()
+    m.nstop = 1
+    m.Run()
+    d = np.load("deltaforce.run0.npy")
+    assert d.shape == (c["nmd"], m.nph)
+    assert drv.calls == c["nmd"]
+    # q_0 = 0, so the first record is zero; later ones are -(K2 - K).q_t / conv
+    assert np.all(d[0] == 0.0) and np.abs(d).max() > 0
+    q_last = None
+    m2, baths2 = build(c)
+    m2.noranvel()
+    m2.initialise()
+    m2.ResetHis()
+    for _ in range(c["nmd"] - 1):
+        m2.vv(0)
+    q_last = np.array(m2.q)
+    assert relerr(d[-1], -(K2 - np.array(m.dyn)) @ q_last / 2.0) < 1e-9
+
+
 def test_run_writes_kappa_files_and_posts(tmp_path, monkeypatch):
     """md.Run() on an ensemble: device noise generation, kappa.* per trajectory, calHF/calTC"""
     from sclmd_b200.md import md
@@ -204,9 +284,18 @@ def test_standalone_force_calls_match_the_oracle():
                      baths[b].zeta1, baths[b].zeta2) for b in range(2)]
     lit = O.LiteralMD(K, c["dt"], c["nmd"], obaths, c["cons"])
     lit.q, lit.p = c["q0"].copy(), c["p0"].copy()
+    m.SaveAll()
     for _ in range(5):
+        p_before = np.array(m.p)
         m.vv(0)
         lit.vv()
+        # md.f = force of evaluation C (md.py:403,411); md.fbaths = bath forces of that evaluation; md.fhis = bath forces of
+        # evaluation A, the ones the heat current is built from (md.py:397-398)
+        assert relerr(m.f, lit.f) < 1e-10
+        for b in range(2):
+            assert relerr(m.fbaths[b], lit.fbaths[b]) < 1e-10
+            cur_t = float(np.dot(m.fhis[b][(m.t - 1) % c["nmd"]], p_before))
+            assert abs(cur_t - baths[b].cur[(m.t - 1) % c["nmd"]]) <= 1e-10 * max(1.0, abs(cur_t))
     q, p = np.array(m.q), np.array(m.p)
     want = lit.force(lit.t, p, q, 1)
     got = m.force(m.t, p, q, 1)

@@ -130,6 +130,13 @@ def test_sig_24x24_vs_oracle():
     wtm = np.array([O.sig_tm(K00, K11, s.K01, s.K10, w, s.eta) for w in om])
     assert np.max(np.abs(tm - wtm)) < 1e-8 * max(1.0, np.abs(wtm).max())
     assert np.array_equal(s.iterations, np.array([O.sig_sgf(K00, K11, s.K01, s.K10, w, s.eta, 'R')[1] for w in om]))
+    # sig.sgf (selfenergy.py:105-131): the surface Green function itself, both leads
+    for d in ('L', 'R'):
+        gs = s.sgf(float(om[3]), d)
+        wg, wit = O.sig_sgf(K00, K11, s.K01, s.K10, float(om[3]), s.eta, d)
+        assert relerr(gs, wg) < 1e-9 and int(s.iterations[0]) == wit
+    with pytest.raises(ValueError):
+        s.sgf(float(om[3]), 'X')
     # sig.retargf (selfenergy.py:145-147) from the device and the reference's own tm formula built on it (selfenergy.py:149-151)
     w = float(om[2])
     sl, sr = s.selfenergy(w, 'L'), s.selfenergy(w, 'R')
