@@ -345,8 +345,44 @@ def run_c4_noise_case():
                         e_au=np.array([u for _, u in captured]), used=used)
 
 
+def run_myio_cases():
+    """the reference's remaining NetCDF readers (myio.py:192-366) on seeded files.  netCDF4 is not installed, so the reference's
+    `Dataset` is replaced by a reader of the NetCDF-classic files written here (I/O only; the arithmetic is the reference's)."""
+    import tempfile
+    from scipy.io import netcdf_file
+    import sclmd.myio as rio
+
+    class Dataset:
+        def __init__(self, filename, mode='r'):
+            with netcdf_file(filename, 'r', mmap=False) as f:
+                self.variables = {k: np.array(v[:], dtype=float if v.typecode() in 'fd' else None) for k, v in f.variables.items()}
+
+        def close(self):
+            pass
+
+    rio.Dataset = Dataset
+    inp = P.myio_inputs()
+    out = {}
+    with tempfile.TemporaryDirectory() as td, refshim.quiet():
+        for kind in ("lam", "wb", "ph", "sg"):
+            P.write_classic_nc(os.path.join(td, kind + ".nc"), inp[kind])
+        for w0 in (0.0, 0.07, 0.5):
+            r = rio.ReadLambda(os.path.join(td, "lam.nc"), w0)
+            out["lam_%g" % w0] = np.array([np.full((6, 6), r[0])] + [np.array(x) for x in r[1:]])
+        r = rio.ReadwbLambda(os.path.join(td, "wb.nc"))
+        out["wb"] = np.array([np.full((6, 6), r[0])] + [np.array(x) for x in r[1:]])
+        for tag, order in (("plain", None), ("reordered", [2, 1])):
+            dyn, U, hw = rio.ReadDynmat(os.path.join(td, "ph.nc"), order)
+            out["dyn_" + tag], out["U_" + tag], out["hw_" + tag] = dyn, U, hw
+        e = rio.ReadSig(os.path.join(td, "sg.nc"))
+        out["sig_wl"], out["sigL"], out["sigR"] = e.wl, e.SigL, e.SigR
+        out["ord2idx"] = rio.ord2idx([3, 1, 2])
+    np.savez_compressed(os.path.join(GOLD, "myio_readers.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
+    run_myio_cases()
     extract_c4_lambda()
     for name, fn in (("ph_full", md_case_ph_full), ("ph_local", md_case_ph_local), ("e_extra", md_case_e_extra),
                      ("c1_shape", md_case_c1_shape), ("c4_shape", P.md_case_c4_shape)):

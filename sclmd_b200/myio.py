@@ -206,6 +206,87 @@ def ReadNetCDFVar(file, var):
     return read_nc_variables(file)[var]
 
 
+def Write2NetCDFFile(file, var, varLabel, dimensions, units=None, description=None):
+    """sclmd/myio.py:174-181 on an open scipy.io.netcdf_file (or netCDF4.Dataset): one float64 variable"""
+    tmp = file.createVariable(varLabel, 'd', dimensions)
+    tmp[:] = np.asarray(var, dtype=float)
+    if units:
+        tmp.units = units
+    if description:
+        tmp.description = description
+
+
+def ReadMDNCFile(filename):
+    """sclmd/myio.py:192-211: cell, coordinates and atom lists of an MD set-up file"""
+    v = read_nc_variables(filename)
+
+    class mdmath:
+        pass
+
+    mdmath.filename = filename
+    mdmath.cell, mdmath.xyz = v['UnitCell'], v['XYZ']
+    mdmath.dynatom, mdmath.atomlist = v['DynamicAtoms'], v['AtomList']
+    return mdmath
+
+
+def ord2idx(order):
+    """sclmd/myio.py:291-297: dof permutation of a 1-based atom order"""
+    order = np.asarray(order, dtype=int)
+    return (3 * (order[:, None] - 1) + np.arange(3)[None, :]).reshape(-1)
+
+
+def ReadDynmat(filename, order=None):
+    """sclmd/myio.py:214-250: dynamical matrix in real space from the phonon file of Inelastica's PHrun (hw, U, DynamicAtoms):
+    dyn = U^T diag(hw^2) U restricted to the dynamic atoms, symmetrised; `order` = new 1-based atom order"""
+    v = read_nc_variables(filename)
+    hw, fullU, dynatoms = v['hw'], v['U'], v['DynamicAtoms']
+    first, last = int(dynatoms[0]) - 1, int(dynatoms[-1])
+    U = np.array([np.asarray(row)[first:last].reshape(-1) for row in fullU], dtype=float)
+    if order is not None:
+        if 3 * len(order) != len(hw):
+            raise ValueError("ReadDynmat: length of order error!")
+        U = U[:, ord2idx(order)]
+    dyn = (U.T * hw ** 2) @ U
+    return 0.5 * (dyn + dyn.T), U, hw
+
+
+def ReadSig(filename):
+    """sclmd/myio.py:300-316: frequency grid and the two lead self-energies"""
+    v = read_nc_variables(filename)
+
+    class eph:
+        pass
+
+    eph.wl = v['Wlist']
+    eph.SigL = v['ReSigL'] + 1j * v['ImSigL']
+    eph.SigR = v['ReSigR'] + 1j * v['ImSigR']
+    return eph
+
+
+def ReadwbLambda(filename, order=None):
+    """sclmd/myio.py:319-336: wide-band electron-phonon matrices (bias is zero by construction)"""
+    v = read_nc_variables(filename)
+    return 0.0, v['eta'], v['xim'], v['xip'], v['zeta1'], v['zeta2']
+
+
+def ReadLambda(filename, w0, order=None):
+    """sclmd/myio.py:339-366: friction / non-conservative / renormalisation / Berry matrices at the grid energy nearest to w0,
+    from the energy-resolved Pi and Lambda of a biased junction"""
+    from .functions import nearest
+    v = read_nc_variables(filename)
+    wl, mus = v['wl'], v['muLR']
+    bias = mus[0] - mus[1]
+    k = nearest(w0, wl)
+    w00 = wl[k]
+    im, re, lam = v['ImPir2'][k], v['RePir2'][k], v['ReLamLR'][k]
+    eta = -(im + im.T) / 2 / w00
+    zeta2 = -(im - im.T) / 2 / w00 / bias
+    xim = -(re - re.T) / 2 / bias
+    zeta1 = (re + re.T) / 2 / bias
+    xip = -np.pi * (lam + lam.T) / 2 / w00
+    return bias, eta, xim, xip, zeta1, zeta2
+
+
 def WriteEPHNCfile(filename, wl, hw, U, DynMat, SigL, SigR, Friction, NC, NCP, zeta1, zeta2):
     """sclmd/myio.py:138-171 in NetCDF classic format (same dimension and variable names; netCDF4 reads it)"""
     from scipy.io import netcdf_file

@@ -199,3 +199,36 @@ def md_case_c4_shape():
 
 MD_CASES = dict(ph_full=md_case_ph_full, ph_local=md_case_ph_local, e_extra=md_case_e_extra, c1_shape=md_case_c1_shape,
                 c4_shape=md_case_c4_shape)
+
+
+def myio_inputs():
+    """seeded contents of the three file kinds the reference's remaining NetCDF readers take (myio.py:192-366): a biased Lambda
+    file (wl, muLR, ImPir2, RePir2, ReLamLR), a wide-band one (eta .. zeta2), a PHrun phonon file (hw, U, DynamicAtoms) and a
+    self-energy file (Wlist, Re/ImSigL/R)"""
+    rng = np.random.default_rng(77)
+    n, nw, natoms_all, first, last = 6, 7, 5, 2, 3          # dynamic atoms 2..3 (1-based) of 5 -> 6 dofs
+    lam = dict(wl=np.linspace(0.01, 0.19, nw), muLR=np.array([0.35, -0.25]), ImPir2=rng.standard_normal((nw, n, n)),
+               RePir2=rng.standard_normal((nw, n, n)), ReLamLR=rng.standard_normal((nw, n, n)))
+    wb = dict(eta=psd(n, 71, 0.1), xim=antisym(n, 72, 0.1), xip=sym(n, 73, 0.1), zeta1=sym(n, 74, 0.1), zeta2=antisym(n, 75, 0.1))
+    ph = dict(hw=0.01 + 0.2 * rng.random(n), U=rng.standard_normal((n, natoms_all, 3)), DynamicAtoms=np.arange(first, last + 1, dtype=np.int32))
+    sg = dict(Wlist=np.linspace(0, 0.2, nw), ReSigL=rng.standard_normal((nw, 3, 3)), ImSigL=rng.standard_normal((nw, 3, 3)),
+              ReSigR=rng.standard_normal((nw, 3, 3)), ImSigR=rng.standard_normal((nw, 3, 3)))
+    return dict(lam=lam, wb=wb, ph=ph, sg=sg)
+
+
+def write_classic_nc(filename, variables):
+    """every array as a float64 (or int32) variable of a NetCDF classic file, one dimension per axis"""
+    from scipy.io import netcdf_file
+    f = netcdf_file(filename, 'w')
+    for name, arr in variables.items():
+        arr = np.asarray(arr)
+        code = 'i' if arr.dtype.kind in 'iu' else 'd'
+        arr = arr.astype(np.int32 if code == 'i' else float)
+        dims = []
+        for ax, ln in enumerate(arr.shape):
+            d = "%s_d%d" % (name, ax)
+            f.createDimension(d, ln)
+            dims.append(d)
+        v = f.createVariable(name, code, tuple(dims))
+        v[:] = arr
+    f.close()

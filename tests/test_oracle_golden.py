@@ -220,3 +220,30 @@ def test_eph_file_round_trip(tmp_path):
     assert np.array_equal(e.wl, args["wl"]) and np.array_equal(e.DynMat, args["DynMat"]) and np.array_equal(e.SigL, args["SigL"])
     assert np.array_equal(e.efric, args["Friction"]) and np.array_equal(e.xim, args["NC"]) and np.array_equal(e.zeta2, args["zeta2"])
     assert np.array_equal(myio.ReadNetCDFVar(fn, "hw"), args["hw"])
+
+
+def test_myio_readers_match_the_reference(tmp_path, golden_dir):
+    """ReadLambda / ReadwbLambda / ReadDynmat / ReadSig / ord2idx (myio.py:214-366) against the reference's own outputs on the
+    same seeded files (oracle/make_golden.py:run_myio_cases)"""
+    from sclmd_b200 import myio
+    g = np.load(os.path.join(golden_dir, "myio_readers.npz"))
+    inp = P.myio_inputs()
+    for kind in ("lam", "wb", "ph", "sg"):
+        P.write_classic_nc(str(tmp_path / (kind + ".nc")), inp[kind])
+    for w0 in (0.0, 0.07, 0.5):
+        r = myio.ReadLambda(str(tmp_path / "lam.nc"), w0)
+        want = g["lam_%g" % w0]
+        assert r[0] == want[0][0, 0]
+        for k in range(5):
+            assert np.array_equal(r[1 + k], want[1 + k])
+    r = myio.ReadwbLambda(str(tmp_path / "wb.nc"))
+    assert r[0] == 0.0 and all(np.array_equal(r[1 + k], g["wb"][1 + k]) for k in range(5))
+    for tag, order in (("plain", None), ("reordered", [2, 1])):
+        dyn, U, hw = myio.ReadDynmat(str(tmp_path / "ph.nc"), order)
+        assert np.array_equal(U, g["U_" + tag]) and np.array_equal(hw, g["hw_" + tag])
+        assert np.max(np.abs(dyn - g["dyn_" + tag])) <= 1e-14 * np.max(np.abs(g["dyn_" + tag]))
+    e = myio.ReadSig(str(tmp_path / "sg.nc"))
+    assert np.array_equal(e.wl, g["sig_wl"]) and np.array_equal(e.SigL, g["sigL"]) and np.array_equal(e.SigR, g["sigR"])
+    assert np.array_equal(myio.ord2idx([3, 1, 2]), g["ord2idx"])
+    with pytest.raises(ValueError):
+        myio.ReadDynmat(str(tmp_path / "ph.nc"), [1, 2, 3])
