@@ -1,7 +1,8 @@
 // Surface self-energies by Sancho-Rubio decimation and the transmission built from them
 // (replaces sig.sgf / sig.selfenergy / sig.retargf / sig.tm / sig.getse / sig.gettm,
 // sclmd/selfenergy.py:105-178).  One CTA per frequency; every m x m complex matrix lives in
-// shared memory (m = 24 in examples/runsig.py -> 9 KB each).
+// shared memory (m = 24 in examples/runsig.py -> 9 KB each).  Lead blocks too large for that (m > 35) use the same
+// code on a per-CTA workspace in global memory (L2-resident for moderate m), up to m = 512.
 #include <algorithm>
 
 #include "common.cuh"
@@ -104,6 +105,8 @@ struct SigArgs {
     double *tm_out;              // [nw]
     int *iters;                  // [nw] (mode 0) or [nw][2]
     int *status;                 // [nw] 0 ok, 1 not converged, 2 singular
+    double *gws;                 // per-CTA matrix workspace in global memory when the matrices do not fit shared memory, else NULL
+    size_t gws_stride;           // doubles per CTA
 };
 
 // selfenergy.py:105-131: returns g = inv(z - s) in `g`; s,e,al,t1,t2,t3 are m x m work matrices
@@ -152,10 +155,10 @@ __device__ int sgf(const SigArgs &a, bool dirR, cplx z, cplx *s, cplx *e, cplx *
 __global__ void __launch_bounds__(ST) k_sig(const SigArgs a) {
     extern __shared__ double smraw[];
     const int m = a.m, mm2 = m * m;
-    cplx *s = reinterpret_cast<cplx *>(smraw), *e = s + mm2, *al = e + mm2, *g = al + mm2, *t1 = g + mm2, *t2 = t1 + mm2, *t3 = t2 + mm2;
+    cplx *s = reinterpret_cast<cplx *>(a.gws ? a.gws + (size_t)blockIdx.x * a.gws_stride : smraw), *e = s + mm2, *al = e + mm2, *g = al + mm2, *t1 = g + mm2, *t2 = t1 + mm2, *t3 = t2 + mm2;
     cplx *sl = t3 + mm2, *sr = sl + mm2;
     cplx *aug = sr + mm2;                        // m x 2m
-    double *red = reinterpret_cast<double *>(aug + 2 * mm2);   // >= max(64, 2m)
+    double *red = a.gws ? smraw : reinterpret_cast<double *>(aug + 2 * mm2);   // >= max(64, 2m), always in shared memory
     __shared__ int ired, bad, notconv;
     for (int iw = blockIdx.x; iw < a.nw; iw += gridDim.x) {
         if (threadIdx.x == 0) { bad = 0; notconv = 0; }
@@ -239,9 +242,14 @@ int run_sig(int device, int m, const double *K00, const double *K11, const doubl
             const double *omegas, int nw, double *se_out, double *tm_out, int32_t *iters_out) {
     SCLMD_REQUIRE(m > 0 && K00 && K11 && K01 && K10 && omegas && nw > 0, "sig: bad arguments");
     if (int e = select_device(device)) return e;
-    const size_t smem = ((size_t)11 * m * m * 2 + std::max(64, 2 * m) + 64) * sizeof(double);
-    SCLMD_REQUIRE(smem <= 220 * 1024, "sig: m=%d too large for the shared-memory decimation (max ~34)", m);
-    DevBuf<double> k00, k11, k01, k10, dom, dse, dtm;
+    const size_t mat_doubles = (size_t)11 * m * m * 2, red_doubles = std::max(64, 2 * m) + 64;
+    const bool in_smem = (mat_doubles + red_doubles) * sizeof(double) <= 220 * 1024;
+    SCLMD_REQUIRE(m <= 512, "sig: m=%d exceeds the supported lead block size (512)", m);
+    const size_t smem = ((in_smem ? mat_doubles : 0) + red_doubles) * sizeof(double);
+    int grid = std::min(nw, 8 * sm_count(device));
+    if (!in_smem) grid = std::min(nw, std::max(1, std::min(2 * sm_count(device), (int)(((size_t)2 << 30) / (mat_doubles * sizeof(double))))));
+    DevBuf<double> k00, k11, k01, k10, dom, dse, dtm, gws;
+    if (!in_smem) SCLMD_CUDA(gws.alloc(mat_doubles * grid));
     DevBuf<int> dit, dst;
     const size_t mm2 = (size_t)m * m;
     SCLMD_CUDA(k00.alloc(mm2)); SCLMD_CUDA(k11.alloc(mm2)); SCLMD_CUDA(k01.alloc(mm2)); SCLMD_CUDA(k10.alloc(mm2));
@@ -256,8 +264,8 @@ int run_sig(int device, int m, const double *K00, const double *K11, const doubl
     SigArgs a{};
     a.m = m; a.nw = nw; a.mode = mode; a.K00 = k00.p; a.K11 = k11.p; a.K01 = k01.p; a.K10 = k10.p; a.eta = eta; a.dirR = dirR;
     a.omegas = dom.p; a.se_out = dse.p; a.tm_out = dtm.p; a.iters = dit.p; a.status = dst.p;
-    SCLMD_CUDA(cudaFuncSetAttribute(k_sig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = std::min(nw, 8 * sm_count(device));
+    a.gws = gws.p; a.gws_stride = mat_doubles;
+    SCLMD_CUDA(cudaFuncSetAttribute(k_sig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)48 * 1024)));
     k_sig<<<grid, ST, smem>>>(a);
     SCLMD_CUDA(cudaGetLastError());
     SCLMD_CUDA(cudaDeviceSynchronize());

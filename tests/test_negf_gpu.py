@@ -146,6 +146,27 @@ def test_sig_24x24_vs_oracle():
     assert abs(t - tm[2]) < 1e-8 * max(1.0, abs(t))
 
 
+def test_sig_large_lead_block_uses_the_global_workspace():
+    """lead blocks whose eleven m x m complex work matrices exceed shared memory (m > 35) run the same decimation on a per-CTA
+    workspace in global memory: m = 60 against the oracle"""
+    from sclmd_b200.selfenergy import sig
+    m = 60
+    K00, K11, K01 = P.chain_blocks(m, seed=9, k2=0.08)
+    full = np.zeros((2 * m, 2 * m))
+    full[:m, :m], full[m:, m:], full[:m, m:], full[m:, :m] = K00, K11, K01, K01.T
+    s = sig(None, 0.06, range(0, m), range(m, 2 * m), dynmatfile=full, num=24, eta=1e-3)
+    om = s.ep[[0, 5, 13, 24]]
+    for d in ('L', 'R'):
+        se = s.selfenergy_sweep(om, d)
+        want = np.array([O.sig_selfenergy(K00, K11, s.K01, s.K10, w, s.eta, d) for w in om])
+        assert relerr(se, want) < 1e-9
+        assert np.array_equal(s.iterations, np.array([O.sig_sgf(K00, K11, s.K01, s.K10, w, s.eta, d)[1] for w in om]))
+    tm = s.tm_sweep(om)
+    wtm = np.array([O.sig_tm(K00, K11, s.K01, s.K10, w, s.eta) for w in om])
+    assert np.max(np.abs(tm - wtm)) < 1e-8 * max(1.0, np.abs(wtm).max())
+    assert relerr(s.sgf(float(om[2]), 'R'), O.sig_sgf(K00, K11, s.K01, s.K10, float(om[2]), s.eta, 'R')[0]) < 1e-9
+
+
 def test_bpt_config3_full_sweep_properties():
     """size-independent properties at the full config-3 shape (n = 483, a few thousand frequencies, several batches and streams):
     reciprocity T_LR(w) = T_RL(w) (the two sweeps factorise differently ordered matrices), 0 <= T <= number of channels,
