@@ -171,6 +171,67 @@ __global__ void __launch_bounds__(256, NBATH <= 2 ? 4 : 1) k_phase_bc(BathSet bs
     }
 }
 
+// Evaluations B and C of step t fused with evaluation A of step t+1 (no constraints, every bath force diagonal in x): the
+// three evaluations see the same K.q', noise row and history tail and differ only in the momentum they are taken at, so the
+// state never leaves registers between them.  Saves one launch and the re-read of p, q and the K-slices of K.q per step.
+template <int NBATH>
+__global__ void __launch_bounds__(256, NBATH <= 2 ? 4 : 1) k_phase_bca(BathSet bs, int nph, int ld, int ntraj, int nmd, long long t, double dt,
+                                                    double *__restrict__ phalf, const double *__restrict__ Gn, int gsplit, size_t gstride,
+                                                    double *__restrict__ pout, double *__restrict__ qn, double *__restrict__ qout,
+                                                    double *__restrict__ etot) {
+    __shared__ double red[32];
+    const int traj = blockIdx.x;
+    const size_t row = (size_t)traj * ld;
+    const int slab = (int)((t + 1) % nmd);
+    double ke = 0.0, cur[NBATH];
+#pragma unroll
+    for (int b = 0; b < NBATH; ++b) cur[b] = 0.0;
+    for (int i = threadIdx.x; i < nph; i += blockDim.x) {
+        const double ph = phalf[row + i];
+        double g = Gn[row + i];
+        for (int z = 1; z < gsplit; ++z) g += Gn[(size_t)z * gstride + row + i];
+        int a[NBATH];
+#pragma unroll
+        for (int b = 0; b < NBATH; ++b) a[b] = b < bs.nb ? bs.b[b].inv[i] : -1;
+        double xi = ph, pnew = 0.0;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {                  // evaluations B and C (md.py:401-404)
+            double f = -g;
+#pragma unroll
+            for (int b = 0; b < NBATH; ++b)
+                if (a[b] >= 0) f += bath_force(bs.b[b], traj, ntraj, a[b], slab, xi);
+            pnew = ph + dt * f / 2.0;
+            xi = pnew;
+        }
+        const double qv = qn[row + i];
+        qout[row + i] = qv;
+        pout[row + i] = pnew;
+        // evaluation A of step t+1 (md.py:383-398) at (p_{t+1}, q_{t+1}) = (pnew, qv); K.q_{t+1} = K.q' without constraints
+        double f = -g;
+#pragma unroll
+        for (int b = 0; b < NBATH; ++b) {
+            if (a[b] >= 0) {
+                const double fb = bath_force(bs.b[b], traj, ntraj, a[b], slab, pnew);
+                cur[b] += fb * pnew;
+                f += fb;
+                bs.b[b].ring[((size_t)traj * bs.b[b].ml + (int)((t + 1) % bs.b[b].ml)) * bs.b[b].ncp + a[b]] = pnew;
+            }
+        }
+        ke += 0.5 * pnew * pnew;
+        phalf[row + i] = pnew + f * dt / 2.0;
+        qn[row + i] = qv + pnew * dt + f * dt * dt / 2.0;
+    }
+    ke = block_sum(ke, red);
+    if (threadIdx.x == 0) etot[(size_t)slab * ntraj + traj] = ke;
+#pragma unroll
+    for (int b = 0; b < NBATH; ++b) {
+        if (b < bs.nb) {
+            const double c = block_sum(cur[b], red);
+            if (threadIdx.x == 0) bs.b[b].cur[(size_t)slab * ntraj + traj] = c;
+        }
+    }
+}
+
 // ---- persistent step kernel for small systems -------------------------------------------------------------------------
 // A single trajectory (or a handful) of a few hundred dofs with time-local diagonal baths -- the reference's own example
 // (examples/runmd.py: 603 dofs, two ml = 1 baths) -- is latency-bound as a chain of launches (~50 us per step).  Here ONE
@@ -1100,7 +1161,10 @@ struct sclmd_md {
         return 0;
     }
 
-    int step() {
+    // `more`: another step follows in the same sclmd_md_run call, so evaluations B, C of this step may be fused with evaluation A
+    // of the next one (k_phase_bca); a_pending is only ever set between the steps of one call
+    bool a_pending = false, fuse_bca = true;
+    int step(bool more = false) {
         BathSet bs = view();
         const bool lin = any_lin();
         if (!g_valid) {
@@ -1111,16 +1175,17 @@ struct sclmd_md {
         if (lin)
             for (auto &b : baths)
                 if (b->has_lin) if (int e = bath_lin(*b, p.p, q.p)) return e;
-        {
+        if (!a_pending) {
             const double *dc = d_valid ? Dc.p : nullptr;
             if (bs.nb <= 2) k_phase_a<2><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, q.p, p.p, G.p, gplan.nsplit, (size_t)ntraj * ld, dc, phalf.p, qn.p, etot.p);
             else k_phase_a<MAXB><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, q.p, p.p, G.p, gplan.nsplit, (size_t)ntraj * ld, dc, phalf.p, qn.p, etot.p);
             SCLMD_CUDA(cudaEventRecord(evObs, st));      // evaluation A wrote etot / currents of this slab
             obs_slab = t % nmd;
+            SCLMD_CUDA(cudaGetLastError());
+            ++launches;
         }
+        a_pending = false;
         d_valid = false;
-        SCLMD_CUDA(cudaGetLastError());
-        ++launches;
         bool any_tail = false;
         for (auto &b : baths) any_tail |= b->ml > 1;
         if (corr() && !kc_valid) {
@@ -1187,7 +1252,17 @@ struct sclmd_md {
             SCLMD_CUDA(cudaStreamWaitEvent(st, evN, 0));
             noise_pending = false;
         }
-        if (int e = enqueue_rest(bs, lin, nullptr)) return e;
+        if (more && fuse_bca && !lin && !has_cons && !want_f && !ext_force) {
+            if (bs.nb <= 2) k_phase_bca<2><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, phalf.p, Gn.p, gplan.nsplit, (size_t)ntraj * ld, p.p, qn.p, q.p, etot.p);
+            else k_phase_bca<MAXB><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, phalf.p, Gn.p, gplan.nsplit, (size_t)ntraj * ld, p.p, qn.p, q.p, etot.p);
+            SCLMD_CUDA(cudaGetLastError());
+            SCLMD_CUDA(cudaEventRecord(evObs, st));      // evaluation A of step t+1 wrote etot / currents of its slab
+            obs_slab = (t + 1) % nmd;
+            ++launches;
+            a_pending = true;
+        } else if (int e = enqueue_rest(bs, lin, nullptr)) {
+            return e;
+        }
         finish_step();
         return 0;
     }
@@ -1222,6 +1297,7 @@ int sclmd_md_create(int nph, int ntraj, double dt, int nmd, int device, sclmd_md
     SCLMD_CUDA(h->d_t.alloc(1));
     h->use_graphs = getenv("SCLMD_NO_GRAPH") == nullptr;
     h->use_persist = getenv("SCLMD_NO_PERSIST") == nullptr;
+    h->fuse_bca = getenv("SCLMD_NO_FUSE") == nullptr;
     SCLMD_CUDA(h->phalf.alloc(n)); SCLMD_CUDA(h->p1.alloc(n)); SCLMD_CUDA(h->qn.alloc(n));
     SCLMD_CUDA(h->etot.alloc((size_t)nmd * ntraj));
     SCLMD_CUDA(h->cons.alloc(nph));
@@ -1515,7 +1591,10 @@ int sclmd_md_run(sclmd_md *h, int64_t nsteps, float *elapsed_ms) {
         if (int e = h->run_persist(nsteps)) return e;
     } else {
         for (int64_t s = 0; s < nsteps; ++s)
-            if (int e = h->step()) return e;
+            if (int e = h->step(s + 1 < nsteps)) {
+                h->a_pending = false;
+                return e;
+            }
     }
     SCLMD_CUDA(cudaEventRecord(h->ev1, h->st));
     if (!elapsed_ms && !h->profiling) return SCLMD_OK;   // asynchronous: the next sclmd_md_get_* synchronises
