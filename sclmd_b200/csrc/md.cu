@@ -1161,10 +1161,28 @@ struct sclmd_md {
         return 0;
     }
 
-    // `more`: another step follows in the same sclmd_md_run call, so evaluations B, C of this step may be fused with evaluation A
-    // of the next one (k_phase_bca); a_pending is only ever set between the steps of one call
-    bool a_pending = false, fuse_bca = true;
-    int step(bool more = false) {
+    // Lazy evaluations B, C: without constraints and with bath forces diagonal in x, a step ends after its K.q' GEMM and leaves B, C
+    // pending (bc_pending; t and the G/Gn roles are already those of the next step).  If another step follows -- in the same
+    // sclmd_md_run call or a later one -- they run fused with its evaluation A (k_phase_bca); anything that reads or changes the
+    // state calls flush() first, which runs them alone.  Nothing is ever computed ahead of the reference's order.
+    bool bc_pending = false, fuse_bca = true;
+    bool lazy_ok(bool lin) const { return fuse_bca && !lin && !has_cons && !want_f && !ext_force; }
+    int flush() {
+        if (!bc_pending) return 0;
+        if (noise_pending) {
+            SCLMD_CUDA(cudaStreamWaitEvent(st, evN, 0));
+            noise_pending = false;
+        }
+        BathSet bs = view();
+        const size_t gs = (size_t)ntraj * ld;
+        if (bs.nb <= 2) k_phase_bc<2><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t - 1, nullptr, dt, nullptr, phalf.p, G.p, gplan.nsplit, gs, p.p, qn.p, q.p, nullptr, 1, 1, nullptr);
+        else k_phase_bc<MAXB><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t - 1, nullptr, dt, nullptr, phalf.p, G.p, gplan.nsplit, gs, p.p, qn.p, q.p, nullptr, 1, 1, nullptr);
+        SCLMD_CUDA(cudaGetLastError());
+        ++launches;
+        bc_pending = false;
+        return 0;
+    }
+    int step() {
         BathSet bs = view();
         const bool lin = any_lin();
         if (!g_valid) {
@@ -1175,7 +1193,19 @@ struct sclmd_md {
         if (lin)
             for (auto &b : baths)
                 if (b->has_lin) if (int e = bath_lin(*b, p.p, q.p)) return e;
-        if (!a_pending) {
+        if (bc_pending) {     // evaluations B, C of step t-1 fused with evaluation A of step t; G = K.q' of step t-1 = K.q_t
+            if (noise_pending) {
+                SCLMD_CUDA(cudaStreamWaitEvent(st, evN, 0));
+                noise_pending = false;
+            }
+            if (bs.nb <= 2) k_phase_bca<2><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t - 1, dt, phalf.p, G.p, gplan.nsplit, (size_t)ntraj * ld, p.p, qn.p, q.p, etot.p);
+            else k_phase_bca<MAXB><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t - 1, dt, phalf.p, G.p, gplan.nsplit, (size_t)ntraj * ld, p.p, qn.p, q.p, etot.p);
+            SCLMD_CUDA(cudaEventRecord(evObs, st));
+            obs_slab = t % nmd;
+            SCLMD_CUDA(cudaGetLastError());
+            ++launches;
+            bc_pending = false;
+        } else {
             const double *dc = d_valid ? Dc.p : nullptr;
             if (bs.nb <= 2) k_phase_a<2><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, q.p, p.p, G.p, gplan.nsplit, (size_t)ntraj * ld, dc, phalf.p, qn.p, etot.p);
             else k_phase_a<MAXB><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, q.p, p.p, G.p, gplan.nsplit, (size_t)ntraj * ld, dc, phalf.p, qn.p, etot.p);
@@ -1184,7 +1214,6 @@ struct sclmd_md {
             SCLMD_CUDA(cudaGetLastError());
             ++launches;
         }
-        a_pending = false;
         d_valid = false;
         bool any_tail = false;
         for (auto &b : baths) any_tail |= b->ml > 1;
@@ -1248,21 +1277,16 @@ struct sclmd_md {
             for (auto &b : baths) if (int e = tail_step(*b, t)) return e;
             if (int e = potforce(qn.p, Gn.p)) return e;
         }
+        if (lazy_ok(lin)) {       // B, C stay pending: fused with the next step's evaluation A, or run by flush()
+            finish_step();
+            bc_pending = true;
+            return 0;
+        }
         if (noise_pending) {   // rows streamed by sclmd_md_set_noise_rows: evaluations B, C read slab t+1
             SCLMD_CUDA(cudaStreamWaitEvent(st, evN, 0));
             noise_pending = false;
         }
-        if (more && fuse_bca && !lin && !has_cons && !want_f && !ext_force) {
-            if (bs.nb <= 2) k_phase_bca<2><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, phalf.p, Gn.p, gplan.nsplit, (size_t)ntraj * ld, p.p, qn.p, q.p, etot.p);
-            else k_phase_bca<MAXB><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, phalf.p, Gn.p, gplan.nsplit, (size_t)ntraj * ld, p.p, qn.p, q.p, etot.p);
-            SCLMD_CUDA(cudaGetLastError());
-            SCLMD_CUDA(cudaEventRecord(evObs, st));      // evaluation A of step t+1 wrote etot / currents of its slab
-            obs_slab = (t + 1) % nmd;
-            ++launches;
-            a_pending = true;
-        } else if (int e = enqueue_rest(bs, lin, nullptr)) {
-            return e;
-        }
+        if (int e = enqueue_rest(bs, lin, nullptr)) return e;
         finish_step();
         return 0;
     }
@@ -1329,6 +1353,7 @@ int sclmd_md_set_dyn(sclmd_md *h, const double *K) {
     if (h) h->drop_graphs();      // captured kernel arguments are about to change
     SCLMD_REQUIRE(h && K, "sclmd_md_set_dyn: NULL argument");
     SCLMD_CUDA(cudaSetDevice(h->device));
+    if (int e = h->flush()) return e;
     SCLMD_CUDA(cudaMemcpy2DAsync(h->K.p, h->ld * sizeof(double), K, h->nph * sizeof(double), h->nph * sizeof(double), h->nph,
                                  cudaMemcpyHostToDevice, h->st));
     SCLMD_CUDA(cudaStreamSynchronize(h->st));
@@ -1343,6 +1368,7 @@ int sclmd_md_set_constraint(sclmd_md *h, const int32_t *idx, int n) {
     if (h) h->drop_graphs();      // captured kernel arguments are about to change
     SCLMD_REQUIRE(h && (n == 0 || idx), "sclmd_md_set_constraint: NULL argument");
     SCLMD_CUDA(cudaSetDevice(h->device));
+    if (int e = h->flush()) return e;
     std::vector<unsigned char> m(h->nph, 0);
     for (int i = 0; i < n; ++i) {
         SCLMD_REQUIRE(idx[i] >= 0 && idx[i] < h->nph, "sclmd_md_set_constraint: index %d out of range", idx[i]);
@@ -1378,6 +1404,7 @@ int sclmd_md_add_bath(sclmd_md *h, const int32_t *cids, int nc, int ml, const do
     SCLMD_REQUIRE((int)h->baths.size() < MAXB, "sclmd_md_add_bath: at most %d baths", MAXB);
     SCLMD_REQUIRE(!(Mq || Mp) || ml == 1, "sclmd_md_add_bath: Mq/Mp only act for time-local baths (baths.py:243-249)");
     SCLMD_CUDA(cudaSetDevice(h->device));
+    if (int e = h->flush()) return e;
     std::unique_ptr<Bath> b(new Bath());
     b->nc = nc; b->ncp = round_up(nc, 2); b->ml = ml; b->kind = kernel_kind;
     b->c0 = ml > 1 ? h->dt : 1.0;  // baths.py:454-457: the dt factor only exists for ml > 1
@@ -1457,6 +1484,7 @@ int sclmd_md_set_noise(sclmd_md *h, int bath, int traj0, int nsel, const double 
     if (int e = check_bath(h, bath, "sclmd_md_set_noise")) return e;
     SCLMD_REQUIRE(noise && traj0 >= 0 && nsel > 0 && traj0 + nsel <= h->ntraj, "sclmd_md_set_noise: bad trajectory range");
     SCLMD_CUDA(cudaSetDevice(h->device));
+    if (int e = h->flush()) return e;
     Bath &b = *h->baths[bath];
     // host [traj][nmd][nc] -> device [nmd][ntraj][ncp]: one strided copy per trajectory
     for (int k = 0; k < nsel; ++k)
@@ -1483,6 +1511,7 @@ int sclmd_md_get_noise(sclmd_md *h, int bath, int traj0, int nsel, double *noise
 int sclmd_md_set_state(sclmd_md *h, const double *q, const double *p, int64_t t) {
     SCLMD_REQUIRE(h, "sclmd_md_set_state: NULL handle");
     SCLMD_CUDA(cudaSetDevice(h->device));
+    if (int e = h->flush()) return e;
     const size_t w = h->nph * sizeof(double), pitch = h->ld * sizeof(double);
     if (q) SCLMD_CUDA(cudaMemcpy2DAsync(h->q.p, pitch, q, w, w, h->ntraj, cudaMemcpyHostToDevice, h->st));
     if (p) SCLMD_CUDA(cudaMemcpy2DAsync(h->p.p, pitch, p, w, w, h->ntraj, cudaMemcpyHostToDevice, h->st));
@@ -1499,6 +1528,7 @@ int sclmd_md_set_state(sclmd_md *h, const double *q, const double *p, int64_t t)
 int sclmd_md_get_state(sclmd_md *h, double *q, double *p, int64_t *t) {
     SCLMD_REQUIRE(h, "sclmd_md_get_state: NULL handle");
     SCLMD_CUDA(cudaSetDevice(h->device));
+    if (int e = h->flush()) return e;
     const size_t w = h->nph * sizeof(double), pitch = h->ld * sizeof(double);
     if (q) SCLMD_CUDA(cudaMemcpy2DAsync(q, w, h->q.p, pitch, w, h->ntraj, cudaMemcpyDeviceToHost, h->st));
     if (p) SCLMD_CUDA(cudaMemcpy2DAsync(p, w, h->p.p, pitch, w, h->ntraj, cudaMemcpyDeviceToHost, h->st));
@@ -1510,6 +1540,7 @@ int sclmd_md_get_state(sclmd_md *h, double *q, double *p, int64_t *t) {
 int sclmd_md_reset_history(sclmd_md *h) {
     SCLMD_REQUIRE(h, "sclmd_md_reset_history: NULL handle");
     SCLMD_CUDA(cudaSetDevice(h->device));
+    if (int e = h->flush()) return e;
     for (auto &b : h->baths) {
         SCLMD_CUDA(cudaMemsetAsync(b->ring.p, 0, b->ring.n * sizeof(double), h->st));
         if (b->tailp.p) SCLMD_CUDA(cudaMemsetAsync(b->tailp.p, 0, b->tailp.n * sizeof(double), h->st));
@@ -1524,6 +1555,7 @@ int sclmd_md_get_history(sclmd_md *h, int bath, double *phis) {
     if (int e = check_bath(h, bath, "sclmd_md_get_history")) return e;
     SCLMD_REQUIRE(phis, "sclmd_md_get_history: NULL buffer");
     SCLMD_CUDA(cudaSetDevice(h->device));
+    if (int e = h->flush()) return e;
     Bath &b = *h->baths[bath];
     std::vector<double> tmp(b.ring.n);
     SCLMD_CUDA(cudaMemcpy(tmp.data(), b.ring.p, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
@@ -1540,6 +1572,7 @@ int sclmd_md_set_history(sclmd_md *h, int bath, const double *phis) {
     if (int e = check_bath(h, bath, "sclmd_md_set_history")) return e;
     SCLMD_REQUIRE(phis, "sclmd_md_set_history: NULL buffer");
     SCLMD_CUDA(cudaSetDevice(h->device));
+    if (int e = h->flush()) return e;
     Bath &b = *h->baths[bath];
     std::vector<double> tmp(b.ring.n, 0.0);
     for (int tr = 0; tr < h->ntraj; ++tr)
@@ -1563,6 +1596,7 @@ int sclmd_md_set_history(sclmd_md *h, int bath, const double *phis) {
 int sclmd_md_set_tail_block(sclmd_md *h, int on) {
     SCLMD_REQUIRE(h, "sclmd_md_set_tail_block: NULL handle");
     SCLMD_CUDA(cudaSetDevice(h->device));
+    if (int e = h->flush()) return e;
     h->tail_block = on != 0;
     h->far_tma = on != 2;    // 2 = time-blocked with the plain-load far kernel (for A/B measurements)
     h->far_ws = on != 3;     // 3 = time-blocked with the two-stage TMA kernel (no producer warp)
@@ -1588,14 +1622,14 @@ int sclmd_md_run(sclmd_md *h, int64_t nsteps, float *elapsed_ms) {
     SCLMD_CUDA(cudaSetDevice(h->device));
     SCLMD_CUDA(cudaEventRecord(h->ev0, h->st));
     if (nsteps > 0 && h->persist_ok()) {
+        if (int e = h->flush()) return e;
         if (int e = h->run_persist(nsteps)) return e;
     } else {
         for (int64_t s = 0; s < nsteps; ++s)
-            if (int e = h->step(s + 1 < nsteps)) {
-                h->a_pending = false;
-                return e;
-            }
+            if (int e = h->step()) return e;
     }
+    if (elapsed_ms || h->profiling)                     // a timed run includes its last evaluations B, C
+        if (int e = h->flush()) return e;
     SCLMD_CUDA(cudaEventRecord(h->ev1, h->st));
     if (!elapsed_ms && !h->profiling) return SCLMD_OK;   // asynchronous: the next sclmd_md_get_* synchronises
     SCLMD_CUDA(cudaStreamSynchronize(h->st));
@@ -1612,6 +1646,8 @@ int sclmd_md_run(sclmd_md *h, int64_t nsteps, float *elapsed_ms) {
 int sclmd_md_set_external_force(sclmd_md *h, int on) {
     SCLMD_REQUIRE(h, "sclmd_md_set_external_force: NULL handle");
     SCLMD_REQUIRE(!h->ext_open, "sclmd_md_set_external_force: a step is open (sclmd_md_step_end missing)");
+    SCLMD_CUDA(cudaSetDevice(h->device));
+    if (int e = h->flush()) return e;
     h->drop_graphs();
     h->ext_force = on != 0;
     h->g_valid = false;
@@ -1663,6 +1699,7 @@ int sclmd_md_step_end(sclmd_md *h, const double *f_trial) {
 int sclmd_md_set_force_output(sclmd_md *h, int on) {
     SCLMD_REQUIRE(h, "sclmd_md_set_force_output: NULL handle");
     SCLMD_CUDA(cudaSetDevice(h->device));
+    if (int e = h->flush()) return e;
     h->drop_graphs();
     if (on) {
         if (!h->fC.p) SCLMD_CUDA(h->fC.alloc((size_t)h->ntraj * h->ld));
@@ -1745,6 +1782,8 @@ int sclmd_md_set_noise_rows(sclmd_md *h, int bath, int slab0, int nslab, const d
     SCLMD_CUDA(cudaSetDevice(h->device));
     Bath &b = *h->baths[bath];
     const size_t rowsz = (size_t)h->ntraj;
+    if (h->bc_pending && (int)(((h->t % h->nmd) - slab0 + h->nmd) % h->nmd) < nslab)     // pending evaluations B, C read slab t
+        if (int e = h->flush()) return e;
     // ASYNCHRONOUS on the handle's copy stream: the upload overlaps the step that is running; the next
     // sclmd_md_run orders itself after it.  `rows` must stay valid until the next synchronising call
     // (sclmd_md_run with elapsed_ms != NULL, any sclmd_md_get_*).  Pinned host memory makes it a true DMA.
@@ -1827,6 +1866,7 @@ int sclmd_md_generate_noise(sclmd_md *h, int bath, sclmd_noise_plan *plan, uint6
     if (int e = sclmd_noise_plan_dims(plan, &pn, &pc)) return e;
     SCLMD_REQUIRE(pn == h->nmd && pc == b.nc, "sclmd_md_generate_noise: plan is for nmd=%d nc=%d, bath needs nmd=%d nc=%d", pn, pc, h->nmd, b.nc);
     SCLMD_CUDA(cudaSetDevice(h->device));
+    if (int e = h->flush()) return e;
     SCLMD_CUDA(cudaStreamSynchronize(h->st));
     return sclmd_noise_plan_generate_into(plan, h->ntraj, seed, traj0, b.noise.p, h->ntraj, b.ncp, 0);
 }
@@ -1854,6 +1894,7 @@ int sclmd_md_time_tail(sclmd_md *h, int bath, int reps, float *avg_ms) {
     if (int e = check_bath(h, bath, "sclmd_md_time_tail")) return e;
     SCLMD_REQUIRE(reps > 0 && avg_ms, "sclmd_md_time_tail: bad arguments");
     SCLMD_CUDA(cudaSetDevice(h->device));
+    if (int e = h->flush()) return e;
     Bath &b = *h->baths[bath];
     SCLMD_REQUIRE(b.ml > 1, "sclmd_md_time_tail: bath %d is time-local (no history tail)", bath);
     // tailp is scratch between steps only in the sense that re-running with the same head is idempotent
@@ -1877,6 +1918,7 @@ int sclmd_md_time_tail(sclmd_md *h, int bath, int reps, float *avg_ms) {
 int sclmd_md_time_potforce(sclmd_md *h, int reps, float *avg_ms) {
     SCLMD_REQUIRE(h && reps > 0 && avg_ms, "sclmd_md_time_potforce: bad arguments");
     SCLMD_CUDA(cudaSetDevice(h->device));
+    if (int e = h->flush()) return e;
     if (int e = h->potforce(h->q.p, h->Gn.p)) return e;
     SCLMD_CUDA(cudaEventRecord(h->ev0, h->st));
     for (int r = 0; r < reps; ++r)

@@ -212,6 +212,67 @@ def test_streamed_noise_rows_and_async_steps_match_resident_table():
     b.close()
 
 
+def test_lazy_evaluations_bc_equal_the_eager_order(monkeypatch):
+    """without constraints the evaluations B, C of a step stay pending and run fused with evaluation A of the next step
+    (k_phase_bca), across sclmd_md_run calls too; every access to the state runs them first.  One call, step-by-step asynchronous
+    calls with streamed noise rows, step-by-step calls with a state read-back after each (always flushed) and the unfused build
+    (SCLMD_NO_FUSE) give bit-identical states, histories and observables"""
+    from sclmd_b200.engine import MDEngine
+    nph, nc, ml, ntraj, dt, nmd = 36, 8, 150, 5, 0.3, 16
+    K = P.psd_project(P.spring_chain_dyn(12, seed=3))
+    kern = P.diag_kernel(ml, nc, dt, 1)
+    nz = P.injected_noise(ntraj, nmd, nc, seed=2)
+    rows = np.ascontiguousarray(nz.transpose(1, 0, 2))
+    nsteps = 37
+
+    def mk(resident=True):
+        e = MDEngine(nph, ntraj, dt, nmd)
+        e.set_dyn(K)
+        e.add_bath(list(range(3, 3 + nc)), kern)
+        e.add_bath(list(range(20, 20 + nc)), kern[:1])
+        e.set_noise(1, 0.5 * nz)
+        if resident:
+            e.set_noise(0, nz)
+        e.set_state(np.full((ntraj, nph), 0.01), np.zeros((ntraj, nph)), 0)
+        return e
+
+    def result(e):
+        q, p, t = e.get_state()
+        return q, p, t, e.get_history(0), e.etot(), e.current(0), e.current(1)
+
+    a = mk()
+    a.run(nsteps)
+    want = result(a)
+    b = mk(resident=False)                                       # streamed rows, asynchronous single steps
+    b.set_noise_rows(0, 0, rows[0:1])
+    for t in range(nsteps):
+        b.set_noise_rows(0, (t + 1) % nmd, rows[(t + 1) % nmd:(t + 1) % nmd + 1])
+        b.run_async(1)
+        ob = b.step_observables(t % nmd)
+        if t >= nsteps - nmd:
+            assert np.array_equal(ob[0], want[4][:, t % nmd]) and np.array_equal(ob[1], want[5][:, t % nmd])
+    c = mk()                                                     # flushed after every step
+    for t in range(nsteps):
+        c.run_async(1)
+        c.get_state()
+    d = mk()                                                     # uneven pieces, a table rewrite (flush) in between
+    d.run_async(5)
+    d.set_noise(0, nz)
+    d.run(11)
+    d.run_async(nsteps - 16)
+    monkeypatch.setenv("SCLMD_NO_FUSE", "1")
+    e = mk()
+    monkeypatch.delenv("SCLMD_NO_FUSE")
+    e.run(nsteps)
+    for other in (b, c, d, e):
+        got = result(other)
+        assert got[2] == want[2] == nsteps
+        for x, y in zip(got, want):
+            assert np.array_equal(x, y)
+        other.close()
+    a.close()
+
+
 def test_history_roundtrip_and_restart():
     """state + history saved from one engine and loaded into another continue identically
     (md.py:552-562 restart semantics)."""
