@@ -177,8 +177,7 @@ __global__ void __launch_bounds__(256, NBATH <= 2 ? 4 : 1) k_phase_bc(BathSet bs
 template <int NBATH>
 __global__ void __launch_bounds__(256, NBATH <= 2 ? 4 : 1) k_phase_bca(BathSet bs, int nph, int ld, int ntraj, int nmd, long long t, double dt,
                                                     double *__restrict__ phalf, const double *__restrict__ Gn, int gsplit, size_t gstride,
-                                                    double *__restrict__ pout, double *__restrict__ qn, double *__restrict__ qout,
-                                                    double *__restrict__ etot) {
+                                                    double *__restrict__ qn, double *__restrict__ etot) {
     __shared__ double red[32];
     const int traj = blockIdx.x;
     const size_t row = (size_t)traj * ld;
@@ -204,8 +203,8 @@ __global__ void __launch_bounds__(256, NBATH <= 2 ? 4 : 1) k_phase_bca(BathSet b
             xi = pnew;
         }
         const double qv = qn[row + i];
-        qout[row + i] = qv;
-        pout[row + i] = pnew;
+        // (p_{t+1}, q_{t+1}) = (pnew, qv) are not stored: the only consumers of the state arrays are flush() and the unfused
+        // kernels, and a flush recomputes the then-current state from phalf / qn.  Two array passes less per step.
         // evaluation A of step t+1 (md.py:383-398) at (p_{t+1}, q_{t+1}) = (pnew, qv); K.q_{t+1} = K.q' without constraints
         double f = -g;
 #pragma unroll
@@ -1198,8 +1197,8 @@ struct sclmd_md {
                 SCLMD_CUDA(cudaStreamWaitEvent(st, evN, 0));
                 noise_pending = false;
             }
-            if (bs.nb <= 2) k_phase_bca<2><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t - 1, dt, phalf.p, G.p, gplan.nsplit, (size_t)ntraj * ld, p.p, qn.p, q.p, etot.p);
-            else k_phase_bca<MAXB><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t - 1, dt, phalf.p, G.p, gplan.nsplit, (size_t)ntraj * ld, p.p, qn.p, q.p, etot.p);
+            if (bs.nb <= 2) k_phase_bca<2><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t - 1, dt, phalf.p, G.p, gplan.nsplit, (size_t)ntraj * ld, qn.p, etot.p);
+            else k_phase_bca<MAXB><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t - 1, dt, phalf.p, G.p, gplan.nsplit, (size_t)ntraj * ld, qn.p, etot.p);
             SCLMD_CUDA(cudaEventRecord(evObs, st));
             obs_slab = t % nmd;
             SCLMD_CUDA(cudaGetLastError());
