@@ -401,6 +401,214 @@ __global__ void __launch_bounds__(256, 1) k_md_persist(const PersistArgs a) {
     }
 }
 
+// ---- ensemble-persistent step kernel ----------------------------------------------------------------------------------------
+// Many trajectories of a small system with time-local diagonal baths (BASELINE configs[1]: 1024 trajectories of the 603-dof
+// junction of examples/runmd.py).  Trajectories never interact, so a CTA takes EN_T = 8 of them -- the row count of the FP64
+// tensor tile -- through ALL steps of a run with no grid-wide synchronisation: state (p, q', K.q, K.q') in shared memory, warp w
+// owns trajectory w in the elementwise phases (observables are warp reductions), and the products K.q' and K[:,fixed].q'[fixed]
+// are DMMA.8x8x4 contractions whose K operand streams from L2 in fragment order (k_build_kfrag: one 512-byte contiguous
+// warp load per two k-steps, no shared-memory staging, no bank or tag conflicts).  Two CTA barriers per step, one launch per run.
+constexpr int EN_T = 8;
+constexpr int EN_D = 4;     // K fragment pairs in flight per tile
+constexpr int EN_G = 5;     // tiles a warp accumulates at a time
+struct EnsArgs {
+    BathSet bs;
+    int nph, ld, lds, ntraj, nmd, has_cons, nk8, nkc8, ncpmax;
+    long long t0, nsteps;
+    double dt;
+    const double *kfrag;            // [ntile][nk8 + nkc8][32][2]: all dofs, then the constrained dofs again (nk8, nkc8 multiples of EN_D)
+    const int *cidx8;               // [nkc8 * 8] constrained dof of contraction slot, -1 = padding
+    double *q, *p, *G;
+    const unsigned char *cons;
+    double *etot;
+};
+
+// fragment-ordered copy of K: out[((j * nkt + s) * 32 + l) * 2 + h] = K[8 j + l / 4][col(8 s + 4 h + l % 4)], zero outside;
+// col(slot) = slot for s < nk8 (all dofs), cols[slot - 8 nk8] after that (the constrained dofs, -1 = padding)
+__global__ void k_build_kfrag(const double *__restrict__ K, int nph, int ld, int nk8, int nkc8, const int *__restrict__ cols,
+                              double *__restrict__ out) {
+    const int j = blockIdx.x, nkt = nk8 + nkc8;
+    for (int e = threadIdx.x; e < nkt * 64; e += blockDim.x) {
+        const int s = e >> 6, l = (e >> 1) & 31, h = e & 1;
+        const int row = 8 * j + (l >> 2), slot = 8 * s + 4 * h + (l & 3);
+        const int col = s < nk8 ? (slot < nph ? slot : -1) : cols[slot - 8 * nk8];
+        out[((size_t)j * nkt) * 64 + e] = (row < nph && col >= 0) ? K[(size_t)row * ld + col] : 0.0;
+    }
+}
+
+template <int NBATH, int NTILE, bool CONS>
+__global__ void __launch_bounds__(256, 1) k_md_ens(const EnsArgs a) {
+    extern __shared__ __align__(16) double esm[];
+    const int nph = a.nph, lds = a.lds;
+    double *sp = esm, *sq = sp + EN_T * lds, *sg = sq + EN_T * lds, *sg1 = sg + EN_T * lds;
+    double *snz = sg1 + EN_T * lds;                       // [NBATH][EN_T][ncpmax]: the noise rows of the current slab
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int gtraj = blockIdx.x * EN_T + w, ltraj = min(gtraj, a.ntraj - 1);
+    const bool live = gtraj < a.ntraj;
+    const double dt = a.dt;
+    double *mp = sp + w * lds, *mq = sq + w * lds, *mg = sg + w * lds, *mg1 = sg1 + w * lds;
+    for (int i = lane; i < lds; i += 32) {
+        const bool ok = i < nph;
+        mp[i] = ok ? a.p[(size_t)ltraj * a.ld + i] : 0.0;
+        mq[i] = ok ? a.q[(size_t)ltraj * a.ld + i] : 0.0;
+        mg[i] = ok ? a.G[(size_t)ltraj * a.ld + i] : 0.0;
+        mg1[i] = 0.0;
+    }
+    auto load_noise = [&](int slab) {      // asynchronous: the rows of this warp's trajectory, 16 bytes at a time
+#pragma unroll
+        for (int b = 0; b < NBATH; ++b)
+            if (b < a.bs.nb) {
+                const double *src = a.bs.b[b].noise + ((size_t)slab * a.ntraj + ltraj) * a.bs.b[b].ncp;
+                double *dst = snz + ((size_t)b * EN_T + w) * a.ncpmax;
+                for (int c = 2 * lane; c < a.bs.b[b].ncp; c += 64) cp_async16_zfill(dst + c, src + c, 16);
+            }
+        cp_async_commit();
+    };
+    load_noise((int)(a.t0 % a.nmd));
+    cp_async_wait<0>();
+    __syncwarp();
+    const int arow = lane >> 2, aslot = lane & 3;
+    for (long long s = 0; s < a.nsteps; ++s) {
+        const long long t = a.t0 + s;
+        const int slab = (int)(t % a.nmd);
+        // ---- evaluation A (md.py:383-398) of this warp's trajectory
+        {
+            double ke = 0.0, cur[NBATH];
+#pragma unroll
+            for (int b = 0; b < NBATH; ++b) cur[b] = 0.0;
+            for (int i = lane; i < nph; i += 32) {
+                const double pi = mp[i];
+                double f = -mg[i];
+#pragma unroll
+                for (int b = 0; b < NBATH; ++b)
+                    if (b < a.bs.nb) {
+                        const int c = a.bs.b[b].inv[i];
+                        if (c >= 0) {
+                            const double fb = snz[((size_t)b * EN_T + w) * a.ncpmax + c] - a.bs.b[b].c0 * a.bs.b[b].k0[c] * pi;
+                            cur[b] += fb * pi;
+                            f += fb;
+                            if (live) a.bs.b[b].ring[((size_t)gtraj * a.bs.b[b].ml + (int)(t % a.bs.b[b].ml)) * a.bs.b[b].ncp + c] = pi;
+                        }
+                    }
+                ke += 0.5 * pi * pi;
+                mp[i] = pi + f * dt / 2.0;                       // p_half
+                mq[i] = mq[i] + pi * dt + f * dt * dt / 2.0;     // q'
+            }
+            ke = warp_sum(ke);
+            if (live && lane == 0) a.etot[(size_t)slab * a.ntraj + gtraj] = ke;
+#pragma unroll
+            for (int b = 0; b < NBATH; ++b)
+                if (b < a.bs.nb) {
+                    const double c = warp_sum(cur[b]);
+                    if (live && lane == 0) a.bs.b[b].cur[(size_t)slab * a.ntraj + gtraj] = c;
+                }
+        }
+        __syncwarp();
+        load_noise((int)((t + 1) % a.nmd));               // evaluations B, C and the next evaluation A read slab t+1
+        __syncthreads();                                  // q' of all eight trajectories is in place
+        // ---- K.q' (and the part of it that comes from the constrained dofs): DMMA over fragment-ordered K
+        {
+            // The K fragments of a tile are ONE stream of nk8 + nkc8 double2 per lane (all dofs, then the constrained ones again);
+            // EN_D of them are in flight per tile (register ring, refilled right after use), for EN_G tiles at a time: the L2
+            // round trip (~1000 cycles under load) is covered by 4 x 5 x 512 bytes per warp.
+            const double *arowp = sq + arow * lds;
+            const int nkt = a.nk8 + a.nkc8;
+            const size_t tstride = (size_t)8 * nkt * 32;        // double2 elements between the tiles w + 8 j of this warp
+#pragma unroll 1
+            for (int g0 = 0; g0 < NTILE; g0 += EN_G) {
+                double acc[EN_G][2], accc[EN_G][2];
+#pragma unroll
+                for (int j = 0; j < EN_G; ++j) acc[j][0] = acc[j][1] = accc[j][0] = accc[j][1] = 0.0;
+                const double2 *kb = reinterpret_cast<const double2 *>(a.kfrag) + ((size_t)(w + 8 * g0) * nkt) * 32 + lane;
+                double2 bn[EN_D][EN_G];
+#pragma unroll
+                for (int d = 0; d < EN_D; ++d)
+#pragma unroll
+                    for (int j = 0; j < EN_G; ++j) bn[d][j] = __ldg(kb + j * tstride + (size_t)d * 32);
+                for (int ks = 0; ks < a.nk8; ks += EN_D) {      // nk8, nkc8 are multiples of EN_D
+#pragma unroll
+                    for (int d = 0; d < EN_D; ++d) {
+                        const double a0 = arowp[8 * (ks + d) + aslot], a1 = arowp[8 * (ks + d) + 4 + aslot];
+#pragma unroll
+                        for (int j = 0; j < EN_G; ++j) dmma884(acc[j][0], acc[j][1], a0, bn[d][j].x);      // EN_G independent chains
+#pragma unroll
+                        for (int j = 0; j < EN_G; ++j) dmma884(acc[j][0], acc[j][1], a1, bn[d][j].y);
+                        if (ks + d + EN_D < nkt) {
+#pragma unroll
+                            for (int j = 0; j < EN_G; ++j) bn[d][j] = __ldg(kb + j * tstride + (size_t)(ks + d + EN_D) * 32);
+                        }
+                    }
+                }
+                if (CONS) {
+                    for (int ks = 0; ks < a.nkc8; ks += EN_D) {
+#pragma unroll
+                        for (int d = 0; d < EN_D; ++d) {
+                            const int c0 = a.cidx8[8 * (ks + d) + aslot], c1 = a.cidx8[8 * (ks + d) + 4 + aslot];
+                            const double a0 = c0 >= 0 ? arowp[c0] : 0.0, a1 = c1 >= 0 ? arowp[c1] : 0.0;
+#pragma unroll
+                            for (int j = 0; j < EN_G; ++j) dmma884(accc[j][0], accc[j][1], a0, bn[d][j].x);
+#pragma unroll
+                            for (int j = 0; j < EN_G; ++j) dmma884(accc[j][0], accc[j][1], a1, bn[d][j].y);
+                            if (a.nk8 + ks + d + EN_D < nkt) {
+#pragma unroll
+                                for (int j = 0; j < EN_G; ++j) bn[d][j] = __ldg(kb + j * tstride + (size_t)(a.nk8 + ks + d + EN_D) * 32);
+                            }
+                        }
+                    }
+                }
+                // D[traj = lane / 4][n = 8 tile + 2 (lane % 4) + {0, 1}]; sg (K.q of the step just evaluated) is free again
+#pragma unroll
+                for (int j = 0; j < EN_G; ++j) {
+                    const int n = 8 * (w + 8 * (g0 + j)) + 2 * aslot;
+                    if (n < nph) {
+                        sg1[arow * lds + n] = acc[j][0];
+                        sg[arow * lds + n] = acc[j][0] - accc[j][0];
+                    }
+                    if (n + 1 < nph) {
+                        sg1[arow * lds + n + 1] = acc[j][1];
+                        sg[arow * lds + n + 1] = acc[j][1] - accc[j][1];
+                    }
+                }
+            }
+        }
+        cp_async_wait<0>();
+        __syncthreads();
+        // ---- evaluations B and C (md.py:401-404), constraint (md.py:407-408)
+        for (int i = lane; i < nph; i += 32) {
+            const double ph = mp[i], g1 = mg1[i];
+            double nz[NBATH], kx[NBATH];
+            bool in[NBATH];
+#pragma unroll
+            for (int b = 0; b < NBATH; ++b) {
+                const int c = b < a.bs.nb ? a.bs.b[b].inv[i] : -1;
+                in[b] = c >= 0;
+                nz[b] = in[b] ? snz[((size_t)b * EN_T + w) * a.ncpmax + c] : 0.0;
+                kx[b] = in[b] ? a.bs.b[b].c0 * a.bs.b[b].k0[c] : 0.0;
+            }
+            double xi = ph, pnew = 0.0;
+#pragma unroll
+            for (int rep = 0; rep < 2; ++rep) {
+                double f = -g1;
+#pragma unroll
+                for (int b = 0; b < NBATH; ++b)
+                    if (in[b]) f += nz[b] - kx[b] * xi;
+                pnew = ph + dt * f / 2.0;
+                xi = pnew;
+            }
+            const bool fx = CONS && a.cons[i];
+            mp[i] = fx ? 0.0 : pnew;
+            if (fx) mq[i] = 0.0;
+        }
+        __syncwarp();
+    }
+    if (live)
+        for (int i = lane; i < nph; i += 32) {
+            a.p[(size_t)gtraj * a.ld + i] = mp[i];
+            a.q[(size_t)gtraj * a.ld + i] = mq[i];
+            a.G[(size_t)gtraj * a.ld + i] = mg[i];
+        }
+}
+
 // G[0] <- sum_z G[z] (- D): the persistent kernel works on one K.q vector per trajectory
 __global__ void k_fold_g(double *G, int nsplit, size_t n, const double *D) {
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1102,6 +1310,88 @@ struct sclmd_md {
         }
         return 0;
     }
+    // whole run(n) of an ensemble in one launch without grid synchronisation (k_md_ens): time-local diagonal baths, nph <= 768
+    bool use_ens = true, kfrag_valid = false;
+    DevBuf<double> kfrag;
+    DevBuf<int> cidx8;
+    int ens_nk8 = 0, ens_nkc8 = 0, ens_ntile = 0;
+    bool ens_ok() const {
+        if (!use_persist || !use_ens || ext_force || want_f || profiling || !have_dyn || ntraj <= PS_MAXT || nph > 760 || baths.size() > 2) return false;
+        for (auto &b : baths)
+            if (b->ml > 1 || b->has_lin || b->kind != SCLMD_KERNEL_DIAG) return false;
+        return true;
+    }
+    int build_kfrag() {
+        ens_nk8 = round_up(cdiv(nph, 8), EN_D);
+        const int need = cdiv(cdiv(nph, 8), 8);
+        ens_ntile = need <= 5 ? 5 : need <= 10 ? 10 : 15;
+        ens_nkc8 = 0;
+        if (has_cons) {
+            std::vector<unsigned char> m(nph);
+            SCLMD_CUDA(cudaMemcpyAsync(m.data(), cons.p, nph, cudaMemcpyDeviceToHost, st));
+            SCLMD_CUDA(cudaStreamSynchronize(st));
+            std::vector<int> idx;
+            for (int i = 0; i < nph; ++i) if (m[i]) idx.push_back(i);
+            ens_nkc8 = round_up(cdiv((int)idx.size(), 8), EN_D);
+            idx.resize((size_t)ens_nkc8 * 8, -1);
+            SCLMD_CUDA(cidx8.alloc(idx.size()));
+            SCLMD_CUDA(cudaMemcpy(cidx8.p, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice));
+        }
+        SCLMD_CUDA(kfrag.alloc((size_t)8 * ens_ntile * (ens_nk8 + ens_nkc8) * 64));
+        k_build_kfrag<<<8 * ens_ntile, 256, 0, st>>>(K.p, nph, ld, ens_nk8, ens_nkc8, cidx8.p, kfrag.p);
+        SCLMD_CUDA(cudaGetLastError());
+        ++launches;
+        kfrag_valid = true;
+        return 0;
+    }
+    template <int NTILE>
+    int launch_ens(const EnsArgs &a, size_t smem) {
+        auto go = [&](auto kernel) -> int {
+            SCLMD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kernel<<<cdiv(ntraj, EN_T), 256, smem, st>>>(a);
+            SCLMD_CUDA(cudaGetLastError());
+            return 0;
+        };
+        return has_cons ? go(k_md_ens<2, NTILE, true>) : go(k_md_ens<2, NTILE, false>);
+    }
+    int run_ens(long long nsteps) {
+        if (!kfrag_valid) if (int e = build_kfrag()) return e;
+        BathSet bs = view();
+        if (!g_valid) {
+            if (int e = potforce(q.p, G.p)) return e;
+            g_valid = true;
+            d_valid = false;
+        }
+        const size_t n = (size_t)ntraj * ld;
+        if (gplan.nsplit > 1 || d_valid) {     // fold the K-slices (and a pending constraint correction) into slice 0
+            k_fold_g<<<cdiv((int)n, 256), 256, 0, st>>>(G.p, gplan.nsplit, n, d_valid ? Dc.p : nullptr);
+            SCLMD_CUDA(cudaGetLastError());
+            d_valid = false;
+            ++launches;
+        }
+        if (noise_pending) {
+            SCLMD_CUDA(cudaStreamWaitEvent(st, evN, 0));
+            noise_pending = false;
+        }
+        EnsArgs a{};
+        a.bs = bs; a.nph = nph; a.ld = ld; a.ntraj = ntraj; a.nmd = nmd; a.has_cons = has_cons ? 1 : 0;
+        a.nk8 = ens_nk8; a.nkc8 = ens_nkc8;
+        a.lds = round_up(8 * ens_nk8, 16) + 4;            // == 4 (mod 16): the eight trajectory rows of an A fragment hit distinct banks
+        a.ncpmax = 2;
+        for (auto &b : baths) a.ncpmax = std::max(a.ncpmax, b->ncp);
+        a.t0 = t; a.nsteps = nsteps; a.dt = dt; a.kfrag = kfrag.p; a.cidx8 = cidx8.p;
+        a.q = q.p; a.p = p.p; a.G = G.p; a.cons = cons.p; a.etot = etot.p;
+        const size_t smem = ((size_t)4 * EN_T * a.lds + (size_t)2 * EN_T * a.ncpmax) * sizeof(double);
+        if (smem > 220 * 1024) return 1;                  // caller falls back to the launch chain
+        int e = ens_ntile == 5 ? launch_ens<5>(a, smem) : ens_ntile == 10 ? launch_ens<10>(a, smem) : launch_ens<15>(a, smem);
+        if (e) return e;
+        ++launches;
+        t += nsteps;
+        dt_synced = false;
+        obs_slab = -1;
+        if (gplan.nsplit > 1) SCLMD_CUDA(cudaMemsetAsync(G.p + n, 0, (size_t)(gplan.nsplit - 1) * n * sizeof(double), st));
+        return 0;
+    }
     void finish_step() {      // host-side state after a step
         if (corr()) {
             d_valid = true;
@@ -1321,6 +1611,7 @@ int sclmd_md_create(int nph, int ntraj, double dt, int nmd, int device, sclmd_md
     h->use_graphs = getenv("SCLMD_NO_GRAPH") == nullptr;
     h->use_persist = getenv("SCLMD_NO_PERSIST") == nullptr;
     h->fuse_bca = getenv("SCLMD_NO_FUSE") == nullptr;
+    h->use_ens = getenv("SCLMD_NO_ENS") == nullptr;
     SCLMD_CUDA(h->phalf.alloc(n)); SCLMD_CUDA(h->p1.alloc(n)); SCLMD_CUDA(h->qn.alloc(n));
     SCLMD_CUDA(h->etot.alloc((size_t)nmd * ntraj));
     SCLMD_CUDA(h->cons.alloc(nph));
@@ -1359,6 +1650,7 @@ int sclmd_md_set_dyn(sclmd_md *h, const double *K) {
     h->have_dyn = true;
     h->g_valid = false;
     h->kc_valid = false;
+    h->kfrag_valid = false;
     h->d_valid = false;
     return SCLMD_OK;
 }
@@ -1381,6 +1673,7 @@ int sclmd_md_set_constraint(sclmd_md *h, const int32_t *idx, int n) {
     h->ldcons = round_up(std::max(h->ncons, 2), 2);
     h->use_corr = h->has_cons && 2 * h->ncons <= h->nph;   // cheaper than a second full K.q
     h->kc_valid = false;
+    h->kfrag_valid = false;
     h->d_valid = false;
     h->g_valid = false;
     if (h->use_corr) {
@@ -1620,7 +1913,15 @@ int sclmd_md_run(sclmd_md *h, int64_t nsteps, float *elapsed_ms) {
     }
     SCLMD_CUDA(cudaSetDevice(h->device));
     SCLMD_CUDA(cudaEventRecord(h->ev0, h->st));
-    if (nsteps > 0 && h->persist_ok()) {
+    bool done = false;
+    if (nsteps >= 8 && h->ens_ok()) {     // short runs (the per-step end-to-end path) stay on the launch chain
+        if (int e = h->flush()) return e;
+        const int e = h->run_ens(nsteps);
+        if (e < 0) return e;
+        done = e == 0;          // 1: the state does not fit shared memory, take the launch chain
+    }
+    if (done) {
+    } else if (nsteps > 0 && h->persist_ok()) {
         if (int e = h->flush()) return e;
         if (int e = h->run_persist(nsteps)) return e;
     } else {

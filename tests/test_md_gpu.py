@@ -416,10 +416,11 @@ def test_edge_shapes_vs_oracle(case):
     eng.close()
 
 
-@pytest.mark.parametrize("ntraj,cons", [(1, True), (2, True), (2, False)])
+@pytest.mark.parametrize("ntraj,cons", [(1, True), (2, True), (2, False), (19, True), (24, False)])
 def test_persistent_kernel_equals_launch_chain_and_oracle(ntraj, cons):
-    """the cooperative persistent kernel (one launch per run, one grid barrier per step; config-1 shape: 603 dofs, two ml = 1 baths,
-    fixed ends) against the per-step launch chain and the oracle: several run() calls, observables, a restart in between"""
+    """the persistent kernels (one launch per run: the cooperative one with a grid barrier per step for one or two trajectories, the
+    ensemble one -- eight trajectories per CTA, no grid barrier -- above that; config-1/2 shape: 603 dofs, two ml = 1 baths, fixed
+    ends) against the per-step launch chain and the oracle: several run() calls, observables, a restart in between"""
     from sclmd_b200.engine import MDEngine
     c = P.md_case_c1_shape()
     K = P.psd_project(c["K"])
