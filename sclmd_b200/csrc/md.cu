@@ -2091,9 +2091,13 @@ int sclmd_md_set_noise_rows(sclmd_md *h, int bath, int slab0, int nslab, const d
     while (done < nslab) {  // at most two pieces (wrap at nmd)
         const int s = (slab0 + done) % h->nmd;
         const int n = std::min(nslab - done, h->nmd - s);
-        SCLMD_CUDA(cudaMemcpy2DAsync(b.noise.p + (size_t)s * rowsz * b.ncp, b.ncp * sizeof(double),
-                                     rows + (size_t)done * rowsz * b.nc, b.nc * sizeof(double), b.nc * sizeof(double),
-                                     (size_t)n * rowsz, cudaMemcpyHostToDevice, h->stc));
+        if (b.nc == b.ncp)       // rows are contiguous on both sides: one linear DMA instead of a row-by-row 2-D copy
+            SCLMD_CUDA(cudaMemcpyAsync(b.noise.p + (size_t)s * rowsz * b.ncp, rows + (size_t)done * rowsz * b.nc,
+                                       (size_t)n * rowsz * b.nc * sizeof(double), cudaMemcpyHostToDevice, h->stc));
+        else
+            SCLMD_CUDA(cudaMemcpy2DAsync(b.noise.p + (size_t)s * rowsz * b.ncp, b.ncp * sizeof(double),
+                                         rows + (size_t)done * rowsz * b.nc, b.nc * sizeof(double), b.nc * sizeof(double),
+                                         (size_t)n * rowsz, cudaMemcpyHostToDevice, h->stc));
         done += n;
     }
     SCLMD_CUDA(cudaEventRecord(h->evN, h->stc));
