@@ -75,7 +75,7 @@ __device__ __forceinline__ double bath_force(const BathDev &b, int traj, int ntr
 
 // evaluation A (md.py:383-398): etot, ring push, f_A, p_half, q_next, heat current
 template <int NBATH>      // baths the per-element loop is unrolled for (register pressure: 128 registers at 8, 1/4 occupancy)
-__global__ void __launch_bounds__(256, NBATH <= 2 ? 4 : 1) k_phase_a(BathSet bs, int nph, int ld, int ntraj, int nmd, long long t, double dt,
+__global__ void __launch_bounds__(256, NBATH <= 2 ? 4 : NBATH <= 4 ? 2 : 1) k_phase_a(BathSet bs, int nph, int ld, int ntraj, int nmd, long long t, double dt,
                                                   const double *__restrict__ q, const double *__restrict__ p,
                                                   const double *__restrict__ G, int gsplit, size_t gstride,
                                                   const double *__restrict__ Dcorr,
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(256, NBATH <= 2 ? 4 : 1) k_phase_a(BathSet bs,
 // evaluation B or C (md.py:401-404): pout = phalf + dt/2 * F(t+1; x, qn); `final` applies the
 // constraint (md.py:407-408) and commits q.
 template <int NBATH>
-__global__ void __launch_bounds__(256, NBATH <= 2 ? 4 : 1) k_phase_bc(BathSet bs, int nph, int ld, int ntraj, int nmd, long long t,
+__global__ void __launch_bounds__(256, NBATH <= 2 ? 4 : NBATH <= 4 ? 2 : 1) k_phase_bc(BathSet bs, int nph, int ld, int ntraj, int nmd, long long t,
                                                                       const long long *__restrict__ tptr, double dt,
                                                    const double *__restrict__ x, const double *__restrict__ phalf,
                                                    const double *__restrict__ Gn, int gsplit, size_t gstride, double *__restrict__ pout,
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(256, NBATH <= 2 ? 4 : 1) k_phase_bc(BathSet bs
 // three evaluations see the same K.q', noise row and history tail and differ only in the momentum they are taken at, so the
 // state never leaves registers between them.  Saves one launch and the re-read of p, q and the K-slices of K.q per step.
 template <int NBATH>
-__global__ void __launch_bounds__(256, NBATH <= 2 ? 4 : 1) k_phase_bca(BathSet bs, int nph, int ld, int ntraj, int nmd, long long t, double dt,
+__global__ void __launch_bounds__(256, NBATH <= 2 ? 4 : NBATH <= 4 ? 2 : 1) k_phase_bca(BathSet bs, int nph, int ld, int ntraj, int nmd, long long t, double dt,
                                                     double *__restrict__ phalf, const double *__restrict__ Gn, int gsplit, size_t gstride,
                                                     double *__restrict__ qn, double *__restrict__ etot) {
     __shared__ double red[32];
@@ -1241,6 +1241,7 @@ struct sclmd_md {
         }
         auto bc = [&](const double *x, double *pout, int final, int fused) -> cudaError_t {
             if (bs.nb <= 2) k_phase_bc<2><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, tptr, dt, x, phalf.p, Gn.p, gplan.nsplit, gs, pout, qn.p, q.p, cm, final, fused, want_f ? fC.p : nullptr);
+            else if (bs.nb <= 4) k_phase_bc<4><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, tptr, dt, x, phalf.p, Gn.p, gplan.nsplit, gs, pout, qn.p, q.p, cm, final, fused, want_f ? fC.p : nullptr);
             else k_phase_bc<MAXB><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, tptr, dt, x, phalf.p, Gn.p, gplan.nsplit, gs, pout, qn.p, q.p, cm, final, fused, want_f ? fC.p : nullptr);
             ++launches;
             return cudaGetLastError();
@@ -1424,6 +1425,7 @@ struct sclmd_md {
             for (auto &b : baths)
                 if (b->has_lin) if (int e = bath_lin(*b, p.p, q.p)) return e;
         if (bs.nb <= 2) k_phase_a<2><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, q.p, p.p, G.p, gplan.nsplit, (size_t)ntraj * ld, nullptr, phalf.p, qn.p, etot.p);
+        else if (bs.nb <= 4) k_phase_a<4><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, q.p, p.p, G.p, gplan.nsplit, (size_t)ntraj * ld, nullptr, phalf.p, qn.p, etot.p);
         else k_phase_a<MAXB><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, q.p, p.p, G.p, gplan.nsplit, (size_t)ntraj * ld, nullptr, phalf.p, qn.p, etot.p);
         SCLMD_CUDA(cudaGetLastError());
         SCLMD_CUDA(cudaEventRecord(evObs, st));
@@ -1465,6 +1467,7 @@ struct sclmd_md {
         BathSet bs = view();
         const size_t gs = (size_t)ntraj * ld;
         if (bs.nb <= 2) k_phase_bc<2><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t - 1, nullptr, dt, nullptr, phalf.p, G.p, gplan.nsplit, gs, p.p, qn.p, q.p, nullptr, 1, 1, nullptr);
+        else if (bs.nb <= 4) k_phase_bc<4><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t - 1, nullptr, dt, nullptr, phalf.p, G.p, gplan.nsplit, gs, p.p, qn.p, q.p, nullptr, 1, 1, nullptr);
         else k_phase_bc<MAXB><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t - 1, nullptr, dt, nullptr, phalf.p, G.p, gplan.nsplit, gs, p.p, qn.p, q.p, nullptr, 1, 1, nullptr);
         SCLMD_CUDA(cudaGetLastError());
         ++launches;
@@ -1488,6 +1491,7 @@ struct sclmd_md {
                 noise_pending = false;
             }
             if (bs.nb <= 2) k_phase_bca<2><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t - 1, dt, phalf.p, G.p, gplan.nsplit, (size_t)ntraj * ld, qn.p, etot.p);
+            else if (bs.nb <= 4) k_phase_bca<4><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t - 1, dt, phalf.p, G.p, gplan.nsplit, (size_t)ntraj * ld, qn.p, etot.p);
             else k_phase_bca<MAXB><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t - 1, dt, phalf.p, G.p, gplan.nsplit, (size_t)ntraj * ld, qn.p, etot.p);
             SCLMD_CUDA(cudaEventRecord(evObs, st));
             obs_slab = t % nmd;
@@ -1497,6 +1501,7 @@ struct sclmd_md {
         } else {
             const double *dc = d_valid ? Dc.p : nullptr;
             if (bs.nb <= 2) k_phase_a<2><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, q.p, p.p, G.p, gplan.nsplit, (size_t)ntraj * ld, dc, phalf.p, qn.p, etot.p);
+            else if (bs.nb <= 4) k_phase_a<4><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, q.p, p.p, G.p, gplan.nsplit, (size_t)ntraj * ld, dc, phalf.p, qn.p, etot.p);
             else k_phase_a<MAXB><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, q.p, p.p, G.p, gplan.nsplit, (size_t)ntraj * ld, dc, phalf.p, qn.p, etot.p);
             SCLMD_CUDA(cudaEventRecord(evObs, st));      // evaluation A wrote etot / currents of this slab
             obs_slab = t % nmd;
