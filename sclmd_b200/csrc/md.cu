@@ -1046,6 +1046,9 @@ struct sclmd_md {
     long long f_step = -1;      // the step (value of t after it) fC / fa belong to
     DevBuf<double> fC;
     bool corr() const { return has_cons && use_corr && !ext_force; }
+    // CTA size of the per-trajectory evaluation kernels: small systems are latency-bound per CTA, so smaller CTAs (eight per SM
+    // instead of four: the whole 1024-trajectory grid resident in one wave) finish sooner
+    int phase_threads() const { return nph <= 1024 ? 128 : 256; }
     int ncons = 0, ldcons = 0;
     DevBuf<int> cidx;
     DevBuf<double> Kc, qc, Dc;   // constraint correction: D = q'[cons] . K[:,cons]^T
@@ -1240,9 +1243,9 @@ struct sclmd_md {
             ++launches;
         }
         auto bc = [&](const double *x, double *pout, int final, int fused) -> cudaError_t {
-            if (bs.nb <= 2) k_phase_bc<2><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, tptr, dt, x, phalf.p, Gn.p, gplan.nsplit, gs, pout, qn.p, q.p, cm, final, fused, want_f ? fC.p : nullptr);
-            else if (bs.nb <= 4) k_phase_bc<4><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, tptr, dt, x, phalf.p, Gn.p, gplan.nsplit, gs, pout, qn.p, q.p, cm, final, fused, want_f ? fC.p : nullptr);
-            else k_phase_bc<MAXB><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, tptr, dt, x, phalf.p, Gn.p, gplan.nsplit, gs, pout, qn.p, q.p, cm, final, fused, want_f ? fC.p : nullptr);
+            if (bs.nb <= 2) k_phase_bc<2><<<ntraj, phase_threads(), 0, st>>>(bs, nph, ld, ntraj, nmd, t, tptr, dt, x, phalf.p, Gn.p, gplan.nsplit, gs, pout, qn.p, q.p, cm, final, fused, want_f ? fC.p : nullptr);
+            else if (bs.nb <= 4) k_phase_bc<4><<<ntraj, phase_threads(), 0, st>>>(bs, nph, ld, ntraj, nmd, t, tptr, dt, x, phalf.p, Gn.p, gplan.nsplit, gs, pout, qn.p, q.p, cm, final, fused, want_f ? fC.p : nullptr);
+            else k_phase_bc<MAXB><<<ntraj, phase_threads(), 0, st>>>(bs, nph, ld, ntraj, nmd, t, tptr, dt, x, phalf.p, Gn.p, gplan.nsplit, gs, pout, qn.p, q.p, cm, final, fused, want_f ? fC.p : nullptr);
             ++launches;
             return cudaGetLastError();
         };
@@ -1424,9 +1427,9 @@ struct sclmd_md {
         if (any_lin())
             for (auto &b : baths)
                 if (b->has_lin) if (int e = bath_lin(*b, p.p, q.p)) return e;
-        if (bs.nb <= 2) k_phase_a<2><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, q.p, p.p, G.p, gplan.nsplit, (size_t)ntraj * ld, nullptr, phalf.p, qn.p, etot.p);
-        else if (bs.nb <= 4) k_phase_a<4><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, q.p, p.p, G.p, gplan.nsplit, (size_t)ntraj * ld, nullptr, phalf.p, qn.p, etot.p);
-        else k_phase_a<MAXB><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, q.p, p.p, G.p, gplan.nsplit, (size_t)ntraj * ld, nullptr, phalf.p, qn.p, etot.p);
+        if (bs.nb <= 2) k_phase_a<2><<<ntraj, phase_threads(), 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, q.p, p.p, G.p, gplan.nsplit, (size_t)ntraj * ld, nullptr, phalf.p, qn.p, etot.p);
+        else if (bs.nb <= 4) k_phase_a<4><<<ntraj, phase_threads(), 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, q.p, p.p, G.p, gplan.nsplit, (size_t)ntraj * ld, nullptr, phalf.p, qn.p, etot.p);
+        else k_phase_a<MAXB><<<ntraj, phase_threads(), 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, q.p, p.p, G.p, gplan.nsplit, (size_t)ntraj * ld, nullptr, phalf.p, qn.p, etot.p);
         SCLMD_CUDA(cudaGetLastError());
         SCLMD_CUDA(cudaEventRecord(evObs, st));
         obs_slab = t % nmd;
@@ -1466,9 +1469,9 @@ struct sclmd_md {
         }
         BathSet bs = view();
         const size_t gs = (size_t)ntraj * ld;
-        if (bs.nb <= 2) k_phase_bc<2><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t - 1, nullptr, dt, nullptr, phalf.p, G.p, gplan.nsplit, gs, p.p, qn.p, q.p, nullptr, 1, 1, nullptr);
-        else if (bs.nb <= 4) k_phase_bc<4><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t - 1, nullptr, dt, nullptr, phalf.p, G.p, gplan.nsplit, gs, p.p, qn.p, q.p, nullptr, 1, 1, nullptr);
-        else k_phase_bc<MAXB><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t - 1, nullptr, dt, nullptr, phalf.p, G.p, gplan.nsplit, gs, p.p, qn.p, q.p, nullptr, 1, 1, nullptr);
+        if (bs.nb <= 2) k_phase_bc<2><<<ntraj, phase_threads(), 0, st>>>(bs, nph, ld, ntraj, nmd, t - 1, nullptr, dt, nullptr, phalf.p, G.p, gplan.nsplit, gs, p.p, qn.p, q.p, nullptr, 1, 1, nullptr);
+        else if (bs.nb <= 4) k_phase_bc<4><<<ntraj, phase_threads(), 0, st>>>(bs, nph, ld, ntraj, nmd, t - 1, nullptr, dt, nullptr, phalf.p, G.p, gplan.nsplit, gs, p.p, qn.p, q.p, nullptr, 1, 1, nullptr);
+        else k_phase_bc<MAXB><<<ntraj, phase_threads(), 0, st>>>(bs, nph, ld, ntraj, nmd, t - 1, nullptr, dt, nullptr, phalf.p, G.p, gplan.nsplit, gs, p.p, qn.p, q.p, nullptr, 1, 1, nullptr);
         SCLMD_CUDA(cudaGetLastError());
         ++launches;
         bc_pending = false;
@@ -1490,9 +1493,9 @@ struct sclmd_md {
                 SCLMD_CUDA(cudaStreamWaitEvent(st, evN, 0));
                 noise_pending = false;
             }
-            if (bs.nb <= 2) k_phase_bca<2><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t - 1, dt, phalf.p, G.p, gplan.nsplit, (size_t)ntraj * ld, qn.p, etot.p);
-            else if (bs.nb <= 4) k_phase_bca<4><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t - 1, dt, phalf.p, G.p, gplan.nsplit, (size_t)ntraj * ld, qn.p, etot.p);
-            else k_phase_bca<MAXB><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t - 1, dt, phalf.p, G.p, gplan.nsplit, (size_t)ntraj * ld, qn.p, etot.p);
+            if (bs.nb <= 2) k_phase_bca<2><<<ntraj, phase_threads(), 0, st>>>(bs, nph, ld, ntraj, nmd, t - 1, dt, phalf.p, G.p, gplan.nsplit, (size_t)ntraj * ld, qn.p, etot.p);
+            else if (bs.nb <= 4) k_phase_bca<4><<<ntraj, phase_threads(), 0, st>>>(bs, nph, ld, ntraj, nmd, t - 1, dt, phalf.p, G.p, gplan.nsplit, (size_t)ntraj * ld, qn.p, etot.p);
+            else k_phase_bca<MAXB><<<ntraj, phase_threads(), 0, st>>>(bs, nph, ld, ntraj, nmd, t - 1, dt, phalf.p, G.p, gplan.nsplit, (size_t)ntraj * ld, qn.p, etot.p);
             SCLMD_CUDA(cudaEventRecord(evObs, st));
             obs_slab = t % nmd;
             SCLMD_CUDA(cudaGetLastError());
@@ -1500,9 +1503,9 @@ struct sclmd_md {
             bc_pending = false;
         } else {
             const double *dc = d_valid ? Dc.p : nullptr;
-            if (bs.nb <= 2) k_phase_a<2><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, q.p, p.p, G.p, gplan.nsplit, (size_t)ntraj * ld, dc, phalf.p, qn.p, etot.p);
-            else if (bs.nb <= 4) k_phase_a<4><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, q.p, p.p, G.p, gplan.nsplit, (size_t)ntraj * ld, dc, phalf.p, qn.p, etot.p);
-            else k_phase_a<MAXB><<<ntraj, 256, 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, q.p, p.p, G.p, gplan.nsplit, (size_t)ntraj * ld, dc, phalf.p, qn.p, etot.p);
+            if (bs.nb <= 2) k_phase_a<2><<<ntraj, phase_threads(), 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, q.p, p.p, G.p, gplan.nsplit, (size_t)ntraj * ld, dc, phalf.p, qn.p, etot.p);
+            else if (bs.nb <= 4) k_phase_a<4><<<ntraj, phase_threads(), 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, q.p, p.p, G.p, gplan.nsplit, (size_t)ntraj * ld, dc, phalf.p, qn.p, etot.p);
+            else k_phase_a<MAXB><<<ntraj, phase_threads(), 0, st>>>(bs, nph, ld, ntraj, nmd, t, dt, q.p, p.p, G.p, gplan.nsplit, (size_t)ntraj * ld, dc, phalf.p, qn.p, etot.p);
             SCLMD_CUDA(cudaEventRecord(evObs, st));      // evaluation A wrote etot / currents of this slab
             obs_slab = t % nmd;
             SCLMD_CUDA(cudaGetLastError());
