@@ -536,6 +536,15 @@ def main():
         except Exception as exc:  # the headline line must not depend on the secondary workload
             line["also_md_config2"] = {"error": str(exc)[:200]}
 
+    # ---------------- BASELINE configs[3] shape: the current-induced junction (three electron baths, one biased with dense matrices)
+    if world == 1 and not args.no_also:
+        try:
+            r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "probe_c4_md.py"), "1024", "512"],
+                               capture_output=True, text=True, timeout=600)
+            line["also_md_config4"] = json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception as exc:
+            line["also_md_config4"] = {"error": str(exc)[:200]}
+
     # ---------------- BASELINE configs[0] shape: ONE trajectory of the same junction (the reference's own mode of operation)
     if world == 1 and not args.no_also:
         try:

@@ -119,8 +119,8 @@ int sclmd_md_get_profile(sclmd_md *h, double *tail_ms, int64_t *tail_launches, d
 int sclmd_md_set_overlap(sclmd_md *h, int on);
 /* 1 (default): sclmd_md_run on a handle whose baths are all time-local and diagonal (the reference's own example,
  * examples/runmd.py) is ONE launch of a persistent kernel: for <= 2 trajectories of <= 1024 dofs a cooperative kernel with one grid
- * barrier per step; for larger ensembles of <= 760 dofs (runs of >= 8 steps) the ensemble kernel, eight trajectories per CTA through
- * all steps with no grid barrier.  0: per-step launches */
+ * barrier per step; for larger ensembles of <= 760 dofs (runs of >= 8 steps; up to four time-local baths, one of them may be a dense
+ * one of <= 64 dofs) the ensemble kernel, eight trajectories per CTA through all steps with no grid barrier.  0: per-step launches */
 int sclmd_md_set_persistent(sclmd_md *h, int on);
 
 /* Force drivers (md.AddPotential, md.py:457-459, 481-485; protocol lammpsdriver.py:83-84): the potential force is a host callback.

@@ -43,6 +43,8 @@ struct BathDev {  // POD view passed to kernels
     double *ring;            // [ntraj][ml][ncp]
     double *cur;             // [nmd][ntraj]
     double *fa, *fc;         // [ntraj][ncp] bath force of evaluation A (md.fhis) / of evaluation C (md.fbaths after vv), or NULL
+    const double *wt;        // has_lin: W^T [Kw][ncp] (the ensemble kernel's matrix-vector product reads it lane-contiguous)
+    int Kw;
 };
 struct BathSet {
     int nb;
@@ -54,7 +56,7 @@ struct Bath {
     bool has_lin = false, has_extra = false;
     double c0 = 1.0;
     DevBuf<int> cids, inv;
-    DevBuf<double> kern, W, ring, xq, lin, tailp, noise, cur, far, fa, fc;
+    DevBuf<double> kern, W, ring, xq, lin, tailp, noise, cur, far, fa, fc, WT;
     bool blocked = false;     // time-blocked tails (diagonal kernel, long memory)
     int far_nsplit = 1;
     long long far_t0 = -1;    // block start the far tails in `far` belong to
@@ -410,10 +412,9 @@ __global__ void __launch_bounds__(256, 1) k_md_persist(const PersistArgs a) {
 // warp load per two k-steps, no shared-memory staging, no bank or tag conflicts).  Two CTA barriers per step, one launch per run.
 constexpr int EN_T = 8;
 constexpr int EN_D = 4;     // K fragment pairs in flight per tile
-constexpr int EN_G = 5;     // tiles a warp accumulates at a time
 struct EnsArgs {
     BathSet bs;
-    int nph, ld, lds, ntraj, nmd, has_cons, nk8, nkc8, ncpmax;
+    int nph, ld, lds, ntraj, nmd, has_cons, nk8, nkc8, ncpmax, lin_bath;
     long long t0, nsteps;
     double dt;
     const double *kfrag;            // [ntile][nk8 + nkc8][32][2]: all dofs, then the constrained dofs again (nk8, nkc8 multiples of EN_D)
@@ -436,13 +437,18 @@ __global__ void k_build_kfrag(const double *__restrict__ K, int nph, int ld, int
     }
 }
 
-template <int NBATH, int NTILE, bool CONS>
+constexpr int EN_LC = 64;   // largest dense (has_lin) bath the ensemble kernel takes: two outputs per lane
+template <int NBATH, int NTILE, int EN_G, bool CONS, bool LIN>
 __global__ void __launch_bounds__(256, 1) k_md_ens(const EnsArgs a) {
     extern __shared__ __align__(16) double esm[];
     const int nph = a.nph, lds = a.lds;
     double *sp = esm, *sq = sp + EN_T * lds, *sg = sq + EN_T * lds, *sg1 = sg + EN_T * lds;
-    double *snz = sg1 + EN_T * lds;                       // [NBATH][EN_T][ncpmax]: the noise rows of the current slab
+    double *snz = sg1 + EN_T * lds;                       // [nb][EN_T][ncpmax]: the noise rows of the current slab
+    // dense bath (at most one): its matrix part W.[x | q] for evaluations A/B (ml0) and C (ml1), and p^1 on its dofs (mx1)
+    double *slin = snz + (size_t)a.bs.nb * EN_T * a.ncpmax;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    double *ml0 = slin + w * EN_LC, *ml1 = slin + (EN_T + w) * EN_LC, *mx1 = slin + (2 * EN_T + w) * EN_LC;
+    const int bl = a.lin_bath;                            // index of the dense bath or -1
     const int gtraj = blockIdx.x * EN_T + w, ltraj = min(gtraj, a.ntraj - 1);
     const bool live = gtraj < a.ntraj;
     const double dt = a.dt;
@@ -464,6 +470,34 @@ __global__ void __launch_bounds__(256, 1) k_md_ens(const EnsArgs a) {
             }
         cp_async_commit();
     };
+    // out[c] = sum_k W[c][k] [x | q][k] of the dense bath for this warp's trajectory (x: the full-length array, or the
+    // bath-ordered copy mx1 when `compact`); lane l owns outputs l and l + 32, W^T rows are read lane-contiguous
+    auto lin_eval = [&](double *out, const double *xsrc, bool compact) {
+        if (!LIN || bl < 0) return;
+        const BathDev &d = a.bs.b[bl];
+        double o0 = 0.0, o1 = 0.0;
+        for (int k = 0; k < d.Kw; ++k) {
+            const int kk = k < d.ncp ? k : k - d.ncp;
+            double xv = 0.0;
+            if (kk < d.nc) {
+                const int dof = d.cids[kk];
+                xv = k < d.ncp ? (compact ? xsrc[kk] : xsrc[dof]) : mq[dof];
+            }
+            const double *wr = d.wt + (size_t)k * d.ncp;
+            if (lane < d.nc) o0 = fma(wr[lane], xv, o0);
+            if (lane + 32 < d.nc) o1 = fma(wr[lane + 32], xv, o1);
+        }
+        __syncwarp();
+        if (lane < d.nc) out[lane] = o0;
+        if (lane + 32 < d.nc) out[lane + 32] = o1;
+        __syncwarp();
+    };
+    auto bforce = [&](int b, int c, double x, const double *lin) -> double {      // bath_force() of the launch chain, ml = 1
+        double fb = snz[((size_t)b * EN_T + w) * a.ncpmax + c];
+        if (!LIN || a.bs.b[b].diag) fb -= a.bs.b[b].c0 * a.bs.b[b].k0[c] * x;
+        if (LIN && b == bl) fb += lin[c];
+        return fb;
+    };
     load_noise((int)(a.t0 % a.nmd));
     cp_async_wait<0>();
     __syncwarp();
@@ -476,6 +510,7 @@ __global__ void __launch_bounds__(256, 1) k_md_ens(const EnsArgs a) {
             double ke = 0.0, cur[NBATH];
 #pragma unroll
             for (int b = 0; b < NBATH; ++b) cur[b] = 0.0;
+            lin_eval(ml0, mp, false);                            // from (p_t, q_t), before they are overwritten below
             for (int i = lane; i < nph; i += 32) {
                 const double pi = mp[i];
                 double f = -mg[i];
@@ -484,7 +519,7 @@ __global__ void __launch_bounds__(256, 1) k_md_ens(const EnsArgs a) {
                     if (b < a.bs.nb) {
                         const int c = a.bs.b[b].inv[i];
                         if (c >= 0) {
-                            const double fb = snz[((size_t)b * EN_T + w) * a.ncpmax + c] - a.bs.b[b].c0 * a.bs.b[b].k0[c] * pi;
+                            const double fb = bforce(b, c, pi, ml0);
                             cur[b] += fb * pi;
                             f += fb;
                             if (live) a.bs.b[b].ring[((size_t)gtraj * a.bs.b[b].ml + (int)(t % a.bs.b[b].ml)) * a.bs.b[b].ncp + c] = pi;
@@ -509,8 +544,8 @@ __global__ void __launch_bounds__(256, 1) k_md_ens(const EnsArgs a) {
         // ---- K.q' (and the part of it that comes from the constrained dofs): DMMA over fragment-ordered K
         {
             // The K fragments of a tile are ONE stream of nk8 + nkc8 double2 per lane (all dofs, then the constrained ones again);
-            // EN_D of them are in flight per tile (register ring, refilled right after use), for EN_G tiles at a time: the L2
-            // round trip (~1000 cycles under load) is covered by 4 x 5 x 512 bytes per warp.
+            // EN_D of them are in flight per tile (register ring, refilled right after use), for EN_G (4 or 5) tiles at a time:
+            // the L2 round trip (~1000 cycles under load) is covered by 4 x 5 x 512 bytes per warp.
             const double *arowp = sq + arow * lds;
             const int nkt = a.nk8 + a.nkc8;
             const size_t tstride = (size_t)8 * nkt * 32;        // double2 elements between the tiles w + 8 j of this warp
@@ -574,30 +609,67 @@ __global__ void __launch_bounds__(256, 1) k_md_ens(const EnsArgs a) {
         cp_async_wait<0>();
         __syncthreads();
         // ---- evaluations B and C (md.py:401-404), constraint (md.py:407-408)
-        for (int i = lane; i < nph; i += 32) {
-            const double ph = mp[i], g1 = mg1[i];
-            double nz[NBATH], kx[NBATH];
-            bool in[NBATH];
-#pragma unroll
-            for (int b = 0; b < NBATH; ++b) {
-                const int c = b < a.bs.nb ? a.bs.b[b].inv[i] : -1;
-                in[b] = c >= 0;
-                nz[b] = in[b] ? snz[((size_t)b * EN_T + w) * a.ncpmax + c] : 0.0;
-                kx[b] = in[b] ? a.bs.b[b].c0 * a.bs.b[b].k0[c] : 0.0;
-            }
-            double xi = ph, pnew = 0.0;
-#pragma unroll
-            for (int rep = 0; rep < 2; ++rep) {
+        if (LIN && bl >= 0) {
+            // a dense bath couples its dofs, so B and C cannot be chained per element: B gives p^1, kept only on the dense
+            // bath's dofs (mx1); C recomputes p^1 of its own element and adds the matrix part taken at p^1
+            lin_eval(ml0, mp, false);                            // from (p_half, q')
+            auto p_one = [&](int i, double ph, double g1) {
                 double f = -g1;
 #pragma unroll
                 for (int b = 0; b < NBATH; ++b)
-                    if (in[b]) f += nz[b] - kx[b] * xi;
-                pnew = ph + dt * f / 2.0;
-                xi = pnew;
+                    if (b < a.bs.nb) {
+                        const int c = a.bs.b[b].inv[i];
+                        if (c >= 0) f += bforce(b, c, ph, ml0);
+                    }
+                return ph + dt * f / 2.0;
+            };
+            for (int i = lane; i < nph; i += 32) {
+                const int c = a.bs.b[bl].inv[i];
+                if (c >= 0) mx1[c] = p_one(i, mp[i], mg1[i]);
             }
-            const bool fx = CONS && a.cons[i];
-            mp[i] = fx ? 0.0 : pnew;
-            if (fx) mq[i] = 0.0;
+            __syncwarp();
+            lin_eval(ml1, mx1, true);                            // from (p^1, q')
+            for (int i = lane; i < nph; i += 32) {
+                const double ph = mp[i], g1 = mg1[i];
+                const double p1 = p_one(i, ph, g1);
+                double f = -g1;
+#pragma unroll
+                for (int b = 0; b < NBATH; ++b)
+                    if (b < a.bs.nb) {
+                        const int c = a.bs.b[b].inv[i];
+                        if (c >= 0) f += bforce(b, c, p1, ml1);
+                    }
+                const double pnew = ph + dt * f / 2.0;
+                const bool fx = CONS && a.cons[i];
+                mp[i] = fx ? 0.0 : pnew;
+                if (fx) mq[i] = 0.0;
+            }
+        } else {
+            for (int i = lane; i < nph; i += 32) {
+                const double ph = mp[i], g1 = mg1[i];
+                double nz[NBATH], kx[NBATH];
+                bool in[NBATH];
+#pragma unroll
+                for (int b = 0; b < NBATH; ++b) {
+                    const int c = b < a.bs.nb ? a.bs.b[b].inv[i] : -1;
+                    in[b] = c >= 0;
+                    nz[b] = in[b] ? snz[((size_t)b * EN_T + w) * a.ncpmax + c] : 0.0;
+                    kx[b] = in[b] ? a.bs.b[b].c0 * a.bs.b[b].k0[c] : 0.0;
+                }
+                double xi = ph, pnew = 0.0;
+#pragma unroll
+                for (int rep = 0; rep < 2; ++rep) {
+                    double f = -g1;
+#pragma unroll
+                    for (int b = 0; b < NBATH; ++b)
+                        if (in[b]) f += nz[b] - kx[b] * xi;
+                    pnew = ph + dt * f / 2.0;
+                    xi = pnew;
+                }
+                const bool fx = CONS && a.cons[i];
+                mp[i] = fx ? 0.0 : pnew;
+                if (fx) mq[i] = 0.0;
+            }
         }
         __syncwarp();
     }
@@ -1121,6 +1193,7 @@ struct sclmd_md {
             d.has_lin = b.has_lin; d.use_tail = b.ml > 1; d.c0 = b.c0;
             d.inv = b.inv.p; d.cids = b.cids.p; d.k0 = b.kern.p; d.noise = b.noise.p;
             d.tailp = b.tailp.p; d.lin = b.lin.p; d.ring = b.ring.p; d.cur = b.cur.p;
+            d.wt = b.WT.p; d.Kw = b.Kw;
             d.fa = want_f ? b.fa.p : nullptr;
             d.fc = want_f ? b.fc.p : nullptr;
         }
@@ -1320,15 +1393,26 @@ struct sclmd_md {
     DevBuf<int> cidx8;
     int ens_nk8 = 0, ens_nkc8 = 0, ens_ntile = 0;
     bool ens_ok() const {
-        if (!use_persist || !use_ens || ext_force || want_f || profiling || !have_dyn || ntraj <= PS_MAXT || nph > 760 || baths.size() > 2) return false;
-        for (auto &b : baths)
-            if (b->ml > 1 || b->has_lin || b->kind != SCLMD_KERNEL_DIAG) return false;
+        if (!use_persist || !use_ens || ext_force || want_f || profiling || !have_dyn || ntraj <= PS_MAXT || nph > 760 || baths.size() > 4) return false;      // 12 tiles x 8 warps x 8 rows = 768
+        int nlin = 0;
+        for (auto &b : baths) {
+            if (b->ml > 1) return false;
+            if (b->has_lin) {          // one small dense bath (full friction matrix and / or the q-dependent matrices of an ebath)
+                if (++nlin > 1 || b->ncp > EN_LC) return false;
+            } else if (b->kind != SCLMD_KERNEL_DIAG) {
+                return false;
+            }
+        }
         return true;
+    }
+    int ens_lin_bath() const {
+        for (size_t i = 0; i < baths.size(); ++i) if (baths[i]->has_lin) return (int)i;
+        return -1;
     }
     int build_kfrag() {
         ens_nk8 = round_up(cdiv(nph, 8), EN_D);
         const int need = cdiv(cdiv(nph, 8), 8);
-        ens_ntile = need <= 5 ? 5 : need <= 10 ? 10 : 15;
+        ens_ntile = need <= 4 ? 4 : need <= 5 ? 5 : need <= 8 ? 8 : need <= 10 ? 10 : 12;      // tiles per warp: groups of 4 or 5
         ens_nkc8 = 0;
         if (has_cons) {
             std::vector<unsigned char> m(nph);
@@ -1348,7 +1432,7 @@ struct sclmd_md {
         kfrag_valid = true;
         return 0;
     }
-    template <int NTILE>
+    template <int NTILE, int G>
     int launch_ens(const EnsArgs &a, size_t smem) {
         auto go = [&](auto kernel) -> int {
             SCLMD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1356,7 +1440,9 @@ struct sclmd_md {
             SCLMD_CUDA(cudaGetLastError());
             return 0;
         };
-        return has_cons ? go(k_md_ens<2, NTILE, true>) : go(k_md_ens<2, NTILE, false>);
+        if (baths.size() > 2 || ens_lin_bath() >= 0)       // up to four baths, one of them dense
+            return has_cons ? go(k_md_ens<4, NTILE, G, true, true>) : go(k_md_ens<4, NTILE, G, false, true>);
+        return has_cons ? go(k_md_ens<2, NTILE, G, true, false>) : go(k_md_ens<2, NTILE, G, false, false>);
     }
     int run_ens(long long nsteps) {
         if (!kfrag_valid) if (int e = build_kfrag()) return e;
@@ -1385,9 +1471,12 @@ struct sclmd_md {
         for (auto &b : baths) a.ncpmax = std::max(a.ncpmax, b->ncp);
         a.t0 = t; a.nsteps = nsteps; a.dt = dt; a.kfrag = kfrag.p; a.cidx8 = cidx8.p;
         a.q = q.p; a.p = p.p; a.G = G.p; a.cons = cons.p; a.etot = etot.p;
-        const size_t smem = ((size_t)4 * EN_T * a.lds + (size_t)2 * EN_T * a.ncpmax) * sizeof(double);
-        if (smem > 220 * 1024) return 1;                  // caller falls back to the launch chain
-        int e = ens_ntile == 5 ? launch_ens<5>(a, smem) : ens_ntile == 10 ? launch_ens<10>(a, smem) : launch_ens<15>(a, smem);
+        a.lin_bath = ens_lin_bath();
+        const bool wide = baths.size() > 2 || a.lin_bath >= 0;
+        const size_t smem = ((size_t)4 * EN_T * a.lds + (size_t)std::max<size_t>(baths.size(), 1) * EN_T * a.ncpmax + (wide ? 3 * EN_T * EN_LC : 0)) * sizeof(double);
+        if (smem > 226 * 1024) return 1;                  // caller falls back to the launch chain
+        int e = ens_ntile == 4 ? launch_ens<4, 4>(a, smem) : ens_ntile == 5 ? launch_ens<5, 5>(a, smem) : ens_ntile == 8 ? launch_ens<8, 4>(a, smem)
+              : ens_ntile == 10 ? launch_ens<10, 5>(a, smem) : launch_ens<12, 4>(a, smem);
         if (e) return e;
         ++launches;
         t += nsteps;
@@ -1741,6 +1830,11 @@ int sclmd_md_add_bath(sclmd_md *h, const int32_t *cids, int nc, int ml, const do
             }
         SCLMD_CUDA(b->W.alloc(W.size()));
         SCLMD_CUDA(cudaMemcpy(b->W.p, W.data(), W.size() * sizeof(double), cudaMemcpyHostToDevice));
+        std::vector<double> WT((size_t)b->Kw * ncp, 0.0);
+        for (int a = 0; a < nc; ++a)
+            for (int k = 0; k < b->Kw; ++k) WT[(size_t)k * ncp + a] = W[(size_t)a * b->Kw + k];
+        SCLMD_CUDA(b->WT.alloc(WT.size()));
+        SCLMD_CUDA(cudaMemcpy(b->WT.p, WT.data(), WT.size() * sizeof(double), cudaMemcpyHostToDevice));
         SCLMD_CUDA(b->xq.alloc((size_t)ntraj * b->Kw));
         SCLMD_CUDA(b->lin.alloc((size_t)ntraj * ncp));
     }

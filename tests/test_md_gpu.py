@@ -473,3 +473,62 @@ def test_persistent_kernel_equals_launch_chain_and_oracle(ntraj, cons):
     assert relerr(qa, qb) < 1e-12 and relerr(pa, pb) < 1e-12
     for e in engs:
         e.close()
+
+
+@pytest.mark.parametrize("cons", [True, False])
+def test_ensemble_kernel_with_a_dense_bath_equals_launch_chain_and_oracle(cons):
+    """config-4 shape (726 dofs, two scalar-friction electron baths and the biased 36-dof bath with dense friction and
+    non-conservative matrices, all time-local) as an ensemble of 11 trajectories: the ensemble-persistent kernel (dense bath:
+    per-trajectory matrix-vector products inside the kernel, evaluations B and C not chained per element) against the per-step
+    launch chain and the oracle"""
+    from sclmd_b200.engine import MDEngine
+    c = P.md_case_c4_shape()
+    K = P.psd_project(c["K"])
+    nph, dt, nmd, ntraj = K.shape[0], c["dt"], c["nmd"], 11
+    cn = c["cons"] if cons else None
+    lam = P.c4_lambda()
+    damp = 100 / 0.658211814201041
+    kern = [np.full((1, 120), 1.0 / damp), np.full((1, 120), 1.0 / damp), np.array([lam["eta_r"]])]
+    bias = 0.7                                                               # baths.py:245-249: the q- and p-dependent extra forces
+    Mq = [None, None, bias * (lam["xim_r"] - lam["zeta1_r"])]
+    Mp = [None, None, -bias * lam["zeta2_r"]]
+    nz = [P.injected_noise(ntraj, nmd, len(c["cids"][b]), seed=70 + b, sigma=0.003) for b in range(3)]
+    rng = np.random.default_rng(6)
+    q0, p0 = 0.05 * rng.standard_normal((ntraj, nph)), 0.02 * rng.standard_normal((ntraj, nph))
+    if cn:
+        for g in cn:
+            q0[:, g] = 0
+            p0[:, g] = 0
+    ens = O.EnsembleMD(K, dt, nmd, ntraj, cn)
+    engs = []
+    for persist in (True, False):
+        e = MDEngine(nph, ntraj, dt, nmd)
+        e.set_persistent(persist)
+        e.set_dyn(K)
+        if cn:
+            e.set_constraint([i for g in cn for i in g])
+        for b in range(3):
+            e.add_bath(c["cids"][b], kern[b], Mq[b], Mp[b])
+            e.set_noise(b, nz[b])
+        e.set_state(q0, p0, 0)
+        engs.append(e)
+    for b in range(3):
+        if b < 2:
+            ens.add_bath(c["cids"][b], kern[b], nz[b])
+        else:
+            ens.add_bath(c["cids"][b], kern[b], nz[b], bias=bias, exim=lam["xim_r"], zeta1=lam["zeta1_r"], zeta2=lam["zeta2_r"], kind="e")
+    ens.q[:], ens.p[:] = q0, p0
+    done = 0
+    for chunk in (9, 40):                # 49 steps: the slot indices wrap (nmd = 32)
+        ens.run(chunk)
+        done += chunk
+        for e in engs:
+            e.run(chunk)
+            q, p, t = e.get_state()
+            assert t == done and relerr(q, ens.q) < TOL_STEP and relerr(p, ens.p) < TOL_STEP, (done,)
+    assert engs[0].launch_count() < 40 < engs[1].launch_count()
+    for e in engs:
+        assert relerr(e.etot(), ens.etot) < TOL_STEP
+        for b in range(3):
+            assert relerr(e.current(b), ens.baths[b]["cur"]) < TOL_OBS
+        e.close()

@@ -36,4 +36,10 @@ t0 = time.perf_counter()
 ms = m.steps(nsteps)
 wall = time.perf_counter() - t0
 print("c4 shape: ntraj %d, %d steps: device %.3f ms/step, %.3e trajectory-steps/s (wall %.3e)"
-      % (ntraj, nsteps, ms / nsteps, ntraj * nsteps / (ms * 1e-3), ntraj * nsteps / wall))
+      % (ntraj, nsteps, ms / nsteps, ntraj * nsteps / (ms * 1e-3), ntraj * nsteps / wall), file=sys.stderr)
+import json                                            # noqa: E402
+print(json.dumps({"metric": "qtb_md_trajectory_steps_per_s", "value": ntraj * nsteps / (ms * 1e-3), "unit": "trajectory-steps/s",
+                  "ms_per_step": ms / nsteps, "wall_value": ntraj * nsteps / wall, "ntraj": ntraj, "steps": nsteps,
+                  "config": "BASELINE configs[3] shape (examples/current-induced/rundp.py): 726 dofs, 72 fixed, two 120-dof electron "
+                            "baths with scalar friction + the biased 36-dof bath with the example's friction / non-conservative / "
+                            "Berry matrices (tests/golden/c4_lambda.npz), ml = 1, through the md / ebath classes"}))
