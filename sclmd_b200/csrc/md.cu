@@ -89,28 +89,47 @@ __global__ void __launch_bounds__(256, NBATH <= 2 ? 4 : NBATH <= 4 ? 2 : 1) k_ph
     double ke = 0.0, cur[NBATH];
 #pragma unroll
     for (int b = 0; b < NBATH; ++b) cur[b] = 0.0;
-    for (int i = threadIdx.x; i < nph; i += blockDim.x) {
-        const double pi = p[row + i], qi = q[row + i];
-        double gsum = G[row + i];
-        for (int z = 1; z < gsplit; ++z) gsum += G[(size_t)z * gstride + row + i];   // K-slices of K.q, fixed order
-        if (Dcorr) gsum -= Dcorr[row + i];   // K.constrain(q') = K.q' - K[:,c].q'[c]
-        double f = -gsum;
+    // two consecutive elements per thread and trip, moved as 16-byte accesses (rows start 16-byte aligned: ld is even); the
+    // fused kernel k_phase_bca walks the elements the same way, so both produce bit-identical partial sums
+    for (int i0 = 2 * threadIdx.x; i0 < nph; i0 += 2 * blockDim.x) {
+        const double2 p2 = *reinterpret_cast<const double2 *>(p + row + i0), q2 = *reinterpret_cast<const double2 *>(q + row + i0);
+        double2 g2 = *reinterpret_cast<const double2 *>(G + row + i0);
+        for (int z = 1; z < gsplit; ++z) {               // K-slices of K.q, fixed order
+            const double2 v = *reinterpret_cast<const double2 *>(G + (size_t)z * gstride + row + i0);
+            g2.x += v.x;
+            g2.y += v.y;
+        }
+        if (Dcorr) {                                     // K.constrain(q') = K.q' - K[:,c].q'[c]
+            const double2 v = *reinterpret_cast<const double2 *>(Dcorr + row + i0);
+            g2.x -= v.x;
+            g2.y -= v.y;
+        }
+        double2 ph2 = make_double2(0.0, 0.0), qn2 = make_double2(0.0, 0.0);
 #pragma unroll
-        for (int b = 0; b < NBATH; ++b) {
-            if (b < bs.nb) {
-                const int a = bs.b[b].inv[i];
-                if (a >= 0) {
-                    const double fb = bath_force(bs.b[b], traj, ntraj, a, slab, pi);
-                    cur[b] += fb * pi;
-                    f += fb;
-                    if (bs.b[b].fa) bs.b[b].fa[(size_t)traj * bs.b[b].ncp + a] = fb;
-                    bs.b[b].ring[((size_t)traj * bs.b[b].ml + (int)(t % bs.b[b].ml)) * bs.b[b].ncp + a] = pi;
+        for (int e = 0; e < 2; ++e) {
+            const int i = i0 + e;
+            if (i >= nph) break;
+            const double pi = e ? p2.y : p2.x, qi = e ? q2.y : q2.x;
+            double f = -(e ? g2.y : g2.x);
+#pragma unroll
+            for (int b = 0; b < NBATH; ++b) {
+                if (b < bs.nb) {
+                    const int a = bs.b[b].inv[i];
+                    if (a >= 0) {
+                        const double fb = bath_force(bs.b[b], traj, ntraj, a, slab, pi);
+                        cur[b] += fb * pi;
+                        f += fb;
+                        if (bs.b[b].fa) bs.b[b].fa[(size_t)traj * bs.b[b].ncp + a] = fb;
+                        bs.b[b].ring[((size_t)traj * bs.b[b].ml + (int)(t % bs.b[b].ml)) * bs.b[b].ncp + a] = pi;
+                    }
                 }
             }
+            ke += 0.5 * pi * pi;
+            const double phv = pi + f * dt / 2.0, qnv = qi + pi * dt + f * dt * dt / 2.0;
+            if (e) { ph2.y = phv; qn2.y = qnv; } else { ph2.x = phv; qn2.x = qnv; }
         }
-        ke += 0.5 * pi * pi;
-        phalf[row + i] = pi + f * dt / 2.0;
-        qn[row + i] = qi + pi * dt + f * dt * dt / 2.0;
+        *reinterpret_cast<double2 *>(phalf + row + i0) = ph2;
+        *reinterpret_cast<double2 *>(qn + row + i0) = qn2;
     }
     ke = block_sum(ke, red);
     if (threadIdx.x == 0) etot[(size_t)slab * ntraj + traj] = ke;
@@ -187,40 +206,52 @@ __global__ void __launch_bounds__(256, NBATH <= 2 ? 4 : NBATH <= 4 ? 2 : 1) k_ph
     double ke = 0.0, cur[NBATH];
 #pragma unroll
     for (int b = 0; b < NBATH; ++b) cur[b] = 0.0;
-    for (int i = threadIdx.x; i < nph; i += blockDim.x) {
-        const double ph = phalf[row + i];
-        double g = Gn[row + i];
-        for (int z = 1; z < gsplit; ++z) g += Gn[(size_t)z * gstride + row + i];
-        int a[NBATH];
+    for (int i0 = 2 * threadIdx.x; i0 < nph; i0 += 2 * blockDim.x) {      // element pairs, as in k_phase_a
+        const double2 ph2 = *reinterpret_cast<const double2 *>(phalf + row + i0), qv2 = *reinterpret_cast<const double2 *>(qn + row + i0);
+        double2 g2 = *reinterpret_cast<const double2 *>(Gn + row + i0);
+        for (int z = 1; z < gsplit; ++z) {
+            const double2 v = *reinterpret_cast<const double2 *>(Gn + (size_t)z * gstride + row + i0);
+            g2.x += v.x;
+            g2.y += v.y;
+        }
+        double2 pho = make_double2(0.0, 0.0), qno = make_double2(0.0, 0.0);
 #pragma unroll
-        for (int b = 0; b < NBATH; ++b) a[b] = b < bs.nb ? bs.b[b].inv[i] : -1;
-        double xi = ph, pnew = 0.0;
+        for (int e = 0; e < 2; ++e) {
+            const int i = i0 + e;
+            if (i >= nph) break;
+            const double ph = e ? ph2.y : ph2.x, g = e ? g2.y : g2.x, qv = e ? qv2.y : qv2.x;
+            int a[NBATH];
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {                  // evaluations B and C (md.py:401-404)
+            for (int b = 0; b < NBATH; ++b) a[b] = b < bs.nb ? bs.b[b].inv[i] : -1;
+            double xi = ph, pnew = 0.0;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {                  // evaluations B and C (md.py:401-404)
+                double f = -g;
+#pragma unroll
+                for (int b = 0; b < NBATH; ++b)
+                    if (a[b] >= 0) f += bath_force(bs.b[b], traj, ntraj, a[b], slab, xi);
+                pnew = ph + dt * f / 2.0;
+                xi = pnew;
+            }
+            // (p_{t+1}, q_{t+1}) = (pnew, qv) are not stored: the only consumers of the state arrays are flush() and the unfused
+            // kernels, and a flush recomputes the then-current state from phalf / qn.  Two array passes less per step.
+            // evaluation A of step t+1 (md.py:383-398) at (p_{t+1}, q_{t+1}) = (pnew, qv); K.q_{t+1} = K.q' without constraints
             double f = -g;
 #pragma unroll
-            for (int b = 0; b < NBATH; ++b)
-                if (a[b] >= 0) f += bath_force(bs.b[b], traj, ntraj, a[b], slab, xi);
-            pnew = ph + dt * f / 2.0;
-            xi = pnew;
-        }
-        const double qv = qn[row + i];
-        // (p_{t+1}, q_{t+1}) = (pnew, qv) are not stored: the only consumers of the state arrays are flush() and the unfused
-        // kernels, and a flush recomputes the then-current state from phalf / qn.  Two array passes less per step.
-        // evaluation A of step t+1 (md.py:383-398) at (p_{t+1}, q_{t+1}) = (pnew, qv); K.q_{t+1} = K.q' without constraints
-        double f = -g;
-#pragma unroll
-        for (int b = 0; b < NBATH; ++b) {
-            if (a[b] >= 0) {
-                const double fb = bath_force(bs.b[b], traj, ntraj, a[b], slab, pnew);
-                cur[b] += fb * pnew;
-                f += fb;
-                bs.b[b].ring[((size_t)traj * bs.b[b].ml + (int)((t + 1) % bs.b[b].ml)) * bs.b[b].ncp + a[b]] = pnew;
+            for (int b = 0; b < NBATH; ++b) {
+                if (a[b] >= 0) {
+                    const double fb = bath_force(bs.b[b], traj, ntraj, a[b], slab, pnew);
+                    cur[b] += fb * pnew;
+                    f += fb;
+                    bs.b[b].ring[((size_t)traj * bs.b[b].ml + (int)((t + 1) % bs.b[b].ml)) * bs.b[b].ncp + a[b]] = pnew;
+                }
             }
+            ke += 0.5 * pnew * pnew;
+            const double phv = pnew + f * dt / 2.0, qnv = qv + pnew * dt + f * dt * dt / 2.0;
+            if (e) { pho.y = phv; qno.y = qnv; } else { pho.x = phv; qno.x = qnv; }
         }
-        ke += 0.5 * pnew * pnew;
-        phalf[row + i] = pnew + f * dt / 2.0;
-        qn[row + i] = qv + pnew * dt + f * dt * dt / 2.0;
+        *reinterpret_cast<double2 *>(phalf + row + i0) = pho;
+        *reinterpret_cast<double2 *>(qn + row + i0) = qno;
     }
     ke = block_sum(ke, red);
     if (threadIdx.x == 0) etot[(size_t)slab * ntraj + traj] = ke;
@@ -551,27 +582,35 @@ __global__ void __launch_bounds__(256, 1) k_md_ens(const EnsArgs a) {
             const size_t tstride = (size_t)8 * nkt * 32;        // double2 elements between the tiles w + 8 j of this warp
 #pragma unroll 1
             for (int g0 = 0; g0 < NTILE; g0 += EN_G) {
-                double acc[EN_G][2], accc[EN_G][2];
+                // two accumulators per tile (even / odd half of a k-block): 2 EN_G independent DMMA chains per warp -- with two
+                // warps per scheduler the tensor pipe needs that many to stay busy; the A operands are fetched one block ahead
+                double acc[2][EN_G][2], accc[2][EN_G][2];
 #pragma unroll
-                for (int j = 0; j < EN_G; ++j) acc[j][0] = acc[j][1] = accc[j][0] = accc[j][1] = 0.0;
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int j = 0; j < EN_G; ++j) acc[h][j][0] = acc[h][j][1] = accc[h][j][0] = accc[h][j][1] = 0.0;
                 const double2 *kb = reinterpret_cast<const double2 *>(a.kfrag) + ((size_t)(w + 8 * g0) * nkt) * 32 + lane;
                 double2 bn[EN_D][EN_G];
 #pragma unroll
                 for (int d = 0; d < EN_D; ++d)
 #pragma unroll
                     for (int j = 0; j < EN_G; ++j) bn[d][j] = __ldg(kb + j * tstride + (size_t)d * 32);
+                double a0 = arowp[aslot], a1 = arowp[4 + aslot];
                 for (int ks = 0; ks < a.nk8; ks += EN_D) {      // nk8, nkc8 are multiples of EN_D
 #pragma unroll
                     for (int d = 0; d < EN_D; ++d) {
-                        const double a0 = arowp[8 * (ks + d) + aslot], a1 = arowp[8 * (ks + d) + 4 + aslot];
+                        const int nx = min(ks + d + 1, a.nk8 - 1);
+                        const double n0 = arowp[8 * nx + aslot], n1 = arowp[8 * nx + 4 + aslot];
 #pragma unroll
-                        for (int j = 0; j < EN_G; ++j) dmma884(acc[j][0], acc[j][1], a0, bn[d][j].x);      // EN_G independent chains
+                        for (int j = 0; j < EN_G; ++j) dmma884(acc[0][j][0], acc[0][j][1], a0, bn[d][j].x);
 #pragma unroll
-                        for (int j = 0; j < EN_G; ++j) dmma884(acc[j][0], acc[j][1], a1, bn[d][j].y);
+                        for (int j = 0; j < EN_G; ++j) dmma884(acc[1][j][0], acc[1][j][1], a1, bn[d][j].y);
                         if (ks + d + EN_D < nkt) {
 #pragma unroll
                             for (int j = 0; j < EN_G; ++j) bn[d][j] = __ldg(kb + j * tstride + (size_t)(ks + d + EN_D) * 32);
                         }
+                        a0 = n0;
+                        a1 = n1;
                     }
                 }
                 if (CONS) {
@@ -579,11 +618,11 @@ __global__ void __launch_bounds__(256, 1) k_md_ens(const EnsArgs a) {
 #pragma unroll
                         for (int d = 0; d < EN_D; ++d) {
                             const int c0 = a.cidx8[8 * (ks + d) + aslot], c1 = a.cidx8[8 * (ks + d) + 4 + aslot];
-                            const double a0 = c0 >= 0 ? arowp[c0] : 0.0, a1 = c1 >= 0 ? arowp[c1] : 0.0;
+                            const double x0 = c0 >= 0 ? arowp[c0] : 0.0, x1 = c1 >= 0 ? arowp[c1] : 0.0;
 #pragma unroll
-                            for (int j = 0; j < EN_G; ++j) dmma884(accc[j][0], accc[j][1], a0, bn[d][j].x);
+                            for (int j = 0; j < EN_G; ++j) dmma884(accc[0][j][0], accc[0][j][1], x0, bn[d][j].x);
 #pragma unroll
-                            for (int j = 0; j < EN_G; ++j) dmma884(accc[j][0], accc[j][1], a1, bn[d][j].y);
+                            for (int j = 0; j < EN_G; ++j) dmma884(accc[1][j][0], accc[1][j][1], x1, bn[d][j].y);
                             if (a.nk8 + ks + d + EN_D < nkt) {
 #pragma unroll
                                 for (int j = 0; j < EN_G; ++j) bn[d][j] = __ldg(kb + j * tstride + (size_t)(a.nk8 + ks + d + EN_D) * 32);
@@ -595,13 +634,15 @@ __global__ void __launch_bounds__(256, 1) k_md_ens(const EnsArgs a) {
 #pragma unroll
                 for (int j = 0; j < EN_G; ++j) {
                     const int n = 8 * (w + 8 * (g0 + j)) + 2 * aslot;
+                    const double v0 = acc[0][j][0] + acc[1][j][0], v1 = acc[0][j][1] + acc[1][j][1];
+                    const double c0 = accc[0][j][0] + accc[1][j][0], c1 = accc[0][j][1] + accc[1][j][1];
                     if (n < nph) {
-                        sg1[arow * lds + n] = acc[j][0];
-                        sg[arow * lds + n] = acc[j][0] - accc[j][0];
+                        sg1[arow * lds + n] = v0;
+                        sg[arow * lds + n] = v0 - c0;
                     }
                     if (n + 1 < nph) {
-                        sg1[arow * lds + n + 1] = acc[j][1];
-                        sg[arow * lds + n + 1] = acc[j][1] - accc[j][1];
+                        sg1[arow * lds + n + 1] = v1;
+                        sg[arow * lds + n + 1] = v1 - c1;
                     }
                 }
             }
