@@ -32,7 +32,8 @@ import problems as P  # noqa: E402
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=32)
+    ap.add_argument("--steps", type=int, default=128,
+                    help="timed steps (default 128 = 8 time blocks, ~0.12 s: long against one nvidia-smi clock sample, which can stall the GPU for ~2 ms)")
     ap.add_argument("--warmup", type=int, default=16)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c5_diag", choices=["c5_diag", "c5_full", "c2"])
@@ -96,13 +97,14 @@ class ClockSampler(threading.Thread):
         except Exception:
             pass
 
-    def stop(self):
+    def stop(self, first=0):
+        """summary of the samples taken from row `first` on (the timed region)"""
         if self.proc:
             self.proc.terminate()
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         sm = []
         reasons = set()
-        for r in self.rows:
+        for r in (self.rows[first:] or self.rows):
             try:
                 sm.append(float(r[1]))
                 out["sm_max_mhz"] = float(r[2])
@@ -112,8 +114,7 @@ class ClockSampler(threading.Thread):
             except Exception:
                 continue
         if sm:
-            hot = sorted(sm)[len(sm) // 2:]           # samples under load dominate the upper half
-            out["sm_mhz"] = float(np.median(hot))
+            out["sm_mhz"] = float(np.median(sm))
             out["samples"] = len(sm)
         out["reasons"] = sorted(reasons)
         return out
@@ -355,7 +356,24 @@ def main():
     # steps), so K steps contain ceil(K/16) passes -- exact for multiples of 16, pessimistic otherwise, never optimistic.
     TBLK = 16
     W_aligned = W + (-W) % TBLK
+    # clock sampling (nvidia-smi, one sample per 100 ms) starts before the warm-up and the warm-up is extended (whole time blocks)
+    # until the first sample has arrived, so that the timed region is guaranteed to contain samples taken under load
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     eng.run(W_aligned)
+    if rank == 0:
+        t_wait = time.perf_counter()
+        while not sampler.rows and time.perf_counter() - t_wait < 5.0:
+            eng.run(TBLK)
+            W_aligned += TBLK
+    if world > 1:                                            # every rank runs the same number of warm-up steps
+        wa = torch.tensor([W_aligned], dtype=torch.int64, device="cuda")
+        dist.all_reduce(wa, op=dist.ReduceOp.MAX)
+        extra = int(wa[0]) - W_aligned
+        if extra > 0:
+            eng.run(extra)
+            W_aligned += extra
     # Per-kernel CUDA events (the roofline block) are recorded inside the timed region when the step is a launch chain anyway
     # (baths with history tails).  A step without tails replays a CUDA graph, which per-kernel events would switch off: there
     # the timed region runs unprofiled and the same K steps are repeated once with events for the roofline block.
@@ -363,11 +381,8 @@ def main():
     if prof_in_region:
         eng.set_profiling(True)
     l0 = eng.launch_count()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
     barrier()
+    n_rows0 = len(sampler.rows)
     t_wall = time.perf_counter()
     ms = eng.run(K)                                          # CUDA events on the engine's stream
     sums = np.array([eng.current_sums(b).sum() for b in range(2)] + [float(ntraj)])
@@ -390,7 +405,11 @@ def main():
         ms_prof = eng.run(K)
     prof_all = eng.profile_all()
     eng.set_profiling(False)
-    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0 and len(sampler.rows) == n_rows0:          # a region shorter than the sampling period: take the next sample under load
+        t_wait = time.perf_counter()
+        while len(sampler.rows) == n_rows0 and time.perf_counter() - t_wait < 1.0:
+            eng.run(TBLK)
+    clocks = sampler.stop(n_rows0) if rank == 0 else None
     tot = torch.tensor([ms + ar_ms, float(launches)], dtype=torch.float64, device="cuda")
     if world > 1:
         mx = tot.clone()
@@ -528,7 +547,7 @@ def main():
     # ---------------- BASELINE configs[1] shape (603-dof junction of the example, ml = 1 baths, fixed ends, 1024 trajectories)
     if world == 1 and not args.no_also and args.workload != "c2":
         try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", "c2", "--steps", "64", "--warmup", "16",
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", "c2", "--steps", "1024", "--warmup", "16",
                                 "--no-also", "--no-cpu-baseline"], capture_output=True, text=True, timeout=600)
             c2 = json.loads(r.stdout.strip().splitlines()[-1])
             line["also_md_config2"] = {k: c2[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "gpu_launches", "config")}
