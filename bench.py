@@ -285,7 +285,7 @@ def negf_also(rank, world, local, barrier, fp64_peak_tflops=None):
         gf = C.c_double(0.0)
         _lib.check(L.sclmd_bpt_get_profile(ms, n, C.byref(gf), C.byref(dev_ms)))
         _lib.check(L.sclmd_bpt_set_profiling(0))
-        names = ["k_build", "k_panel", "k_gemm (rank-16, panel columns)", "k_block_trsm", "k_gemm (rank-64 trailing update)", "k_backsub", "k_observe"]
+        names = ["k_build", "k_panel", "k_gemm (rank-16, panel columns)", "k_block_trsm", "k_gemm (rank-64 trailing update)", "back substitution (k_block_trsm_upper + k_gemm)", "k_observe"]
         tot = sum(ms)
         peak = fp64_peak_tflops or 37.1
         ach = gf.value / (ms[4] * 1e-3) / 1e12 if ms[4] > 0 else None
