@@ -79,3 +79,52 @@ def phbath_from_sig(s, direction, T, cats, nw, dt, nmd, ml, mcof=2.0, debye=None
         debye = float(gwl[-1]) / mcof
     return phbath(T, cats, debye, nw, dt, nmd, ml=ml, mcof=mcof, sig=sig_md, gwl=gwl, eta_ad=eta_ad, classical=classical,
                   zpmotion=zpmotion)
+
+
+def get_atomname(mass):
+    """tools.py:218-226: element whose tabulated mass lies within 0.01 amu of `mass` (None if there is none)"""
+    from . import units as U
+    for name, m in U.AtomicMassTable.items():
+        if abs(mass - m) < 0.01:
+            return name
+    return None
+
+
+def get_atommass(name):
+    """tools.py:229-237: tabulated mass of an element (None for an unknown name)"""
+    from . import units as U
+    return U.AtomicMassTable.get(name)
+
+
+def eff(dynmatfilename='dynmat.dat'):
+    """tools.py:240-259, 'eliminate false frequencies': symmetrise the dynamical matrix of the text file, set negative eigenvalues
+    to zero and rebuild, until none is left; writes 'mod<file>' and returns the matrix"""
+    dat = np.loadtxt(dynmatfilename)
+    n = int(3 * np.sqrt(len(dat) / 3))
+    dyn = dat.reshape((n, n))
+    dyn = (dyn + dyn.T) / 2
+    w, v = np.linalg.eigh(dyn)
+    while not (w > 0).all():
+        for i in np.nonzero(w < 0)[0]:
+            print('False frequency exists in system DOF %i ' % i)
+        w = np.where(w < 0, 0.0, w)
+        dyn = (v * w) @ np.linalg.inv(v)
+        dyn = (dyn + dyn.T) / 2
+        w, v = np.linalg.eigh(dyn)
+    np.savetxt('mod' + dynmatfilename, dyn)
+    return dyn
+
+
+def avdf(dffiles=["deltaforce.run0.npy"], outputname="deltaforce", abs=False):
+    """tools.py:7-32: running mean and standard deviation of the force differences md.CompareForce recorded
+    (deltaforce.run<j>.npy), over the first 1, 2, ... files; writes <outputname>-mean<i>.dat and -deviation<i>.dat"""
+    chunks = [np.load(f) for f in dffiles]
+    per = len(chunks[0])
+    allv = np.concatenate(chunks, axis=0)
+    if abs:
+        allv = np.abs(allv)
+    for i in range(len(dffiles)):
+        part = allv[0:int((i + 1) * per)]
+        mean = np.mean(part, axis=0)
+        np.savetxt(outputname + "-mean" + str(i) + ".dat", mean)
+        np.savetxt(outputname + "-deviation" + str(i) + ".dat", np.sqrt(np.mean((part - mean) ** 2, axis=0)))

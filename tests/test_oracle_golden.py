@@ -247,3 +247,27 @@ def test_myio_readers_match_the_reference(tmp_path, golden_dir):
     assert np.array_equal(myio.ord2idx([3, 1, 2]), g["ord2idx"])
     with pytest.raises(ValueError):
         myio.ReadDynmat(str(tmp_path / "ph.nc"), [1, 2, 3])
+
+
+def test_small_tools(tmp_path, monkeypatch):
+    """tools.get_atomname / get_atommass / eff / avdf (tools.py:7-32, 218-259) against their definitions"""
+    from sclmd_b200 import tools as T
+    monkeypatch.chdir(tmp_path)
+    assert T.get_atommass("C") == 12.0107 and T.get_atomname(12.011) == "C" and T.get_atomname(196.97) == "Au"
+    assert T.get_atommass("Xx") is None and T.get_atomname(500.0) is None
+    rng = np.random.default_rng(4)
+    a = rng.standard_normal((6, 6))
+    dyn = a @ a.T - 0.8 * np.eye(6)                              # one or two negative eigenvalues
+    assert (np.linalg.eigvalsh(dyn) < 0).any()
+    np.savetxt("dynmat.dat", (dyn + 1e-3 * rng.standard_normal((6, 6))).reshape(-1, 3))
+    out = T.eff("dynmat.dat")
+    w = np.linalg.eigvalsh(out)
+    assert np.allclose(out, out.T) and w.min() > -1e-12 and np.allclose(np.loadtxt("moddynmat.dat"), out)
+    f0, f1 = rng.standard_normal((5, 4)), rng.standard_normal((5, 4))
+    np.save("deltaforce.run0.npy", f0)
+    np.save("deltaforce.run1.npy", f1)
+    T.avdf(["deltaforce.run0.npy", "deltaforce.run1.npy"], outputname="df", abs=True)
+    both = np.abs(np.concatenate((f0, f1)))
+    assert np.allclose(np.loadtxt("df-mean0.dat"), np.abs(f0).mean(axis=0))
+    assert np.allclose(np.loadtxt("df-mean1.dat"), both.mean(axis=0))
+    assert np.allclose(np.loadtxt("df-deviation1.dat"), both.std(axis=0))
