@@ -11,8 +11,11 @@ from ._lib import as_f64, as_i32, check, dptr, iptr
 
 class bpt:
     def __init__(self, infile, maxomega, damp, dofatomofbath, dofatomfixed=[[], []], dynmatfile=None, num=1000,
-                 natoms=None, device=0):
+                 natoms=None, device=0, write_files=None):
         self.rpc = 6.582119569e-4     # reduced Planck constant, eV*ps
+        # falsefrequencies.dat / omegas.dat / eigvecs.dat in the working directory (negf.py:100-102): by default whenever the
+        # dynamical matrix comes from a file, as in the reference's flow; not when the caller hands over an array
+        self.write_files = (not isinstance(dynmatfile, np.ndarray)) if write_files is None else bool(write_files)
         self.bc = 8.617333262e-5      # Boltzmann constant, eV/K
         self.damp = damp              # ps
         self.maxomega = maxomega / self.rpc
@@ -85,6 +88,12 @@ class bpt:
             raise ValueError('System DOF test failed, check again')
         eigvals, self.eigvecs = np.linalg.eigh(self.dynmat)
         self.omegas = [np.sqrt(v) * self.rpc if v > 0 else -np.sqrt(-v) * self.rpc for v in eigvals]
+        ffi = [i for i, v in enumerate(eigvals) if not v > 0]
+        print('%i false frequencies exist in %i frequencies' % (len(ffi), len(self.omegas)))
+        if self.write_files:                              # negf.py:100-102
+            np.savetxt('falsefrequencies.dat', ffi, fmt='%d')
+            np.savetxt('omegas.dat', self.omegas)
+            np.savetxt('eigvecs.dat', self.eigvecs)
 
     def _reduced(self, dofs):
         """negf.py:195-204: bath dofs are in the unreduced 3N numbering; the leading fixed block is removed"""

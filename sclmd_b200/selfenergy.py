@@ -34,6 +34,18 @@ class sig:
             dynlen = int(3 * np.sqrt(len(dat) / 3))
             self.dynmat = dat.reshape((dynlen, dynlen))
         self.natoms = self.dynmat.shape[0] // 3
+        # frequencies of the system without its fixed dofs (selfenergy.py:66-91); the three text files are written whenever the
+        # matrix comes from a file, as in the reference's flow
+        fixed = list(self.dofatomfixed[0]) + list(self.dofatomfixed[1])
+        red = np.delete(np.delete(self.dynmat, fixed, axis=0), fixed, axis=1)
+        eigvals, eigvecs = np.linalg.eigh(red)
+        self.omegas = [np.sqrt(v) * self.rpc if v > 0 else -np.sqrt(-v) * self.rpc for v in eigvals]
+        ffi = [i for i, v in enumerate(eigvals) if not v > 0]
+        print('%i false frequencies exist in %i frequencies' % (len(ffi), len(self.omegas)))
+        if not isinstance(self.dynmatfile, np.ndarray):
+            np.savetxt('falsefrequencies.dat', ffi, fmt='%d')
+            np.savetxt('omegas.dat', self.omegas)
+            np.savetxt('eigvecs.dat', eigvecs)
 
     def getdk(self):
         """selfenergy.py:93-103"""

@@ -271,3 +271,30 @@ def test_small_tools(tmp_path, monkeypatch):
     assert np.allclose(np.loadtxt("df-mean0.dat"), np.abs(f0).mean(axis=0))
     assert np.allclose(np.loadtxt("df-mean1.dat"), both.mean(axis=0))
     assert np.allclose(np.loadtxt("df-deviation1.dat"), both.std(axis=0))
+
+
+def test_bpt_and_sig_write_the_reference_frequency_files(tmp_path, monkeypatch):
+    """negf.py:92-102 / selfenergy.py:76-91: omegas.dat (signed sqrt of the eigenvalues times hbar), eigvecs.dat and
+    falsefrequencies.dat appear when the dynamical matrix is loaded from a file (host code, no device needed)"""
+    from sclmd_b200.negf import bpt
+    from sclmd_b200.selfenergy import sig
+    monkeypatch.chdir(tmp_path)
+    K = P.spring_chain_dyn(12, seed=80)
+    K[5, 5] -= 3.0 * abs(K[5, 5])                                              # force a false (imaginary) frequency
+    K = 0.5 * (K + K.T)
+    np.savetxt("dyn.dat", K.reshape(-1, 3))
+    fixed = [list(range(0, 3)), list(range(33, 36))]
+    b = bpt(None, 0.25, 0.1, [list(range(3, 12)), list(range(24, 33))], fixed, dynmatfile="dyn.dat", num=4)
+    red = np.delete(np.delete(K, fixed[0] + fixed[1], axis=0), fixed[0] + fixed[1], axis=1)
+    w = np.linalg.eigvalsh(red)
+    want = np.where(w > 0, np.sqrt(np.abs(w)), -np.sqrt(np.abs(w))) * b.rpc
+    assert np.allclose(np.loadtxt("omegas.dat"), want) and np.allclose(b.omegas, want)
+    assert np.loadtxt("eigvecs.dat").shape == (30, 30)
+    assert list(np.atleast_1d(np.loadtxt("falsefrequencies.dat", dtype=int))) == list(np.nonzero(~(w > 0))[0])
+    for f in ("omegas.dat", "eigvecs.dat", "falsefrequencies.dat"):
+        os.remove(f)
+    s = sig(None, 0.06, range(3, 12), range(12, 21), dofatomfixed=fixed, dynmatfile="dyn.dat", num=4, eta=1e-3)
+    assert np.allclose(np.loadtxt("omegas.dat"), want * s.rpc / b.rpc) and os.path.exists("eigvecs.dat")
+    os.remove("omegas.dat")
+    bpt(None, 0.25, 0.1, [list(range(3, 12)), list(range(24, 33))], fixed, dynmatfile=K, num=4)   # array in: nothing written
+    assert not os.path.exists("omegas.dat")
