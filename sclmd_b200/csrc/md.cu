@@ -469,22 +469,27 @@ __global__ void k_build_kfrag(const double *__restrict__ K, int nph, int ld, int
 }
 
 constexpr int EN_LC = 64;   // largest dense (has_lin) bath the ensemble kernel takes: two outputs per lane
-template <int NBATH, int NTILE, int EN_G, bool CONS, bool LIN>
-__global__ void __launch_bounds__(256, 1) k_md_ens(const EnsArgs a) {
+// EN_W warps per CTA: the first EN_T own a trajectory each in the elementwise phases, all of them share the DMMA product (sixteen
+// warps = four per scheduler hide the latency of the DMMA / operand chains that eight leave exposed; 128 registers per thread then)
+template <int NBATH, int NTILE, int EN_G, bool CONS, bool LIN, int EN_W>
+__global__ void __launch_bounds__(EN_W * 32, 1) k_md_ens(const EnsArgs a) {
     extern __shared__ __align__(16) double esm[];
     const int nph = a.nph, lds = a.lds;
     double *sp = esm, *sq = sp + EN_T * lds, *sg = sq + EN_T * lds, *sg1 = sg + EN_T * lds;
     double *snz = sg1 + EN_T * lds;                       // [nb][EN_T][ncpmax]: the noise rows of the current slab
     // dense bath (at most one): its matrix part W.[x | q] for evaluations A/B (ml0) and C (ml1), and p^1 on its dofs (mx1)
     double *slin = snz + (size_t)a.bs.nb * EN_T * a.ncpmax;
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, wg = tid >> 5;       // wg: warp in the product
+    const bool own = wg < EN_T;                                          // this warp owns trajectory w in the elementwise phases
+    const int w = own ? wg : 0;
+    constexpr int ED = EN_W == 8 ? EN_D : 2;                             // fragment pairs in flight per tile
     double *ml0 = slin + w * EN_LC, *ml1 = slin + (EN_T + w) * EN_LC, *mx1 = slin + (2 * EN_T + w) * EN_LC;
     const int bl = a.lin_bath;                            // index of the dense bath or -1
     const int gtraj = blockIdx.x * EN_T + w, ltraj = min(gtraj, a.ntraj - 1);
     const bool live = gtraj < a.ntraj;
     const double dt = a.dt;
     double *mp = sp + w * lds, *mq = sq + w * lds, *mg = sg + w * lds, *mg1 = sg1 + w * lds;
-    for (int i = lane; i < lds; i += 32) {
+    for (int i = lane; own && i < lds; i += 32) {
         const bool ok = i < nph;
         mp[i] = ok ? a.p[(size_t)ltraj * a.ld + i] : 0.0;
         mq[i] = ok ? a.q[(size_t)ltraj * a.ld + i] : 0.0;
@@ -529,7 +534,7 @@ __global__ void __launch_bounds__(256, 1) k_md_ens(const EnsArgs a) {
         if (LIN && b == bl) fb += lin[c];
         return fb;
     };
-    load_noise((int)(a.t0 % a.nmd));
+    if (own) load_noise((int)(a.t0 % a.nmd));
     cp_async_wait<0>();
     __syncwarp();
     const int arow = lane >> 2, aslot = lane & 3;
@@ -537,7 +542,7 @@ __global__ void __launch_bounds__(256, 1) k_md_ens(const EnsArgs a) {
         const long long t = a.t0 + s;
         const int slab = (int)(t % a.nmd);
         // ---- evaluation A (md.py:383-398) of this warp's trajectory
-        {
+        if (own) {
             double ke = 0.0, cur[NBATH];
 #pragma unroll
             for (int b = 0; b < NBATH; ++b) cur[b] = 0.0;
@@ -570,7 +575,7 @@ __global__ void __launch_bounds__(256, 1) k_md_ens(const EnsArgs a) {
                 }
         }
         __syncwarp();
-        load_noise((int)((t + 1) % a.nmd));               // evaluations B, C and the next evaluation A read slab t+1
+        if (own) load_noise((int)((t + 1) % a.nmd));      // evaluations B, C and the next evaluation A read slab t+1
         __syncthreads();                                  // q' of all eight trajectories is in place
         // ---- K.q' (and the part of it that comes from the constrained dofs): DMMA over fragment-ordered K
         {
@@ -579,7 +584,7 @@ __global__ void __launch_bounds__(256, 1) k_md_ens(const EnsArgs a) {
             // the L2 round trip (~1000 cycles under load) is covered by 4 x 5 x 512 bytes per warp.
             const double *arowp = sq + arow * lds;
             const int nkt = a.nk8 + a.nkc8;
-            const size_t tstride = (size_t)8 * nkt * 32;        // double2 elements between the tiles w + 8 j of this warp
+            const size_t tstride = (size_t)EN_W * nkt * 32;     // double2 elements between the tiles wg + EN_W j of this warp
 #pragma unroll 1
             for (int g0 = 0; g0 < NTILE; g0 += EN_G) {
                 // two accumulators per tile (even / odd half of a k-block): 2 EN_G independent DMMA chains per warp -- with two
@@ -589,43 +594,43 @@ __global__ void __launch_bounds__(256, 1) k_md_ens(const EnsArgs a) {
                 for (int h = 0; h < 2; ++h)
 #pragma unroll
                     for (int j = 0; j < EN_G; ++j) acc[h][j][0] = acc[h][j][1] = accc[h][j][0] = accc[h][j][1] = 0.0;
-                const double2 *kb = reinterpret_cast<const double2 *>(a.kfrag) + ((size_t)(w + 8 * g0) * nkt) * 32 + lane;
-                double2 bn[EN_D][EN_G];
+                const double2 *kb = reinterpret_cast<const double2 *>(a.kfrag) + ((size_t)(wg + EN_W * g0) * nkt) * 32 + lane;
+                double2 bn[ED][EN_G];
 #pragma unroll
-                for (int d = 0; d < EN_D; ++d)
+                for (int d = 0; d < ED; ++d)
 #pragma unroll
                     for (int j = 0; j < EN_G; ++j) bn[d][j] = __ldg(kb + j * tstride + (size_t)d * 32);
                 double a0 = arowp[aslot], a1 = arowp[4 + aslot];
-                for (int ks = 0; ks < a.nk8; ks += EN_D) {      // nk8, nkc8 are multiples of EN_D
+                for (int ks = 0; ks < a.nk8; ks += ED) {        // nk8, nkc8 are multiples of EN_D (and of ED)
 #pragma unroll
-                    for (int d = 0; d < EN_D; ++d) {
+                    for (int d = 0; d < ED; ++d) {
                         const int nx = min(ks + d + 1, a.nk8 - 1);
                         const double n0 = arowp[8 * nx + aslot], n1 = arowp[8 * nx + 4 + aslot];
 #pragma unroll
                         for (int j = 0; j < EN_G; ++j) dmma884(acc[0][j][0], acc[0][j][1], a0, bn[d][j].x);
 #pragma unroll
                         for (int j = 0; j < EN_G; ++j) dmma884(acc[1][j][0], acc[1][j][1], a1, bn[d][j].y);
-                        if (ks + d + EN_D < nkt) {
+                        if (ks + d + ED < nkt) {
 #pragma unroll
-                            for (int j = 0; j < EN_G; ++j) bn[d][j] = __ldg(kb + j * tstride + (size_t)(ks + d + EN_D) * 32);
+                            for (int j = 0; j < EN_G; ++j) bn[d][j] = __ldg(kb + j * tstride + (size_t)(ks + d + ED) * 32);
                         }
                         a0 = n0;
                         a1 = n1;
                     }
                 }
                 if (CONS) {
-                    for (int ks = 0; ks < a.nkc8; ks += EN_D) {
+                    for (int ks = 0; ks < a.nkc8; ks += ED) {
 #pragma unroll
-                        for (int d = 0; d < EN_D; ++d) {
+                        for (int d = 0; d < ED; ++d) {
                             const int c0 = a.cidx8[8 * (ks + d) + aslot], c1 = a.cidx8[8 * (ks + d) + 4 + aslot];
                             const double x0 = c0 >= 0 ? arowp[c0] : 0.0, x1 = c1 >= 0 ? arowp[c1] : 0.0;
 #pragma unroll
                             for (int j = 0; j < EN_G; ++j) dmma884(accc[0][j][0], accc[0][j][1], x0, bn[d][j].x);
 #pragma unroll
                             for (int j = 0; j < EN_G; ++j) dmma884(accc[1][j][0], accc[1][j][1], x1, bn[d][j].y);
-                            if (a.nk8 + ks + d + EN_D < nkt) {
+                            if (a.nk8 + ks + d + ED < nkt) {
 #pragma unroll
-                                for (int j = 0; j < EN_G; ++j) bn[d][j] = __ldg(kb + j * tstride + (size_t)(a.nk8 + ks + d + EN_D) * 32);
+                                for (int j = 0; j < EN_G; ++j) bn[d][j] = __ldg(kb + j * tstride + (size_t)(a.nk8 + ks + d + ED) * 32);
                             }
                         }
                     }
@@ -633,7 +638,7 @@ __global__ void __launch_bounds__(256, 1) k_md_ens(const EnsArgs a) {
                 // D[traj = lane / 4][n = 8 tile + 2 (lane % 4) + {0, 1}]; sg (K.q of the step just evaluated) is free again
 #pragma unroll
                 for (int j = 0; j < EN_G; ++j) {
-                    const int n = 8 * (w + 8 * (g0 + j)) + 2 * aslot;
+                    const int n = 8 * (wg + EN_W * (g0 + j)) + 2 * aslot;
                     const double v0 = acc[0][j][0] + acc[1][j][0], v1 = acc[0][j][1] + acc[1][j][1];
                     const double c0 = accc[0][j][0] + accc[1][j][0], c1 = accc[0][j][1] + accc[1][j][1];
                     if (n < nph) {
@@ -650,7 +655,8 @@ __global__ void __launch_bounds__(256, 1) k_md_ens(const EnsArgs a) {
         cp_async_wait<0>();
         __syncthreads();
         // ---- evaluations B and C (md.py:401-404), constraint (md.py:407-408)
-        if (LIN && bl >= 0) {
+        if (!own) {
+        } else if (LIN && bl >= 0) {
             // a dense bath couples its dofs, so B and C cannot be chained per element: B gives p^1, kept only on the dense
             // bath's dofs (mx1); C recomputes p^1 of its own element and adds the matrix part taken at p^1
             lin_eval(ml0, mp, false);                            // from (p_half, q')
@@ -714,7 +720,7 @@ __global__ void __launch_bounds__(256, 1) k_md_ens(const EnsArgs a) {
         }
         __syncwarp();
     }
-    if (live)
+    if (own && live)
         for (int i = lane; i < nph; i += 32) {
             a.p[(size_t)gtraj * a.ld + i] = mp[i];
             a.q[(size_t)gtraj * a.ld + i] = mq[i];
@@ -1473,17 +1479,17 @@ struct sclmd_md {
         kfrag_valid = true;
         return 0;
     }
-    template <int NTILE, int G>
+    template <int NTILE, int G, int W>
     int launch_ens(const EnsArgs &a, size_t smem) {
         auto go = [&](auto kernel) -> int {
             SCLMD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kernel<<<cdiv(ntraj, EN_T), 256, smem, st>>>(a);
+            kernel<<<cdiv(ntraj, EN_T), W * 32, smem, st>>>(a);
             SCLMD_CUDA(cudaGetLastError());
             return 0;
         };
         if (baths.size() > 2 || ens_lin_bath() >= 0)       // up to four baths, one of them dense
-            return has_cons ? go(k_md_ens<4, NTILE, G, true, true>) : go(k_md_ens<4, NTILE, G, false, true>);
-        return has_cons ? go(k_md_ens<2, NTILE, G, true, false>) : go(k_md_ens<2, NTILE, G, false, false>);
+            return has_cons ? go(k_md_ens<4, NTILE, G, true, true, W>) : go(k_md_ens<4, NTILE, G, false, true, W>);
+        return has_cons ? go(k_md_ens<2, NTILE, G, true, false, W>) : go(k_md_ens<2, NTILE, G, false, false, W>);
     }
     int run_ens(long long nsteps) {
         if (!kfrag_valid) if (int e = build_kfrag()) return e;
@@ -1516,8 +1522,14 @@ struct sclmd_md {
         const bool wide = baths.size() > 2 || a.lin_bath >= 0;
         const size_t smem = ((size_t)4 * EN_T * a.lds + (size_t)std::max<size_t>(baths.size(), 1) * EN_T * a.ncpmax + (wide ? 3 * EN_T * EN_LC : 0)) * sizeof(double);
         if (smem > 226 * 1024) return 1;                  // caller falls back to the launch chain
-        int e = ens_ntile == 4 ? launch_ens<4, 4>(a, smem) : ens_ntile == 5 ? launch_ens<5, 5>(a, smem) : ens_ntile == 8 ? launch_ens<8, 4>(a, smem)
-              : ens_ntile == 10 ? launch_ens<10, 5>(a, smem) : launch_ens<12, 4>(a, smem);
+        // ens_ntile tiles per warp of an 8-warp CTA; even counts are split over 16 warps (SCLMD_ENS_WARPS=8 keeps eight)
+        static const bool wide16 = !(getenv("SCLMD_ENS_WARPS") && atoi(getenv("SCLMD_ENS_WARPS")) == 8);
+        int e;
+        if (wide16 && ens_ntile == 8) e = launch_ens<4, 4, 16>(a, smem);
+        else if (wide16 && ens_ntile == 10) e = launch_ens<5, 5, 16>(a, smem);
+        else if (wide16 && ens_ntile == 12) e = launch_ens<6, 3, 16>(a, smem);
+        else e = ens_ntile == 4 ? launch_ens<4, 4, 8>(a, smem) : ens_ntile == 5 ? launch_ens<5, 5, 8>(a, smem) : ens_ntile == 8 ? launch_ens<8, 4, 8>(a, smem)
+               : ens_ntile == 10 ? launch_ens<10, 5, 8>(a, smem) : launch_ens<12, 4, 8>(a, smem);
         if (e) return e;
         ++launches;
         t += nsteps;
