@@ -547,7 +547,8 @@ __global__ void __launch_bounds__(EN_W * 32, 1) k_md_ens(const EnsArgs a) {
 #pragma unroll
             for (int b = 0; b < NBATH; ++b) cur[b] = 0.0;
             lin_eval(ml0, mp, false);                            // from (p_t, q_t), before they are overwritten below
-            for (int i = lane; i < nph; i += 32) {
+#pragma unroll 4
+            for (int i = lane; i < nph; i += 32) {      // unrolled: the dependent table loads (inv -> k0) of four elements overlap
                 const double pi = mp[i];
                 double f = -mg[i];
 #pragma unroll
@@ -579,6 +580,8 @@ __global__ void __launch_bounds__(EN_W * 32, 1) k_md_ens(const EnsArgs a) {
         __syncthreads();                                  // q' of all eight trajectories is in place
         // ---- K.q' (and the part of it that comes from the constrained dofs): DMMA over fragment-ordered K
         {
+            // (the fragment loads bypass L1 -- ld.global.nc.L1::no_allocate -- so that the 3.5 MB streamed per step do not evict the
+            // bath index / friction / constraint tables the elementwise phases read through L1)
             // The K fragments of a tile are ONE stream of nk8 + nkc8 double2 per lane (all dofs, then the constrained ones again);
             // EN_D of them are in flight per tile (register ring, refilled right after use), for EN_G (4 or 5) tiles at a time:
             // the L2 round trip (~1000 cycles under load) is covered by 4 x 5 x 512 bytes per warp.
@@ -599,7 +602,7 @@ __global__ void __launch_bounds__(EN_W * 32, 1) k_md_ens(const EnsArgs a) {
 #pragma unroll
                 for (int d = 0; d < ED; ++d)
 #pragma unroll
-                    for (int j = 0; j < EN_G; ++j) bn[d][j] = __ldg(kb + j * tstride + (size_t)d * 32);
+                    for (int j = 0; j < EN_G; ++j) bn[d][j] = ld_stream2(reinterpret_cast<const double *>(kb + j * tstride + (size_t)d * 32));
                 double a0 = arowp[aslot], a1 = arowp[4 + aslot];
                 for (int ks = 0; ks < a.nk8; ks += ED) {        // nk8, nkc8 are multiples of EN_D (and of ED)
 #pragma unroll
@@ -612,7 +615,7 @@ __global__ void __launch_bounds__(EN_W * 32, 1) k_md_ens(const EnsArgs a) {
                         for (int j = 0; j < EN_G; ++j) dmma884(acc[1][j][0], acc[1][j][1], a1, bn[d][j].y);
                         if (ks + d + ED < nkt) {
 #pragma unroll
-                            for (int j = 0; j < EN_G; ++j) bn[d][j] = __ldg(kb + j * tstride + (size_t)(ks + d + ED) * 32);
+                            for (int j = 0; j < EN_G; ++j) bn[d][j] = ld_stream2(reinterpret_cast<const double *>(kb + j * tstride + (size_t)(ks + d + ED) * 32));
                         }
                         a0 = n0;
                         a1 = n1;
@@ -630,7 +633,7 @@ __global__ void __launch_bounds__(EN_W * 32, 1) k_md_ens(const EnsArgs a) {
                             for (int j = 0; j < EN_G; ++j) dmma884(accc[1][j][0], accc[1][j][1], x1, bn[d][j].y);
                             if (a.nk8 + ks + d + ED < nkt) {
 #pragma unroll
-                                for (int j = 0; j < EN_G; ++j) bn[d][j] = __ldg(kb + j * tstride + (size_t)(a.nk8 + ks + d + ED) * 32);
+                                for (int j = 0; j < EN_G; ++j) bn[d][j] = ld_stream2(reinterpret_cast<const double *>(kb + j * tstride + (size_t)(a.nk8 + ks + d + ED) * 32));
                             }
                         }
                     }
@@ -692,6 +695,7 @@ __global__ void __launch_bounds__(EN_W * 32, 1) k_md_ens(const EnsArgs a) {
                 if (fx) mq[i] = 0.0;
             }
         } else {
+#pragma unroll 4
             for (int i = lane; i < nph; i += 32) {
                 const double ph = mp[i], g1 = mg1[i];
                 double nz[NBATH], kx[NBATH];
