@@ -335,3 +335,13 @@ def ReadNewEPHNCFile(filename):
     eph.efric, eph.xim, eph.xip = v['Friction'], v['NC'], v['NCP']
     eph.zeta1, eph.zeta2 = v.get('zeta1'), v.get('zeta2')
     return eph
+
+
+def reordxyz(anr, xyz, ord):
+    """sclmd/myio.py:64-77: move the atoms listed in `ord` (1-based, a contiguous index range in any order) into that order;
+    atoms before and after the range keep their places.  Returns the permuted atom numbers and coordinates."""
+    lo, hi = min(ord), max(ord)
+    perm = list(range(lo - 1)) + [i - 1 for i in ord] + list(range(hi, len(xyz)))
+    if len(perm) != len(anr):
+        raise ValueError("reordxyz:length error")
+    return [anr[i] for i in perm], [xyz[i] for i in perm]

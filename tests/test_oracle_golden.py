@@ -298,3 +298,14 @@ def test_bpt_and_sig_write_the_reference_frequency_files(tmp_path, monkeypatch):
     os.remove("omegas.dat")
     bpt(None, 0.25, 0.1, [list(range(3, 12)), list(range(24, 33))], fixed, dynmatfile=K, num=4)   # array in: nothing written
     assert not os.path.exists("omegas.dat")
+
+
+def test_reordxyz():
+    """myio.reordxyz (myio.py:64-77)"""
+    from sclmd_b200 import myio
+    anr = [6, 6, 1, 1, 79, 79]
+    xyz = [[float(i), 0.0, 0.0] for i in range(6)]
+    a2, x2 = myio.reordxyz(anr, xyz, [4, 2, 3])
+    assert a2 == [6, 1, 6, 1, 79, 79] and [x[0] for x in x2] == [0.0, 3.0, 1.0, 2.0, 4.0, 5.0]
+    with pytest.raises(ValueError):
+        myio.reordxyz(anr, xyz, [2, 5])
