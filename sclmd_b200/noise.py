@@ -203,3 +203,19 @@ def enoise(efric, exim, exip, bias, T, ecut, dt, nmd, classical=False, zpmotion=
     out = plan.generate(1 if ntraj is None else ntraj, _seed(seed), 0, xi)
     plan.close()
     return out[0] if ntraj is None else out
+
+
+def vargau(eval, evec, cof=1.0, device=0):
+    """noise.py:273-305: one multivariate Gaussian draw from an eigen-decomposed covariance, V . r with r_k ~ N(0, sqrt(cof lambda_k))
+    for the positive eigenvalues and 0 otherwise.  The normal deviates come from np.random.normal in the reference's order (drawn
+    only for positive eigenvalues), so a seeded script reproduces the reference's numbers; the product runs on the device.
+    (The bath classes do not call this: their noise is generated by the device generator, sclmd_noise_plan_*.)"""
+    import sys
+    nvec = np.array(evec)
+    if nvec.ndim != 2 or len(eval) != nvec.shape[0] or nvec.shape[0] != nvec.shape[1]:
+        print("vargau: shape error")
+        sys.exit(0)
+    rval = np.array([np.random.normal(0.0, np.sqrt(cof * v)) if cof * v > 0 else 0.0 for v in eval])
+    if np.iscomplexobj(nvec):
+        return _lib.dgemm_nt(rval[None, :], nvec.real, 1.0, device)[0] + 1j * _lib.dgemm_nt(rval[None, :], nvec.imag, 1.0, device)[0]
+    return _lib.dgemm_nt(rval[None, :], nvec, 1.0, device)[0]

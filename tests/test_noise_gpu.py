@@ -234,3 +234,24 @@ def test_fft_rejects_unsupported_lengths():
     from sclmd_b200._lib import SclmdError
     with pytest.raises(SclmdError):
         device_fft(np.ones(14), -1, 1.0)          # 7 is not a supported radix
+
+
+def test_vargau_reproduces_the_reference_draw_order():
+    """noise.vargau (noise.py:273-305): deviates from np.random.normal drawn only for positive eigenvalues, V.r on the device"""
+    from sclmd_b200.noise import vargau
+    rng = np.random.default_rng(12)
+    a = rng.standard_normal((7, 7))
+    lam, vec = np.linalg.eigh(a @ a.T - 2.0 * np.eye(7))          # some negative eigenvalues
+    assert (lam <= 0).any() and (lam > 0).any()
+    np.random.seed(5)
+    got = vargau(lam, vec, cof=0.5)
+    np.random.seed(5)
+    r = np.array([np.random.normal(0.0, np.sqrt(0.5 * v)) if v > 0 else 0.0 for v in lam])
+    assert np.max(np.abs(got - vec @ r)) < 1e-12 * max(1.0, np.abs(vec @ r).max())
+    h = a + 1j * rng.standard_normal((7, 7))
+    lamc, vecc = np.linalg.eigh(h @ h.conj().T)
+    np.random.seed(6)
+    gotc = vargau(lamc, vecc)
+    np.random.seed(6)
+    rc = np.array([np.random.normal(0.0, np.sqrt(v)) if v > 0 else 0.0 for v in lamc])
+    assert np.max(np.abs(gotc - vecc @ rc)) < 1e-12 * np.abs(vecc @ rc).max()
