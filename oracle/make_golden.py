@@ -380,10 +380,101 @@ def run_myio_cases():
     np.savez_compressed(os.path.join(GOLD, "myio_readers.npz"), **out)
 
 
+# -------------------------------------------------------------- tools.calHF / calTC (tools.py:132-215)
+def run_tools_cases():
+    """the reference's own calHF / calTC on seeded kappa files: two and three baths, dlist 0 / 1 / 2, with and without
+    the conductivity geometry (L, A), delta == 0"""
+    import tempfile
+    import sclmd.tools as rtools
+    out = {}
+    cases = P.KAPPA_CASES
+    cwd = os.getcwd()
+    for name, seed, nb, nr, T, kw in cases:
+        vals, T = P.kappa_case(seed, nb, nr, T)
+        with tempfile.TemporaryDirectory() as td:
+            os.chdir(td)
+            try:
+                P.write_kappa_files(vals, T)
+                with refshim.quiet():
+                    rtools.calHF(dlist=kw["dlist"], bathnum=nb)
+                    rtools.calTC(kw["delta"], dlist=kw["dlist"], bathnum=nb, L=kw.get("L"), A=kw.get("A"))
+                out[name + "_hf"] = np.loadtxt("heatflux.%d.dat" % T)
+                out[name + "_jb"] = np.loadtxt("heatflux-between-baths.%d.dat" % T)
+                if kw["delta"] != 0:
+                    out[name + "_tc"] = np.loadtxt("thermalconductance.%d.dat" % T)
+                if kw.get("L") is not None:
+                    out[name + "_cond"] = np.loadtxt("thermalconductivity.%d.dat" % T)
+            finally:
+                os.chdir(cwd)
+    np.savez_compressed(os.path.join(GOLD, "tools.npz"), **out)
+    print("tools          calHF / calTC of the reference on %d seeded kappa sets" % len(cases))
+
+
+# -------------------------------------------------------------- phbath(sig=...) -> ggamma -> gmem (baths.py:322-327,375-395,412-446)
+def run_phbath_sig_case():
+    nc, gwl, sig = P.phbath_sig_inputs()
+    dt, nmd, ml, nw = 0.25 / 0.658, 64, 11, 48
+    out = {}
+    for tag, eta in (("eta0", 0), ("eta1", 0.02)):
+        with refshim.quiet():
+            b = rbaths.phbath(300.0, list(range(nc)), 0.06, nw, dt, nmd, ml=ml, mcof=2.0, sig=sig, gwl=gwl, eta_ad=eta)
+            gam0 = np.array(b.gamma)
+            b.gmem()
+        out["gamma_" + tag], out["kernel_" + tag], out["gamma_after_" + tag] = gam0, np.array(b.kernel), np.array(b.gamma)
+        assert relerr(O.ggamma(sig, gwl), gam0) == 0.0
+        tl = [dt * i for i in range(ml)]
+        assert relerr(O.gamt(tl, b.wl, gwl, gam0, eta), b.kernel) < 1e-13
+    np.savez_compressed(os.path.join(GOLD, "phbath_sig.npz"), **out)
+    print("phbath(sig)    ggamma exact, gmem vs oracle.gamt < 1e-13 (both eta_ad branches)")
+
+
+# -------------------------------------------------------------- an independent pin of c4_lambda.npz
+def pin_c4_lambda_by_raw_scan():
+    """tests/golden/c4_lambda.npz is extracted with the product's own HDF5 walker.  Independent check that does not parse HDF5
+    at all: the example file stores its 36 x 36 float64 matrices contiguous and uncompressed, so every
+    byte offset whose 10368-byte block is a finite matrix (anti)symmetric to rounding (1e-9 relative) is a stored matrix.  The five fixtures must
+    each equal one such raw block bit for bit, in the order the variables were written."""
+    fn = os.path.join(refshim.REFERENCE_ROOT, "examples", "current-induced", "grapheneLambda-r-0.3-ver2.nc")
+    raw = open(fn, "rb").read()
+    n = 36
+    found = []
+    for c in range(8):
+        arr = np.frombuffer(raw[c:c + 8 * ((len(raw) - c) // 8)], dtype="<f8")
+        m = len(arr) - n * n
+        with np.errstate(all="ignore"):
+            a01, a10 = arr[1:1 + m], arr[n:n + m]
+            a02, a20 = arr[2:2 + m], arr[2 * n:2 * n + m]
+            near = lambda x, y: (np.abs(x - y) <= 1e-9 * np.abs(x)) | (np.abs(x + y) <= 1e-9 * np.abs(x))
+            cand = np.nonzero(np.isfinite(a01) & (np.abs(a01) > 1e-300) & (np.abs(a01) < 1e6) & near(a01, a10) &
+                              np.isfinite(a02) & near(a02, a20))[0]
+        for s0 in cand:
+            blk = arr[s0:s0 + n * n].reshape(n, n)
+            if not np.all(np.isfinite(blk)):
+                continue
+            top = np.abs(blk).max()
+            if 0 < top < 1e6 and min(np.abs(blk - blk.T).max(), np.abs(blk + blk.T).max()) <= 1e-9 * top:
+                found.append((c + 8 * int(s0), blk.copy()))
+    found.sort(key=lambda t: t[0])
+    lam = P.c4_lambda()
+    offs = {}
+    for k, a in lam.items():
+        hits = [o for o, blk in found if np.array_equal(blk, a)]
+        assert len(hits) == 1, "fixture %s is not a raw block of the example file (hits: %s)" % (k, hits)
+        offs[k] = hits[0]
+    order = sorted(offs, key=offs.get)
+    assert order == ["eta_r", "xim_r", "xip_r", "zeta1_r", "zeta2_r"], order
+    print("c4_lambda      raw-scan pin: %d (anti)symmetric 36x36 blocks in the file, fixtures at byte offsets %s" %
+          (len(found), [offs[k] for k in order]))
+    np.savez_compressed(os.path.join(GOLD, "c4_lambda_offsets.npz"), **{k: np.int64(v) for k, v in offs.items()})
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     run_myio_cases()
     extract_c4_lambda()
+    pin_c4_lambda_by_raw_scan()
+    run_tools_cases()
+    run_phbath_sig_case()
     for name, fn in (("ph_full", md_case_ph_full), ("ph_local", md_case_ph_local), ("e_extra", md_case_e_extra),
                      ("c1_shape", md_case_c1_shape), ("c4_shape", P.md_case_c4_shape)):
         run_md_case(name, fn())

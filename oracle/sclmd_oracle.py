@@ -407,7 +407,9 @@ class EnsembleMD:
         hist = b["ring"][:, slots, :]                       # [ntraj, ml-1, nc]
         if b["diag"]:
             return self.dt * np.einsum("jc,tjc->tc", b["kernel"][1:], hist)
-        return self.dt * np.einsum("jab,tjb->ta", b["kernel"][1:], hist)
+        if "kmat" not in b:                                 # [(ml-1) nc, nc]: sum_j kernel[j] . p as ONE matrix product (BLAS)
+            b["kmat"] = np.ascontiguousarray(b["kernel"][1:].transpose(0, 2, 1)).reshape((ml - 1) * b["nc"], b["nc"])
+        return self.dt * (hist.reshape(self.ntraj, (ml - 1) * b["nc"]) @ b["kmat"])
 
     def step(self):
         dt, t = self.dt, self.t

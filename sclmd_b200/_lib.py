@@ -76,6 +76,7 @@ _PROTOS = {
     "sclmd_noise_plan_generate": (C.c_int, [C.c_void_p, C.c_int, c_double_p, C.c_uint64, C.c_int64, c_double_p]),
     "sclmd_noise_plan_generate_into": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "sclmd_noise_plan_launch_count": (C.c_int64, [C.c_void_p]),
+    "sclmd_noise_plan_get_profile": (C.c_int, [C.c_void_p, c_double_p]),
     "sclmd_md_generate_noise": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_int64]),
     "sclmd_fft": (C.c_int, [C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, C.c_int, C.c_double, c_double_p, c_double_p]),
     "sclmd_cos_transform": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, C.c_double, C.c_double, c_double_p]),

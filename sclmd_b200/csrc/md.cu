@@ -2009,7 +2009,8 @@ int sclmd_md_get_history(sclmd_md *h, int bath, double *phis) {
     if (int e = h->flush()) return e;
     Bath &b = *h->baths[bath];
     std::vector<double> tmp(b.ring.n);
-    SCLMD_CUDA(cudaMemcpy(tmp.data(), b.ring.p, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    SCLMD_CUDA(cudaMemcpyAsync(tmp.data(), b.ring.p, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    SCLMD_CUDA(cudaStreamSynchronize(h->st));
     for (int tr = 0; tr < h->ntraj; ++tr)
         for (int i = 0; i < b.ml; ++i) {
             long long s = (h->t - 1 - i) % b.ml;
@@ -2032,7 +2033,8 @@ int sclmd_md_set_history(sclmd_md *h, int bath, const double *phis) {
             if (s < 0) s += b.ml;
             memcpy(tmp.data() + ((size_t)tr * b.ml + s) * b.ncp, phis + ((size_t)tr * b.ml + i) * b.nc, b.nc * sizeof(double));
         }
-    SCLMD_CUDA(cudaMemcpy(b.ring.p, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice));
+    SCLMD_CUDA(cudaMemcpyAsync(b.ring.p, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    SCLMD_CUDA(cudaStreamSynchronize(h->st));      // `tmp` is pageable: the copy has landed before the tail kernel below is queued
     // the tail for evaluation A of the next step: ring as if p_{t-1} had just been pushed
     if (b.ml > 1) {
         b.far_t0 = -1;
@@ -2286,7 +2288,9 @@ int sclmd_md_get_step_observables(sclmd_md *h, int slab, double *out) {
 
 static int get_slots(sclmd_md *h, const double *dev, double *host) {  // device [nmd][ntraj] -> host [ntraj][nmd]
     std::vector<double> tmp((size_t)h->nmd * h->ntraj);
-    SCLMD_CUDA(cudaMemcpy(tmp.data(), dev, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    // on the handle's own (non-blocking) stream: ordered after every queued step, e.g. after sclmd_md_run(h, n, NULL)
+    SCLMD_CUDA(cudaMemcpyAsync(tmp.data(), dev, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    SCLMD_CUDA(cudaStreamSynchronize(h->st));
     for (int k = 0; k < h->nmd; ++k)
         for (int tr = 0; tr < h->ntraj; ++tr) host[(size_t)tr * h->nmd + k] = tmp[(size_t)k * h->ntraj + tr];
     return SCLMD_OK;

@@ -553,6 +553,10 @@ struct sclmd_noise_plan {
     DevBuf<double> L;      // [nw][nc*(1+cplx)][ncp]
     DevBuf<double> evals;  // [nw][nc]
     int64_t launches = 0;
+    // stage timing of the last generate call (CUDA events on the generating stream): 0 draws, 1 x = L xi, 2 transform
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    double stage_ms[3] = {0, 0, 0};
+    double factor_ms = 0;
 };
 
 namespace {
@@ -627,10 +631,14 @@ int generate(sclmd_noise_plan *pl, int ntraj, const double *xi_host, uint64_t se
     SCLMD_CUDA(X.alloc((size_t)nw * chunk * ncx));
     if (!direct) SCLMD_CUDA(scratch.alloc((size_t)chunk * npair * N));
     const double scale = 1.0 / (pl->dt * N);   // dw/2pi (functions.py:51)
+    for (int i = 0; i < 4; ++i)
+        if (!pl->ev[i]) SCLMD_CUDA(cudaEventCreate(&pl->ev[i]));
+    pl->stage_ms[0] = pl->stage_ms[1] = pl->stage_ms[2] = 0.0;
     for (int t0 = 0; t0 < ntraj; t0 += chunk) {
         const int cnt = std::min(chunk, ntraj - t0);
         const size_t nel = (size_t)nw * cnt * ncp;
         const int blocks = (int)std::min<size_t>((nel + 255) / 256, (size_t)pl->nsm * 16);
+        SCLMD_CUDA(cudaEventRecord(pl->ev[0], st));
         if (xi_host) {
             SCLMD_CUDA(xih.alloc((size_t)cnt * nw * nc));
             SCLMD_CUDA(cudaMemcpyAsync(xih.p, xi_host + (size_t)t0 * nw * nc, (size_t)cnt * nw * nc * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -639,6 +647,7 @@ int generate(sclmd_noise_plan *pl, int ntraj, const double *xi_host, uint64_t se
             k_fill_xi<<<blocks, 256, 0, st>>>(xi.p, nw, cnt, nc, ncp, seed, traj0 + t0);
         }
         SCLMD_CUDA(cudaGetLastError());
+        SCLMD_CUDA(cudaEventRecord(pl->ev[1], st));
         // X[w] (cnt x ncx) = xi[w] (cnt x ncp) . L[w]^T   -- batched over w through gridDim.z
         GemmArgs g{};
         g.M = cnt; g.N = nc * E; g.Kseg = ncp; g.nseg = nw; g.segs_per_split = 1;
@@ -659,6 +668,7 @@ int generate(sclmd_noise_plan *pl, int ntraj, const double *xi_host, uint64_t se
                 ++pl->launches;
             }
         }
+        SCLMD_CUDA(cudaEventRecord(pl->ev[2], st));
         double *o = out + (size_t)t0 * out_tstride;
         if (direct) {
             SCLMD_CUDA(cudaFuncSetAttribute(k_fft_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_direct));
@@ -676,7 +686,12 @@ int generate(sclmd_noise_plan *pl, int ntraj, const double *xi_host, uint64_t se
             SCLMD_CUDA(cudaGetLastError());
             pl->launches += 3;
         }
+        SCLMD_CUDA(cudaEventRecord(pl->ev[3], st));
         SCLMD_CUDA(cudaStreamSynchronize(st));
+        for (int i = 0; i < 3; ++i) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, pl->ev[i], pl->ev[i + 1]) == cudaSuccess) pl->stage_ms[i] += ms;
+        }
     }
     return 0;
 }
@@ -708,6 +723,10 @@ int sclmd_noise_plan_create(int device, int nmd, double dt, int nc, int nbasis, 
     const int E = cplx ? 2 : 1;
     SCLMD_CUDA(pl->L.alloc((size_t)nw * nc * E * pl->ncp));
     SCLMD_CUDA(pl->evals.alloc((size_t)nw * nc));
+    cudaEvent_t f0 = nullptr, f1 = nullptr;
+    SCLMD_CUDA(cudaEventCreate(&f0));
+    SCLMD_CUDA(cudaEventCreate(&f1));
+    SCLMD_CUDA(cudaEventRecord(f0, pl->st));
     // single real basis matrix for every frequency: factor once, scale per frequency
     bool single = !cplx;
     int b0 = -1;
@@ -737,6 +756,12 @@ int sclmd_noise_plan_create(int device, int nmd, double dt, int nc, int nbasis, 
     } else {
         if (int e = factor_batch(pl.get(), nw, nbasis, basis, nterm, idx, cre, cim, cplx, pl->L.p, pl->evals.p)) return e;
     }
+    SCLMD_CUDA(cudaEventRecord(f1, pl->st));
+    SCLMD_CUDA(cudaStreamSynchronize(pl->st));
+    float fms = 0;
+    if (cudaEventElapsedTime(&fms, f0, f1) == cudaSuccess) pl->factor_ms = fms;
+    cudaEventDestroy(f0);
+    cudaEventDestroy(f1);
     *out = pl.release();
     return SCLMD_OK;
 }
@@ -745,6 +770,8 @@ int sclmd_noise_plan_destroy(sclmd_noise_plan *pl) {
     if (!pl) return SCLMD_OK;
     cudaSetDevice(pl->device);
     if (pl->st) { cudaStreamSynchronize(pl->st); cudaStreamDestroy(pl->st); }
+    for (int i = 0; i < 4; ++i)
+        if (pl->ev[i]) cudaEventDestroy(pl->ev[i]);
     delete pl;
     return SCLMD_OK;
 }
@@ -804,6 +831,15 @@ int sclmd_noise_plan_generate(sclmd_noise_plan *pl, int ntraj, const double *xi,
 }
 
 int64_t sclmd_noise_plan_launch_count(sclmd_noise_plan *pl) { return pl ? pl->launches : -1; }
+
+// ms[4]: device milliseconds of the last generate call per stage (0 draws, 1 x = L xi, 2 transform) and of the factorisation
+// at plan creation (3)
+int sclmd_noise_plan_get_profile(sclmd_noise_plan *pl, double *ms) {
+    SCLMD_REQUIRE(pl && ms, "sclmd_noise_plan_get_profile: NULL argument");
+    for (int i = 0; i < 3; ++i) ms[i] = pl->stage_ms[i];
+    ms[3] = pl->factor_ms;
+    return SCLMD_OK;
+}
 
 // device-to-device variant used by md.cu: writes into a [nmd][ntraj_total][ncp] table
 int sclmd_noise_plan_generate_into(sclmd_noise_plan *pl, int ntraj, uint64_t seed, int64_t traj0, double *table, int ntraj_total,

@@ -136,6 +136,12 @@ class NoisePlan:
     def launch_count(self):
         return int(_lib.lib().sclmd_noise_plan_launch_count(self._h))
 
+    def profile(self):
+        """device ms of the last generate call per stage, and of the factorisation at plan creation"""
+        ms = np.zeros(4)
+        check(_lib.lib().sclmd_noise_plan_get_profile(self._h, dptr(ms)))
+        return dict(draws_ms=float(ms[0]), gemm_ms=float(ms[1]), transform_ms=float(ms[2]), factor_ms=float(ms[3]))
+
 
 def ph_plan(gamma, wl, T, phcut, dt, nmd, classical=False, zpmotion=True, device=0):
     """Spectral weights of noise.py:73-79 as a device plan: A(w_i) = (dt nmd) equ(w_i) flinterp(w_i, wl, gamma)."""

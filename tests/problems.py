@@ -216,6 +216,38 @@ def myio_inputs():
     return dict(lam=lam, wb=wb, ph=ph, sg=sg)
 
 
+# ---------------------------------------------------------------- post-processing / pipeline-glue cases
+# name, seed, baths, runs, T, calHF / calTC arguments (tools.py:132-215)
+KAPPA_CASES = [("b2_d1", 11, 2, 7, 300, dict(delta=0.1, dlist=1)),
+               ("b2_d0", 12, 2, 5, 300, dict(delta=0.2, dlist=0)),
+               ("b3_d2", 13, 3, 6, 250, dict(delta=0.1, dlist=2, L=12.5, A=30.0)),
+               ("b2_delta0", 14, 2, 4, 300, dict(delta=0, dlist=1))]
+
+
+def kappa_case(seed, bathnum, nruns, T):
+    """seeded kappa.<T>.bath<i>.run<j>.dat contents as md.Run writes them (md.py:658-664): run index, T, mean current"""
+    rng = np.random.default_rng(seed)
+    base = np.array([1.7, -1.5, 0.3])[:bathnum]
+    return base[:, None] + 0.2 * rng.standard_normal((bathnum, nruns)), T
+
+
+def write_kappa_files(vals, T):
+    for i in range(vals.shape[0]):
+        for j in range(vals.shape[1]):
+            with open("kappa." + str(T) + ".bath" + str(i) + ".run" + str(j) + ".dat", "w") as f:
+                f.write("%i %f    %f \n" % (j, T, vals[i, j]))
+
+
+def phbath_sig_inputs():
+    """a seeded retarded self-energy on a frequency grid that starts at 0 (ggamma copies index 1 there, baths.py:386-388):
+    Sigma(w) = Re - i w Gamma(w) with Gamma PSD, in the MD units (eV^2 / eV)"""
+    nc, ngw = 5, 9
+    gwl, g = gamma_grid(ngw, nc, 91, wmax=0.24)
+    re = np.array([sym(nc, 92 + i, 0.01) for i in range(ngw)])
+    sig = re - 1j * gwl[:, None, None] * g
+    return nc, gwl, sig
+
+
 def write_classic_nc(filename, variables):
     """every array as a float64 (or int32) variable of a NetCDF classic file, one dimension per axis"""
     from scipy.io import netcdf_file

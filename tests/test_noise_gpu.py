@@ -171,6 +171,20 @@ def test_gmem_with_artificial_damping_rederives_gamma():
     assert relerr(b.gamma, want) < 1e-12 and relerr(b.gammaOld, gam) == 0
 
 
+def test_gmem_from_a_self_energy_equals_the_reference(golden_dir):
+    """phbath(sig=..., gwl=...) -> ggamma -> gmem (baths.py:322-327,375-395,412-446), both eta_ad branches, against the
+    reference's own kernel and re-derived gamma (tests/golden/phbath_sig.npz)"""
+    from sclmd_b200.baths import phbath
+    g = np.load(os.path.join(golden_dir, "phbath_sig.npz"))
+    nc, gwl, sig = P.phbath_sig_inputs()
+    for tag, eta in (("eta0", 0), ("eta1", 0.02)):
+        b = phbath(300.0, list(range(nc)), 0.06, 48, DT, 64, ml=11, mcof=2.0, sig=sig, gwl=gwl, eta_ad=eta)
+        assert np.array_equal(b.gamma, g["gamma_" + tag])
+        b.gmem()
+        assert relerr(b.kernel, g["kernel_" + tag]) < 1e-12, tag
+        assert relerr(b.gamma, g["gamma_after_" + tag]) < 1e-12, tag
+
+
 def test_odd_nmd_is_rejected():
     from sclmd_b200 import noise as N
     from sclmd_b200._lib import SclmdError
