@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--no-also", action="store_true", help="skip the secondary workloads (C2 MD, NEGF)")
     ap.add_argument("--no-overlap", action="store_true", help="run the K.q GEMM on the same stream as the history-tail kernels (A/B measurement)")
     ap.add_argument("--tail-block", type=int, default=1, help="1: time-blocked history tails (default); 0: direct, one ring pass per step")
+    ap.add_argument("--no-modal", action="store_true", help="propagate in real space (K.q GEMM every step) instead of the eigenbasis of md.setDyn (A/B measurement)")
     return ap.parse_args()
 
 
@@ -57,7 +58,8 @@ WORKLOADS = {
 def build_problem(w):
     """K (PSD-projected as md.setDyn does), bath dof lists, kernels."""
     nph = 3 * w["natoms"]
-    K = P.psd_project(P.spring_chain_dyn(w["natoms"], seed=5))
+    K, lam, U = P.psd_project_modes(P.spring_chain_dyn(w["natoms"], seed=5))
+    w["_modes"] = (lam, U)                                   # what md.setDyn keeps next to the projected matrix (md.py:266-281)
     f = w["fixed"]
     cids = [list(range(f, f + w["nc"])), list(range(nph - f - w["nc"], nph - f))]
     cons = list(range(0, f)) + list(range(nph - f, nph)) if f else []
@@ -206,6 +208,7 @@ def make_engine(w, device, ntraj):
     nph, K, cids, cons, kern = build_problem(w)
     eng = MDEngine(nph, ntraj, w["dt"], w["nmd"], device=device)
     eng.set_dyn(K)
+    eng.set_modes(*w["_modes"])
     if cons:
         eng.set_constraint(cons)
     for b in range(2):
@@ -347,6 +350,8 @@ def main():
     rng = np.random.default_rng(2000 + rank)
     eng.set_state(0.05 * rng.standard_normal((ntraj, nph)), 0.02 * rng.standard_normal((ntraj, nph)), 0)
     eng.set_tail_block(args.tail_block)
+    if args.no_modal:
+        eng.set_modal(False)
     if args.no_overlap:
         eng.set_overlap(False)
     K, W = args.steps, max(args.warmup, 3)
@@ -403,7 +408,8 @@ def main():
     if not prof_in_region:
         eng.set_profiling(True)
         ms_prof = eng.run(K)
-    prof_all = eng.profile_all()
+    prof_all = eng.profile_ex()
+    modal = eng.modal_active()
     eng.set_profiling(False)
     if rank == 0 and len(sampler.rows) == n_rows0:          # a region shorter than the sampling period: take the next sample under load
         t_wait = time.perf_counter()
@@ -495,6 +501,17 @@ def main():
                       "peak_source": "measured live: FP64 DMMA.8x8x4 chain probe (sclmd_probe_fp64); DFMA chain %.1f" % probe["dfma_tflops"],
                       "algorithmic_flops_per_launch": fl, "avg_launch_ms": per, "launches_timed": pa["potforce"]["launches"],
                       "share_of_step": pa["potforce"]["ms"] / ms_prof})
+    ncs = 2 * (w["nc"] + w["nc"] % 2)
+    for key, name, K_ in (("modal_scatter", "scatter product W = (fC + fA) . E, [ntraj x sum nc] . [sum nc x nph]", ncs),
+                          ("modal_gather", "gather product (K q')[cids] = Q' . (E lam)^T, [ntraj x nph] . [nph x sum nc]", nph_)):
+        if pa[key]["launches"]:
+            per = pa[key]["ms"] / pa[key]["launches"]
+            fl = 2.0 * nph_ * ncs * ntraj
+            cands.append({"kernel": "dgemm_nt_seg_kernel (eigenbasis mode, %s; DMMA.8x8x4)" % name, "bound": "tensor",
+                          "achieved": fl / (per * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fl / (per * 1e-3) / 1e12 / fp64_peak,
+                          "traffic": None, "peak_source": "measured live: FP64 DMMA.8x8x4 chain probe (sclmd_probe_fp64)",
+                          "algorithmic_flops_per_launch": fl, "avg_launch_ms": per, "launches_timed": pa[key]["launches"],
+                          "share_of_step": pa[key]["ms"] / ms_prof})
     if pa["tail_far"]["launches"]:
         per = pa["tail_far"]["ms"] / pa["tail_far"]["launches"]
         cands.append({"kernel": "k_tail_far_ws<2,8,5> (time-blocked history pass, 16 steps per ring pass; producer warp + 5 TMA stages of 8 ring rows)", "bound": "hbm",
@@ -522,10 +539,21 @@ def main():
     roof = cands[0] if cands else None
     if roof is not None:
         roof["other_kernels"] = cands[1:]
+        roof["elementwise_kernels_ms_per_step"] = {k: pa[k]["ms"] / K for k in ("modal_bath", "modal_update", "tail_near") if pa[k]["launches"]}
+        tails_fl = sum(2.0 * w["nc"] * w["ml"] for _ in range(2)) * ntraj if w["kind"] == "diag" else sum(2.0 * w["nc"] ** 2 * w["ml"] for _ in range(2)) * ntraj
+        exec_fl = (2.0 * 2.0 * nph_ * ncs * ntraj if modal else 2.0 * nph_ * nph_ * ntraj) + tails_fl
+        roof["whole_step"] = {"executed_flops_per_step": exec_fl, "executed_tflops": exec_fl / (ms / K * 1e-3) / 1e12,
+                              "frac_of_fp64_peak": exec_fl / (ms / K * 1e-3) / 1e12 / fp64_peak,
+                              "algorithmic_flops_per_step_real_space": 2.0 * nph_ * nph_ * ntraj + tails_fl,
+                              "note": "executed = what the kernels of this mode compute (eigenbasis: gather + scatter products 4 nph sum(nc) per "
+                                      "trajectory instead of K.q, 2 nph^2); the history tails are the same in both modes"}
         roof["step_algorithmic_GBs_direct_algorithm"] = algorithmic_bytes_per_traj_step(w) * ntraj * K / (ms * 1e-3) / 1e9
         roof["direct_tail_kernel_standalone"] = direct_tail
         kq_alone["frac_of_fp64_peak"] = kq_alone["tflops"] / fp64_peak
-        kq_alone["share_of_step_serialised"] = kq_alone["avg_launch_ms"] * K / ms     # what an ncu launch list (serialised kernels) shows
+        if modal:
+            kq_alone["note"] = "not on the path in the eigenbasis mode; kept as the measurement of the real-space K.q product"
+        else:
+            kq_alone["share_of_step_serialised"] = kq_alone["avg_launch_ms"] * K / ms     # what an ncu launch list (serialised kernels) shows
         roof["kq_gemm_standalone"] = kq_alone
         roof["profiled_pass"] = ("the timed region itself" if prof_in_region else
                                  "a repeat of the same K steps with per-kernel events (%.4f ms per step; the timed region replays CUDA graphs)" % (ms_prof / K))
@@ -542,7 +570,9 @@ def main():
             "gpu_launches": launches_total, "roofline": roof, "wall_ms_timed_region": wall_ms, "allreduce_ms": ar_ms,
             "heat_current_mean": [float(sums[b] / sums[2] / w["nmd"]) for b in range(2)],
             "noise_generation_s": noise_gen_s, "fp64_probe_tflops": probe, "also": also,
-            "tail_mode": "time-blocked (ring streamed once per 16 steps)" if args.tail_block else "direct (ring streamed every step)"}
+            "tail_mode": "time-blocked (ring streamed once per 16 steps)" if args.tail_block else "direct (ring streamed every step)",
+            "propagation": ("eigenbasis of md.setDyn (sclmd_md_set_modes): diagonal harmonic force, gather + scatter products over the bath dofs"
+                            if modal else "real space: K.q GEMM every step")}
 
     # ---------------- BASELINE configs[1] shape (603-dof junction of the example, ml = 1 baths, fixed ends, 1024 trajectories)
     if world == 1 and not args.no_also and args.workload != "c2":

@@ -54,6 +54,17 @@ int sclmd_md_destroy(sclmd_md *h);
 
 /* md.setDyn (md.py:250-292): K[nph*nph] row-major, already PSD-projected by the host */
 int sclmd_md_set_dyn(sclmd_md *h, const double *K);
+/* The eigen-decomposition md.setDyn projects with (md.py:266-281: K = U diag(lam) U^T, hw = sqrt(lam)): lam[nph] (clipped at 0),
+ * U[nph*nph] row-major, eigenvectors as COLUMNS (numpy.linalg.eigh).  Optional.  With it the handle propagates in the eigenbasis
+ * (Q = U^T q, Pi = U^T p: diagonal harmonic force, one gather and one scatter product over the bath dofs per step, 4 nph sum(nc)
+ * flops per trajectory-step instead of 2 nph^2) whenever the problem allows it: no constraints, no force driver, diagonal-kernel
+ * baths on disjoint dofs with 2 sum(nc) <= nph.  Same trajectories to rounding; q, p are converted back on every read.  Must follow
+ * sclmd_md_set_dyn (checked: max |K U - U diag(lam)| <= 1e-9 max(lam)); a new sclmd_md_set_dyn discards it. */
+int sclmd_md_set_modes(sclmd_md *h, const double *lam, const double *U);
+/* 1 (default): eigenbasis propagation when possible; 0: always real space (A/B measurements, tests) */
+int sclmd_md_set_modal(sclmd_md *h, int on);
+/* 1 if the next sclmd_md_run propagates in the eigenbasis, 0 if in real space */
+int sclmd_md_modal_active(sclmd_md *h);
 /* md.AddConstr (md.py:189, 782-794): dofs zeroed in p,q after every step; n=0 clears */
 int sclmd_md_set_constraint(sclmd_md *h, const int32_t *idx, int n);
 
@@ -150,6 +161,8 @@ int sclmd_md_get_bath_force(sclmd_md *h, int bath, int evaluation, double *fb);
 int sclmd_md_set_tail_block(sclmd_md *h, int on);
 /* ms[4], n[4] since profiling was switched on: 0 direct tail, 1 potential force, 2 far pass, 3 near pass */
 int sclmd_md_get_profile_all(sclmd_md *h, double *ms, int64_t *n);
+/* ms[8], n[8]: the four kinds above, then the eigenbasis mode: 4 scatter product, 5 gather product, 6 bath-dof kernel, 7 modal update */
+int sclmd_md_get_profile_ex(sclmd_md *h, double *ms, int64_t *n);
 
 /* instrumentation: kernels launched by this handle so far; name/time of the dominant kernel */
 int64_t sclmd_md_launch_count(sclmd_md *h);

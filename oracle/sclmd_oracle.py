@@ -452,6 +452,123 @@ class EnsembleMD:
             self.step()
 
 
+class ModalMD:
+    """The same integrator (md.vv, md.py:367-411) propagated in the eigenbasis md.setDyn computes (md.py:266-281):
+    K = U diag(lam) U^T, Q = U^T q, Pi = U^T p.  The harmonic force is diagonal there; only the bath dofs need real space.
+    Prototype / specification of the CUDA engine's modal mode (sclmd_md_set_modes); must equal EnsembleMD to rounding.
+
+    Restrictions (the engine falls back to real space otherwise): no constraints, baths on DISJOINT dof sets, every bath
+    force diagonal in the momentum (diagonal kernels, no exim/zeta terms).
+
+    With E_b = U[cids_b, :]  (p[cids_b] = E_b Pi, scatter U^T S_b f = E_b^T f) and the bath force fA_b(t) of evaluation A:
+        Pt_t     = Pi_t + h/2 sum_b E_b^T fA_b(t)                          (momentum half-kicked by the baths)
+        Q_{t+1}  = Q_t + h Pt_t - h^2/2 lam Q_t                            (md.py:392)
+        on the bath dofs, in real space, with g = (K q)[cids] = E_b (lam Q):   evaluations A, B, C exactly as md.py:390-404
+        Pt_{t+1} = Pt_t - h/2 lam (Q_t + Q_{t+1}) + h/2 sum_b E_b^T (fC_b(t) + fA_b(t+1))
+        etot     = Pi.Pi/2,  Pi.Pi = Pt.Pt - h sum_b p_c.fA_b - h^2/4 sum_b |fA_b|^2     (E_b E_b'^T = delta_bb')
+    Per step: ONE gather product [ntraj x nph].[nph x sum nc] and ONE scatter product [ntraj x sum nc].[sum nc x nph]
+    (4 nph sum_nc flops per trajectory) instead of K.q (2 nph^2)."""
+
+    def __init__(self, lam, U, dt, nmd, ntraj):
+        self.lam, self.U = np.asarray(lam, dtype=float), np.asarray(U, dtype=float)
+        self.nph = self.U.shape[0]
+        self.dt, self.nmd, self.ntraj = dt, nmd, ntraj
+        self.baths = []
+        self.t = 0
+        self.etot = np.zeros((ntraj, nmd))
+        self.Q = np.zeros((ntraj, self.nph))
+        self.Pt = np.zeros((ntraj, self.nph))
+        self._primed = False
+
+    def add_bath(self, cids, kernel, noise):
+        kernel = np.asarray(kernel, dtype=float)
+        assert kernel.ndim == 2, "modal mode: diagonal kernels only"
+        cids = np.asarray(cids, dtype=int)
+        for b in self.baths:
+            assert not set(b["cids"]) & set(cids), "modal mode: baths must act on disjoint dofs"
+        E = self.U[cids, :]
+        b = dict(cids=cids, nc=len(cids), kernel=kernel, ml=kernel.shape[0], noise=np.asarray(noise, dtype=float), E=E, EL=E * self.lam[None, :],
+                 ring=np.zeros((self.ntraj, kernel.shape[0], len(cids))), tail=np.zeros((self.ntraj, len(cids))),
+                 cur=np.zeros((self.ntraj, self.nmd)))
+        self.baths.append(b)
+
+    def set_state(self, q, p):
+        """real-space state in; the half-kicked momentum is formed when the first step starts"""
+        self.Q = np.asarray(q, dtype=float) @ self.U
+        self.Pi0 = np.asarray(p, dtype=float) @ self.U
+        for b in self.baths:
+            b["pc"] = np.asarray(p, dtype=float)[:, b["cids"]].copy()
+        self._primed = False
+
+    def _fb(self, b, it, x):
+        c0 = self.dt if b["ml"] > 1 else 1.0
+        return b["noise"][:, it % self.nmd, :] - c0 * b["kernel"][0][None, :] * x - b["tail"]
+
+    def _tail(self, b):
+        ml = b["ml"]
+        if ml == 1:
+            return np.zeros((self.ntraj, b["nc"]))
+        head = self.t % ml
+        slots = (head - np.arange(0, ml - 1)) % ml
+        return self.dt * np.einsum("jc,tjc->tc", b["kernel"][1:], b["ring"][:, slots, :])
+
+    def _observe(self):
+        """etot, cur, ring push of evaluation A at the current time; needs b["fA"], b["pc"]"""
+        t, h = self.t, self.dt
+        pp = np.einsum("ti,ti->t", self.Pt, self.Pt)
+        for b in self.baths:
+            pp = pp - h * np.einsum("tc,tc->t", b["pc"], b["fA"]) - h * h / 4.0 * np.einsum("tc,tc->t", b["fA"], b["fA"])
+            b["cur"][:, t % self.nmd] = np.einsum("tc,tc->t", b["fA"], b["pc"])
+            b["ring"][:, t % b["ml"], :] = b["pc"]
+        self.etot[:, t % self.nmd] = 0.5 * pp
+
+    def _prime(self):
+        h = self.dt
+        self.Pt = self.Pi0.copy()
+        for b in self.baths:
+            b["g"] = self.Q @ b["EL"].T                     # (K q_t)[cids]
+            b["fA"] = self._fb(b, self.t, b["pc"])
+            self.Pt += h / 2.0 * (b["fA"] @ b["E"])
+        self._observe()
+        self._primed = True
+
+    def step(self):
+        if not self._primed:
+            self._prime()
+        h, t = self.dt, self.t
+        Qn = self.Q + h * self.Pt - h * h / 2.0 * self.lam[None, :] * self.Q
+        W = np.zeros_like(self.Q)
+        for b in self.baths:
+            b["tail"] = self._tail(b)                        # S'(t): ring holds p_t
+            gn = Qn @ b["EL"].T                              # gather: (K q')[cids]
+            ph = b["pc"] + h / 2.0 * (-b["g"] + b["fA"])
+            x = ph
+            for _ in range(2):                               # evaluations B and C (md.py:401-404)
+                fb = self._fb(b, t + 1, x)
+                x = ph + h / 2.0 * (-gn + fb)
+            fC = fb
+            b["pc"], b["g"] = x, gn
+            b["fA"] = self._fb(b, t + 1, x)                  # evaluation A of step t+1: same noise row, same tail
+            W += (fC + b["fA"]) @ b["E"]                     # scatter
+        self.Pt = self.Pt - h / 2.0 * self.lam[None, :] * (self.Q + Qn) + h / 2.0 * W
+        self.Q = Qn
+        self.t = t + 1
+        self._observe()
+
+    def run(self, n):
+        for _ in range(n):
+            self.step()
+
+    def state(self):
+        """real-space (q, p) at the current time"""
+        if not self._primed:
+            return self.Q @ self.U.T, self.Pi0 @ self.U.T
+        Pi = self.Pt.copy()
+        for b in self.baths:
+            Pi -= self.dt / 2.0 * (b["fA"] @ b["E"])
+        return self.Q @ self.U.T, Pi @ self.U.T
+
+
 # --------------------------------------------------------------------------
 # NEGF (negf.py) and surface self-energy (selfenergy.py)
 # --------------------------------------------------------------------------

@@ -35,6 +35,10 @@ _PROTOS = {
     "sclmd_md_destroy": (C.c_int, [C.c_void_p]),
     "sclmd_md_set_dyn": (C.c_int, [C.c_void_p, c_double_p]),
     "sclmd_md_set_constraint": (C.c_int, [C.c_void_p, c_int32_p, C.c_int]),
+    "sclmd_md_set_modes": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
+    "sclmd_md_set_modal": (C.c_int, [C.c_void_p, C.c_int]),
+    "sclmd_md_modal_active": (C.c_int, [C.c_void_p]),
+    "sclmd_md_get_profile_ex": (C.c_int, [C.c_void_p, c_double_p, c_int64_p]),
     "sclmd_md_add_bath": (C.c_int, [C.c_void_p, c_int32_p, C.c_int, C.c_int, c_double_p, C.c_int, c_double_p, c_double_p, c_int32_p]),
     "sclmd_md_set_noise": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p]),
     "sclmd_md_get_noise": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p]),

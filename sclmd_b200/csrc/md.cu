@@ -60,6 +60,7 @@ struct Bath {
     bool blocked = false;     // time-blocked tails (diagonal kernel, long memory)
     int far_nsplit = 1;
     long long far_t0 = -1;    // block start the far tails in `far` belong to
+    std::vector<int> cids_h;  // host copy of the dof list (disjointness test of the modal mode)
 };
 
 // ---------------------------------------------------------------- kernels
@@ -1142,6 +1143,178 @@ __global__ void k_sum_slots(const double *__restrict__ cur, int nmd, int ntraj, 
     sums[traj] = s;
 }
 
+
+// ---- modal (eigenbasis) propagation ------------------------------------------------------------------------------------------
+// md.setDyn keeps K = U diag(lam) U^T (md.py:266-281).  With Q = U^T q, Pi = U^T p the harmonic force is diagonal; only the
+// bath dofs need real space.  Per step ONE gather product (K q')[cids] = Q' . (E lam)^T and ONE scatter product of the bath forces,
+// W = (fC(t-1) + fA(t)) . E, E = U[cids,:]: 4 nph sum(nc) flops per trajectory instead of 2 nph^2 (specification: oracle ModalMD).
+//   Pt_t    = Pi_t + h/2 E^T fA(t)                   momentum half-kicked by the bath forces of evaluation A
+//   Q_{t+1} = Q_t + h Pt_t - h^2/2 lam Q_t           (md.py:392)
+//   bath dofs, real space: evaluations A, B, C exactly as md.py:390-404 with g = (K q)[cids]
+//   Pt_{t+1} = Pt_t - h/2 lam (Q_t + Q_{t+1}) + h/2 E^T (fC(t) + fA(t+1))
+//   Pi.Pi   = Pt.Pt - h sum_b p_c.fA_b - h^2/4 sum_b |fA_b|^2        (rows of E are orthonormal, baths disjoint)
+// As in the fused real-space path evaluations B, C of a step stay pending and run with evaluation A of the next one.
+struct ModalArgs {
+    BathSet bs;
+    int off[MAXB];                 // first slot of bath b in the concatenated bath-dof arrays [ntraj][ncs]
+    int ncs, ntraj, nmd, pending, doA, gsplit;
+    long long t;                   // time of evaluation A (and of the noise slab / tail the pending B, C read)
+    double dt;
+    double *pc, *fA, *g, *sbuf, *ecorr;
+    const double *gn;              // [gsplit][ntraj][ncs] K-slices of the gather product
+};
+
+template <int NBATH>
+__global__ void __launch_bounds__(128) k_modal_bath(const ModalArgs a) {
+    __shared__ double red[32];
+    const int traj = blockIdx.x;
+    const double h = a.dt;
+    const int slab = (int)(a.t % a.nmd);
+    const size_t row = (size_t)traj * a.ncs;
+    double cur[NBATH], ec = 0.0;
+#pragma unroll
+    for (int b = 0; b < NBATH; ++b) cur[b] = 0.0;
+    for (int e = threadIdx.x; e < a.ncs; e += blockDim.x) {
+        int b = 0;
+#pragma unroll
+        for (int k = 1; k < NBATH; ++k)
+            if (k < a.bs.nb && e >= a.off[k]) b = k;
+        const int c = e - a.off[b];
+        if (c >= a.bs.b[b].nc) {               // pad column
+            a.sbuf[row + e] = 0.0;
+            continue;
+        }
+        double x = a.pc[row + e], gold = a.g[row + e], s = 0.0;
+        if (a.pending) {                       // evaluations B and C of step t-1 (md.py:401-404): noise row t, tail S'(t-1)
+            double gnew = a.gn[row + e];
+            for (int z = 1; z < a.gsplit; ++z) gnew += a.gn[(size_t)z * a.ntraj * a.ncs + row + e];
+            const double ph = x + (a.fA[row + e] - gold) * h / 2.0;
+            double xi = ph, fb = 0.0;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                fb = bath_force(a.bs.b[b], traj, a.ntraj, c, slab, xi);
+                xi = ph + h * (fb - gnew) / 2.0;
+            }
+            x = xi;
+            gold = gnew;
+            s = fb;
+            a.pc[row + e] = x;
+            a.g[row + e] = gold;
+        }
+        if (a.doA) {                           // evaluation A of step t (md.py:383-398) on the bath dofs
+            const double fa = bath_force(a.bs.b[b], traj, a.ntraj, c, slab, x);
+#pragma unroll
+            for (int k = 0; k < NBATH; ++k)
+                if (k == b) cur[k] += fa * x;
+            a.bs.b[b].ring[((size_t)traj * a.bs.b[b].ml + (int)(a.t % a.bs.b[b].ml)) * a.bs.b[b].ncp + c] = x;
+            ec -= h * x * fa + h * h / 4.0 * fa * fa;
+            a.fA[row + e] = fa;
+            s += fa;
+        }
+        a.sbuf[row + e] = s;
+    }
+    if (!a.doA) return;
+    ec = block_sum(ec, red);
+    if (threadIdx.x == 0) a.ecorr[traj] = ec;
+#pragma unroll
+    for (int b = 0; b < NBATH; ++b)
+        if (b < a.bs.nb) {
+            const double cc = block_sum(cur[b], red);
+            if (threadIdx.x == 0) a.bs.b[b].cur[(size_t)slab * a.ntraj + traj] = cc;
+        }
+}
+
+// Pt <- Pbase + h/2 W - [pending] h/2 lam (Qold + Q);  [advance] etot[t] = (Pt.Pt + ecorr)/2 and Q_{t+1} into Qold's buffer
+__global__ void __launch_bounds__(256, 4) k_modal_pq(int nph, int ld, int ntraj, int nmd, long long t, double dt, int pending, int advance,
+                                                      const double *__restrict__ lam, double *__restrict__ Pm, const double *__restrict__ Q,
+                                                      double *__restrict__ Qo, const double *__restrict__ W, int wsplit, size_t wstride,
+                                                      const double *__restrict__ ecorr, double *__restrict__ etot) {
+    __shared__ double red[32];
+    const int traj = blockIdx.x;
+    const size_t row = (size_t)traj * ld;
+    const double h = dt;
+    double ke = 0.0;
+    for (int i0 = 2 * threadIdx.x; i0 < nph; i0 += 2 * blockDim.x) {
+        double2 w2 = *reinterpret_cast<const double2 *>(W + row + i0);
+        for (int z = 1; z < wsplit; ++z) {
+            const double2 v = *reinterpret_cast<const double2 *>(W + (size_t)z * wstride + row + i0);
+            w2.x += v.x;
+            w2.y += v.y;
+        }
+        const double2 p2 = *reinterpret_cast<const double2 *>(Pm + row + i0), q2 = *reinterpret_cast<const double2 *>(Q + row + i0);
+        const double2 l2 = *reinterpret_cast<const double2 *>(lam + i0);
+        double2 o2 = make_double2(0.0, 0.0);
+        if (pending) o2 = *reinterpret_cast<const double2 *>(Qo + row + i0);
+        double2 pn, qn;
+        pn.x = p2.x + h / 2.0 * w2.x - (pending ? h / 2.0 * l2.x * (o2.x + q2.x) : 0.0);
+        pn.y = p2.y + h / 2.0 * w2.y - (pending ? h / 2.0 * l2.y * (o2.y + q2.y) : 0.0);
+        if (i0 + 1 >= nph) pn.y = 0.0;
+        ke += pn.x * pn.x + pn.y * pn.y;
+        *reinterpret_cast<double2 *>(Pm + row + i0) = pn;
+        if (advance) {
+            qn.x = q2.x + h * pn.x - h * h / 2.0 * l2.x * q2.x;
+            qn.y = i0 + 1 < nph ? q2.y + h * pn.y - h * h / 2.0 * l2.y * q2.y : 0.0;
+            *reinterpret_cast<double2 *>(Qo + row + i0) = qn;
+        }
+    }
+    if (!advance) return;
+    ke = block_sum(ke, red);
+    if (threadIdx.x == 0) etot[(size_t)(t % nmd) * ntraj + traj] = 0.5 * (ke + ecorr[traj]);
+}
+
+// pc[traj][off + a] = p[traj][cids[a]]
+__global__ void k_modal_gather_pc(const int *__restrict__ cids, int nc, int off, int ncs, int ld, const double *__restrict__ p, double *__restrict__ pc) {
+    const int traj = blockIdx.x;
+    for (int a = threadIdx.x; a < nc; a += blockDim.x) pc[(size_t)traj * ncs + off + a] = p[(size_t)traj * ld + cids[a]];
+}
+// g <- sum_z gn[z]
+__global__ void k_modal_fold(const double *__restrict__ gn, int nsplit, size_t n, double *__restrict__ g) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    double v = gn[e];
+    for (int z = 1; z < nsplit; ++z) v += gn[(size_t)z * n + e];
+    g[e] = v;
+}
+// tables from U [nph][ld] (columns = eigenvectors): UT[k][i] = U[i][k];  EL[off+a][k] = U[cid_a][k] lam_k;  ET[k][off+a] = U[cid_a][k]
+__global__ void k_modal_transpose(const double *__restrict__ U, int nph, int ld, double *__restrict__ UT) {
+    __shared__ double tile[32][33];
+    const int i0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int i = i0 + r, k = k0 + threadIdx.x;
+        tile[r][threadIdx.x] = (i < nph && k < nph) ? U[(size_t)i * ld + k] : 0.0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int k = k0 + r, i = i0 + threadIdx.x;
+        if (k < nph && i < nph) UT[(size_t)k * ld + i] = tile[threadIdx.x][r];
+    }
+}
+__global__ void k_modal_tables(const double *__restrict__ U, const double *__restrict__ lam, int nph, int ld, const int *__restrict__ cids, int nc,
+                               int off, int ncs, double *__restrict__ EL, double *__restrict__ ET) {
+    const int a = blockIdx.x;
+    const int i = cids[a];
+    for (int k = threadIdx.x; k < nph; k += blockDim.x) {
+        const double u = U[(size_t)i * ld + k];
+        EL[(size_t)(off + a) * ld + k] = u * lam[k];
+        ET[(size_t)k * ncs + off + a] = u;
+    }
+}
+// max_ik |KU[i][k] - U[i][k] lam_k| and max |lam| as bit patterns of non-negative doubles (atomicMax on unsigned long long)
+__global__ void k_modal_residual(const double *__restrict__ KU, const double *__restrict__ U, const double *__restrict__ lam, int nph, int ld,
+                                 unsigned long long *__restrict__ out) {
+    const int i = blockIdx.x;
+    double m = 0.0;
+    for (int k = threadIdx.x; k < nph; k += blockDim.x) m = fmax(m, fabs(KU[(size_t)i * ld + k] - U[(size_t)i * ld + k] * lam[k]));
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
+    if (i == 0) {
+        double l = 0.0;
+        for (int k = threadIdx.x; k < nph; k += blockDim.x) l = fmax(l, fabs(lam[k]));
+        for (int o = 16; o > 0; o >>= 1) l = fmax(l, __shfl_xor_sync(0xffffffffu, l, o));
+        if ((threadIdx.x & 31) == 0) atomicMax(out + 1, (unsigned long long)__double_as_longlong(l));
+    }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------- handle
@@ -1182,8 +1355,9 @@ struct sclmd_md {
     std::vector<cudaEvent_t> ev_pool;
     std::vector<int> ev_kind;  // 0 = tail, 1 = potforce; events come in (start, stop) pairs
     size_t ev_used = 0, ev_open = 0;
-    double prof_ms[4] = {0, 0, 0, 0};   // 0 direct tail, 1 potforce, 2 far pass, 3 near
-    long long prof_n[4] = {0, 0, 0, 0};
+    // 0 direct tail, 1 potforce, 2 far pass, 3 near; modal mode: 4 scatter GEMM, 5 gather GEMM, 6 bath-dof kernel, 7 modal update
+    double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long prof_n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     bool tail_block = true, far_tma = true, far_ws = true;
     SplitPlan gplan{0, 1, 0}, cplan{0, 1, 0};
     // Steps without history tails (every bath ml == 1: the reference's shipped examples) are launch-bound for small systems:
@@ -1202,7 +1376,7 @@ struct sclmd_md {
     }
 
     void prof_begin(int kind, cudaStream_t stream = nullptr) {
-        if (!profiling) return;
+        if (!profiling || kind < 0) return;
         if (!stream) stream = st;
         if (ev_used + 2 > ev_pool.size()) {
             for (int i = 0; i < 2; ++i) {
@@ -1216,8 +1390,8 @@ struct sclmd_md {
         ev_open = ev_used;
         ev_used += 2;
     }
-    void prof_end(cudaStream_t stream = nullptr) {
-        if (!profiling) return;
+    void prof_end(cudaStream_t stream = nullptr, int kind = 0) {
+        if (!profiling || kind < 0) return;
         cudaEventRecord(ev_pool[ev_open + 1], stream ? stream : st);
     }
     void prof_collect() {  // call after the stream is synchronised
@@ -1608,6 +1782,7 @@ struct sclmd_md {
     bool bc_pending = false, fuse_bca = true;
     bool lazy_ok(bool lin) const { return fuse_bca && !lin && !has_cons && !want_f && !ext_force; }
     int flush() {
+        if (modal_state) return modal_flush();
         if (!bc_pending) return 0;
         if (noise_pending) {
             SCLMD_CUDA(cudaStreamWaitEvent(st, evN, 0));
@@ -1623,6 +1798,169 @@ struct sclmd_md {
         bc_pending = false;
         return 0;
     }
+
+    // ---- modal (eigenbasis) mode: see k_modal_bath.  State lives in (Q, Pt / Pi, p_c, g) while modal_state is set; the
+    // real-space arrays q, p are stale then and sync_real() brings them back.
+    bool have_modes = false, modal_on = true, modal_state = false, m_pending = false, modal_tables = false;
+    DevBuf<double> mU, mUT, mlam, mEL, mET, mQ[2], mP, mW, mpc, mfA, mg, mgn, msb, mec;
+    int mqi = 0;               // mQ[mqi] = Q_t; mQ[mqi ^ 1] = Q_{t-1} while evaluations B, C are pending
+    int ncs = 0, moff[MAXB] = {0, 0, 0, 0, 0, 0, 0, 0};
+    SplitPlan splan{0, 1, 0}, gaplan{0, 1, 0};     // scatter (K = ncs) and gather (K = nph) products
+    bool modal_ok() const {
+        if (!have_modes || !modal_on || !have_dyn || has_cons || ext_force || want_f || baths.empty()) return false;
+        std::vector<char> used(nph, 0);
+        int tot = 0;
+        for (auto &b : baths) {
+            if (b->kind != SCLMD_KERNEL_DIAG || b->has_lin) return false;
+            for (int c : b->cids_h) {
+                if (used[c]) return false;       // E_b E_b'^T = delta_bb' needs disjoint dof sets
+                used[c] = 1;
+            }
+            tot += b->ncp;
+        }
+        return 2 * tot <= nph;                    // gather + scatter (4 nph sum nc) against K.q (2 nph^2)
+    }
+    SplitPlan one_plan() const { return SplitPlan{ntraj > 64 ? 0 : (ntraj > 16 ? 1 : 2), 1, ld}; }
+    int gemm_nt(int M, int N, int K, const double *A, long long lda, const double *B, long long ldb, double *C, long long ldc,
+                const SplitPlan &pl, int kind, cudaStream_t stream) {
+        GemmArgs g{};
+        g.M = M; g.N = N; g.Kseg = pl.kseg; g.nseg = pl.nsplit; g.segs_per_split = 1; g.Ktot = K;
+        g.A = A; g.lda = lda; g.a_seg_stride = pl.kseg; g.B = B; g.ldb = ldb; g.b_seg_stride = pl.kseg;
+        g.C = C; g.ldc = ldc; g.c_split_stride = (long long)M * ldc; g.alpha = 1.0;
+        prof_begin(kind, stream);
+        SCLMD_CUDA(launch_dgemm(g, pl.nsplit, stream, pl.cfg));
+        prof_end(stream, kind);
+        ++launches;
+        return 0;
+    }
+    int build_modal_tables() {
+        ncs = 0;
+        for (size_t i = 0; i < baths.size(); ++i) {
+            moff[i] = ncs;
+            ncs += baths[i]->ncp;
+        }
+        const size_t n = (size_t)ntraj * ld, nb = (size_t)ntraj * ncs;
+        SCLMD_CUDA(mEL.alloc((size_t)ncs * ld));          // zero-initialised: pad rows / columns stay 0
+        SCLMD_CUDA(mET.alloc((size_t)nph * ncs));
+        for (size_t i = 0; i < baths.size(); ++i) {
+            k_modal_tables<<<baths[i]->nc, 256, 0, st>>>(mU.p, mlam.p, nph, ld, baths[i]->cids.p, baths[i]->nc, moff[i], ncs, mEL.p, mET.p);
+            SCLMD_CUDA(cudaGetLastError());
+            ++launches;
+        }
+        splan = plan_split_k(ntraj, nph, ncs, nsm, 4);
+        gaplan = plan_split_k(ntraj, ncs, ld, nsm, 16);
+        if (const char *e = getenv("SCLMD_MODAL_SPLITS")) {      // "scatter,gather" K-split counts for A/B measurements
+            int a = 0, b = 0;
+            if (sscanf(e, "%d,%d", &a, &b) == 2 && a > 0 && b > 0) {
+                splan.kseg = round_up(cdiv(ncs, a), 16); splan.nsplit = cdiv(ncs, splan.kseg);
+                gaplan.kseg = round_up(cdiv(ld, b), 16); gaplan.nsplit = cdiv(ld, gaplan.kseg);
+            }
+        }
+        SCLMD_CUDA(mQ[0].alloc(n)); SCLMD_CUDA(mQ[1].alloc(n)); SCLMD_CUDA(mP.alloc(n));
+        SCLMD_CUDA(mW.alloc(n * splan.nsplit));
+        SCLMD_CUDA(mpc.alloc(nb)); SCLMD_CUDA(mfA.alloc(nb)); SCLMD_CUDA(mg.alloc(nb)); SCLMD_CUDA(msb.alloc(nb));
+        SCLMD_CUDA(mgn.alloc(nb * gaplan.nsplit));
+        SCLMD_CUDA(mec.alloc(ntraj));
+        modal_tables = true;
+        return 0;
+    }
+    int modal_bath(const BathSet &bs, int pending, int doA) {
+        ModalArgs a;
+        memset(&a, 0, sizeof(a));
+        a.bs = bs;
+        for (int i = 0; i < MAXB; ++i) a.off[i] = moff[i];
+        a.ncs = ncs; a.ntraj = ntraj; a.nmd = nmd; a.pending = pending; a.doA = doA; a.gsplit = gaplan.nsplit;
+        a.t = t; a.dt = dt;
+        a.pc = mpc.p; a.fA = mfA.p; a.g = mg.p; a.sbuf = msb.p; a.ecorr = mec.p; a.gn = mgn.p;
+        prof_begin(6);
+        if (bs.nb <= 2) k_modal_bath<2><<<ntraj, 128, 0, st>>>(a);
+        else if (bs.nb <= 4) k_modal_bath<4><<<ntraj, 128, 0, st>>>(a);
+        else k_modal_bath<MAXB><<<ntraj, 128, 0, st>>>(a);
+        prof_end();
+        SCLMD_CUDA(cudaGetLastError());
+        ++launches;
+        return 0;
+    }
+    int modal_pq(int pending, int advance, cudaStream_t stream) {
+        prof_begin(7, stream);
+        k_modal_pq<<<ntraj, 256, 0, stream>>>(nph, ld, ntraj, nmd, t, dt, pending, advance, mlam.p, mP.p, mQ[mqi].p, mQ[mqi ^ 1].p, mW.p, splan.nsplit,
+                                              (size_t)ntraj * ld, mec.p, etot.p);
+        prof_end(stream);
+        SCLMD_CUDA(cudaGetLastError());
+        ++launches;
+        return 0;
+    }
+    int enter_modal() {       // real-space (q, p) -> (Q, Pi, p_c, g); the real-space path has been flushed by the caller
+        if (!modal_tables) if (int e = build_modal_tables()) return e;
+        const SplitPlan one = one_plan();
+        mqi = 0;
+        if (int e = gemm_nt(ntraj, nph, ld, q.p, ld, mUT.p, ld, mQ[0].p, ld, one, -1, st)) return e;       // Q = q . U
+        if (int e = gemm_nt(ntraj, nph, ld, p.p, ld, mUT.p, ld, mP.p, ld, one, -1, st)) return e;          // Pi = p . U
+        for (size_t i = 0; i < baths.size(); ++i) {
+            k_modal_gather_pc<<<ntraj, 128, 0, st>>>(baths[i]->cids.p, baths[i]->nc, moff[i], ncs, ld, p.p, mpc.p);
+            SCLMD_CUDA(cudaGetLastError());
+            ++launches;
+        }
+        if (int e = gemm_nt(ntraj, ncs, ld, mQ[0].p, ld, mEL.p, ld, mgn.p, ncs, gaplan, -1, st)) return e; // g = (K q)[cids]
+        const size_t nb = (size_t)ntraj * ncs;
+        k_modal_fold<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(mgn.p, gaplan.nsplit, nb, mg.p);
+        SCLMD_CUDA(cudaGetLastError());
+        ++launches;
+        m_pending = false;
+        modal_state = true;
+        return 0;
+    }
+    int modal_flush() {       // pending evaluations B, C of step t-1; afterwards mP holds Pi_t (no half kick)
+        if (!m_pending) return 0;
+        if (noise_pending) {
+            SCLMD_CUDA(cudaStreamWaitEvent(st, evN, 0));
+            noise_pending = false;
+        }
+        if (int e = modal_bath(view(), 1, 0)) return e;
+        if (int e = gemm_nt(ntraj, nph, ncs, msb.p, ncs, mET.p, ncs, mW.p, ld, splan, -1, st)) return e;
+        if (int e = modal_pq(1, 0, st)) return e;
+        m_pending = false;
+        return 0;
+    }
+    int leave_modal() {       // (Q, Pi) -> real-space (q, p)
+        if (int e = modal_flush()) return e;
+        const SplitPlan one = one_plan();
+        if (int e = gemm_nt(ntraj, nph, ld, mQ[mqi].p, ld, mU.p, ld, q.p, ld, one, -1, st)) return e;      // q = Q . U^T
+        if (int e = gemm_nt(ntraj, nph, ld, mP.p, ld, mU.p, ld, p.p, ld, one, -1, st)) return e;           // p = Pi . U^T
+        modal_state = false;
+        g_valid = false;
+        d_valid = false;
+        bc_pending = false;
+        return 0;
+    }
+    int sync_real() {         // whatever mode the state is in: finish pending evaluations and make q, p current
+        if (modal_state) return leave_modal();
+        return flush();
+    }
+    int modal_step() {
+        if (noise_pending) {
+            SCLMD_CUDA(cudaStreamWaitEvent(st, evN, 0));
+            noise_pending = false;
+        }
+        if (int e = modal_bath(view(), m_pending ? 1 : 0, 1)) return e;      // [B, C of step t-1] + A of step t; pushes p_t[cids]
+        SCLMD_CUDA(cudaEventRecord(evA, st));
+        SCLMD_CUDA(cudaStreamWaitEvent(st2, evA, 0));
+        // st2: scatter -> modal update (etot[t], Q_{t+1}) -> gather;   st: the history tails S'(t)
+        if (int e = gemm_nt(ntraj, nph, ncs, msb.p, ncs, mET.p, ncs, mW.p, ld, splan, 4, st2)) return e;
+        if (int e = modal_pq(m_pending ? 1 : 0, 1, st2)) return e;
+        SCLMD_CUDA(cudaEventRecord(evObs, st2));
+        obs_slab = t % nmd;
+        if (int e = gemm_nt(ntraj, ncs, ld, mQ[mqi ^ 1].p, ld, mEL.p, ld, mgn.p, ncs, gaplan, 5, st2)) return e;
+        SCLMD_CUDA(cudaEventRecord(evG, st2));
+        for (auto &b : baths) if (int e = tail_step(*b, t)) return e;
+        SCLMD_CUDA(cudaStreamWaitEvent(st, evG, 0));
+        mqi ^= 1;
+        ++t;
+        dt_synced = false;
+        m_pending = true;
+        return 0;
+    }
+
     int step() {
         BathSet bs = view();
         const bool lin = any_lin();
@@ -1797,11 +2135,12 @@ int sclmd_md_set_dyn(sclmd_md *h, const double *K) {
     if (h) h->drop_graphs();      // captured kernel arguments are about to change
     SCLMD_REQUIRE(h && K, "sclmd_md_set_dyn: NULL argument");
     SCLMD_CUDA(cudaSetDevice(h->device));
-    if (int e = h->flush()) return e;
+    if (int e = h->sync_real()) return e;
     SCLMD_CUDA(cudaMemcpy2DAsync(h->K.p, h->ld * sizeof(double), K, h->nph * sizeof(double), h->nph * sizeof(double), h->nph,
                                  cudaMemcpyHostToDevice, h->st));
     SCLMD_CUDA(cudaStreamSynchronize(h->st));
     h->have_dyn = true;
+    h->have_modes = false;       // the eigen-decomposition belongs to the previous matrix: sclmd_md_set_modes again
     h->g_valid = false;
     h->kc_valid = false;
     h->kfrag_valid = false;
@@ -1813,7 +2152,7 @@ int sclmd_md_set_constraint(sclmd_md *h, const int32_t *idx, int n) {
     if (h) h->drop_graphs();      // captured kernel arguments are about to change
     SCLMD_REQUIRE(h && (n == 0 || idx), "sclmd_md_set_constraint: NULL argument");
     SCLMD_CUDA(cudaSetDevice(h->device));
-    if (int e = h->flush()) return e;
+    if (int e = h->sync_real()) return e;
     std::vector<unsigned char> m(h->nph, 0);
     for (int i = 0; i < n; ++i) {
         SCLMD_REQUIRE(idx[i] >= 0 && idx[i] < h->nph, "sclmd_md_set_constraint: index %d out of range", idx[i]);
@@ -1850,7 +2189,7 @@ int sclmd_md_add_bath(sclmd_md *h, const int32_t *cids, int nc, int ml, const do
     SCLMD_REQUIRE((int)h->baths.size() < MAXB, "sclmd_md_add_bath: at most %d baths", MAXB);
     SCLMD_REQUIRE(!(Mq || Mp) || ml == 1, "sclmd_md_add_bath: Mq/Mp only act for time-local baths (baths.py:243-249)");
     SCLMD_CUDA(cudaSetDevice(h->device));
-    if (int e = h->flush()) return e;
+    if (int e = h->sync_real()) return e;
     std::unique_ptr<Bath> b(new Bath());
     b->nc = nc; b->ncp = round_up(nc, 2); b->ml = ml; b->kind = kernel_kind;
     b->c0 = ml > 1 ? h->dt : 1.0;  // baths.py:454-457: the dt factor only exists for ml > 1
@@ -1863,6 +2202,7 @@ int sclmd_md_add_bath(sclmd_md *h, const int32_t *cids, int nc, int ml, const do
         SCLMD_REQUIRE(inv[cids[a]] < 0, "sclmd_md_add_bath: duplicate dof index %d", cids[a]);
         inv[cids[a]] = a;
     }
+    b->cids_h.assign(cids, cids + nc);
     SCLMD_CUDA(b->cids.alloc(nc)); SCLMD_CUDA(b->inv.alloc(h->nph));
     SCLMD_CUDA(cudaMemcpy(b->cids.p, cids, nc * sizeof(int), cudaMemcpyHostToDevice));
     SCLMD_CUDA(cudaMemcpy(b->inv.p, inv.data(), h->nph * sizeof(int), cudaMemcpyHostToDevice));
@@ -1921,6 +2261,7 @@ int sclmd_md_add_bath(sclmd_md *h, const int32_t *cids, int nc, int ml, const do
     SCLMD_CUDA(b->noise.alloc((size_t)h->nmd * ntraj * ncp));
     SCLMD_CUDA(b->cur.alloc((size_t)h->nmd * ntraj));
     if (bath_out) *bath_out = (int)h->baths.size();
+    h->modal_tables = false;
     h->baths.push_back(std::move(b));
     return SCLMD_OK;
 }
@@ -1962,7 +2303,7 @@ int sclmd_md_get_noise(sclmd_md *h, int bath, int traj0, int nsel, double *noise
 int sclmd_md_set_state(sclmd_md *h, const double *q, const double *p, int64_t t) {
     SCLMD_REQUIRE(h, "sclmd_md_set_state: NULL handle");
     SCLMD_CUDA(cudaSetDevice(h->device));
-    if (int e = h->flush()) return e;
+    if (int e = h->sync_real()) return e;
     const size_t w = h->nph * sizeof(double), pitch = h->ld * sizeof(double);
     if (q) SCLMD_CUDA(cudaMemcpy2DAsync(h->q.p, pitch, q, w, w, h->ntraj, cudaMemcpyHostToDevice, h->st));
     if (p) SCLMD_CUDA(cudaMemcpy2DAsync(h->p.p, pitch, p, w, w, h->ntraj, cudaMemcpyHostToDevice, h->st));
@@ -1979,7 +2320,7 @@ int sclmd_md_set_state(sclmd_md *h, const double *q, const double *p, int64_t t)
 int sclmd_md_get_state(sclmd_md *h, double *q, double *p, int64_t *t) {
     SCLMD_REQUIRE(h, "sclmd_md_get_state: NULL handle");
     SCLMD_CUDA(cudaSetDevice(h->device));
-    if (int e = h->flush()) return e;
+    if (int e = h->sync_real()) return e;
     const size_t w = h->nph * sizeof(double), pitch = h->ld * sizeof(double);
     if (q) SCLMD_CUDA(cudaMemcpy2DAsync(q, w, h->q.p, pitch, w, h->ntraj, cudaMemcpyDeviceToHost, h->st));
     if (p) SCLMD_CUDA(cudaMemcpy2DAsync(p, w, h->p.p, pitch, w, h->ntraj, cudaMemcpyDeviceToHost, h->st));
@@ -2075,16 +2416,27 @@ int sclmd_md_run(sclmd_md *h, int64_t nsteps, float *elapsed_ms) {
     SCLMD_CUDA(cudaSetDevice(h->device));
     SCLMD_CUDA(cudaEventRecord(h->ev0, h->st));
     bool done = false;
-    if (nsteps >= 8 && h->ens_ok()) {     // short runs (the per-step end-to-end path) stay on the launch chain
+    const bool ens = h->ens_ok(), persist = h->persist_ok();
+    const bool modal = nsteps > 0 && !ens && !persist && h->modal_ok();
+    if (h->modal_state && !modal && nsteps > 0)
+        if (int e = h->sync_real()) return e;
+    if (nsteps >= 8 && ens) {             // short runs (the per-step end-to-end path) stay on the launch chain
         if (int e = h->flush()) return e;
         const int e = h->run_ens(nsteps);
         if (e < 0) return e;
         done = e == 0;          // 1: the state does not fit shared memory, take the launch chain
     }
     if (done) {
-    } else if (nsteps > 0 && h->persist_ok()) {
+    } else if (nsteps > 0 && persist) {
         if (int e = h->flush()) return e;
         if (int e = h->run_persist(nsteps)) return e;
+    } else if (modal) {                   // eigenbasis propagation: gather + scatter products instead of K.q
+        if (!h->modal_state) {
+            if (int e = h->flush()) return e;
+            if (int e = h->enter_modal()) return e;
+        }
+        for (int64_t s = 0; s < nsteps; ++s)
+            if (int e = h->modal_step()) return e;
     } else {
         for (int64_t s = 0; s < nsteps; ++s)
             if (int e = h->step()) return e;
@@ -2108,7 +2460,7 @@ int sclmd_md_set_external_force(sclmd_md *h, int on) {
     SCLMD_REQUIRE(h, "sclmd_md_set_external_force: NULL handle");
     SCLMD_REQUIRE(!h->ext_open, "sclmd_md_set_external_force: a step is open (sclmd_md_step_end missing)");
     SCLMD_CUDA(cudaSetDevice(h->device));
-    if (int e = h->flush()) return e;
+    if (int e = h->sync_real()) return e;
     h->drop_graphs();
     h->ext_force = on != 0;
     h->g_valid = false;
@@ -2160,7 +2512,7 @@ int sclmd_md_step_end(sclmd_md *h, const double *f_trial) {
 int sclmd_md_set_force_output(sclmd_md *h, int on) {
     SCLMD_REQUIRE(h, "sclmd_md_set_force_output: NULL handle");
     SCLMD_CUDA(cudaSetDevice(h->device));
-    if (int e = h->flush()) return e;
+    if (int e = h->sync_real()) return e;
     h->drop_graphs();
     if (on) {
         if (!h->fC.p) SCLMD_CUDA(h->fC.alloc((size_t)h->ntraj * h->ld));
@@ -2216,7 +2568,7 @@ int sclmd_md_set_persistent(sclmd_md *h, int on) {
 int sclmd_md_set_profiling(sclmd_md *h, int on) {
     SCLMD_REQUIRE(h, "sclmd_md_set_profiling: NULL handle");
     h->profiling = on != 0;
-    for (int i = 0; i < 4; ++i) { h->prof_ms[i] = 0; h->prof_n[i] = 0; }
+    for (int i = 0; i < 8; ++i) { h->prof_ms[i] = 0; h->prof_n[i] = 0; }
     return SCLMD_OK;
 }
 
@@ -2236,6 +2588,69 @@ int sclmd_md_get_profile_all(sclmd_md *h, double *ms, int64_t *n) {
     return SCLMD_OK;
 }
 
+// ms[8], n[8]: kinds 0-3 as above; modal mode: 4 = scatter product, 5 = gather product, 6 = bath-dof kernel, 7 = modal update
+int sclmd_md_get_profile_ex(sclmd_md *h, double *ms, int64_t *n) {
+    SCLMD_REQUIRE(h && ms && n, "sclmd_md_get_profile_ex: NULL argument");
+    for (int i = 0; i < 8; ++i) { ms[i] = h->prof_ms[i]; n[i] = h->prof_n[i]; }
+    return SCLMD_OK;
+}
+
+// md.setDyn keeps the eigen-decomposition it projects with (md.py:266-281: hw = sqrt(lam), U): handing it over lets the handle
+// propagate in the eigenbasis (k_modal_bath) whenever that is cheaper and the problem allows it (no constraints, no force driver,
+// diagonal-kernel baths on disjoint dofs).  lam[nph] (already clipped at 0), U[nph*nph] row-major with the eigenvectors as COLUMNS
+// (numpy.linalg.eigh).  Checked against the matrix of sclmd_md_set_dyn: max |K U - U diag(lam)| <= 1e-9 max(lam).
+int sclmd_md_set_modes(sclmd_md *h, const double *lam, const double *U) {
+    SCLMD_REQUIRE(h && lam && U, "sclmd_md_set_modes: NULL argument");
+    if (!h->have_dyn) {
+        set_error("sclmd_md_set_modes: set the dynamical matrix first (sclmd_md_set_dyn)");
+        return SCLMD_ERR_STATE;
+    }
+    SCLMD_CUDA(cudaSetDevice(h->device));
+    if (int e = h->sync_real()) return e;
+    const int nph = h->nph, ld = h->ld;
+    h->have_modes = false;
+    h->modal_tables = false;
+    SCLMD_CUDA(h->mU.alloc((size_t)nph * ld)); SCLMD_CUDA(h->mUT.alloc((size_t)nph * ld)); SCLMD_CUDA(h->mlam.alloc(ld));
+    SCLMD_CUDA(cudaMemcpy2DAsync(h->mU.p, ld * sizeof(double), U, nph * sizeof(double), nph * sizeof(double), nph, cudaMemcpyHostToDevice, h->st));
+    SCLMD_CUDA(cudaMemcpyAsync(h->mlam.p, lam, nph * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    k_modal_transpose<<<dim3(cdiv(nph, 32), cdiv(nph, 32)), dim3(32, 8), 0, h->st>>>(h->mU.p, nph, ld, h->mUT.p);
+    SCLMD_CUDA(cudaGetLastError());
+    // residual of the decomposition against the matrix the real-space path multiplies with
+    DevBuf<double> KU;
+    DevBuf<unsigned long long> mx;
+    SCLMD_CUDA(KU.alloc((size_t)nph * ld)); SCLMD_CUDA(mx.alloc(2));
+    const SplitPlan one{nph > 64 ? 0 : (nph > 16 ? 1 : 2), 1, ld};
+    if (int e = h->gemm_nt(nph, nph, ld, h->K.p, ld, h->mUT.p, ld, KU.p, ld, one, -1, h->st)) return e;
+    k_modal_residual<<<nph, 128, 0, h->st>>>(KU.p, h->mU.p, h->mlam.p, nph, ld, mx.p);
+    SCLMD_CUDA(cudaGetLastError());
+    unsigned long long bits[2] = {0, 0};
+    SCLMD_CUDA(cudaMemcpyAsync(bits, mx.p, sizeof(bits), cudaMemcpyDeviceToHost, h->st));
+    SCLMD_CUDA(cudaStreamSynchronize(h->st));
+    h->launches += 3;
+    double res, lmax;
+    memcpy(&res, &bits[0], 8);
+    memcpy(&lmax, &bits[1], 8);
+    for (int k = 0; k < nph; ++k)
+        SCLMD_REQUIRE(lam[k] >= 0.0, "sclmd_md_set_modes: negative eigenvalue %g (md.setDyn clips them to 0, md.py:268-274)", lam[k]);
+    SCLMD_REQUIRE(res <= 1e-9 * std::max(lmax, 1e-300), "sclmd_md_set_modes: K U != U diag(lam): residual %.3e against max(lam) = %.3e", res, lmax);
+    h->have_modes = true;
+    return SCLMD_OK;
+}
+
+// 1 (default): use the eigenbasis propagation when modes are set and the problem allows it; 0: always real space
+int sclmd_md_set_modal(sclmd_md *h, int on) {
+    SCLMD_REQUIRE(h, "sclmd_md_set_modal: NULL handle");
+    SCLMD_CUDA(cudaSetDevice(h->device));
+    if (int e = h->sync_real()) return e;
+    h->modal_on = on != 0;
+    return SCLMD_OK;
+}
+// 1 when the next sclmd_md_run would propagate in the eigenbasis
+int sclmd_md_modal_active(sclmd_md *h) {
+    SCLMD_REQUIRE(h, "sclmd_md_modal_active: NULL handle");
+    return (!h->ens_ok() && !h->persist_ok() && h->modal_ok()) ? 1 : 0;
+}
+
 // rows[nslab][ntraj][nc] (time-major, as the device table) for time slabs [slab0, slab0+nslab) mod nmd
 int sclmd_md_set_noise_rows(sclmd_md *h, int bath, int slab0, int nslab, const double *rows) {
     if (int e = check_bath(h, bath, "sclmd_md_set_noise_rows")) return e;
@@ -2243,7 +2658,7 @@ int sclmd_md_set_noise_rows(sclmd_md *h, int bath, int slab0, int nslab, const d
     SCLMD_CUDA(cudaSetDevice(h->device));
     Bath &b = *h->baths[bath];
     const size_t rowsz = (size_t)h->ntraj;
-    if (h->bc_pending && (int)(((h->t % h->nmd) - slab0 + h->nmd) % h->nmd) < nslab)     // pending evaluations B, C read slab t
+    if ((h->bc_pending || h->m_pending) && (int)(((h->t % h->nmd) - slab0 + h->nmd) % h->nmd) < nslab)     // pending evaluations B, C read slab t
         if (int e = h->flush()) return e;
     // ASYNCHRONOUS on the handle's copy stream: the upload overlaps the step that is running; the next
     // sclmd_md_run orders itself after it.  `rows` must stay valid until the next synchronising call
@@ -2385,7 +2800,7 @@ int sclmd_md_time_tail(sclmd_md *h, int bath, int reps, float *avg_ms) {
 int sclmd_md_time_potforce(sclmd_md *h, int reps, float *avg_ms) {
     SCLMD_REQUIRE(h && reps > 0 && avg_ms, "sclmd_md_time_potforce: bad arguments");
     SCLMD_CUDA(cudaSetDevice(h->device));
-    if (int e = h->flush()) return e;
+    if (int e = h->sync_real()) return e;
     if (int e = h->potforce(h->q.p, h->Gn.p)) return e;
     SCLMD_CUDA(cudaEventRecord(h->ev0, h->st));
     for (int r = 0; r < reps; ++r)

@@ -35,6 +35,19 @@ class MDEngine:
         K = as_f64(K, (self.nph, self.nph))
         check(_lib.lib().sclmd_md_set_dyn(self._h, dptr(K)))
 
+    def set_modes(self, lam, U):
+        """eigen-decomposition of the matrix given to set_dyn (K = U diag(lam) U^T, eigenvectors as columns, md.py:266-281):
+        enables the eigenbasis propagation where the problem allows it"""
+        lam = as_f64(lam, (self.nph,))
+        U = as_f64(U, (self.nph, self.nph))
+        check(_lib.lib().sclmd_md_set_modes(self._h, dptr(lam), dptr(U)))
+
+    def set_modal(self, on=True):
+        check(_lib.lib().sclmd_md_set_modal(self._h, 1 if on else 0))
+
+    def modal_active(self):
+        return bool(check(_lib.lib().sclmd_md_modal_active(self._h)))
+
     def set_constraint(self, idx):
         idx = as_i32(idx)
         check(_lib.lib().sclmd_md_set_constraint(self._h, iptr(idx), len(idx)))
@@ -103,6 +116,13 @@ class MDEngine:
         n = np.zeros(4, dtype=np.int64)
         check(_lib.lib().sclmd_md_get_profile_all(self._h, dptr(ms), n.ctypes.data_as(_lib.c_int64_p)))
         names = ("tail_direct", "potforce", "tail_far", "tail_near")
+        return {k: dict(ms=float(ms[i]), launches=int(n[i])) for i, k in enumerate(names)}
+
+    def profile_ex(self):
+        ms = np.zeros(8)
+        n = np.zeros(8, dtype=np.int64)
+        check(_lib.lib().sclmd_md_get_profile_ex(self._h, dptr(ms), n.ctypes.data_as(_lib.c_int64_p)))
+        names = ("tail_direct", "potforce", "tail_far", "tail_near", "modal_scatter", "modal_gather", "modal_bath", "modal_update")
         return {k: dict(ms=float(ms[i]), launches=int(n[i])) for i, k in enumerate(names)}
 
     def set_profiling(self, on=True):

@@ -177,6 +177,7 @@ class md:
             self.dyn = None
             self.hw = [1.0]
             self.U = None
+            self._av = None
             return
         ndyn = np.array(dyn)
         n = chkShape(ndyn)
@@ -191,6 +192,7 @@ class md:
             av = np.where(av < 0, 0.0, av)
         self.hw = np.sqrt(av)
         self.U = np.array(au)
+        self._av = np.array(av)            # clipped eigenvalues: the device propagates in this eigenbasis when it can
         self.dyn = mdot(self.U, np.diag(np.array(av)), np.transpose(self.U))
         self._eng_sig = None
 
@@ -245,6 +247,11 @@ class md:
             eng.set_external_force(True)
         else:
             eng.set_dyn(self.dyn)
+            if getattr(self, "_av", None) is not None and self.U is not None and np.shape(self.U) == (self.nph, self.nph):
+                try:
+                    eng.set_modes(self._av, self.U)
+                except _lib.SclmdError:      # md.dyn was reassigned after setDyn: U, hw no longer belong to it -> real space
+                    pass
         if self.constraint is not None:
             eng.set_constraint(np.concatenate([np.asarray(list(c), dtype=np.int32) for c in self.constraint]))
         for b in self.baths:

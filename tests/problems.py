@@ -42,6 +42,14 @@ def psd_project(K):
     return au @ np.diag(av) @ au.T
 
 
+def psd_project_modes(K):
+    """psd_project together with the decomposition md.setDyn keeps (md.py:266-281): (K, lam clipped at 0, U)"""
+    K = 0.5 * (K + K.T)
+    av, au = np.linalg.eigh(K)
+    av = np.where(av < 0, 0.0, av)
+    return au @ np.diag(av) @ au.T, av, au
+
+
 def full_kernel(ml, nc, dt, seed, gamma0=0.02, tau=12.0, w0=0.15, eps=0.1):
     """kernel[j] = gamma0 exp(-j dt/tau) cos(w0 j dt) (I + eps S), S symmetric seeded."""
     rng = np.random.default_rng(seed)

@@ -309,3 +309,34 @@ def test_reordxyz():
     assert a2 == [6, 1, 6, 1, 79, 79] and [x[0] for x in x2] == [0.0, 3.0, 1.0, 2.0, 4.0, 5.0]
     with pytest.raises(ValueError):
         myio.reordxyz(anr, xyz, [2, 5])
+
+
+def test_modal_restatement_equals_the_real_space_one():
+    """oracle.ModalMD (propagation in the eigenbasis of md.setDyn, the specification of the engine's modal mode) against
+    oracle.EnsembleMD over 1024 steps: the difference stays at the level a 1-ulp change of K produces"""
+    natoms, nc, ml, ntraj, nmd = 30, 10, 40, 2, 64
+    nph, dt = 3 * natoms, 0.25 / 0.658
+    Kraw = P.spring_chain_dyn(natoms, seed=5)
+    lam, U = np.linalg.eigh(0.5 * (Kraw + Kraw.T))
+    lam = np.where(lam < 0, 0.0, lam)
+    K = U @ np.diag(lam) @ U.T
+    cids = [list(range(0, nc)), list(range(nph - nc, nph))]
+    ens, mod = O.EnsembleMD(K, dt, nmd, ntraj, None), O.ModalMD(lam, U, dt, nmd, ntraj)
+    for b in range(2):
+        kern, nz = P.diag_kernel(ml if b == 0 else 1, nc, dt, 50 + b), P.injected_noise(ntraj, nmd, nc, seed=60 + b)
+        ens.add_bath(cids[b], kern, nz)
+        mod.add_bath(cids[b], kern, nz)
+    rng = np.random.default_rng(7)
+    q0, p0 = 0.05 * rng.standard_normal((ntraj, nph)), 0.02 * rng.standard_normal((ntraj, nph))
+    ens.q[:], ens.p[:] = q0, p0
+    mod.set_state(q0, p0)
+    for s in range(1024):
+        ens.step()
+        mod.step()
+        if s in (0, 1, 63, 1023):
+            q, p = mod.state()
+            assert relerr(q, ens.q) < 1e-12 and relerr(p, ens.p) < 1e-12, s
+    keep = [k for k in range(nmd) if k != 1024 % nmd]          # ModalMD records evaluation A of the NEXT step at the end of a step
+    assert relerr(mod.etot[:, keep], ens.etot[:, keep]) < 1e-11
+    for b in range(2):
+        assert relerr(mod.baths[b]["cur"][:, keep], ens.baths[b]["cur"][:, keep]) < 1e-11
