@@ -24,6 +24,7 @@
 
 #include "common.cuh"
 #include "dgemm.cuh"
+#include "dgemm_tma.cuh"
 
 using namespace sclmd;
 
@@ -1430,17 +1431,7 @@ struct sclmd_md {
     }
 
     int potforce(const double *qsrc, double *dst, cudaStream_t stream = nullptr) {  // dst = qsrc . K^T   (md.py:467, sign applied by consumers)
-        if (!stream) stream = st;
-        GemmArgs g{};
-        g.M = ntraj; g.N = nph; g.Kseg = gplan.kseg; g.nseg = gplan.nsplit; g.segs_per_split = 1; g.Ktot = ld;
-        g.A = qsrc; g.lda = ld; g.a_seg_stride = gplan.kseg; g.a_head = 0; g.a_mod = 0;
-        g.B = K.p; g.ldb = ld; g.b_seg_stride = gplan.kseg; g.b_seg0 = 0;
-        g.C = dst; g.ldc = ld; g.c_split_stride = (long long)ntraj * ld; g.alpha = 1.0;
-        prof_begin(1, stream);
-        SCLMD_CUDA(launch_dgemm(g, gplan.nsplit, stream, gplan.cfg));
-        prof_end(stream);
-        ++launches;
-        return 0;
+        return gemm_nt(ntraj, nph, ld, qsrc, ld, K.p, ld, dst, ld, gplan, 1, stream ? stream : st);
     }
     int bath_lin(Bath &b, const double *x, const double *qq) {  // lin = [x|q][cids] . W^T
         k_gather_xq<<<ntraj, 128, 0, st>>>(b.cids.p, b.nc, b.ncp, b.Kw, ld, x, qq, b.xq.p);
@@ -1820,9 +1811,22 @@ struct sclmd_md {
         }
         return 2 * tot <= nph;                    // gather + scatter (4 nph sum nc) against K.q (2 nph^2)
     }
-    SplitPlan one_plan() const { return SplitPlan{ntraj > 64 ? 0 : (ntraj > 16 ? 1 : 2), 1, ld}; }
+    SplitPlan one_plan() const { return tma_usable(ntraj, nph) ? SplitPlan{-2, 1, ld} : SplitPlan{ntraj > 64 ? 0 : (ntraj > 16 ? 1 : 2), 1, ld}; }
+    TmaWorkspace tws[2];       // stream-K scratch of the TMA GEMM: one per stream it is launched on (st, st2)
+    // cfg -2 = persistent TMA / stream-K kernel (dgemm_tma.cuh): one C, no K-slices; otherwise the cp.async kernel with split-K
+    SplitPlan plan_gemm(int M, int N, int K, int max_split) const {
+        if (tma_usable(M, N)) return SplitPlan{-2, 1, K};
+        return plan_split_k(M, N, K, nsm, max_split);
+    }
     int gemm_nt(int M, int N, int K, const double *A, long long lda, const double *B, long long ldb, double *C, long long ldc,
                 const SplitPlan &pl, int kind, cudaStream_t stream) {
+        if (pl.cfg == -2) {
+            prof_begin(kind, stream);
+            if (int e = launch_dgemm_tma_plain(M, N, K, A, lda, B, ldb, C, ldc, 1.0, tws[stream == st2 ? 1 : 0], nsm, stream)) return e;
+            prof_end(stream, kind);
+            ++launches;
+            return 0;
+        }
         GemmArgs g{};
         g.M = M; g.N = N; g.Kseg = pl.kseg; g.nseg = pl.nsplit; g.segs_per_split = 1; g.Ktot = K;
         g.A = A; g.lda = lda; g.a_seg_stride = pl.kseg; g.B = B; g.ldb = ldb; g.b_seg_stride = pl.kseg;
@@ -1847,11 +1851,11 @@ struct sclmd_md {
             SCLMD_CUDA(cudaGetLastError());
             ++launches;
         }
-        splan = plan_split_k(ntraj, nph, ncs, nsm, 4);
-        gaplan = plan_split_k(ntraj, ncs, ld, nsm, 16);
+        splan = plan_gemm(ntraj, nph, ncs, 4);
+        gaplan = plan_gemm(ntraj, ncs, ld, 16);
         if (const char *e = getenv("SCLMD_MODAL_SPLITS")) {      // "scatter,gather" K-split counts for A/B measurements
             int a = 0, b = 0;
-            if (sscanf(e, "%d,%d", &a, &b) == 2 && a > 0 && b > 0) {
+            if (sscanf(e, "%d,%d", &a, &b) == 2 && a > 0 && b > 0 && splan.cfg != -2) {
                 splan.kseg = round_up(cdiv(ncs, a), 16); splan.nsplit = cdiv(ncs, splan.kseg);
                 gaplan.kseg = round_up(cdiv(ld, b), 16); gaplan.nsplit = cdiv(ld, gaplan.kseg);
             }
@@ -2096,7 +2100,7 @@ int sclmd_md_create(int nph, int ntraj, double dt, int nmd, int device, sclmd_md
     SCLMD_CUDA(cudaEventCreate(&h->ev1));
     const size_t n = (size_t)ntraj * h->ld;
     SCLMD_CUDA(h->K.alloc((size_t)nph * h->ld));
-    h->gplan = plan_split_k(ntraj, nph, h->ld, h->nsm, 4);
+    h->gplan = h->plan_gemm(ntraj, nph, h->ld, 4);
     SCLMD_CUDA(h->q.alloc(n)); SCLMD_CUDA(h->p.alloc(n));
     SCLMD_CUDA(h->G.alloc(n * h->gplan.nsplit)); SCLMD_CUDA(h->Gn.alloc(n * h->gplan.nsplit));
     SCLMD_CUDA(h->d_t.alloc(1));
@@ -2619,7 +2623,7 @@ int sclmd_md_set_modes(sclmd_md *h, const double *lam, const double *U) {
     DevBuf<double> KU;
     DevBuf<unsigned long long> mx;
     SCLMD_CUDA(KU.alloc((size_t)nph * ld)); SCLMD_CUDA(mx.alloc(2));
-    const SplitPlan one{nph > 64 ? 0 : (nph > 16 ? 1 : 2), 1, ld};
+    const SplitPlan one = tma_usable(nph, nph) ? SplitPlan{-2, 1, ld} : SplitPlan{nph > 64 ? 0 : (nph > 16 ? 1 : 2), 1, ld};
     if (int e = h->gemm_nt(nph, nph, ld, h->K.p, ld, h->mUT.p, ld, KU.p, ld, one, -1, h->st)) return e;
     k_modal_residual<<<nph, 128, 0, h->st>>>(KU.p, h->mU.p, h->mlam.p, nph, ld, mx.p);
     SCLMD_CUDA(cudaGetLastError());
@@ -2763,11 +2767,17 @@ int sclmd_dgemm_nt(int device, int M, int N, int K, const double *A, const doubl
     SCLMD_CUDA(dA.alloc((size_t)M * ldk)); SCLMD_CUDA(dB.alloc((size_t)N * ldk)); SCLMD_CUDA(dC.alloc((size_t)M * ldc));
     SCLMD_CUDA(cudaMemcpy2D(dA.p, ldk * sizeof(double), A, K * sizeof(double), K * sizeof(double), M, cudaMemcpyHostToDevice));
     SCLMD_CUDA(cudaMemcpy2D(dB.p, ldk * sizeof(double), B, K * sizeof(double), K * sizeof(double), N, cudaMemcpyHostToDevice));
-    GemmArgs g{};
-    g.M = M; g.N = N; g.Kseg = ldk; g.nseg = 1; g.segs_per_split = 1;
-    g.A = dA.p; g.lda = ldk; g.B = dB.p; g.ldb = ldk; g.C = dC.p; g.ldc = ldc; g.alpha = alpha;
-    SCLMD_CUDA(launch_dgemm(g, 1, nullptr));
-    SCLMD_CUDA(cudaDeviceSynchronize());
+    if (tma_usable(M, N)) {       // persistent TMA / stream-K kernel
+        TmaWorkspace w;
+        if (int e = launch_dgemm_tma_plain(M, N, K, dA.p, ldk, dB.p, ldk, dC.p, ldc, alpha, w, sm_count(device), nullptr)) return e;
+        SCLMD_CUDA(cudaDeviceSynchronize());
+    } else {
+        GemmArgs g{};
+        g.M = M; g.N = N; g.Kseg = ldk; g.nseg = 1; g.segs_per_split = 1;
+        g.A = dA.p; g.lda = ldk; g.B = dB.p; g.ldb = ldk; g.C = dC.p; g.ldc = ldc; g.alpha = alpha;
+        SCLMD_CUDA(launch_dgemm(g, 1, nullptr));
+        SCLMD_CUDA(cudaDeviceSynchronize());
+    }
     SCLMD_CUDA(cudaMemcpy2D(C, N * sizeof(double), dC.p, ldc * sizeof(double), N * sizeof(double), M, cudaMemcpyDeviceToHost));
     return SCLMD_OK;
 }
