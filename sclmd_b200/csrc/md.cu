@@ -1101,10 +1101,111 @@ __global__ void __launch_bounds__(352, 1) k_tail_far_ws(const double *__restrict
     }
 }
 
+// Generalisation of k_tail_far_ws to a time block of TBK steps and a WS-entry circular kernel window (WS >= TBK + SR, WS a
+// multiple of SR).  Sub-stage q consumes SR ring rows and needs the window entries [q SR, q SR + SR + TBK - 1).  Entry q SR + u is
+// dead once row u has been processed; the entry the NEXT sub-stage needs at its row u is loaded right then into a slot that has
+// just died, so at most TBK + SR entries are live and a load has a whole sub-stage (SR x TBK FMAs) to arrive.  All window indices
+// are compile-time (the sub-stage body is instantiated for the WS / SR phases of the circle).
+//   <T = 1, TBK = 32, SR = 8, NST = 10, WS = 40>: ONE ring pass per 32 steps (half the HBM traffic of the 16-step block) with the
+//   same register budget as <2, 16>: 32 accumulators per thread, and still one kernel-window load per 32 FMAs.
+template <int T, int TBK, int SR, int NST, int WS>
+// (11 warps x 184 registers = 64768: one CTA per SM; with launch bounds of 352 threads ptxas would stop at 168 and spill)
+__global__ void __maxnreg__(184) k_tail_far_wsx(const double *__restrict__ ring, const double *__restrict__ kern,
+                                                          double *__restrict__ out, int ntraj, int ml, int ncp, int base,
+                                                          int ages_per_split, double dt) {
+    static_assert(WS % SR == 0 && WS >= TBK + SR, "window too small");
+    constexpr int PH = WS / SR;
+    extern __shared__ __align__(128) double stage_mem[];   // [NST][T][SR][ncp]
+    __shared__ __align__(8) uint64_t full[NST], empty[NST];
+    const int ncons = blockDim.x - 32;
+    const int traj0 = blockIdx.x * T;
+    const int d_lo = blockIdx.y * ages_per_split, d_hi = min(d_lo + ages_per_split, ml);
+    const int nsub = (d_hi - d_lo + SR - 1) / SR;
+    const size_t tstride = (size_t)ml * ncp, stage_elems = (size_t)T * SR * ncp;
+    const unsigned rowbytes = (unsigned)ncp * 8u;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < NST; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], (unsigned)(ncons / 32));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if ((int)threadIdx.x >= ncons) {                        // ---- producer warp (one elected lane)
+        if ((int)threadIdx.x == ncons) {
+            for (int sc = 0; sc < nsub; ++sc) {
+                const int st = sc % NST;
+                if (sc >= NST) mbar_wait(&empty[st], (unsigned)(((sc / NST) - 1) & 1));
+                double *dst = stage_mem + (size_t)st * stage_elems;
+                mbar_expect_tx(&full[st], (unsigned)(T * SR) * rowbytes);
+                int lo = (base - (d_lo + sc * SR) - (SR - 1)) % ml;
+                if (lo < 0) lo += ml;
+                const int n1 = min(SR, ml - lo);
+#pragma unroll
+                for (int k = 0; k < T; ++k) {
+                    const double *src = ring + (size_t)min(traj0 + k, ntraj - 1) * tstride;
+                    bulk_g2s(dst + (size_t)k * SR * ncp, src + (size_t)lo * ncp, (unsigned)n1 * rowbytes, &full[st]);
+                    if (n1 < SR) bulk_g2s(dst + ((size_t)k * SR + n1) * ncp, src, (unsigned)(SR - n1) * rowbytes, &full[st]);
+                }
+            }
+        }
+        return;
+    }
+    const int c = threadIdx.x;
+    const bool active = c < ncp;
+    const int cc = active ? c : 0;
+    double acc[T][TBK];
+#pragma unroll
+    for (int k = 0; k < T; ++k)
+#pragma unroll
+        for (int s2 = 0; s2 < TBK; ++s2) acc[k][s2] = 0.0;
+    double W[WS];
+    const double *kbase = kern + (size_t)(d_lo + 2) * ncp + cc;     // window entry e: kbase[e * ncp]
+#pragma unroll
+    for (int i = 0; i < WS; ++i) W[i] = i < TBK + SR - 1 ? kbase[(size_t)i * ncp] : 0.0;
+    auto sub = [&](auto ph, int q) {
+        constexpr int O = decltype(ph)::value * SR;
+        const double *knew = kbase + (size_t)(q * SR + SR + TBK - 1) * ncp;       // entries the next sub-stage adds
+        const int st = q % NST;
+        mbar_wait(&full[st], (unsigned)((q / NST) & 1));
+        const double *sp = stage_mem + (size_t)st * stage_elems + cc;
+#pragma unroll
+        for (int u = 0; u < SR; ++u) {
+            double pv[T];
+#pragma unroll
+            for (int k = 0; k < T; ++k) pv[k] = sp[((size_t)k * SR + (SR - 1 - u)) * ncp];
+#pragma unroll
+            for (int s2 = 0; s2 < TBK; ++s2)
+#pragma unroll
+                for (int k = 0; k < T; ++k) acc[k][s2] = fma(W[(O + u + s2) % WS], pv[k], acc[k][s2]);
+            W[(O + SR + TBK - 1 + u) % WS] = knew[(size_t)u * ncp];       // slot of an entry that died at row u - 1 (or earlier)
+        }
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[st]);
+    };
+    for (int q0 = 0; q0 < nsub; q0 += PH) {
+        sub(std::integral_constant<int, 0>{}, q0);
+        if constexpr (PH > 1) if (q0 + 1 < nsub) sub(std::integral_constant<int, 1 % PH>{}, q0 + 1);
+        if constexpr (PH > 2) if (q0 + 2 < nsub) sub(std::integral_constant<int, 2 % PH>{}, q0 + 2);
+        if constexpr (PH > 3) if (q0 + 3 < nsub) sub(std::integral_constant<int, 3 % PH>{}, q0 + 3);
+        if constexpr (PH > 4) if (q0 + 4 < nsub) sub(std::integral_constant<int, 4 % PH>{}, q0 + 4);
+        if constexpr (PH > 5) if (q0 + 5 < nsub) sub(std::integral_constant<int, 5 % PH>{}, q0 + 5);
+        static_assert(PH <= 6, "add phases");
+    }
+    if (active) {
+#pragma unroll
+        for (int s2 = 0; s2 < TBK; ++s2)
+#pragma unroll
+            for (int k = 0; k < T; ++k)
+                if (traj0 + k < ntraj) out[(((size_t)blockIdx.y * TBK + s2) * ntraj + traj0 + k) * ncp + c] = dt * acc[k][s2];
+    }
+}
+
 // tail[traj][c] = Near_s + sum_z Far[z][s]   (written where the phase kernels expect a single partial)
 __global__ void __launch_bounds__(256) k_tail_near(const double *__restrict__ ring, const double *__restrict__ kern,
                                                     const double *__restrict__ far, double *__restrict__ out, int ntraj, int ml,
-                                                    int ncp, int head, int s, int nsplit, double dt) {
+                                                    int ncp, int head, int s, int nsplit, double dt, int tb) {
     const int traj = blockIdx.x;
     const double *r = ring + (size_t)traj * ml * ncp;
     for (int c = threadIdx.x; c < ncp; c += blockDim.x) {
@@ -1115,7 +1216,7 @@ __global__ void __launch_bounds__(256) k_tail_near(const double *__restrict__ ri
             slot = slot == 0 ? ml - 1 : slot - 1;
         }
         double f = 0.0;
-        for (int z = 0; z < nsplit; ++z) f += far[(((size_t)z * TB + s) * ntraj + traj) * ncp + c];
+        for (int z = 0; z < nsplit; ++z) f += far[(((size_t)z * tb + s) * ntraj + traj) * ncp + c];
         out[(size_t)traj * ncp + c] = dt * acc + f;
     }
 }
@@ -1475,20 +1576,33 @@ struct sclmd_md {
         return 0;
     }
 
+    // length of the time block of bath b: 32 steps with the windowed ring-pass kernel (one trajectory per CTA), 16 with the others
+    bool far32 = true;
+    int block_len(const Bath &b) const { return (b.ncp <= 320 && far_tma && far_ws && far32) ? 2 * TB : TB; }
     // friction tail S'(tt) of step tt (ring already holds p_tt)
     int tail_step(Bath &b, long long tt) {
         if (b.ml <= 1) return 0;
         auto fmod_ll = [](long long a, long long m) { long long r = a % m; return r < 0 ? r + m : r; };
         if (!(b.blocked && tail_block)) return tail_direct(b, (int)fmod_ll(tt, b.ml));
-        const long long t0 = tt - fmod_ll(tt, TB);
+        const int tb = block_len(b);
+        const long long t0 = tt - fmod_ll(tt, tb);
         const int T = ntraj >= 4 ? 4 : 1;
         if (b.far_t0 != t0) {
             const int base = (int)fmod_ll(t0 - 1, b.ml);
             const int ntiles = cdiv(b.ncp, 256), ct = cdiv(b.ncp, ntiles);
-            const int aps = round_up(cdiv(b.ml, b.far_nsplit), TB);
+            const int aps = round_up(cdiv(b.ml, b.far_nsplit), tb);
             dim3 grid(cdiv(ntraj, T), b.far_nsplit, ntiles);
             prof_begin(2);
-            if (b.ncp <= 320 && ntraj >= 2 && far_tma) {
+            if (tb == 2 * TB) {
+                auto kern = k_tail_far_wsx<1, 2 * TB, 8, 10, 40>;
+                static bool cfg = false;
+                if (!cfg) {
+                    SCLMD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+                    cfg = true;
+                }
+                const size_t smx = (size_t)10 * 1 * 8 * b.ncp * sizeof(double);    // ten stages x 1 trajectory x 8 rows
+                kern<<<dim3(ntraj, b.far_nsplit), round_up(b.ncp, 32) + 32, smx, st>>>(b.ring.p, b.kern.p, b.far.p, ntraj, b.ml, b.ncp, base, aps, dt);
+            } else if (b.ncp <= 320 && ntraj >= 2 && far_tma) {
                 static bool cfg = false;
                 if (!cfg) {
                     SCLMD_CUDA(cudaFuncSetAttribute(k_tail_far_tma<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -1514,7 +1628,7 @@ struct sclmd_md {
         }
         prof_begin(3);
         k_tail_near<<<ntraj, 256, 0, st>>>(b.ring.p, b.kern.p, b.far.p, b.tailp.p, ntraj, b.ml, b.ncp, (int)fmod_ll(tt, b.ml), (int)(tt - t0),
-                                           b.far_nsplit, dt);
+                                           b.far_nsplit, dt, tb);
         prof_end();
         SCLMD_CUDA(cudaGetLastError());
         ++launches;
@@ -2212,7 +2326,7 @@ int sclmd_md_add_bath(sclmd_md *h, const int32_t *cids, int nc, int ml, const do
     SCLMD_CUDA(cudaMemcpy(b->inv.p, inv.data(), h->nph * sizeof(int), cudaMemcpyHostToDevice));
     // kernel
     if (kernel_kind == SCLMD_KERNEL_DIAG) {
-        SCLMD_CUDA(b->kern.alloc((size_t)(ml + 5 * TB + 2) * ncp));   // rows >= ml stay 0 (branch-free drop-out / far-tail padding)
+        SCLMD_CUDA(b->kern.alloc((size_t)(ml + 8 * TB + 2) * ncp));   // rows >= ml stay 0 (branch-free drop-out / far-tail padding)
         SCLMD_CUDA(cudaMemcpy2D(b->kern.p, ncp * sizeof(double), kernel, nc * sizeof(double), nc * sizeof(double), ml, cudaMemcpyHostToDevice));
     } else {
         SCLMD_CUDA(b->kern.alloc((size_t)ml * nc * ncp));
@@ -2259,7 +2373,7 @@ int sclmd_md_add_bath(sclmd_md *h, const int32_t *cids, int nc, int ml, const do
             b->blocked = true;
             const int ctas = cdiv(ntraj, ntraj >= 4 ? 4 : 1) * cdiv(ncp, 256);
             b->far_nsplit = std::max(1, std::min({cdiv(4 * h->nsm, ctas), 16, ml / (4 * TB)}));
-            SCLMD_CUDA(b->far.alloc((size_t)b->far_nsplit * TB * ntraj * ncp));
+            SCLMD_CUDA(b->far.alloc((size_t)b->far_nsplit * 2 * TB * ntraj * ncp));     // up to 32 far tails per pass
         }
     }
     SCLMD_CUDA(b->noise.alloc((size_t)h->nmd * ntraj * ncp));
@@ -2398,6 +2512,7 @@ int sclmd_md_set_tail_block(sclmd_md *h, int on) {
     h->tail_block = on != 0;
     h->far_tma = on != 2;    // 2 = time-blocked with the plain-load far kernel (for A/B measurements)
     h->far_ws = on != 3;     // 3 = time-blocked with the two-stage TMA kernel (no producer warp)
+    h->far32 = on != 4;      // 4 = 16-step blocks with the warp-specialised kernel (two trajectories per CTA); default: 32-step blocks
     for (auto &b : h->baths) {   // the partial-tail layout differs between the modes: rebuild S'(t-1)
         b->far_t0 = -1;
         if (b->ml > 1) if (int e = h->tail_step(*b, h->t - 1)) return e;
