@@ -33,7 +33,7 @@ def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=128,
-                    help="timed steps (default 128 = 4 time blocks, ~0.12 s: long against one nvidia-smi clock sample, which can stall the GPU for ~2 ms)")
+                    help="timed steps (default 128 = 8 time blocks, ~0.12 s: long against one nvidia-smi clock sample, which can stall the GPU for ~2 ms)")
     ap.add_argument("--warmup", type=int, default=16)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c5_diag", choices=["c5_diag", "c5_full", "c2"])
@@ -359,7 +359,7 @@ def main():
     # ---------------- device-resident throughput (`value`)
     # The time-blocked history pass runs once per 16 steps: the timed region always starts on a block boundary (extra untimed
     # steps), so K steps contain ceil(K/16) passes -- exact for multiples of 16, pessimistic otherwise, never optimistic.
-    TBLK = 32
+    TBLK = 32 if args.tail_block == 4 else 16
     W_aligned = W + (-W) % TBLK
     # clock sampling (nvidia-smi, one sample per 100 ms) starts before the warm-up and the warm-up is extended (whole time blocks)
     # until the first sample has arrived, so that the timed region is guaranteed to contain samples taken under load
@@ -514,7 +514,8 @@ def main():
                           "share_of_step": pa[key]["ms"] / ms_prof})
     if pa["tail_far"]["launches"]:
         per = pa["tail_far"]["ms"] / pa["tail_far"]["launches"]
-        cands.append({"kernel": "k_tail_far_wsx<1,32,8,10,40> (time-blocked history pass, 32 steps per ring pass; producer warp + 10 bulk-copy stages of 8 ring rows)", "bound": "hbm",
+        cands.append({"kernel": ("k_tail_far_wsx<1,32,4,20,36> (time-blocked history pass, 32 steps per ring pass; producer warp + 20 bulk-copy stages of 4 ring rows)" if TBLK == 32 else
+                                 "k_tail_far_ws<2,8,5> (time-blocked history pass, 16 steps per ring pass; producer warp + 5 bulk-copy stages of 8 ring rows)"), "bound": "hbm",
                       "achieved": alg_ring / (per * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                       "frac": alg_ring / (per * 1e-3) / 1e9 / hbm_peak, "traffic": (traffic or {}).get("far_dram_bytes_per_launch"),
                       "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_ring, "avg_launch_ms": per,
@@ -571,7 +572,7 @@ def main():
             "gpu_launches": launches_total, "roofline": roof, "wall_ms_timed_region": wall_ms, "allreduce_ms": ar_ms,
             "heat_current_mean": [float(sums[b] / sums[2] / w["nmd"]) for b in range(2)],
             "noise_generation_s": noise_gen_s, "fp64_probe_tflops": probe, "also": also,
-            "tail_mode": "time-blocked (ring streamed once per 32 steps)" if args.tail_block == 1 else ("time-blocked, other kernel (--tail-block %d)" % args.tail_block if args.tail_block else "direct (ring streamed every step)"),
+            "tail_mode": "time-blocked (ring streamed once per 16 steps)" if args.tail_block == 1 else ("time-blocked, other kernel (--tail-block %d)" % args.tail_block if args.tail_block else "direct (ring streamed every step)"),
             "propagation": ("eigenbasis of md.setDyn (sclmd_md_set_modes): diagonal harmonic force, gather + scatter products over the bath dofs"
                             if modal else "real space: K.q GEMM every step")}
 

@@ -1106,11 +1106,19 @@ __global__ void __launch_bounds__(352, 1) k_tail_far_ws(const double *__restrict
 // dead once row u has been processed; the entry the NEXT sub-stage needs at its row u is loaded right then into a slot that has
 // just died, so at most TBK + SR entries are live and a load has a whole sub-stage (SR x TBK FMAs) to arrive.  All window indices
 // are compile-time (the sub-stage body is instantiated for the WS / SR phases of the circle).
-//   <T = 1, TBK = 32, SR = 8, NST = 10, WS = 40>: ONE ring pass per 32 steps (half the HBM traffic of the 16-step block) with the
-//   same register budget as <2, 16>: 32 accumulators per thread, and still one kernel-window load per 32 FMAs.
+//   <T = 1, TBK = 32, SR = 4, NST = 20, WS = 36>: ONE ring pass per 32 steps (half the HBM traffic of the 16-step block) within the
+//   168 registers that 352 threads allow (32 accumulators + 36 window entries per thread), one kernel-window load per 32 FMAs.
+template <int I, int N, class F>
+__device__ __forceinline__ void for_phases(F &f, int q0, int nsub) {      // f(phase I, sub-stage q0 + I) for the phases of one turn of the circle
+    if constexpr (I < N) {
+        if (q0 + I < nsub) {
+            f(std::integral_constant<int, I>{}, q0 + I);
+            for_phases<I + 1, N>(f, q0, nsub);
+        }
+    }
+}
 template <int T, int TBK, int SR, int NST, int WS>
-// (11 warps x 184 registers = 64768: one CTA per SM; with launch bounds of 352 threads ptxas would stop at 168 and spill)
-__global__ void __maxnreg__(184) k_tail_far_wsx(const double *__restrict__ ring, const double *__restrict__ kern,
+__global__ void __launch_bounds__(352, 1) k_tail_far_wsx(const double *__restrict__ ring, const double *__restrict__ kern,
                                                           double *__restrict__ out, int ntraj, int ml, int ncp, int base,
                                                           int ages_per_split, double dt) {
     static_assert(WS % SR == 0 && WS >= TBK + SR, "window too small");
@@ -1164,35 +1172,41 @@ __global__ void __maxnreg__(184) k_tail_far_wsx(const double *__restrict__ ring,
     const double *kbase = kern + (size_t)(d_lo + 2) * ncp + cc;     // window entry e: kbase[e * ncp]
 #pragma unroll
     for (int i = 0; i < WS; ++i) W[i] = i < TBK + SR - 1 ? kbase[(size_t)i * ncp] : 0.0;
-    auto sub = [&](auto ph, int q) {
+    // running stage cursor (no divisions in the loop): stage index, its barrier parity, its rows, and the kernel rows the next
+    // sub-stage adds; row offsets inside a stage are kept in registers
+    int st = 0;
+    unsigned par = 0;
+    const double *sp = stage_mem + cc;
+    const double *knew = kbase + (size_t)(SR + TBK - 1) * ncp;
+    int roff[SR];
+#pragma unroll
+    for (int u = 0; u < SR; ++u) roff[u] = u * ncp;
+    auto sub = [&](auto ph, int) {
         constexpr int O = decltype(ph)::value * SR;
-        const double *knew = kbase + (size_t)(q * SR + SR + TBK - 1) * ncp;       // entries the next sub-stage adds
-        const int st = q % NST;
-        mbar_wait(&full[st], (unsigned)((q / NST) & 1));
-        const double *sp = stage_mem + (size_t)st * stage_elems + cc;
+        mbar_wait(&full[st], par);
 #pragma unroll
         for (int u = 0; u < SR; ++u) {
             double pv[T];
 #pragma unroll
-            for (int k = 0; k < T; ++k) pv[k] = sp[((size_t)k * SR + (SR - 1 - u)) * ncp];
+            for (int k = 0; k < T; ++k) pv[k] = sp[k * SR * ncp + roff[SR - 1 - u]];
 #pragma unroll
             for (int s2 = 0; s2 < TBK; ++s2)
 #pragma unroll
                 for (int k = 0; k < T; ++k) acc[k][s2] = fma(W[(O + u + s2) % WS], pv[k], acc[k][s2]);
-            W[(O + SR + TBK - 1 + u) % WS] = knew[(size_t)u * ncp];       // slot of an entry that died at row u - 1 (or earlier)
+            W[(O + SR + TBK - 1 + u) % WS] = knew[roff[u]];       // slot of an entry that died at row u - 1 (or earlier)
         }
         __syncwarp();
         if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[st]);
+        knew += SR * ncp;
+        if (++st == NST) {
+            st = 0;
+            par ^= 1u;
+            sp = stage_mem + cc;
+        } else {
+            sp += stage_elems;
+        }
     };
-    for (int q0 = 0; q0 < nsub; q0 += PH) {
-        sub(std::integral_constant<int, 0>{}, q0);
-        if constexpr (PH > 1) if (q0 + 1 < nsub) sub(std::integral_constant<int, 1 % PH>{}, q0 + 1);
-        if constexpr (PH > 2) if (q0 + 2 < nsub) sub(std::integral_constant<int, 2 % PH>{}, q0 + 2);
-        if constexpr (PH > 3) if (q0 + 3 < nsub) sub(std::integral_constant<int, 3 % PH>{}, q0 + 3);
-        if constexpr (PH > 4) if (q0 + 4 < nsub) sub(std::integral_constant<int, 4 % PH>{}, q0 + 4);
-        if constexpr (PH > 5) if (q0 + 5 < nsub) sub(std::integral_constant<int, 5 % PH>{}, q0 + 5);
-        static_assert(PH <= 6, "add phases");
-    }
+    for (int q0 = 0; q0 < nsub; q0 += PH) for_phases<0, PH>(sub, q0, nsub);
     if (active) {
 #pragma unroll
         for (int s2 = 0; s2 < TBK; ++s2)
@@ -1576,8 +1590,8 @@ struct sclmd_md {
         return 0;
     }
 
-    // length of the time block of bath b: 32 steps with the windowed ring-pass kernel (one trajectory per CTA), 16 with the others
-    bool far32 = true;
+    // length of the time block of bath b: 16 steps; 32 with the windowed ring-pass kernel (one trajectory per CTA, A/B option)
+    bool far32 = false;      // measured at the config-5 shape: 5.09 ms per 32-step pass (15.8 TFLOP/s) against 2.18 ms per 16-step pass (18.3): off by default
     int block_len(const Bath &b) const { return (b.ncp <= 320 && far_tma && far_ws && far32) ? 2 * TB : TB; }
     // friction tail S'(tt) of step tt (ring already holds p_tt)
     int tail_step(Bath &b, long long tt) {
@@ -1594,13 +1608,13 @@ struct sclmd_md {
             dim3 grid(cdiv(ntraj, T), b.far_nsplit, ntiles);
             prof_begin(2);
             if (tb == 2 * TB) {
-                auto kern = k_tail_far_wsx<1, 2 * TB, 8, 10, 40>;
+                auto kern = k_tail_far_wsx<1, 2 * TB, 4, 20, 36>;
                 static bool cfg = false;
                 if (!cfg) {
                     SCLMD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
                     cfg = true;
                 }
-                const size_t smx = (size_t)10 * 1 * 8 * b.ncp * sizeof(double);    // ten stages x 1 trajectory x 8 rows
+                const size_t smx = (size_t)20 * 1 * 4 * b.ncp * sizeof(double);    // twenty stages x 1 trajectory x 4 rows
                 kern<<<dim3(ntraj, b.far_nsplit), round_up(b.ncp, 32) + 32, smx, st>>>(b.ring.p, b.kern.p, b.far.p, ntraj, b.ml, b.ncp, base, aps, dt);
             } else if (b.ncp <= 320 && ntraj >= 2 && far_tma) {
                 static bool cfg = false;
@@ -2512,7 +2526,7 @@ int sclmd_md_set_tail_block(sclmd_md *h, int on) {
     h->tail_block = on != 0;
     h->far_tma = on != 2;    // 2 = time-blocked with the plain-load far kernel (for A/B measurements)
     h->far_ws = on != 3;     // 3 = time-blocked with the two-stage TMA kernel (no producer warp)
-    h->far32 = on != 4;      // 4 = 16-step blocks with the warp-specialised kernel (two trajectories per CTA); default: 32-step blocks
+    h->far32 = on == 4;      // 4 = 32-step blocks (k_tail_far_wsx, one trajectory per CTA): half the ring traffic, but FMA-issue bound
     for (auto &b : h->baths) {   // the partial-tail layout differs between the modes: rebuild S'(t-1)
         b->far_t0 = -1;
         if (b->ml > 1) if (int e = h->tail_step(*b, h->t - 1)) return e;

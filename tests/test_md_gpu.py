@@ -136,7 +136,7 @@ def test_time_blocked_tails_equal_direct_tails(ml, nc, ntraj):
     ens.add_bath(list(range(nc)), kern, nz)
     ens.q[:], ens.p[:] = q0, p0
     engs = []
-    for mode in (1, 0):
+    for mode in (1, 0, 4):              # 16-step blocks, direct, 32-step blocks (k_tail_far_wsx)
         e = MDEngine(nph, ntraj, dt, nmd)
         e.set_dyn(K)
         e.add_bath(list(range(nc)), kern)
@@ -153,7 +153,8 @@ def test_time_blocked_tails_equal_direct_tails(ml, nc, ntraj):
             q, p, t = e.get_state()
             assert t == done and relerr(q, ens.q) < TOL_STEP and relerr(p, ens.p) < TOL_STEP, (ml, done)
     engs[0].set_tail_block(0)        # switch modes in the middle of a block
-    engs[1].set_tail_block(1)
+    engs[1].set_tail_block(4)
+    engs[2].set_tail_block(1)
     ens.run(23)
     for e in engs:
         e.run(23)
