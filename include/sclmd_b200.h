@@ -207,8 +207,9 @@ int sclmd_noise_plan_generate(sclmd_noise_plan *pl, int ntraj, const double *xi,
 int sclmd_noise_plan_generate_into(sclmd_noise_plan *pl, int ntraj, uint64_t seed, int64_t traj0,
                                    double *table, int ntraj_total, int ncp_table, int traj_offset);
 int64_t sclmd_noise_plan_launch_count(sclmd_noise_plan *pl);
-/* device milliseconds (CUDA events on the plan's stream): ms[0..2] = the stages of the last generate call (normal draws,
- * x = L xi, mirrored transform), ms[3] = the per-frequency factorisation at plan creation */
+/* ms[6]: device milliseconds (CUDA events on the plan's stream) of the stages of the last generate call (0 normal draws,
+ * 1 x = L xi, 2 mirrored transform) and of the per-frequency factorisation at plan creation (3); how many frequencies were
+ * factorised by the pivoted Cholesky kernel (4: positive semi-definite spectra) and by one-sided Jacobi (5: the others) */
 int sclmd_noise_plan_get_profile(sclmd_noise_plan *pl, double *ms);
 /* bath.gnoi() for every trajectory of an MD handle, no host round trip (baths.py:176-192,397-409) */
 int sclmd_md_generate_noise(sclmd_md *h, int bath, sclmd_noise_plan *plan, uint64_t seed, int64_t traj0);

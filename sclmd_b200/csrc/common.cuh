@@ -50,6 +50,17 @@ struct DevBuf {
         p = nullptr;
         n = 0;
     }
+    cudaError_t alloc_raw(size_t count) {      // scratch that is fully written before it is read: no zero-fill
+        release();
+        if (count == 0) return cudaSuccess;
+        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return e;
+        }
+        n = count;
+        return cudaSuccess;
+    }
     cudaError_t alloc(size_t count) {
         release();
         if (count == 0) return cudaSuccess;

@@ -13,10 +13,12 @@
 //      transform.  series = Re(FFT)/(dt*nmd)  (functions.py:51-53, baths.py:191,408)
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <memory>
 
 #include "common.cuh"
 #include "dgemm.cuh"
+#include "dgemm_tma.cuh"
 
 using namespace sclmd;
 
@@ -29,8 +31,9 @@ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint
     const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
     c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
 }
-__device__ __forceinline__ double philox_normal(uint64_t seed, uint32_t w, uint32_t k, uint64_t traj) {
-    uint32_t c[4] = {w, k, (uint32_t)traj, (uint32_t)(traj >> 32)};
+// two independent standard normals from one Philox4x32-10 block (Box-Muller: both branches): counter = (w, column pair, trajectory)
+__device__ __forceinline__ double2 philox_normal2(uint64_t seed, uint32_t w, uint32_t kpair, uint64_t traj) {
+    uint32_t c[4] = {w, kpair, (uint32_t)traj, (uint32_t)(traj >> 32)};
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
@@ -41,17 +44,23 @@ __device__ __forceinline__ double philox_normal(uint64_t seed, uint32_t w, uint3
     const uint64_t a = ((uint64_t)c[0] << 32) | c[1], b = ((uint64_t)c[2] << 32) | c[3];
     const double u1 = ((double)(a >> 11) + 0.5) * (1.0 / 9007199254740992.0);  // (0,1)
     const double u2 = ((double)(b >> 11) + 0.5) * (1.0 / 9007199254740992.0);
-    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+    const double rad = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    return make_double2(rad * cs, rad * sn);
 }
 
-// xi[w][traj][ncp] (pads zero)
+// xi[w][traj][ncp] (pads zero): one thread per column pair
 __global__ void k_fill_xi(double *__restrict__ xi, int nw, int ntraj, int nc, int ncp, uint64_t seed, long long traj0) {
-    const size_t n = (size_t)nw * ntraj * ncp;
+    const int hp = ncp / 2;
+    const size_t n = (size_t)nw * ntraj * hp;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
-        const int k = (int)(e % ncp);
-        const size_t r = e / ncp;
+        const int kp = (int)(e % hp);
+        const size_t r = e / hp;
         const int tr = (int)(r % ntraj), w = (int)(r / ntraj);
-        xi[e] = k < nc ? philox_normal(seed, (uint32_t)w, (uint32_t)k, (uint64_t)(traj0 + tr)) : 0.0;
+        double2 v = philox_normal2(seed, (uint32_t)w, (uint32_t)kp, (uint64_t)(traj0 + tr));
+        if (2 * kp + 1 >= nc) v.y = 0.0;
+        *reinterpret_cast<double2 *>(xi + 2 * e) = v;
     }
 }
 // injected draws: host layout [ntraj][nw][nc] -> [w][traj][ncp]
@@ -137,15 +146,15 @@ __global__ void __launch_bounds__(512) k_factor(const double *__restrict__ basis
                                                  const int *__restrict__ idx, const double *__restrict__ cre,
                                                  const double *__restrict__ cim, double *__restrict__ Aglob,
                                                  double *__restrict__ Gglob, int use_smem, double *__restrict__ L,
-                                                 double *__restrict__ evals) {
+                                                 double *__restrict__ evals, const int *__restrict__ wlist, int w0) {
     constexpr int E = CPLX ? 2 : 1;
     extern __shared__ double sm[];
     __shared__ double red[32];
     __shared__ int flag;
-    const int w = blockIdx.x, n = nc;
+    const int w = wlist ? wlist[w0 + blockIdx.x] : w0 + blockIdx.x, n = nc;      // frequency index; scratch is indexed by the CTA
     const size_t nn = (size_t)n * n * E;
-    double *A = Aglob + (size_t)w * nn;                 // column-major copy of the hermitianised covariance
-    double *G = use_smem ? sm : Gglob + (size_t)w * nn;
+    double *A = Aglob + (size_t)blockIdx.x * nn;        // column-major copy of the hermitianised covariance
+    double *G = use_smem ? sm : Gglob + (size_t)blockIdx.x * nn;
     double nf = 0.0;
     for (size_t e = threadIdx.x; e < (size_t)n * n; e += blockDim.x) {
         const int i = (int)(e % n), j = (int)(e / n);   // element (i,j), column-major
@@ -236,6 +245,170 @@ __global__ void __launch_bounds__(512) k_factor(const double *__restrict__ basis
         __syncthreads();
         if (!flag) break;
         __syncthreads();
+    }
+}
+
+
+// Pivoted Cholesky of a positive SEMI-definite covariance, one CTA per frequency: L L^H = A = clamp+(A) -- any such factor gives
+// the same Gaussian law as the reference's V sqrt(lambda+) (noise.py:82-84, 299-303), at n^3/3 flops and n barriers instead of
+// Jacobi sweeps.  A(w) = hermitianize(sum_m (cre + i cim) basis[idx]) is evaluated on the fly (never stored); thread i owns row i
+// and the remaining diagonal d_i of the Schur complement.  Diagonal pivoting stops when max d_i <= 1e-13 max|a_ii|: for a PSD matrix
+// every remaining entry is then below that bound.  A frequency is handed to the Jacobi kernel (status = 1) when the matrix is not
+// PSD: a remaining diagonal below -1e-11 max|a_ii|, or |(A - L L^H) v|_2 > 1e-11 max|a_ii| for a +-1 pseudo-random vector v.
+// L is kept column-major ([column k][row i]) in shared memory (n*n*E*8 <= 200 KB) or in a global scratch.
+template <bool CPLX>
+__global__ void __launch_bounds__(1024) k_chol(const double *__restrict__ basis, int nc, int ncp, int nterm, const int *__restrict__ idx,
+                                                const double *__restrict__ cre, const double *__restrict__ cim, double *__restrict__ Lglob,
+                                                int use_smem, double *__restrict__ L, int *__restrict__ status) {
+    constexpr int E = CPLX ? 2 : 1;
+    extern __shared__ double sm[];
+    __shared__ double red[32], sval[4];
+    __shared__ int redi[32], sidx;
+    const int w = blockIdx.x, n = nc, i = threadIdx.x;
+    const bool row = i < n;
+    double *Lc = use_smem ? sm : Lglob + (size_t)blockIdx.x * n * n * E;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+    auto aij = [&](int r, int c, double &ar, double &ai) {       // hermitianised covariance element (functions.py:198-200)
+        ar = 0.0;
+        ai = 0.0;
+        for (int m = 0; m < nterm; ++m) {
+            const int bi = idx[w * nterm + m];
+            if (bi < 0) continue;
+            const double *B = basis + (size_t)bi * n * n;
+            const double brc = B[(size_t)r * n + c], bcr = B[(size_t)c * n + r];
+            ar += 0.5 * cre[w * nterm + m] * (brc + bcr);
+            if (CPLX) ai += 0.5 * cim[w * nterm + m] * (brc - bcr);
+        }
+    };
+    auto block_max = [&](double v, int id, double &vmax, int &imax) {   // arg-max over the CTA (first index on ties)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, id, o);
+            if (ov > v || (ov == v && oi < id)) { v = ov; id = oi; }
+        }
+        __syncthreads();
+        if (lane == 0) { red[warp] = v; redi[warp] = id; }
+        __syncthreads();
+        if (warp == 0) {
+            v = lane < nwarp ? red[lane] : -1e300;
+            id = lane < nwarp ? redi[lane] : 0x7fffffff;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, id, o);
+                if (ov > v || (ov == v && oi < id)) { v = ov; id = oi; }
+            }
+            if (lane == 0) { sval[0] = v; sidx = id; }
+        }
+        __syncthreads();
+        vmax = sval[0];
+        imax = sidx;
+    };
+    double d = 0.0, dummy;
+    if (row) aij(i, i, d, dummy);
+    double amax;
+    int piv;
+    block_max(row ? fabs(d) : -1.0, i, amax, piv);
+    double *Lw = L + (size_t)w * n * ncp * E;
+    if (!(amax > 0.0)) {                                  // A == 0 (above the spectral cut-off): L = 0
+        for (int e = threadIdx.x; e < n * ncp * E; e += blockDim.x) Lw[e] = 0.0;
+        if (threadIdx.x == 0) status[w] = 0;
+        return;
+    }
+    const double tol = 1e-13 * amax;
+    bool done = !row;
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+        double dmax;
+        block_max(done ? -1e300 : d, i, dmax, piv);
+        if (!(dmax > tol)) break;
+        rank = j + 1;
+        const double inv = 1.0 / sqrt(dmax);
+        if (row) {
+            double lr = 0.0, li = 0.0;
+            if (i == piv) {
+                lr = sqrt(dmax);
+            } else if (!done) {
+                double ar, ai;
+                aij(i, piv, ar, ai);
+                for (int k = 0; k < j; ++k) {             // a_{i,piv} - sum_k L_ik conj(L_{piv,k})
+                    const double *lk = Lc + (size_t)k * n * E;
+                    if (CPLX) {
+                        const double xr = lk[2 * i], xi = lk[2 * i + 1], yr = lk[2 * piv], yi = lk[2 * piv + 1];
+                        ar -= xr * yr + xi * yi;
+                        ai -= xi * yr - xr * yi;
+                    } else {
+                        ar -= lk[i] * lk[piv];
+                    }
+                }
+                lr = ar * inv;
+                li = ai * inv;
+                d -= lr * lr + li * li;
+            }
+            double *lj = Lc + (size_t)j * n * E;
+            if (CPLX) { lj[2 * i] = lr; lj[2 * i + 1] = li; } else lj[i] = lr;
+            if (i == piv) { done = true; d = 0.0; }
+        }
+        __syncthreads();
+    }
+    // not PSD?  (1) a clearly negative remaining diagonal
+    double dmin;
+    block_max(done ? -1e300 : -d, i, dmin, piv);
+    int bad = (-dmin < -1e-11 * amax) ? 1 : 0;            // dmin = max(-d_i)  ->  min d_i = -dmin
+    // (2) residual of the factorisation on a pseudo-random +-1 vector: y = L^H v, r = A v - L y
+    auto sgn = [&](int k) { return ((unsigned)(k * 2654435761u + (unsigned)w * 40503u) >> 15) & 1u ? 1.0 : -1.0; };
+    // y lives in the first unused column of Lc (columns >= rank are free); with full rank, in the output buffer before it is written
+    double *ybuf = rank < n ? Lc + (size_t)rank * n * E : Lw;
+    __syncthreads();
+    if (row && i < rank) {                                 // thread k = i: y_k = sum_r conj(L_rk) v_r
+        const double *lk = Lc + (size_t)i * n * E;
+        double yr = 0.0, yi = 0.0;
+        for (int r = 0; r < n; ++r) {
+            const double v = sgn(r);
+            if (CPLX) { yr += lk[2 * r] * v; yi -= lk[2 * r + 1] * v; } else yr += lk[r] * v;
+        }
+        if (CPLX) { ybuf[2 * i] = yr; ybuf[2 * i + 1] = yi; } else ybuf[i] = yr;
+    }
+    __syncthreads();
+    double r2 = 0.0;
+    if (row) {
+        double rr = 0.0, ri = 0.0;
+        for (int c = 0; c < n; ++c) {
+            double ar, ai;
+            aij(i, c, ar, ai);
+            const double v = sgn(c);
+            rr += ar * v;
+            ri += ai * v;
+        }
+        for (int k = 0; k < rank; ++k) {
+            const double *lk = Lc + (size_t)k * n * E;
+            if (CPLX) {
+                const double xr = lk[2 * i], xi = lk[2 * i + 1], yr = ybuf[2 * k], yi = ybuf[2 * k + 1];
+                rr -= xr * yr - xi * yi;
+                ri -= xr * yi + xi * yr;
+            } else {
+                rr -= lk[i] * ybuf[k];
+            }
+        }
+        r2 = rr * rr + ri * ri;
+    }
+    r2 = block_sum(r2, red);
+    if (threadIdx.x == 0) sval[1] = r2;
+    __syncthreads();
+    if (sqrt(sval[1]) > 1e-11 * amax) bad = 1;
+    if (threadIdx.x == 0) status[w] = bad;
+    if (bad) return;
+    __syncthreads();
+    for (int e = threadIdx.x; e < n * ncp; e += blockDim.x) {      // L rows [n][ncp] (+ the imaginary block), zero beyond the rank
+        const int r = e / ncp, k = e % ncp;
+        double lr = 0.0, li = 0.0;
+        if (k < rank) {
+            const double *lk = Lc + (size_t)k * n * E;
+            if (CPLX) { lr = lk[2 * r]; li = lk[2 * r + 1]; } else lr = lk[r];
+        }
+        Lw[(size_t)r * ncp + k] = lr;
+        if (CPLX) Lw[(size_t)(n + r) * ncp + k] = li;
     }
 }
 
@@ -385,24 +558,85 @@ __device__ __forceinline__ double2 load_Z(const double *__restrict__ X, int k, i
     return make_double2(ar - bi, ai + br);   // (ar + i ai) + i (br + i bi)
 }
 
-// N fits one CTA: one (trajectory, column pair) per CTA.
-__global__ void __launch_bounds__(256) k_fft_direct(const double *__restrict__ X, FftPlan pl, int ntraj_chunk, int nc, int ncp, int ncx,
-                                                     int imoff, double scale, double *__restrict__ out, size_t out_tstride,
-                                                     size_t out_nstride) {
+
+// ---- in-place transform in shared memory (decimation in time) ----
+// One buffer of N complex numbers instead of the Stockham ping-pong pair: N = 8192 (128 KB) fits one CTA.  The input is loaded in
+// digit-reversed order (a gather from global memory anyway), the passes then work in place and leave the result in natural order.
+// Pass p (radix R_p, ns = R_0 ... R_{p-1}): for every group g and k < ns the elements g ns R_p + k + m ns (m < R_p) are multiplied by
+// w^{m k}, w = exp(-2 pi i / (ns R_p)), and replaced by their R_p-point DFT.  Twiddles come from a table tw[j] = exp(-2 pi i j / N)
+// (built once per plan, L1/L2-resident): one 16-byte load and R-2 complex products per butterfly instead of sincospi calls.
+__global__ void k_twiddle(double2 *__restrict__ tw, int N) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    double sn, cs;
+    sincospi(-2.0 * (double)j / (double)N, &sn, &cs);
+    tw[j] = make_double2(cs, sn);
+}
+__device__ __forceinline__ int digit_reverse(int pos, const FftPlan &pl) {     // source index of position `pos`
+    int n = 0;
+    for (int q = 0; q < pl.npass; ++q) {      // digit q of pos (radix R_q, least significant first) becomes the next more significant digit of n
+        n = n * pl.radix[q] + pos % pl.radix[q];
+        pos /= pl.radix[q];
+    }
+    return n;
+}
+template <int R>
+__device__ __forceinline__ void dit_pass(double2 *__restrict__ a, int N, int ns, const double2 *__restrict__ tw) {
+    const int per = N / R, np = ns * R, tstep = N / np;
+    for (int j = threadIdx.x; j < per; j += blockDim.x) {
+        const int k = j % ns, g = j / ns;
+        double2 *base = a + (size_t)g * np + k;
+        double2 v[R];
+#pragma unroll
+        for (int m = 0; m < R; ++m) v[m] = base[(size_t)m * ns];
+        if (k > 0) {
+            const double2 w1 = __ldg(tw + (size_t)k * tstep);
+            double2 wm = w1;
+#pragma unroll
+            for (int m = 1; m < R; ++m) {
+                v[m] = cmul(v[m], wm);
+                if (m + 1 < R) wm = cmul(wm, w1);
+            }
+        }
+        dft_small<R>(v);
+#pragma unroll
+        for (int m = 0; m < R; ++m) base[(size_t)m * ns] = v[m];
+    }
+}
+__device__ void fft_inplace_smem(double2 *a, const FftPlan &pl, const double2 *__restrict__ tw) {
+    int ns = 1;
+    for (int p = 0; p < pl.npass; ++p) {
+        const int R = pl.radix[p];
+        if (R == 4) dit_pass<4>(a, pl.n, ns, tw);
+        else if (R == 2) dit_pass<2>(a, pl.n, ns, tw);
+        else if (R == 5) dit_pass<5>(a, pl.n, ns, tw);
+        else dit_pass<3>(a, pl.n, ns, tw);
+        ns *= R;
+        __syncthreads();
+    }
+}
+// one (trajectory, column pair) per CTA; CTAs of neighbouring pairs run side by side and touch the same rows of X and of the
+// output table at the same time (the 16-byte accesses of a pair combine to full sectors / DRAM pages in L2)
+__global__ void __launch_bounds__(512) k_fft_inplace(const double *__restrict__ X, FftPlan pl, const double2 *__restrict__ tw, int ntraj_chunk,
+                                                      int nc, int ncp, int ncx, int imoff, double scale, double *__restrict__ out,
+                                                      size_t out_tstride, size_t out_nstride) {
     extern __shared__ double2 fs[];
     const int N = pl.n, h = N / 2;
     const int pair = blockIdx.x, tr = blockIdx.y;
     const int c0 = 2 * pair;
     const bool has_b = c0 + 1 < nc;
-    double2 *a = fs, *b = fs + N;
     const size_t wstride = (size_t)ntraj_chunk * ncx, off = (size_t)tr * ncx + c0;
-    for (int k = threadIdx.x; k < N; k += blockDim.x) a[k] = load_Z(X, k, N, h, wstride, off, imoff, has_b);
+    for (int pos = threadIdx.x; pos < N; pos += blockDim.x) fs[pos] = load_Z(X, digit_reverse(pos, pl), N, h, wstride, off, imoff, has_b);
     __syncthreads();
-    double2 *y = fft_smem(a, b, pl, 1);
+    fft_inplace_smem(fs, pl, tw);
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
         double *o = out + (size_t)n * out_nstride + (size_t)tr * out_tstride + c0;
-        o[0] = y[n].x * scale;
-        if (has_b) o[1] = y[n].y * scale;
+        if (has_b && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+            *reinterpret_cast<double2 *>(o) = make_double2(fs[n].x * scale, fs[n].y * scale);
+        } else {
+            o[0] = fs[n].x * scale;
+            if (has_b) o[1] = fs[n].y * scale;
+        }
     }
 }
 
@@ -552,9 +786,11 @@ struct sclmd_noise_plan {
     cudaStream_t st = nullptr;
     DevBuf<double> L;      // [nw][nc*(1+cplx)][ncp]
     DevBuf<double> evals;  // [nw][nc]
+    DevBuf<double2> tw;    // twiddle table exp(-2 pi i j / nmd) of the in-place transform
+    TmaWorkspace tws;      // stream-K scratch of the batched x = L xi product
     int64_t launches = 0;
+    int nchol = 0, njacobi = 0;     // frequencies factorised by the pivoted Cholesky kernel / handed to Jacobi
     // stage timing of the last generate call (CUDA events on the generating stream): 0 draws, 1 x = L xi, 2 transform
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     double stage_ms[3] = {0, 0, 0};
     double factor_ms = 0;
 };
@@ -562,10 +798,10 @@ struct sclmd_noise_plan {
 namespace {
 
 int factor_batch(sclmd_noise_plan *pl, int nw, int nbasis, const double *basis_h, int nterm, const int *idx_h, const double *cre_h,
-                 const double *cim_h, bool cplx, double *Ldst, double *evdst) {
+                 const double *cim_h, bool cplx, double *Ldst, double *evdst, bool eigen_only) {
     const int nc = pl->nc, ncp = pl->ncp, E = cplx ? 2 : 1;
     DevBuf<double> basis, cre, cim, A, G;
-    DevBuf<int> idx;
+    DevBuf<int> idx, status, wlist_d;
     SCLMD_CUDA(basis.alloc((size_t)nbasis * nc * nc));
     SCLMD_CUDA(cre.alloc((size_t)nw * nterm));
     SCLMD_CUDA(cim.alloc((size_t)nw * nterm));
@@ -577,18 +813,48 @@ int factor_batch(sclmd_noise_plan *pl, int nw, int nbasis, const double *basis_h
     const size_t nn = (size_t)nc * nc * E;
     const size_t smem = nn * sizeof(double);
     const int use_smem = smem <= 200 * 1024;
+    std::vector<int> wlist;
+    if (eigen_only || getenv("SCLMD_NOISE_JACOBI")) {       // the single-basis shortcut needs eigenvectors; the switch is for A/B runs
+        for (int w = 0; w < nw; ++w) wlist.push_back(w);
+    } else {
+        // pivoted Cholesky for every frequency; the ones that turn out not to be positive semi-definite go to Jacobi
+        SCLMD_CUDA(status.alloc(nw));
+        auto ck = cplx ? k_chol<true> : k_chol<false>;
+        if (use_smem) SCLMD_CUDA(cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int slab = use_smem ? nw : (int)std::max<size_t>(1, std::min<size_t>(nw, ((size_t)2 << 30) / (nn * sizeof(double))));
+        DevBuf<double> Lcol;
+        if (!use_smem) SCLMD_CUDA(Lcol.alloc(nn * slab));
+        const int threads = std::max(64, round_up(nc, 32));
+        for (int w0 = 0; w0 < nw; w0 += slab) {
+            const int cnt = std::min(slab, nw - w0);
+            ck<<<cnt, threads, use_smem ? smem : 0, pl->st>>>(basis.p, nc, ncp, nterm, idx.p + (size_t)w0 * nterm, cre.p + (size_t)w0 * nterm,
+                                                           cim.p + (size_t)w0 * nterm, Lcol.p, use_smem, Ldst + (size_t)w0 * nc * E * ncp,
+                                                           status.p + w0);
+            SCLMD_CUDA(cudaGetLastError());
+            ++pl->launches;
+        }
+        std::vector<int> st_h(nw);
+        SCLMD_CUDA(cudaMemcpyAsync(st_h.data(), status.p, nw * sizeof(int), cudaMemcpyDeviceToHost, pl->st));
+        SCLMD_CUDA(cudaStreamSynchronize(pl->st));
+        for (int w = 0; w < nw; ++w)
+            if (st_h[w]) wlist.push_back(w);
+        pl->nchol += nw - (int)wlist.size();
+    }
+    pl->njacobi += (int)wlist.size();
+    if (wlist.empty()) return 0;
+    const int nj = (int)wlist.size();
+    SCLMD_CUDA(wlist_d.alloc(nj));
+    SCLMD_CUDA(cudaMemcpy(wlist_d.p, wlist.data(), nj * sizeof(int), cudaMemcpyHostToDevice));
     // frequencies are processed in slabs so the scratch (A, and G when it does not fit in smem) stays bounded
-    const int slab = (int)std::max<size_t>(1, std::min<size_t>(nw, ((size_t)2 << 30) / (nn * sizeof(double) * (use_smem ? 1 : 2))));
+    const int slab = (int)std::max<size_t>(1, std::min<size_t>(nj, ((size_t)2 << 30) / (nn * sizeof(double) * (use_smem ? 1 : 2))));
     SCLMD_CUDA(A.alloc(nn * slab));
     if (!use_smem) SCLMD_CUDA(G.alloc(nn * slab));
     auto kern = cplx ? k_factor<true> : k_factor<false>;
     if (use_smem) SCLMD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int threads = nc >= 64 ? 512 : 128;
-    for (int w0 = 0; w0 < nw; w0 += slab) {
-        const int cnt = std::min(slab, nw - w0);
-        kern<<<cnt, threads, use_smem ? smem : 0, pl->st>>>(basis.p, nc, ncp, nterm, idx.p + (size_t)w0 * nterm, cre.p + (size_t)w0 * nterm,
-                                                         cim.p + (size_t)w0 * nterm, A.p, G.p, use_smem,
-                                                         Ldst + (size_t)w0 * nc * E * ncp, evdst ? evdst + (size_t)w0 * nc : nullptr);
+    for (int w0 = 0; w0 < nj; w0 += slab) {
+        const int cnt = std::min(slab, nj - w0);
+        kern<<<cnt, threads, use_smem ? smem : 0, pl->st>>>(basis.p, nc, ncp, nterm, idx.p, cre.p, cim.p, A.p, G.p, use_smem, Ldst, evdst, wlist_d.p, w0);
         SCLMD_CUDA(cudaGetLastError());
         ++pl->launches;
     }
@@ -604,14 +870,14 @@ int generate(sclmd_noise_plan *pl, int ntraj, const double *xi_host, uint64_t se
     const int imoff = pl->cplx ? ncp : 0;
     FftPlan full, p1, p2;
     int N1 = 0, N2 = 0;
-    const size_t smem_direct = (size_t)2 * N * sizeof(double2);
-    const bool direct = make_fft_plan(N, full) && smem_direct <= 200 * 1024;
+    if (!make_fft_plan(N, full)) {
+        set_error("noise: nmd=%d is not of the form 2^a 3^b 5^c (needed by the in-house FFT)", N);
+        return SCLMD_ERR_ARG;
+    }
+    const size_t smem_inplace = (size_t)N * sizeof(double2);
+    const bool direct = smem_inplace <= 200 * 1024;          // one in-place buffer: N <= 12800 (nmd = 8192 of configs 1, 2, 5 included)
     if (!direct) {
         // balanced 5-smooth split N = N1*N2, both transforms small enough to tile several per CTA
-        if (!make_fft_plan(N, full)) {
-            set_error("noise: nmd=%d is not of the form 2^a 3^b 5^c (needed by the in-house FFT)", N);
-            return SCLMD_ERR_ARG;
-        }
         int best = 1;
         for (int d = 1; (long long)d * d <= N; ++d)
             if (N % d == 0) best = d;
@@ -620,61 +886,95 @@ int generate(sclmd_noise_plan *pl, int ntraj, const double *xi_host, uint64_t se
             set_error("noise: cannot split nmd=%d for the four-step FFT", N);
             return SCLMD_ERR_ARG;
         }
+    } else if (!pl->tw.p) {
+        SCLMD_CUDA(pl->tw.alloc(N));
+        k_twiddle<<<cdiv(N, 256), 256, 0, st>>>(pl->tw.p, N);
+        SCLMD_CUDA(cudaGetLastError());
+        ++pl->launches;
     }
     const int npair = (nc + 1) / 2;
-    // trajectory chunk bounded by ~3 GB of scratch
-    const size_t per_traj = (size_t)nw * (ncp + ncx) * sizeof(double) + (direct ? 0 : (size_t)npair * N * sizeof(double2));
-    const int chunk = (int)std::max<size_t>(1, std::min<size_t>(ntraj, ((size_t)3 << 30) / per_traj));
+    // trajectory chunk: the scratch (draws + spectrum, + the four-step intermediate) takes at most half of the free device memory,
+    // and at most 24 GB; whole 128-row tiles of the batched product when possible
+    size_t free_b = 0, total_b = 0;
+    SCLMD_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t budget = std::min<size_t>(free_b / 2, (size_t)24 << 30);
+    const size_t per_traj = (size_t)nw * (ncp + ncx) * sizeof(double) + (direct ? 0 : (size_t)npair * N * sizeof(double2)) +
+                            (xi_host ? (size_t)nw * nc * sizeof(double) : 0);
+    int chunk = (int)std::max<size_t>(1, std::min<size_t>(ntraj, budget / per_traj));
+    if (chunk >= 128 && chunk < ntraj) chunk -= chunk % 128;
     DevBuf<double> xi, X, xih;
     DevBuf<double2> scratch;
-    SCLMD_CUDA(xi.alloc((size_t)nw * chunk * ncp));
-    SCLMD_CUDA(X.alloc((size_t)nw * chunk * ncx));
-    if (!direct) SCLMD_CUDA(scratch.alloc((size_t)chunk * npair * N));
+    SCLMD_CUDA(xi.alloc_raw((size_t)nw * chunk * ncp));
+    SCLMD_CUDA(X.alloc_raw((size_t)nw * chunk * ncx));       // the pad column of an odd nc is neither written nor read
+    if (!direct) SCLMD_CUDA(scratch.alloc_raw((size_t)chunk * npair * N));
+    if (xi_host) SCLMD_CUDA(xih.alloc_raw((size_t)chunk * nw * nc));
     const double scale = 1.0 / (pl->dt * N);   // dw/2pi (functions.py:51)
-    for (int i = 0; i < 4; ++i)
-        if (!pl->ev[i]) SCLMD_CUDA(cudaEventCreate(&pl->ev[i]));
+    std::vector<cudaEvent_t> evs;
     pl->stage_ms[0] = pl->stage_ms[1] = pl->stage_ms[2] = 0.0;
-    for (int t0 = 0; t0 < ntraj; t0 += chunk) {
+    auto mark = [&]() {
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        evs.push_back(e);
+    };
+    int rc = 0;
+    for (int t0 = 0; t0 < ntraj && !rc; t0 += chunk) {
         const int cnt = std::min(chunk, ntraj - t0);
-        const size_t nel = (size_t)nw * cnt * ncp;
+        const size_t nel = (size_t)nw * cnt * (ncp / 2);
         const int blocks = (int)std::min<size_t>((nel + 255) / 256, (size_t)pl->nsm * 16);
-        SCLMD_CUDA(cudaEventRecord(pl->ev[0], st));
+        mark();
         if (xi_host) {
-            SCLMD_CUDA(xih.alloc((size_t)cnt * nw * nc));
             SCLMD_CUDA(cudaMemcpyAsync(xih.p, xi_host + (size_t)t0 * nw * nc, (size_t)cnt * nw * nc * sizeof(double), cudaMemcpyHostToDevice, st));
             k_scatter_xi<<<blocks, 256, 0, st>>>(xih.p, xi.p, nw, cnt, nc, ncp);
         } else {
             k_fill_xi<<<blocks, 256, 0, st>>>(xi.p, nw, cnt, nc, ncp, seed, traj0 + t0);
         }
         SCLMD_CUDA(cudaGetLastError());
-        SCLMD_CUDA(cudaEventRecord(pl->ev[1], st));
-        // X[w] (cnt x ncx) = xi[w] (cnt x ncp) . L[w]^T   -- batched over w through gridDim.z
-        GemmArgs g{};
-        g.M = cnt; g.N = nc * E; g.Kseg = ncp; g.nseg = nw; g.segs_per_split = 1;
-        g.A = xi.p; g.lda = ncp; g.a_seg_stride = (long long)cnt * ncp; g.a_mod = 0;
-        g.B = pl->L.p; g.ldb = ncp; g.b_seg_stride = (long long)nc * E * ncp; g.b_seg0 = 0;
-        g.C = X.p; g.ldc = ncx; g.c_split_stride = (long long)cnt * ncx; g.alpha = 1.0;
-        for (int w0 = 0; w0 < nw; w0 += 32768) {   // gridDim.z limit
-            const int wc = std::min(32768, nw - w0);
-            g.nseg = wc;
-            g.A = xi.p + (size_t)w0 * cnt * ncp;
-            g.N = nc;
-            g.B = pl->L.p + (size_t)w0 * nc * E * ncp; g.C = X.p + (size_t)w0 * cnt * ncx;
-            SCLMD_CUDA(launch_dgemm(g, wc, st));
-            ++pl->launches;
-            if (pl->cplx) {   // imaginary rows of L -> imaginary block [ncp, ncp+nc) of x
-                g.B += (size_t)nc * ncp; g.C += ncp;
-                SCLMD_CUDA(launch_dgemm(g, wc, st));
+        ++pl->launches;
+        mark();
+        // X[w] (cnt x ncx) = xi[w] (cnt x ncp) . L[w]^T   -- one product per frequency
+        if (tma_usable(cnt, nc)) {
+            // persistent TMA / stream-K kernel over the whole frequency batch (dgemm_tma.cuh): operands as rank-3 tensors [w][row][k]
+            for (int part = 0; part < E && !rc; ++part) {        // imaginary rows of L -> imaginary block [ncp, ncp+nc) of x
+                TmaGemm g{};
+                g.M = cnt; g.N = nc; g.K = ncp; g.nbatch = nw; g.nseg = 1;
+                g.A = TmaOperand{xi.p, {(unsigned long long)ncp, (unsigned long long)cnt, (unsigned long long)nw},
+                                 {(unsigned long long)ncp, (unsigned long long)cnt * ncp}, 0, 0};
+                g.B = TmaOperand{pl->L.p + (size_t)part * nc * ncp, {(unsigned long long)ncp, (unsigned long long)nc, (unsigned long long)nw},
+                                 {(unsigned long long)ncp, (unsigned long long)nc * E * ncp}, 0, 0};
+                g.C = X.p + (size_t)part * ncp; g.ldc = ncx; g.c_batch_stride = (long long)cnt * ncx; g.alpha = 1.0;
+                rc = launch_dgemm_tma(g, pl->tws, pl->nsm, st);
                 ++pl->launches;
             }
+            if (rc) break;
+        } else {
+            GemmArgs g{};
+            g.M = cnt; g.N = nc; g.Kseg = ncp; g.nseg = nw; g.segs_per_split = 1;
+            g.A = xi.p; g.lda = ncp; g.a_seg_stride = (long long)cnt * ncp; g.a_mod = 0;
+            g.B = pl->L.p; g.ldb = ncp; g.b_seg_stride = (long long)nc * E * ncp; g.b_seg0 = 0;
+            g.C = X.p; g.ldc = ncx; g.c_split_stride = (long long)cnt * ncx; g.alpha = 1.0;
+            for (int w0 = 0; w0 < nw; w0 += 32768) {   // gridDim.z limit
+                const int wc = std::min(32768, nw - w0);
+                g.nseg = wc;
+                g.A = xi.p + (size_t)w0 * cnt * ncp;
+                g.B = pl->L.p + (size_t)w0 * nc * E * ncp; g.C = X.p + (size_t)w0 * cnt * ncx;
+                SCLMD_CUDA(launch_dgemm(g, wc, st));
+                ++pl->launches;
+                if (pl->cplx) {   // imaginary rows of L -> imaginary block [ncp, ncp+nc) of x
+                    g.B += (size_t)nc * ncp; g.C += ncp;
+                    SCLMD_CUDA(launch_dgemm(g, wc, st));
+                    ++pl->launches;
+                }
+            }
         }
-        SCLMD_CUDA(cudaEventRecord(pl->ev[2], st));
+        mark();
         double *o = out + (size_t)t0 * out_tstride;
         if (direct) {
-            SCLMD_CUDA(cudaFuncSetAttribute(k_fft_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_direct));
-            k_fft_direct<<<dim3(npair, cnt), 256, smem_direct, st>>>(X.p, full, cnt, nc, ncp, ncx, imoff, scale, o, out_tstride, out_nstride);
+            SCLMD_CUDA(cudaFuncSetAttribute(k_fft_inplace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_inplace));
+            k_fft_inplace<<<dim3(npair, cnt), N >= 2048 ? 512 : 128, smem_inplace, st>>>(X.p, full, pl->tw.p, cnt, nc, ncp, ncx, imoff, scale, o, out_tstride,
+                                                                                      out_nstride);
             SCLMD_CUDA(cudaGetLastError());
-            pl->launches += 2;
+            ++pl->launches;
         } else {
             const int tile1 = std::max(1, std::min(N2, 2048 / N1)), tile2 = std::max(1, std::min(N1, 2048 / N2));
             const size_t sm1 = (size_t)2 * tile1 * N1 * sizeof(double2), sm2 = (size_t)2 * tile2 * N2 * sizeof(double2);
@@ -684,15 +984,19 @@ int generate(sclmd_noise_plan *pl, int ntraj, const double *xi_host, uint64_t se
             SCLMD_CUDA(cudaGetLastError());
             k_fft_step2<<<dim3(npair, cnt, cdiv(N1, tile2)), 256, sm2, st>>>(scratch.p, p2, N, N1, tile2, nc, scale, o, out_tstride, out_nstride);
             SCLMD_CUDA(cudaGetLastError());
-            pl->launches += 3;
+            pl->launches += 2;
         }
-        SCLMD_CUDA(cudaEventRecord(pl->ev[3], st));
-        SCLMD_CUDA(cudaStreamSynchronize(st));
-        for (int i = 0; i < 3; ++i) {
-            float ms = 0;
-            if (cudaEventElapsedTime(&ms, pl->ev[i], pl->ev[i + 1]) == cudaSuccess) pl->stage_ms[i] += ms;
-        }
+        mark();
     }
+    const cudaError_t se = cudaStreamSynchronize(st);       // the scratch buffers go out of scope below
+    for (size_t i = 0; i + 3 < evs.size(); i += 4)
+        for (int k = 0; k < 3; ++k) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, evs[i + k], evs[i + k + 1]) == cudaSuccess) pl->stage_ms[k] += ms;
+        }
+    for (cudaEvent_t e : evs) cudaEventDestroy(e);
+    if (rc) return rc;
+    SCLMD_CUDA(se);
     return 0;
 }
 
@@ -745,7 +1049,7 @@ int sclmd_noise_plan_create(int device, int nmd, double dt, int nc, int nbasis, 
         DevBuf<double> L2, ev2, V, lam, cwd;
         SCLMD_CUDA(L2.alloc((size_t)2 * nc * pl->ncp)); SCLMD_CUDA(ev2.alloc((size_t)2 * nc));
         SCLMD_CUDA(V.alloc((size_t)nc * pl->ncp)); SCLMD_CUDA(lam.alloc(nc)); SCLMD_CUDA(cwd.alloc(nw));
-        if (int e = factor_batch(pl.get(), 2, 1, basis + (size_t)b0 * nc * nc, 1, one_idx, cpos, nullptr, false, L2.p, ev2.p)) return e;
+        if (int e = factor_batch(pl.get(), 2, 1, basis + (size_t)b0 * nc * nc, 1, one_idx, cpos, nullptr, false, L2.p, ev2.p, true)) return e;
         k_unit_vectors<<<1, 256, 0, pl->st>>>(L2.p, L2.p + (size_t)nc * pl->ncp, ev2.p, ev2.p + nc, nc, pl->ncp, V.p, lam.p);
         SCLMD_CUDA(cudaGetLastError());
         SCLMD_CUDA(cudaMemcpyAsync(cwd.p, cw.data(), nw * sizeof(double), cudaMemcpyHostToDevice, pl->st));
@@ -754,7 +1058,7 @@ int sclmd_noise_plan_create(int device, int nmd, double dt, int nc, int nbasis, 
         SCLMD_CUDA(cudaStreamSynchronize(pl->st));
         pl->launches += 2;
     } else {
-        if (int e = factor_batch(pl.get(), nw, nbasis, basis, nterm, idx, cre, cim, cplx, pl->L.p, pl->evals.p)) return e;
+        if (int e = factor_batch(pl.get(), nw, nbasis, basis, nterm, idx, cre, cim, cplx, pl->L.p, pl->evals.p, false)) return e;
     }
     SCLMD_CUDA(cudaEventRecord(f1, pl->st));
     SCLMD_CUDA(cudaStreamSynchronize(pl->st));
@@ -770,8 +1074,6 @@ int sclmd_noise_plan_destroy(sclmd_noise_plan *pl) {
     if (!pl) return SCLMD_OK;
     cudaSetDevice(pl->device);
     if (pl->st) { cudaStreamSynchronize(pl->st); cudaStreamDestroy(pl->st); }
-    for (int i = 0; i < 4; ++i)
-        if (pl->ev[i]) cudaEventDestroy(pl->ev[i]);
     delete pl;
     return SCLMD_OK;
 }
@@ -832,12 +1134,14 @@ int sclmd_noise_plan_generate(sclmd_noise_plan *pl, int ntraj, const double *xi,
 
 int64_t sclmd_noise_plan_launch_count(sclmd_noise_plan *pl) { return pl ? pl->launches : -1; }
 
-// ms[4]: device milliseconds of the last generate call per stage (0 draws, 1 x = L xi, 2 transform) and of the factorisation
-// at plan creation (3)
+// ms[6]: device milliseconds of the last generate call per stage (0 draws, 1 x = L xi, 2 transform) and of the factorisation
+// at plan creation (3); number of frequencies factorised by pivoted Cholesky (4) and by Jacobi (5)
 int sclmd_noise_plan_get_profile(sclmd_noise_plan *pl, double *ms) {
     SCLMD_REQUIRE(pl && ms, "sclmd_noise_plan_get_profile: NULL argument");
     for (int i = 0; i < 3; ++i) ms[i] = pl->stage_ms[i];
     ms[3] = pl->factor_ms;
+    ms[4] = pl->nchol;
+    ms[5] = pl->njacobi;
     return SCLMD_OK;
 }
 

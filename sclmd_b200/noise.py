@@ -138,9 +138,10 @@ class NoisePlan:
 
     def profile(self):
         """device ms of the last generate call per stage, and of the factorisation at plan creation"""
-        ms = np.zeros(4)
+        ms = np.zeros(6)
         check(_lib.lib().sclmd_noise_plan_get_profile(self._h, dptr(ms)))
-        return dict(draws_ms=float(ms[0]), gemm_ms=float(ms[1]), transform_ms=float(ms[2]), factor_ms=float(ms[3]))
+        return dict(draws_ms=float(ms[0]), gemm_ms=float(ms[1]), transform_ms=float(ms[2]), factor_ms=float(ms[3]),
+                    n_cholesky=int(ms[4]), n_jacobi=int(ms[5]))
 
 
 def ph_plan(gamma, wl, T, phcut, dt, nmd, classical=False, zpmotion=True, device=0):

@@ -73,6 +73,39 @@ def test_device_factor_reproduces_clamped_covariance(nc, ngw, nmd):
     plan.close()
 
 
+def test_pivoted_cholesky_takes_semidefinite_spectra_and_jacobi_the_indefinite_ones():
+    """positive SEMI-definite covariances (full rank, rank-deficient, zero above the cut-off) are factorised by the pivoted Cholesky
+    kernel -- any L with L L^H = A gives the reference's Gaussian law (noise.py:82-84) -- and only the frequencies whose covariance
+    has a negative eigenvalue (where vargau's clamp matters, noise.py:299-303) fall back to one-sided Jacobi"""
+    from sclmd_b200 import noise as N
+    nc, nmd = 40, 32
+    nw = nmd // 2 + 1
+    rng = np.random.default_rng(17)
+    low = rng.standard_normal((nc, 5))
+    gam = np.array([0.02 * low @ low.T / 5, P.psd(nc, 3, 0.02), P.psd(nc, 4, 0.02) - 0.004 * np.eye(nc)])   # rank 5 | full rank | indefinite
+    gwl = np.array([0.0, 0.9, 1.8]) * np.pi / DT / 2
+    phcut = 0.8 * np.pi / DT
+    plan = N.ph_plan(gam, gwl, 300.0, phcut, DT, nmd)
+    prof = plan.profile()
+    assert prof["n_cholesky"] + prof["n_jacobi"] == nw and 0 < prof["n_jacobi"] < nw and prof["n_cholesky"] >= nw // 2
+    L = plan.factors()
+    for i in range(nw):
+        A = O.ph_covariance(i, gam, gwl, 300.0, phcut, DT, nmd)
+        ev, evec = np.linalg.eigh(A)
+        want = (evec * np.where(ev > 0, ev, 0.0)) @ evec.T
+        assert np.abs(L[i] @ L[i].T - want).max() / max(np.abs(A).max(), 1e-300) < 1e-11, i
+    plan.close()
+    # complex Hermitian PSD: efric dominates the bias terms
+    efric, exim, exip = P.psd(12, 1, 0.05) + 0.05 * np.eye(12), P.antisym(12, 2, 0.002), P.sym(12, 3, 0.002)
+    plan = N.e_plan(efric, exim, exip, 0.05, 300.0, 2.0, DT, nmd, False, True)
+    assert plan.is_complex and plan.profile()["n_jacobi"] == 0
+    L = plan.factors()
+    for i in range(nw):
+        A = O.e_covariance(i, efric, exim, exip, 0.05, 300.0, 2.0, DT, nmd, False, True)
+        assert np.abs(L[i] @ L[i].conj().T - A).max() / max(np.abs(A).max(), 1e-300) < 1e-12, i
+    plan.close()
+
+
 def test_complex_factor_and_single_basis_shortcut():
     from sclmd_b200 import noise as N
     nc, nmd = 12, 16
