@@ -202,8 +202,8 @@ int sclmd_noise_plan_set_factors(sclmd_noise_plan *pl, const double *L, int is_c
  * out: [ntraj][nmd][nc] */
 int sclmd_noise_plan_generate(sclmd_noise_plan *pl, int ntraj, const double *xi, uint64_t seed,
                               int64_t traj0, double *out);
-/* same, straight into a device table laid out [nmd][ntraj_total][ncp_table] (used by
- * sclmd_md_generate_noise; `table` is a DEVICE pointer) */
+/* same, straight into a trajectory-major device table [ntraj_total][nmd][ncp_table], trajectories
+ * [traj_offset, traj_offset + ntraj) (used by sclmd_md_generate_noise; `table` is a DEVICE pointer) */
 int sclmd_noise_plan_generate_into(sclmd_noise_plan *pl, int ntraj, uint64_t seed, int64_t traj0,
                                    double *table, int ntraj_total, int ncp_table, int traj_offset);
 int64_t sclmd_noise_plan_launch_count(sclmd_noise_plan *pl);

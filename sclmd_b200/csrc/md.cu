@@ -12,7 +12,8 @@
 //   K           [nph][ld]
 //   ring_b      [ntraj][ml_b][ncp_b]   slot s holds p_{t'}[cids] with t' mod ml_b == s
 //   kernel_b    diag [ml_b+1][ncp_b] (last row 0)   |   full [ml_b][nc_b][ncp_b]
-//   noise_b     [nmd][ntraj][ncp_b]    time-major: a step streams one contiguous slab
+//   noise_b     [ntraj][nmd][ncp_b]    trajectory-major: a trajectory's series is one contiguous block (the generator's transform
+//                                      writes it row by row; a time-major table would put every row on another page)
 //   cur_b,etot  [nmd][ntraj]
 //   tailp_b     [nsplit_b][ntraj][ncp_b]   partial tails, summed in fixed order by consumers
 #include <algorithm>
@@ -38,7 +39,8 @@ struct BathDev {  // POD view passed to kernels
     const int *inv;          // [nph] -> position in bath or -1
     const int *cids;         // [nc]
     const double *k0;        // diag: kernel row 0 [ncp]
-    const double *noise;     // [nmd][ntraj][ncp]
+    const double *noise;     // [ntraj][nmd][ncp]
+    int nmd;
     const double *tailp;     // [nsplit][ntraj][ncp]
     const double *lin;       // [ntraj][ncp]
     double *ring;            // [ntraj][ml][ncp]
@@ -57,7 +59,7 @@ struct Bath {
     bool has_lin = false, has_extra = false;
     double c0 = 1.0;
     DevBuf<int> cids, inv;
-    DevBuf<double> kern, W, ring, xq, lin, tailp, noise, cur, far, fa, fc, WT;
+    DevBuf<double> kern, W, ring, xq, lin, tailp, noise, cur, far, fa, fc, WT, rowstage;
     bool blocked = false;     // time-blocked tails (diagonal kernel, long memory)
     int far_nsplit = 1;
     long long far_t0 = -1;    // block start the far tails in `far` belong to
@@ -66,7 +68,7 @@ struct Bath {
 
 // ---------------------------------------------------------------- kernels
 __device__ __forceinline__ double bath_force(const BathDev &b, int traj, int ntraj, int a, int slab, double x) {
-    double fb = b.noise[((size_t)slab * ntraj + traj) * b.ncp + a];
+    double fb = b.noise[((size_t)traj * b.nmd + slab) * b.ncp + a];
     if (b.diag) fb -= b.c0 * b.k0[a] * x;
     if (b.has_lin) fb += b.lin[(size_t)traj * b.ncp + a];
     if (b.use_tail) {
@@ -321,7 +323,7 @@ __global__ void __launch_bounds__(256, 1) k_md_persist(const PersistArgs a) {
             g[k][j] = ok ? a.G[(size_t)k * ld + i] : 0.0;
 #pragma unroll
             for (int b = 0; b < NBATH; ++b)
-                nz[k][j][b] = bc[j][b] >= 0 ? a.bs.b[b].noise[((size_t)slab0 * NT + k) * a.bs.b[b].ncp + bc[j][b]] : 0.0;
+                nz[k][j][b] = bc[j][b] >= 0 ? a.bs.b[b].noise[((size_t)k * a.nmd + slab0) * a.bs.b[b].ncp + bc[j][b]] : 0.0;
         }
     }
     for (long long s = 0; s < a.nsteps; ++s) {
@@ -354,7 +356,7 @@ __global__ void __launch_bounds__(256, 1) k_md_persist(const PersistArgs a) {
                 // the noise of step t+1: in flight during the matrix-vector product and the grid barrier
 #pragma unroll
                 for (int b = 0; b < NBATH; ++b)
-                    n1[k][j][b] = bc[j][b] >= 0 ? a.bs.b[b].noise[((size_t)slab1 * NT + k) * a.bs.b[b].ncp + bc[j][b]] : 0.0;
+                    n1[k][j][b] = bc[j][b] >= 0 ? a.bs.b[b].noise[((size_t)k * a.nmd + slab1) * a.bs.b[b].ncp + bc[j][b]] : 0.0;
             }
             if (blockIdx.x == 0) {
                 ke = block_sum(ke, red);
@@ -502,7 +504,7 @@ __global__ void __launch_bounds__(EN_W * 32, 1) k_md_ens(const EnsArgs a) {
 #pragma unroll
         for (int b = 0; b < NBATH; ++b)
             if (b < a.bs.nb) {
-                const double *src = a.bs.b[b].noise + ((size_t)slab * a.ntraj + ltraj) * a.bs.b[b].ncp;
+                const double *src = a.bs.b[b].noise + ((size_t)ltraj * a.nmd + slab) * a.bs.b[b].ncp;
                 double *dst = snz + ((size_t)b * EN_T + w) * a.ncpmax;
                 for (int c = 2 * lane; c < a.bs.b[b].ncp; c += 64) cp_async16_zfill(dst + c, src + c, 16);
             }
@@ -1246,6 +1248,15 @@ __global__ void k_gather_qc(const double *__restrict__ qn, int ld, const int *__
     for (int k = threadIdx.x; k < ncons; k += blockDim.x) qc[(size_t)traj * ldc + k] = qn[(size_t)traj * ld + cidx[k]];
 }
 
+// streamed noise rows: stage[i][traj][nc] (time slab slab0 + i, mod nmd) -> table[traj][nmd][ncp]
+__global__ void k_scatter_rows(const double *__restrict__ stage, double *__restrict__ table, int slab0, int ntraj, int nc, int ncp, int nmd) {
+    const int traj = blockIdx.x, i = blockIdx.y;
+    const int slab = (slab0 + i) % nmd;
+    const double *src = stage + ((size_t)i * ntraj + traj) * nc;
+    double *dst = table + ((size_t)traj * nmd + slab) * ncp;
+    for (int c = threadIdx.x; c < nc; c += blockDim.x) dst[c] = src[c];
+}
+
 __global__ void k_negate(double *__restrict__ x, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) x[i] = -x[i];
@@ -1532,7 +1543,7 @@ struct sclmd_md {
             d.nc = b.nc; d.ncp = b.ncp; d.ml = b.ml; d.nsplit = (b.blocked && tail_block) ? 1 : b.nsplit;
             d.diag = b.kind == SCLMD_KERNEL_DIAG;
             d.has_lin = b.has_lin; d.use_tail = b.ml > 1; d.c0 = b.c0;
-            d.inv = b.inv.p; d.cids = b.cids.p; d.k0 = b.kern.p; d.noise = b.noise.p;
+            d.inv = b.inv.p; d.cids = b.cids.p; d.k0 = b.kern.p; d.noise = b.noise.p; d.nmd = nmd;
             d.tailp = b.tailp.p; d.lin = b.lin.p; d.ring = b.ring.p; d.cur = b.cur.p;
             d.wt = b.WT.p; d.Kw = b.Kw;
             d.fa = want_f ? b.fa.p : nullptr;
@@ -2410,11 +2421,9 @@ int sclmd_md_set_noise(sclmd_md *h, int bath, int traj0, int nsel, const double 
     SCLMD_CUDA(cudaSetDevice(h->device));
     if (int e = h->flush()) return e;
     Bath &b = *h->baths[bath];
-    // host [traj][nmd][nc] -> device [nmd][ntraj][ncp]: one strided copy per trajectory
-    for (int k = 0; k < nsel; ++k)
-        SCLMD_CUDA(cudaMemcpy2DAsync(b.noise.p + (size_t)(traj0 + k) * b.ncp, (size_t)h->ntraj * b.ncp * sizeof(double),
-                                     noise + (size_t)k * h->nmd * b.nc, b.nc * sizeof(double), b.nc * sizeof(double), h->nmd,
-                                     cudaMemcpyHostToDevice, h->st));
+    // host [traj][nmd][nc] -> device [traj][nmd][ncp]: one pitched copy
+    SCLMD_CUDA(cudaMemcpy2DAsync(b.noise.p + (size_t)traj0 * h->nmd * b.ncp, b.ncp * sizeof(double), noise, b.nc * sizeof(double),
+                                 b.nc * sizeof(double), (size_t)nsel * h->nmd, cudaMemcpyHostToDevice, h->st));
     SCLMD_CUDA(cudaStreamSynchronize(h->st));
     return SCLMD_OK;
 }
@@ -2424,10 +2433,8 @@ int sclmd_md_get_noise(sclmd_md *h, int bath, int traj0, int nsel, double *noise
     SCLMD_REQUIRE(noise && traj0 >= 0 && nsel > 0 && traj0 + nsel <= h->ntraj, "sclmd_md_get_noise: bad trajectory range");
     SCLMD_CUDA(cudaSetDevice(h->device));
     Bath &b = *h->baths[bath];
-    for (int k = 0; k < nsel; ++k)
-        SCLMD_CUDA(cudaMemcpy2DAsync(noise + (size_t)k * h->nmd * b.nc, b.nc * sizeof(double),
-                                     b.noise.p + (size_t)(traj0 + k) * b.ncp, (size_t)h->ntraj * b.ncp * sizeof(double),
-                                     b.nc * sizeof(double), h->nmd, cudaMemcpyDeviceToHost, h->st));
+    SCLMD_CUDA(cudaMemcpy2DAsync(noise, b.nc * sizeof(double), b.noise.p + (size_t)traj0 * h->nmd * b.ncp, b.ncp * sizeof(double),
+                                 b.nc * sizeof(double), (size_t)nsel * h->nmd, cudaMemcpyDeviceToHost, h->st));
     SCLMD_CUDA(cudaStreamSynchronize(h->st));
     return SCLMD_OK;
 }
@@ -2796,17 +2803,17 @@ int sclmd_md_set_noise_rows(sclmd_md *h, int bath, int slab0, int nslab, const d
     // ASYNCHRONOUS on the handle's copy stream: the upload overlaps the step that is running; the next
     // sclmd_md_run orders itself after it.  `rows` must stay valid until the next synchronising call
     // (sclmd_md_run with elapsed_ms != NULL, any sclmd_md_get_*).  Pinned host memory makes it a true DMA.
+    // one linear DMA into a staging buffer, then a small kernel on the copy stream scatters the rows into the trajectory-major table
+    const size_t cap_slabs = std::max<size_t>(1, ((size_t)64 << 20) / (rowsz * b.nc * sizeof(double)));
     int done = 0;
-    while (done < nslab) {  // at most two pieces (wrap at nmd)
-        const int s = (slab0 + done) % h->nmd;
-        const int n = std::min(nslab - done, h->nmd - s);
-        if (b.nc == b.ncp)       // rows are contiguous on both sides: one linear DMA instead of a row-by-row 2-D copy
-            SCLMD_CUDA(cudaMemcpyAsync(b.noise.p + (size_t)s * rowsz * b.ncp, rows + (size_t)done * rowsz * b.nc,
-                                       (size_t)n * rowsz * b.nc * sizeof(double), cudaMemcpyHostToDevice, h->stc));
-        else
-            SCLMD_CUDA(cudaMemcpy2DAsync(b.noise.p + (size_t)s * rowsz * b.ncp, b.ncp * sizeof(double),
-                                         rows + (size_t)done * rowsz * b.nc, b.nc * sizeof(double), b.nc * sizeof(double),
-                                         (size_t)n * rowsz, cudaMemcpyHostToDevice, h->stc));
+    while (done < nslab) {
+        const int n = (int)std::min<size_t>(nslab - done, cap_slabs);
+        const size_t cnt = (size_t)n * rowsz * b.nc;
+        if (b.rowstage.n < cnt) SCLMD_CUDA(b.rowstage.alloc_raw(cnt));
+        SCLMD_CUDA(cudaMemcpyAsync(b.rowstage.p, rows + (size_t)done * rowsz * b.nc, cnt * sizeof(double), cudaMemcpyHostToDevice, h->stc));
+        k_scatter_rows<<<dim3(h->ntraj, n), 128, 0, h->stc>>>(b.rowstage.p, b.noise.p, (slab0 + done) % h->nmd, h->ntraj, b.nc, b.ncp, h->nmd);
+        SCLMD_CUDA(cudaGetLastError());
+        ++h->launches;
         done += n;
     }
     SCLMD_CUDA(cudaEventRecord(h->evN, h->stc));
@@ -2883,7 +2890,7 @@ int sclmd_md_generate_noise(sclmd_md *h, int bath, sclmd_noise_plan *plan, uint6
     SCLMD_CUDA(cudaSetDevice(h->device));
     if (int e = h->flush()) return e;
     SCLMD_CUDA(cudaStreamSynchronize(h->st));
-    return sclmd_noise_plan_generate_into(plan, h->ntraj, seed, traj0, b.noise.p, h->ntraj, b.ncp, 0);
+    return sclmd_noise_plan_generate_into(plan, h->ntraj, seed, traj0, b.noise.p, h->ntraj, b.ncp, 0);      // table [ntraj][nmd][ncp]
 }
 
 // C[M x N] = alpha * A[M x K] . B[N x K]^T on the device with host buffers (the DMMA GEMM of dgemm.cuh).  The stand-alone force

@@ -540,7 +540,7 @@ __device__ double2 *fft_smem(double2 *a, double2 *b, const FftPlan &pl, int batc
 }
 
 // value of the mirrored, column-packed spectrum Z[k] = Xa[k] + i Xb[k] (noise.py:87-94):
-//   X[k] = x_k (k < h),  conj(x_{N-k}) (k >= h)     with x stored as [w][traj][ncx] (re block, then im block)
+//   X[k] = x_k (k < h),  conj(x_{N-k}) (k >= h)     with x stored as [traj][w][ncx] (re block, then im block)
 __device__ __forceinline__ double2 load_Z(const double *__restrict__ X, int k, int N, int h, size_t wstride, size_t off, int imoff,
                                           bool has_b) {
     const bool mir = k >= h;
@@ -580,17 +580,22 @@ __device__ __forceinline__ int digit_reverse(int pos, const FftPlan &pl) {     /
     }
     return n;
 }
+__global__ void k_digit_reverse(int *__restrict__ perm, FftPlan pl) {           // once per plan: the load order of the in-place transform
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos < pl.n) perm[pos] = digit_reverse(pos, pl);
+}
+// lg >= 0: ns = 2^lg (shifts instead of integer divisions; every pass of a power-of-two length)
 template <int R>
-__device__ __forceinline__ void dit_pass(double2 *__restrict__ a, int N, int ns, const double2 *__restrict__ tw) {
+__device__ __forceinline__ void dit_pass(double2 *__restrict__ a, int N, int ns, int lg, const double2 *__restrict__ tw) {
     const int per = N / R, np = ns * R, tstep = N / np;
     for (int j = threadIdx.x; j < per; j += blockDim.x) {
-        const int k = j % ns, g = j / ns;
-        double2 *base = a + (size_t)g * np + k;
+        const int k = lg >= 0 ? (j & (ns - 1)) : j % ns, g = lg >= 0 ? (j >> lg) : j / ns;
+        double2 *base = a + g * np + k;
         double2 v[R];
 #pragma unroll
-        for (int m = 0; m < R; ++m) v[m] = base[(size_t)m * ns];
+        for (int m = 0; m < R; ++m) v[m] = base[m * ns];
         if (k > 0) {
-            const double2 w1 = __ldg(tw + (size_t)k * tstep);
+            const double2 w1 = __ldg(tw + k * tstep);
             double2 wm = w1;
 #pragma unroll
             for (int m = 1; m < R; ++m) {
@@ -600,24 +605,26 @@ __device__ __forceinline__ void dit_pass(double2 *__restrict__ a, int N, int ns,
         }
         dft_small<R>(v);
 #pragma unroll
-        for (int m = 0; m < R; ++m) base[(size_t)m * ns] = v[m];
+        for (int m = 0; m < R; ++m) base[m * ns] = v[m];
     }
 }
 __device__ void fft_inplace_smem(double2 *a, const FftPlan &pl, const double2 *__restrict__ tw) {
     int ns = 1;
     for (int p = 0; p < pl.npass; ++p) {
         const int R = pl.radix[p];
-        if (R == 4) dit_pass<4>(a, pl.n, ns, tw);
-        else if (R == 2) dit_pass<2>(a, pl.n, ns, tw);
-        else if (R == 5) dit_pass<5>(a, pl.n, ns, tw);
-        else dit_pass<3>(a, pl.n, ns, tw);
+        const int lg = (ns & (ns - 1)) == 0 ? 31 - __clz(ns) : -1;
+        if (R == 4) dit_pass<4>(a, pl.n, ns, lg, tw);
+        else if (R == 2) dit_pass<2>(a, pl.n, ns, lg, tw);
+        else if (R == 5) dit_pass<5>(a, pl.n, ns, lg, tw);
+        else dit_pass<3>(a, pl.n, ns, lg, tw);
         ns *= R;
         __syncthreads();
     }
 }
 // one (trajectory, column pair) per CTA; CTAs of neighbouring pairs run side by side and touch the same rows of X and of the
 // output table at the same time (the 16-byte accesses of a pair combine to full sectors / DRAM pages in L2)
-__global__ void __launch_bounds__(512) k_fft_inplace(const double *__restrict__ X, FftPlan pl, const double2 *__restrict__ tw, int ntraj_chunk,
+__global__ void __launch_bounds__(512) k_fft_inplace(const double *__restrict__ X, FftPlan pl, const double2 *__restrict__ tw,
+                                                      const int *__restrict__ perm, int ntraj_chunk,
                                                       int nc, int ncp, int ncx, int imoff, double scale, double *__restrict__ out,
                                                       size_t out_tstride, size_t out_nstride) {
     extern __shared__ double2 fs[];
@@ -625,8 +632,8 @@ __global__ void __launch_bounds__(512) k_fft_inplace(const double *__restrict__ 
     const int pair = blockIdx.x, tr = blockIdx.y;
     const int c0 = 2 * pair;
     const bool has_b = c0 + 1 < nc;
-    const size_t wstride = (size_t)ntraj_chunk * ncx, off = (size_t)tr * ncx + c0;
-    for (int pos = threadIdx.x; pos < N; pos += blockDim.x) fs[pos] = load_Z(X, digit_reverse(pos, pl), N, h, wstride, off, imoff, has_b);
+    const size_t wstride = (size_t)ncx, off = (size_t)tr * (h + 1) * ncx + c0;       // X is [traj][w][ncx]
+    for (int pos = threadIdx.x; pos < N; pos += blockDim.x) fs[pos] = load_Z(X, __ldg(perm + pos), N, h, wstride, off, imoff, has_b);
     __syncthreads();
     fft_inplace_smem(fs, pl, tw);
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
@@ -650,7 +657,7 @@ __global__ void __launch_bounds__(256) k_fft_step1(const double *__restrict__ X,
     const int c0 = 2 * pair;
     const bool has_b = c0 + 1 < nc;
     double2 *a = fs, *b = fs + (size_t)tile * N1;
-    const size_t wstride = (size_t)ntraj_chunk * ncx, off = (size_t)tr * ncx + c0;
+    const size_t wstride = (size_t)ncx, off = (size_t)tr * (h + 1) * ncx + c0;       // X is [traj][w][ncx]
     for (int e = threadIdx.x; e < nt * N1; e += blockDim.x) {
         const int f = e % nt, k1 = e / nt;     // consecutive threads -> consecutive k2 (adjacent frequencies)
         a[(size_t)f * N1 + k1] = load_Z(X, k1 * N2 + k20 + f, N, h, wstride, off, imoff, has_b);
@@ -787,6 +794,7 @@ struct sclmd_noise_plan {
     DevBuf<double> L;      // [nw][nc*(1+cplx)][ncp]
     DevBuf<double> evals;  // [nw][nc]
     DevBuf<double2> tw;    // twiddle table exp(-2 pi i j / nmd) of the in-place transform
+    DevBuf<int> perm;      // its digit-reversed load order
     TmaWorkspace tws;      // stream-K scratch of the batched x = L xi product
     int64_t launches = 0;
     int nchol = 0, njacobi = 0;     // frequencies factorised by the pivoted Cholesky kernel / handed to Jacobi
@@ -888,9 +896,11 @@ int generate(sclmd_noise_plan *pl, int ntraj, const double *xi_host, uint64_t se
         }
     } else if (!pl->tw.p) {
         SCLMD_CUDA(pl->tw.alloc(N));
+        SCLMD_CUDA(pl->perm.alloc(N));
         k_twiddle<<<cdiv(N, 256), 256, 0, st>>>(pl->tw.p, N);
+        k_digit_reverse<<<cdiv(N, 256), 256, 0, st>>>(pl->perm.p, full);
         SCLMD_CUDA(cudaGetLastError());
-        ++pl->launches;
+        pl->launches += 2;
     }
     const int npair = (nc + 1) / 2;
     // trajectory chunk: the scratch (draws + spectrum, + the four-step intermediate) takes at most half of the free device memory,
@@ -942,7 +952,7 @@ int generate(sclmd_noise_plan *pl, int ntraj, const double *xi_host, uint64_t se
                                  {(unsigned long long)ncp, (unsigned long long)cnt * ncp}, 0, 0};
                 g.B = TmaOperand{pl->L.p + (size_t)part * nc * ncp, {(unsigned long long)ncp, (unsigned long long)nc, (unsigned long long)nw},
                                  {(unsigned long long)ncp, (unsigned long long)nc * E * ncp}, 0, 0};
-                g.C = X.p + (size_t)part * ncp; g.ldc = ncx; g.c_batch_stride = (long long)cnt * ncx; g.alpha = 1.0;
+                g.C = X.p + (size_t)part * ncp; g.ldc = (long long)nw * ncx; g.c_batch_stride = ncx; g.alpha = 1.0;      // X[traj][w][ncx]
                 rc = launch_dgemm_tma(g, pl->tws, pl->nsm, st);
                 ++pl->launches;
             }
@@ -952,12 +962,12 @@ int generate(sclmd_noise_plan *pl, int ntraj, const double *xi_host, uint64_t se
             g.M = cnt; g.N = nc; g.Kseg = ncp; g.nseg = nw; g.segs_per_split = 1;
             g.A = xi.p; g.lda = ncp; g.a_seg_stride = (long long)cnt * ncp; g.a_mod = 0;
             g.B = pl->L.p; g.ldb = ncp; g.b_seg_stride = (long long)nc * E * ncp; g.b_seg0 = 0;
-            g.C = X.p; g.ldc = ncx; g.c_split_stride = (long long)cnt * ncx; g.alpha = 1.0;
+            g.C = X.p; g.ldc = (long long)nw * ncx; g.c_split_stride = ncx; g.alpha = 1.0;                               // X[traj][w][ncx]
             for (int w0 = 0; w0 < nw; w0 += 32768) {   // gridDim.z limit
                 const int wc = std::min(32768, nw - w0);
                 g.nseg = wc;
                 g.A = xi.p + (size_t)w0 * cnt * ncp;
-                g.B = pl->L.p + (size_t)w0 * nc * E * ncp; g.C = X.p + (size_t)w0 * cnt * ncx;
+                g.B = pl->L.p + (size_t)w0 * nc * E * ncp; g.C = X.p + (size_t)w0 * ncx;
                 SCLMD_CUDA(launch_dgemm(g, wc, st));
                 ++pl->launches;
                 if (pl->cplx) {   // imaginary rows of L -> imaginary block [ncp, ncp+nc) of x
@@ -971,7 +981,7 @@ int generate(sclmd_noise_plan *pl, int ntraj, const double *xi_host, uint64_t se
         double *o = out + (size_t)t0 * out_tstride;
         if (direct) {
             SCLMD_CUDA(cudaFuncSetAttribute(k_fft_inplace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_inplace));
-            k_fft_inplace<<<dim3(npair, cnt), N >= 2048 ? 512 : 128, smem_inplace, st>>>(X.p, full, pl->tw.p, cnt, nc, ncp, ncx, imoff, scale, o, out_tstride,
+            k_fft_inplace<<<dim3(npair, cnt), N >= 2048 ? 512 : 128, smem_inplace, st>>>(X.p, full, pl->tw.p, pl->perm.p, cnt, nc, ncp, ncx, imoff, scale, o, out_tstride,
                                                                                       out_nstride);
             SCLMD_CUDA(cudaGetLastError());
             ++pl->launches;
@@ -1145,13 +1155,13 @@ int sclmd_noise_plan_get_profile(sclmd_noise_plan *pl, double *ms) {
     return SCLMD_OK;
 }
 
-// device-to-device variant used by md.cu: writes into a [nmd][ntraj_total][ncp] table
+// device-to-device variant used by md.cu: writes into a trajectory-major table [ntraj_total][nmd][ncp_table]
 int sclmd_noise_plan_generate_into(sclmd_noise_plan *pl, int ntraj, uint64_t seed, int64_t traj0, double *table, int ntraj_total,
                                    int ncp_table, int traj_offset) {
-    SCLMD_REQUIRE(pl && table, "sclmd_noise_plan_generate_into: bad arguments");
+    SCLMD_REQUIRE(pl && table && traj_offset >= 0 && traj_offset + ntraj <= ntraj_total, "sclmd_noise_plan_generate_into: bad arguments");
     SCLMD_CUDA(cudaSetDevice(pl->device));
-    return generate(pl, ntraj, nullptr, seed, traj0, table + (size_t)traj_offset * ncp_table, (size_t)ncp_table,
-                    (size_t)ntraj_total * ncp_table, pl->st);
+    return generate(pl, ntraj, nullptr, seed, traj0, table + (size_t)traj_offset * pl->nmd * ncp_table, (size_t)pl->nmd * ncp_table,
+                    (size_t)ncp_table, pl->st);
 }
 
 int sclmd_noise_plan_dims(sclmd_noise_plan *pl, int *nmd, int *nc) {
