@@ -22,11 +22,10 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for _p in (ROOT, os.path.join(ROOT, "tests")):
-    if _p not in sys.path:
-        sys.path.insert(0, _p)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
-import problems as P  # noqa: E402
+from sclmd_b200 import synthetic as P  # noqa: E402
 
 
 def parse():
@@ -224,12 +223,25 @@ def fill_noise(eng, w, ntraj, seed, traj0):
     from sclmd_b200 import _lib, noise as N
     rng = np.random.default_rng(seed)
     t0 = time.perf_counter()
+    stages = {"draws_ms": 0.0, "gemm_ms": 0.0, "transform_ms": 0.0, "factor_ms": 0.0}
     for b in range(2):
         gam = np.array([np.eye(w["nc"]) * 0.05 * np.pi / 6.0])
         plan = N.ph_plan(gam, np.array([0.0]), 300.0 * (1.05 if b == 0 else 0.95), 0.5, w["dt"], w["nmd"], device=eng.device)
         _lib.check(_lib.lib().sclmd_md_generate_noise(eng._h, b, plan._h, C.c_uint64(seed), int(traj0)))
+        pr = plan.profile()
+        for k in stages:
+            stages[k] += pr[k]
         plan.close()
     gen_s = time.perf_counter() - t0
+    dev_s = (stages["draws_ms"] + stages["gemm_ms"] + stages["transform_ms"]) * 1e-3
+    nsamp = 2.0 * ntraj * w["nmd"] * w["nc"]
+    fill_noise.report = {
+        "what": "device noise generator, both baths: Philox draws -> x = L xi (batched TMA/stream-K DMMA product) -> mirrored transform "
+                "(big-radix in-place FFT in shared memory) straight into the trajectory-major noise tables",
+        "samples": nsamp, "device_s": dev_s, "samples_per_s_device": nsamp / dev_s if dev_s > 0 else None,
+        "frac_of_hbm_roofline_16B_per_sample": (nsamp * 16 / dev_s) / (peaks()[0] * 1e9) if dev_s > 0 else None,
+        "stage_ms": stages, "wall_s_incl_plan_setup_on_the_host": gen_s,
+        "gemm_tflops": 2.0 * w["nc"] ** 2 * (w["nmd"] // 2 + 1) * ntraj * 2 / (stages["gemm_ms"] * 1e-3) / 1e12 if stages["gemm_ms"] > 0 else None}
     nblk = min(32, w["nmd"])
     blocks = []
     for b in range(2):
@@ -463,7 +475,7 @@ def main():
         gbs = 8.0 * w["nc"] * (w["ml"] - 1) * ntraj / (tms * 1e-3) / 1e9
         direct_tail = {"kernel": "k_tail_diag<4>", "avg_launch_ms": tms, "achieved_GBs": gbs, "frac_of_hbm_peak": gbs / hp}
     pf_ms = eng.time_potforce(5)
-    kq_alone = {"kernel": "dgemm_nt_seg_kernel (K.q) timed alone", "avg_launch_ms": pf_ms,
+    kq_alone = {"kernel": "dgemm_tma_kernel (K.q) timed alone", "avg_launch_ms": pf_ms,
                 "tflops": 2.0 * (3 * w["natoms"]) ** 2 * ntraj / (pf_ms * 1e-3) / 1e12}
     import ctypes as _C
     from sclmd_b200 import _lib as _L
@@ -495,7 +507,7 @@ def main():
     if pa["potforce"]["launches"]:
         per = pa["potforce"]["ms"] / pa["potforce"]["launches"]
         fl = 2.0 * nph_ * nph_ * ntraj
-        cands.append({"kernel": "dgemm_nt_seg_kernel (K.q, DMMA.8x8x4)", "bound": "tensor", "achieved": fl / (per * 1e-3) / 1e12,
+        cands.append({"kernel": "dgemm_tma_kernel (K.q: TMA-fed persistent stream-K, DMMA.8x8x4)", "bound": "tensor", "achieved": fl / (per * 1e-3) / 1e12,
                       "peak": fp64_peak, "unit": "TFLOP/s", "frac": fl / (per * 1e-3) / 1e12 / fp64_peak,
                       "traffic": (traffic or {}).get("dgemm_dram_bytes_per_launch"),
                       "peak_source": "measured live: FP64 DMMA.8x8x4 chain probe (sclmd_probe_fp64); DFMA chain %.1f" % probe["dfma_tflops"],
@@ -507,7 +519,7 @@ def main():
         if pa[key]["launches"]:
             per = pa[key]["ms"] / pa[key]["launches"]
             fl = 2.0 * nph_ * ncs * ntraj
-            cands.append({"kernel": "dgemm_nt_seg_kernel (eigenbasis mode, %s; DMMA.8x8x4)" % name, "bound": "tensor",
+            cands.append({"kernel": "dgemm_tma_kernel (eigenbasis mode, %s; TMA-fed persistent stream-K, DMMA.8x8x4)" % name, "bound": "tensor",
                           "achieved": fl / (per * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fl / (per * 1e-3) / 1e12 / fp64_peak,
                           "traffic": None, "peak_source": "measured live: FP64 DMMA.8x8x4 chain probe (sclmd_probe_fp64)",
                           "algorithmic_flops_per_launch": fl, "avg_launch_ms": per, "launches_timed": pa[key]["launches"],
@@ -525,7 +537,7 @@ def main():
     if pa["tail_direct"]["launches"] and w["kind"] == "full":
         per = pa["tail_direct"]["ms"] / pa["tail_direct"]["launches"]
         fl = 2.0 * (w["ml"] - 1) * w["nc"] * w["nc"] * ntraj
-        cands.append({"kernel": "dgemm_nt_seg_kernel (full memory-kernel tail over the history ring, DMMA.8x8x4, split-K)", "bound": "tensor",
+        cands.append({"kernel": "dgemm_tma_kernel (full memory-kernel tail: TMA-fed stream-K DMMA contraction over the rotating history ring)", "bound": "tensor",
                       "achieved": fl / (per * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fl / (per * 1e-3) / 1e12 / fp64_peak,
                       "traffic": None, "peak_source": "measured live: FP64 DMMA.8x8x4 chain probe (sclmd_probe_fp64)",
                       "algorithmic_flops_per_launch": fl, "avg_launch_ms": per, "launches_timed": pa["tail_direct"]["launches"],
@@ -571,10 +583,38 @@ def main():
                                       "sclmd_md_get_step_observables (D2H, synchronises) every step"},
             "gpu_launches": launches_total, "roofline": roof, "wall_ms_timed_region": wall_ms, "allreduce_ms": ar_ms,
             "heat_current_mean": [float(sums[b] / sums[2] / w["nmd"]) for b in range(2)],
-            "noise_generation_s": noise_gen_s, "fp64_probe_tflops": probe, "also": also,
+            "noise_generation_s": noise_gen_s, "noise": getattr(fill_noise, "report", None), "fp64_probe_tflops": probe, "also": also,
             "tail_mode": "time-blocked (ring streamed once per 16 steps)" if args.tail_block == 1 else ("time-blocked, other kernel (--tail-block %d)" % args.tail_block if args.tail_block else "direct (ring streamed every step)"),
             "propagation": ("eigenbasis of md.setDyn (sclmd_md_set_modes): diagonal harmonic force, gather + scatter products over the bath dofs"
                             if modal else "real space: K.q GEMM every step")}
+
+    # ---------------- BASELINE configs[4], full-kernel variant (the FP64-bound one): 256 trajectories, ring-segment GEMM tails
+    if world == 1 and not args.no_also and args.workload == "c5_diag":
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", "c5_full", "--steps", "8", "--warmup", "3",
+                                "--no-also", "--no-cpu-baseline"], capture_output=True, text=True, timeout=900)
+            cf = json.loads(r.stdout.strip().splitlines()[-1])
+            line["also_md_c5_full"] = {k: cf[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "gpu_launches", "config")}
+            rf = cf.get("roofline") or {}
+            line["also_md_c5_full"]["roofline"] = {k: rf.get(k) for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "avg_launch_ms", "share_of_step")}
+        except Exception as exc:
+            line["also_md_c5_full"] = {"error": str(exc)[:200]}
+
+    # flat copies of the secondary headline numbers inside `roofline` (the driver keeps the scalar keys of that object)
+    if roof is not None:
+        if also:
+            roof["negf_omega_points_per_s"] = also.get("value")
+            roof["negf_whole_sweep_frac_of_fp64_peak"] = (also.get("roofline") or {}).get("whole_sweep_algorithmic_frac_of_peak")
+            roof["negf_rank64_update_frac_of_fp64_peak"] = (also.get("roofline") or {}).get("frac")
+        cfull = line.get("also_md_c5_full") or {}
+        if "value" in cfull:
+            roof["c5_full_trajectory_steps_per_s"] = cfull["value"]
+            roof["c5_full_ring_gemm_frac_of_fp64_peak"] = (cfull.get("roofline") or {}).get("frac")
+        nz = line.get("noise") or {}
+        roof["noise_samples_per_s"] = nz.get("samples_per_s_device")
+        roof["noise_frac_of_hbm_roofline"] = nz.get("frac_of_hbm_roofline_16B_per_sample")
+        roof["whole_step_frac_of_fp64_peak"] = (roof.get("whole_step") or {}).get("frac_of_fp64_peak")
+        roof["traffic_source"] = "stored ncu --set full capture (profiles/r01_tail_traffic.json), not measured in this run"
 
     # ---------------- BASELINE configs[1] shape (603-dof junction of the example, ml = 1 baths, fixed ends, 1024 trajectories)
     if world == 1 and not args.no_also and args.workload != "c2":

@@ -79,6 +79,7 @@ struct DevBuf {
 
 int select_device(int device);
 int sm_count(int device);
+void release_noise_scratch();      // cached device scratch of the noise generator (noise.cu); part of sclmd_release_workspace()
 
 // ------------------------------------------------------------------ device side
 #ifdef __CUDACC__

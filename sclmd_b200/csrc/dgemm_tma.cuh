@@ -276,7 +276,7 @@ struct TmaWorkspace {
     int grid = 0;
 };
 
-constexpr int TMA_BM = 128, TMA_BN = 128;
+constexpr int TMA_BM = 128, TMA_BN_MAX = 160;
 inline bool tma_disabled() {
     static const bool off = getenv("SCLMD_NO_TMA") != nullptr;
     return off;
@@ -294,28 +294,42 @@ struct TmaGemm {
     double alpha;
 };
 
-inline int launch_dgemm_tma(const TmaGemm &g, TmaWorkspace &w, int nsm, cudaStream_t st) {
-    using Cfg = TmaCfg<TMA_BM, TMA_BN, 64, 32, 6>;
-    auto kern = dgemm_tma_kernel<TMA_BM, TMA_BN, 64, 32, 6>;
+// tile width: 2 x 4 consumer warps of 64 x (BN / 4); the width that pads N least wins (ties: the wider tile, more operand reuse).
+// nc = 300 (config 5): 2 tiles of 160 (6 % padding) instead of 3 of 128 (22 %)
+inline int tma_pick_bn(int N) {
+    const int cand[4] = {160, 128, 96, 64};
+    int best = 128;
+    long long best_pad = -1;
+    for (int c : cand) {
+        const long long padded = (long long)cdiv(N, c) * c;
+        if (best_pad < 0 || padded < best_pad) { best_pad = padded; best = c; }
+    }
+    return best;
+}
+
+template <int BN, int STAGES>
+inline int launch_dgemm_tma_bn(const TmaGemm &g, TmaWorkspace &w, int nsm, cudaStream_t st) {
+    using Cfg = TmaCfg<TMA_BM, BN, 64, BN / 4, STAGES>;
+    auto kern = dgemm_tma_kernel<TMA_BM, BN, 64, BN / 4, STAGES>;
     static bool configured = false;
     if (!configured) {
         SCLMD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         configured = true;
     }
     if (w.grid != nsm) {
-        SCLMD_CUDA(w.ws.alloc((size_t)nsm * TMA_BM * TMA_BN));
+        SCLMD_CUDA(w.ws.alloc((size_t)nsm * TMA_BM * TMA_BN_MAX));
         SCLMD_CUDA(w.flags.alloc(nsm));
         w.grid = nsm;
         w.epoch = 0;
     }
     TmaOperand A = g.A, B = g.B;
     if (g.a_mode == 1) { A.box1 = 1; A.box2 = TMA_BM; } else { A.box1 = TMA_BM; A.box2 = 1; }
-    B.box1 = TMA_BN; B.box2 = 1;
+    B.box1 = BN; B.box2 = 1;
     CUtensorMap mA, mB;
     if (int e = tma_make_map(&mA, A)) return e;
     if (int e = tma_make_map(&mB, B)) return e;
     TmaGemmParams p{};
-    p.M = g.M; p.N = g.N; p.mt = cdiv(g.M, TMA_BM); p.nt = cdiv(g.N, TMA_BN); p.ntiles = g.nbatch * p.mt * p.nt;
+    p.M = g.M; p.N = g.N; p.mt = cdiv(g.M, TMA_BM); p.nt = cdiv(g.N, BN); p.ntiles = g.nbatch * p.mt * p.nt;
     p.kslabs = cdiv(g.K, Cfg::BK); p.KI = g.nseg * p.kslabs;
     p.a_mode = g.a_mode; p.a_head = g.a_head; p.a_mod = g.a_mod; p.b_mode = g.b_mode; p.b_seg0 = g.b_seg0;
     p.C = g.C; p.ldc = g.ldc; p.c_batch_stride = g.c_batch_stride; p.alpha = g.alpha;
@@ -329,6 +343,14 @@ inline int launch_dgemm_tma(const TmaGemm &g, TmaWorkspace &w, int nsm, cudaStre
         return SCLMD_ERR_CUDA;
     }
     return 0;
+}
+inline int launch_dgemm_tma(const TmaGemm &g, TmaWorkspace &w, int nsm, cudaStream_t st) {
+    switch (tma_pick_bn(g.N)) {          // stages: as many 16-double slabs of (128 + BN) rows as fit ~190 KB
+        case 160: return launch_dgemm_tma_bn<160, 5>(g, w, nsm, st);
+        case 96: return launch_dgemm_tma_bn<96, 6>(g, w, nsm, st);
+        case 64: return launch_dgemm_tma_bn<64, 8>(g, w, nsm, st);
+        default: return launch_dgemm_tma_bn<128, 6>(g, w, nsm, st);
+    }
 }
 
 // plain product C[M x N] = alpha A[M x K] . B[N x K]^T

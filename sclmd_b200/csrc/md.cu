@@ -1588,6 +1588,22 @@ struct sclmd_md {
                 k_tail_diag<1><<<grid, threads, sm, st>>>(b.ring.p, b.kern.p, b.tailp.p, ntraj, b.ml, b.ncp, head, rps, cpt, rg, dt);
             SCLMD_CUDA(cudaGetLastError());
         } else {
+            if (b.gemm_cfg == -2) {
+                // persistent TMA / stream-K kernel over the rotating ring: A = ring as a rank-3 tensor [traj][slot][ncp] (box 16 x 1 x 128),
+                // B = kernel [j][nc][ncp]; one K loop over (ml - 1) segments x ceil(ncp / 16) slabs, no K-slices of the tail in HBM
+                TmaGemm g{};
+                g.M = ntraj; g.N = b.nc; g.K = b.ncp; g.nbatch = 1; g.nseg = b.ml - 1;
+                g.A = TmaOperand{b.ring.p, {(unsigned long long)b.ncp, (unsigned long long)b.ml, (unsigned long long)ntraj},
+                                 {(unsigned long long)b.ncp, (unsigned long long)b.ml * b.ncp}, 0, 0};
+                g.B = TmaOperand{b.kern.p, {(unsigned long long)b.ncp, (unsigned long long)b.nc, (unsigned long long)b.ml},
+                                 {(unsigned long long)b.ncp, (unsigned long long)b.nc * b.ncp}, 0, 0};
+                g.a_mode = 1; g.a_head = head; g.a_mod = b.ml; g.b_mode = 1; g.b_seg0 = 1;
+                g.C = b.tailp.p; g.ldc = b.ncp; g.c_batch_stride = 0; g.alpha = dt;
+                if (int e = launch_dgemm_tma(g, tws[0], nsm, st)) return e;
+                prof_end();
+                ++launches;
+                return 0;
+            }
             GemmArgs g{};
             g.M = ntraj; g.N = b.nc; g.Kseg = b.ncp; g.nseg = b.ml - 1;
             g.segs_per_split = cdiv(g.nseg, b.nsplit);
@@ -2385,7 +2401,10 @@ int sclmd_md_add_bath(sclmd_md *h, const int32_t *cids, int nc, int ml, const do
                                                       : cdiv(ntraj, 128) * cdiv(nc, 128);
         int want = kernel_kind == SCLMD_KERNEL_DIAG ? 4 * h->nsm : 2 * h->nsm;
         b->nsplit = std::max(1, std::min({cdiv(want, tiles), 32, std::max(1, (ml - 1) / 64)}));
-        if (kernel_kind == SCLMD_KERNEL_FULL && ntraj > 64) {
+        if (kernel_kind == SCLMD_KERNEL_FULL && tma_usable(ntraj, nc)) {
+            b->gemm_cfg = -2;       // the ring-segment contraction runs on the TMA / stream-K kernel: one tail, no K-slices
+            b->nsplit = 1;
+        } else if (kernel_kind == SCLMD_KERNEL_FULL && ntraj > 64) {
             // ring-segment GEMM [ntraj x nc] with a very deep K: 64-wide tiles when 128-wide ones would be mostly padding, and a
             // split count that fills whole waves (6 tiles x 32 splits on 148 SMs ran two waves at 65 %)
             const bool narrow = round_up(nc, 128) - nc >= 64;

@@ -1127,6 +1127,7 @@ int sclmd_release_workspace(void) {
         if (cudaSetDevice(w->device) == cudaSuccess) w->release();
     }
     g_ws.clear();
+    sclmd::release_noise_scratch();
     return SCLMD_OK;
 }
 

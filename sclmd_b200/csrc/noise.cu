@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <memory>
+#include <mutex>
 
 #include "common.cuh"
 #include "dgemm.cuh"
@@ -621,6 +622,145 @@ __device__ void fft_inplace_smem(double2 *a, const FftPlan &pl, const double2 *_
         __syncthreads();
     }
 }
+// ---- power-of-two lengths: big-radix passes with the butterflies in registers ----
+// 8192 = 16 x 16 x 32: THREE passes instead of seven radix-4 ones, and the first / last of them read global memory / write the
+// noise table directly, so a series crosses shared memory twice (write, read+write, read) instead of fourteen times -- the radix-4
+// kernel above is bound by exactly that traffic.  Shared-memory index i is stored at i + (i >> 4): the stride-16 / stride-256
+// accesses of the passes then fall on distinct banks.  A radix-R butterfly (R <= 32) is an unrolled radix-2 DIT network on registers
+// with compile-time twiddles exp(-2 pi i k / 32).
+__device__ constexpr double FFT_C32[32] = {1, 0.98078528040323043, 0.92387953251128674, 0.83146961230254524, 0.70710678118654757, 0.55557023301960229, 0.38268343236508984, 0.19509032201612833, 6.123233995736766e-17, -0.19509032201612819, -0.38268343236508973, -0.55557023301960196, -0.70710678118654746, -0.83146961230254535, -0.92387953251128674, -0.98078528040323043, -1, -0.98078528040323043, -0.92387953251128685, -0.83146961230254546, -0.70710678118654768, -0.55557023301960218, -0.38268343236509034, -0.19509032201612866, -1.8369701987210297e-16, 0.1950903220161283, 0.38268343236509, 0.55557023301960184, 0.70710678118654735, 0.83146961230254524, 0.92387953251128652, 0.98078528040323032};
+__device__ constexpr double FFT_S32[32] = {-0, -0.19509032201612825, -0.38268343236508978, -0.55557023301960218, -0.70710678118654746, -0.83146961230254524, -0.92387953251128674, -0.98078528040323043, -1, -0.98078528040323043, -0.92387953251128674, -0.83146961230254546, -0.70710678118654757, -0.55557023301960218, -0.38268343236508989, -0.19509032201612861, -1.2246467991473532e-16, 0.19509032201612836, 0.38268343236508967, 0.55557023301960196, 0.70710678118654746, 0.83146961230254524, 0.92387953251128652, 0.98078528040323032, 1, 0.98078528040323043, 0.92387953251128663, 0.83146961230254546, 0.70710678118654768, 0.55557023301960218, 0.38268343236509039, 0.19509032201612872};     // -sin: forward transform
+__device__ constexpr int FFT_BR32[32] = {0, 16, 8, 24, 4, 20, 12, 28, 2, 18, 10, 26, 6, 22, 14, 30, 1, 17, 9, 25, 5, 21, 13, 29, 3, 19, 11, 27, 7, 23, 15, 31};
+__host__ __device__ constexpr int fft_log2(int r) { return r <= 1 ? 0 : 1 + fft_log2(r >> 1); }
+template <int R, int LEN>
+struct FftStage {       // one radix-2 stage (butterflies of span LEN) of the register network, then the next one
+    static __device__ __forceinline__ void run(double2 (&t)[R]) {
+#pragma unroll
+        for (int i = 0; i < R; i += LEN) {
+#pragma unroll
+            for (int k = 0; k < LEN / 2; ++k) {
+                constexpr int step = 32 / LEN;           // exp(-2 pi i k / LEN) = table entry k * 32 / LEN
+                const int e = k * step;
+                const double2 u = t[i + k], y = t[i + k + LEN / 2];
+                double2 x;
+                if (e == 0) x = y;
+                else if (e == 8) x = make_double2(y.y, -y.x);      // times -i
+                else x = make_double2(y.x * FFT_C32[e] - y.y * FFT_S32[e], y.x * FFT_S32[e] + y.y * FFT_C32[e]);
+                t[i + k] = make_double2(u.x + x.x, u.y + x.y);
+                t[i + k + LEN / 2] = make_double2(u.x - x.x, u.y - x.y);
+            }
+        }
+        FftStage<R, LEN * 2>::run(t);
+    }
+};
+template <int R>
+struct FftStage<R, 2 * R> {
+    static __device__ __forceinline__ void run(double2 (&)[R]) {}
+};
+template <int R>
+__device__ __forceinline__ void fft_reg(double2 (&v)[R]) {
+    constexpr int L = fft_log2(R);
+    double2 t[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) t[FFT_BR32[i] >> (5 - L)] = v[i];        // bit reversal in L bits
+    FftStage<R, 2>::run(t);
+#pragma unroll
+    for (int i = 0; i < R; ++i) v[i] = t[i];
+}
+__host__ __device__ __forceinline__ int fft_pad(int i) { return i + (i >> 4); }
+
+struct BigFftArgs {
+    const double *X;
+    const double2 *tw;
+    const int *perm;
+    double2 *fs;
+    int N, h, nc, imoff, has_b;
+    size_t wstride, off;
+    double scale;
+    double *out;
+    size_t out_nstride;
+};
+template <int R, bool FIRST, bool LAST>
+__device__ __forceinline__ void big_pass(const BigFftArgs &a, int ns, int lg) {
+    const int N = a.N, per = N / R, np = ns * R, tstep = N / np;
+    for (int j = threadIdx.x; j < per; j += blockDim.x) {
+        const int k = j & (ns - 1), g = j >> lg;
+        const int i0 = g * np + k;
+        double2 v[R];
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+            const int i = i0 + m * ns;
+            if (FIRST) v[m] = load_Z(a.X, __ldg(a.perm + i), N, a.h, a.wstride, a.off, a.imoff, a.has_b != 0);
+            else v[m] = a.fs[fft_pad(i)];
+        }
+        if (!FIRST && k > 0) {          // the first pass has ns = 1: no twiddles
+            const double2 w1 = __ldg(a.tw + k * tstep);
+            double2 wm = w1;
+#pragma unroll
+            for (int m = 1; m < R; ++m) {
+                if ((m & 7) == 0) wm = __ldg(a.tw + ((m * k * tstep) & (N - 1)));      // fresh from the table: bounds the rounding of the running product
+                v[m] = cmul(v[m], wm);
+                if (m + 1 < R && ((m + 1) & 7) != 0) wm = cmul(wm, w1);
+            }
+        }
+        fft_reg<R>(v);
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+            const int i = i0 + m * ns;
+            if (LAST) {
+                double *o = a.out + (size_t)i * a.out_nstride;
+                if (a.has_b && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+                    *reinterpret_cast<double2 *>(o) = make_double2(v[m].x * a.scale, v[m].y * a.scale);
+                } else {
+                    o[0] = v[m].x * a.scale;
+                    if (a.has_b) o[1] = v[m].y * a.scale;
+                }
+            } else {
+                a.fs[fft_pad(i)] = v[m];
+            }
+        }
+    }
+}
+template <bool FIRST, bool LAST>
+__device__ __forceinline__ void big_pass_r(int R, const BigFftArgs &a, int ns, int lg) {
+    if (R == 16) big_pass<16, FIRST, LAST>(a, ns, lg);
+    else if (R == 32) big_pass<32, FIRST, LAST>(a, ns, lg);
+    else if (R == 8) big_pass<8, FIRST, LAST>(a, ns, lg);
+    else if (R == 4) big_pass<4, FIRST, LAST>(a, ns, lg);
+    else big_pass<2, FIRST, LAST>(a, ns, lg);
+}
+__global__ void __launch_bounds__(256, 1) k_fft_big(const double *__restrict__ X, FftPlan pl, const double2 *__restrict__ tw, const int *__restrict__ perm,
+                                                     int nc, int ncp, int ncx, int imoff, double scale, double *__restrict__ out, size_t out_tstride,
+                                                     size_t out_nstride) {
+    extern __shared__ double2 fs[];
+    const int pair = blockIdx.x, tr = blockIdx.y, c0 = 2 * pair;
+    BigFftArgs a;
+    a.X = X; a.tw = tw; a.perm = perm; a.fs = fs; a.N = pl.n; a.h = pl.n / 2; a.nc = nc; a.imoff = imoff; a.has_b = c0 + 1 < nc;
+    a.wstride = (size_t)ncx; a.off = (size_t)tr * (a.h + 1) * ncx + c0;
+    a.scale = scale; a.out = out + (size_t)tr * out_tstride + c0; a.out_nstride = out_nstride;
+    int ns = 1;
+    for (int p = 0; p < pl.npass; ++p) {
+        const int R = pl.radix[p], lg = 31 - __clz(ns);
+        const bool first = p == 0, last = p == pl.npass - 1;
+        if (first && last) big_pass_r<true, true>(R, a, ns, lg);
+        else if (first) big_pass_r<true, false>(R, a, ns, lg);
+        else if (last) big_pass_r<false, true>(R, a, ns, lg);
+        else big_pass_r<false, false>(R, a, ns, lg);
+        ns *= R;
+        if (!last) __syncthreads();
+    }
+}
+// radix sequence of the big-radix kernel for N = 2^e >= 2: 16, 16, ..., rest (<= 32)
+bool make_big_plan(int n, FftPlan &pl) {
+    if (n < 2 || (n & (n - 1))) return false;
+    pl.n = n;
+    pl.npass = 0;
+    int rem = n;
+    while (rem > 32) { pl.radix[pl.npass++] = 16; rem /= 16; }
+    pl.radix[pl.npass++] = rem;
+    return true;
+}
+
 // one (trajectory, column pair) per CTA; CTAs of neighbouring pairs run side by side and touch the same rows of X and of the
 // output table at the same time (the 16-byte accesses of a pair combine to full sectors / DRAM pages in L2)
 __global__ void __launch_bounds__(512) k_fft_inplace(const double *__restrict__ X, FftPlan pl, const double2 *__restrict__ tw,
@@ -870,6 +1010,25 @@ int factor_batch(sclmd_noise_plan *pl, int nw, int nbasis, const double *basis_h
     return 0;
 }
 
+// Scratch of the generator (draws, spectrum, four-step intermediate, injected draws), cached per device between calls: cudaMalloc /
+// cudaFree of multi-GB buffers cost ~10 ms per GB, more than the kernels that use them.  One generation at a time per process.
+struct NoiseScratch {
+    int device = -1;
+    DevBuf<double> xi, X, xih;
+    DevBuf<double2> four;
+};
+std::mutex g_scratch_mutex;
+std::vector<std::unique_ptr<NoiseScratch>> g_scratch;
+NoiseScratch &noise_scratch(int device) {
+    for (auto &s : g_scratch)
+        if (s->device == device) return *s;
+    g_scratch.emplace_back(new NoiseScratch());
+    g_scratch.back()->device = device;
+    return *g_scratch.back();
+}
+template <typename T>
+cudaError_t reserve(DevBuf<T> &b, size_t count) { return b.n >= count ? cudaSuccess : b.alloc_raw(count); }
+
 // series for `ntraj` trajectories written to out[(n*out_nstride) + traj*out_tstride + c]
 int generate(sclmd_noise_plan *pl, int ntraj, const double *xi_host, uint64_t seed, long long traj0, double *out, size_t out_tstride,
              size_t out_nstride, cudaStream_t st) {
@@ -894,30 +1053,36 @@ int generate(sclmd_noise_plan *pl, int ntraj, const double *xi_host, uint64_t se
             set_error("noise: cannot split nmd=%d for the four-step FFT", N);
             return SCLMD_ERR_ARG;
         }
-    } else if (!pl->tw.p) {
+    }
+    FftPlan big;
+    const bool use_big = direct && !getenv("SCLMD_FFT_RADIX4") && make_big_plan(N, big) && (size_t)fft_pad(N) * sizeof(double2) <= 200 * 1024;
+    if (direct && !pl->tw.p) {
         SCLMD_CUDA(pl->tw.alloc(N));
         SCLMD_CUDA(pl->perm.alloc(N));
         k_twiddle<<<cdiv(N, 256), 256, 0, st>>>(pl->tw.p, N);
-        k_digit_reverse<<<cdiv(N, 256), 256, 0, st>>>(pl->perm.p, full);
+        k_digit_reverse<<<cdiv(N, 256), 256, 0, st>>>(pl->perm.p, use_big ? big : full);
         SCLMD_CUDA(cudaGetLastError());
         pl->launches += 2;
     }
     const int npair = (nc + 1) / 2;
-    // trajectory chunk: the scratch (draws + spectrum, + the four-step intermediate) takes at most half of the free device memory,
-    // and at most 24 GB; whole 128-row tiles of the batched product when possible
+    // trajectory chunk: the scratch (draws + spectrum, + the four-step intermediate) takes at most a quarter of the free device memory
+    // and at most 6 GB (cached between calls); whole 128-row tiles of the batched product when possible
+    std::lock_guard<std::mutex> lock(g_scratch_mutex);
+    NoiseScratch &sc = noise_scratch(pl->device);
     size_t free_b = 0, total_b = 0;
     SCLMD_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    const size_t budget = std::min<size_t>(free_b / 2, (size_t)24 << 30);
+    const size_t have = (sc.xi.n + sc.X.n + sc.xih.n) * sizeof(double) + sc.four.n * sizeof(double2);
+    const size_t budget = std::min<size_t>((free_b + have) / 4, (size_t)6 << 30);
     const size_t per_traj = (size_t)nw * (ncp + ncx) * sizeof(double) + (direct ? 0 : (size_t)npair * N * sizeof(double2)) +
                             (xi_host ? (size_t)nw * nc * sizeof(double) : 0);
     int chunk = (int)std::max<size_t>(1, std::min<size_t>(ntraj, budget / per_traj));
     if (chunk >= 128 && chunk < ntraj) chunk -= chunk % 128;
-    DevBuf<double> xi, X, xih;
-    DevBuf<double2> scratch;
-    SCLMD_CUDA(xi.alloc_raw((size_t)nw * chunk * ncp));
-    SCLMD_CUDA(X.alloc_raw((size_t)nw * chunk * ncx));       // the pad column of an odd nc is neither written nor read
-    if (!direct) SCLMD_CUDA(scratch.alloc_raw((size_t)chunk * npair * N));
-    if (xi_host) SCLMD_CUDA(xih.alloc_raw((size_t)chunk * nw * nc));
+    DevBuf<double> &xi = sc.xi, &X = sc.X, &xih = sc.xih;
+    DevBuf<double2> &scratch = sc.four;
+    SCLMD_CUDA(reserve(xi, (size_t)nw * chunk * ncp));
+    SCLMD_CUDA(reserve(X, (size_t)nw * chunk * ncx));        // the pad column of an odd nc is neither written nor read
+    if (!direct) SCLMD_CUDA(reserve(scratch, (size_t)chunk * npair * N));
+    if (xi_host) SCLMD_CUDA(reserve(xih, (size_t)chunk * nw * nc));
     const double scale = 1.0 / (pl->dt * N);   // dw/2pi (functions.py:51)
     std::vector<cudaEvent_t> evs;
     pl->stage_ms[0] = pl->stage_ms[1] = pl->stage_ms[2] = 0.0;
@@ -979,7 +1144,14 @@ int generate(sclmd_noise_plan *pl, int ntraj, const double *xi_host, uint64_t se
         }
         mark();
         double *o = out + (size_t)t0 * out_tstride;
-        if (direct) {
+        if (use_big) {
+            const size_t smem_big = (size_t)(N + (N >> 4) + 1) * sizeof(double2);
+            SCLMD_CUDA(cudaFuncSetAttribute(k_fft_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big));
+            k_fft_big<<<dim3(npair, cnt), std::min(256, std::max(32, N / 16)), smem_big, st>>>(X.p, big, pl->tw.p, pl->perm.p, nc, ncp, ncx, imoff, scale, o,
+                                                                                           out_tstride, out_nstride);
+            SCLMD_CUDA(cudaGetLastError());
+            ++pl->launches;
+        } else if (direct) {
             SCLMD_CUDA(cudaFuncSetAttribute(k_fft_inplace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_inplace));
             k_fft_inplace<<<dim3(npair, cnt), N >= 2048 ? 512 : 128, smem_inplace, st>>>(X.p, full, pl->tw.p, pl->perm.p, cnt, nc, ncp, ncx, imoff, scale, o, out_tstride,
                                                                                       out_nstride);
@@ -998,7 +1170,7 @@ int generate(sclmd_noise_plan *pl, int ntraj, const double *xi_host, uint64_t se
         }
         mark();
     }
-    const cudaError_t se = cudaStreamSynchronize(st);       // the scratch buffers go out of scope below
+    const cudaError_t se = cudaStreamSynchronize(st);       // the cached scratch may be reused by the next call
     for (size_t i = 0; i + 3 < evs.size(); i += 4)
         for (int k = 0; k < 3; ++k) {
             float ms = 0;
@@ -1011,6 +1183,13 @@ int generate(sclmd_noise_plan *pl, int ntraj, const double *xi_host, uint64_t se
 }
 
 }  // namespace
+
+void sclmd::release_noise_scratch() {
+    std::lock_guard<std::mutex> lock(g_scratch_mutex);
+    for (auto &s : g_scratch)
+        if (cudaSetDevice(s->device) == cudaSuccess) { s->xi.release(); s->X.release(); s->xih.release(); s->four.release(); }
+    g_scratch.clear();
+}
 
 extern "C" {
 
@@ -1059,9 +1238,22 @@ int sclmd_noise_plan_create(int device, int nmd, double dt, int nc, int nbasis, 
         DevBuf<double> L2, ev2, V, lam, cwd;
         SCLMD_CUDA(L2.alloc((size_t)2 * nc * pl->ncp)); SCLMD_CUDA(ev2.alloc((size_t)2 * nc));
         SCLMD_CUDA(V.alloc((size_t)nc * pl->ncp)); SCLMD_CUDA(lam.alloc(nc)); SCLMD_CUDA(cwd.alloc(nw));
-        if (int e = factor_batch(pl.get(), 2, 1, basis + (size_t)b0 * nc * nc, 1, one_idx, cpos, nullptr, false, L2.p, ev2.p, true)) return e;
-        k_unit_vectors<<<1, 256, 0, pl->st>>>(L2.p, L2.p + (size_t)nc * pl->ncp, ev2.p, ev2.p + nc, nc, pl->ncp, V.p, lam.p);
-        SCLMD_CUDA(cudaGetLastError());
+        const double *B0 = basis + (size_t)b0 * nc * nc;
+        bool diagonal = true;
+        for (int i = 0; i < nc && diagonal; ++i)
+            for (int j = 0; j < nc; ++j)
+                if (i != j && B0[(size_t)i * nc + j] != 0.0) { diagonal = false; break; }
+        if (diagonal) {      // Debye friction, efric = I/damp: the eigenvectors are the unit vectors
+            std::vector<double> Vh((size_t)nc * pl->ncp, 0.0), lh(nc);
+            for (int i = 0; i < nc; ++i) { Vh[(size_t)i * pl->ncp + i] = 1.0; lh[i] = B0[(size_t)i * nc + i]; }
+            SCLMD_CUDA(cudaMemcpyAsync(V.p, Vh.data(), Vh.size() * sizeof(double), cudaMemcpyHostToDevice, pl->st));
+            SCLMD_CUDA(cudaMemcpyAsync(lam.p, lh.data(), nc * sizeof(double), cudaMemcpyHostToDevice, pl->st));
+            SCLMD_CUDA(cudaStreamSynchronize(pl->st));
+        } else {
+            if (int e = factor_batch(pl.get(), 2, 1, B0, 1, one_idx, cpos, nullptr, false, L2.p, ev2.p, true)) return e;
+            k_unit_vectors<<<1, 256, 0, pl->st>>>(L2.p, L2.p + (size_t)nc * pl->ncp, ev2.p, ev2.p + nc, nc, pl->ncp, V.p, lam.p);
+            SCLMD_CUDA(cudaGetLastError());
+        }
         SCLMD_CUDA(cudaMemcpyAsync(cwd.p, cw.data(), nw * sizeof(double), cudaMemcpyHostToDevice, pl->st));
         k_scale_factor<<<nw, 256, 0, pl->st>>>(V.p, lam.p, cwd.p, nc, pl->ncp, pl->L.p);
         SCLMD_CUDA(cudaGetLastError());

@@ -80,12 +80,12 @@ def test_myfft_at_the_config4_length():
     assert relerr(f.Fourier1D(f.iFourier1D(a)), a) < 1e-11
 
 
-@pytest.mark.parametrize("ntraj", [3, 66])
+@pytest.mark.parametrize("ntraj", [3, 130])
 def test_config5_full_kernels_at_full_size_vs_oracle(ntraj):
     """BASELINE configs[4], full-kernel variant, per-trajectory shape at full size: 3000 dofs, two baths of 300 dofs with
     FULL 300 x 300 memory kernels of 4096 steps (2.9 GB per bath), random pre-existing history so that the whole memory acts
-    from the first step.  ntraj = 3 takes the skinny GEMM tiles, ntraj = 66 the production path (64-wide tiles, wave-fitting
-    split-K over the history ring, a ragged last row tile); <= 1e-10 per step against the oracle (baths.py:448-458)"""
+    from the first step.  ntraj = 3 takes the skinny cp.async GEMM tiles, ntraj = 130 the production path (TMA-fed stream-K contraction
+    over the rotating ring: 77 805 K-slabs per tile cut across all SMs, a ragged last row tile); <= 1e-10 per step against the oracle (baths.py:448-458)"""
     from sclmd_b200.engine import MDEngine
     natoms, nc, ml, nmd = 1000, 300, 4096, 32
     nph, dt = 3 * natoms, 0.25 / 0.658

@@ -78,7 +78,8 @@ def test_golden_trajectories(name, golden_dir):
     ("full", 40, 30, 5, 90),        # split-K full-kernel tail
     ("full", 2, 7, 2, 11),          # odd nc -> padded rows
     ("full", 6, 30, 70, 12),        # > 64 trajectories, narrow output: 64-wide GEMM tiles with a wave-fitting split count
-    ("full", 3, 150, 130, 8),       # > 64 trajectories, wide output: 128-wide tiles
+    ("full", 3, 150, 130, 8),       # >= 96 trajectories: TMA / stream-K contraction over the ring, 160-wide tiles
+    ("full", 37, 34, 100, 80),      # the same kernel with a ring that wraps (80 steps > ml), ragged 16-wide K slabs (ncp = 34)
 ])
 def test_memory_kernels_vs_oracle(kind, ml, nc, ntraj, nsteps):
     from sclmd_b200.engine import MDEngine
