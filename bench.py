@@ -224,10 +224,15 @@ def fill_noise(eng, w, ntraj, seed, traj0):
     rng = np.random.default_rng(seed)
     t0 = time.perf_counter()
     stages = {"draws_ms": 0.0, "gemm_ms": 0.0, "transform_ms": 0.0, "factor_ms": 0.0}
+    t_plan = t_gen = 0.0
     for b in range(2):
         gam = np.array([np.eye(w["nc"]) * 0.05 * np.pi / 6.0])
+        ta = time.perf_counter()
         plan = N.ph_plan(gam, np.array([0.0]), 300.0 * (1.05 if b == 0 else 0.95), 0.5, w["dt"], w["nmd"], device=eng.device)
+        tb = time.perf_counter()
         _lib.check(_lib.lib().sclmd_md_generate_noise(eng._h, b, plan._h, C.c_uint64(seed), int(traj0)))
+        t_gen += time.perf_counter() - tb
+        t_plan += tb - ta
         pr = plan.profile()
         for k in stages:
             stages[k] += pr[k]
@@ -240,7 +245,7 @@ def fill_noise(eng, w, ntraj, seed, traj0):
                 "(big-radix in-place FFT in shared memory) straight into the trajectory-major noise tables",
         "samples": nsamp, "device_s": dev_s, "samples_per_s_device": nsamp / dev_s if dev_s > 0 else None,
         "frac_of_hbm_roofline_16B_per_sample": (nsamp * 16 / dev_s) / (peaks()[0] * 1e9) if dev_s > 0 else None,
-        "stage_ms": stages, "wall_s_incl_plan_setup_on_the_host": gen_s,
+        "stage_ms": stages, "wall_s_incl_plan_setup_on_the_host": gen_s, "wall_s_plan_setup": t_plan, "wall_s_generate_calls": t_gen,
         "gemm_tflops": 2.0 * w["nc"] ** 2 * (w["nmd"] // 2 + 1) * ntraj * 2 / (stages["gemm_ms"] * 1e-3) / 1e12 if stages["gemm_ms"] > 0 else None}
     nblk = min(32, w["nmd"])
     blocks = []

@@ -77,8 +77,13 @@ class _BathBase:
         return k
 
     def _generate_device_noise(self, engine, index, traj0):
+        from . import parallel as PAR
         plan = self._plan(engine.device)
+        # ONE Philox key for the whole ensemble (rank 0's draw); the counters carry the GLOBAL trajectory index, so a sharded
+        # ensemble gets the same noise as the same ensemble on one GPU
         seed = int(np.random.randint(0, 2 ** 62))
+        if self._md is not None and getattr(self._md, "sharded", False):
+            seed = PAR.broadcast_int(seed)
         check(_lib.lib().sclmd_md_generate_noise(engine._h, index, plan._h, seed, int(traj0)))
         plan.close()
         return seed

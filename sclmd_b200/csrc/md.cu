@@ -1455,6 +1455,12 @@ struct sclmd_md {
     cudaStream_t str = nullptr;                   // read-back stream of sclmd_md_get_step_observables
     long long obs_slab = -1;
     bool noise_pending = false;
+    // time slabs of the pending streamed upload(s); np_mixed: uploads of different slab ranges are pending together
+    int np_slab0 = 0, np_nslab = 0;
+    bool np_mixed = false;
+    bool pending_upload_covers(long long slab) const {
+        return np_mixed || (int)(((slab % nmd) - np_slab0 + nmd) % nmd) < np_nslab;
+    }
     cudaStream_t st = nullptr, st2 = nullptr;   // st2: the FP64-bound K.q GEMM overlaps the HBM-bound history tails
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evG = nullptr;
     bool overlap = true;
@@ -2097,7 +2103,10 @@ struct sclmd_md {
         return flush();
     }
     int modal_step() {
-        if (noise_pending) {
+        // every kernel of this step reads noise slab t only: an upload of other slabs (the streaming path sends slab t + 1 while
+        // step t runs) must not hold the step back -- the wait then goes to the end of the step, ahead of the next one
+        const bool defer_wait = noise_pending && !pending_upload_covers(t);
+        if (noise_pending && !defer_wait) {
             SCLMD_CUDA(cudaStreamWaitEvent(st, evN, 0));
             noise_pending = false;
         }
@@ -2113,6 +2122,10 @@ struct sclmd_md {
         SCLMD_CUDA(cudaEventRecord(evG, st2));
         for (auto &b : baths) if (int e = tail_step(*b, t)) return e;
         SCLMD_CUDA(cudaStreamWaitEvent(st, evG, 0));
+        if (defer_wait) {
+            SCLMD_CUDA(cudaStreamWaitEvent(st, evN, 0));
+            noise_pending = false;
+        }
         mqi ^= 1;
         ++t;
         dt_synced = false;
@@ -2836,6 +2849,10 @@ int sclmd_md_set_noise_rows(sclmd_md *h, int bath, int slab0, int nslab, const d
         done += n;
     }
     SCLMD_CUDA(cudaEventRecord(h->evN, h->stc));
+    if (h->noise_pending && (h->np_slab0 != slab0 || h->np_nslab != nslab)) h->np_mixed = true;
+    if (!h->noise_pending) h->np_mixed = false;
+    h->np_slab0 = slab0;
+    h->np_nslab = nslab;
     h->noise_pending = true;
     return SCLMD_OK;
 }

@@ -14,6 +14,7 @@ import numpy as np
 from . import _lib
 from numpy import linalg as LA
 
+from . import parallel as PAR
 from . import units as U
 from .engine import MDEngine
 from .functions import bose, chkShape, mdot, symmetrize
@@ -21,12 +22,23 @@ from .functions import bose, chkShape, mdot, symmetrize
 
 class md:
     def __init__(self, dt, nmd, T, syslist=None, axyz=None, dyn=None, nstart=0, nstop=1, npie=1, md2ang=0.06466,
-                 ntraj=1, device=0):
+                 ntraj=1, device=None):
         self.nstart, self.nstop = nstart, nstop
         self.dt, self.nmd = dt, nmd
         self.T = T
         self.npie = npie
-        self.ntraj, self.device = int(ntraj), int(device)
+        # `ntraj` is the size of the WHOLE ensemble.  Inside a torch.distributed job (one process per GPU, torchrun) every rank
+        # takes a contiguous block of it: independent trajectories, no data-path collective.  The noise
+        # streams are indexed by the global trajectory number, so results do not depend on the number of ranks.
+        self.ntraj_global = int(ntraj)
+        self.rank, self.world = PAR.rank_world()
+        if self.world > 1 and self.ntraj_global >= self.world:
+            lo, hi = PAR.shard_range(self.ntraj_global, self.rank, self.world)
+            self.traj0, self.ntraj = lo, hi - lo
+        else:                               # a single trajectory does not shard: replicas only
+            self.traj0, self.ntraj = 0, self.ntraj_global
+        self.sharded = self.ntraj != self.ntraj_global
+        self.device = PAR.local_device(0) if device is None else int(device)
         self.saveall = self.savep = self.saveq = self.rmnc = False
         self.nstep = None
         self.pforce = None
@@ -210,7 +222,9 @@ class md:
             am = np.zeros(len(av))
             ok = av >= 0.01                          # md.py:317: no motion in slow modes
             am[ok] = np.array([((bose(a, self.T) + 0.5) * 2.0 / a) ** 0.5 for a in av[ok]])
-            r = np.random.rand(self.ntraj, len(av))
+            r = np.random.rand(self.ntraj_global, len(av))
+            if self.sharded:                         # rank 0's draw for the whole ensemble, every rank keeps its block
+                r = PAR.broadcast_array(r)[self.traj0:self.traj0 + self.ntraj]
             dis = (am * np.cos(2. * np.pi * r)) @ au.T
             vel = -(av * am * np.sin(2. * np.pi * r)) @ au.T
             dis, vel = ApplyConstraint(dis, self.constraint), ApplyConstraint(vel, self.constraint)
@@ -276,6 +290,8 @@ class md:
                 nz = np.asarray(b._noise, dtype=float)
                 if nz.ndim == 2:
                     nz = np.broadcast_to(nz, (self.ntraj,) + nz.shape)
+                elif self.sharded and nz.shape[0] == self.ntraj_global:      # injected for the whole ensemble: keep this rank's block
+                    nz = nz[self.traj0:self.traj0 + self.ntraj]
                 self._eng.set_noise(i, nz)
                 self._noise_seen[i] = b._noise_version
 
@@ -288,7 +304,7 @@ class md:
     def _device_noise(self, bath):
         """called by bath.gnoi(): fill the device table for every trajectory, no host round trip"""
         self._ensure_engine()
-        bath._generate_device_noise(self._eng, bath._index, 0)
+        bath._generate_device_noise(self._eng, bath._index, self.traj0)
         bath._noise_version += 1
         self._noise_seen[bath._index] = bath._noise_version
         if self.ntraj == 1:
@@ -431,7 +447,8 @@ class md:
         self.info()
         for j in range(self.nstart, self.nstop):
             print("\n" + "MD run: " + str(j))
-            fn, fnm = "MD" + str(j) + ".nc", "MD" + str(j - 1) + ".nc"
+            tag = (".rank%d" % self.rank) if self.sharded else ""      # one checkpoint per rank of a sharded ensemble
+            fn, fnm = "MD" + str(j) + tag + ".nc", "MD" + str(j - 1) + tag + ".nc"
             ipie = -1
             if os.path.isfile(fn):
                 ck = self._read_checkpoint(fn)
@@ -484,7 +501,7 @@ class md:
             for ii, b in enumerate(self.baths):
                 cur = np.asarray(b.cur).reshape(self.ntraj, self.nmd)
                 for k in range(self.ntraj):
-                    run = j if self.ntraj == 1 else j * self.ntraj + k
+                    run = j if self.ntraj_global == 1 else j * self.ntraj_global + self.traj0 + k      # globally unique run index
                     with open("kappa." + str(self.T) + "." + "bath" + str(ii) + ".run" + str(run) + ".dat", "w") as fk:
                         fk.write("%i %f    %f \n" % (run, self.T, np.mean(cur[k]) * U.curcof))
             if self.saveq:
@@ -497,11 +514,13 @@ class md:
                 os.remove(fnm)
 
     def mean_currents(self):
-        """[nbaths] ensemble- and time-averaged heat current * curcof (what the kappa files hold),
-        summed on the device; the multi-GPU all-reduce payload (sum, count)."""
+        """[nbaths] heat current * curcof averaged over time and over EVERY trajectory of the ensemble (what the kappa files hold):
+        per-bath sums on the device, then ONE all-reduce of [sums..., count] over the ranks of a sharded ensemble -- the only
+        collective of the path.  Returns (means, global sums, global count)."""
         self._ensure_engine()
         sums = np.array([self._eng.current_sums(i).sum() for i in range(len(self.baths))])
-        return sums / (self.ntraj * self.nmd) * U.curcof, sums, self.ntraj * self.nmd
+        tot = PAR.allreduce_sum(list(sums) + [float(self.ntraj * self.nmd)]) if self.sharded else np.append(sums, self.ntraj * self.nmd)
+        return tot[:-1] / tot[-1] * U.curcof, tot[:-1], int(tot[-1])
 
     def _write_frame(self, trajfile):
         q = np.asarray(self.q).reshape(self.ntraj, self.nph)[0]
@@ -526,7 +545,7 @@ class md:
     # the per-bath history rings `ring<i>` [ntraj, ml_i, nc_i]; an ensemble adds a leading `ntraj` dimension to p, q, phis, energy.
     def dump(self, ipie, id):
         from scipy.io import netcdf_file
-        f = netcdf_file("MD" + str(id) + ".nc", 'w')
+        f = netcdf_file("MD" + str(id) + ((".rank%d" % self.rank) if self.sharded else "") + ".nc", 'w')
         f.title = 'Output from sclmd_b200.md'
         f.createDimension('nph', self.nph)
         f.createDimension('one', 1)

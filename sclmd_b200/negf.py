@@ -11,7 +11,7 @@ from ._lib import as_f64, as_i32, check, dptr, iptr
 
 class bpt:
     def __init__(self, infile, maxomega, damp, dofatomofbath, dofatomfixed=[[], []], dynmatfile=None, num=1000,
-                 natoms=None, device=0, write_files=None):
+                 natoms=None, device=None, write_files=None):
         self.rpc = 6.582119569e-4     # reduced Planck constant, eV*ps
         # falsefrequencies.dat / omegas.dat / eigvecs.dat in the working directory (negf.py:100-102): by default whenever the
         # dynamical matrix comes from a file, as in the reference's flow; not when the caller hands over an array
@@ -25,6 +25,9 @@ class bpt:
         self.dofatomofbias = []
         self.dofatomofbath = [list(dofatomofbath[0]), list(dofatomofbath[1])]
         self.dynmatfile = dynmatfile
+        if device is None:                 # the GPU of this rank under torchrun
+            from . import parallel as _PAR
+            device = _PAR.local_device(0)
         self.device = device
         self.natoms = natoms
         self.getdynmat(infile)
@@ -213,9 +216,12 @@ class bpt:
 
     def gettm(self, vector=False):
         """negf.py:104-119"""
+        from . import parallel as PAR
         x = np.linspace(0, self.maxomega, self.intnum + 1)
-        self.tmnumber = np.array(np.column_stack((x, self.tm_sweep(x))))
-        np.savetxt('transmission.dat', np.column_stack((self.tmnumber[:, 0] * self.rpc, self.tmnumber[:, 1])))
+        # inside a torch.distributed job the grid is cut into contiguous blocks over the ranks and all-gathered (frequencies are independent)
+        self.tmnumber = np.array(np.column_stack((x, PAR.sharded_sweep(self.tm_sweep, x))))
+        if PAR.rank_world()[0] == 0:
+            np.savetxt('transmission.dat', np.column_stack((self.tmnumber[:, 0] * self.rpc, self.tmnumber[:, 1])))
 
     def ps_sweep(self, omegas, T, atomlist):
         om = as_f64(omegas)
@@ -244,9 +250,11 @@ class bpt:
         if atomlist is None:
             atomlist = np.array(range(0, len(self.dynmat))) + len(self.dofatomfixed[0])
         x2 = np.sort(omegalist) / self.rpc if omegalist is not None else np.linspace(0, maxomega / self.rpc, intnum + 1)
-        self.psnumber = np.array(np.column_stack((x2, self.ps_sweep(x2, T, atomlist))))
+        from . import parallel as PAR
+        self.psnumber = np.array(np.column_stack((x2, PAR.sharded_sweep(lambda om: self.ps_sweep(om, T, atomlist), x2))))
         name = 'powerspectrum.' + (str(filename) + '.' if filename is not None else '') + str(T) + '.dat'
-        np.savetxt(name, np.column_stack((self.psnumber[:, 0] * self.rpc, self.psnumber[:, 1])))
+        if PAR.rank_world()[0] == 0:
+            np.savetxt(name, np.column_stack((self.psnumber[:, 0] * self.rpc, self.psnumber[:, 1])))
 
     def thermalcurrent(self, T, delta):
         """negf.py:245-270: trapezoid over the stored transmission, nW"""

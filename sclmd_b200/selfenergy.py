@@ -8,7 +8,7 @@ from ._lib import as_f64, check, dptr
 
 class sig:
     def __init__(self, infile, maxomega, atomgroup0, atomgroup1, dofatomfixed=[[], []], dynmatfile=None, num=1000,
-                 eta=0.164e-3, device=0):
+                 eta=0.164e-3, device=None):
         self.rpc = 6.582119569e-4
         self.maxomega = maxomega / self.rpc
         self.intnum = num
@@ -17,6 +17,9 @@ class sig:
         self.dofatomK11 = list(atomgroup1)
         self.dofatomfixed = dofatomfixed
         self.dynmatfile = dynmatfile
+        if device is None:                 # the GPU of this rank under torchrun
+            from . import parallel as _PAR
+            device = _PAR.local_device(0)
         self.device = device
         self.ep = np.linspace(0, self.maxomega, self.intnum + 1)
         self.getdynmat(infile)
@@ -131,13 +134,17 @@ class sig:
 
     def getse(self, direction):
         """selfenergy.py:153-166"""
-        se = self.selfenergy_sweep(self.ep, direction)
+        from . import parallel as PAR
+        se = PAR.sharded_sweep(lambda om: self.selfenergy_sweep(om, direction), self.ep)      # frequency blocks over the ranks, all-gathered
         dosx = -np.trace(np.imag(se), axis1=1, axis2=2) * self.ep / np.pi
         self.dos = np.array(np.column_stack((self.ep, dosx)))
-        np.savetxt('densityofstates_' + str(direction) + '.dat', np.column_stack((self.dos[:, 0] * self.rpc, self.dos[:, 1])))
+        if PAR.rank_world()[0] == 0:
+            np.savetxt('densityofstates_' + str(direction) + '.dat', np.column_stack((self.dos[:, 0] * self.rpc, self.dos[:, 1])))
         return se
 
     def gettm(self):
         """selfenergy.py:168-178"""
-        self.tmnumber = np.array(np.column_stack((self.ep, self.tm_sweep(self.ep))))
-        np.savetxt('transmission.dat', np.column_stack((self.tmnumber[:, 0] * self.rpc, self.tmnumber[:, 1])))
+        from . import parallel as PAR
+        self.tmnumber = np.array(np.column_stack((self.ep, PAR.sharded_sweep(self.tm_sweep, self.ep))))
+        if PAR.rank_world()[0] == 0:
+            np.savetxt('transmission.dat', np.column_stack((self.tmnumber[:, 0] * self.rpc, self.tmnumber[:, 1])))

@@ -80,3 +80,62 @@ def test_single_process_is_identity():
     m = PAR.ensemble_mean_currents([2.0, -2.0], 4, curcof=1.0)
     assert np.allclose(m, [0.5, -0.5])
     assert PAR.thermal_conductance(m, 300.0, 0.1) == pytest.approx(0.5 / 30.0)
+
+
+# ---------------------------------------------------------------- the md / bpt classes inside a distributed job (host logic)
+def _facade_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import contextlib
+        import io
+        from sclmd_b200.md import md
+        from sclmd_b200.synthetic import spring_chain_dyn
+        natoms, ntraj = 6, 7
+        K = spring_chain_dyn(natoms, seed=3)
+        np.random.seed(100 if rank == 0 else 999)            # only rank 0's stream may matter
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = md(0.3, 16, 300.0, axyz=[["C", float(i), 0.0, 0.0] for i in range(natoms)], dyn=K, ntraj=ntraj)
+            m.initialise()
+        seed = PAR.broadcast_int(np.random.randint(0, 2 ** 62))
+        # a frequency sweep through the sharding helper (what bpt.gettm / sig.getse do)
+        om = np.linspace(0.0, 2.0, 11)
+        full = PAR.sharded_sweep(lambda w: np.stack([np.cos(w), np.sin(w)], axis=1) * (1 + 1j), om)
+        q.put((rank, m.traj0, m.ntraj, m.ntraj_global, m.sharded, np.array(m.q), np.array(m.p), seed, full))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_md_class_shards_its_ensemble_inside_a_distributed_job():
+    """md(..., ntraj=N) under torch.distributed (gloo here, NCCL on the GPUs): contiguous trajectory blocks, initial conditions cut
+    from rank 0's draw for the whole ensemble, one broadcast seed; the sweep helper returns the full grid on every rank"""
+    import contextlib
+    import io
+    from sclmd_b200.md import md
+    from sclmd_b200.synthetic import spring_chain_dyn
+    world, natoms, ntraj = 2, 6, 7
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_facade_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in range(world)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # the same ensemble in ONE process with rank 0's random stream
+    np.random.seed(100)
+    with contextlib.redirect_stdout(io.StringIO()):
+        one = md(0.3, 16, 300.0, axyz=[["C", float(i), 0.0, 0.0] for i in range(natoms)], dyn=spring_chain_dyn(natoms, seed=3), ntraj=ntraj)
+        one.initialise()
+    assert not one.sharded and one.traj0 == 0 and one.ntraj == ntraj
+    seed_one = int(np.random.randint(0, 2 ** 62))
+    blocks = [(r[1], r[2]) for r in res]
+    assert blocks == [(0, 4), (4, 3)] and all(r[3] == ntraj and r[4] for r in res)
+    assert np.array_equal(np.concatenate([r[5] for r in res]), one.q) and np.array_equal(np.concatenate([r[6] for r in res]), one.p)
+    assert res[0][7] == res[1][7] == seed_one
+    om = np.linspace(0.0, 2.0, 11)
+    want = np.stack([np.cos(om), np.sin(om)], axis=1) * (1 + 1j)
+    assert all(np.array_equal(r[8], want) for r in res)
