@@ -51,7 +51,19 @@ class _BathBase:
     _index = None
     _noise = None
     _noise_version = 0
-    device = 0
+    _device = None
+
+    @property
+    def device(self):
+        """the GPU the bath's own device work (gmem, gnoi before AddBath) runs on: the md's device once attached, else this rank's"""
+        if self._device is None:
+            from . import parallel as PAR
+            return PAR.local_device(0)
+        return self._device
+
+    @device.setter
+    def device(self, value):
+        self._device = None if value is None else int(value)
 
     @property
     def noise(self):

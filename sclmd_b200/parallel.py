@@ -23,9 +23,14 @@ def _dist():
 
 
 def _device_for_backend():
+    """where collective payloads live: the GPU of this rank for NCCL (LOCAL_RANK under torchrun -- NOT the CUDA runtime's current
+    device, which the C library switches when a handle on another device is used), the host for gloo"""
+    import os
     import torch
     dist = _dist()
     if dist is not None and dist.get_backend() == "nccl":
+        if "LOCAL_RANK" in os.environ:
+            return torch.device("cuda", int(os.environ["LOCAL_RANK"]))
         return torch.device("cuda", torch.cuda.current_device())
     return torch.device("cpu")
 

@@ -101,10 +101,15 @@ def test_two_rank_nccl_job_equals_one_gpu(tmp_path, monkeypatch):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q, str(tmp_path))) for r in range(2)]
     for p in procs:
         p.start()
-    res = dict(q.get(timeout=600) for _ in range(2))
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+    try:
+        res = dict(q.get(timeout=150) for _ in range(2))
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+    finally:
+        for p in procs:                  # a rank that died leaves the other one inside a collective: do not wait for NCCL's timeout
+            if p.is_alive():
+                p.kill()
     assert (res[0]["traj0"], res[0]["ntraj"], res[1]["traj0"], res[1]["ntraj"]) == (0, 3, 3, 3)
     rel = lambda a, b: float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(np.max(np.abs(b)), 1e-300))
     for i in range(2):

@@ -121,10 +121,15 @@ def test_md_class_shards_its_ensemble_inside_a_distributed_job():
     procs = [ctx.Process(target=_facade_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted([q.get(timeout=180) for _ in range(world)], key=lambda r: r[0])
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    try:
+        res = sorted([q.get(timeout=180) for _ in range(world)], key=lambda r: r[0])
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+    finally:
+        for p in procs:
+            if p.is_alive():
+                p.kill()
     # the same ensemble in ONE process with rank 0's random stream
     np.random.seed(100)
     with contextlib.redirect_stdout(io.StringIO()):
