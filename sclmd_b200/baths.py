@@ -73,6 +73,7 @@ class _BathBase:
     def noise(self, value):
         self._noise = None if value is None else np.asarray(value, dtype=float)
         self._noise_version += 1
+        self._noise_seed = None           # an injected series: no Philox key regenerates it
 
     def _noise_row(self, t):
         nz = self.noise
@@ -90,14 +91,19 @@ class _BathBase:
 
     def _generate_device_noise(self, engine, index, traj0):
         from . import parallel as PAR
-        plan = self._plan(engine.device)
         # ONE Philox key for the whole ensemble (rank 0's draw); the counters carry the GLOBAL trajectory index, so a sharded
         # ensemble gets the same noise as the same ensemble on one GPU
         seed = int(np.random.randint(0, 2 ** 62))
         if self._md is not None and getattr(self._md, "sharded", False):
             seed = PAR.broadcast_int(seed)
-        check(_lib.lib().sclmd_md_generate_noise(engine._h, index, plan._h, seed, int(traj0)))
+        return self._regenerate_device_noise(engine, index, traj0, seed)
+
+    def _regenerate_device_noise(self, engine, index, traj0, seed):
+        """fill the device table from a known Philox key (also the resume path of md.Run: the key is stored in the checkpoint)"""
+        plan = self._plan(engine.device)
+        check(_lib.lib().sclmd_md_generate_noise(engine._h, index, plan._h, int(seed), int(traj0)))
         plan.close()
+        self._noise_seed = int(seed)
         return seed
 
 

@@ -128,7 +128,7 @@ class md:
 
     def AddPowerSection(self, atomlist):
         self.atomlist = atomlist
-        self.poweratomlist = np.empty((len(self.atomlist), self.nmd, 2))
+        self.poweratomlist = np.zeros((len(self.atomlist), self.nmd, 2))
 
     def AddConstr(self, constr):
         self.constraint = constr
@@ -136,7 +136,7 @@ class md:
 
     def CalPowerSpec(self, cal=True):
         self.savep = cal
-        self.power = np.empty((self.nmd, 2))
+        self.power = np.zeros((self.nmd, 2))       # (the reference leaves it uninitialised; it is only ever weighted with 0 before the first run)
 
     def CalAveStruct(self, cal=True):
         self.saveq = cal
@@ -242,8 +242,13 @@ class md:
 
     # ------------------------------------------------------------ device plumbing
     def _signature(self):
+        # everything that is baked into the device handle: kernels, and for electron baths the bias and the matrices behind the
+        # q- and p-dependent forces (ebath.setbias / CheckEmat after AddBath must rebuild it: the reference reads them live, baths.py:243-249)
+        def bath_sig(b):
+            return (id(b.kernel), b.ml, getattr(b, "bias", None), id(getattr(b, "exim", None)), id(getattr(b, "zeta1", None)),
+                    id(getattr(b, "zeta2", None)), id(getattr(b, "efric", None)), tuple(np.asarray(b.cids).tolist()))
         return (self.nph, self.ntraj, self.dt, self.nmd, len(self.baths), id(self.dyn), id(self.pforce),
-                tuple(id(b.kernel) for b in self.baths), id(self.constraint))
+                tuple(bath_sig(b) for b in self.baths), id(self.constraint))
 
     def _ensure_engine(self):
         if self.pforce is None and self.dyn is None:
@@ -281,10 +286,14 @@ class md:
 
     def _push(self):
         """host attributes -> device (state if it was reassigned, injected noise if it changed)"""
-        if getattr(self, "_state_dirty", True) or getattr(self, "_last_p", None) is not self.p or getattr(self, "_last_q", None) is not self.q:
+        # reassigned arrays are seen by identity, in-place edits (md.p[:] = ..., md.q *= 0) by a fingerprint of the values
+        changed = (getattr(self, "_state_dirty", True) or getattr(self, "_last_p", None) is not self.p or getattr(self, "_last_q", None) is not self.q
+                   or getattr(self, "_last_print", None) != self._fingerprint())
+        if changed:
             self._eng.set_state(np.asarray(self.q, dtype=float).reshape(self.ntraj, self.nph),
                                 np.asarray(self.p, dtype=float).reshape(self.ntraj, self.nph), int(self.t))
             self._state_dirty = False
+            self._last_p, self._last_q, self._last_print = self.p, self.q, self._fingerprint()
         for i, b in enumerate(self.baths):
             if b._noise is not None and self._noise_seen.get(i) != b._noise_version:
                 nz = np.asarray(b._noise, dtype=float)
@@ -295,11 +304,15 @@ class md:
                 self._eng.set_noise(i, nz)
                 self._noise_seen[i] = b._noise_version
 
+    def _fingerprint(self):
+        p, q = np.asarray(self.p, dtype=float), np.asarray(self.q, dtype=float)
+        return (p.shape, float(p.sum()), float(np.vdot(p, p)), float(q.sum()), float(np.vdot(q, q)), int(self.t))
+
     def _pull(self):
         q, p, t = self._eng.get_state()
         shape = (self.nph,) if self.ntraj == 1 else (self.ntraj, self.nph)
         self.q, self.p, self.t = q.reshape(shape), p.reshape(shape), t
-        self._last_p, self._last_q = self.p, self.q
+        self._last_p, self._last_q, self._last_print = self.p, self.q, self._fingerprint()
 
     def _device_noise(self, bath):
         """called by bath.gnoi(): fill the device table for every trajectory, no host round trip"""
@@ -453,18 +466,27 @@ class md:
             if os.path.isfile(fn):
                 ck = self._read_checkpoint(fn)
                 ipie = int(ck["ipie"][0])
-                if ipie + 1 == self.npie:
+                if ipie + 1 == self.npie:                 # md.py:535-543
                     print("finished run")
+                    if self.savep:
+                        self._restore_power(ck)
                     self.t = int(ck["t"][0])
                     continue
-                print("unfinished run: reading resume information")
-                self._restore(ck, with_noise=True)
+                if ipie + 1 > self.npie:                  # md.py:544-547
+                    print("ipie error")
+                    print("ipie=", ipie)
+                    sys.exit()
+                print("unfinished run")                   # md.py:515-534
+                print("reading resume information")
+                self._restore(ck, resume=True)
             else:
                 print("new run")
                 if os.path.isfile(fnm):
                     print("reading history from previous run")
-                    self._restore(self._read_checkpoint(fnm), with_noise=False)
-                elif j != self.nstart and j != 0:
+                    self._restore(self._read_checkpoint(fnm), resume=False)
+                elif j == 0 or j == self.nstart:
+                    print("initialize a new simulation")
+                else:
                     print("no previous nc file exists")
                     sys.exit()
                 for b in self.baths:
@@ -487,16 +509,22 @@ class md:
             if self.cf:                                   # md.py:599-602
                 np.save("deltaforce" + ".run" + str(j), np.array(self.cflist) / self.forcedriver.conv)
                 self.cflist = []
-            if self.savep:
+            if self.savep:                                # md.py:604-653
                 power = np.copy(self.power)
+                if self.atomlist is not None:
+                    poweratomlist = [np.copy(self.poweratomlist[layers]) for layers in range(len(self.atomlist))]
                 self.GetPower()
-                self.power = (power * (j - self.nstart) + self.power) / float(j - self.nstart + 1)
-                with open("power." + str(self.T) + "." + "run" + str(j) + ".dat", "w") as f:
-                    for ni in range(len(self.power)):
-                        if self.power[ni, 0] < 1.5 * max(self.hw):
-                            f.write("%f     %f \n" % (self.power[ni, 0], self.power[ni, 1]))
-                        else:
-                            break
+                nrun = j - self.nstart
+                self.power = (power * nrun + self.power) / float(nrun + 1)
+                if self.atomlist is not None:
+                    for layers in range(len(self.atomlist)):
+                        self.poweratomlist[layers] = (poweratomlist[layers] * nrun + self.poweratomlist[layers]) / float(nrun + 1)
+                self._write_power("power." + str(self.T) + "." + "run" + str(j) + ".dat", self.power)
+                if self.atomlist is not None:
+                    for layers in range(len(self.atomlist)):
+                        self._write_power("poweratomlist." + str(layers) + "." + str(self.T) + "." + "run" + str(j) + ".dat",
+                                          self.poweratomlist[layers])
+                self.dump(self.npie - 1, j)               # md.py:654-655: dump again, to make sure power is all right
             # heat current (md.py:658-664)
             for ii, b in enumerate(self.baths):
                 cur = np.asarray(b.cur).reshape(self.ntraj, self.nmd)
@@ -521,6 +549,20 @@ class md:
         sums = np.array([self._eng.current_sums(i).sum() for i in range(len(self.baths))])
         tot = PAR.allreduce_sum(list(sums) + [float(self.ntraj * self.nmd)]) if self.sharded else np.append(sums, self.ntraj * self.nmd)
         return tot[:-1] / tot[-1] * U.curcof, tot[:-1], int(tot[-1])
+
+    def _write_power(self, name, power):
+        """md.py:619-653: only up to 1.5 max(hw)"""
+        with open(name, "w") as f:
+            for ni in range(len(power)):
+                if self.hw is not None and not power[ni, 0] < 1.5 * max(self.hw):
+                    break
+                f.write("%f     %f \n" % (power[ni, 0], power[ni, 1]))
+
+    def _restore_power(self, ck):
+        if "power" in ck:
+            self.power = ck["power"]
+        if self.atomlist is not None and "poweratomlist" in ck:
+            self.poweratomlist = ck["poweratomlist"]
 
     def _write_frame(self, trajfile):
         q = np.asarray(self.q).reshape(self.ntraj, self.nph)[0]
@@ -573,11 +615,18 @@ class md:
             put('ring' + str(i), self._eng.get_history(i), ('ntraj', 'm' + str(i), 'n' + str(i)))
             if self.saveall and self.ntraj == 1 and b._noise is not None:
                 put('noise' + str(i), np.asarray(b._noise).reshape(self.nmd, b.nc), ('nmd', 'n' + str(i)))
+            seed = getattr(b, "_noise_seed", None)
+            if seed is not None:                          # device-generated table: the Philox key regenerates it (global trajectory streams)
+                v = f.createVariable('noise_seed' + str(i), 'i', ('two',))
+                v[:] = np.array([seed >> 31, seed & 0x7fffffff], dtype=np.int32)
             if self.saveall and i < len(self.fhis):       # md.py:713-714
                 put('fhis' + str(i), self.fhis[i], ('nmd', 'nph'))
         if self.savep:
             f.createDimension('npw', len(self.power))
             put('power', self.power, ('npw', 'two'))
+            if self.atomlist is not None:                 # md.py:724-726
+                f.createDimension('atomlist', len(self.atomlist))
+                put('poweratomlist', self.poweratomlist, ('atomlist', 'npw', 'two'))
             if self.saveall:
                 put('ps', self.ps, ('nmd', 'nph'))
         if self.saveq and self.saveall:
@@ -586,11 +635,21 @@ class md:
 
     @staticmethod
     def _read_checkpoint(fn):
+        """MD<run>.nc written by dump() (NetCDF classic).  The reference's own checkpoints are NetCDF-4 / HDF5 with zlib-compressed
+        variables (md.py:748-756), which neither scipy nor the package's HDF5 walker (contiguous data only) can read."""
         from scipy.io import netcdf_file
+        with open(fn, "rb") as fh:
+            if fh.read(4) == b"\x89HDF":
+                raise RuntimeError(fn + " is a NetCDF-4 (HDF5) file: checkpoints of the reference package cannot be read here "
+                                   "(compressed variables); re-save it in NetCDF classic format, e.g. nccopy -k classic")
         with netcdf_file(fn, 'r', mmap=False) as f:
-            return {k: np.array(v[:], dtype=float) for k, v in f.variables.items()}
+            return {k: np.array(v[:], dtype=(np.int64 if v.typecode() == 'i' else float)) for k, v in f.variables.items()}
 
-    def _restore(self, ck, with_noise):
+    def _restore(self, ck, resume):
+        """state and histories from a checkpoint (md.py:552-562); resume = True: an unfinished run (md.py:515-534) -- also the power
+        spectra, the saved p / q series and the noise of the run.  The reference can only continue with saveall, savep and saveq all
+        set (the noise series is stored with saveall only); a noise table generated on the device is restored from its Philox key
+        instead, whatever the flags."""
         self.p, self.q, self.t = ck["p"], ck["q"], int(ck["t"][0])
         self._ensure_engine()
         self._state_dirty = True
@@ -601,11 +660,30 @@ class md:
                 self._eng.set_history(i, ck[key])
             elif "phis" in ck and self.ntraj == 1 and ck["phis"].shape[0] >= b.ml:      # a checkpoint in the reference's layout
                 self._eng.set_history(i, np.ascontiguousarray(ck["phis"][:b.ml][:, b.cids])[None])
-            if with_noise:
-                if "noise%d" % i not in ck:
-                    print("saveall savep & saveq need to be set true to continue")
-                    sys.exit(0)
+        if not resume:
+            return
+        if self.savep:
+            self._restore_power(ck)
+        self.ResetSavepq()
+        missing = (self.savep and "ps" not in ck) or (self.saveq and "qs" not in ck)
+        for i, b in enumerate(self.baths):
+            if "noise%d" % i in ck:
                 b.noise = ck["noise%d" % i]
+            elif "noise_seed%d" % i in ck:
+                hi, lo = (int(x) for x in ck["noise_seed%d" % i])
+                b._regenerate_device_noise(self._eng, i, self.traj0, (hi << 31) | lo)
+                b._noise_version += 1
+                self._noise_seen[i] = b._noise_version
+                b._noise = self._eng.get_noise(i)[0] if self.ntraj == 1 else None
+            else:
+                missing = True
+        if missing:
+            print("saveall savep & saveq need to be set true to continue")
+            sys.exit(0)
+        if self.savep:
+            self.ps = ck["ps"]
+        if self.saveq:
+            self.qs = ck["qs"]
 
 
 def ApplyConstraint(f, constr=None):

@@ -362,3 +362,159 @@ def test_checkpoint_is_netcdf_with_the_reference_variable_names(tmp_path, monkey
         for _ in range(5):
             m3.vv(0)
         assert relerr(m2.q, m3.q) < 1e-13
+
+
+class _Killed(Exception):
+    pass
+
+
+def _restart_job(ntraj, nstop, npie, flags, inject):
+    """md + two baths for the restart tests; `inject`: host noise series (the reference's own mode) instead of the device generator"""
+    from sclmd_b200.md import md
+    from sclmd_b200.baths import ebath
+    natoms, dt, nmd, T = 12, 0.25 / 0.658, 64, 300.0
+    K = P.spring_chain_dyn(natoms, seed=23)
+    m = md(dt, nmd, T, axyz=axyz(natoms), dyn=K, nstart=0, nstop=nstop, npie=npie, ntraj=ntraj)
+    damp = 100 / 0.658211814201041
+    for i, cats in enumerate((range(3, 9), range(27, 33))):
+        b = ebath(list(cats), T * (1.05 if i == 0 else 0.95), dt, nmd, wmax=1., nw=100, bias=0.0, efric=np.identity(6) / damp)
+        if inject:
+            b.noise = P.injected_noise(1, nmd, 6, seed=70 + i)[0]
+            b.gnoi = lambda: None                       # as the oracle recipe does with the reference (SURVEY appendix B)
+        m.AddBath(b)
+    m.AddConstr([range(0, 3), range(33, 36)])
+    if "saveall" in flags:
+        m.SaveAll()
+    if "savep" in flags:
+        m.CalPowerSpec()
+    if "saveq" in flags:
+        m.CalAveStruct()
+    return m
+
+
+def _kill_after(m, ndumps):
+    """make Run() die right after its `ndumps`-th checkpoint (a job hitting its wall-clock limit)"""
+    real, count = m.dump, [0]
+
+    def dump(ipie, id):
+        real(ipie, id)
+        count[0] += 1
+        if count[0] == ndumps:
+            raise _Killed()
+    m.dump = dump
+
+
+def _kappa():
+    return {f: open(f).read() for f in sorted(os.listdir(".")) if f.startswith("kappa.")}
+
+
+def test_run_resumes_an_unfinished_run_like_the_reference(tmp_path, monkeypatch):
+    """md.Run restart flow (md.py:511-567) with saveall + savep + saveq, one trajectory, injected noise, two runs of two pieces: a job
+    killed after the first piece of run 0 and restarted in a fresh process state ends with the same trajectory, kappa.* files,
+    power spectrum and average structure as the uninterrupted job (noise, p/q series and power come back from MD0.nc; run 1 continues
+    from MD0.nc's state)"""
+    flags = ("saveall", "savep", "saveq")
+    (tmp_path / "a").mkdir()
+    (tmp_path / "b").mkdir()
+    monkeypatch.chdir(tmp_path / "a")
+    a = _restart_job(1, 2, 2, flags, inject=True)
+    np.random.seed(9)
+    a.Run()
+    want = (np.array(a.q), np.array(a.p), int(a.t), _kappa(), np.array(a.power), open("avestructure.300.0.run1.dat").read())
+    monkeypatch.chdir(tmp_path / "b")
+    b = _restart_job(1, 2, 2, flags, inject=True)
+    _kill_after(b, 1)
+    np.random.seed(9)
+    with pytest.raises(_Killed):
+        b.Run()
+    assert os.path.exists("MD0.nc") and not os.path.exists("kappa.300.0.bath0.run0.dat")
+    c = _restart_job(1, 2, 2, flags, inject=True)       # a new process: nothing but the files survives
+    for bb in c.baths:
+        bb.noise = None                                  # the series must come from the checkpoint
+    np.random.seed(1234)
+    c.Run()
+    assert int(c.t) == want[2] == 128
+    assert relerr(c.q, want[0]) < 1e-12 and relerr(c.p, want[1]) < 1e-12
+    assert _kappa() == want[3]
+    assert relerr(c.power, want[4]) < 1e-10
+    assert open("avestructure.300.0.run1.dat").read() == want[5]
+    # a third start finds both runs finished and only reloads time and power (md.py:535-543)
+    d = _restart_job(1, 2, 2, flags, inject=True)
+    d.Run()
+    assert int(d.t) == 128 and relerr(d.power, want[4]) < 1e-10
+    # without saveall the reference cannot continue (md.py:527-532), and neither can an injected-noise job here
+    monkeypatch.chdir(tmp_path)
+    (tmp_path / "e").mkdir()
+    monkeypatch.chdir(tmp_path / "e")
+    e = _restart_job(1, 1, 2, (), inject=True)
+    _kill_after(e, 1)
+    with pytest.raises(_Killed):
+        e.Run()
+    e2 = _restart_job(1, 1, 2, (), inject=True)
+    for bb in e2.baths:
+        bb.noise = None
+    with pytest.raises(SystemExit):
+        e2.Run()
+
+
+def test_run_resumes_an_ensemble_from_its_noise_keys(tmp_path, monkeypatch):
+    """an ensemble with device-generated noise: the checkpoint stores the Philox key of every bath, the restarted job regenerates the
+    same tables (global trajectory streams) and finishes with the same state and kappa.* files -- no saveall needed"""
+    (tmp_path / "a").mkdir()
+    (tmp_path / "b").mkdir()
+    monkeypatch.chdir(tmp_path / "a")
+    a = _restart_job(5, 1, 4, (), inject=False)
+    np.random.seed(11)
+    a.Run()
+    want = (np.array(a.q), np.array(a.p), _kappa(), a.get_noise(0))
+    monkeypatch.chdir(tmp_path / "b")
+    b = _restart_job(5, 1, 4, (), inject=False)
+    _kill_after(b, 2)
+    np.random.seed(11)
+    with pytest.raises(_Killed):
+        b.Run()
+    c = _restart_job(5, 1, 4, (), inject=False)
+    np.random.seed(555)                                  # must not matter: the keys come from MD0.nc
+    c.Run()
+    assert int(c.t) == 64 and np.array_equal(c.get_noise(0), want[3])
+    assert relerr(c.q, want[0]) < 1e-12 and relerr(c.p, want[1]) < 1e-12
+    assert _kappa() == want[2]
+
+
+def test_in_place_state_edits_and_bias_changes_reach_the_device():
+    """md.p[:] = ... / md.q *= 0 between steps, and ebath.setbias after AddBath (the reference reads p, q and bias live,
+    md.py:372, baths.py:243-249): the handle follows"""
+    from sclmd_b200.md import md
+    from sclmd_b200.baths import ebath
+    natoms, dt, nmd, T = 8, 0.5 / 0.658, 16, 300.0
+    K = P.psd_project(P.spring_chain_dyn(natoms, seed=31))
+    nz = P.injected_noise(1, nmd, 6, seed=5)[0]
+
+    def job(bias):
+        m = md(dt, nmd, T, axyz=axyz(natoms), dyn=K)
+        b = ebath(list(range(3, 9)), T, dt, nmd, wmax=1., nw=50, bias=bias, efric=P.psd(6, 1, 0.03), exim=P.antisym(6, 2, 0.01),
+                  exip=P.sym(6, 3, 0.01), zeta1=P.sym(6, 4, 0.004), zeta2=P.antisym(6, 5, 0.004))
+        b.noise = nz
+        m.AddBath(b)
+        m.noranvel()
+        m.initialise()
+        m.ResetHis()
+        return m, b
+    m, b = job(0.2)
+    m.q = 0.01 * np.arange(24, dtype=float)
+    m.vv(0)
+    m.p[:] = 0.0                                         # in place
+    m.q *= 0.5
+    b.setbias(0.9)
+    m.vv(0)
+    ens = O.EnsembleMD(K, dt, nmd, 1, None)              # the oracle, told the same story
+    ob = ens.add_bath(list(range(3, 9)), np.array([b.efric]), nz[None], bias=0.2, exim=b.exim, zeta1=b.zeta1, zeta2=b.zeta2, kind="e")
+    ens.q[0] = 0.01 * np.arange(24, dtype=float)
+    ens.step()
+    ens.p[:] = 0.0
+    ens.q *= 0.5
+    ens.Kq = None
+    ens.baths[ob]["Mq"] = 0.9 * (b.exim - b.zeta1)
+    ens.baths[ob]["Mp"] = -0.9 * b.zeta2
+    ens.step()
+    assert relerr(m.q, ens.q[0]) < 1e-10 and relerr(m.p, ens.p[0]) < 1e-10
