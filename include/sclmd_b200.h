@@ -108,6 +108,9 @@ int sclmd_md_run(sclmd_md *h, int64_t nsteps, float *elapsed_ms);
 /* bath.cur (md.py:397) and md.etot (md.py:383): [ntraj][nmd], index t % nmd */
 int sclmd_md_get_current(sclmd_md *h, int bath, double *cur);
 int sclmd_md_get_etot(sclmd_md *h, double *etot);
+/* restart of an unfinished run (md.py:515-534): the slots recorded by the process that wrote the checkpoint, same layout */
+int sclmd_md_set_current(sclmd_md *h, int bath, const double *cur);
+int sclmd_md_set_etot(sclmd_md *h, const double *etot);
 /* per-bath sum over the nmd slots of cur for each trajectory (np.mean(cur)*nmd, md.py:663):
  * sums[ntraj] -- the payload of the multi-GPU all-reduce */
 int sclmd_md_get_current_sums(sclmd_md *h, int bath, double *sums);

@@ -66,6 +66,8 @@ _PROTOS = {
     "sclmd_md_run": (C.c_int, [C.c_void_p, C.c_int64, c_float_p]),
     "sclmd_md_get_current": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
     "sclmd_md_get_etot": (C.c_int, [C.c_void_p, c_double_p]),
+    "sclmd_md_set_current": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
+    "sclmd_md_set_etot": (C.c_int, [C.c_void_p, c_double_p]),
     "sclmd_md_get_current_sums": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
     "sclmd_md_launch_count": (C.c_int64, [C.c_void_p]),
     "sclmd_dgemm_nt": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, C.c_double, c_double_p]),

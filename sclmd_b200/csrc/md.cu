@@ -2887,6 +2887,28 @@ static int get_slots(sclmd_md *h, const double *dev, double *host) {  // device 
     return SCLMD_OK;
 }
 
+static int set_slots(sclmd_md *h, double *dev, const double *host) {  // host [ntraj][nmd] -> device [nmd][ntraj]
+    std::vector<double> tmp((size_t)h->nmd * h->ntraj);
+    for (int k = 0; k < h->nmd; ++k)
+        for (int tr = 0; tr < h->ntraj; ++tr) tmp[(size_t)k * h->ntraj + tr] = host[(size_t)tr * h->nmd + k];
+    SCLMD_CUDA(cudaMemcpyAsync(dev, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    SCLMD_CUDA(cudaStreamSynchronize(h->st));
+    return SCLMD_OK;
+}
+
+// restart: the observables recorded so far by an earlier process (bath.cur, md.etot; [ntraj][nmd], index t % nmd)
+int sclmd_md_set_current(sclmd_md *h, int bath, const double *cur) {
+    if (int e = check_bath(h, bath, "sclmd_md_set_current")) return e;
+    SCLMD_REQUIRE(cur, "sclmd_md_set_current: NULL buffer");
+    SCLMD_CUDA(cudaSetDevice(h->device));
+    return set_slots(h, h->baths[bath]->cur.p, cur);
+}
+int sclmd_md_set_etot(sclmd_md *h, const double *etot) {
+    SCLMD_REQUIRE(h && etot, "sclmd_md_set_etot: NULL argument");
+    SCLMD_CUDA(cudaSetDevice(h->device));
+    return set_slots(h, h->etot.p, etot);
+}
+
 int sclmd_md_get_current(sclmd_md *h, int bath, double *cur) {
     if (int e = check_bath(h, bath, "sclmd_md_get_current")) return e;
     SCLMD_REQUIRE(cur, "sclmd_md_get_current: NULL buffer");

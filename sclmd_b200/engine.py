@@ -211,6 +211,14 @@ class MDEngine:
         check(_lib.lib().sclmd_md_get_current(self._h, bath, dptr(out)))
         return out
 
+    def set_current(self, bath, cur):
+        cur = as_f64(np.asarray(cur, dtype=float).reshape(self.ntraj, self.nmd))
+        check(_lib.lib().sclmd_md_set_current(self._h, bath, dptr(cur)))
+
+    def set_etot(self, etot):
+        etot = as_f64(np.asarray(etot, dtype=float).reshape(self.ntraj, self.nmd))
+        check(_lib.lib().sclmd_md_set_etot(self._h, dptr(etot)))
+
     def etot(self):
         out = np.empty((self.ntraj, self.nmd))
         check(_lib.lib().sclmd_md_get_etot(self._h, dptr(out)))

@@ -613,6 +613,7 @@ class md:
             f.createDimension('n' + str(i), b.nc)
             f.createDimension('m' + str(i), b.ml)
             put('ring' + str(i), self._eng.get_history(i), ('ntraj', 'm' + str(i), 'n' + str(i)))
+            put('cur' + str(i), self._eng.current(i), ('ntraj', 'nmd'))       # so that a resumed run averages over ALL its steps
             if self.saveall and self.ntraj == 1 and b._noise is not None:
                 put('noise' + str(i), np.asarray(b._noise).reshape(self.nmd, b.nc), ('nmd', 'n' + str(i)))
             seed = getattr(b, "_noise_seed", None)
@@ -662,6 +663,13 @@ class md:
                 self._eng.set_history(i, np.ascontiguousarray(ck["phis"][:b.ml][:, b.cids])[None])
         if not resume:
             return
+        # heat currents and energies recorded before the interruption (the reference keeps them in memory only, so its resumed runs
+        # average the later pieces alone; here the kappa of a resumed run equals that of the uninterrupted one)
+        for i, b in enumerate(self.baths):
+            if "cur%d" % i in ck:
+                self._eng.set_current(i, ck["cur%d" % i])
+        if "energy" in ck and ck["energy"].size == self.ntraj * self.nmd:
+            self._eng.set_etot(ck["energy"])
         if self.savep:
             self._restore_power(ck)
         self.ResetSavepq()

@@ -350,7 +350,7 @@ def test_checkpoint_is_netcdf_with_the_reference_variable_names(tmp_path, monkey
         m2 = make(1)
         m2.initialise()
         m2.ResetHis()
-        m2._restore(ck, with_noise=False)
+        m2._restore(ck, resume=False)
         assert m2.t == m.t and relerr(m2.q, m.q) == 0 and relerr(m2.p, m.p) == 0
         assert relerr(m2.phis, m.phis) == 0
         for _ in range(5):
@@ -358,7 +358,7 @@ def test_checkpoint_is_netcdf_with_the_reference_variable_names(tmp_path, monkey
         m3 = make(1)
         m3.initialise()
         m3.ResetHis()
-        m3._restore(dict(v), with_noise=False)
+        m3._restore(dict(v), resume=False)
         for _ in range(5):
             m3.vv(0)
         assert relerr(m2.q, m3.q) < 1e-13
