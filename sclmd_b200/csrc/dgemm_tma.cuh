@@ -11,7 +11,7 @@
 //   2s+1 (A and B agree, so the contraction is merely reordered).  Fragment row j reads tile row pi(j) = (j >> 1) | ((j & 1) << 2)
 //   of its 8-row group: the eight lanes of a quarter-warp then touch rows with swizzle keys r and r ^ 4, i.e. all eight 16-byte
 //   chunks of a 128-byte line -- no bank conflict.  The same permutation maps accumulator rows / columns back on the way out.
-// * Stream-K: the grid is one CTA per SM; the iteration space (tiles x K-slabs) is cut into equal contiguous ranges, so there is
+// * Stream-K: the grid is one CTA per SM (cooperative launch: all CTAs resident); the iteration space (tiles x K-slabs) is cut into equal contiguous ranges, so there is
 //   no wave quantisation and no split-K partial C in HBM.  A CTA whose range starts inside a tile stores that partial
 //   accumulator tile to a small workspace right away and raises a flag; the CTA that holds the head of the tile adds the
 //   partials in CTA order (deterministic) and writes C once.
@@ -336,7 +336,16 @@ inline int launch_dgemm_tma_bn(const TmaGemm &g, TmaWorkspace &w, int nsm, cudaS
     p.ws = w.ws.p; p.flags = w.flags.p; p.epoch = ++w.epoch;
     const long long total = (long long)p.ntiles * p.KI;
     const int grid = (int)std::max<long long>(1, std::min<long long>(nsm, total));
-    kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(mA, mB, p);
+    // CTAs of this grid wait on one another (stream-K fix-up): a cooperative launch guarantees that they are all resident.  (Inside a
+    // stream capture the plain launch is used; one CTA per SM is resident then as well.)
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    if (cap == cudaStreamCaptureStatusNone) {
+        void *args[] = {(void *)&mA, (void *)&mB, (void *)&p};
+        cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(Cfg::THREADS), args, Cfg::SMEM, st);
+    } else {
+        kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(mA, mB, p);
+    }
     const cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) {
         set_error("dgemm_tma_kernel launch failed: %s", cudaGetErrorString(ce));
