@@ -284,7 +284,7 @@ def negf_also(rank, world, local, barrier, fp64_peak_tflops=None):
     sweep_s = t1 - t0
     L = _lib.lib()
     dev_ms = C.c_double(0.0)
-    _lib.check(L.sclmd_bpt_get_profile(None, None, None, C.byref(dev_ms)))
+    _lib.check(L.sclmd_bpt_get_profile(b._handle(), None, None, None, C.byref(dev_ms)))
     device_s = dev_ms.value * 1e-3
     if world > 1:
         dt, sweep_s, device_s = max_over_ranks(dt), max_over_ranks(sweep_s), max_over_ranks(device_s)
@@ -298,13 +298,13 @@ def negf_also(rank, world, local, barrier, fp64_peak_tflops=None):
                      "blocks sharded + all-gather; host buffers in and out" % per}
     if rank == 0:
         nprof = 2960
-        _lib.check(L.sclmd_bpt_set_profiling(1))
+        _lib.check(L.sclmd_bpt_set_profiling(b._handle(), 1))
         b.tm_sweep(om[lo:lo + nprof])
         ms = (C.c_double * 7)()
         n = (C.c_int64 * 7)()
         gf = C.c_double(0.0)
-        _lib.check(L.sclmd_bpt_get_profile(ms, n, C.byref(gf), C.byref(dev_ms)))
-        _lib.check(L.sclmd_bpt_set_profiling(0))
+        _lib.check(L.sclmd_bpt_get_profile(b._handle(), ms, n, C.byref(gf), C.byref(dev_ms)))
+        _lib.check(L.sclmd_bpt_set_profiling(b._handle(), 0))
         names = ["k_build", "k_panel", "k_gemm (rank-16, panel columns)", "k_block_trsm", "k_gemm (rank-64 trailing update)", "back substitution (k_block_trsm_upper + k_gemm)", "k_observe"]
         tot = sum(ms)
         peak = fp64_peak_tflops or 37.1
@@ -504,7 +504,7 @@ def main():
     nph_ = 3 * w["natoms"]
     alg_ring = 8.0 * w["nc"] * (w["ml"] - 1) * ntraj          # 8*nc*(ml-1) B per trajectory-step per bath
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_tail_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r02_tail_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp))
     cands = []
@@ -619,7 +619,7 @@ def main():
         roof["noise_samples_per_s"] = nz.get("samples_per_s_device")
         roof["noise_frac_of_hbm_roofline"] = nz.get("frac_of_hbm_roofline_16B_per_sample")
         roof["whole_step_frac_of_fp64_peak"] = (roof.get("whole_step") or {}).get("frac_of_fp64_peak")
-        roof["traffic_source"] = "stored ncu --set full capture (profiles/r01_tail_traffic.json), not measured in this run"
+        roof["traffic_source"] = "stored ncu --set full capture (profiles/r02_tail_traffic.json <- profiles/r02n_far_ncu_raw.csv), not measured in this run"
 
     # ---------------- BASELINE configs[1] shape (603-dof junction of the example, ml = 1 baths, fixed ends, 1024 trajectories)
     if world == 1 and not args.no_also and args.workload != "c2":

@@ -237,48 +237,44 @@ int sclmd_fft(int device, int n, int batch, const double *re, const double *im, 
 int sclmd_cos_transform(int device, int nt, int nw, int m, const double *tl, const double *wl,
                         const double *giT, double eta, double alpha, double *out);
 
-/* The frequency sweeps keep their device workspace (batch buffers, streams) between calls; this frees it. */
+/* Frees the device scratch the noise generator caches between calls (the frequency sweeps keep theirs in their handles). */
 int sclmd_release_workspace(void);
-/* Per-kernel-class CUDA-event timing of the bpt sweeps (build, panel, rank-16 update, block trsm, rank-64 update, back
- * substitution, observable): ms[7], n[7], flops executed by the rank-64 update, device time of the last sweep. */
-int sclmd_bpt_set_profiling(int on);
-int sclmd_bpt_get_profile(double *ms, int64_t *n, double *gemm_flops, double *last_device_ms);
 
 /* ---------------------------------------------------------------- NEGF ---
- * bpt.tm over a frequency list (negf.py:104-119, 206-208, 240-242) for
- * diagonal lead self-energies Sigma = -i w/damp on the bath dofs
- * (negf.py:153-157):  T(w) = Re Tr[G Gamma_L G^dagger Gamma_R].
- *   K[n*n] reduced dynamical matrix (fixed dofs removed), idxL/idxR reduced indices */
-int sclmd_bpt_tm(int device, int n, const double *K, const int32_t *idxL, int nL,
-                 const int32_t *idxR, int nR, double damp, const double *omegas, int nw,
-                 double *tm_out);
-/* bpt.ps without bias (negf.py:232): -2 w^2 nB Tr Im G[sel,sel]; nb[nw] = bosedist(w,T) */
-int sclmd_bpt_ps(int device, int n, const double *K, const int32_t *idxL, int nL,
-                 const int32_t *idxR, int nR, double damp, const double *omegas, const double *nb,
-                 int nw, const int32_t *sel, int nsel, double *ps_out);
-
-/* bpt with a biased electron bath (bpt.setbias, negf.py:27-37): Sigma_b^r = -i w bdamp - bias chiminus on the contiguous
- * dof block [b0, b0+nb) (negf.py:162-172; reduced numbering), bias in angular units (eV/hbar, as bpt stores it).
- * bdamp, chiplus, chiminus: [nb*nb]. */
-int sclmd_bpt_tm_bias(int device, int n, const double *K, const int32_t *idxL, int nL,
-                      const int32_t *idxR, int nR, double damp, int b0, int nb, const double *bdamp,
-                      const double *chiplus, const double *chiminus, double bias, const double *omegas,
-                      int nw, double *tm_out);
+ * The reference's class bpt (negf.py:8-277) as a handle: bpt.__init__ / getdynmat (negf.py:8-25, 39-102) leave the reduced
+ * dynamical matrix (fixed dofs removed), the dofs of the two leads and the damping; sclmd_bpt_create uploads K once and the
+ * handle owns everything its sweeps need on the device (batch workspace, streams, profiling state) until sclmd_bpt_destroy.
+ * No state of the sweeps lives outside the handle; one sweep at a time per handle, handles are independent.
+ *   K[n*n] row-major, idxL/idxR reduced indices (dofatomofbath - len(dofatomfixed[0]), negf.py:195-204), damp in ps, n <= 4096.
+ * Diagonal lead self-energies Sigma = -i w/damp on the bath dofs (negf.py:153-157). */
+typedef struct sclmd_bpt sclmd_bpt;
+int sclmd_bpt_create(int device, int n, const double *K, const int32_t *idxL, int nL, const int32_t *idxR, int nR,
+                     double damp, sclmd_bpt **out);
+int sclmd_bpt_destroy(sclmd_bpt *h);
+/* bpt.setbias (negf.py:27-37): a biased electron bath, Sigma_b^r = -i w bdamp - bias chiminus on the contiguous dof block
+ * [b0, b0+nb) (negf.py:162-172; reduced numbering), bias in angular units (eV/hbar, as bpt stores it);
+ * bdamp, chiplus, chiminus: [nb*nb], copied.  nb == 0 removes the block. */
+int sclmd_bpt_set_bias(sclmd_bpt *h, int b0, int nb, const double *bdamp, const double *chiplus,
+                       const double *chiminus, double bias);
+/* bpt.tm over a frequency list (negf.py:104-119, 206-208, 240-242): T(w) = Re Tr[G Gamma_L G^dagger Gamma_R]; G carries the
+ * retarded self-energy of the bias block when one is set.  Singular M(w): SCLMD_ERR_STATE (numpy.linalg.LinAlgError there). */
+int sclmd_bpt_tm(sclmd_bpt *h, const double *omegas, int nw, double *tm_out);
+/* bpt.ps without bias (negf.py:232): -2 w^2 nB Tr Im G[sel,sel]; nb[nw] = bosedist(w,T).  Error if a bias block is set. */
+int sclmd_bpt_ps(sclmd_bpt *h, const double *omegas, const double *nb, int nw, const int32_t *sel, int nsel,
+                 double *ps_out);
 /* bpt.retargf / bpt.advangf (negf.py:206-212): the full Green function, green_out[nw][n][n] complex (interleaved re, im);
- * nb == 0: no bias block; advanced != 0: advanced self-energies (the +i eps of z is kept, as negf.py:212 does). */
-int sclmd_bpt_green(int device, int n, const double *K, const int32_t *idxL, int nL,
-                    const int32_t *idxR, int nR, double damp, int b0, int nb, const double *bdamp,
-                    const double *chiplus, const double *chiminus, double bias, const double *omegas, int nw,
-                    int advanced, double *green_out);
-
+ * advanced != 0: advanced self-energies (the +i eps of z is kept, as negf.py:212 does). */
+int sclmd_bpt_green(sclmd_bpt *h, const double *omegas, int nw, int advanced, double *green_out);
 /* bpt.ps with bias (negf.py:234-236): w^2 Re Tr[(G^r Sigma^K G^a)[sel,sel]] with Sigma^K = totalkselfenergy
  * (negf.py:177-193) = kd[w] on the lead dofs + kr1[w] bdamp + kr2[w] chiplus + i ki[w] chiminus on the bias block;
  * the per-frequency weights carry the Bose factors (bosedist edge cases stay on the host side). */
-int sclmd_bpt_ps_bias(int device, int n, const double *K, const int32_t *idxL, int nL,
-                      const int32_t *idxR, int nR, double damp, int b0, int nb, const double *bdamp,
-                      const double *chiplus, const double *chiminus, double bias, const double *omegas,
-                      const double *kd, const double *kr1, const double *kr2, const double *ki, int nw,
-                      const int32_t *sel, int nsel, double *ps_out);
+int sclmd_bpt_ps_bias(sclmd_bpt *h, const double *omegas, const double *kd, const double *kr1, const double *kr2,
+                      const double *ki, int nw, const int32_t *sel, int nsel, double *ps_out);
+/* Per-kernel-class CUDA-event timing of this handle's sweeps (build, panel, rank-16 update, block trsm, rank-64 update, back
+ * substitution, observable): ms[7], n[7], flops executed by the rank-64 update, device time of the last sweep.
+ * Switching it on resets the totals; while on, sweeps run on one stream. */
+int sclmd_bpt_set_profiling(sclmd_bpt *h, int on);
+int sclmd_bpt_get_profile(sclmd_bpt *h, double *ms, int64_t *n, double *gemm_flops, double *last_device_ms);
 
 /* sig.selfenergy / sig.getse (selfenergy.py:105-140, 153-166): Sancho-Rubio decimation.
  *   K00,K11,K01,K10: [m*m]; direction 'L' or 'R'; se_out: [nw][m][m] interleaved complex;

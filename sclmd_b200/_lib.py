@@ -88,13 +88,15 @@ _PROTOS = {
     "sclmd_cos_transform": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, C.c_double, C.c_double, c_double_p]),
     "sclmd_gamt": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p]),
     "sclmd_release_workspace": (C.c_int, []),
-    "sclmd_bpt_set_profiling": (C.c_int, [C.c_int]),
-    "sclmd_bpt_get_profile": (C.c_int, [c_double_p, c_int64_p, c_double_p, c_double_p]),
-    "sclmd_bpt_tm": (C.c_int, [C.c_int, C.c_int, c_double_p, c_int32_p, C.c_int, c_int32_p, C.c_int, C.c_double, c_double_p, C.c_int, c_double_p]),
-    "sclmd_bpt_ps": (C.c_int, [C.c_int, C.c_int, c_double_p, c_int32_p, C.c_int, c_int32_p, C.c_int, C.c_double, c_double_p, c_double_p, C.c_int, c_int32_p, C.c_int, c_double_p]),
-    "sclmd_bpt_tm_bias": (C.c_int, [C.c_int, C.c_int, c_double_p, c_int32_p, C.c_int, c_int32_p, C.c_int, C.c_double, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, C.c_double, c_double_p, C.c_int, c_double_p]),
-    "sclmd_bpt_green": (C.c_int, [C.c_int, C.c_int, c_double_p, c_int32_p, C.c_int, c_int32_p, C.c_int, C.c_double, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, C.c_double, c_double_p, C.c_int, C.c_int, c_double_p]),
-    "sclmd_bpt_ps_bias": (C.c_int, [C.c_int, C.c_int, c_double_p, c_int32_p, C.c_int, c_int32_p, C.c_int, C.c_double, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, C.c_double, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, C.c_int, c_int32_p, C.c_int, c_double_p]),
+    "sclmd_bpt_create": (C.c_int, [C.c_int, C.c_int, c_double_p, c_int32_p, C.c_int, c_int32_p, C.c_int, C.c_double, C.POINTER(C.c_void_p)]),
+    "sclmd_bpt_destroy": (C.c_int, [C.c_void_p]),
+    "sclmd_bpt_set_bias": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, C.c_double]),
+    "sclmd_bpt_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "sclmd_bpt_get_profile": (C.c_int, [C.c_void_p, c_double_p, c_int64_p, c_double_p, c_double_p]),
+    "sclmd_bpt_tm": (C.c_int, [C.c_void_p, c_double_p, C.c_int, c_double_p]),
+    "sclmd_bpt_ps": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int, c_int32_p, C.c_int, c_double_p]),
+    "sclmd_bpt_green": (C.c_int, [C.c_void_p, c_double_p, C.c_int, C.c_int, c_double_p]),
+    "sclmd_bpt_ps_bias": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, C.c_int, c_int32_p, C.c_int, c_double_p]),
     "sclmd_sig_selfenergy": (C.c_int, [C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p, C.c_double, C.c_char, c_double_p, C.c_int, c_double_p, c_int32_p]),
     "sclmd_sig_sgf": (C.c_int, [C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p, C.c_double, C.c_char, c_double_p, C.c_int, c_double_p, c_int32_p]),
     "sclmd_sig_green": (C.c_int, [C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p, C.c_double, c_double_p, C.c_int, c_double_p]),

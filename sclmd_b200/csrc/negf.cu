@@ -761,15 +761,9 @@ __global__ void __launch_bounds__(256) k_observe(Geo g, Problem p, const double 
     }
 }
 
-struct BiasBlock {
-    int b0 = 0, nb = 0;
-    const double *bdamp = nullptr, *chiplus = nullptr, *chiminus = nullptr;
-    double bias = 0.0;
-    const double *kd = nullptr, *kr1 = nullptr, *kr2 = nullptr, *ki = nullptr;
-};
 
-// Per-device workspace kept between calls (cudaMalloc of several GB costs more than a whole sweep): grow-only raw buffers and
-// the streams of the batch slots; released by sclmd_release_workspace().  One sweep at a time per process (g_ws_mutex).
+// Workspace of a sclmd_bpt handle, kept between its sweeps (cudaMalloc of several GB costs more than a whole sweep): grow-only raw
+// buffers and the streams of the batch slots; freed by sclmd_bpt_destroy.  One sweep at a time per handle (its mutex).
 struct RawBuf {
     void *p = nullptr;
     size_t bytes = 0;
@@ -800,7 +794,7 @@ struct Workspace {
         arena.release();
     }
 };
-// Optional per-kernel-class timing (sclmd_bpt_set_profiling): one stream, a CUDA event pair around every launch.
+// Optional per-kernel-class timing of a handle (sclmd_bpt_set_profiling): one stream, a CUDA event pair around every launch.
 // classes: 0 build, 1 panel, 2 panel-column update (k_gemm, rank 16), 3 block trsm, 4 trailing update (k_gemm, rank 64),
 //          5 back substitution, 6 observable/save
 constexpr int NPROF = 7;
@@ -830,21 +824,36 @@ struct Prof {
         ev.clear(); kind.clear();
     }
 };
-Prof g_prof;
-std::mutex g_ws_mutex;
-std::vector<std::unique_ptr<Workspace>> g_ws;
-
-Workspace &workspace(int device) {
-    for (auto &w : g_ws) if (w->device == device) return *w;
-    g_ws.emplace_back(new Workspace());
-    g_ws.back()->device = device;
-    return *g_ws.back();
+__global__ void k_permute_k(const double *__restrict__ K, const int *__restrict__ order, int n, double *__restrict__ Kp) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)n * n) return;
+    const int i = (int)(e / n), j = (int)(e % n);
+    Kp[e] = K[(size_t)order[i] * n + order[j]];
 }
 
+}  // namespace
+
+// The handle of the frequency sweeps: the junction (K on the device, lead dofs, damping, optional bias block), the batch workspace,
+// the streams and the profiling state.  Nothing of the sweeps lives outside it.
+struct sclmd_bpt {
+    int device = 0, n = 0;
+    double damp = 0.0;
+    DevBuf<double> dK;                  // K in the caller's numbering, uploaded once
+    std::vector<int> idxL, idxR;
+    std::vector<double> mask;           // number of leads a dof belongs to
+    int b0 = 0, nb = 0;
+    std::vector<double> bdamp, chiplus, chiminus;
+    double bias = 0.0;
+    Workspace ws;
+    Prof prof;
+    std::mutex mu;
+};
+
+namespace {
+
 // enqueue the factorisation + solve of one batch (nbat frequencies starting at w0) on slot s
-cudaError_t enqueue_lu(const Geo &g, const Problem &p, StreamSlot &s, int *status, int w0, int nbat, int row_stop, double sgn, int tblk,
+cudaError_t enqueue_lu(Prof &pf, const Geo &g, const Problem &p, StreamSlot &s, int *status, int w0, int nbat, int row_stop, double sgn, int tblk,
                        unsigned long long *tiles) {
-    Prof &pf = g_prof;
     cudaStream_t st = s.st;
     double *W = static_cast<double *>(s.W.p);
     int *act = static_cast<int *>(s.act.p), *flags = static_cast<int *>(s.flags.p);
@@ -900,31 +909,25 @@ cudaError_t enqueue_lu(const Geo &g, const Problem &p, StreamSlot &s, int *statu
     return cudaGetLastError();
 }
 
-int run_lu(int device, int n, const double *K, const int32_t *idxL, int nL, const int32_t *idxR, int nR, double damp,
-           const double *omegas, int nw, int mode, const double *weight, const int32_t *sel, int nsel, double *out,
-           const BiasBlock *bb = nullptr, int advanced = 0) {
+struct Keldysh {
+    const double *kd = nullptr, *kr1 = nullptr, *kr2 = nullptr, *ki = nullptr;
+};
+
+int run_lu(sclmd_bpt &h, const double *omegas, int nw, int mode, const double *weight, const int32_t *sel, int nsel, double *out,
+           const Keldysh *kw = nullptr, int advanced = 0) {
     // mode 0 transmission, 1 power spectrum, 2 biased power spectrum, 3 the full Green function (out = [nw][n][n] complex, interleaved)
-    SCLMD_REQUIRE(n > 0 && K && idxL && idxR && nL > 0 && nR > 0 && omegas && nw > 0 && out && damp != 0.0, "bpt: bad arguments");
-    SCLMD_REQUIRE(n <= 4096, "bpt: n=%d exceeds the register-resident panel (n <= 4096)", n);
+    SCLMD_REQUIRE(omegas && nw > 0 && out, "bpt: bad arguments");
+    std::lock_guard<std::mutex> lock(h.mu);
+    const int n = h.n, device = h.device, nb = h.nb, b0 = h.b0;
+    const double damp = h.damp;
     if (int e = select_device(device)) return e;
-    std::vector<double> mask(n, 0.0);
-    for (int i = 0; i < nL; ++i) {
-        SCLMD_REQUIRE(idxL[i] >= 0 && idxL[i] < n, "bpt: left bath dof %d out of range", idxL[i]);
-        mask[idxL[i]] += 1.0;
-    }
-    for (int i = 0; i < nR; ++i) {
-        SCLMD_REQUIRE(idxR[i] >= 0 && idxR[i] < n, "bpt: right bath dof %d out of range", idxR[i]);
-        mask[idxR[i]] += 1.0;
-    }
-    if (bb && bb->nb > 0)
-        SCLMD_REQUIRE(bb->b0 >= 0 && bb->b0 + bb->nb <= n && bb->bdamp && bb->chiminus && bb->chiplus, "bpt: bad bias block");
-    SCLMD_REQUIRE(mode != 2 || (bb && bb->nb > 0 && bb->kd && bb->kr1 && bb->kr2 && bb->ki), "bpt.ps (biased): missing Keldysh weights");
-    const int nb = bb ? bb->nb : 0, b0 = bb ? bb->b0 : 0;
+    SCLMD_REQUIRE(mode != 2 || (nb > 0 && kw && kw->kd && kw->kr1 && kw->kr2 && kw->ki), "bpt.ps (biased): no bias block set or missing Keldysh weights");
+    const std::vector<double> &mask = h.mask;
     // right-hand sides and the rows of the solution the observable reads (original numbering)
     std::vector<int> rhs_o, rows_o;
     if (mode == 0) {
-        rhs_o.assign(idxL, idxL + nL);
-        rows_o.assign(idxR, idxR + nR);
+        rhs_o = h.idxL;
+        rows_o = h.idxR;
     } else if (mode == 3) {
         rhs_o.resize(n);
         std::iota(rhs_o.begin(), rhs_o.end(), 0);
@@ -947,12 +950,9 @@ int run_lu(int device, int n, const double *K, const int32_t *idxL, int nL, cons
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
     for (int i = 0; i < n; ++i) pos[order[i]] = i;
-    std::vector<double> Kp((size_t)n * n), maskp(n);
+    std::vector<double> maskp(n);
     std::vector<int> bmap(n, -1), bpos(std::max(nb, 1), 0);
     for (int i = 0; i < n; ++i) {
-        const double *src = K + (size_t)order[i] * n;
-        double *dst = Kp.data() + (size_t)i * n;
-        for (int j = 0; j < n; ++j) dst[j] = src[order[j]];
         maskp[i] = mask[order[i]];
         if (order[i] >= b0 && order[i] < b0 + nb) { bmap[i] = order[i] - b0; bpos[order[i] - b0] = i; }
     }
@@ -971,15 +971,15 @@ int run_lu(int device, int n, const double *K, const int32_t *idxL, int nL, cons
     int bmax = 4 * sms;
     while (bmax > 8 && (size_t)bmax * per_w * 3 > ((size_t)24 << 30)) bmax /= 2;
     const int nbatch = cdiv(nw, bmax), bsz = cdiv(nw, nbatch);
-    const int nslots = g_prof.on ? 1 : std::min(3, nbatch);
+    Prof &prof = h.prof;
+    const int nslots = prof.on ? 1 : std::min(3, nbatch);
 
-    std::lock_guard<std::mutex> lock(g_ws_mutex);
-    Workspace &ws = workspace(device);
+    Workspace &ws = h.ws;
     StreamSlot *slots = ws.slot;
     // the per-call device arrays come out of one cached arena (no cudaMalloc / cudaFree per sweep)
     const size_t nb2 = (size_t)nb * nb;
     const size_t arena_bytes = sizeof(double) * ((size_t)n * n + n + 7 * (size_t)nw + 3 * nb2) +
-                               sizeof(int) * (rhs.size() + rows.size() + (size_t)nw + n + bpos.size()) + 256 * 24;
+                               sizeof(int) * (rhs.size() + rows.size() + (size_t)nw + 2 * (size_t)n + bpos.size()) + 256 * 24;
     SCLMD_CUDA(ws.arena.reserve(((arena_bytes >> 24) + 1) << 24));      // 16 MB granules: sweeps of similar length reuse the arena
     char *cursor = static_cast<char *>(ws.arena.p);
     auto take = [&](size_t bytes) { char *r = cursor; cursor += (bytes + 255) / 256 * 256; return static_cast<void *>(r); };
@@ -987,7 +987,11 @@ int run_lu(int device, int n, const double *K, const int32_t *idxL, int nL, cons
     auto take_i = [&](size_t cnt) { return static_cast<int *>(take(cnt * sizeof(int))); };
     double *dK = take_d((size_t)n * n), *dmask = take_d(n), *dom = take_d(nw), *dwt = take_d(nw), *dout = take_d(nw);
     int *drhs = take_i(rhs.size()), *drows = take_i(rows.size()), *dstat = take_i(nw), *dbmap = take_i(n), *dbpos = take_i(bpos.size());
-    SCLMD_CUDA(cudaMemcpy(dK, Kp.data(), (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice));
+    int *dorder = take_i(n);
+    // K stays on the device with the handle; only its re-ordering for this observable is rebuilt (a device gather)
+    SCLMD_CUDA(cudaMemcpy(dorder, order.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+    k_permute_k<<<(unsigned)(((size_t)n * n + 255) / 256), 256>>>(h.dK.p, dorder, n, dK);
+    SCLMD_CUDA(cudaGetLastError());
     SCLMD_CUDA(cudaMemcpy(dmask, maskp.data(), n * sizeof(double), cudaMemcpyHostToDevice));
     SCLMD_CUDA(cudaMemcpy(dom, omegas, nw * sizeof(double), cudaMemcpyHostToDevice));
     if (weight) SCLMD_CUDA(cudaMemcpy(dwt, weight, nw * sizeof(double), cudaMemcpyHostToDevice));
@@ -1001,13 +1005,13 @@ int run_lu(int device, int n, const double *K, const int32_t *idxL, int nL, cons
     p.nb = nb; p.damp = damp; p.eps = 1e-9; p.omegas = dom; p.weight = dwt;
     if (nb > 0) {
         double *dbd = take_d(nb2), *dcp = take_d(nb2), *dcm = take_d(nb2);
-        SCLMD_CUDA(cudaMemcpy(dbd, bb->bdamp, nb2 * sizeof(double), cudaMemcpyHostToDevice));
-        SCLMD_CUDA(cudaMemcpy(dcp, bb->chiplus, nb2 * sizeof(double), cudaMemcpyHostToDevice));
-        SCLMD_CUDA(cudaMemcpy(dcm, bb->chiminus, nb2 * sizeof(double), cudaMemcpyHostToDevice));
-        p.bdamp = dbd; p.chiplus = dcp; p.chiminus = dcm; p.bias = bb->bias;
+        SCLMD_CUDA(cudaMemcpy(dbd, h.bdamp.data(), nb2 * sizeof(double), cudaMemcpyHostToDevice));
+        SCLMD_CUDA(cudaMemcpy(dcp, h.chiplus.data(), nb2 * sizeof(double), cudaMemcpyHostToDevice));
+        SCLMD_CUDA(cudaMemcpy(dcm, h.chiminus.data(), nb2 * sizeof(double), cudaMemcpyHostToDevice));
+        p.bdamp = dbd; p.chiplus = dcp; p.chiminus = dcm; p.bias = h.bias;
         if (mode == 2) {
             double *dkw = take_d((size_t)4 * nw);
-            const double *src[4] = {bb->kd, bb->kr1, bb->kr2, bb->ki};
+            const double *src[4] = {kw->kd, kw->kr1, kw->kr2, kw->ki};
             for (int q = 0; q < 4; ++q) SCLMD_CUDA(cudaMemcpy(dkw + (size_t)q * nw, src[q], nw * sizeof(double), cudaMemcpyHostToDevice));
             p.kd = dkw; p.kr1 = dkw + nw; p.kr2 = dkw + 2 * (size_t)nw; p.ki = dkw + 3 * (size_t)nw;
         }
@@ -1024,7 +1028,7 @@ int run_lu(int device, int n, const double *K, const int32_t *idxL, int nL, cons
     SCLMD_CUDA(cudaFuncSetAttribute(k_block_trsm_upper, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSM_SMEM));
 
     DevBuf<unsigned long long> dtiles;
-    if (g_prof.on) SCLMD_CUDA(dtiles.alloc(1));
+    if (prof.on) SCLMD_CUDA(dtiles.alloc(1));
     DevBuf<double> dgreen;
     if (mode == 3) {
         SCLMD_REQUIRE((size_t)nw * n * n <= ((size_t)1 << 28), "bpt: %d full Green functions of order %d do not fit the output buffer; sweep in pieces", nw, n);
@@ -1041,21 +1045,21 @@ int run_lu(int device, int n, const double *K, const int32_t *idxL, int nL, cons
         const int w0 = ib * bsz, nbat = std::min(bsz, nw - w0);
         if (nbat <= 0) break;
         if (mode == 2) {
-            SCLMD_CUDA(enqueue_lu(g, p, s, dstat, w0, nbat, row_stop, -1.0, 1, dtiles.p));
+            SCLMD_CUDA(enqueue_lu(prof, g, p, s, dstat, w0, nbat, row_stop, -1.0, 1, dtiles.p));
             k_save<<<dim3(cdiv(g.np * g.nrhs, 256), nbat), 256, 0, s.st>>>(g, static_cast<const double *>(s.W.p), static_cast<const int *>(s.act.p), static_cast<double *>(s.Xs.p));
-            SCLMD_CUDA(enqueue_lu(g, p, s, dstat, w0, nbat, row_stop, 1.0, 1, dtiles.p));
+            SCLMD_CUDA(enqueue_lu(prof, g, p, s, dstat, w0, nbat, row_stop, 1.0, 1, dtiles.p));
         } else if (mode == 3) {
-            SCLMD_CUDA(enqueue_lu(g, p, s, dstat, w0, nbat, row_stop, advanced ? -1.0 : 1.0, advanced ? 1 : 0, dtiles.p));
+            SCLMD_CUDA(enqueue_lu(prof, g, p, s, dstat, w0, nbat, row_stop, advanced ? -1.0 : 1.0, advanced ? 1 : 0, dtiles.p));
             k_extract<<<dim3(cdiv(n * n, 256), nbat), 256, 0, s.st>>>(g, static_cast<const double *>(s.W.p), static_cast<const int *>(s.act.p),
                                                                       dgreen.p + (size_t)w0 * n * n * 2, dstat, w0);
             SCLMD_CUDA(cudaGetLastError());
             continue;
         } else {
-            SCLMD_CUDA(enqueue_lu(g, p, s, dstat, w0, nbat, row_stop, 1.0, 0, dtiles.p));
+            SCLMD_CUDA(enqueue_lu(prof, g, p, s, dstat, w0, nbat, row_stop, 1.0, 0, dtiles.p));
         }
-        g_prof.begin(6, s.st);
+        prof.begin(6, s.st);
         k_observe<<<nbat, 256, 0, s.st>>>(g, p, static_cast<const double *>(s.W.p), static_cast<const int *>(s.act.p), static_cast<const double *>(s.Xs.p), dout, dstat, w0, mode);
-        g_prof.end(s.st);
+        prof.end(s.st);
         SCLMD_CUDA(cudaGetLastError());
     }
     // the end marker waits for every slot
@@ -1072,13 +1076,13 @@ int run_lu(int device, int n, const double *K, const int32_t *idxL, int nL, cons
     SCLMD_CUDA(cudaEventElapsedTime(&kms, e0, e1));
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    g_prof.last_device_ms = kms;
-    if (g_prof.on) {
-        g_prof.collect();
+    prof.last_device_ms = kms;
+    if (prof.on) {
+        prof.collect();
         unsigned long long t = 0;
         SCLMD_CUDA(cudaMemcpy(&t, dtiles.p, sizeof(t), cudaMemcpyDeviceToHost));
-        g_prof.tiles += t;
-        g_prof.gemm_flops += (double)t * 8.0 * TS * TS * TS;      // full 64-deep tiles (the last block of an n that is not a multiple of 64 is shallower)
+        prof.tiles += t;
+        prof.gemm_flops += (double)t * 8.0 * TS * TS * TS;      // full 64-deep tiles (the last block of an n that is not a multiple of 64 is shallower)
     }
     if (want_timing)
         fprintf(stderr, "[bpt] device %.3f ms for %d frequencies in %d batches of %d on %d streams (%.0f omega/s device-only)\n", kms, nw,
@@ -1099,78 +1103,125 @@ int run_lu(int device, int n, const double *K, const int32_t *idxL, int nL, cons
 
 extern "C" {
 
-// per-kernel-class timing of the bpt sweeps (one stream, event pair per launch); switching it on resets the totals
-int sclmd_bpt_set_profiling(int on) {
-    std::lock_guard<std::mutex> lock(g_ws_mutex);
-    g_prof = Prof();
-    g_prof.on = on != 0;
+// bpt.__init__ / getdynmat (negf.py:8-25, 39-102) leave the reduced dynamical matrix, the lead dofs and the damping: that is the handle.
+// K is uploaded once; every sweep of the handle reuses it, the batch workspace and the streams.
+int sclmd_bpt_create(int device, int n, const double *K, const int32_t *idxL, int nL, const int32_t *idxR, int nR, double damp,
+                     sclmd_bpt **out) {
+    SCLMD_REQUIRE(out, "sclmd_bpt_create: NULL output");
+    *out = nullptr;
+    SCLMD_REQUIRE(n > 0 && K && idxL && idxR && nL > 0 && nR > 0 && damp != 0.0, "sclmd_bpt_create: bad arguments");
+    SCLMD_REQUIRE(n <= 4096, "bpt: n=%d exceeds the register-resident panel (n <= 4096)", n);
+    if (int e = select_device(device)) return e;
+    std::unique_ptr<sclmd_bpt> h(new sclmd_bpt());
+    h->device = device; h->n = n; h->damp = damp;
+    h->mask.assign(n, 0.0);
+    for (int i = 0; i < nL; ++i) {
+        SCLMD_REQUIRE(idxL[i] >= 0 && idxL[i] < n, "bpt: left bath dof %d out of range", idxL[i]);
+        h->mask[idxL[i]] += 1.0;
+    }
+    for (int i = 0; i < nR; ++i) {
+        SCLMD_REQUIRE(idxR[i] >= 0 && idxR[i] < n, "bpt: right bath dof %d out of range", idxR[i]);
+        h->mask[idxR[i]] += 1.0;
+    }
+    h->idxL.assign(idxL, idxL + nL);
+    h->idxR.assign(idxR, idxR + nR);
+    SCLMD_CUDA(h->dK.alloc_raw((size_t)n * n));
+    SCLMD_CUDA(cudaMemcpy(h->dK.p, K, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice));
+    *out = h.release();
+    return SCLMD_OK;
+}
+
+int sclmd_bpt_destroy(sclmd_bpt *h) {
+    if (!h) return SCLMD_OK;
+    {
+        std::lock_guard<std::mutex> lock(h->mu);
+        if (cudaSetDevice(h->device) == cudaSuccess) {
+            cudaDeviceSynchronize();
+            h->ws.release();
+        }
+        h->prof.collect();
+    }
+    delete h;
+    return SCLMD_OK;
+}
+
+// bpt.setbias (negf.py:27-37): Sigma_b^r = -i w bdamp - bias chiminus on the contiguous dof block [b0, b0+nb) (negf.py:162-172);
+// bias in angular units (eV/hbar, as bpt stores it); nb == 0 removes the block
+int sclmd_bpt_set_bias(sclmd_bpt *h, int b0, int nb, const double *bdamp, const double *chiplus, const double *chiminus, double bias) {
+    SCLMD_REQUIRE(h, "sclmd_bpt_set_bias: NULL handle");
+    std::lock_guard<std::mutex> lock(h->mu);
+    if (nb == 0) {
+        h->b0 = h->nb = 0; h->bias = 0.0;
+        h->bdamp.clear(); h->chiplus.clear(); h->chiminus.clear();
+        return SCLMD_OK;
+    }
+    SCLMD_REQUIRE(nb > 0 && b0 >= 0 && b0 + nb <= h->n && bdamp && chiplus && chiminus, "bpt: bad bias block");
+    const size_t nb2 = (size_t)nb * nb;
+    h->b0 = b0; h->nb = nb; h->bias = bias;
+    h->bdamp.assign(bdamp, bdamp + nb2);
+    h->chiplus.assign(chiplus, chiplus + nb2);
+    h->chiminus.assign(chiminus, chiminus + nb2);
+    return SCLMD_OK;
+}
+
+// per-kernel-class timing of this handle's sweeps (one stream, event pair per launch); switching it on resets the totals
+int sclmd_bpt_set_profiling(sclmd_bpt *h, int on) {
+    SCLMD_REQUIRE(h, "sclmd_bpt_set_profiling: NULL handle");
+    std::lock_guard<std::mutex> lock(h->mu);
+    h->prof.collect();
+    h->prof = Prof();
+    h->prof.on = on != 0;
     return SCLMD_OK;
 }
 
 // ms[7], n[7]: build, panel, rank-16 panel-column update, block trsm, rank-64 trailing update, back substitution, observable;
 // gemm_flops: flops executed by the rank-64 update tiles; last_device_ms: device time of the most recent sweep (always kept)
-int sclmd_bpt_get_profile(double *ms, int64_t *n, double *gemm_flops, double *last_device_ms) {
-    std::lock_guard<std::mutex> lock(g_ws_mutex);
+int sclmd_bpt_get_profile(sclmd_bpt *h, double *ms, int64_t *n, double *gemm_flops, double *last_device_ms) {
+    SCLMD_REQUIRE(h, "sclmd_bpt_get_profile: NULL handle");
+    std::lock_guard<std::mutex> lock(h->mu);
     for (int i = 0; i < NPROF; ++i) {
-        if (ms) ms[i] = g_prof.ms[i];
-        if (n) n[i] = g_prof.n[i];
+        if (ms) ms[i] = h->prof.ms[i];
+        if (n) n[i] = h->prof.n[i];
     }
-    if (gemm_flops) *gemm_flops = g_prof.gemm_flops;
-    if (last_device_ms) *last_device_ms = g_prof.last_device_ms;
+    if (gemm_flops) *gemm_flops = h->prof.gemm_flops;
+    if (last_device_ms) *last_device_ms = h->prof.last_device_ms;
     return SCLMD_OK;
 }
 
-// frees the device workspace the sweeps keep between calls
+// frees the device scratch the noise generator caches between calls (the sweeps' workspaces belong to their handles)
 int sclmd_release_workspace(void) {
-    std::lock_guard<std::mutex> lock(g_ws_mutex);
-    for (auto &w : g_ws) {
-        if (cudaSetDevice(w->device) == cudaSuccess) w->release();
-    }
-    g_ws.clear();
     sclmd::release_noise_scratch();
     return SCLMD_OK;
 }
 
-int sclmd_bpt_tm(int device, int n, const double *K, const int32_t *idxL, int nL, const int32_t *idxR, int nR, double damp,
-                 const double *omegas, int nw, double *tm_out) {
-    return run_lu(device, n, K, idxL, nL, idxR, nR, damp, omegas, nw, 0, nullptr, nullptr, 0, tm_out);
+// bpt.tm (negf.py:240-242); with a bias block set G includes its retarded self-energy
+int sclmd_bpt_tm(sclmd_bpt *h, const double *omegas, int nw, double *tm_out) {
+    SCLMD_REQUIRE(h, "sclmd_bpt_tm: NULL handle");
+    return run_lu(*h, omegas, nw, 0, nullptr, nullptr, 0, tm_out);
 }
 
-int sclmd_bpt_ps(int device, int n, const double *K, const int32_t *idxL, int nL, const int32_t *idxR, int nR, double damp,
-                 const double *omegas, const double *nb, int nw, const int32_t *sel, int nsel, double *ps_out) {
-    return run_lu(device, n, K, idxL, nL, idxR, nR, damp, omegas, nw, 1, nb, sel, nsel, ps_out);
+// bpt.ps without bias (negf.py:232)
+int sclmd_bpt_ps(sclmd_bpt *h, const double *omegas, const double *nb, int nw, const int32_t *sel, int nsel, double *ps_out) {
+    SCLMD_REQUIRE(h, "sclmd_bpt_ps: NULL handle");
+    SCLMD_REQUIRE(h->nb == 0, "sclmd_bpt_ps: the handle carries a bias block; use sclmd_bpt_ps_bias");
+    return run_lu(*h, omegas, nw, 1, nb, sel, nsel, ps_out);
 }
 
-// bpt.tm with a biased electron bath attached (bpt.setbias, negf.py:27-37): G includes Sigma_b^r = -i w bdamp - bias chiminus
-// on the contiguous dof block [b0, b0+nb) (negf.py:162-172); bias in angular units (eV/hbar, as bpt stores it)
-int sclmd_bpt_tm_bias(int device, int n, const double *K, const int32_t *idxL, int nL, const int32_t *idxR, int nR, double damp,
-                      int b0, int nb, const double *bdamp, const double *chiplus, const double *chiminus, double bias,
-                      const double *omegas, int nw, double *tm_out) {
-    BiasBlock bb;
-    bb.b0 = b0; bb.nb = nb; bb.bdamp = bdamp; bb.chiplus = chiplus; bb.chiminus = chiminus; bb.bias = bias;
-    return run_lu(device, n, K, idxL, nL, idxR, nR, damp, omegas, nw, 0, nullptr, nullptr, 0, tm_out, &bb);
-}
-
-// bpt.retargf / bpt.advangf (negf.py:206-212): the full Green function of every frequency, G[nw][n][n] complex (interleaved re, im);
-// nb == 0: no bias block.  advangf keeps the +i eps of z (negf.py:212) and takes the advanced self-energies.
-int sclmd_bpt_green(int device, int n, const double *K, const int32_t *idxL, int nL, const int32_t *idxR, int nR, double damp,
-                    int b0, int nb, const double *bdamp, const double *chiplus, const double *chiminus, double bias,
-                    const double *omegas, int nw, int advanced, double *green_out) {
-    BiasBlock bb;
-    bb.b0 = b0; bb.nb = nb; bb.bdamp = bdamp; bb.chiplus = chiplus; bb.chiminus = chiminus; bb.bias = bias;
-    return run_lu(device, n, K, idxL, nL, idxR, nR, damp, omegas, nw, 3, nullptr, nullptr, 0, green_out, nb > 0 ? &bb : nullptr, advanced);
+// bpt.retargf / bpt.advangf (negf.py:206-212): the full Green function of every frequency, G[nw][n][n] complex (interleaved re, im).
+// advangf keeps the +i eps of z (negf.py:212) and takes the advanced self-energies.
+int sclmd_bpt_green(sclmd_bpt *h, const double *omegas, int nw, int advanced, double *green_out) {
+    SCLMD_REQUIRE(h, "sclmd_bpt_green: NULL handle");
+    return run_lu(*h, omegas, nw, 3, nullptr, nullptr, 0, green_out, nullptr, advanced);
 }
 
 // bpt.ps with bias (negf.py:234-236): w^2 Re Tr[(G^r Sigma^K G^a)[sel,sel]], Sigma^K = totalkselfenergy (negf.py:177-193)
 //   = kd(w) on the lead dofs (kd = (2w/damp) n_B) + kr1 bdamp + kr2 chiplus + i ki chiminus on the bias block
-int sclmd_bpt_ps_bias(int device, int n, const double *K, const int32_t *idxL, int nL, const int32_t *idxR, int nR, double damp,
-                      int b0, int nb, const double *bdamp, const double *chiplus, const double *chiminus, double bias,
-                      const double *omegas, const double *kd, const double *kr1, const double *kr2, const double *ki, int nw,
+int sclmd_bpt_ps_bias(sclmd_bpt *h, const double *omegas, const double *kd, const double *kr1, const double *kr2, const double *ki, int nw,
                       const int32_t *sel, int nsel, double *ps_out) {
-    BiasBlock bb;
-    bb.b0 = b0; bb.nb = nb; bb.bdamp = bdamp; bb.chiplus = chiplus; bb.chiminus = chiminus; bb.bias = bias;
-    bb.kd = kd; bb.kr1 = kr1; bb.kr2 = kr2; bb.ki = ki;
-    return run_lu(device, n, K, idxL, nL, idxR, nR, damp, omegas, nw, 2, nullptr, sel, nsel, ps_out, &bb);
+    SCLMD_REQUIRE(h, "sclmd_bpt_ps_bias: NULL handle");
+    Keldysh kw;
+    kw.kd = kd; kw.kr1 = kr1; kw.kr2 = kr2; kw.ki = ki;
+    return run_lu(*h, omegas, nw, 2, nullptr, sel, nsel, ps_out, &kw);
 }
 
 }  // extern "C"

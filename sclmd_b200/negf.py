@@ -30,6 +30,7 @@ class bpt:
             device = _PAR.local_device(0)
         self.device = device
         self.natoms = natoms
+        self._h, self._hkey = None, None
         self.getdynmat(infile)
 
     def setbias(self, bias, bdamp=None, chiplus=None, chiminus=None, dofatomofbias=[]):
@@ -51,6 +52,37 @@ class bpt:
         nb = t2 - t1
         mats = [as_f64(np.ascontiguousarray(m), (nb, nb)) for m in (self.biasgamma, self.chiplus, self.chiminus)]
         return b0, nb, mats
+
+    def _handle(self):
+        """the device handle of this junction (sclmd_bpt_create): K uploaded once, workspace and streams kept between sweeps;
+        re-created when the matrix, the leads or the damping change, the bias block re-set before every sweep (O(nb^2) host copy)"""
+        iL, iR = self._reduced(self.dofatomofbath[0]), self._reduced(self.dofatomofbath[1])
+        k = self.dynmat
+        key = (k.shape, float(k.sum()), float(np.abs(k).sum()), float(self.damp), iL.tobytes(), iR.tobytes(), self.device)
+        if self._h is None or key != self._hkey:
+            self.close()
+            h = C.c_void_p()
+            check(_lib.lib().sclmd_bpt_create(self.device, len(k), dptr(as_f64(k)), iptr(iL), len(iL), iptr(iR), len(iR), float(self.damp),
+                                              C.byref(h)))
+            self._h, self._hkey = h, key
+        if self.isbias:
+            b0, nb, (bd, cp, cm) = self._bias_block()
+            check(_lib.lib().sclmd_bpt_set_bias(self._h, b0, nb, dptr(bd), dptr(cp), dptr(cm), float(self.bias)))
+        else:
+            check(_lib.lib().sclmd_bpt_set_bias(self._h, 0, 0, None, None, None, 0.0))
+        return self._h
+
+    def close(self):
+        """frees the device side (sclmd_bpt_destroy); the next sweep creates it again"""
+        if getattr(self, "_h", None) is not None:
+            _lib.lib().sclmd_bpt_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def _keldysh_weights(self, om, T):
         """per-frequency scalars of totalkselfenergy (negf.py:177-193), Bose factors evaluated with bpt.bosedist"""
@@ -177,15 +209,8 @@ class bpt:
         """full Green functions G(w) [len(omegas), n, n] from the device (batched LU with the identity as right-hand side)"""
         om = as_f64(np.atleast_1d(omegas))
         n = len(self.dynmat)
-        iL, iR = self._reduced(self.dofatomofbath[0]), self._reduced(self.dofatomofbath[1])
         out = np.empty((len(om), n, n), dtype=np.complex128)
-        if self.isbias:
-            b0, nb, (bd, cp, cm) = self._bias_block()
-            args = (b0, nb, dptr(bd), dptr(cp), dptr(cm), float(self.bias))
-        else:
-            args = (0, 0, None, None, None, 0.0)
-        check(_lib.lib().sclmd_bpt_green(self.device, n, dptr(self.dynmat), iptr(iL), len(iL), iptr(iR), len(iR), float(self.damp), *args,
-                                         dptr(om), len(om), 1 if advanced else 0, out.ctypes.data_as(_lib.c_double_p)))
+        check(_lib.lib().sclmd_bpt_green(self._handle(), dptr(om), len(om), 1 if advanced else 0, out.ctypes.data_as(_lib.c_double_p)))
         return out
 
     def retargf(self, omega):
@@ -199,16 +224,8 @@ class bpt:
     def tm_sweep(self, omegas):
         """T(w) for an array of frequencies (ps^-1) on the device (negf.py:240-242 for each)"""
         om = as_f64(omegas)
-        iL, iR = self._reduced(self.dofatomofbath[0]), self._reduced(self.dofatomofbath[1])
         out = np.empty(len(om))
-        if self.isbias:
-            b0, nb, (bd, cp, cm) = self._bias_block()
-            check(_lib.lib().sclmd_bpt_tm_bias(self.device, len(self.dynmat), dptr(self.dynmat), iptr(iL), len(iL), iptr(iR), len(iR),
-                                               float(self.damp), b0, nb, dptr(bd), dptr(cp), dptr(cm), float(self.bias), dptr(om),
-                                               len(om), dptr(out)))
-            return out
-        check(_lib.lib().sclmd_bpt_tm(self.device, len(self.dynmat), dptr(self.dynmat), iptr(iL), len(iL), iptr(iR), len(iR),
-                                      float(self.damp), dptr(om), len(om), dptr(out)))
+        check(_lib.lib().sclmd_bpt_tm(self._handle(), dptr(om), len(om), dptr(out)))
         return out
 
     def tm(self, omega):
@@ -226,19 +243,15 @@ class bpt:
     def ps_sweep(self, omegas, T, atomlist):
         om = as_f64(omegas)
         sel = self._reduced(atomlist)
-        iL, iR = self._reduced(self.dofatomofbath[0]), self._reduced(self.dofatomofbath[1])
         out = np.empty(len(om))
+        h = self._handle()
         if self.isbias:   # negf.py:234-236
-            b0, nbk, (bd, cp, cm) = self._bias_block()
             kd, kr1, kr2, ki = self._keldysh_weights(om, T)
-            check(_lib.lib().sclmd_bpt_ps_bias(self.device, len(self.dynmat), dptr(self.dynmat), iptr(iL), len(iL), iptr(iR), len(iR),
-                                               float(self.damp), b0, nbk, dptr(bd), dptr(cp), dptr(cm), float(self.bias), dptr(om),
-                                               dptr(kd), dptr(kr1), dptr(kr2), dptr(ki), len(om), iptr(sel), len(sel), dptr(out)))
+            check(_lib.lib().sclmd_bpt_ps_bias(h, dptr(om), dptr(kd), dptr(kr1), dptr(kr2), dptr(ki), len(om), iptr(sel), len(sel), dptr(out)))
             return out
         with np.errstate(all="ignore"):
             nb = np.array([float(self.bosedist(w, T)) for w in om])
-        check(_lib.lib().sclmd_bpt_ps(self.device, len(self.dynmat), dptr(self.dynmat), iptr(iL), len(iL), iptr(iR), len(iR),
-                                      float(self.damp), dptr(om), dptr(nb), len(om), iptr(sel), len(sel), dptr(out)))
+        check(_lib.lib().sclmd_bpt_ps(h, dptr(om), dptr(nb), len(om), iptr(sel), len(sel), dptr(out)))
         return out
 
     def ps(self, omega, T, atomlist):

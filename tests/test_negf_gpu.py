@@ -274,3 +274,54 @@ def test_bpt_systems_beyond_1024_dofs(natoms):
     iL, iR = O.bpt_reduce_index(bath[0], 3), O.bpt_reduce_index(bath[1], 3)
     want = np.array([O.bpt_tm(b.dynmat, w, 0.1, iL, iR) for w in om])
     assert np.max(np.abs(got - want)) < 1e-8 * max(1.0, np.abs(want).max())
+
+
+def test_bpt_handles_are_independent_and_own_their_state(tmp_path, monkeypatch):
+    """the C-ABI handle of the sweeps (sclmd_bpt_create ... destroy): two junctions side by side, one with a bias block set and removed
+    again, per-handle profiling; the matrix is uploaded once per handle and a changed matrix gives a new handle"""
+    import ctypes as C
+    from sclmd_b200 import _lib
+    from sclmd_b200.negf import bpt
+    monkeypatch.chdir(tmp_path)
+    fixed = [list(range(0, 3)), list(range(33, 36))]
+    bath = [list(range(3, 12)), list(range(24, 33))]
+    Ka = P.spring_chain_dyn(12, seed=80) / O.RPC ** 2
+    Kb = P.spring_chain_dyn(12, seed=91) / O.RPC ** 2
+    a = bpt(None, 0.25, 0.1, bath, fixed, dynmatfile=Ka, num=20)
+    b = bpt(None, 0.25, 0.2, bath, fixed, dynmatfile=Kb, num=20)
+    om = np.linspace(5.0, 300.0, 17)
+    iL, iR = O.bpt_reduce_index(bath[0], 3), O.bpt_reduce_index(bath[1], 3)
+    wa = np.array([O.bpt_tm(a.dynmat, w, 0.1, iL, iR) for w in om])
+    wb = np.array([O.bpt_tm(b.dynmat, w, 0.2, iL, iR) for w in om])
+    L = _lib.lib()
+    _lib.check(L.sclmd_bpt_set_profiling(a._handle(), 1))
+    ta1, tb1, ta2 = a.tm_sweep(om), b.tm_sweep(om), a.tm_sweep(om)
+    assert a._handle().value != b._handle().value
+    assert relerr(ta1, wa) < 1e-8 and relerr(tb1, wb) < 1e-8 and np.array_equal(ta1, ta2)
+    ms, n = (C.c_double * 7)(), (C.c_int64 * 7)()
+    _lib.check(L.sclmd_bpt_get_profile(a._handle(), ms, n, None, None))
+    assert n[0] == 2 and sum(ms) > 0                      # two sweeps of handle a, one k_build launch each
+    _lib.check(L.sclmd_bpt_get_profile(b._handle(), ms, n, None, None))
+    assert sum(n) == 0                                    # profiling is a property of the handle
+    # bias block on / off on the same handle
+    bd, cp, cm = P.psd(6, 82, 2.0), P.sym(6, 83, 1.5), P.antisym(6, 84, 1.5)
+    h0 = a._handle().value
+    a.setbias(0.6, bdamp=bd, chiplus=cp, chiminus=cm, dofatomofbias=list(range(15, 21)))
+    tbias = a.tm_sweep(om)
+    assert a._handle().value == h0 and relerr(tbias, wa) > 1e-3
+    a.isbias = False
+    assert np.array_equal(a.tm_sweep(om), ta1)
+    with pytest.raises(_lib.SclmdError):                  # ps without Keldysh weights on a handle that carries a bias block
+        _lib.check(L.sclmd_bpt_set_bias(a._handle(), 12, 6, _lib.dptr(bd), _lib.dptr(cp), _lib.dptr(cm), 0.3))
+        nb = np.ones(len(om))
+        sel = _lib.as_i32(range(12, 18))
+        out = np.empty(len(om))
+        _lib.check(L.sclmd_bpt_ps(a._h, _lib.dptr(om), _lib.dptr(nb), len(om), _lib.iptr(sel), len(sel), _lib.dptr(out)))
+    # an edited matrix is seen (new handle), close() frees the device side and the next sweep comes back
+    a.dynmat = a.dynmat * 1.01
+    t3 = a.tm_sweep(om)
+    assert relerr(t3, np.array([O.bpt_tm(a.dynmat, w, 0.1, iL, iR) for w in om])) < 1e-8
+    a.close()
+    assert a._h is None and np.array_equal(a.tm_sweep(om), t3)
+    a.close()
+    b.close()
