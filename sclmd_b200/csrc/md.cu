@@ -60,6 +60,10 @@ struct Bath {
     double c0 = 1.0;
     DevBuf<int> cids, inv;
     DevBuf<double> kern, W, ring, xq, lin, tailp, noise, cur, far, fa, fc, WT, rowstage;
+    DevBuf<double> kT;        // tensor-pipe far pass: transposed kernel table [ncp][ldk] and the tensor map of the ring
+    int ldk = 0, far_used = 1;
+    CUtensorMap ringmap;
+    bool mma_ready = false;
     bool blocked = false;     // time-blocked tails (diagonal kernel, long memory)
     int far_nsplit = 1;
     long long far_t0 = -1;    // block start the far tails in `far` belong to
@@ -1218,6 +1222,149 @@ __global__ void __launch_bounds__(352, 1) k_tail_far_wsx(const double *__restric
     }
 }
 
+// ---- far pass on the tensor pipe ---------------------------------------------------------------------------------------------
+// For one dof c the TBK far tails of a block are a matrix product over the ages d:
+//   Far[traj][s] = dt sum_d  P_c[traj][d] H_c[d][s],   P_c[traj][d] = p_{t0-1-d}[traj][c],   H_c[d][s] = k_c[s + 2 + d]   (Hankel)
+// i.e. DMMA.8x8x4 tiles with M = 8 trajectories, K = 4 ages, N = 8 steps.  Against the DFMA kernels above an instruction does 256
+// instead of 32 multiply-adds, the accumulators of a (dof, 8 trajectories, 32 steps) block are 16 registers instead of 256, and the
+// Hankel operand needs ONE new fragment per k-step and dof: the fragment of (step tile nt, ages d0..d0+3) is F(d0 + 8 nt) with
+// F(x)[lane] = k_c[x + 2 + lane/4 + lane%4], so the four tiles of a k-step take every second entry of a ring of fragments that advances
+// by one entry per k-step.  That makes a 32-step block (half the ring traffic of the 16-step block) cheaper than the 16-step DFMA pass.
+//   CTA = 8 trajectories x 32 dofs x an age range; warp w owns the dof pair (2w, 2w+1) of the chunk, both fed by one LDS.128.
+//   A producer lane streams the ring through shared memory with cp.async.bulk.tensor (boxes of 16 dofs x 4 slots x 8 trajectories,
+//   128-byte swizzle: the eight lanes of a quarter-warp -- trajectories 2i, 2i+1 x 4 ages -- hit eight different 16-byte chunks),
+//   FM_NST stages of two k-steps each against full / empty mbarriers.  The kernel rows come from a transposed copy kT[c][j]
+//   (fragment loads are 11 consecutive doubles, L1 hits, fetched ten k-steps ahead of their first use).
+constexpr int FM_W = 16;                         // consumer warps (one dof pair each)
+constexpr int FM_DC = 2 * FM_W;                  // dofs per CTA: two 16-dof boxes per ring row
+constexpr int FM_SR = 8;                         // ages per stage (two k-steps)
+constexpr int FM_NST = 8;                        // stages in flight
+constexpr int FM_BOX = 8 * 4 * 16 * 8;           // one box: 8 trajectories x 4 slots x 16 dofs
+constexpr int FM_STAGE = 4 * FM_BOX;             // [slot group][dof half]: 16 KB
+constexpr int FM_RB = 10;                        // ring of Hankel fragments per dof: 4 k-steps x 2 live + 2 ahead
+constexpr size_t FM_SMEM = (size_t)FM_NST * FM_STAGE + 1024 + 2 * FM_NST * 8 + 64;
+struct FarMmaArgs {
+    const double *kT;      // [ncp][ldk], zero beyond row ml - 1
+    double *out;           // [nsplit][TBK][ntraj][ncp]
+    int ldk, ntraj, ml, ncp, base, ages_per_split;
+    double dt;
+};
+// kT[c][j] = kern[j][c] for j < ml, 0 up to ldk
+__global__ void k_kernel_transpose(const double *__restrict__ kern, int ml, int ncp, int ldk, double *__restrict__ kT) {
+    __shared__ double tile[32][33];
+    const int j0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int j = j0 + r, c = c0 + threadIdx.x;
+        tile[r][threadIdx.x] = (j < ml && c < ncp) ? kern[(size_t)j * ncp + c] : 0.0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int c = c0 + r, j = j0 + threadIdx.x;
+        if (c < ncp && j < ldk) kT[(size_t)c * ldk + j] = tile[threadIdx.x][r];
+    }
+}
+template <int I, int N, class F>
+__device__ __forceinline__ void fm_unroll(F &f, int q0, int nk) {
+    if constexpr (I < N) {
+        if (q0 + I < nk) {
+            f(std::integral_constant<int, I>{}, q0 + I);
+            fm_unroll<I + 1, N>(f, q0, nk);
+        }
+    }
+}
+template <int TBK>
+__global__ void __launch_bounds__((FM_W + 1) * 32, 1) k_tail_far_mma(const __grid_constant__ CUtensorMap ringmap, const FarMmaArgs a) {
+    constexpr int NT = TBK / 8;
+    static_assert(NT >= 1 && 2 * (NT - 1) + 1 <= FM_RB - 2, "fragment ring too short for this block length");
+    extern __shared__ unsigned char fm_raw[];
+    unsigned char *sm = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(fm_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *full = reinterpret_cast<uint64_t *>(sm + (size_t)FM_NST * FM_STAGE), *empty = full + FM_NST;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int c0 = blockIdx.x * FM_DC, traj0 = blockIdx.y * 8;
+    const int d_lo = blockIdx.z * a.ages_per_split, d_hi = min(d_lo + a.ages_per_split, a.ml);
+    const int nstage = (d_hi - d_lo) / FM_SR, nk = 2 * nstage;          // ages_per_split and ml are multiples of FM_SR
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < FM_NST; ++i) {
+            tma_mbar_init(&full[i], 1);
+            tma_mbar_init(&empty[i], FM_W);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == FM_W) {                                      // ---- producer
+        if (lane == 0) {
+            for (int sc = 0; sc < nstage; ++sc) {
+                const int st = sc % FM_NST;
+                if (sc >= FM_NST) tma_mbar_wait(&empty[st], (unsigned)(((sc / FM_NST) - 1) & 1));
+                tma_mbar_expect(&full[st], (unsigned)FM_STAGE);
+                int lo = (a.base - (d_lo + sc * FM_SR) - (FM_SR - 1)) % a.ml;      // slots lo .. lo+7 hold the ages d+7 .. d (no wrap: base+1, ml, d are multiples of 8)
+                if (lo < 0) lo += a.ml;
+                unsigned char *dst = sm + (size_t)st * FM_STAGE;
+#pragma unroll
+                for (int g = 0; g < 2; ++g)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) tma_load_3d(dst + (g * 2 + h) * FM_BOX, &ringmap, &full[st], c0 + 16 * h, lo + 4 * g, traj0);
+            }
+        }
+        return;
+    }
+    // ---- consumers: warp = dof pair
+    const int c = c0 + 2 * warp;                             // dofs c, c + 1 (both < ncp or both pads: ncp is even)
+    const int fr = lane >> 2, fk = lane & 3;                 // A: trajectory fr, age fk | B: age fk, step fr | C: trajectory fr, steps 2 fk, 2 fk + 1
+    const int ri = fr * 4 + (3 - fk);                        // row of the box that holds (trajectory fr, age d0 + fk): slots run against the ages
+    const unsigned offA = (unsigned)((warp >> 3) * FM_BOX + ri * 128 + (((warp & 7) ^ (ri & 7)) << 4));
+    const double *kb0 = a.kT + (size_t)min(c, a.ncp - 1) * a.ldk + d_lo + 2 + fr + fk, *kb1 = a.kT + (size_t)min(c + 1, a.ncp - 1) * a.ldk + d_lo + 2 + fr + fk;
+    double acc[2][NT][2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+#pragma unroll
+        for (int n = 0; n < NT; ++n) acc[e][n][0] = acc[e][n][1] = 0.0;
+    double f0[FM_RB], f1[FM_RB];                             // F(4 q) lives in slot q % FM_RB
+#pragma unroll
+    for (int i = 0; i < FM_RB; ++i) {
+        f0[i] = __ldg(kb0 + 4 * i);
+        f1[i] = __ldg(kb1 + 4 * i);
+    }
+    int st = 0;
+    unsigned par = 0;
+    const unsigned char *sp = sm;
+    auto kstep = [&](auto ph, int q) {
+        constexpr int I = decltype(ph)::value;               // q % FM_RB (FM_RB is even: I % 2 is the k-step inside the stage)
+        if constexpr (I % 2 == 0) tma_mbar_wait(&full[st], par);
+        // k-step 0 of a stage holds the younger ages = the upper slot group
+        const double2 av = *reinterpret_cast<const double2 *>(sp + (I % 2 == 0 ? 2 * FM_BOX : 0) + offA);
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            dmma884(acc[0][n][0], acc[0][n][1], av.x, f0[(I + 2 * n) % FM_RB]);
+            dmma884(acc[1][n][0], acc[1][n][1], av.y, f1[(I + 2 * n) % FM_RB]);
+        }
+        f0[I] = __ldg(kb0 + 4 * (q + FM_RB));                // first needed FM_RB - 2 (NT - 1) k-steps from now
+        f1[I] = __ldg(kb1 + 4 * (q + FM_RB));
+        if constexpr (I % 2 == 1) {
+            __syncwarp();
+            if (lane == 0) tma_mbar_arrive(&empty[st]);
+            if (++st == FM_NST) {
+                st = 0;
+                par ^= 1u;
+                sp = sm;
+            } else {
+                sp += FM_STAGE;
+            }
+        }
+    };
+    for (int q0 = 0; q0 < nk; q0 += FM_RB) fm_unroll<0, FM_RB>(kstep, q0, nk);
+    if (c < a.ncp && traj0 + fr < a.ntraj) {
+        double *o = a.out + (((size_t)blockIdx.z * TBK) * a.ntraj + traj0 + fr) * a.ncp + c;
+        const size_t sstride = (size_t)a.ntraj * a.ncp;
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                *reinterpret_cast<double2 *>(o + (size_t)(8 * n + 2 * fk + i) * sstride) = make_double2(a.dt * acc[0][n][i], a.dt * acc[1][n][i]);
+    }
+}
+
 // tail[traj][c] = Near_s + sum_z Far[z][s]   (written where the phase kernels expect a single partial)
 __global__ void __launch_bounds__(256) k_tail_near(const double *__restrict__ ring, const double *__restrict__ kern,
                                                     const double *__restrict__ far, double *__restrict__ out, int ntraj, int ml,
@@ -1292,7 +1439,7 @@ struct ModalArgs {
 };
 
 template <int NBATH>
-__global__ void __launch_bounds__(128) k_modal_bath(const ModalArgs a) {
+__global__ void __launch_bounds__(320) k_modal_bath(const ModalArgs a) {
     __shared__ double red[32];
     const int traj = blockIdx.x;
     const double h = a.dt;
@@ -1625,7 +1772,22 @@ struct sclmd_md {
 
     // length of the time block of bath b: 16 steps; 32 with the windowed ring-pass kernel (one trajectory per CTA, A/B option)
     bool far32 = false;      // measured at the config-5 shape: 5.09 ms per 32-step pass (15.8 TFLOP/s) against 2.18 ms per 16-step pass (18.3): off by default
-    int block_len(const Bath &b) const { return (b.ncp <= 320 && far_tma && far_ws && far32) ? 2 * TB : TB; }
+    bool far_mma = true;     // tensor-pipe far pass (k_tail_far_mma): 32-step blocks, ring streamed by TMA boxes
+    bool mma_ok(const Bath &b) const { return far_mma && far_tma && far_ws && b.ml % FM_SR == 0 && !tma_disabled() && tma_encoder() != nullptr; }
+    int block_len(const Bath &b) const { return (mma_ok(b) || (b.ncp <= 320 && far_tma && far_ws && far32)) ? 2 * TB : TB; }
+    int prepare_mma(Bath &b) {
+        b.ldk = round_up(b.ml + 64, 16);
+        SCLMD_CUDA(b.kT.alloc_raw((size_t)b.ncp * b.ldk));
+        k_kernel_transpose<<<dim3(cdiv(b.ldk, 32), cdiv(b.ncp, 32)), dim3(32, 8), 0, st>>>(b.kern.p, b.ml, b.ncp, b.ldk, b.kT.p);
+        SCLMD_CUDA(cudaGetLastError());
+        ++launches;
+        const TmaOperand op{b.ring.p, {(unsigned long long)b.ncp, (unsigned long long)b.ml, (unsigned long long)ntraj},
+                            {(unsigned long long)b.ncp, (unsigned long long)b.ml * b.ncp}, 4, 8};
+        if (int e = tma_make_map(&b.ringmap, op)) return e;
+        SCLMD_CUDA(cudaFuncSetAttribute(k_tail_far_mma<2 * TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FM_SMEM));
+        b.mma_ready = true;
+        return 0;
+    }
     // friction tail S'(tt) of step tt (ring already holds p_tt)
     int tail_step(Bath &b, long long tt) {
         if (b.ml <= 1) return 0;
@@ -1639,8 +1801,21 @@ struct sclmd_md {
             const int ntiles = cdiv(b.ncp, 256), ct = cdiv(b.ncp, ntiles);
             const int aps = round_up(cdiv(b.ml, b.far_nsplit), tb);
             dim3 grid(cdiv(ntraj, T), b.far_nsplit, ntiles);
+            const bool mma = mma_ok(b);
+            if (mma && !b.mma_ready) if (int e = prepare_mma(b)) return e;
             prof_begin(2);
-            if (tb == 2 * TB) {
+            if (mma) {
+                // CTA = 32 dofs x 8 trajectories x an age range; neighbouring CTAs (x) read neighbouring pieces of the same ring rows
+                const int chunks = cdiv(b.ncp, FM_DC), groups = cdiv(ntraj, 8);
+                int ns = std::max(1, std::min(b.far_nsplit, cdiv(4 * nsm, chunks * groups)));
+                const int apm = round_up(cdiv(b.ml, ns), FM_SR);
+                ns = cdiv(b.ml, apm);
+                b.far_used = ns;
+                FarMmaArgs fa{};
+                fa.kT = b.kT.p; fa.out = b.far.p; fa.ldk = b.ldk; fa.ntraj = ntraj; fa.ml = b.ml; fa.ncp = b.ncp; fa.base = base;
+                fa.ages_per_split = apm; fa.dt = dt;
+                k_tail_far_mma<2 * TB><<<dim3(chunks, groups, ns), (FM_W + 1) * 32, FM_SMEM, st>>>(b.ringmap, fa);
+            } else if (tb == 2 * TB) {
                 auto kern = k_tail_far_wsx<1, 2 * TB, 4, 20, 36>;
                 static bool cfg = false;
                 if (!cfg) {
@@ -1675,7 +1850,7 @@ struct sclmd_md {
         }
         prof_begin(3);
         k_tail_near<<<ntraj, 256, 0, st>>>(b.ring.p, b.kern.p, b.far.p, b.tailp.p, ntraj, b.ml, b.ncp, (int)fmod_ll(tt, b.ml), (int)(tt - t0),
-                                           b.far_nsplit, dt, tb);
+                                           mma_ok(b) ? b.far_used : b.far_nsplit, dt, tb);
         prof_end();
         SCLMD_CUDA(cudaGetLastError());
         ++launches;
@@ -2038,9 +2213,11 @@ struct sclmd_md {
         a.t = t; a.dt = dt;
         a.pc = mpc.p; a.fA = mfA.p; a.g = mg.p; a.sbuf = msb.p; a.ecorr = mec.p; a.gn = mgn.p;
         prof_begin(6);
-        if (bs.nb <= 2) k_modal_bath<2><<<ntraj, 128, 0, st>>>(a);
-        else if (bs.nb <= 4) k_modal_bath<4><<<ntraj, 128, 0, st>>>(a);
-        else k_modal_bath<MAXB><<<ntraj, 128, 0, st>>>(a);
+        // at most two elements per thread: the dependent loads of an element (state, K.q slices, noise row, tail) are the whole cost
+        const int nthr = std::min(320, std::max(64, round_up(cdiv(ncs, 2), 32)));
+        if (bs.nb <= 2) k_modal_bath<2><<<ntraj, nthr, 0, st>>>(a);
+        else if (bs.nb <= 4) k_modal_bath<4><<<ntraj, nthr, 0, st>>>(a);
+        else k_modal_bath<MAXB><<<ntraj, nthr, 0, st>>>(a);
         prof_end();
         SCLMD_CUDA(cudaGetLastError());
         ++launches;
@@ -2276,6 +2453,7 @@ int sclmd_md_create(int nph, int ntraj, double dt, int nmd, int device, sclmd_md
     h->use_persist = getenv("SCLMD_NO_PERSIST") == nullptr;
     h->fuse_bca = getenv("SCLMD_NO_FUSE") == nullptr;
     h->use_ens = getenv("SCLMD_NO_ENS") == nullptr;
+    h->far_mma = getenv("SCLMD_NO_FAR_MMA") == nullptr;
     SCLMD_CUDA(h->phalf.alloc(n)); SCLMD_CUDA(h->p1.alloc(n)); SCLMD_CUDA(h->qn.alloc(n));
     SCLMD_CUDA(h->etot.alloc((size_t)nmd * ntraj));
     SCLMD_CUDA(h->cons.alloc(nph));
@@ -2565,6 +2743,7 @@ int sclmd_md_set_tail_block(sclmd_md *h, int on) {
     h->tail_block = on != 0;
     h->far_tma = on != 2;    // 2 = time-blocked with the plain-load far kernel (for A/B measurements)
     h->far_ws = on != 3;     // 3 = time-blocked with the two-stage TMA kernel (no producer warp)
+    h->far_mma = on == 1;    // 1 = the default: tensor-pipe far pass over 32-step blocks; 5 = the 16-step DFMA kernel with the producer warp (previous default)
     h->far32 = on == 4;      // 4 = 32-step blocks (k_tail_far_wsx, one trajectory per CTA): half the ring traffic, but FMA-issue bound
     for (auto &b : h->baths) {   // the partial-tail layout differs between the modes: rebuild S'(t-1)
         b->far_t0 = -1;

@@ -75,6 +75,27 @@ __global__ void k_scatter_xi(const double *__restrict__ src, double *__restrict_
     }
 }
 
+// diagonal factors (diagonal spectra, e.g. the diagonal memory kernels of config 5): x[traj][w][c] = Ld[w][c] * xi, the draws made in
+// place (same Philox counters as k_fill_xi, so the series equal those of the general path bit for bit) or read from injected xi[w][traj][ncp].
+// One thread per column pair; consecutive threads write consecutive 16-byte pieces of a spectrum row.
+__global__ void k_fill_x_diag(double *__restrict__ X, const double *__restrict__ Ld, const double *__restrict__ xi, int nw, int ntraj, int nc,
+                              int ncp, uint64_t seed, long long traj0) {
+    const int hp = ncp / 2;
+    const size_t n = (size_t)nw * ntraj * hp;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        const int kp = (int)(e % hp);
+        const size_t r = e / hp;
+        const int w = (int)(r % nw), tr = (int)(r / nw);           // X is [traj][w][ncp]
+        double2 v;
+        if (xi) v = *reinterpret_cast<const double2 *>(xi + ((size_t)w * ntraj + tr) * ncp + 2 * kp);
+        else v = philox_normal2(seed, (uint32_t)w, (uint32_t)kp, (uint64_t)(traj0 + tr));
+        const double2 l = *reinterpret_cast<const double2 *>(Ld + (size_t)w * ncp + 2 * kp);
+        v.x *= l.x;
+        v.y = 2 * kp + 1 < nc ? v.y * l.y : 0.0;
+        *reinterpret_cast<double2 *>(X + 2 * e) = v;
+    }
+}
+
 // ------------------------------------------------------------------ covariance + Jacobi factor
 // G: column-major n x n (complex: interleaved), lives in shared or global memory.
 template <bool CPLX>
@@ -933,6 +954,8 @@ struct sclmd_noise_plan {
     cudaStream_t st = nullptr;
     DevBuf<double> L;      // [nw][nc*(1+cplx)][ncp]
     DevBuf<double> evals;  // [nw][nc]
+    DevBuf<double> Ld;     // [nw][ncp]: the factors' diagonals when every L_w is diagonal (diagonal spectra: x = Ld * xi, no product)
+    bool diagL = false;
     DevBuf<double2> tw;    // twiddle table exp(-2 pi i j / nmd) of the in-place transform
     DevBuf<int> perm;      // its digit-reversed load order
     TmaWorkspace tws;      // stream-K scratch of the batched x = L xi product
@@ -1098,17 +1121,23 @@ int generate(sclmd_noise_plan *pl, int ntraj, const double *xi_host, uint64_t se
         const size_t nel = (size_t)nw * cnt * (ncp / 2);
         const int blocks = (int)std::min<size_t>((nel + 255) / 256, (size_t)pl->nsm * 16);
         mark();
+        const bool diag = pl->diagL && !pl->cplx && !getenv("SCLMD_NOISE_NO_DIAG");
         if (xi_host) {
             SCLMD_CUDA(cudaMemcpyAsync(xih.p, xi_host + (size_t)t0 * nw * nc, (size_t)cnt * nw * nc * sizeof(double), cudaMemcpyHostToDevice, st));
             k_scatter_xi<<<blocks, 256, 0, st>>>(xih.p, xi.p, nw, cnt, nc, ncp);
-        } else {
+        } else if (!diag) {
             k_fill_xi<<<blocks, 256, 0, st>>>(xi.p, nw, cnt, nc, ncp, seed, traj0 + t0);
         }
         SCLMD_CUDA(cudaGetLastError());
         ++pl->launches;
+        if (diag) {          // the draws (or the injected ones) times the factors' diagonals, straight into the spectrum rows
+            k_fill_x_diag<<<blocks, 256, 0, st>>>(X.p, pl->Ld.p, xi_host ? xi.p : nullptr, nw, cnt, nc, ncp, seed, traj0 + t0);
+            SCLMD_CUDA(cudaGetLastError());
+        }
         mark();
         // X[w] (cnt x ncx) = xi[w] (cnt x ncp) . L[w]^T   -- one product per frequency
-        if (tma_usable(cnt, nc)) {
+        if (diag) {
+        } else if (tma_usable(cnt, nc)) {
             // persistent TMA / stream-K kernel over the whole frequency batch (dgemm_tma.cuh): operands as rank-3 tensors [w][row][k]
             for (int part = 0; part < E && !rc; ++part) {        // imaginary rows of L -> imaginary block [ncp, ncp+nc) of x
                 TmaGemm g{};
@@ -1249,6 +1278,16 @@ int sclmd_noise_plan_create(int device, int nmd, double dt, int nc, int nbasis, 
             SCLMD_CUDA(cudaMemcpyAsync(V.p, Vh.data(), Vh.size() * sizeof(double), cudaMemcpyHostToDevice, pl->st));
             SCLMD_CUDA(cudaMemcpyAsync(lam.p, lh.data(), nc * sizeof(double), cudaMemcpyHostToDevice, pl->st));
             SCLMD_CUDA(cudaStreamSynchronize(pl->st));
+            // every L_w is diagonal: keep the diagonals (same expression as k_scale_factor) for the product-free generation path
+            std::vector<double> ldh((size_t)nw * pl->ncp, 0.0);
+            for (int w = 0; w < nw; ++w)
+                for (int k = 0; k < nc; ++k) {
+                    const double sv = cw[w] * lh[k];
+                    ldh[(size_t)w * pl->ncp + k] = sv > 0 ? 1.0 * sqrt(sv) : 0.0;
+                }
+            SCLMD_CUDA(pl->Ld.alloc_raw(ldh.size()));
+            SCLMD_CUDA(cudaMemcpy(pl->Ld.p, ldh.data(), ldh.size() * sizeof(double), cudaMemcpyHostToDevice));
+            pl->diagL = true;
         } else {
             if (int e = factor_batch(pl.get(), 2, 1, B0, 1, one_idx, cpos, nullptr, false, L2.p, ev2.p, true)) return e;
             k_unit_vectors<<<1, 256, 0, pl->st>>>(L2.p, L2.p + (size_t)nc * pl->ncp, ev2.p, ev2.p + nc, nc, pl->ncp, V.p, lam.p);
@@ -1308,6 +1347,7 @@ int sclmd_noise_plan_set_factors(sclmd_noise_plan *pl, const double *L, int is_c
     SCLMD_CUDA(cudaSetDevice(pl->device));
     const int nc = pl->nc, ncp = pl->ncp, E = is_complex ? 2 : 1;
     pl->cplx = is_complex ? 1 : 0;
+    pl->diagL = false;          // injected factors are general
     SCLMD_CUDA(pl->L.alloc((size_t)pl->nw * nc * E * ncp));
     std::vector<double> tmp(pl->L.n, 0.0);
     for (int w = 0; w < pl->nw; ++w)

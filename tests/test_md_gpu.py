@@ -123,8 +123,9 @@ def test_memory_kernels_vs_oracle(kind, ml, nc, ntraj, nsteps):
 
 @pytest.mark.parametrize("ml,nc,ntraj", [(200, 22, 5), (4096, 12, 4), (131, 7, 1)])
 def test_time_blocked_tails_equal_direct_tails(ml, nc, ntraj):
-    """the 16-step time-blocked far/near split of the friction tail is the same sum in another order:
-    both modes against the oracle, with a mode switch and run() calls that end mid-block"""
+    """the time-blocked far/near split of the friction tail is the same sum in another order: the tensor-pipe far pass over 32-step
+    blocks (k_tail_far_mma, needs ml % 8 == 0: the ml = 131 case falls back to the 16-step kernel), the direct pass, the 32-step DFMA
+    kernel and the 16-step DFMA kernel against the oracle, with mode switches and run() calls that end mid-block"""
     from sclmd_b200.engine import MDEngine
     natoms = 12
     nph, dt, nmd = 3 * natoms, 0.25 / 0.658, 64
@@ -137,7 +138,7 @@ def test_time_blocked_tails_equal_direct_tails(ml, nc, ntraj):
     ens.add_bath(list(range(nc)), kern, nz)
     ens.q[:], ens.p[:] = q0, p0
     engs = []
-    for mode in (1, 0, 4):              # 16-step blocks, direct, 32-step blocks (k_tail_far_wsx)
+    for mode in (1, 0, 4, 5):           # tensor-pipe 32-step blocks, direct, 32-step blocks (k_tail_far_wsx), 16-step blocks (k_tail_far_ws)
         e = MDEngine(nph, ntraj, dt, nmd)
         e.set_dyn(K)
         e.add_bath(list(range(nc)), kern)
@@ -156,6 +157,7 @@ def test_time_blocked_tails_equal_direct_tails(ml, nc, ntraj):
     engs[0].set_tail_block(0)        # switch modes in the middle of a block
     engs[1].set_tail_block(4)
     engs[2].set_tail_block(1)
+    engs[3].set_tail_block(1)
     ens.run(23)
     for e in engs:
         e.run(23)

@@ -151,6 +151,43 @@ def test_transform_pipeline_vs_oracle(nmd, nc, cplx):
     plan.close()
 
 
+@pytest.mark.parametrize("nmd,nc", [(256, 5), (8192, 6), (20000, 3)])
+def test_diagonal_spectra_skip_the_product_and_equal_the_general_path(nmd, nc, monkeypatch):
+    """a diagonal friction spectrum (the diagonal memory kernels of config 5) has diagonal factors: the generator then multiplies the
+    draws by the diagonals (k_fill_x_diag) instead of running x = L xi -- same Philox counters, the same series bit for bit as the
+    general path (SCLMD_NOISE_NO_DIAG=1), with injected draws too, and equal to the oracle"""
+    from sclmd_b200 import noise as N
+    ntraj = 5
+    gam = np.array([np.diag(np.linspace(0.01, 0.05, nc))])
+    plan = N.ph_plan(gam, np.array([0.0]), 300.0, 2.0, DT, nmd)
+    plan.generate(1, seed=1)                                    # (the first call also builds the twiddle / permutation tables)
+    n0 = plan.launch_count()
+    a = plan.generate(ntraj, seed=5, traj0=3)
+    n_fast = plan.launch_count() - n0
+    xi = np.random.default_rng(4).standard_normal((ntraj, nmd // 2 + 1, nc))
+    ai = plan.generate(ntraj, xi=xi)
+    monkeypatch.setenv("SCLMD_NOISE_NO_DIAG", "1")
+    n0 = plan.launch_count()
+    b = plan.generate(ntraj, seed=5, traj0=3)
+    n_general = plan.launch_count() - n0
+    bi = plan.generate(ntraj, xi=xi)
+    monkeypatch.delenv("SCLMD_NOISE_NO_DIAG")
+    assert np.array_equal(a, b) and np.array_equal(ai, bi)
+    assert n_fast < n_general                                   # no product launch on the diagonal path
+    L = plan.factors()
+    assert not np.any(L * (1 - np.eye(nc))[None])               # the factors are diagonal
+    for k in range(ntraj):
+        assert relerr(ai[k], O.noise_from_factors(L, xi[k], DT, nmd)) < 1e-11, k
+    # injected (general) factors switch the shortcut off
+    rng = np.random.default_rng(9)
+    Lg = L + 1e-3 * rng.standard_normal(L.shape) * np.sqrt(np.abs(L).max())
+    plan.set_factors(Lg)
+    ci = plan.generate(ntraj, xi=xi)
+    for k in range(ntraj):
+        assert relerr(ci[k], O.noise_from_factors(Lg, xi[k], DT, nmd)) < 1e-11, k
+    plan.close()
+
+
 def test_philox_draws_are_standard_normal_and_reproducible():
     from sclmd_b200 import noise as N
     nc, nmd, ntraj = 8, 4096, 16
