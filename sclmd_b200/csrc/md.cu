@@ -488,8 +488,18 @@ __global__ void __launch_bounds__(EN_W * 32, 1) k_md_ens(const EnsArgs a) {
     // dense bath (at most one): its matrix part W.[x | q] for evaluations A/B (ml0) and C (ml1), and p^1 on its dofs (mx1)
     double *slin = snz + (size_t)a.bs.nb * EN_T * a.ncpmax;
     const int tid = threadIdx.x, lane = tid & 31, wg = tid >> 5;       // wg: warp in the product
-    const bool own = wg < EN_T;                                          // this warp owns trajectory w in the elementwise phases
-    const int w = own ? wg : 0;
+    // warps per trajectory in the elementwise phases: with sixteen warps and no dense bath two warps share a trajectory (elements
+    // lane + 32 hf, stride 64; the observables of the two halves are combined through shared memory after the barrier)
+    constexpr int NH = (!LIN && EN_W >= 2 * EN_T) ? 2 : 1;
+    const bool own = wg < NH * EN_T;                                     // this warp works on trajectory w in the elementwise phases
+    const int w = own ? wg % EN_T : 0, hf = own ? wg / EN_T : 0;
+    const int e0 = lane + 32 * hf;
+    constexpr int ES = 32 * NH;
+    __shared__ double sred[2 * EN_T * (1 + NBATH)];
+    // per-dof bath tables of the diagonal baths (position in the bath, c0 k0[c]) in shared memory: the elementwise phases read them three
+    // times per step, and through L1 the position -> coefficient chain was two dependent global loads per element
+    double *skx = slin + (LIN ? 3 * EN_T * EN_LC : 0);
+    int *sinv = reinterpret_cast<int *>(skx + NBATH * lds);
     constexpr int ED = EN_W == 8 ? EN_D : 2;                             // fragment pairs in flight per tile
     double *ml0 = slin + w * EN_LC, *ml1 = slin + (EN_T + w) * EN_LC, *mx1 = slin + (2 * EN_T + w) * EN_LC;
     const int bl = a.lin_bath;                            // index of the dense bath or -1
@@ -497,7 +507,15 @@ __global__ void __launch_bounds__(EN_W * 32, 1) k_md_ens(const EnsArgs a) {
     const bool live = gtraj < a.ntraj;
     const double dt = a.dt;
     double *mp = sp + w * lds, *mq = sq + w * lds, *mg = sg + w * lds, *mg1 = sg1 + w * lds;
-    for (int i = lane; own && i < lds; i += 32) {
+    if constexpr (!LIN) {
+        for (int e = tid; e < NBATH * lds; e += EN_W * 32) {
+            const int b = e / lds, i = e % lds;
+            const int c = (b < a.bs.nb && i < nph) ? a.bs.b[b].inv[i] : -1;
+            sinv[e] = c;
+            skx[e] = c >= 0 ? a.bs.b[b].c0 * a.bs.b[b].k0[c] : 0.0;
+        }
+    }
+    for (int i = e0; own && i < lds; i += ES) {
         const bool ok = i < nph;
         mp[i] = ok ? a.p[(size_t)ltraj * a.ld + i] : 0.0;
         mq[i] = ok ? a.q[(size_t)ltraj * a.ld + i] : 0.0;
@@ -510,7 +528,7 @@ __global__ void __launch_bounds__(EN_W * 32, 1) k_md_ens(const EnsArgs a) {
             if (b < a.bs.nb) {
                 const double *src = a.bs.b[b].noise + ((size_t)ltraj * a.nmd + slab) * a.bs.b[b].ncp;
                 double *dst = snz + ((size_t)b * EN_T + w) * a.ncpmax;
-                for (int c = 2 * lane; c < a.bs.b[b].ncp; c += 64) cp_async16_zfill(dst + c, src + c, 16);
+                for (int c = 2 * e0; c < a.bs.b[b].ncp; c += 2 * ES) cp_async16_zfill(dst + c, src + c, 16);
             }
         cp_async_commit();
     };
@@ -544,7 +562,7 @@ __global__ void __launch_bounds__(EN_W * 32, 1) k_md_ens(const EnsArgs a) {
     };
     if (own) load_noise((int)(a.t0 % a.nmd));
     cp_async_wait<0>();
-    __syncwarp();
+    __syncthreads();                                      // tables, state and noise rows of every warp are in place
     const int arow = lane >> 2, aslot = lane & 3;
     for (long long s = 0; s < a.nsteps; ++s) {
         const long long t = a.t0 + s;
@@ -556,15 +574,15 @@ __global__ void __launch_bounds__(EN_W * 32, 1) k_md_ens(const EnsArgs a) {
             for (int b = 0; b < NBATH; ++b) cur[b] = 0.0;
             lin_eval(ml0, mp, false);                            // from (p_t, q_t), before they are overwritten below
 #pragma unroll 4
-            for (int i = lane; i < nph; i += 32) {      // unrolled: the dependent table loads (inv -> k0) of four elements overlap
+            for (int i = e0; i < nph; i += ES) {        // unrolled: the table loads of four elements overlap
                 const double pi = mp[i];
                 double f = -mg[i];
 #pragma unroll
                 for (int b = 0; b < NBATH; ++b)
                     if (b < a.bs.nb) {
-                        const int c = a.bs.b[b].inv[i];
+                        const int c = LIN ? a.bs.b[b].inv[i] : sinv[b * lds + i];
                         if (c >= 0) {
-                            const double fb = bforce(b, c, pi, ml0);
+                            const double fb = LIN ? bforce(b, c, pi, ml0) : snz[((size_t)b * EN_T + w) * a.ncpmax + c] - skx[b * lds + i] * pi;
                             cur[b] += fb * pi;
                             f += fb;
                             if (live) a.bs.b[b].ring[((size_t)gtraj * a.bs.b[b].ml + (int)(t % a.bs.b[b].ml)) * a.bs.b[b].ncp + c] = pi;
@@ -575,17 +593,29 @@ __global__ void __launch_bounds__(EN_W * 32, 1) k_md_ens(const EnsArgs a) {
                 mq[i] = mq[i] + pi * dt + f * dt * dt / 2.0;     // q'
             }
             ke = warp_sum(ke);
-            if (live && lane == 0) a.etot[(size_t)slab * a.ntraj + gtraj] = ke;
+            if (NH == 1) {
+                if (live && lane == 0) a.etot[(size_t)slab * a.ntraj + gtraj] = ke;
+            } else if (lane == 0) {
+                sred[(hf * EN_T + w) * (1 + NBATH)] = ke;
+            }
 #pragma unroll
             for (int b = 0; b < NBATH; ++b)
                 if (b < a.bs.nb) {
                     const double c = warp_sum(cur[b]);
-                    if (live && lane == 0) a.bs.b[b].cur[(size_t)slab * a.ntraj + gtraj] = c;
+                    if (NH == 1) {
+                        if (live && lane == 0) a.bs.b[b].cur[(size_t)slab * a.ntraj + gtraj] = c;
+                    } else if (lane == 0) {
+                        sred[(hf * EN_T + w) * (1 + NBATH) + 1 + b] = c;
+                    }
                 }
         }
-        __syncwarp();
-        if (own) load_noise((int)((t + 1) % a.nmd));      // evaluations B, C and the next evaluation A read slab t+1
-        __syncthreads();                                  // q' of all eight trajectories is in place
+        __syncthreads();                                  // q' of all eight trajectories is in place; every warp is done with noise slab t
+        if (own) load_noise((int)((t + 1) % a.nmd));      // evaluations B, C and the next evaluation A read slab t+1 (lands under the product)
+        if (NH == 2 && own && hf == 0 && live && lane <= NBATH) {      // observables: first half + second half
+            const double v = sred[w * (1 + NBATH) + lane] + sred[(EN_T + w) * (1 + NBATH) + lane];
+            if (lane == 0) a.etot[(size_t)slab * a.ntraj + gtraj] = v;
+            else if (lane - 1 < a.bs.nb) a.bs.b[lane - 1].cur[(size_t)slab * a.ntraj + gtraj] = v;
+        }
         // ---- K.q' (and the part of it that comes from the constrained dofs): DMMA over fragment-ordered K
         {
             // (the fragment loads bypass L1 -- ld.global.nc.L1::no_allocate -- so that the 3.5 MB streamed per step do not evict the
@@ -704,16 +734,16 @@ __global__ void __launch_bounds__(EN_W * 32, 1) k_md_ens(const EnsArgs a) {
             }
         } else {
 #pragma unroll 4
-            for (int i = lane; i < nph; i += 32) {
+            for (int i = e0; i < nph; i += ES) {
                 const double ph = mp[i], g1 = mg1[i];
                 double nz[NBATH], kx[NBATH];
                 bool in[NBATH];
 #pragma unroll
                 for (int b = 0; b < NBATH; ++b) {
-                    const int c = b < a.bs.nb ? a.bs.b[b].inv[i] : -1;
+                    const int c = sinv[b * lds + i];
                     in[b] = c >= 0;
                     nz[b] = in[b] ? snz[((size_t)b * EN_T + w) * a.ncpmax + c] : 0.0;
-                    kx[b] = in[b] ? a.bs.b[b].c0 * a.bs.b[b].k0[c] : 0.0;
+                    kx[b] = skx[b * lds + i];
                 }
                 double xi = ph, pnew = 0.0;
 #pragma unroll
@@ -733,7 +763,7 @@ __global__ void __launch_bounds__(EN_W * 32, 1) k_md_ens(const EnsArgs a) {
         __syncwarp();
     }
     if (own && live)
-        for (int i = lane; i < nph; i += 32) {
+        for (int i = e0; i < nph; i += ES) {
             a.p[(size_t)gtraj * a.ld + i] = mp[i];
             a.q[(size_t)gtraj * a.ld + i] = mq[i];
             a.G[(size_t)gtraj * a.ld + i] = mg[i];
@@ -1326,21 +1356,24 @@ __global__ void __launch_bounds__((FM_W + 1) * 32, 1) k_tail_far_mma(const __gri
         f0[i] = __ldg(kb0 + 4 * i);
         f1[i] = __ldg(kb1 + 4 * i);
     }
+    const bool live = c < a.ncp;
     int st = 0;
     unsigned par = 0;
     const unsigned char *sp = sm;
     auto kstep = [&](auto ph, int q) {
         constexpr int I = decltype(ph)::value;               // q % FM_RB (FM_RB is even: I % 2 is the k-step inside the stage)
         if constexpr (I % 2 == 0) tma_mbar_wait(&full[st], par);
-        // k-step 0 of a stage holds the younger ages = the upper slot group
-        const double2 av = *reinterpret_cast<const double2 *>(sp + (I % 2 == 0 ? 2 * FM_BOX : 0) + offA);
+        if (live) {                                          // (warps on pad dofs of the last chunk only keep the barriers going)
+            // k-step 0 of a stage holds the younger ages = the upper slot group
+            const double2 av = *reinterpret_cast<const double2 *>(sp + (I % 2 == 0 ? 2 * FM_BOX : 0) + offA);
 #pragma unroll
-        for (int n = 0; n < NT; ++n) {
-            dmma884(acc[0][n][0], acc[0][n][1], av.x, f0[(I + 2 * n) % FM_RB]);
-            dmma884(acc[1][n][0], acc[1][n][1], av.y, f1[(I + 2 * n) % FM_RB]);
+            for (int n = 0; n < NT; ++n) {
+                dmma884(acc[0][n][0], acc[0][n][1], av.x, f0[(I + 2 * n) % FM_RB]);
+                dmma884(acc[1][n][0], acc[1][n][1], av.y, f1[(I + 2 * n) % FM_RB]);
+            }
+            f0[I] = __ldg(kb0 + 4 * (q + FM_RB));            // first needed FM_RB - 2 (NT - 1) k-steps from now
+            f1[I] = __ldg(kb1 + 4 * (q + FM_RB));
         }
-        f0[I] = __ldg(kb0 + 4 * (q + FM_RB));                // first needed FM_RB - 2 (NT - 1) k-steps from now
-        f1[I] = __ldg(kb1 + 4 * (q + FM_RB));
         if constexpr (I % 2 == 1) {
             __syncwarp();
             if (lane == 0) tma_mbar_arrive(&empty[st]);
@@ -2025,7 +2058,9 @@ struct sclmd_md {
         a.q = q.p; a.p = p.p; a.G = G.p; a.cons = cons.p; a.etot = etot.p;
         a.lin_bath = ens_lin_bath();
         const bool wide = baths.size() > 2 || a.lin_bath >= 0;
-        const size_t smem = ((size_t)4 * EN_T * a.lds + (size_t)std::max<size_t>(baths.size(), 1) * EN_T * a.ncpmax + (wide ? 3 * EN_T * EN_LC : 0)) * sizeof(double);
+        // state + noise rows + (dense bath scratch | per-dof bath tables of the two-bath kernel: coefficient and position)
+        const size_t smem = ((size_t)4 * EN_T * a.lds + (size_t)std::max<size_t>(baths.size(), 1) * EN_T * a.ncpmax + (wide ? 3 * EN_T * EN_LC : 0)) * sizeof(double) +
+                            (wide ? 0 : (size_t)2 * a.lds * (sizeof(double) + sizeof(int)));
         if (smem > 226 * 1024) return 1;                  // caller falls back to the launch chain
         // ens_ntile tiles per warp of an 8-warp CTA; even counts are split over 16 warps (SCLMD_ENS_WARPS=8 keeps eight)
         static const bool wide16 = !(getenv("SCLMD_ENS_WARPS") && atoi(getenv("SCLMD_ENS_WARPS")) == 8);

@@ -781,9 +781,10 @@ struct StreamSlot {
     cudaStream_t st = nullptr;
     RawBuf W, Xs, act, flags;
 };
+constexpr int NSLOT = 6;
 struct Workspace {
     int device = -1;
-    StreamSlot slot[3];
+    StreamSlot slot[NSLOT];
     RawBuf arena;
     void release() {
         for (auto &s : slot) {
@@ -968,11 +969,14 @@ int run_lu(sclmd_bpt &h, const double *omegas, int nw, int mode, const double *w
     // batches: several in flight on separate streams; slot memory bounded
     const int sms = sm_count(device);
     const size_t per_w = 2 * g.plane * sizeof(double);
-    int bmax = 4 * sms;
-    while (bmax > 8 && (size_t)bmax * per_w * 3 > ((size_t)24 << 30)) bmax /= 2;
+    // A/B switches: SCLMD_BPT_BATCH = frequencies per batch in units of the SM count (default 4), SCLMD_BPT_SLOTS = batches in flight (default 3)
+    static const int batch_mult = getenv("SCLMD_BPT_BATCH") ? std::max(1, atoi(getenv("SCLMD_BPT_BATCH"))) : 4;
+    static const int slots_max = getenv("SCLMD_BPT_SLOTS") ? std::min(NSLOT, std::max(1, atoi(getenv("SCLMD_BPT_SLOTS")))) : 3;
+    int bmax = batch_mult * sms;
+    while (bmax > 8 && (size_t)bmax * per_w * slots_max > ((size_t)24 << 30)) bmax /= 2;
     const int nbatch = cdiv(nw, bmax), bsz = cdiv(nw, nbatch);
     Prof &prof = h.prof;
-    const int nslots = prof.on ? 1 : std::min(3, nbatch);
+    const int nslots = prof.on ? 1 : std::min(slots_max, nbatch);
 
     Workspace &ws = h.ws;
     StreamSlot *slots = ws.slot;
