@@ -1461,8 +1461,15 @@ __global__ void k_sum_slots(const double *__restrict__ cur, int nmd, int ntraj, 
 //   Pt_{t+1} = Pt_t - h/2 lam (Q_t + Q_{t+1}) + h/2 E^T (fC(t) + fA(t+1))
 //   Pi.Pi   = Pt.Pt - h sum_b p_c.fA_b - h^2/4 sum_b |fA_b|^2        (rows of E are orthonormal, baths disjoint)
 // As in the fused real-space path evaluations B, C of a step stay pending and run with evaluation A of the next one.
+// near part of a time-blocked tail evaluated inside k_modal_bath (what k_tail_near writes to tailp, same expression and order):
+//   S'(tt) = dt sum_{j=1}^{s+1} k[j] p_{tt+1-j} + sum_z Far[z][s],   s = tt - t0, head = slot of p_tt
+struct NearSpec {
+    const double *kern, *far;
+    int on, head, s, tb, nsplit;
+};
 struct ModalArgs {
     BathSet bs;
+    NearSpec near[MAXB];
     int off[MAXB];                 // first slot of bath b in the concatenated bath-dof arrays [ntraj][ncs]
     int ncs, ntraj, nmd, pending, doA, gsplit;
     long long t;                   // time of evaluation A (and of the noise slab / tail the pending B, C read)
@@ -1492,6 +1499,43 @@ __global__ void __launch_bounds__(320) k_modal_bath(const ModalArgs a) {
             continue;
         }
         double x = a.pc[row + e], gold = a.g[row + e], s = 0.0;
+        // the three evaluations of this element see the same noise row, friction coefficient and tail S'(t-1): fetched / summed once
+        // (eigenbasis mode: diagonal time-local part, no dense matrices); the expression and its order are those of bath_force()
+        const BathDev &bd = a.bs.b[b];
+        const double nzv = bd.noise[((size_t)traj * bd.nmd + slab) * bd.ncp + c], kx = bd.c0 * bd.k0[c];
+        double tail = 0.0;
+        if (bd.use_tail) {
+            const NearSpec &ns = a.near[b];
+            if (ns.on) {
+                const double *r = bd.ring + (size_t)traj * bd.ml * bd.ncp + c;
+                double acc = 0.0;
+                int slot = ns.head;
+                const int nj = ns.s + 1;
+                for (int j0 = 1; j0 <= nj; j0 += 8) {          // eight rows in flight per trip (same summation order as k_tail_near)
+                    double kv[8], rv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const bool ok = j0 + u <= nj;
+                        kv[u] = ok ? ns.kern[(size_t)(j0 + u) * bd.ncp + c] : 0.0;
+                        rv[u] = ok ? r[(size_t)slot * bd.ncp] : 0.0;
+                        slot = slot == 0 ? bd.ml - 1 : slot - 1;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) acc = fma(kv[u], rv[u], acc);
+                }
+                double f = 0.0;
+                for (int z = 0; z < ns.nsplit; ++z) f += ns.far[(((size_t)z * ns.tb + ns.s) * a.ntraj + traj) * bd.ncp + c];
+                tail = h * acc + f;
+            } else {
+                for (int z = 0; z < bd.nsplit; ++z) tail += bd.tailp[((size_t)z * a.ntraj + traj) * bd.ncp + c];
+            }
+        }
+        auto force = [&](double xv) {
+            double fb = nzv;
+            fb -= kx * xv;
+            if (bd.use_tail) fb -= tail;
+            return fb;
+        };
         if (a.pending) {                       // evaluations B and C of step t-1 (md.py:401-404): noise row t, tail S'(t-1)
             double gnew = a.gn[row + e];
             for (int z = 1; z < a.gsplit; ++z) gnew += a.gn[(size_t)z * a.ntraj * a.ncs + row + e];
@@ -1499,7 +1543,7 @@ __global__ void __launch_bounds__(320) k_modal_bath(const ModalArgs a) {
             double xi = ph, fb = 0.0;
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
-                fb = bath_force(a.bs.b[b], traj, a.ntraj, c, slab, xi);
+                fb = force(xi);
                 xi = ph + h * (fb - gnew) / 2.0;
             }
             x = xi;
@@ -1509,7 +1553,7 @@ __global__ void __launch_bounds__(320) k_modal_bath(const ModalArgs a) {
             a.g[row + e] = gold;
         }
         if (a.doA) {                           // evaluation A of step t (md.py:383-398) on the bath dofs
-            const double fa = bath_force(a.bs.b[b], traj, a.ntraj, c, slab, x);
+            const double fa = force(x);
 #pragma unroll
             for (int k = 0; k < NBATH; ++k)
                 if (k == b) cur[k] += fa * x;
@@ -1805,6 +1849,10 @@ struct sclmd_md {
 
     // length of the time block of bath b: 16 steps; 32 with the windowed ring-pass kernel (one trajectory per CTA, A/B option)
     bool far32 = false;      // measured at the config-5 shape: 5.09 ms per 32-step pass (15.8 TFLOP/s) against 2.18 ms per 16-step pass (18.3): off by default
+    // eigenbasis step: near part of the time-blocked tails inside k_modal_bath instead of separate k_tail_near launches (SCLMD_FUSE_NEAR=1).
+    // Off by default -- measured at config 5: 0.545 ms per step fused against 0.540: the near kernels run on the tail stream beside the
+    // products of the other stream, inside the bath-dof kernel their work sits on the step's critical path (bath -> scatter -> update -> gather)
+    bool fuse_near = false;
     bool far_mma = true;     // tensor-pipe far pass (k_tail_far_mma): 32-step blocks, ring streamed by TMA boxes
     bool mma_ok(const Bath &b) const { return far_mma && far_tma && far_ws && b.ml % FM_SR == 0 && !tma_disabled() && tma_encoder() != nullptr; }
     int block_len(const Bath &b) const { return (mma_ok(b) || (b.ncp <= 320 && far_tma && far_ws && far32)) ? 2 * TB : TB; }
@@ -1821,8 +1869,9 @@ struct sclmd_md {
         b.mma_ready = true;
         return 0;
     }
-    // friction tail S'(tt) of step tt (ring already holds p_tt)
-    int tail_step(Bath &b, long long tt) {
+    // friction tail S'(tt) of step tt (ring already holds p_tt).  near = false: only the far tails of the block of tt are brought up to
+    // date (the eigenbasis step evaluates the near part inside its bath-dof kernel, see NearSpec)
+    int tail_step(Bath &b, long long tt, bool near = true) {
         if (b.ml <= 1) return 0;
         auto fmod_ll = [](long long a, long long m) { long long r = a % m; return r < 0 ? r + m : r; };
         if (!(b.blocked && tail_block)) return tail_direct(b, (int)fmod_ll(tt, b.ml));
@@ -1881,6 +1930,7 @@ struct sclmd_md {
             b.far_t0 = t0;
             ++launches;
         }
+        if (!near) return 0;
         prof_begin(3);
         k_tail_near<<<ntraj, 256, 0, st>>>(b.ring.p, b.kern.p, b.far.p, b.tailp.p, ntraj, b.ml, b.ncp, (int)fmod_ll(tt, b.ml), (int)(tt - t0),
                                            mma_ok(b) ? b.far_used : b.far_nsplit, dt, tb);
@@ -2247,6 +2297,18 @@ struct sclmd_md {
         a.ncs = ncs; a.ntraj = ntraj; a.nmd = nmd; a.pending = pending; a.doA = doA; a.gsplit = gaplan.nsplit;
         a.t = t; a.dt = dt;
         a.pc = mpc.p; a.fA = mfA.p; a.g = mg.p; a.sbuf = msb.p; a.ecorr = mec.p; a.gn = mgn.p;
+        // time-blocked baths: the kernel sums the near part of S'(t-1) itself (at most block_len fresh ring rows per element, L2 hits)
+        // on top of the far tails of the block of t-1, which must be current -- they are, unless the state was just set
+        auto fmod_ll = [](long long x, long long m) { long long r = x % m; return r < 0 ? r + m : r; };
+        for (size_t i = 0; i < baths.size(); ++i) {
+            Bath &b = *baths[i];
+            if (!(fuse_near && b.ml > 1 && b.blocked && tail_block)) continue;
+            if (int e = tail_step(b, t - 1, false)) return e;
+            const int tb = block_len(b);
+            NearSpec &ns = a.near[i];
+            ns.on = 1; ns.kern = b.kern.p; ns.far = b.far.p; ns.tb = tb; ns.nsplit = mma_ok(b) ? b.far_used : b.far_nsplit;
+            ns.head = (int)fmod_ll(t - 1, b.ml); ns.s = (int)fmod_ll(t - 1, tb);
+        }
         prof_begin(6);
         // at most two elements per thread: the dependent loads of an element (state, K.q slices, noise row, tail) are the whole cost
         const int nthr = std::min(320, std::max(64, round_up(cdiv(ncs, 2), 32)));
@@ -2308,6 +2370,9 @@ struct sclmd_md {
         g_valid = false;
         d_valid = false;
         bc_pending = false;
+        if (fuse_near)               // the real-space kernels read S'(t-1) from tailp, which the eigenbasis steps did not keep up to date
+            for (auto &b : baths)
+                if (b->ml > 1 && b->blocked && tail_block) if (int e = tail_step(*b, t - 1)) return e;
         return 0;
     }
     int sync_real() {         // whatever mode the state is in: finish pending evaluations and make q, p current
@@ -2332,7 +2397,7 @@ struct sclmd_md {
         obs_slab = t % nmd;
         if (int e = gemm_nt(ntraj, ncs, ld, mQ[mqi ^ 1].p, ld, mEL.p, ld, mgn.p, ncs, gaplan, 5, st2)) return e;
         SCLMD_CUDA(cudaEventRecord(evG, st2));
-        for (auto &b : baths) if (int e = tail_step(*b, t)) return e;
+        for (auto &b : baths) if (int e = tail_step(*b, t, !(fuse_near && b->blocked && tail_block))) return e;     // far tails at a block start; near part: next k_modal_bath
         SCLMD_CUDA(cudaStreamWaitEvent(st, evG, 0));
         if (defer_wait) {
             SCLMD_CUDA(cudaStreamWaitEvent(st, evN, 0));
@@ -2489,6 +2554,7 @@ int sclmd_md_create(int nph, int ntraj, double dt, int nmd, int device, sclmd_md
     h->fuse_bca = getenv("SCLMD_NO_FUSE") == nullptr;
     h->use_ens = getenv("SCLMD_NO_ENS") == nullptr;
     h->far_mma = getenv("SCLMD_NO_FAR_MMA") == nullptr;
+    h->fuse_near = getenv("SCLMD_FUSE_NEAR") != nullptr;
     SCLMD_CUDA(h->phalf.alloc(n)); SCLMD_CUDA(h->p1.alloc(n)); SCLMD_CUDA(h->qn.alloc(n));
     SCLMD_CUDA(h->etot.alloc((size_t)nmd * ntraj));
     SCLMD_CUDA(h->cons.alloc(nph));

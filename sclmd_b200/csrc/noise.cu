@@ -700,6 +700,7 @@ struct BigFftArgs {
     double scale;
     double *out;
     size_t out_nstride;
+    const double2 *stage;    // real spectra: the h + 1 rows (x_a[w], x_b[w]) of this column pair staged in shared memory, or NULL
 };
 template <int R, bool FIRST, bool LAST>
 __device__ __forceinline__ void big_pass(const BigFftArgs &a, int ns, int lg) {
@@ -711,8 +712,13 @@ __device__ __forceinline__ void big_pass(const BigFftArgs &a, int ns, int lg) {
 #pragma unroll
         for (int m = 0; m < R; ++m) {
             const int i = i0 + m * ns;
-            if (FIRST) v[m] = load_Z(a.X, __ldg(a.perm + i), N, a.h, a.wstride, a.off, a.imoff, a.has_b != 0);
-            else v[m] = a.fs[fft_pad(i)];
+            if (FIRST) {
+                const int k2 = __ldg(a.perm + i);
+                // real spectrum: Z[k] = x_a[w] + i x_b[w], w = k below the Nyquist bin, N - k above it (mirror without conjugation work)
+                v[m] = a.stage ? a.stage[k2 >= a.h ? N - k2 : k2] : load_Z(a.X, k2, N, a.h, a.wstride, a.off, a.imoff, a.has_b != 0);
+            } else {
+                v[m] = a.fs[fft_pad(i)];
+            }
         }
         if (!FIRST && k > 0) {          // the first pass has ns = 1: no twiddles
             const double2 w1 = __ldg(a.tw + k * tstep);
@@ -752,13 +758,28 @@ __device__ __forceinline__ void big_pass_r(int R, const BigFftArgs &a, int ns, i
 }
 __global__ void __launch_bounds__(256, 1) k_fft_big(const double *__restrict__ X, FftPlan pl, const double2 *__restrict__ tw, const int *__restrict__ perm,
                                                      int nc, int ncp, int ncx, int imoff, double scale, double *__restrict__ out, size_t out_tstride,
-                                                     size_t out_nstride) {
+                                                     size_t out_nstride, int stage_ok) {
     extern __shared__ double2 fs[];
     const int pair = blockIdx.x, tr = blockIdx.y, c0 = 2 * pair;
+    const bool stage_rows = stage_ok && c0 + 1 < nc;       // (the odd last column of an odd nc keeps the register path)
     BigFftArgs a;
     a.X = X; a.tw = tw; a.perm = perm; a.fs = fs; a.N = pl.n; a.h = pl.n / 2; a.nc = nc; a.imoff = imoff; a.has_b = c0 + 1 < nc;
     a.wstride = (size_t)ncx; a.off = (size_t)tr * (a.h + 1) * ncx + c0;
     a.scale = scale; a.out = out + (size_t)tr * out_tstride + c0; a.out_nstride = out_nstride;
+    a.stage = nullptr;
+    if (stage_rows) {
+        // Real spectra with both columns present: the h + 1 spectrum rows of this pair (16 bytes each at a row stride of ncx doubles) go to
+        // shared memory as cp.async copies that are all in flight at once; the digit-reversed, mirrored gather of the first pass then
+        // reads shared memory.  (Register-staged, the gather was 2 x 8-byte loads per point, every row fetched twice, and their latency
+        // sat in front of the first butterflies: 1 TB/s.)
+        double2 *stg = fs + fft_pad(a.N) + 1;
+        const double *src = X + a.off;
+        for (int w = threadIdx.x; w <= a.h; w += blockDim.x) cp_async16_zfill(stg + w, src + (size_t)w * a.wstride, 16);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        a.stage = stg;
+    }
     int ns = 1;
     for (int p = 0; p < pl.npass; ++p) {
         const int R = pl.radix[p], lg = 31 - __clz(ns);
@@ -1174,10 +1195,14 @@ int generate(sclmd_noise_plan *pl, int ntraj, const double *xi_host, uint64_t se
         mark();
         double *o = out + (size_t)t0 * out_tstride;
         if (use_big) {
-            const size_t smem_big = (size_t)(N + (N >> 4) + 1) * sizeof(double2);
+            size_t smem_big = (size_t)(N + (N >> 4) + 1) * sizeof(double2);
+            // real spectra: room for the staged half spectrum of the pair behind the transform buffer (nmd = 8192: 139 + 66 KB)
+            const size_t smem_staged = smem_big + (size_t)(N / 2 + 2) * sizeof(double2);
+            const int stage_ok = !pl->cplx && smem_staged <= 220 * 1024 && !getenv("SCLMD_FFT_NO_STAGE") ? 1 : 0;
+            if (stage_ok) smem_big = smem_staged;
             SCLMD_CUDA(cudaFuncSetAttribute(k_fft_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big));
             k_fft_big<<<dim3(npair, cnt), std::min(256, std::max(32, N / 16)), smem_big, st>>>(X.p, big, pl->tw.p, pl->perm.p, nc, ncp, ncx, imoff, scale, o,
-                                                                                           out_tstride, out_nstride);
+                                                                                           out_tstride, out_nstride, stage_ok);
             SCLMD_CUDA(cudaGetLastError());
             ++pl->launches;
         } else if (direct) {
