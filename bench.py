@@ -641,7 +641,7 @@ def main():
         roof["noise_samples_per_s"] = nz.get("samples_per_s_device")
         roof["noise_frac_of_hbm_roofline"] = nz.get("frac_of_hbm_roofline_16B_per_sample")
         roof["whole_step_frac_of_fp64_peak"] = (roof.get("whole_step") or {}).get("frac_of_fp64_peak")
-        roof["traffic_source"] = "stored ncu --set full capture (profiles/r02_tail_traffic.json <- profiles/r02n_far_ncu_raw.csv), not measured in this run"
+        roof["traffic_source"] = "stored ncu --set full capture (profiles/r02_tail_traffic.json <- profiles/r02s_far_ncu_raw.csv), not measured in this run"
 
     # ---------------- BASELINE configs[1] shape (603-dof junction of the example, ml = 1 baths, fixed ends, 1024 trajectories)
     if world == 1 and not args.no_also and args.workload != "c2":
