@@ -598,10 +598,11 @@ def main():
         roof["kq_gemm_standalone"] = kq_alone
         roof["profiled_pass"] = ("the timed region itself" if prof_in_region else
                                  "a repeat of the same K steps with per-kernel events (%.4f ms per step; the timed region replays CUDA graphs)" % (ms_prof / K))
-        roof["note"] = ("avg_launch_ms of the K.q GEMM is measured inside the step, where it runs on a second stream concurrently "
-                        "with the history-tail and phase kernels (so the shares of overlapping kernels add up to more than 1); "
-                        "kq_gemm_standalone is the same kernel timed alone, and its share_of_step_serialised is the figure to "
-                        "compare with the serialised ncu launch list under profiles/")
+        roof["note"] = ("per-kernel times are CUDA-event pairs around every launch inside the timed region, on the stream of the launch; the "
+                        "products run on a second stream, so event intervals of kernels queued on different streams can overlap and the "
+                        "shares may add up to more than 1 (the serialised ncu launch list under profiles/ gives the exclusive times: "
+                        "a step is the sum of its kernels, none of them co-reside on an SM); kq_gemm_standalone is the real-space K.q "
+                        "product timed alone")
     line = {"metric": "qtb_md_trajectory_steps_per_s", "value": value, "unit": "trajectory-steps/s", "n_gpus": world,
             "steps": K, "warmup": W, "warmup_run": W_aligned, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, w, ntraj * world),

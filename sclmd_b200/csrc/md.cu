@@ -1407,9 +1407,17 @@ __global__ void __launch_bounds__(256) k_tail_near(const double *__restrict__ ri
     for (int c = threadIdx.x; c < ncp; c += blockDim.x) {
         double acc = 0.0;
         int slot = head;
-        for (int j = 1; j <= s + 1; ++j) {
-            acc = fma(kern[(size_t)j * ncp + c], r[(size_t)slot * ncp + c], acc);
-            slot = slot == 0 ? ml - 1 : slot - 1;
+        for (int j0 = 1; j0 <= s + 1; j0 += 8) {          // eight rows in flight per trip (the sum keeps its order)
+            double kv[8], rv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const bool ok = j0 + u <= s + 1;
+                kv[u] = ok ? kern[(size_t)(j0 + u) * ncp + c] : 0.0;
+                rv[u] = ok ? r[(size_t)slot * ncp + c] : 0.0;
+                slot = slot == 0 ? ml - 1 : slot - 1;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc = fma(kv[u], rv[u], acc);
         }
         double f = 0.0;
         for (int z = 0; z < nsplit; ++z) f += far[(((size_t)z * tb + s) * ntraj + traj) * ncp + c];
@@ -1479,7 +1487,7 @@ struct ModalArgs {
 };
 
 template <int NBATH>
-__global__ void __launch_bounds__(320) k_modal_bath(const ModalArgs a) {
+__global__ void __launch_bounds__(320) k_modal_bath(const ModalArgs a) {      // (launched with 256 threads by default)
     __shared__ double red[32];
     const int traj = blockIdx.x;
     const double h = a.dt;
@@ -2310,8 +2318,9 @@ struct sclmd_md {
             ns.head = (int)fmod_ll(t - 1, b.ml); ns.s = (int)fmod_ll(t - 1, tb);
         }
         prof_begin(6);
-        // at most two elements per thread: the dependent loads of an element (state, K.q slices, noise row, tail) are the whole cost
-        const int nthr = std::min(320, std::max(64, round_up(cdiv(ncs, 2), 32)));
+        // two or three elements per thread: the dependent loads of an element (state, K.q slices, noise row, tail) are the whole cost
+        static const int bath_thr = getenv("SCLMD_BATH_THREADS") ? atoi(getenv("SCLMD_BATH_THREADS")) : 256;      // 1024 CTAs in ONE wave (8 per SM); ncu: 16.3 us against 24.4 (320) and 18.8 (192)
+        const int nthr = std::min(bath_thr, std::max(64, round_up(cdiv(ncs, 2), 32)));
         if (bs.nb <= 2) k_modal_bath<2><<<ntraj, nthr, 0, st>>>(a);
         else if (bs.nb <= 4) k_modal_bath<4><<<ntraj, nthr, 0, st>>>(a);
         else k_modal_bath<MAXB><<<ntraj, nthr, 0, st>>>(a);
