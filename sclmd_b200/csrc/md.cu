@@ -61,7 +61,7 @@ struct Bath {
     DevBuf<int> cids, inv;
     DevBuf<double> kern, W, ring, xq, lin, tailp, noise, cur, far, fa, fc, WT, rowstage;
     DevBuf<double> kT;        // tensor-pipe far pass: transposed kernel table [ncp][ldk] and the tensor map of the ring
-    int ldk = 0, far_used = 1;
+    int ldk = 0, far_used = 1, far_cap = 1;
     CUtensorMap ringmap;
     bool mma_ready = false;
     bool blocked = false;     // time-blocked tails (diagonal kernel, long memory)
@@ -1897,7 +1897,18 @@ struct sclmd_md {
             if (mma) {
                 // CTA = 32 dofs x 8 trajectories x an age range; neighbouring CTAs (x) read neighbouring pieces of the same ring rows
                 const int chunks = cdiv(b.ncp, FM_DC), groups = cdiv(ntraj, 8);
-                int ns = std::max(1, std::min(b.far_nsplit, cdiv(4 * nsm, chunks * groups)));
+                // age splits: enough CTAs to fill the machine, and among 1..4 the count whose last wave is fullest (config 5: 1280 CTAs
+                // are 8.65 waves on 148 SMs, a 9th wave at 65 %; three splits are 25.95 waves)
+                int ns = std::max(1, std::min(b.far_cap, cdiv(4 * nsm, chunks * groups)));
+                {
+                    double best = 1e30;
+                    int pick = ns;
+                    for (int cand = ns; cand <= std::min(b.far_cap, std::max(ns, 4)); ++cand) {
+                        const double wv = (double)chunks * groups * cand / nsm, loss = std::ceil(wv) / wv;
+                        if (loss < best - 0.01) { best = loss; pick = cand; }
+                    }
+                    ns = pick;
+                }
                 const int apm = round_up(cdiv(b.ml, ns), FM_SR);
                 ns = cdiv(b.ml, apm);
                 b.far_used = ns;
@@ -2718,7 +2729,8 @@ int sclmd_md_add_bath(sclmd_md *h, const int32_t *cids, int nc, int ml, const do
             b->blocked = true;
             const int ctas = cdiv(ntraj, ntraj >= 4 ? 4 : 1) * cdiv(ncp, 256);
             b->far_nsplit = std::max(1, std::min({cdiv(4 * h->nsm, ctas), 16, ml / (4 * TB)}));
-            SCLMD_CUDA(b->far.alloc((size_t)b->far_nsplit * 2 * TB * ntraj * ncp));     // up to 32 far tails per pass
+            b->far_cap = std::max(b->far_nsplit, 4);                                    // the tensor-pipe pass may use up to four age splits
+            SCLMD_CUDA(b->far.alloc((size_t)b->far_cap * 2 * TB * ntraj * ncp));        // up to 32 far tails per pass and split
         }
     }
     SCLMD_CUDA(b->noise.alloc((size_t)h->nmd * ntraj * ncp));
