@@ -2408,17 +2408,21 @@ struct sclmd_md {
             noise_pending = false;
         }
         if (int e = modal_bath(view(), m_pending ? 1 : 0, 1)) return e;      // [B, C of step t-1] + A of step t; pushes p_t[cids]
-        SCLMD_CUDA(cudaEventRecord(evA, st));
-        SCLMD_CUDA(cudaStreamWaitEvent(st2, evA, 0));
-        // st2: scatter -> modal update (etot[t], Q_{t+1}) -> gather;   st: the history tails S'(t)
-        if (int e = gemm_nt(ntraj, nph, ncs, msb.p, ncs, mET.p, ncs, mW.p, ld, splan, 4, st2)) return e;
-        if (int e = modal_pq(m_pending ? 1 : 0, 1, st2)) return e;
-        SCLMD_CUDA(cudaEventRecord(evObs, st2));
+        // second stream: scatter -> modal update (etot[t], Q_{t+1}) -> gather;   st: the history tails S'(t)
+        // (sclmd_md_set_overlap(h, 0): everything on st, no cross-stream events -- A/B)
+        cudaStream_t ms = overlap ? st2 : st;
+        if (overlap) {
+            SCLMD_CUDA(cudaEventRecord(evA, st));
+            SCLMD_CUDA(cudaStreamWaitEvent(st2, evA, 0));
+        }
+        if (int e = gemm_nt(ntraj, nph, ncs, msb.p, ncs, mET.p, ncs, mW.p, ld, splan, 4, ms)) return e;
+        if (int e = modal_pq(m_pending ? 1 : 0, 1, ms)) return e;
+        SCLMD_CUDA(cudaEventRecord(evObs, ms));
         obs_slab = t % nmd;
-        if (int e = gemm_nt(ntraj, ncs, ld, mQ[mqi ^ 1].p, ld, mEL.p, ld, mgn.p, ncs, gaplan, 5, st2)) return e;
-        SCLMD_CUDA(cudaEventRecord(evG, st2));
+        if (int e = gemm_nt(ntraj, ncs, ld, mQ[mqi ^ 1].p, ld, mEL.p, ld, mgn.p, ncs, gaplan, 5, ms)) return e;
+        if (overlap) SCLMD_CUDA(cudaEventRecord(evG, st2));
         for (auto &b : baths) if (int e = tail_step(*b, t, !(fuse_near && b->blocked && tail_block))) return e;     // far tails at a block start; near part: next k_modal_bath
-        SCLMD_CUDA(cudaStreamWaitEvent(st, evG, 0));
+        if (overlap) SCLMD_CUDA(cudaStreamWaitEvent(st, evG, 0));
         if (defer_wait) {
             SCLMD_CUDA(cudaStreamWaitEvent(st, evN, 0));
             noise_pending = false;
