@@ -188,7 +188,7 @@ class _Dataset:
 
     def __init__(self, filename, mode='r'):
         if mode != 'r':
-            raise ValueError("sclmd_b200.myio.Dataset is read-only (checkpoints are written as .npz, see md.dump)")
+            raise ValueError("sclmd_b200.myio.Dataset is read-only (checkpoints are written by md.dump as NetCDF classic files with scipy.io.netcdf_file)")
         self.variables = read_nc_variables(filename)
 
     def __getitem__(self, name):
