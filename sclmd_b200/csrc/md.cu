@@ -54,6 +54,11 @@ struct BathSet {
     BathDev b[MAXB];
 };
 
+// segment of the tensor-pipe far pass (see k_tail_far_mma / plan_far)
+constexpr int FM_SPC = 2;                        // segments per CTA (a CTA's contiguous range crosses at most one pair boundary)
+struct FarSeg {
+    int c0, traj0, a_lo, a_hi, slot, nlive;      // nlive: warps with real dofs (equal for the segments of one CTA)
+};
 struct Bath {
     int nc = 0, ncp = 0, ml = 1, kind = 0, nsplit = 1, Kw = 0, gemm_cfg = -1;
     bool has_lin = false, has_extra = false;
@@ -64,6 +69,15 @@ struct Bath {
     int ldk = 0, far_used = 1, far_cap = 1;
     CUtensorMap ringmap;
     bool mma_ready = false;
+    // tensor-pipe far pass, spread over the steps of a block: segment plan (FarPlan), two halves of partial far tails (the block in use /
+    // the next block, accumulated one slice per step), per-pair partial counts for the near pass
+    DevBuf<FarSeg> fsegs, fmid;
+    DevBuf<int> fnslot;
+    std::vector<int> slice0;          // first CTA of slice i in fsegs (FM_SLICES + 1 entries)
+    int fchunks = 0, fnpairs = 0, fslots = 0, fcur = 0;
+    size_t fhalf = 0;                 // doubles per half: fslots * 2 TB * ntraj * ncp
+    long long nxt_block = -1;         // block start the other half is being filled for, and how many of its slices are done
+    int nxt_done = 0;
     bool blocked = false;     // time-blocked tails (diagonal kernel, long memory)
     int far_nsplit = 1;
     long long far_t0 = -1;    // block start the far tails in `far` belong to
@@ -1273,10 +1287,14 @@ constexpr int FM_BOX = 8 * 4 * 16 * 8;           // one box: 8 trajectories x 4 
 constexpr int FM_STAGE = 4 * FM_BOX;             // [slot group][dof half]: 16 KB
 constexpr int FM_RB = 10;                        // ring of Hankel fragments per dof: 4 k-steps x 2 live + 2 ahead
 constexpr size_t FM_SMEM = (size_t)FM_NST * FM_STAGE + 1024 + 2 * FM_NST * 8 + 64;
+// The pass is cut into SEGMENTS: stages [a_lo, a_hi) (8 ages each, first age d0 + 8 a_lo) of one (32-dof chunk, 8-trajectory group) pair,
+// whose 32 partial tails go to partial slot `slot` of that pair.  A CTA works through FM_SPC segments; the host plan (FarPlan) deals the
+// segments of a whole pass out to 32 slices of about one CTA per SM each, so that one slice can be launched per MD step.
 struct FarMmaArgs {
     const double *kT;      // [ncp][ldk], zero beyond row ml - 1
-    double *out;           // [nsplit][TBK][ntraj][ncp]
-    int ldk, ntraj, ml, ncp, base, ages_per_split;
+    double *out;           // [slot][TBK][ntraj][ncp]
+    const FarSeg *segs;    // [gridDim.x][FM_SPC] of this launch
+    int ldk, ntraj, ml, ncp, base, d0;
     double dt;
 };
 // kT[c][j] = kern[j][c] for j < ml, 0 up to ldk
@@ -1303,17 +1321,15 @@ __device__ __forceinline__ void fm_unroll(F &f, int q0, int nk) {
     }
 }
 template <int TBK>
-__global__ void __launch_bounds__((FM_W + 1) * 32, 1) k_tail_far_mma(const __grid_constant__ CUtensorMap ringmap, const FarMmaArgs a) {
+__device__ __forceinline__ void far_mma_body(const CUtensorMap *ringmap, const FarMmaArgs &a, int cta) {
     constexpr int NT = TBK / 8;
     static_assert(NT >= 1 && 2 * (NT - 1) + 1 <= FM_RB - 2, "fragment ring too short for this block length");
     extern __shared__ unsigned char fm_raw[];
     unsigned char *sm = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(fm_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *full = reinterpret_cast<uint64_t *>(sm + (size_t)FM_NST * FM_STAGE), *empty = full + FM_NST;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int c0 = blockIdx.x * FM_DC, traj0 = blockIdx.y * 8;
-    const int d_lo = blockIdx.z * a.ages_per_split, d_hi = min(d_lo + a.ages_per_split, a.ml);
-    const int nstage = (d_hi - d_lo) / FM_SR, nk = 2 * nstage;          // ages_per_split and ml are multiples of FM_SR
-    const int nlive = min(FM_W, (a.ncp - c0) / 2);           // warps with real dofs (the last chunk may be partly padding): only they consume
+    const FarSeg *my = a.segs + (size_t)cta * FM_SPC;
+    const int nlive = my[0].nlive;                           // warps with real dofs (the last chunk may be partly padding): only they consume
     if (tid == 0) {
 #pragma unroll
         for (int i = 0; i < FM_NST; ++i) {
@@ -1327,81 +1343,105 @@ __global__ void __launch_bounds__((FM_W + 1) * 32, 1) k_tail_far_mma(const __gri
     if (warp == FM_W) {                                      // ---- producer (a warp of its own: merged into a consumer warp the refills
                                                              //      come late -- 3.44 instead of 2.83 ms -- even though 16 warps could have 128 registers)
         if (lane == 0) {
-            for (int sc = 0; sc < nstage; ++sc) {
-                const int st = sc % FM_NST;
-                if (sc >= FM_NST) tma_mbar_wait(&empty[st], (unsigned)(((sc / FM_NST) - 1) & 1));
-                tma_mbar_expect(&full[st], (unsigned)FM_STAGE);
-                int lo = (a.base - (d_lo + sc * FM_SR) - (FM_SR - 1)) % a.ml;      // slots lo .. lo+7 hold the ages d+7 .. d (no wrap: base+1, ml, d are multiples of 8)
-                if (lo < 0) lo += a.ml;
-                unsigned char *dst = sm + (size_t)st * FM_STAGE;
+            int sc = 0;                                      // stages issued so far, over all segments of this CTA
+            for (int g = 0; g < FM_SPC; ++g) {
+                const FarSeg sg = my[g];
+                for (int ai = sg.a_lo; ai < sg.a_hi; ++ai, ++sc) {
+                    const int st = sc % FM_NST;
+                    if (sc >= FM_NST) tma_mbar_wait(&empty[st], (unsigned)(((sc / FM_NST) - 1) & 1));
+                    tma_mbar_expect(&full[st], (unsigned)FM_STAGE);
+                    int lo = (a.base - (a.d0 + ai * FM_SR) - (FM_SR - 1)) % a.ml;      // slots lo .. lo+7 hold the ages d+7 .. d (no wrap: base+1, ml, d are multiples of 8)
+                    if (lo < 0) lo += a.ml;
+                    unsigned char *dst = sm + (size_t)st * FM_STAGE;
 #pragma unroll
-                for (int g = 0; g < 2; ++g)
+                    for (int gg = 0; gg < 2; ++gg)
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) tma_load_3d(dst + (g * 2 + h) * FM_BOX, &ringmap, &full[st], c0 + 16 * h, lo + 4 * g, traj0);
+                        for (int h = 0; h < 2; ++h) tma_load_3d(dst + (gg * 2 + h) * FM_BOX, ringmap, &full[st], sg.c0 + 16 * h, lo + 4 * gg, sg.traj0);
+                }
             }
         }
         return;
     }
     // ---- consumers: warp = dof pair
-    const int c = c0 + 2 * warp;                             // dofs c, c + 1 (both < ncp or both pads: ncp is even)
     const int fr = lane >> 2, fk = lane & 3;                 // A: trajectory fr, age fk | B: age fk, step fr | C: trajectory fr, steps 2 fk, 2 fk + 1
     const int ri = fr * 4 + (3 - fk);                        // row of the box that holds (trajectory fr, age d0 + fk): slots run against the ages
     const unsigned offA = (unsigned)((warp >> 3) * FM_BOX + ri * 128 + (((warp & 7) ^ (ri & 7)) << 4));
-    const double *kb0 = a.kT + (size_t)min(c, a.ncp - 1) * a.ldk + d_lo + 2 + fr + fk, *kb1 = a.kT + (size_t)min(c + 1, a.ncp - 1) * a.ldk + d_lo + 2 + fr + fk;
-    double acc[2][NT][2];
-#pragma unroll
-    for (int e = 0; e < 2; ++e)
-#pragma unroll
-        for (int n = 0; n < NT; ++n) acc[e][n][0] = acc[e][n][1] = 0.0;
-    double f0[FM_RB], f1[FM_RB];                             // F(4 q) lives in slot q % FM_RB
-#pragma unroll
-    for (int i = 0; i < FM_RB; ++i) {
-        f0[i] = __ldg(kb0 + 4 * i);
-        f1[i] = __ldg(kb1 + 4 * i);
-    }
-    int st = 0;
+    int st = 0;                                              // stage cursor: runs on across the segments, like the producer's
     unsigned par = 0;
     const unsigned char *sp = sm;
-    auto kstep = [&](auto ph, int q) {
-        constexpr int I = decltype(ph)::value;               // q % FM_RB (FM_RB is even: I % 2 is the k-step inside the stage)
-        if constexpr (I % 2 == 0) tma_mbar_wait(&full[st], par);
-        // k-step 0 of a stage holds the younger ages = the upper slot group
-        const double2 av = *reinterpret_cast<const double2 *>(sp + (I % 2 == 0 ? 2 * FM_BOX : 0) + offA);
+    const size_t sstride = (size_t)a.ntraj * a.ncp;
+#pragma unroll 1
+    for (int g = 0; g < FM_SPC; ++g) {
+        const FarSeg sg = my[g];
+        const int nk = 2 * (sg.a_hi - sg.a_lo);
+        if (nk <= 0) continue;
+        const int c = sg.c0 + 2 * warp;                      // dofs c, c + 1 (both < ncp: this warp is live)
+        const int dlo = a.d0 + sg.a_lo * FM_SR;
+        const double *kb0 = a.kT + (size_t)min(c, a.ncp - 1) * a.ldk + dlo + 2 + fr + fk, *kb1 = a.kT + (size_t)min(c + 1, a.ncp - 1) * a.ldk + dlo + 2 + fr + fk;
+        double acc[2][NT][2];
 #pragma unroll
-        for (int n = 0; n < NT; ++n) {
-            dmma884(acc[0][n][0], acc[0][n][1], av.x, f0[(I + 2 * n) % FM_RB]);
-            dmma884(acc[1][n][0], acc[1][n][1], av.y, f1[(I + 2 * n) % FM_RB]);
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int n = 0; n < NT; ++n) acc[e][n][0] = acc[e][n][1] = 0.0;
+        double f0[FM_RB], f1[FM_RB];                         // F(4 q) lives in slot q % FM_RB
+#pragma unroll
+        for (int i = 0; i < FM_RB; ++i) {
+            f0[i] = __ldg(kb0 + 4 * i);
+            f1[i] = __ldg(kb1 + 4 * i);
         }
-        f0[I] = __ldg(kb0 + 4 * (q + FM_RB));                // first needed FM_RB - 2 (NT - 1) k-steps from now
-        f1[I] = __ldg(kb1 + 4 * (q + FM_RB));
-        if constexpr (I % 2 == 1) {
-            __syncwarp();
-            if (lane == 0) tma_mbar_arrive(&empty[st]);
-            if (++st == FM_NST) {
-                st = 0;
-                par ^= 1u;
-                sp = sm;
-            } else {
-                sp += FM_STAGE;
+        auto kstep = [&](auto ph, int q) {
+            constexpr int I = decltype(ph)::value;           // q % FM_RB (FM_RB is even: I % 2 is the k-step inside the stage)
+            if constexpr (I % 2 == 0) tma_mbar_wait(&full[st], par);
+            // k-step 0 of a stage holds the younger ages = the upper slot group
+            const double2 av = *reinterpret_cast<const double2 *>(sp + (I % 2 == 0 ? 2 * FM_BOX : 0) + offA);
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+                dmma884(acc[0][n][0], acc[0][n][1], av.x, f0[(I + 2 * n) % FM_RB]);
+                dmma884(acc[1][n][0], acc[1][n][1], av.y, f1[(I + 2 * n) % FM_RB]);
             }
+            f0[I] = __ldg(kb0 + 4 * (q + FM_RB));            // first needed FM_RB - 2 (NT - 1) k-steps from now
+            f1[I] = __ldg(kb1 + 4 * (q + FM_RB));
+            if constexpr (I % 2 == 1) {
+                __syncwarp();
+                if (lane == 0) tma_mbar_arrive(&empty[st]);
+                if (++st == FM_NST) {
+                    st = 0;
+                    par ^= 1u;
+                    sp = sm;
+                } else {
+                    sp += FM_STAGE;
+                }
+            }
+        };
+        for (int q0 = 0; q0 < nk; q0 += FM_RB) fm_unroll<0, FM_RB>(kstep, q0, nk);
+        if (c < a.ncp && sg.traj0 + fr < a.ntraj) {
+            double *o = a.out + (((size_t)sg.slot * TBK) * a.ntraj + sg.traj0 + fr) * a.ncp + c;
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+                    *reinterpret_cast<double2 *>(o + (size_t)(8 * n + 2 * fk + i) * sstride) = make_double2(a.dt * acc[0][n][i], a.dt * acc[1][n][i]);
         }
-    };
-    for (int q0 = 0; q0 < nk; q0 += FM_RB) fm_unroll<0, FM_RB>(kstep, q0, nk);
-    if (c < a.ncp && traj0 + fr < a.ntraj) {
-        double *o = a.out + (((size_t)blockIdx.z * TBK) * a.ntraj + traj0 + fr) * a.ncp + c;
-        const size_t sstride = (size_t)a.ntraj * a.ncp;
-#pragma unroll
-        for (int n = 0; n < NT; ++n)
-#pragma unroll
-            for (int i = 0; i < 2; ++i)
-                *reinterpret_cast<double2 *>(o + (size_t)(8 * n + 2 * fk + i) * sstride) = make_double2(a.dt * acc[0][n][i], a.dt * acc[1][n][i]);
     }
+}
+
+template <int TBK>
+__global__ void __launch_bounds__((FM_W + 1) * 32, 1) k_tail_far_mma(const __grid_constant__ CUtensorMap ringmap, const FarMmaArgs a) {
+    far_mma_body<TBK>(&ringmap, a, blockIdx.x);
+}
+// the slices of two baths in one launch (CTAs [0, n0) work for the first bath): one ramp and one drain per step instead of two
+template <int TBK>
+__global__ void __launch_bounds__((FM_W + 1) * 32, 1) k_tail_far_mma2(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
+                                                                         const FarMmaArgs a0, const FarMmaArgs a1, int n0) {
+    if ((int)blockIdx.x < n0) far_mma_body<TBK>(&map0, a0, blockIdx.x);
+    else far_mma_body<TBK>(&map1, a1, blockIdx.x - n0);
 }
 
 // tail[traj][c] = Near_s + sum_z Far[z][s]   (written where the phase kernels expect a single partial)
 __global__ void __launch_bounds__(256) k_tail_near(const double *__restrict__ ring, const double *__restrict__ kern,
                                                     const double *__restrict__ far, double *__restrict__ out, int ntraj, int ml,
-                                                    int ncp, int head, int s, int nsplit, double dt, int tb) {
+                                                    int ncp, int head, int s, int nsplit, double dt, int tb,
+                                                    const int *__restrict__ nslot, int chunks) {
     const int traj = blockIdx.x;
     const double *r = ring + (size_t)traj * ml * ncp;
     for (int c = threadIdx.x; c < ncp; c += blockDim.x) {
@@ -1420,7 +1460,9 @@ __global__ void __launch_bounds__(256) k_tail_near(const double *__restrict__ ri
             for (int u = 0; u < 8; ++u) acc = fma(kv[u], rv[u], acc);
         }
         double f = 0.0;
-        for (int z = 0; z < nsplit; ++z) f += far[(((size_t)z * tb + s) * ntraj + traj) * ncp + c];
+        // partial far tails: a fixed count, or (tensor-pipe pass) the slots of this element's (32-dof chunk, 8-trajectory group) pair
+        const int nz = nslot ? nslot[(traj >> 3) * chunks + (c >> 5)] : nsplit;
+        for (int z = 0; z < nz; ++z) f += far[(((size_t)z * tb + s) * ntraj + traj) * ncp + c];
         out[(size_t)traj * ncp + c] = dt * acc + f;
     }
 }
@@ -1469,15 +1511,8 @@ __global__ void k_sum_slots(const double *__restrict__ cur, int nmd, int ntraj, 
 //   Pt_{t+1} = Pt_t - h/2 lam (Q_t + Q_{t+1}) + h/2 E^T (fC(t) + fA(t+1))
 //   Pi.Pi   = Pt.Pt - h sum_b p_c.fA_b - h^2/4 sum_b |fA_b|^2        (rows of E are orthonormal, baths disjoint)
 // As in the fused real-space path evaluations B, C of a step stay pending and run with evaluation A of the next one.
-// near part of a time-blocked tail evaluated inside k_modal_bath (what k_tail_near writes to tailp, same expression and order):
-//   S'(tt) = dt sum_{j=1}^{s+1} k[j] p_{tt+1-j} + sum_z Far[z][s],   s = tt - t0, head = slot of p_tt
-struct NearSpec {
-    const double *kern, *far;
-    int on, head, s, tb, nsplit;
-};
 struct ModalArgs {
     BathSet bs;
-    NearSpec near[MAXB];
     int off[MAXB];                 // first slot of bath b in the concatenated bath-dof arrays [ntraj][ncs]
     int ncs, ntraj, nmd, pending, doA, gsplit;
     long long t;                   // time of evaluation A (and of the noise slab / tail the pending B, C read)
@@ -1512,32 +1547,8 @@ __global__ void __launch_bounds__(320) k_modal_bath(const ModalArgs a) {      //
         const BathDev &bd = a.bs.b[b];
         const double nzv = bd.noise[((size_t)traj * bd.nmd + slab) * bd.ncp + c], kx = bd.c0 * bd.k0[c];
         double tail = 0.0;
-        if (bd.use_tail) {
-            const NearSpec &ns = a.near[b];
-            if (ns.on) {
-                const double *r = bd.ring + (size_t)traj * bd.ml * bd.ncp + c;
-                double acc = 0.0;
-                int slot = ns.head;
-                const int nj = ns.s + 1;
-                for (int j0 = 1; j0 <= nj; j0 += 8) {          // eight rows in flight per trip (same summation order as k_tail_near)
-                    double kv[8], rv[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const bool ok = j0 + u <= nj;
-                        kv[u] = ok ? ns.kern[(size_t)(j0 + u) * bd.ncp + c] : 0.0;
-                        rv[u] = ok ? r[(size_t)slot * bd.ncp] : 0.0;
-                        slot = slot == 0 ? bd.ml - 1 : slot - 1;
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) acc = fma(kv[u], rv[u], acc);
-                }
-                double f = 0.0;
-                for (int z = 0; z < ns.nsplit; ++z) f += ns.far[(((size_t)z * ns.tb + ns.s) * a.ntraj + traj) * bd.ncp + c];
-                tail = h * acc + f;
-            } else {
-                for (int z = 0; z < bd.nsplit; ++z) tail += bd.tailp[((size_t)z * a.ntraj + traj) * bd.ncp + c];
-            }
-        }
+        if (bd.use_tail)
+            for (int z = 0; z < bd.nsplit; ++z) tail += bd.tailp[((size_t)z * a.ntraj + traj) * bd.ncp + c];
         auto force = [&](double xv) {
             double fb = nzv;
             fb -= kx * xv;
@@ -1857,10 +1868,6 @@ struct sclmd_md {
 
     // length of the time block of bath b: 16 steps; 32 with the windowed ring-pass kernel (one trajectory per CTA, A/B option)
     bool far32 = false;      // measured at the config-5 shape: 5.09 ms per 32-step pass (15.8 TFLOP/s) against 2.18 ms per 16-step pass (18.3): off by default
-    // eigenbasis step: near part of the time-blocked tails inside k_modal_bath instead of separate k_tail_near launches (SCLMD_FUSE_NEAR=1).
-    // Off by default -- measured at config 5: 0.545 ms per step fused against 0.540: the near kernels run on the tail stream beside the
-    // products of the other stream, inside the bath-dof kernel their work sits on the step's critical path (bath -> scatter -> update -> gather)
-    bool fuse_near = false;
     bool far_mma = true;     // tensor-pipe far pass (k_tail_far_mma): 32-step blocks, ring streamed by TMA boxes
     bool mma_ok(const Bath &b) const { return far_mma && far_tma && far_ws && b.ml % FM_SR == 0 && !tma_disabled() && tma_encoder() != nullptr; }
     int block_len(const Bath &b) const { return (mma_ok(b) || (b.ncp <= 320 && far_tma && far_ws && far32)) ? 2 * TB : TB; }
@@ -1874,15 +1881,193 @@ struct sclmd_md {
                             {(unsigned long long)b.ncp, (unsigned long long)b.ml * b.ncp}, 4, 8};
         if (int e = tma_make_map(&b.ringmap, op)) return e;
         SCLMD_CUDA(cudaFuncSetAttribute(k_tail_far_mma<2 * TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FM_SMEM));
+        SCLMD_CUDA(cudaFuncSetAttribute(k_tail_far_mma2<2 * TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FM_SMEM));
+        if (int e = plan_far(b)) return e;
         b.mma_ready = true;
         return 0;
     }
-    // friction tail S'(tt) of step tt (ring already holds p_tt).  near = false: only the far tails of the block of tt are brought up to
-    // date (the eigenbasis step evaluates the near part inside its bath-dof kernel, see NearSpec)
-    int tail_step(Bath &b, long long tt, bool near = true) {
+    // FarPlan: the far-far part of a pass (ages >= 32 relative to the block start: ring rows that are final one block EARLIER) as
+    // FM_SLICES slices of about one CTA per SM, so that the pass for block B + 1 is worked off one slice per step during block B; the
+    // ages 0..31 (the rows of block B itself) follow as a short "mid" pass at the block boundary.  Every step then costs the same.
+    // Linear order: (trajectory group, stage); a work item is a range of stages of one group (cut at most once by a group boundary) and
+    // becomes one CTA per 32-dof chunk, side by side: the CTAs of an item run together and read neighbouring pieces of the same ring
+    // rows (with the 256-byte L2 promotion of the tensor map every DRAM sector is then fetched once; chunk-major items measured 36 %
+    // slower).  The k-th segment of a (chunk, group) pair writes partial slot k of that pair: a fixed order.
+    static constexpr int FM_SLICES = 2 * TB;
+    int plan_far(Bath &b) {
+        const int chunks = cdiv(b.ncp, FM_DC), groups = cdiv(ntraj, 8), npairs = chunks * groups;
+        const int na = (b.ml - 2 * TB) / FM_SR;                     // far-far stages per pair
+        const long long total = (long long)groups * na;
+        const long long per_slice = std::max<long long>(1, (total + FM_SLICES - 1) / FM_SLICES);
+        const int items = std::max(1, nsm / chunks);                 // work items of a slice: about one CTA per SM
+        const long long per_item = std::max<long long>(8, (per_slice + items - 1) / items);
+        std::vector<FarSeg> segs;
+        std::vector<int> cnt(npairs, 0);
+        b.slice0.assign(FM_SLICES + 1, 0);
+        auto nlive_of = [&](int chunk) { return std::min(FM_W, (b.ncp - chunk * FM_DC) / 2); };
+        long long pos = 0;
+        for (int sl = 0; sl < FM_SLICES; ++sl) {
+            b.slice0[sl] = (int)(segs.size() / FM_SPC);
+            const long long send = std::min(total, (sl + 1) * per_slice);
+            while (pos < send) {
+                long long left = std::min(per_item, send - pos);
+                int nseg = 0, gg[FM_SPC], lo[FM_SPC], hi[FM_SPC];
+                while (left > 0 && nseg < FM_SPC) {
+                    gg[nseg] = (int)(pos / na);
+                    lo[nseg] = (int)(pos % na);
+                    hi[nseg] = (int)std::min<long long>(na, lo[nseg] + left);
+                    left -= hi[nseg] - lo[nseg];
+                    pos += hi[nseg] - lo[nseg];
+                    ++nseg;
+                }
+                for (int ch = 0; ch < chunks; ++ch)
+                    for (int k = 0; k < FM_SPC; ++k) {
+                        if (k < nseg) segs.push_back(FarSeg{ch * FM_DC, gg[k] * 8, lo[k], hi[k], cnt[gg[k] * chunks + ch]++, nlive_of(ch)});
+                        else segs.push_back(FarSeg{0, 0, 0, 0, 0, nlive_of(ch)});
+                    }
+            }
+        }
+        b.slice0[FM_SLICES] = (int)(segs.size() / FM_SPC);
+        // mid pass: ages 0..31, one CTA per pair (chunks side by side), slot right behind the pair's far-far slots
+        std::vector<FarSeg> mid;
+        int maxslot = 0;
+        for (int gr = 0; gr < groups; ++gr)
+            for (int ch = 0; ch < chunks; ++ch) {
+                const int pid = gr * chunks + ch;
+                mid.push_back(FarSeg{ch * FM_DC, gr * 8, 0, 2 * TB / FM_SR, cnt[pid]++, nlive_of(ch)});
+                for (int k = 1; k < FM_SPC; ++k) mid.push_back(FarSeg{0, 0, 0, 0, 0, nlive_of(ch)});
+                maxslot = std::max(maxslot, cnt[pid]);
+            }
+        b.fchunks = chunks; b.fnpairs = npairs; b.fslots = maxslot;
+        b.fhalf = (size_t)maxslot * 2 * TB * ntraj * b.ncp;
+        if (segs.empty()) segs.push_back(FarSeg{0, 0, 0, 0, 0, FM_W});
+        SCLMD_CUDA(b.fsegs.alloc_raw(segs.size()));
+        SCLMD_CUDA(cudaMemcpy(b.fsegs.p, segs.data(), segs.size() * sizeof(FarSeg), cudaMemcpyHostToDevice));
+        SCLMD_CUDA(b.fmid.alloc_raw(mid.size()));
+        SCLMD_CUDA(cudaMemcpy(b.fmid.p, mid.data(), mid.size() * sizeof(FarSeg), cudaMemcpyHostToDevice));
+        SCLMD_CUDA(b.fnslot.alloc_raw(npairs));
+        SCLMD_CUDA(cudaMemcpy(b.fnslot.p, cnt.data(), npairs * sizeof(int), cudaMemcpyHostToDevice));
+        if (b.far.n < 2 * b.fhalf) SCLMD_CUDA(b.far.alloc_raw(2 * b.fhalf));
+        b.fcur = 0;
+        b.far_t0 = -1;
+        b.nxt_block = -1;
+        return 0;
+    }
+    FarMmaArgs far_args(Bath &b, long long t0, int half, int d0) {
+        auto fmod_ll = [](long long x, long long m) { long long r = x % m; return r < 0 ? r + m : r; };
+        FarMmaArgs fa{};
+        fa.kT = b.kT.p; fa.out = b.far.p + (size_t)half * b.fhalf; fa.ldk = b.ldk; fa.ntraj = ntraj; fa.ml = b.ml; fa.ncp = b.ncp;
+        fa.base = (int)fmod_ll(t0 - 1, b.ml); fa.d0 = d0; fa.dt = dt;
+        return fa;
+    }
+    // background work of a step, collected by tail_step_mma and launched by flush_far(): slice `sl` of the next block's pass for
+    // every bath (two baths per launch), then -- after the last step of a block -- the mid pass and the change of halves
+    struct FarPending { Bath *b; long long t1; int s0, s1; };
+    std::vector<FarPending> far_pending;
+    int flush_far() {
+        std::vector<FarPending> pend;
+        pend.swap(far_pending);
+        size_t i = 0;
+        while (i < pend.size()) {
+            FarPending &p0 = pend[i];
+            // a second bath with the same slice range (the normal case) shares the launch
+            if (i + 1 < pend.size() && pend[i + 1].s0 == p0.s0 && pend[i + 1].s1 == p0.s1 && p0.s0 == p0.s1 && pend[i + 1].b != p0.b) {
+                FarPending &p1 = pend[i + 1];
+                Bath &b0 = *p0.b, &b1 = *p1.b;
+                const int sl = p0.s0;
+                const int n0 = b0.slice0[sl + 1] - b0.slice0[sl], n1 = b1.slice0[sl + 1] - b1.slice0[sl];
+                if (n0 > 0 && n1 > 0) {
+                    FarMmaArgs a0 = far_args(b0, p0.t1, b0.fcur ^ 1, 2 * TB), a1 = far_args(b1, p1.t1, b1.fcur ^ 1, 2 * TB);
+                    a0.segs = b0.fsegs.p + (size_t)b0.slice0[sl] * FM_SPC;
+                    a1.segs = b1.fsegs.p + (size_t)b1.slice0[sl] * FM_SPC;
+                    prof_begin(2);
+                    k_tail_far_mma2<2 * TB><<<n0 + n1, (FM_W + 1) * 32, FM_SMEM, st>>>(b0.ringmap, b1.ringmap, a0, a1, n0);
+                    prof_end();
+                    SCLMD_CUDA(cudaGetLastError());
+                    ++launches;
+                    i += 2;
+                    continue;
+                }
+            }
+            if (int e = far_slices(*p0.b, p0.t1, p0.b->fcur ^ 1, p0.s0, p0.s1)) return e;
+            ++i;
+        }
+        for (auto &p : pend)
+            if (p.s1 == FM_SLICES - 1) {
+                Bath &b = *p.b;
+                if (int e = far_mid(b, p.t1, b.fcur ^ 1)) return e;
+                b.fcur ^= 1;
+                b.far_t0 = p.t1;
+                b.nxt_block = -1;
+            }
+        return 0;
+    }
+    // slices [s0, s1] of the far-far pass of the block starting at t0 into half `half`
+    int far_slices(Bath &b, long long t0, int half, int s0, int s1) {
+        auto fmod_ll = [](long long x, long long m) { long long r = x % m; return r < 0 ? r + m : r; };
+        FarMmaArgs fa{};
+        fa.kT = b.kT.p; fa.out = b.far.p + (size_t)half * b.fhalf; fa.ldk = b.ldk; fa.ntraj = ntraj; fa.ml = b.ml; fa.ncp = b.ncp;
+        fa.base = (int)fmod_ll(t0 - 1, b.ml); fa.d0 = 2 * TB; fa.dt = dt;
+        for (int sl = s0; sl <= s1; ++sl) {
+            const int n = b.slice0[sl + 1] - b.slice0[sl];
+            if (n <= 0) continue;
+            fa.segs = b.fsegs.p + (size_t)b.slice0[sl] * FM_SPC;
+            prof_begin(2);
+            k_tail_far_mma<2 * TB><<<n, (FM_W + 1) * 32, FM_SMEM, st>>>(b.ringmap, fa);
+            prof_end();
+            SCLMD_CUDA(cudaGetLastError());
+            ++launches;
+        }
+        return 0;
+    }
+    int far_mid(Bath &b, long long t0, int half) {
+        auto fmod_ll = [](long long x, long long m) { long long r = x % m; return r < 0 ? r + m : r; };
+        FarMmaArgs fa{};
+        fa.kT = b.kT.p; fa.out = b.far.p + (size_t)half * b.fhalf; fa.ldk = b.ldk; fa.ntraj = ntraj; fa.ml = b.ml; fa.ncp = b.ncp;
+        fa.base = (int)fmod_ll(t0 - 1, b.ml); fa.d0 = 0; fa.dt = dt; fa.segs = b.fmid.p;
+        prof_begin(2);
+        k_tail_far_mma<2 * TB><<<b.fnpairs, (FM_W + 1) * 32, FM_SMEM, st>>>(b.ringmap, fa);
+        prof_end();
+        SCLMD_CUDA(cudaGetLastError());
+        ++launches;
+        return 0;
+    }
+    // tensor-pipe far pass, one slice per step: see plan_far
+    int tail_step_mma(Bath &b, long long tt) {
+        auto fmod_ll = [](long long x, long long m) { long long r = x % m; return r < 0 ? r + m : r; };
+        if (!b.mma_ready) if (int e = prepare_mma(b)) return e;
+        const int tb = 2 * TB, s = (int)fmod_ll(tt, tb);
+        const long long t0 = tt - s, t1 = t0 + tb;
+        if (b.far_t0 != t0) {            // nothing usable for this block (first step, state or history just set): the whole pass now
+            if (int e = far_slices(b, t0, b.fcur, 0, FM_SLICES - 1)) return e;
+            if (int e = far_mid(b, t0, b.fcur)) return e;
+            b.far_t0 = t0;
+            b.nxt_block = -1;
+        }
+        prof_begin(3);
+        k_tail_near<<<ntraj, 256, 0, st>>>(b.ring.p, b.kern.p, b.far.p + (size_t)b.fcur * b.fhalf, b.tailp.p, ntraj, b.ml, b.ncp, (int)fmod_ll(tt, b.ml), s,
+                                           0, dt, tb, b.fnslot.p, b.fchunks);
+        prof_end();
+        SCLMD_CUDA(cudaGetLastError());
+        ++launches;
+        // the next block: its far-far ages are rows older than t0, all final -- slice s now (and any slices a late start has skipped);
+        // after the last step of the block its own 32 rows are in the ring too: mid pass, and the halves change roles
+        if (b.nxt_block != t1) {
+            b.nxt_block = t1;
+            b.nxt_done = 0;
+        }
+        if (b.nxt_done <= s) {
+            far_pending.push_back(FarPending{&b, t1, b.nxt_done, s});      // launched by flush_far() once every bath has queued its near pass
+            b.nxt_done = s + 1;
+        }
+        return 0;
+    }
+    // friction tail S'(tt) of step tt (ring already holds p_tt)
+    int tail_step(Bath &b, long long tt) {
         if (b.ml <= 1) return 0;
         auto fmod_ll = [](long long a, long long m) { long long r = a % m; return r < 0 ? r + m : r; };
         if (!(b.blocked && tail_block)) return tail_direct(b, (int)fmod_ll(tt, b.ml));
+        if (mma_ok(b)) return tail_step_mma(b, tt);
         const int tb = block_len(b);
         const long long t0 = tt - fmod_ll(tt, tb);
         const int T = ntraj >= 4 ? 4 : 1;
@@ -1891,32 +2076,8 @@ struct sclmd_md {
             const int ntiles = cdiv(b.ncp, 256), ct = cdiv(b.ncp, ntiles);
             const int aps = round_up(cdiv(b.ml, b.far_nsplit), tb);
             dim3 grid(cdiv(ntraj, T), b.far_nsplit, ntiles);
-            const bool mma = mma_ok(b);
-            if (mma && !b.mma_ready) if (int e = prepare_mma(b)) return e;
             prof_begin(2);
-            if (mma) {
-                // CTA = 32 dofs x 8 trajectories x an age range; neighbouring CTAs (x) read neighbouring pieces of the same ring rows
-                const int chunks = cdiv(b.ncp, FM_DC), groups = cdiv(ntraj, 8);
-                // age splits: enough CTAs to fill the machine, and among 1..4 the count whose last wave is fullest (config 5: 1280 CTAs
-                // are 8.65 waves on 148 SMs, a 9th wave at 65 %; three splits are 25.95 waves)
-                int ns = std::max(1, std::min(b.far_cap, cdiv(4 * nsm, chunks * groups)));
-                {
-                    double best = 1e30;
-                    int pick = ns;
-                    for (int cand = ns; cand <= std::min(b.far_cap, std::max(ns, 4)); ++cand) {
-                        const double wv = (double)chunks * groups * cand / nsm, loss = std::ceil(wv) / wv;
-                        if (loss < best - 0.01) { best = loss; pick = cand; }
-                    }
-                    ns = pick;
-                }
-                const int apm = round_up(cdiv(b.ml, ns), FM_SR);
-                ns = cdiv(b.ml, apm);
-                b.far_used = ns;
-                FarMmaArgs fa{};
-                fa.kT = b.kT.p; fa.out = b.far.p; fa.ldk = b.ldk; fa.ntraj = ntraj; fa.ml = b.ml; fa.ncp = b.ncp; fa.base = base;
-                fa.ages_per_split = apm; fa.dt = dt;
-                k_tail_far_mma<2 * TB><<<dim3(chunks, groups, ns), (FM_W + 1) * 32, FM_SMEM, st>>>(b.ringmap, fa);
-            } else if (tb == 2 * TB) {
+            if (tb == 2 * TB) {
                 auto kern = k_tail_far_wsx<1, 2 * TB, 4, 20, 36>;
                 static bool cfg = false;
                 if (!cfg) {
@@ -1949,10 +2110,9 @@ struct sclmd_md {
             b.far_t0 = t0;
             ++launches;
         }
-        if (!near) return 0;
         prof_begin(3);
         k_tail_near<<<ntraj, 256, 0, st>>>(b.ring.p, b.kern.p, b.far.p, b.tailp.p, ntraj, b.ml, b.ncp, (int)fmod_ll(tt, b.ml), (int)(tt - t0),
-                                           mma_ok(b) ? b.far_used : b.far_nsplit, dt, tb);
+                                           b.far_nsplit, dt, tb, nullptr, 0);
         prof_end();
         SCLMD_CUDA(cudaGetLastError());
         ++launches;
@@ -2186,7 +2346,7 @@ struct sclmd_md {
         obs_slab = t % nmd;
         ++launches;
         dt_synced = false;
-        for (auto &b : baths) if (int e = tail_step(*b, t)) return e;
+        { for (auto &b : baths) if (int e = tail_step(*b, t)) return e; if (int e = flush_far()) return e; }
         const size_t w = nph * sizeof(double);
         SCLMD_CUDA(cudaMemcpy2DAsync(q_trial, w, qn.p, ld * sizeof(double), w, ntraj, cudaMemcpyDeviceToHost, st));
         SCLMD_CUDA(cudaStreamSynchronize(st));
@@ -2316,18 +2476,6 @@ struct sclmd_md {
         a.ncs = ncs; a.ntraj = ntraj; a.nmd = nmd; a.pending = pending; a.doA = doA; a.gsplit = gaplan.nsplit;
         a.t = t; a.dt = dt;
         a.pc = mpc.p; a.fA = mfA.p; a.g = mg.p; a.sbuf = msb.p; a.ecorr = mec.p; a.gn = mgn.p;
-        // time-blocked baths: the kernel sums the near part of S'(t-1) itself (at most block_len fresh ring rows per element, L2 hits)
-        // on top of the far tails of the block of t-1, which must be current -- they are, unless the state was just set
-        auto fmod_ll = [](long long x, long long m) { long long r = x % m; return r < 0 ? r + m : r; };
-        for (size_t i = 0; i < baths.size(); ++i) {
-            Bath &b = *baths[i];
-            if (!(fuse_near && b.ml > 1 && b.blocked && tail_block)) continue;
-            if (int e = tail_step(b, t - 1, false)) return e;
-            const int tb = block_len(b);
-            NearSpec &ns = a.near[i];
-            ns.on = 1; ns.kern = b.kern.p; ns.far = b.far.p; ns.tb = tb; ns.nsplit = mma_ok(b) ? b.far_used : b.far_nsplit;
-            ns.head = (int)fmod_ll(t - 1, b.ml); ns.s = (int)fmod_ll(t - 1, tb);
-        }
         prof_begin(6);
         // two or three elements per thread: the dependent loads of an element (state, K.q slices, noise row, tail) are the whole cost
         static const int bath_thr = getenv("SCLMD_BATH_THREADS") ? atoi(getenv("SCLMD_BATH_THREADS")) : 256;      // 1024 CTAs in ONE wave (8 per SM); ncu: 16.3 us against 24.4 (320) and 18.8 (192)
@@ -2390,9 +2538,6 @@ struct sclmd_md {
         g_valid = false;
         d_valid = false;
         bc_pending = false;
-        if (fuse_near)               // the real-space kernels read S'(t-1) from tailp, which the eigenbasis steps did not keep up to date
-            for (auto &b : baths)
-                if (b->ml > 1 && b->blocked && tail_block) if (int e = tail_step(*b, t - 1)) return e;
         return 0;
     }
     int sync_real() {         // whatever mode the state is in: finish pending evaluations and make q, p current
@@ -2421,7 +2566,7 @@ struct sclmd_md {
         obs_slab = t % nmd;
         if (int e = gemm_nt(ntraj, ncs, ld, mQ[mqi ^ 1].p, ld, mEL.p, ld, mgn.p, ncs, gaplan, 5, ms)) return e;
         if (overlap) SCLMD_CUDA(cudaEventRecord(evG, st2));
-        for (auto &b : baths) if (int e = tail_step(*b, t, !(fuse_near && b->blocked && tail_block))) return e;     // far tails at a block start; near part: next k_modal_bath
+        { for (auto &b : baths) if (int e = tail_step(*b, t)) return e; if (int e = flush_far()) return e; }
         if (overlap) SCLMD_CUDA(cudaStreamWaitEvent(st, evG, 0));
         if (defer_wait) {
             SCLMD_CUDA(cudaStreamWaitEvent(st, evN, 0));
@@ -2525,10 +2670,10 @@ struct sclmd_md {
             SCLMD_CUDA(cudaStreamWaitEvent(st2, evA, 0));
             if (int e = potforce(qn.p, Gn.p, st2)) return e;
             SCLMD_CUDA(cudaEventRecord(evG, st2));
-            for (auto &b : baths) if (int e = tail_step(*b, t)) return e;
+            { for (auto &b : baths) if (int e = tail_step(*b, t)) return e; if (int e = flush_far()) return e; }
             SCLMD_CUDA(cudaStreamWaitEvent(st, evG, 0));
         } else {
-            for (auto &b : baths) if (int e = tail_step(*b, t)) return e;
+            { for (auto &b : baths) if (int e = tail_step(*b, t)) return e; if (int e = flush_far()) return e; }
             if (int e = potforce(qn.p, Gn.p)) return e;
         }
         if (lazy_ok(lin)) {       // B, C stay pending: fused with the next step's evaluation A, or run by flush()
@@ -2578,7 +2723,6 @@ int sclmd_md_create(int nph, int ntraj, double dt, int nmd, int device, sclmd_md
     h->fuse_bca = getenv("SCLMD_NO_FUSE") == nullptr;
     h->use_ens = getenv("SCLMD_NO_ENS") == nullptr;
     h->far_mma = getenv("SCLMD_NO_FAR_MMA") == nullptr;
-    h->fuse_near = getenv("SCLMD_FUSE_NEAR") != nullptr;
     SCLMD_CUDA(h->phalf.alloc(n)); SCLMD_CUDA(h->p1.alloc(n)); SCLMD_CUDA(h->qn.alloc(n));
     SCLMD_CUDA(h->etot.alloc((size_t)nmd * ntraj));
     SCLMD_CUDA(h->cons.alloc(nph));
@@ -2855,6 +2999,8 @@ int sclmd_md_set_history(sclmd_md *h, int bath, const double *phis) {
     if (b.ml > 1) {
         b.far_t0 = -1;
         if (int e = h->tail_step(b, h->t - 1)) return e;
+    if (int e = h->flush_far()) return e;
+        if (int e = h->flush_far()) return e;
         SCLMD_CUDA(cudaStreamSynchronize(h->st));
     }
     return SCLMD_OK;
@@ -2874,6 +3020,7 @@ int sclmd_md_set_tail_block(sclmd_md *h, int on) {
     for (auto &b : h->baths) {   // the partial-tail layout differs between the modes: rebuild S'(t-1)
         b->far_t0 = -1;
         if (b->ml > 1) if (int e = h->tail_step(*b, h->t - 1)) return e;
+        if (int e = h->flush_far()) return e;
     }
     SCLMD_CUDA(cudaStreamSynchronize(h->st));
     return SCLMD_OK;
@@ -3302,6 +3449,7 @@ int sclmd_md_time_tail(sclmd_md *h, int bath, int reps, float *avg_ms) {
     *avg_ms = ms / reps;
     b.far_t0 = -1;   // restore the tail in the handle's own mode
     if (int e = h->tail_step(b, h->t - 1)) return e;
+    if (int e = h->flush_far()) return e;
     SCLMD_CUDA(cudaStreamSynchronize(h->st));
     return SCLMD_OK;
 }

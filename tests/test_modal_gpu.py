@@ -241,41 +241,6 @@ def test_config5_shape_full_size_modal_vs_oracle():
     e.close()
 
 
-def test_near_tails_inside_the_bath_kernel_equal_the_separate_near_pass(monkeypatch):
-    """SCLMD_FUSE_NEAR=1 (read at handle creation; off by default, measured slower at config 5): the eigenbasis step sums the near part of
-    the time-blocked tails inside k_modal_bath instead of launching k_tail_near -- the same expression in the same order.  Both handles
-    against the oracle and against each other, across block boundaries, a mid-run read (leaves and re-enters the eigenbasis, which
-    rebuilds the partial tails the real-space kernels read) and a tail-mode switch."""
-    natoms, ntraj, nmd, dt = 50, 6, 256, 0.3
-    baths = [(list(range(3, 23)), 200), (list(range(120, 141)), 136)]
-    a, ens = build(natoms, baths, ntraj, nmd, dt, seed=12, modal=True)
-    monkeypatch.setenv("SCLMD_FUSE_NEAR", "1")
-    b, _ = build(natoms, baths, ntraj, nmd, dt, seed=12, modal=True)
-    monkeypatch.delenv("SCLMD_FUSE_NEAR")
-    assert a.modal_active() and b.modal_active()
-    done = 0
-    for chunk in (33, 70, 1, 31):
-        ens.run(chunk)
-        done += chunk
-        for e in (a, b):
-            e.run(chunk)
-        check_state(a, ens, done)
-        check_state(b, ens, done)
-    assert a.launch_count() > b.launch_count()                       # no k_tail_near launches in the fused handle
-    for e in (a, b):
-        e.set_tail_block(5)                                          # 16-step blocks from here on
-        e.run_async(45)
-    ens.run(45)
-    qa, pa, _ = a.get_state()
-    qb, pb, _ = b.get_state()
-    assert relerr(qa, qb) < 1e-13 and relerr(pa, pb) < 1e-13
-    check_state(b, ens, done + 45)
-    for i in range(2):
-        assert relerr(b.current(i), ens.baths[i]["cur"]) < 1e-8
-    a.close()
-    b.close()
-
-
 def test_eigenbasis_step_on_one_stream_equals_the_two_stream_step():
     """sclmd_md_set_overlap(h, 0): the products, the modal update and the tail kernels of the eigenbasis step all on the handle's stream
     (A/B switch: measured 0.567 against 0.534 ms per step at config 5, the near passes are hidden beside the products otherwise)"""
