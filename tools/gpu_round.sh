@@ -24,7 +24,7 @@ $B > $o/${tag}_plain.log 2>&1 &&
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'dgemm_tma_kernel|k_modal|k_tail_near' -s 40 -c 6 -f -o $o/${tag}_step $B > $o/${tag}_ncu_step.log 2>&1
 export_rep ${tag}_step
 $B > $o/${tag}_plain.log 2>&1 &&
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_tail_far_mma" -s 2 -c 1 -f -o $o/${tag}_far $B > $o/${tag}_ncu_far.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_tail_far_mma" -s 70 -c 2 -f -o $o/${tag}_far $B > $o/${tag}_ncu_far.log 2>&1
 export_rep ${tag}_far
 N="python tools/probe_noise.py 256 300 8192"
 $N > $o/${tag}_plain_noise.log 2>&1 &&
