@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary workloads (C2 MD, NEGF)")
     ap.add_argument("--no-overlap", action="store_true", help="run the K.q GEMM on the same stream as the history-tail kernels (A/B measurement)")
-    ap.add_argument("--tail-block", type=int, default=1, help="1: time-blocked history tails (default); 0: direct, one ring pass per step")
+    ap.add_argument("--tail-block", type=int, default=1, help="1: time-blocked history tails, tensor-pipe far pass spread over the steps (default); 0: direct, one ring pass per step; 2-5: earlier far-pass kernels (A/B)")
     ap.add_argument("--no-modal", action="store_true", help="propagate in real space (K.q GEMM every step) instead of the eigenbasis of md.setDyn (A/B measurement)")
     return ap.parse_args()
 
@@ -620,7 +620,7 @@ def main():
             "gpu_launches": launches_total, "roofline": roof, "wall_ms_timed_region": wall_ms, "allreduce_ms": ar_ms,
             "heat_current_mean": [float(sums[b] / sums[2] / w["nmd"]) for b in range(2)],
             "noise_generation_s": noise_gen_s, "noise": getattr(fill_noise, "report", None), "fp64_probe_tflops": probe, "also": also,
-            "tail_mode": "time-blocked (ring streamed once per 32 steps, tensor-pipe far pass)" if args.tail_block == 1 else ("time-blocked, other kernel (--tail-block %d)" % args.tail_block if args.tail_block else "direct (ring streamed every step)"),
+            "tail_mode": "time-blocked (ring streamed once per 32 steps by the tensor-pipe far pass, one slice per step)" if args.tail_block == 1 else ("time-blocked, other kernel (--tail-block %d)" % args.tail_block if args.tail_block else "direct (ring streamed every step)"),
             "propagation": ("eigenbasis of md.setDyn (sclmd_md_set_modes): diagonal harmonic force, gather + scatter products over the bath dofs"
                             if modal else "real space: K.q GEMM every step")}
 

@@ -158,9 +158,14 @@ int sclmd_md_set_force_output(sclmd_md *h, int on);
 int sclmd_md_get_force(sclmd_md *h, double *f);
 int sclmd_md_get_bath_force(sclmd_md *h, int bath, int evaluation, double *fb);
 
-/* 1 (default): diagonal-kernel baths with ml >= 128 stream their history ring from HBM once per 16 steps
- * (time-blocked far/near tails, same flops, same results to rounding); 0: one full ring pass per step -- the
- * direct single-tail algorithm on which the HBM roofline of SURVEY.md section 8d is defined */
+/* How diagonal-kernel baths with ml >= 128 contract their history (same flops, same results to rounding in every mode):
+ *   1 (default) time-blocked far/near tails over 32-step blocks: the ring is read from HBM once per 32 steps by the tensor-pipe
+ *               far pass (Hankel x history products on DMMA.8x8x4, needs ml % 8 == 0, else mode 5), the pass of the next block
+ *               worked off one slice per step so that every step costs the same;
+ *   0           one full ring pass per step -- the direct single-tail algorithm on which the HBM roofline of SURVEY.md
+ *               section 8d is defined;
+ *   2, 3, 4, 5  earlier far-pass kernels kept for A/B measurements (plain loads; two-stage bulk copies; 32-step DFMA blocks;
+ *               16-step DFMA blocks with a producer warp = the round-1 default). */
 int sclmd_md_set_tail_block(sclmd_md *h, int on);
 /* ms[4], n[4] since profiling was switched on: 0 direct tail, 1 potential force, 2 far pass, 3 near pass */
 int sclmd_md_get_profile_all(sclmd_md *h, double *ms, int64_t *n);
