@@ -409,7 +409,11 @@ def main():
     # Per-kernel CUDA events (the roofline block) are recorded inside the timed region when the step is a launch chain anyway
     # (baths with history tails).  A step without tails replays a CUDA graph, which per-kernel events would switch off: there
     # the timed region runs unprofiled and the same K steps are repeated once with events for the roofline block.
-    prof_in_region = w["ml"] > 1
+    # The eigenbasis step runs its products on a second stream beside the history-tail kernels: event pairs would then also contain the
+    # time a kernel waits for SMs that a kernel of the other stream holds (none of them co-reside).  That case is timed unprofiled as
+    # well, and the roofline block comes from a repeat of the same K steps on ONE stream, where an event pair brackets exactly one kernel.
+    modal_two_streams = w["ml"] > 1 and eng.modal_active() and not args.no_overlap
+    prof_in_region = w["ml"] > 1 and not modal_two_streams
     if prof_in_region:
         eng.set_profiling(True)
     l0 = eng.launch_count()
@@ -433,8 +437,12 @@ def main():
     launches = eng.launch_count() - l0
     ms_prof = ms
     if not prof_in_region:
+        if modal_two_streams:
+            eng.set_overlap(False)
         eng.set_profiling(True)
         ms_prof = eng.run(K)
+        if modal_two_streams:
+            eng.set_overlap(True)
     prof_all = eng.profile_ex()
     modal = eng.modal_active()
     eng.set_profiling(False)
@@ -554,8 +562,8 @@ def main():
                           "bound": "tensor",
                           "achieved": far_fl_region / (far_ms * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
                           "frac": far_fl_region / (far_ms * 1e-3) / 1e12 / fp64_peak,
-                          "traffic": (traffic or {}).get("far_mma_dram_bytes_per_launch"),
-                          "traffic_note": "ncu figure of a whole pass (32 slices), captured before the pass was cut into slices",
+                          "traffic": 2.0 * (traffic or {}).get("far_slice_dram_bytes_per_launch_one_bath", 0.0) or None,
+                          "traffic_note": "2 x the ncu DRAM bytes of a one-bath slice (profiles/r02J_far_ncu_raw.csv); a launch carries one slice of each bath",
                           "peak_source": "measured live: FP64 DMMA.8x8x4 chain probe (sclmd_probe_fp64)",
                           "algorithmic_flops_per_launch": far_fl_region / max(1, nlaunch), "algorithmic_bytes_per_launch": 2.0 * alg_ring * K / 32.0 / max(1, nlaunch),
                           "avg_launch_ms": far_ms / max(1, nlaunch), "launches_timed": nlaunch, "ms_per_step": far_ms / K,
@@ -605,12 +613,14 @@ def main():
             kq_alone["share_of_step_serialised"] = kq_alone["avg_launch_ms"] * K / ms     # what an ncu launch list (serialised kernels) shows
         roof["kq_gemm_standalone"] = kq_alone
         roof["profiled_pass"] = ("the timed region itself" if prof_in_region else
+                                 ("a repeat of the same K steps on one stream with an event pair per launch (%.4f ms per step: exclusive kernel times, "
+                                  "the near passes are not hidden beside the products; the timed region runs the same kernels on two streams)" % (ms_prof / K))
+                                 if modal_two_streams else
                                  "a repeat of the same K steps with per-kernel events (%.4f ms per step; the timed region replays CUDA graphs)" % (ms_prof / K))
-        roof["note"] = ("per-kernel times are CUDA-event pairs around every launch inside the timed region, on the stream of the launch; the "
-                        "products run on a second stream, so event intervals of kernels queued on different streams can overlap and the "
-                        "shares may add up to more than 1 (the serialised ncu launch list under profiles/ gives the exclusive times: "
-                        "a step is the sum of its kernels, none of them co-reside on an SM); kq_gemm_standalone is the real-space K.q "
-                        "product timed alone")
+        roof["note"] = ("per-kernel times are CUDA-event pairs around every launch of the profiled pass, on the stream of the launch (see "
+                        "profiled_pass); share_of_step is relative to that pass and is the figure to compare with the serialised ncu launch "
+                        "list under profiles/ (a step is the sum of its kernels, none of them co-reside on an SM); kq_gemm_standalone is "
+                        "the real-space K.q product timed alone")
     line = {"metric": "qtb_md_trajectory_steps_per_s", "value": value, "unit": "trajectory-steps/s", "n_gpus": world,
             "steps": K, "warmup": W, "warmup_run": W_aligned, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, w, ntraj * world),
@@ -650,7 +660,7 @@ def main():
         roof["noise_samples_per_s"] = nz.get("samples_per_s_device")
         roof["noise_frac_of_hbm_roofline"] = nz.get("frac_of_hbm_roofline_16B_per_sample")
         roof["whole_step_frac_of_fp64_peak"] = (roof.get("whole_step") or {}).get("frac_of_fp64_peak")
-        roof["traffic_source"] = "stored ncu --set full capture (profiles/r02_tail_traffic.json <- profiles/r02s_far_ncu_raw.csv), not measured in this run"
+        roof["traffic_source"] = "stored ncu --set full capture (profiles/r02_tail_traffic.json <- profiles/r02J_far_ncu_raw.csv), not measured in this run"
 
     # ---------------- BASELINE configs[1] shape (603-dof junction of the example, ml = 1 baths, fixed ends, 1024 trajectories)
     if world == 1 and not args.no_also and args.workload != "c2":
