@@ -11,10 +11,13 @@
 //   2s+1 (A and B agree, so the contraction is merely reordered).  Fragment row j reads tile row pi(j) = (j >> 1) | ((j & 1) << 2)
 //   of its 8-row group: the eight lanes of a quarter-warp then touch rows with swizzle keys r and r ^ 4, i.e. all eight 16-byte
 //   chunks of a 128-byte line -- no bank conflict.  The same permutation maps accumulator rows / columns back on the way out.
-// * Stream-K: the grid is one CTA per SM (cooperative launch: all CTAs resident); the iteration space (tiles x K-slabs) is cut into equal contiguous ranges, so there is
-//   no wave quantisation and no split-K partial C in HBM.  A CTA whose range starts inside a tile stores that partial
-//   accumulator tile to a small workspace right away and raises a flag; the CTA that holds the head of the tile adds the
-//   partials in CTA order (deterministic) and writes C once.
+// * Stream-K: the grid is one CTA per SM; the iteration space (tiles x K-slabs) is cut into equal contiguous ranges, so there is
+//   no wave quantisation and no split-K partial C in HBM.  A CTA works through its range from the LAST tile to the first: the piece
+//   of a tile that does not reach the tile's end is stored to a small workspace right away (at most one per CTA) and a flag is
+//   raised; the CTA that holds the END of the tile -- its first tile, which it does last -- adds the partials of the earlier pieces
+//   in descending CTA order (deterministic) and writes C once.  A CTA therefore waits only for CTAs with a LOWER logical index, and
+//   the logical index is a ticket drawn when the CTA starts: every CTA that is waited for is already running, so the kernel needs no
+//   co-residency guarantee (plain launch: its CTAs start as SMs become free; a cooperative launch cost 1.9 % of the config-5 step).
 //
 // Operands are described as rank-3 tensors so that one kernel covers plain products (K.q, the eigenbasis gather / scatter),
 // frequency-batched products (noise x = L xi) and contractions over a rotating history ring (full memory-kernel tails).
@@ -40,6 +43,8 @@ struct TmaGemmParams {
     double *ws;               // [gridDim.x][BM * BN] partial accumulator tiles (stream-K fix-up)
     unsigned *flags;          // [gridDim.x]
     unsigned epoch;
+    unsigned *ticket;         // [2]: CTAs started / CTAs finished in this launch; the last CTA to finish sets both back to zero, so the
+                              // scheme survives CUDA-graph replays (nothing launch-specific is baked into the arguments)
 };
 
 #ifdef __CUDACC__
@@ -96,19 +101,23 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    __shared__ unsigned s_bid;
+    if (tid == 0) s_bid = atomicAdd(p.ticket, 1u);                          // logical index in the order in which the CTAs start
     __syncthreads();
+    const unsigned bid = s_bid;
     const long long total = (long long)p.ntiles * p.KI;
-    const long long beg = total * blockIdx.x / gridDim.x, end = total * (blockIdx.x + 1) / gridDim.x;
+    const long long beg = total * bid / gridDim.x, end = total * (bid + 1) / gridDim.x;
     const int per_z = p.mt * p.nt;
 
     if (warp >= NW) {   // ------------------------------------------------ producer warpgroup: one lane feeds the ring of stages
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         if (warp == NW && lane == 0) {
-            long long it = beg;
+            long long hi = end;
             unsigned fill = 0;
-            while (it < end) {
-                const int tile = (int)(it / p.KI), kbeg = (int)(it % p.KI);
-                const int kend = (int)min((long long)p.KI, kbeg + (end - it));
+            while (hi > beg) {                                   // pieces of the range, last tile first
+                const int tile = (int)((hi - 1) / p.KI);
+                const long long tstart = (long long)tile * p.KI, lo = max(beg, tstart);
+                const int kbeg = (int)(lo - tstart), kend = (int)(hi - tstart);
                 const int z = tile / per_z, rem = tile % per_z;
                 const int m0 = (rem % p.mt) * BM, n0 = (rem / p.mt) * BN;
                 for (int kk = kbeg; kk < kend; ++kk, ++fill) {
@@ -128,7 +137,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     tma_load_3d(dst, &mapA, &full[st], k0, a1, a2);
                     tma_load_3d(dst + BM * 128, &mapB, &full[st], k0, n0, b2);
                 }
-                it += kend - kbeg;
+                hi = lo;
             }
         }
         return;
@@ -142,11 +151,12 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const int ch0 = ((fcol) ^ pr) * 16, ch1 = ((4 + fcol) ^ pr) * 16;   // swizzled byte offsets of this lane's two 16-byte chunks
     const int arow = (wm + pr) * 128, brow = (wn + pr) * 128;
     double acc[FM][FN][2];
-    long long it = beg;
+    long long hi = end;
     unsigned use = 0;
-    while (it < end) {
-        const int tile = (int)(it / p.KI), kbeg = (int)(it % p.KI);
-        const int kend = (int)min((long long)p.KI, kbeg + (end - it));
+    while (hi > beg) {
+        const int tile = (int)((hi - 1) / p.KI);
+        const long long tstart = (long long)tile * p.KI, lo = max(beg, tstart);
+        const int kbeg = (int)(lo - tstart), kend = (int)(hi - tstart);
 #pragma unroll
         for (int i = 0; i < FM; ++i)
 #pragma unroll
@@ -173,9 +183,10 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             __syncwarp();
             if (lane == 0) tma_mbar_arrive(&empty[st]);
         }
-        if (kbeg != 0) {
-            // this range started inside the tile: hand the partial accumulators to the CTA that holds the head of the tile
-            double *w = p.ws + (size_t)blockIdx.x * (BM * BN) + tid;
+        if (kend < p.KI) {
+            // this piece does not reach the end of the tile (it is the last tile of the range, done first): hand the partial
+            // accumulators to the CTA that holds the end of the tile
+            double *w = p.ws + (size_t)bid * (BM * BN) + tid;
 #pragma unroll
             for (int i = 0; i < FM; ++i)
 #pragma unroll
@@ -185,11 +196,10 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 }
             __threadfence();
             consumer_sync(CT);
-            if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.flags + blockIdx.x), "r"(p.epoch) : "memory");
+            if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.flags + bid), "r"(p.epoch) : "memory");
         } else {
-            if (kend < p.KI) {   // the rest of the tile lives in the following CTAs: add their partials in CTA order
-                const long long tile_end = (long long)(tile + 1) * p.KI;
-                for (int cc = blockIdx.x + 1; cc < (int)gridDim.x && total * cc / gridDim.x < tile_end; ++cc) {
+            if (kbeg > 0) {      // the start of the tile lives in the preceding CTAs (they did it first): add their partials, nearest first
+                for (int cc = (int)bid - 1; cc >= 0 && total * (cc + 1) / gridDim.x > tstart; --cc) {
                     if (tid == 0) {
                         unsigned v;
                         do {
@@ -224,7 +234,14 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 }
             }
         }
-        it += kend - kbeg;
+        hi = lo;
+    }
+    consumer_sync(CT);
+    if (tid == 0 && atomicAdd(p.ticket + 1, 1u) == gridDim.x - 1) {             // last CTA out: counters and flags ready for the next launch on
+        for (unsigned i = 0; i < gridDim.x; ++i) p.flags[i] = 0;                 // this workspace (also when a CUDA graph replays this very launch)
+        p.ticket[0] = 0;
+        p.ticket[1] = 0;
+        __threadfence();
     }
 }
 
@@ -271,7 +288,7 @@ inline int tma_make_map(CUtensorMap *map, const TmaOperand &o) {
 // per-stream scratch of the stream-K fix-up (launches that share it must be ordered on one stream)
 struct TmaWorkspace {
     DevBuf<double> ws;
-    DevBuf<unsigned> flags;
+    DevBuf<unsigned> flags, ticket;
     unsigned epoch = 0;
     int grid = 0;
 };
@@ -319,6 +336,7 @@ inline int launch_dgemm_tma_bn(const TmaGemm &g, TmaWorkspace &w, int nsm, cudaS
     if (w.grid != nsm) {
         SCLMD_CUDA(w.ws.alloc((size_t)nsm * TMA_BM * TMA_BN_MAX));
         SCLMD_CUDA(w.flags.alloc(nsm));
+        SCLMD_CUDA(w.ticket.alloc(2));
         w.grid = nsm;
         w.epoch = 0;
     }
@@ -333,19 +351,12 @@ inline int launch_dgemm_tma_bn(const TmaGemm &g, TmaWorkspace &w, int nsm, cudaS
     p.kslabs = cdiv(g.K, Cfg::BK); p.KI = g.nseg * p.kslabs;
     p.a_mode = g.a_mode; p.a_head = g.a_head; p.a_mod = g.a_mod; p.b_mode = g.b_mode; p.b_seg0 = g.b_seg0;
     p.C = g.C; p.ldc = g.ldc; p.c_batch_stride = g.c_batch_stride; p.alpha = g.alpha;
-    p.ws = w.ws.p; p.flags = w.flags.p; p.epoch = ++w.epoch;
+    p.ws = w.ws.p; p.flags = w.flags.p; p.epoch = 1; ++w.epoch;
     const long long total = (long long)p.ntiles * p.KI;
     const int grid = (int)std::max<long long>(1, std::min<long long>(nsm, total));
-    // CTAs of this grid wait on one another (stream-K fix-up): a cooperative launch guarantees that they are all resident.  (Inside a
-    // stream capture the plain launch is used; one CTA per SM is resident then as well.)
-    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    cudaStreamIsCapturing(st, &cap);
-    if (cap == cudaStreamCaptureStatusNone) {
-        void *args[] = {(void *)&mA, (void *)&mB, (void *)&p};
-        cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(Cfg::THREADS), args, Cfg::SMEM, st);
-    } else {
-        kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(mA, mB, p);
-    }
+    // CTAs of this grid wait on one another (stream-K fix-up), but only on CTAs that drew an earlier ticket: a plain launch is enough
+    p.ticket = w.ticket.p;
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(mA, mB, p);
     const cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) {
         set_error("dgemm_tma_kernel launch failed: %s", cudaGetErrorString(ce));

@@ -1899,7 +1899,8 @@ struct sclmd_md {
         const int na = (b.ml - 2 * TB) / FM_SR;                     // far-far stages per pair
         const long long total = (long long)groups * na;
         const long long per_slice = std::max<long long>(1, (total + FM_SLICES - 1) / FM_SLICES);
-        const int items = std::max(1, nsm / chunks);                 // work items of a slice: about one CTA per SM
+        static const int items_add = getenv("SCLMD_FAR_ITEMS_ADD") ? atoi(getenv("SCLMD_FAR_ITEMS_ADD")) : 0;      // A/B switch
+        const int items = std::max(1, nsm / chunks + items_add);     // work items of a slice: about one CTA per SM
         const long long per_item = std::max<long long>(8, (per_slice + items - 1) / items);
         std::vector<FarSeg> segs;
         std::vector<int> cnt(npairs, 0);
