@@ -311,15 +311,18 @@ struct TmaGemm {
     double alpha;
 };
 
-// tile width: 2 x 4 consumer warps of 64 x (BN / 4); the width that pads N least wins (ties: the wider tile, more operand reuse).
-// nc = 300 (config 5): 2 tiles of 160 (6 % padding) instead of 3 of 128 (22 %)
+// tile width: 2 x 4 consumer warps of 64 x (BN / 4); the width that pads N least wins.
+// nc = 300 (config 5): 320 columns (6 % padding) as 5 tiles of 64 or 2 of 160, instead of 3 of 128 (22 %)
 inline int tma_pick_bn(int N) {
     const int cand[4] = {160, 128, 96, 64};
     int best = 128;
     long long best_pad = -1;
+    // ties go to the narrower tile: with stream-K a narrow tile is split over fewer CTAs (smaller, fewer partial tiles at the end) and the
+    // 64-wide configuration runs the main loop as well as the wide ones (config-5 gather product 0.141 -> 0.125 ms; SCLMD_TMA_TIE_WIDE=1: A/B)
+    static const bool narrow = getenv("SCLMD_TMA_TIE_WIDE") == nullptr;
     for (int c : cand) {
         const long long padded = (long long)cdiv(N, c) * c;
-        if (best_pad < 0 || padded < best_pad) { best_pad = padded; best = c; }
+        if (best_pad < 0 || padded < best_pad || (narrow && padded == best_pad)) { best_pad = padded; best = c; }
     }
     return best;
 }
