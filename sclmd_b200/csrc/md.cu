@@ -1899,8 +1899,15 @@ struct sclmd_md {
         const int na = (b.ml - 2 * TB) / FM_SR;                     // far-far stages per pair
         const long long total = (long long)groups * na;
         const long long per_slice = std::max<long long>(1, (total + FM_SLICES - 1) / FM_SLICES);
-        static const int items_add = getenv("SCLMD_FAR_ITEMS_ADD") ? atoi(getenv("SCLMD_FAR_ITEMS_ADD")) : 0;      // A/B switch
-        const int items = std::max(1, nsm / chunks + items_add);     // work items of a slice: about one CTA per SM
+        // work items of a slice: about one CTA per SM.  The slices of two baths share a launch: when nsm / chunks leaves SMs over, every
+        // second bath takes one item more, so that the two grids together come closer to two full waves (config 5: 150 + 140 CTAs on
+        // 2 x 148 SMs instead of 140 + 140)
+        size_t bidx = 0;
+        for (size_t i = 0; i < baths.size(); ++i) if (baths[i].get() == &b) bidx = i;
+        static const int items_alt = getenv("SCLMD_FAR_ITEMS_ALT") ? atoi(getenv("SCLMD_FAR_ITEMS_ALT")) : 1;      // A/B switch
+        const int base_items = std::max(1, nsm / chunks);
+        const bool spare = 2 * nsm - (2 * base_items + 1) * chunks >= 0;
+        const int items = base_items + ((items_alt && spare && bidx % 2 == 0 && baths.size() > 1) ? 1 : 0);
         const long long per_item = std::max<long long>(8, (per_slice + items - 1) / items);
         std::vector<FarSeg> segs;
         std::vector<int> cnt(npairs, 0);
