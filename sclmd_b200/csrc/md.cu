@@ -74,7 +74,7 @@ struct Bath {
     DevBuf<FarSeg> fsegs, fmid;
     DevBuf<int> fnslot;
     std::vector<int> slice0;          // first CTA of slice i in fsegs (FM_SLICES + 1 entries)
-    int fchunks = 0, fnpairs = 0, fslots = 0, fcur = 0;
+    int fchunks = 0, fnpairs = 0, fslots = 0, fcur = 0, fnmid = 0;
     size_t fhalf = 0;                 // doubles per half: fslots * 2 TB * ntraj * ncp
     long long nxt_block = -1;         // block start the other half is being filled for, and how many of its slices are done
     int nxt_done = 0;
@@ -1939,14 +1939,21 @@ struct sclmd_md {
         // mid pass: ages 0..31, one CTA per pair (chunks side by side), slot right behind the pair's far-far slots
         std::vector<FarSeg> mid;
         int maxslot = 0;
-        for (int gr = 0; gr < groups; ++gr)
-            for (int ch = 0; ch < chunks; ++ch) {
-                const int pid = gr * chunks + ch;
-                mid.push_back(FarSeg{ch * FM_DC, gr * 8, 0, 2 * TB / FM_SR, cnt[pid]++, nlive_of(ch)});
-                for (int k = 1; k < FM_SPC; ++k) mid.push_back(FarSeg{0, 0, 0, 0, 0, nlive_of(ch)});
-                maxslot = std::max(maxslot, cnt[pid]);
+        int nmid = 0;
+        for (int gr = 0; gr < groups; gr += FM_SPC)                   // FM_SPC groups of one chunk per CTA: four stages each, so the fixed
+            for (int ch = 0; ch < chunks; ++ch) {                      // cost of a CTA (pipeline fill, epilogue) is shared
+                for (int k = 0; k < FM_SPC; ++k) {
+                    if (gr + k < groups) {
+                        const int pid = (gr + k) * chunks + ch;
+                        mid.push_back(FarSeg{ch * FM_DC, (gr + k) * 8, 0, 2 * TB / FM_SR, cnt[pid]++, nlive_of(ch)});
+                        maxslot = std::max(maxslot, cnt[pid]);
+                    } else {
+                        mid.push_back(FarSeg{0, 0, 0, 0, 0, nlive_of(ch)});
+                    }
+                }
+                ++nmid;
             }
-        b.fchunks = chunks; b.fnpairs = npairs; b.fslots = maxslot;
+        b.fchunks = chunks; b.fnpairs = npairs; b.fslots = maxslot; b.fnmid = nmid;
         b.fhalf = (size_t)maxslot * 2 * TB * ntraj * b.ncp;
         if (segs.empty()) segs.push_back(FarSeg{0, 0, 0, 0, 0, FM_W});
         SCLMD_CUDA(b.fsegs.alloc_raw(segs.size()));
@@ -2034,7 +2041,7 @@ struct sclmd_md {
         fa.kT = b.kT.p; fa.out = b.far.p + (size_t)half * b.fhalf; fa.ldk = b.ldk; fa.ntraj = ntraj; fa.ml = b.ml; fa.ncp = b.ncp;
         fa.base = (int)fmod_ll(t0 - 1, b.ml); fa.d0 = 0; fa.dt = dt; fa.segs = b.fmid.p;
         prof_begin(2);
-        k_tail_far_mma<2 * TB><<<b.fnpairs, (FM_W + 1) * 32, FM_SMEM, st>>>(b.ringmap, fa);
+        k_tail_far_mma<2 * TB><<<b.fnmid, (FM_W + 1) * 32, FM_SMEM, st>>>(b.ringmap, fa);
         prof_end();
         SCLMD_CUDA(cudaGetLastError());
         ++launches;
