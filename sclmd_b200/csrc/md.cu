@@ -1438,10 +1438,17 @@ __global__ void __launch_bounds__((FM_W + 1) * 32, 1) k_tail_far_mma2(const __gr
 }
 
 // tail[traj][c] = Near_s + sum_z Far[z][s]   (written where the phase kernels expect a single partial)
-__global__ void __launch_bounds__(256) k_tail_near(const double *__restrict__ ring, const double *__restrict__ kern,
-                                                    const double *__restrict__ far, double *__restrict__ out, int ntraj, int ml,
-                                                    int ncp, int head, int s, int nsplit, double dt, int tb,
-                                                    const int *__restrict__ nslot, int chunks) {
+struct NearArgs {
+    const double *ring, *kern, *far;
+    double *out;
+    const int *nslot;
+    int ntraj, ml, ncp, head, s, nsplit, tb, chunks;
+    double dt;
+};
+__device__ __forceinline__ void tail_near_body(const double *__restrict__ ring, const double *__restrict__ kern,
+                                               const double *__restrict__ far, double *__restrict__ out, int ntraj, int ml,
+                                               int ncp, int head, int s, int nsplit, double dt, int tb,
+                                               const int *__restrict__ nslot, int chunks) {
     const int traj = blockIdx.x;
     const double *r = ring + (size_t)traj * ml * ncp;
     for (int c = threadIdx.x; c < ncp; c += blockDim.x) {
@@ -1465,6 +1472,17 @@ __global__ void __launch_bounds__(256) k_tail_near(const double *__restrict__ ri
         for (int z = 0; z < nz; ++z) f += far[(((size_t)z * tb + s) * ntraj + traj) * ncp + c];
         out[(size_t)traj * ncp + c] = dt * acc + f;
     }
+}
+__global__ void __launch_bounds__(256) k_tail_near(const double *__restrict__ ring, const double *__restrict__ kern,
+                                                    const double *__restrict__ far, double *__restrict__ out, int ntraj, int ml,
+                                                    int ncp, int head, int s, int nsplit, double dt, int tb,
+                                                    const int *__restrict__ nslot, int chunks) {
+    tail_near_body(ring, kern, far, out, ntraj, ml, ncp, head, s, nsplit, dt, tb, nslot, chunks);
+}
+// the near passes of two baths in one launch (blockIdx.y = bath)
+__global__ void __launch_bounds__(256) k_tail_near2(const NearArgs a0, const NearArgs a1) {
+    const NearArgs &a = blockIdx.y ? a1 : a0;
+    tail_near_body(a.ring, a.kern, a.far, a.out, a.ntraj, a.ml, a.ncp, a.head, a.s, a.nsplit, a.dt, a.tb, a.nslot, a.chunks);
 }
 
 // Kc[i][k] = K[i][cons_k]  (columns of K that multiply the constrained dofs)
@@ -1977,15 +1995,29 @@ struct sclmd_md {
     }
     // background work of a step, collected by tail_step_mma and launched by flush_far(): slice `sl` of the next block's pass for
     // every bath (two baths per launch), then -- after the last step of a block -- the mid pass and the change of halves
-    struct FarPending { Bath *b; long long t1; int s0, s1; };
+    struct FarPending { Bath *b; long long t1; int s0, s1; NearArgs near; };
     std::vector<FarPending> far_pending;
     int flush_far() {
         std::vector<FarPending> pend;
         pend.swap(far_pending);
+        // the near passes S'(tt) first (the next step's bath-dof kernel waits for them), two baths per launch
+        for (size_t k = 0; k < pend.size(); k += 2) {
+            prof_begin(3);
+            if (k + 1 < pend.size()) {
+                k_tail_near2<<<dim3(ntraj, 2), 256, 0, st>>>(pend[k].near, pend[k + 1].near);
+            } else {
+                const NearArgs &a = pend[k].near;
+                k_tail_near<<<ntraj, 256, 0, st>>>(a.ring, a.kern, a.far, a.out, a.ntraj, a.ml, a.ncp, a.head, a.s, a.nsplit, a.dt, a.tb, a.nslot, a.chunks);
+            }
+            prof_end();
+            SCLMD_CUDA(cudaGetLastError());
+            ++launches;
+        }
         size_t i = 0;
         while (i < pend.size()) {
             FarPending &p0 = pend[i];
             // a second bath with the same slice range (the normal case) shares the launch
+            if (p0.s0 > p0.s1) { ++i; continue; }          // (near pass only)
             if (i + 1 < pend.size() && pend[i + 1].s0 == p0.s0 && pend[i + 1].s1 == p0.s1 && p0.s0 == p0.s1 && pend[i + 1].b != p0.b) {
                 FarPending &p1 = pend[i + 1];
                 Bath &b0 = *p0.b, &b1 = *p1.b;
@@ -2008,7 +2040,7 @@ struct sclmd_md {
             ++i;
         }
         for (auto &p : pend)
-            if (p.s1 == FM_SLICES - 1) {
+            if (p.s0 <= p.s1 && p.s1 == FM_SLICES - 1) {
                 Bath &b = *p.b;
                 if (int e = far_mid(b, p.t1, b.fcur ^ 1)) return e;
                 b.fcur ^= 1;
@@ -2059,21 +2091,22 @@ struct sclmd_md {
             b.far_t0 = t0;
             b.nxt_block = -1;
         }
-        prof_begin(3);
-        k_tail_near<<<ntraj, 256, 0, st>>>(b.ring.p, b.kern.p, b.far.p + (size_t)b.fcur * b.fhalf, b.tailp.p, ntraj, b.ml, b.ncp, (int)fmod_ll(tt, b.ml), s,
-                                           0, dt, tb, b.fnslot.p, b.fchunks);
-        prof_end();
-        SCLMD_CUDA(cudaGetLastError());
-        ++launches;
+        NearArgs na{};
+        na.ring = b.ring.p; na.kern = b.kern.p; na.far = b.far.p + (size_t)b.fcur * b.fhalf; na.out = b.tailp.p; na.nslot = b.fnslot.p;
+        na.ntraj = ntraj; na.ml = b.ml; na.ncp = b.ncp; na.head = (int)fmod_ll(tt, b.ml); na.s = s; na.nsplit = 0; na.tb = tb; na.chunks = b.fchunks;
+        na.dt = dt;
         // the next block: its far-far ages are rows older than t0, all final -- slice s now (and any slices a late start has skipped);
         // after the last step of the block its own 32 rows are in the ring too: mid pass, and the halves change roles
         if (b.nxt_block != t1) {
             b.nxt_block = t1;
             b.nxt_done = 0;
         }
+        // near pass and slice are launched by flush_far() once every bath has queued them (two baths per launch)
         if (b.nxt_done <= s) {
-            far_pending.push_back(FarPending{&b, t1, b.nxt_done, s});      // launched by flush_far() once every bath has queued its near pass
+            far_pending.push_back(FarPending{&b, t1, b.nxt_done, s, na});
             b.nxt_done = s + 1;
+        } else {
+            far_pending.push_back(FarPending{&b, t1, 1, 0, na});          // the slices of this step are done already: near pass only
         }
         return 0;
     }
