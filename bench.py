@@ -562,8 +562,8 @@ def main():
                           "bound": "tensor",
                           "achieved": far_fl_region / (far_ms * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
                           "frac": far_fl_region / (far_ms * 1e-3) / 1e12 / fp64_peak,
-                          "traffic": 2.0 * (traffic or {}).get("far_slice_dram_bytes_per_launch_one_bath", 0.0) or None,
-                          "traffic_note": "2 x the ncu DRAM bytes of a one-bath slice (profiles/r02J_far_ncu_raw.csv); a launch carries one slice of each bath",
+                          "traffic": (traffic or {}).get("far_slice2_dram_bytes_per_launch"),
+                          "traffic_note": "ncu DRAM bytes of one per-step launch (one slice of each bath), profiles/r02X_farslice_ncu_raw.csv",
                           "peak_source": "measured live: FP64 DMMA.8x8x4 chain probe (sclmd_probe_fp64)",
                           "algorithmic_flops_per_launch": far_fl_region / max(1, nlaunch), "algorithmic_bytes_per_launch": 2.0 * alg_ring * K / 32.0 / max(1, nlaunch),
                           "avg_launch_ms": far_ms / max(1, nlaunch), "launches_timed": nlaunch, "ms_per_step": far_ms / K,
@@ -660,7 +660,7 @@ def main():
         roof["noise_samples_per_s"] = nz.get("samples_per_s_device")
         roof["noise_frac_of_hbm_roofline"] = nz.get("frac_of_hbm_roofline_16B_per_sample")
         roof["whole_step_frac_of_fp64_peak"] = (roof.get("whole_step") or {}).get("frac_of_fp64_peak")
-        roof["traffic_source"] = "stored ncu --set full capture (profiles/r02_tail_traffic.json <- profiles/r02J_far_ncu_raw.csv), not measured in this run"
+        roof["traffic_source"] = "stored ncu --set full capture (profiles/r02_tail_traffic.json <- profiles/r02X_farslice_ncu_raw.csv), not measured in this run"
 
     # ---------------- BASELINE configs[1] shape (603-dof junction of the example, ml = 1 baths, fixed ends, 1024 trajectories)
     if world == 1 and not args.no_also and args.workload != "c2":
