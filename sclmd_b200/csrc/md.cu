@@ -1986,6 +1986,9 @@ struct sclmd_md {
         b.nxt_block = -1;
         return 0;
     }
+    // 256 threads per trajectory (one column per thread -- 320 threads at config 5 -- measured slower: 0.063 against 0.057 ms per step for the
+    // two baths, fewer CTAs per SM)
+    static int near_threads(int ncp) { return std::min(256, std::max(64, round_up(ncp, 32))); }
     FarMmaArgs far_args(Bath &b, long long t0, int half, int d0) {
         auto fmod_ll = [](long long x, long long m) { long long r = x % m; return r < 0 ? r + m : r; };
         FarMmaArgs fa{};
@@ -2004,10 +2007,10 @@ struct sclmd_md {
         for (size_t k = 0; k < pend.size(); k += 2) {
             prof_begin(3);
             if (k + 1 < pend.size()) {
-                k_tail_near2<<<dim3(ntraj, 2), 256, 0, st>>>(pend[k].near, pend[k + 1].near);
+                k_tail_near2<<<dim3(ntraj, 2), near_threads(std::max(pend[k].near.ncp, pend[k + 1].near.ncp)), 0, st>>>(pend[k].near, pend[k + 1].near);
             } else {
                 const NearArgs &a = pend[k].near;
-                k_tail_near<<<ntraj, 256, 0, st>>>(a.ring, a.kern, a.far, a.out, a.ntraj, a.ml, a.ncp, a.head, a.s, a.nsplit, a.dt, a.tb, a.nslot, a.chunks);
+                k_tail_near<<<ntraj, near_threads(a.ncp), 0, st>>>(a.ring, a.kern, a.far, a.out, a.ntraj, a.ml, a.ncp, a.head, a.s, a.nsplit, a.dt, a.tb, a.nslot, a.chunks);
             }
             prof_end();
             SCLMD_CUDA(cudaGetLastError());
@@ -2159,7 +2162,7 @@ struct sclmd_md {
             ++launches;
         }
         prof_begin(3);
-        k_tail_near<<<ntraj, 256, 0, st>>>(b.ring.p, b.kern.p, b.far.p, b.tailp.p, ntraj, b.ml, b.ncp, (int)fmod_ll(tt, b.ml), (int)(tt - t0),
+        k_tail_near<<<ntraj, near_threads(b.ncp), 0, st>>>(b.ring.p, b.kern.p, b.far.p, b.tailp.p, ntraj, b.ml, b.ncp, (int)fmod_ll(tt, b.ml), (int)(tt - t0),
                                            b.far_nsplit, dt, tb, nullptr, 0);
         prof_end();
         SCLMD_CUDA(cudaGetLastError());
