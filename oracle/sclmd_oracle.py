@@ -701,3 +701,38 @@ def sig_tm(K00, K11, K01, K10, omega, eta):
     G = np.linalg.inv((omega + 1e-8 * 1j) ** 2 * np.identity(len(K00)) - K00 - sl - sr)
     gam = lambda P: -1j * (P - P.conj().T)
     return float(np.real(np.trace(G @ gam(sl) @ G.conj().T @ gam(sr))))
+
+
+def blocked_tail_parts(kernel, ring, t0, s, dt, tb=32, sr=8, seg=None):
+    """The friction tail S'(t0 + s) of a diagonal kernel as the device evaluates it in time-blocked mode (test infrastructure: the
+    specification of k_tail_near / k_tail_far_mma).  ring[slot] = p_{t'} with t' mod ml == slot, rows up to
+    t0 + s present; kernel [ml, nc] (zero beyond row ml - 1).  Returns (near, mid, farfar):
+      near    = dt sum_{j=1}^{s+1} k[j] p_{t0+s+1-j}                  rows of the current block
+      mid     = dt sum_{d=0}^{tb-1} k[s+2+d] p_{t0-1-d}               rows of the previous block (one short pass at the block boundary)
+      farfar  = dt sum_{d>=tb}      k[s+2+d] p_{t0-1-d}               older rows: final one block early, worked off one slice per step;
+                                                                      `seg` = list of (d_lo, d_hi) age ranges summed separately and then
+                                                                      in order (the partial slots of the device), default one range
+    near + mid + farfar == dt sum_{j=1}^{ml-1} k[j] p_{t0+s+1-j} (md.py:386-387 / baths.py:453-457 restricted to j >= 1)."""
+    ml, nc = kernel.shape
+    kp = np.vstack([kernel, np.zeros((tb + 2 + sr, nc))])      # zero rows past ml - 1 retire ring slots that were overwritten
+    t = t0 + s
+    near = np.zeros(nc)
+    for j in range(1, s + 2):
+        near += kp[j] * ring[(t + 1 - j) % ml]
+    def ages(lo, hi):
+        acc = np.zeros(nc)
+        for d in range(lo, hi):
+            acc += kp[s + 2 + d] * ring[(t0 - 1 - d) % ml]
+        return acc
+    mid = ages(0, tb)
+    seg = seg or [(tb, ml)]
+    farfar = np.zeros(nc)
+    for lo, hi in seg:
+        farfar = farfar + dt * ages(lo, hi)
+    return dt * near, dt * mid, farfar
+
+
+def hankel_tile(kvec, x, n):
+    """fragment F(x) of the Hankel operand of the tensor-pipe far pass: an 8 x 4 tile H[s][a] = k[x + 2 + s + a] of step tile n at ages
+    x - 8 n .. x - 8 n + 3 (k_tail_far_mma: one new fragment per k-step and dof, a tile of step tile n is F(d0 + 8 n))"""
+    return np.array([[kvec[x + 2 + s + a] for a in range(4)] for s in range(8)])

@@ -340,3 +340,30 @@ def test_modal_restatement_equals_the_real_space_one():
     assert relerr(mod.etot[:, keep], ens.etot[:, keep]) < 1e-11
     for b in range(2):
         assert relerr(mod.baths[b]["cur"][:, keep], ens.baths[b]["cur"][:, keep]) < 1e-11
+
+
+def test_time_blocked_tail_decomposition_equals_the_direct_tail():
+    """near + mid + far-far (in any split into age ranges) is the direct tail of md.py:386-387 for every step of a block, also when the
+    ring has wrapped and slots of the oldest rows have been overwritten by the block's own rows; and the Hankel-fragment identity the
+    tensor-pipe far pass relies on: the tile of step tile n at ages d0..d0+3 is the fragment F(d0 + 8 n)"""
+    rng = np.random.default_rng(5)
+    ml, nc, dt, tb = 96, 3, 0.37, 32
+    kern = rng.standard_normal((ml, nc)) * np.exp(-np.arange(ml) / 40.0)[:, None]
+    for t0 in (0, 32, 96, 160):
+        p_of = {tt: rng.standard_normal(nc) for tt in range(t0 - 2 * ml, t0 + tb)}
+        for s in (0, 1, 7, 31):
+            t = t0 + s
+            ring = np.zeros((ml, nc))
+            for tt in range(t - ml + 1, t + 1):                # the ring holds the last ml rows
+                ring[tt % ml] = p_of[tt]
+            direct = dt * sum(kern[j] * p_of[t + 1 - j] for j in range(1, ml))
+            near, mid, far = O.blocked_tail_parts(kern, ring, t0, s, dt, tb)
+            assert np.max(np.abs(near + mid + far - direct)) <= 1e-13 * np.max(np.abs(direct))
+            _, _, far3 = O.blocked_tail_parts(kern, ring, t0, s, dt, tb, seg=[(32, 48), (48, 80), (80, ml)])
+            assert np.max(np.abs(far3 - far)) <= 1e-13 * max(np.max(np.abs(far)), 1e-300)
+    # Hankel fragments: H[s_global][d] = k[s_global + 2 + d]; tile (n, d0) == F(d0 + 8 n)
+    kvec = rng.standard_normal(200)
+    for n in range(4):
+        for d0 in (0, 4, 40):
+            tile = np.array([[kvec[(8 * n + s) + 2 + (d0 + a)] for a in range(4)] for s in range(8)])
+            assert np.array_equal(tile, O.hankel_tile(kvec, d0 + 8 * n, n))
