@@ -144,3 +144,45 @@ def test_md_class_shards_its_ensemble_inside_a_distributed_job():
     om = np.linspace(0.0, 2.0, 11)
     want = np.stack([np.cos(om), np.sin(om)], axis=1) * (1 + 1j)
     assert all(np.array_equal(r[8], want) for r in res)
+
+
+def _stream_k_schedule(ntiles, KI, grid):
+    """host-side restatement of the work split of dgemm_tma_kernel (sclmd_b200/csrc/dgemm_tma.cuh): equal contiguous ranges of the
+    (tile, K-slab) space, each CTA walking its range from the last tile to the first"""
+    total = ntiles * KI
+    ctas = []
+    for bid in range(grid):
+        beg, end = total * bid // grid, total * (bid + 1) // grid
+        pieces, hi = [], end
+        while hi > beg:
+            tile = (hi - 1) // KI
+            tstart = tile * KI
+            lo = max(beg, tstart)
+            pieces.append((tile, lo - tstart, hi - tstart))
+            hi = lo
+        ctas.append(pieces)
+    return ctas
+
+
+@pytest.mark.parametrize("ntiles,KI,grid", [(152, 38, 148), (80, 188, 148), (376, 38, 148), (1, 5, 5), (7, 3, 4), (65552, 19, 148), (3, 100, 148)])
+def test_stream_k_schedule_covers_every_tile_once_and_waits_only_on_earlier_ctas(ntiles, KI, grid):
+    """the properties the fix-up of the TMA GEMM relies on: the pieces of a tile tile it exactly; one CTA -- the one holding the tile's
+    end -- finalises it and needs partials only from CTAs with a LOWER logical index (tickets are drawn at start: those CTAs are already
+    running, so a plain launch cannot deadlock); a CTA stores at most one partial, and stores it before any piece it has to wait for"""
+    grid = min(grid, ntiles * KI)
+    ctas = _stream_k_schedule(ntiles, KI, grid)
+    cover = {}
+    for bid, pieces in enumerate(ctas):
+        assert pieces, bid
+        partial_steps = [i for i, (t, kb, ke) in enumerate(pieces) if ke < KI]
+        assert len(partial_steps) <= 1 and all(i == 0 for i in partial_steps)      # the partial is the FIRST thing a CTA does
+        for tile, kb, ke in pieces:
+            cover.setdefault(tile, []).append((kb, ke, bid))
+    assert sorted(cover) == list(range(ntiles))
+    for tile, segs in cover.items():
+        segs.sort()
+        assert segs[0][0] == 0 and segs[-1][1] == KI
+        for (a0, a1, _), (b0, b1, _) in zip(segs, segs[1:]):
+            assert a1 == b0                                                         # no gap, no overlap
+        finaliser = segs[-1][2]
+        assert all(bid < finaliser for _, _, bid in segs[:-1])                      # waits only on CTAs that drew an earlier ticket
